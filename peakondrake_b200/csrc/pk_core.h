@@ -1,0 +1,691 @@
+// pk_core.h -- thread-level phases of the batched stochastic Camassa-Holm timestep
+// (scheme 'hydrodynamic'/'no_gradient', timestepping 'midpoint').
+//
+// Replaces, for an ensemble of realisations, what the reference does once per call in
+//   Equations.solve()            /root/reference/peakondrake/equations.py:193-199  (SNES Newton, LU)
+//   StochasticFunctions.update() /root/reference/peakondrake/stochastic_functions.py:204-236
+// The weak form is equations.py:80-87; element integrals are the closed forms of SURVEY.md
+// App. A.1, the Newton system is reduced exactly (App. A.3) to
+//   P du = -(H Rpsi + D Rphi - M Rzeta),  P = H(M + N1'/2) - D f'/2 + M g'/2   (cyclic pentadiagonal)
+//   dF_new = H^-1 ( f(uh) + f'/2 du ),  dG_new = H^-1 ( g(uh) + g'/2 du )        (constant coefficients)
+//
+// Parallel layout: one CTA per realisation, T = 2^k threads, thread t owns the contiguous row
+// chunk [s_t, s_t + m_t), m_t in {M-1, M}.  Rows 0,1 of a chunk are SEPARATOR rows, the rest is
+// the chunk INTERIOR.  The pentadiagonal solve is a two-level nested dissection:
+//   level 1 (per thread, registers): LU of the interior block, carrying the fill of the
+//            coupling to the own separators; back-substitution of 5 columns gives the "tips";
+//   level 2 (block): cyclic block-tridiagonal (2x2 blocks) Schur system on the separators,
+//            solved by parallel cyclic reduction;
+// the Helmholtz solves are two first-order recursive filters (H = kappa (1-rho S)(1-rho S^-1))
+// evaluated as chunk-local recurrences plus a cyclic affine scan over threads.
+//
+// Everything here is __host__ __device__ so that the identical code is executed by the CUDA
+// kernels (pk_kernels.cu) and by the CPU emulation harness the not-gpu tests use
+// (tests/emu/pk_emu.cpp).  Per-thread state that lives across a barrier is a member of Thread.
+#pragma once
+#include "pk_params.h"
+
+#if defined(__CUDACC__)
+#define PK_HD __host__ __device__ __forceinline__
+#define PK_UNROLL _Pragma("unroll")
+#else
+#define PK_HD inline __attribute__((always_inline))
+#define PK_UNROLL
+#endif
+
+namespace pk {
+
+// Shared (per-realisation) storage. Field arrays are [M*T] doubles, interleaved: row j of chunk t
+// lives at j*T + t (conflict-free when all threads touch their row j).
+struct Shared {
+  double *U0, *U1, *F, *G, *X, *Xx, *Xxx;
+  double *xb;   // [18*T] exchange slots / PCR rows: slot c of thread t at c*T + t
+  double *dW;   // [max(nxi,1)]
+};
+
+enum { XB_SLOTS = 18 };
+
+// natural row index i in [0, ne)  ->  interleaved slot j*T + t
+PK_HD int row_slot(const Params& p, int i) {
+  const int big = p.rem * p.M;
+  int t, j;
+  if (i < big) { t = i / p.M; j = i - t * p.M; }
+  else { const int k = i - big; const int q = k / (p.M - 1); t = p.rem + q; j = k - q * (p.M - 1); }
+  return j * p.T + t;
+}
+
+struct NodeS { double a, v, w, F, G, x, y; };
+
+// Contributions of one cell (left node A, right node B) to its two nodes, and their derivatives
+// with respect to the two nodal values of uh.  SURVEY.md App. A.1.
+template <int MODE>
+struct CellC {
+  double N1L, N1R, fL, fR, gL, gR;
+  double dN1L0, dN1L1, dN1R0, dN1R1;
+  double dfL0, dfL1, dfR0, dfR1;
+  double dgL0, dgL1, dgR0, dgR1;
+  PK_HD void compute(const Params& p, const NodeS& A, const NodeS& B) {
+    const double da = B.a - A.a;
+    const double sL = 2.0 * A.v + B.v, sR = A.v + 2.0 * B.v;
+    const double da6 = da * (1.0 / 6.0);
+    N1L = da6 * sL; N1R = da6 * sR;
+    const double dd = da6 * p.dt;
+    dN1L0 = -sL * (1.0 / 6.0) + 2.0 * dd; dN1L1 = sL * (1.0 / 6.0) + dd;
+    dN1R0 = -sR * (1.0 / 6.0) + dd;       dN1R1 = sR * (1.0 / 6.0) + 2.0 * dd;
+    const double a0 = A.a, a1 = B.a;
+    const double a00 = a0 * a0, a01 = a0 * a1, a11 = a1 * a1;
+    const double cda2 = p.c2 * da * da;
+    fL = p.c1 * (3.0 * a00 + 2.0 * a01 + a11) + cda2;
+    fR = p.c1 * (a00 + 2.0 * a01 + 3.0 * a11) + cda2;
+    const double k = 2.0 * p.c2 * da;
+    const double s2 = 2.0 * p.c1 * (a0 + a1);
+    dfL0 = p.c1 * (6.0 * a0 + 2.0 * a1) - k; dfL1 = s2 + k;
+    dfR0 = s2 - k;                           dfR1 = p.c1 * (2.0 * a0 + 6.0 * a1) + k;
+    if (MODE == NOISE_FULL) {
+      const double x0 = A.x, x1 = B.x, y0 = A.y, y1 = B.y;
+      const double yL = 2.0 * y0 + y1, yR = y0 + 2.0 * y1;
+      const double xs = x0 + x1;
+      gL = p.h6 * (a0 * (3.0 * x0 + x1) + a1 * xs) + p.a26 * da * yL;
+      gR = p.h6 * (a0 * xs + a1 * (x0 + 3.0 * x1)) + p.a26 * da * yR;
+      dgL0 = p.h6 * (3.0 * x0 + x1) - p.a26 * yL; dgL1 = p.h6 * xs + p.a26 * yL;
+      dgR0 = p.h6 * xs - p.a26 * yR;              dgR1 = p.h6 * (x0 + 3.0 * x1) + p.a26 * yR;
+    } else {
+      gL = gR = dgL0 = dgL1 = dgR0 = dgR1 = 0.0;
+    }
+  }
+};
+
+// What node l contributes to pentadiagonal rows l-1 (Cp,Qp), l (C0,Q0) and l+1 (Cm,Qm).
+struct Packet { double Cm[3], C0[3], Cp[3], Qm, Q0, Qp; };
+
+PK_HD void inv2(const double* D, double* Di) {
+  const double det = D[0] * D[3] - D[1] * D[2];
+  const double id = 1.0 / det;
+  Di[0] = D[3] * id; Di[1] = -D[1] * id; Di[2] = -D[2] * id; Di[3] = D[0] * id;
+}
+// C = A*B (2x2 row-major)
+PK_HD void mm2(const double* A, const double* B, double* C) {
+  C[0] = A[0] * B[0] + A[1] * B[2]; C[1] = A[0] * B[1] + A[1] * B[3];
+  C[2] = A[2] * B[0] + A[3] * B[2]; C[3] = A[2] * B[1] + A[3] * B[3];
+}
+// C += A*B
+PK_HD void mma2(const double* A, const double* B, double* C) {
+  C[0] += A[0] * B[0] + A[1] * B[2]; C[1] += A[0] * B[1] + A[1] * B[3];
+  C[2] += A[2] * B[0] + A[3] * B[2]; C[3] += A[2] * B[1] + A[3] * B[3];
+}
+// y += A*x
+PK_HD void mva2(const double* A, const double* x, double* y) {
+  y[0] += A[0] * x[0] + A[1] * x[1]; y[1] += A[2] * x[0] + A[3] * x[1];
+}
+
+template <int M, int MODE>
+struct Thread {
+  enum { NI = M - 2 };
+  // geometry
+  int t, m, s, ext, tl, tr, ml, active;
+  // level-1 factors of the interior block (interior row k <-> chunk row k+2)
+  double r[NI], e[NI], f[NI], zb[NI], zw1[NI], zw2[NI];
+  // separator rows (a,b,c,e,f) and right-hand sides
+  double sp0[5], sp1[5], sb0, sb1;
+  // streaming window of the assembly pass
+  NodeS nm, n0, np;
+  CellC<MODE> pc;                 // previous cell
+  double wCm2[3], wQm2;           // Cm,Qm of node n-2
+  double wCm1[3], wQm1;           // Cm,Qm of node n-1
+  double wC01[3], wQ01;           // C0,Q0 of node n-1
+  // tips of the interior solution columns (y, W1, W2, V1, V2) at interior rows 0,1 ("F2")
+  double F2a[5], F2b[5];
+  // reduced block row
+  double Lb[4], Db[4], Ub[4], rb[2];
+  // results
+  double xs0, xs1;                // separator solution
+  double du[M];
+  double hF[M], hG[M];            // Helmholtz work (rhs -> y -> x)
+  double fn2, sn2, xn2;           // partial sums: |R|^2, |delta|^2, |w1|^2
+  double Xs;                      // NOISE_SCALAR: dXi value of this step
+
+  PK_HD void init(const Params& p, int tid) {
+    t = tid; active = (tid < p.T);
+    const int tt = active ? tid : 0;
+    m = chunk_rows(p, tt); s = chunk_start(p, tt); ext = (m == M);
+    tl = (tt + p.T - 1) & (p.T - 1); tr = (tt + 1) & (p.T - 1);
+    ml = chunk_rows(p, tl);
+    fn2 = sn2 = xn2 = 0.0; Xs = 0.0;
+  }
+
+  // ---- smem index helpers -------------------------------------------------------------
+  PK_HD int idx(const Params& p, int j) const { return j * p.T + t; }
+  // node with local index j in [-1, m]: own rows, last row of the left chunk, first row of the right chunk
+  PK_HD int nidx(const Params& p, int j) const {
+    return j < 0 ? (ml - 1) * p.T + tl : (j < m ? j * p.T + t : tr);
+  }
+
+  PK_HD void load_node(const Params& p, const Shared& sh, int j, NodeS& n) const {
+    const int i = nidx(p, j);
+    const double u0 = sh.U0[i], u1 = sh.U1[i];
+    n.a = 0.5 * (u1 + u0);
+    n.w = u1 - u0;
+    n.F = sh.F[i];
+    if (MODE == NOISE_FULL) { n.G = sh.G[i]; n.x = sh.Xx[i]; n.y = sh.Xxx[i]; }
+    else { n.G = 0.0; n.x = 0.0; n.y = 0.0; }
+    const double X = (MODE == NOISE_SCALAR) ? Xs : sh.X[i];
+    n.v = p.dt * n.a + X;
+  }
+
+  // Residual and Jacobian rows of node n0 (neighbours nm, np; cells pc = (nm,n0), cc = (n0,np)).
+  PK_HD void node_packet(const Params& p, const CellC<MODE>& cc, Packet& k) {
+    const double N1 = pc.N1R + cc.N1L, ff = pc.fR + cc.fL;
+    const double Rpsi = p.mb * (nm.w + np.w) + p.ma * n0.w + N1 - 0.5 * (nm.F - np.F)
+                        + ((MODE == NOISE_FULL) ? (p.mb * (nm.G + np.G) + p.ma * n0.G) : 0.0);
+    const double Rphi = p.hb * (nm.F + np.F) + p.ha * n0.F - ff;
+    double Rzeta = 0.0;
+    if (MODE == NOISE_FULL) Rzeta = p.hb * (nm.G + np.G) + p.ha * n0.G - (pc.gR + cc.gL);
+    fn2 += Rpsi * Rpsi + Rphi * Rphi + Rzeta * Rzeta;
+    const double B[3] = {0.5 * pc.dN1R0, 0.5 * (pc.dN1R1 + cc.dN1L0), 0.5 * cc.dN1L1};
+    const double Fm[3] = {0.5 * pc.dfR0, 0.5 * (pc.dfR1 + cc.dfL0), 0.5 * cc.dfL1};
+    double Gm[3] = {0.0, 0.0, 0.0};
+    if (MODE == NOISE_FULL) { Gm[0] = 0.5 * pc.dgR0; Gm[1] = 0.5 * (pc.dgR1 + cc.dgL0); Gm[2] = 0.5 * cc.dgL1; }
+    PK_UNROLL
+    for (int c = 0; c < 3; ++c) {
+      const double S = p.hb * B[c] + p.mb * Gm[c];
+      k.Cm[c] = S - 0.5 * Fm[c];
+      k.Cp[c] = S + 0.5 * Fm[c];
+      k.C0[c] = p.ha * B[c] + p.ma * Gm[c];
+    }
+    const double hr = p.hb * Rpsi - p.mb * Rzeta;
+    k.Qm = hr + 0.5 * Rphi;
+    k.Qp = hr - 0.5 * Rphi;
+    k.Q0 = p.ha * Rpsi - p.ma * Rzeta;
+  }
+
+  // LU step of interior row k (static after inlining) with the three carried columns.
+  PK_HD void elim(int k, double a, double b, double c, double ee, double ff, double rhs) {
+    double d, z, w1, w2;
+    if (k == 0) {
+      d = c; z = rhs; w1 = a; w2 = b;
+    } else if (k == 1) {
+      const double l1 = b * r[0];
+      d = c - l1 * e[0]; ee = ee - l1 * f[0];
+      z = rhs - l1 * zb[0]; w1 = -l1 * zw1[0]; w2 = a - l1 * zw2[0];
+    } else {
+      const double l2 = a * r[k - 2];
+      const double bb = b - l2 * e[k - 2];
+      const double l1 = bb * r[k - 1];
+      d = c - l2 * f[k - 2] - l1 * e[k - 1];
+      ee = ee - l1 * f[k - 1];
+      z = rhs - l2 * zb[k - 2] - l1 * zb[k - 1];
+      w1 = -l2 * zw1[k - 2] - l1 * zw1[k - 1];
+      w2 = -l2 * zw2[k - 2] - l1 * zw2[k - 1];
+    }
+    r[k] = 1.0 / d; e[k] = ee; f[k] = ff; zb[k] = z; zw1[k] = w1; zw2[k] = w2;
+  }
+
+  // Row (n-1) is complete once packet n is known: separator rows are stored, interior rows eliminated.
+  // cp/qp = Cp,Qp of node n (own or, for the last row, the right neighbour's first node).
+  PK_HD void finish_row(const Params& p, int row, const double* cp, double qp) {
+    if (row == 0) {
+      sp0[2] += cp[0]; sp0[3] += cp[1]; sp0[4] += cp[2]; sb0 -= qp;
+      return;
+    }
+    const double a = p.hm2 + wCm2[0];
+    const double b = p.hm1 + wCm2[1] + wC01[0];
+    const double c = p.hm0 + wCm2[2] + wC01[1] + cp[0];
+    const double ee = p.hm1 + wC01[2] + cp[1];
+    const double ff = p.hm2 + cp[2];
+    const double rhs = -(wQm2 + wQ01 + qp);
+    if (row == 1) {
+      sp1[0] = a; sp1[1] = b; sp1[2] = c; sp1[3] = ee; sp1[4] = ff; sb1 = rhs;
+    } else {
+      elim(row - 2, a, b, c, ee, ff, rhs);
+    }
+  }
+
+  PK_HD void push_packet(const Packet& k) {
+    PK_UNROLL
+    for (int c = 0; c < 3; ++c) { wCm2[c] = wCm1[c]; wCm1[c] = k.Cm[c]; wC01[c] = k.C0[c]; }
+    wQm2 = wQm1; wQm1 = k.Qm; wQ01 = k.Q0;
+  }
+
+  // One streaming iteration q >= 1: cell (q-1, q); finalises node q-1 and row q-2.
+  PK_HD void stream(const Params& p, const Shared& sh, int q) {
+    load_node(p, sh, q, np);
+    CellC<MODE> cc; cc.compute(p, n0, np);
+    Packet k; node_packet(p, cc, k);           // node q-1
+    const int n = q - 1;
+    if (n == 0) {
+      // separator row 0 so far: H*M part, own C0/Q0 (Cm of the left neighbour is added in reduce_build)
+      sp0[0] = p.hm2; sp0[1] = p.hm1 + k.C0[0]; sp0[2] = p.hm0 + k.C0[1]; sp0[3] = p.hm1 + k.C0[2]; sp0[4] = p.hm2;
+      sb0 = -k.Q0;
+      // publish what the left neighbour's last row needs from my first node
+      sh.xb[14 * p.T + t] = k.Cp[0]; sh.xb[15 * p.T + t] = k.Cp[1]; sh.xb[16 * p.T + t] = k.Cp[2];
+      sh.xb[17 * p.T + t] = k.Qp;
+    } else {
+      finish_row(p, n - 1, k.Cp, k.Qp);
+    }
+    push_packet(k);
+    nm = n0; n0 = np; pc = cc;
+  }
+
+  // ---- phase A1: first two cells, publish first-node packet --------------------------------
+  PK_HD void assemble_begin(const Params& p, const Shared& sh) {
+    fn2 = 0.0;
+    load_node(p, sh, -1, nm);
+    load_node(p, sh, 0, n0);
+    pc.compute(p, nm, n0);
+    PK_UNROLL
+    for (int c = 0; c < 3; ++c) { wCm1[c] = 0.0; wCm2[c] = 0.0; wC01[c] = 0.0; }
+    wQm1 = wQm2 = wQ01 = 0.0;
+    stream(p, sh, 1);
+  }
+
+  // ---- phase A2: rest of the chunk, interior LU, tips; publishes tips + last packet --------
+  PK_HD void assemble_finish(const Params& p, const Shared& sh) {
+    PK_UNROLL
+    for (int q = 2; q <= M - 1; ++q) stream(p, sh, q);
+    if (ext) stream(p, sh, M);
+    // last row (m-1): Cp,Qp come from the right neighbour's first node
+    double cp[3];
+    cp[0] = sh.xb[14 * p.T + tr]; cp[1] = sh.xb[15 * p.T + tr]; cp[2] = sh.xb[16 * p.T + tr];
+    const double qp = sh.xb[17 * p.T + tr];
+    if (ext) finish_row(p, M - 1, cp, qp); else finish_row(p, M - 2, cp, qp);
+    // publish my last node's Cm,Qm for the right neighbour's separator row 0
+    sh.xb[10 * p.T + t] = wCm1[0]; sh.xb[11 * p.T + t] = wCm1[1]; sh.xb[12 * p.T + t] = wCm1[2];
+    sh.xb[13 * p.T + t] = wQm1;
+
+    // back-substitute the five columns  x_I = y + Wn1 xs0 + Wn2 xs1 + Vn1 xR0 + Vn2 xR1
+    const int nI = m - 2;
+    double xp1[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
+    double xp2[5] = {0.0, 0.0, 0.0, 0.0, 1.0};
+    double L2a[5], L2b[5];
+    PK_UNROLL
+    for (int c = 0; c < 5; ++c) { L2a[c] = L2b[c] = 0.0; F2a[c] = F2b[c] = 0.0; }
+    PK_UNROLL
+    for (int k = NI - 1; k >= 0; --k) {
+      if (k < nI) {
+        const double zc[5] = {zb[k], -zw1[k], -zw2[k], 0.0, 0.0};
+        PK_UNROLL
+        for (int c = 0; c < 5; ++c) {
+          const double x = r[k] * (zc[c] - e[k] * xp1[c] - f[k] * xp2[c]);
+          xp2[c] = xp1[c]; xp1[c] = x;
+          if (k == nI - 1) L2b[c] = x;
+          if (k == nI - 2) L2a[c] = x;
+          if (k == 1) F2b[c] = x;
+          if (k == 0) F2a[c] = x;
+        }
+      }
+    }
+    // slots 0..9: tips at the LAST two interior rows, read by the right neighbour
+    sh.xb[0 * p.T + t] = L2a[0]; sh.xb[1 * p.T + t] = L2b[0];
+    sh.xb[2 * p.T + t] = L2a[1]; sh.xb[3 * p.T + t] = L2a[2];
+    sh.xb[4 * p.T + t] = L2b[1]; sh.xb[5 * p.T + t] = L2b[2];
+    sh.xb[6 * p.T + t] = L2a[3]; sh.xb[7 * p.T + t] = L2a[4];
+    sh.xb[8 * p.T + t] = L2b[3]; sh.xb[9 * p.T + t] = L2b[4];
+  }
+
+  // ---- phase B1: build the reduced (Schur) block row of my separator pair -------------------
+  PK_HD void reduce_build(const Params& p, const Shared& sh) {
+    const int T = p.T;
+    const double yL[2] = {sh.xb[0 * T + tl], sh.xb[1 * T + tl]};
+    const double WL[4] = {sh.xb[2 * T + tl], sh.xb[3 * T + tl], sh.xb[4 * T + tl], sh.xb[5 * T + tl]};
+    const double VL[4] = {sh.xb[6 * T + tl], sh.xb[7 * T + tl], sh.xb[8 * T + tl], sh.xb[9 * T + tl]};
+    sp0[0] += sh.xb[10 * T + tl]; sp0[1] += sh.xb[11 * T + tl]; sp0[2] += sh.xb[12 * T + tl];
+    sb0 -= sh.xb[13 * T + tl];
+    const double E[4] = {sp0[0], sp0[1], 0.0, sp1[0]};
+    const double C[4] = {sp0[2], sp0[3], sp1[1], sp1[2]};
+    const double Gc[4] = {sp0[4], 0.0, sp1[3], sp1[4]};
+    const double WF[4] = {F2a[1], F2a[2], F2b[1], F2b[2]};
+    const double VF[4] = {F2a[3], F2a[4], F2b[3], F2b[4]};
+    const double yF[2] = {F2a[0], F2b[0]};
+    mm2(E, WL, Lb);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) Db[c] = C[c];
+    mma2(E, VL, Db); mma2(Gc, WF, Db);
+    mm2(Gc, VF, Ub);
+    double tmp[2] = {0.0, 0.0};
+    mva2(E, yL, tmp); mva2(Gc, yF, tmp);
+    rb[0] = sb0 - tmp[0]; rb[1] = sb1 - tmp[1];
+  }
+
+  // write my block row (L, U, D^-1, r) to the exchange slots 0..13
+  PK_HD void reduce_publish(const Params& p, const Shared& sh) {
+    const int T = p.T;
+    double Di[4]; inv2(Db, Di);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) {
+      sh.xb[c * T + t] = Lb[c]; sh.xb[(4 + c) * T + t] = Ub[c]; sh.xb[(8 + c) * T + t] = Di[c];
+    }
+    sh.xb[12 * T + t] = rb[0]; sh.xb[13 * T + t] = rb[1];
+  }
+
+  // one parallel-cyclic-reduction step with stride d (reads only)
+  PK_HD void pcr_step(const Params& p, const Shared& sh, int d) {
+    const int T = p.T;
+    const int ql = (t + T - d) & (T - 1), qr = (t + d) & (T - 1);
+    double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) {
+      Ll[c] = sh.xb[c * T + ql]; Ul[c] = sh.xb[(4 + c) * T + ql]; Dl[c] = sh.xb[(8 + c) * T + ql];
+      Lr[c] = sh.xb[c * T + qr]; Ur[c] = sh.xb[(4 + c) * T + qr]; Dr[c] = sh.xb[(8 + c) * T + qr];
+    }
+    rl[0] = sh.xb[12 * T + ql]; rl[1] = sh.xb[13 * T + ql];
+    rr[0] = sh.xb[12 * T + qr]; rr[1] = sh.xb[13 * T + qr];
+    double al[4], ga[4];
+    mm2(Lb, Dl, al); mm2(Ub, Dr, ga);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { al[c] = -al[c]; ga[c] = -ga[c]; }
+    mm2(al, Ll, Lb);
+    mm2(ga, Ur, Ub);
+    mma2(al, Ul, Db); mma2(ga, Lr, Db);
+    mva2(al, rl, rb); mva2(ga, rr, rb);
+  }
+
+  // last level: rows t and t+T/2 form a closed 2-block system
+  PK_HD void pcr_final(const Params& p, const Shared& sh) {
+    const int T = p.T;
+    const int q = (t + T / 2) & (T - 1);
+    double Lq[4], Uq[4], Dq[4], rq[2];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) {
+      Lq[c] = sh.xb[c * T + q]; Uq[c] = sh.xb[(4 + c) * T + q]; Dq[c] = sh.xb[(8 + c) * T + q];
+    }
+    rq[0] = sh.xb[12 * T + q]; rq[1] = sh.xb[13 * T + q];
+    double S[4], Sq[4], SD[4], A[4], Ai[4], rhs[2];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { S[c] = Lb[c] + Ub[c]; Sq[c] = Lq[c] + Uq[c]; A[c] = Db[c]; }
+    mm2(S, Dq, SD);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) SD[c] = -SD[c];
+    mma2(SD, Sq, A);
+    rhs[0] = rb[0]; rhs[1] = rb[1];
+    mva2(SD, rq, rhs);
+    inv2(A, Ai);
+    xs0 = Ai[0] * rhs[0] + Ai[1] * rhs[1];
+    xs1 = Ai[2] * rhs[0] + Ai[3] * rhs[1];
+    sh.xb[14 * T + t] = xs0; sh.xb[15 * T + t] = xs1;
+  }
+
+  // ---- phase C: interior solution with known separators --------------------------------------
+  PK_HD void interior_solve(const Params& p, const Shared& sh) {
+    const int T = p.T;
+    const int nI = m - 2;
+    double xp1 = sh.xb[14 * T + tr], xp2 = sh.xb[15 * T + tr];
+    du[0] = xs0; du[1] = xs1;
+    PK_UNROLL
+    for (int k = NI - 1; k >= 0; --k) {
+      if (k < nI) {
+        const double z = zb[k] - zw1[k] * xs0 - zw2[k] * xs1;
+        const double x = r[k] * (z - e[k] * xp1 - f[k] * xp2);
+        xp2 = xp1; xp1 = x;
+        du[k + 2] = x;
+      } else {
+        du[k + 2] = 0.0;
+      }
+    }
+    sh.xb[16 * T + t] = ext ? du[M - 1] : du[M - 2];   // my last row, for the right neighbour
+  }
+
+  // ---- phase D1: Helmholtz right-hand sides f + f'/2 du, g + g'/2 du; causal local pass ------
+  // returns the chunk aggregate (value with zero carry-in) in cF, cG and the multiplier A = rho^m
+  PK_HD void helm_causal_local(const Params& p, const Shared& sh, double& A, double& cF, double& cG) {
+    const int T = p.T;
+    NodeS A0, B0;
+    load_node(p, sh, -1, A0);
+    double ea = 0.5 * sh.xb[16 * T + tl];      // half the increment of the left neighbour's last row
+    double prevFR = 0.0, prevGR = 0.0;
+    PK_UNROLL
+    for (int q = 0; q <= M; ++q) {
+      if (q <= m) {
+        load_node(p, sh, q, B0);
+        const double eb = 0.5 * ((q < m) ? du[q < M ? q : M - 1] : sh.xb[14 * T + tr]);
+        CellC<MODE> cc; cc.compute(p, A0, B0);
+        const double fLv = cc.fL + cc.dfL0 * ea + cc.dfL1 * eb;
+        const double fRv = cc.fR + cc.dfR0 * ea + cc.dfR1 * eb;
+        double gLv = 0.0, gRv = 0.0;
+        if (MODE == NOISE_FULL) {
+          gLv = cc.gL + cc.dgL0 * ea + cc.dgL1 * eb;
+          gRv = cc.gR + cc.dgR0 * ea + cc.dgR1 * eb;
+        }
+        if (q >= 1) { hF[q - 1] = (prevFR + fLv) * p.ikappa; hG[q - 1] = (prevGR + gLv) * p.ikappa; }
+        prevFR = fRv; prevGR = gRv;
+        A0 = B0; ea = eb;
+      }
+    }
+    // causal recurrence with zero carry-in
+    double yF = 0.0, yG = 0.0, pw = 1.0;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (j < m) {
+        yF = hF[j] + p.rho * yF; hF[j] = yF;
+        if (MODE == NOISE_FULL) { yG = hG[j] + p.rho * yG; hG[j] = yG; }
+        pw *= p.rho;
+      }
+    }
+    A = pw; cF = yF; cG = yG;
+  }
+
+  // ---- phase D2: apply causal carry, anticausal local pass -----------------------------------
+  PK_HD void helm_anticausal_local(const Params& p, double inF, double inG, double& A, double& cF, double& cG) {
+    double pw = p.rho;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (j < m) {
+        hF[j] += pw * inF;
+        if (MODE == NOISE_FULL) hG[j] += pw * inG;
+        pw *= p.rho;
+      }
+    }
+    double xF = 0.0, xG = 0.0; pw = 1.0;
+    PK_UNROLL
+    for (int j = M - 1; j >= 0; --j) {
+      if (j < m) {
+        xF = hF[j] + p.rho * xF; hF[j] = xF;
+        if (MODE == NOISE_FULL) { xG = hG[j] + p.rho * xG; hG[j] = xG; }
+        pw *= p.rho;
+      }
+    }
+    A = pw; cF = xF; cG = xG;
+  }
+
+  // ---- phase D3: apply anticausal carry, write the new iterate, accumulate |delta|^2, |w1|^2 ---
+  PK_HD void helm_finish_update(const Params& p, const Shared& sh, double inF, double inG) {
+    sn2 = 0.0; xn2 = 0.0;
+    // x_j = xl_j + rho^(m-j) * carry
+    double pwv[M];
+    double pw = p.rho;
+    PK_UNROLL
+    for (int j = M - 1; j >= 0; --j) {
+      if (j < m) { pwv[j] = pw; pw *= p.rho; } else { pwv[j] = 0.0; }
+    }
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (j < m) {
+        const int i = idx(p, j);
+        const double u1n = sh.U1[i] + du[j];
+        const double Fn = hF[j] + pwv[j] * inF;
+        const double dFv = Fn - sh.F[i];
+        sh.U1[i] = u1n; sh.F[i] = Fn;
+        double s2 = du[j] * du[j] + dFv * dFv, x2 = u1n * u1n + Fn * Fn;
+        if (MODE == NOISE_FULL) {
+          const double Gn = hG[j] + pwv[j] * inG;
+          const double dGv = Gn - sh.G[i];
+          sh.G[i] = Gn;
+          s2 += dGv * dGv; x2 += Gn * Gn;
+        }
+        sn2 += s2; xn2 += x2;
+      }
+    }
+  }
+
+  // ---- accept the step: u <- u1 (equations.py:195) ----------------------------------------------
+  PK_HD void accept(const Params& p, const Shared& sh) {
+    PK_UNROLL
+    for (int j = 0; j < M; ++j)
+      if (j < m) { const int i = idx(p, j); sh.U0[i] = sh.U1[i]; }
+  }
+
+  // ---- noise fields of this step: dXi = sum_k dW_k xi_k (stochastic_functions.py:229-234) -------
+  PK_HD void fill_noise(const Params& p, const Shared& sh, const double* xi, const double* xi_x, const double* xi_xx) {
+    if (MODE == NOISE_SCALAR) {
+      Xs = (p.nxi > 0) ? sh.dW[0] * p.xi_const : 0.0;
+      return;
+    }
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (j < m) {
+        const int g = s + j;
+        double X = 0.0, Xx = 0.0, Xxx = 0.0;
+        for (int k = 0; k < p.nxi; ++k) {
+          const double w = sh.dW[k];
+          X += w * xi[k * p.ne + g];
+          if (MODE == NOISE_FULL) { Xx += w * xi_x[k * p.ne + g]; Xxx += w * xi_xx[k * p.ne + g]; }
+        }
+        const int i = idx(p, j);
+        sh.X[i] = X;
+        if (MODE == NOISE_FULL) { sh.Xx[i] = Xx; sh.Xxx[i] = Xxx; }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator + Box-Muller. Counter =
+// (global realisation id, step, mode, sub-update), key = 64-bit seed: results do not depend on how
+// the ensemble is sharded over GPUs.
+// ------------------------------------------------------------------------------------------------
+PK_HD void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+  PK_UNROLL
+  for (int i = 0; i < 10; ++i) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+    const unsigned n1 = (unsigned)p1;
+    const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+    const unsigned n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step, unsigned mode, unsigned sub) {
+  unsigned o[4];
+  philox4x32_10(rid, step, mode, sub, (unsigned)seed, (unsigned)(seed >> 32), o);
+  const double two53 = 1.0 / 9007199254740992.0;
+  const double u1 = ((double)(((unsigned long long)(o[0] >> 5) << 26) | (o[1] >> 6)) + 0.5) * two53;
+  const double u2 = ((double)(((unsigned long long)(o[2] >> 5) << 26) | (o[3] >> 6)) + 0.5) * two53;
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-level orchestration, templated on an executor that provides
+//   each(f)            run f(Thread&) on every thread of the realisation
+//   sync()             barrier
+//   allreduce3(f, out) out[0..2] = sum over threads of the three partials f(th, v) fills
+//   scan_fwd(get, put) cyclic exclusive scan of the affine maps x -> A x + c (two channels sharing A)
+//                      that get() returns, in thread order 0..T-1; put() receives the value entering
+//                      its thread and returns the maps of the following reverse scan
+//   scan_rev(fin)      the reverse cyclic scan (order T-1..0); fin() receives the entering value
+//   one(f)             run f() once (thread 0)
+// ------------------------------------------------------------------------------------------------
+struct StepIO {
+  const double* dW_in;    // [nsteps, R, nxi] or null -> Philox
+  double* dW_out;         // [nsteps, R, nxi] or null
+  const double *xi, *xi_x, *xi_xx;   // [nxi, ne]
+  int R;                  // realisations in this launch (stride of dW_in/out)
+  int r;                  // this realisation (local index)
+  unsigned rid;           // global realisation id (Philox counter)
+  unsigned long long seed;
+  int step0;              // global index of the first step of this launch
+  int nsteps;
+  int* fail_step;         // [R] in/out: -1 = healthy, else global step index at which SNES diverged
+  int* its_last;          // [R] out: Newton iterations of the last attempted step
+  int* its_total;         // [R] in/out: accumulated Newton iterations
+  int* fail_reason;       // [R] out: 0 ok, 1 max_it, 2 nan, 3 dtol
+};
+
+template <class Exec, class Th>
+PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& io) {
+  int failed = io.fail_step[io.r];
+  int its_last = 0, its_total = io.its_total[io.r], reason = 0;
+  for (int n = 0; n < io.nsteps; ++n) {
+    // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
+    ex.each([&](Th& th) {
+      for (int k = th.t; k < p.nxi; k += p.T) {
+        const long long o = ((long long)n * io.R + io.r) * p.nxi + k;
+        double w;
+        if (io.dW_in) {
+          w = io.dW_in[o];
+        } else {
+          w = 0.0;
+          for (int j = 0; j < p.nupd; ++j)
+            w += philox_normal(io.seed, io.rid, (unsigned)(io.step0 + n), (unsigned)k, (unsigned)j) * p.sdt;
+        }
+        sh.dW[k] = w;
+        if (io.dW_out) io.dW_out[o] = w;
+      }
+    });
+    if (failed >= 0) { ex.sync(); continue; }
+    ex.sync();
+    ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
+    ex.sync();
+
+    // ---- SNES newtonls, basic line search ----
+    int it = 0;
+    double fnorm0 = 0.0;
+    bool converged = false, fail = false;
+    while (true) {
+      ex.each([&](Th& th) { th.assemble_begin(p, sh); });
+      ex.sync();
+      ex.each([&](Th& th) { th.assemble_finish(p, sh); });
+      double nrm[3];
+      ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);  // includes barriers
+      const double fnorm = sqrt(nrm[0]);
+      if (!(fnorm == fnorm) || fnorm > 1.7e308) { fail = true; reason = 2; break; }
+      if (it == 0) {
+        fnorm0 = fnorm;
+        if (fnorm < p.atol) { converged = true; break; }
+      } else {
+        if (fnorm < p.atol || fnorm <= p.rtol * fnorm0) { converged = true; break; }
+        if (sqrt(nrm[1]) < p.stol * sqrt(nrm[2])) { converged = true; break; }
+        if (fnorm > p.divtol * fnorm0) { fail = true; reason = 3; break; }
+      }
+      if (it >= p.max_it) { fail = true; reason = 1; break; }
+      // ---- linear solve + update ----
+      ex.each([&](Th& th) { th.reduce_build(p, sh); });
+      ex.sync();
+      ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+      ex.sync();
+      for (int d = 1; d < p.T / 2; d *= 2) {
+        ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
+        ex.sync();
+        ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+        ex.sync();
+      }
+      ex.each([&](Th& th) { th.pcr_final(p, sh); });
+      ex.sync();
+      ex.each([&](Th& th) { th.interior_solve(p, sh); });
+      ex.sync();
+      // forward cyclic scan (causal filter); its carries feed the anticausal local pass, whose maps
+      // are scanned in reverse; the reverse carries finish the update.
+      ex.scan_fwd([&](Th& th, double& A, double& c0, double& c1) { th.helm_causal_local(p, sh, A, c0, c1); },
+                  [&](Th& th, double in0, double in1, double& A, double& c0, double& c1) {
+                    th.helm_anticausal_local(p, in0, in1, A, c0, c1); });
+      ex.scan_rev([&](Th& th, double in0, double in1) { th.helm_finish_update(p, sh, in0, in1); });
+      ex.sync();
+      ++it;
+    }
+    its_last = it; its_total += it;
+    if (converged) {
+      ex.each([&](Th& th) { th.accept(p, sh); });
+    } else if (fail) {
+      failed = io.step0 + n;
+    }
+    ex.sync();
+  }
+  ex.one([&]() {
+    io.fail_step[io.r] = failed; io.its_last[io.r] = its_last; io.its_total[io.r] = its_total;
+    if (io.fail_reason) io.fail_reason[io.r] = reason;
+  });
+}
+
+}  // namespace pk

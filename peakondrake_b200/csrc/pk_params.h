@@ -1,0 +1,73 @@
+// pk_params.h -- POD parameter block shared by the CUDA kernels, the C-ABI host code and the
+// CPU emulation harness used by the not-gpu tests.  Plain C++, no CUDA types.
+//
+// Discretisation constants follow SURVEY.md App. A (CG1 on PeriodicIntervalMesh(ne, Ld),
+// reference experiment.py:171,178,208):  M_e = h/6 [[2,1],[1,2]], K_e = 1/h [[1,-1],[-1,1]],
+// D_e = 1/2 [[-1,-1],[1,1]],  H = M + alphasq K.
+#pragma once
+#include <cmath>
+
+namespace pk {
+
+enum NoiseMode {
+  NOISE_SCALAR = 0,   // dXi is one number per step (num_Xis==0, or Xi_family 'constant'); dXi_x=dXi_xx=0 => dG == 0
+  NOISE_X = 1,        // dXi varies in space, dXi_x=dXi_xx=0 ('no_gradient', stochastic_functions.py:121,189,232) => dG == 0
+  NOISE_FULL = 2      // 'hydrodynamic' with tables xi, xi_x, xi_xx (stochastic_functions.py:128-154,189-201)
+};
+
+struct Params {
+  int ne;        // cells == CG1 dofs
+  int T;         // threads (row chunks) per realisation, power of two, >= 2
+  int M;         // max rows per chunk; chunks have M or M-1 rows
+  int rem;       // chunks t < rem have M rows, the others M-1:  ne = T*(M-1) + rem
+  int nxi;       // number of noise modes (num_Xis)
+  int nupd;      // nXi_updates (stochastic_functions.py:213-217)
+  int mode;      // NoiseMode
+  int max_it;    // SNES max_it (50)
+  double h, dt, alphasq;
+  double mb, ma;          // M: off-diagonal h/6, diagonal 2h/3
+  double hb, ha;          // H: off-diagonal h/6 - a2/h, diagonal 2h/3 + 2 a2/h
+  double hm0, hm1, hm2;   // H*M circulant, offsets 0, +-1, +-2
+  double c1, c2;          // Dt*h/12, alphasq*Dt/(4h)
+  double h6, a26;         // h/6, alphasq/6
+  double rho, ikappa;     // H = kappa (1 - rho S)(1 - rho S^-1): |rho|<1
+  double rtol, atol, stol, divtol;  // PETSc SNES defaults 1e-8, 1e-50, 1e-8, 1e4
+  double sdt;             // sqrt(dt / nupd)
+  double xi_const;        // NOISE_SCALAR: the (spatially constant) value of xi_0, 0 if nxi==0
+};
+
+// chunk geometry
+static inline int chunk_rows(const Params& p, int t) { return t < p.rem ? p.M : p.M - 1; }
+static inline int chunk_start(const Params& p, int t) { return t * (p.M - 1) + (t < p.rem ? t : p.rem); }
+
+// Choose (T, M, rem) for a given ne: T = smallest power of two with 8T >= ne, chunks of
+// ceil/floor(ne/T) rows, which is then in [4, 8].  Returns false if ne < 8.
+static inline bool choose_layout(int ne, int* T, int* M, int* rem) {
+  if (ne < 8) return false;
+  int t = 2;
+  while (8 * t < ne) t *= 2;
+  int lo = ne / t;             // floor
+  int r = ne - lo * t;         // chunks with lo+1 rows
+  if (r == 0) { *M = lo; *rem = t; if (lo < 5) { *M = lo + 1; *rem = 0; } }
+  else { *M = lo + 1; *rem = r; }
+  *T = t;
+  return (*M >= 5 && *M <= 8);
+}
+
+static inline void fill_constants(Params& p) {
+  const double h = p.h, a2 = p.alphasq;
+  p.mb = h / 6.0; p.ma = 2.0 * h / 3.0;
+  p.hb = h / 6.0 - a2 / h; p.ha = 2.0 * h / 3.0 + 2.0 * a2 / h;
+  p.hm0 = 2.0 * p.hb * p.mb + p.ha * p.ma;
+  p.hm1 = p.hb * p.ma + p.ha * p.mb;
+  p.hm2 = p.hb * p.mb;
+  p.c1 = p.dt * h / 12.0; p.c2 = a2 * p.dt / (4.0 * h);
+  p.h6 = h / 6.0; p.a26 = a2 / 6.0;
+  const double disc = std::sqrt(p.ha * p.ha - 4.0 * p.hb * p.hb);
+  const double kappa = 0.5 * (p.ha + disc);
+  p.rho = -p.hb / kappa;
+  p.ikappa = 1.0 / kappa;
+  p.sdt = std::sqrt(p.dt / (p.nupd > 0 ? p.nupd : 1));
+}
+
+}  // namespace pk

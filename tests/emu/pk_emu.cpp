@@ -1,0 +1,130 @@
+// pk_emu.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// Executes the *device* code of peakondrake_b200/csrc/pk_core.h on the CPU by running the threads
+// of one CTA one after another between barriers.  The authoring container has no GPU; this lets
+// the not-gpu test-suite check the kernel's algorithm (assembly closed forms, two-level
+// pentadiagonal solve, Helmholtz scans, SNES logic) against the NumPy/SciPy oracle.  Threads are
+// run in ascending or descending order (`order`): any intra-phase race would make the two
+// orders disagree bit-wise, which tests/test_emulation.py checks.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <cmath>
+#include "../../peakondrake_b200/csrc/pk_core.h"
+
+using namespace pk;
+
+template <int M, int MODE>
+struct EmuExec {
+  typedef Thread<M, MODE> Th;
+  std::vector<Th> th;
+  int T, order;
+  std::vector<double> A, c0, c1;
+  EmuExec(const Params& p, int order_) : th(p.T), T(p.T), order(order_), A(p.T), c0(p.T), c1(p.T) {
+    for (int t = 0; t < T; ++t) th[t].init(p, t);
+  }
+  template <class F> void each(F f) {
+    if (order == 0) for (int t = 0; t < T; ++t) f(th[t]);
+    else for (int t = T - 1; t >= 0; --t) f(th[t]);
+  }
+  void sync() {}
+  template <class F> void one(F f) { f(); }
+  template <class F> void allreduce3(F f, double* out) {
+    out[0] = out[1] = out[2] = 0.0;
+    for (int t = 0; t < T; ++t) { double v[3]; f(th[t], v); out[0] += v[0]; out[1] += v[1]; out[2] += v[2]; }
+  }
+  // cyclic exclusive scan in thread order (dir=+1: 0..T-1, dir=-1: T-1..0)
+  void cyc_scan(int dir, std::vector<double>& in0, std::vector<double>& in1) {
+    double At = 1.0, t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < T; ++k) {
+      const int t = dir > 0 ? k : T - 1 - k;
+      t0 = A[t] * t0 + c0[t]; t1 = A[t] * t1 + c1[t]; At *= A[t];
+    }
+    double x0 = t0 / (1.0 - At), x1 = t1 / (1.0 - At);
+    for (int k = 0; k < T; ++k) {
+      const int t = dir > 0 ? k : T - 1 - k;
+      in0[t] = x0; in1[t] = x1;
+      x0 = A[t] * x0 + c0[t]; x1 = A[t] * x1 + c1[t];
+    }
+  }
+  template <class G, class P> void scan_fwd(G get, P put) {
+    each([&](Th& h) { get(h, A[h.t], c0[h.t], c1[h.t]); });
+    std::vector<double> in0(T), in1(T);
+    cyc_scan(+1, in0, in1);
+    each([&](Th& h) { double a, b, c; put(h, in0[h.t], in1[h.t], a, b, c); A[h.t] = a; c0[h.t] = b; c1[h.t] = c; });
+  }
+  template <class F> void scan_rev(F fin) {
+    std::vector<double> in0(T), in1(T);
+    cyc_scan(-1, in0, in1);
+    each([&](Th& h) { fin(h, in0[h.t], in1[h.t]); });
+  }
+};
+
+template <int M, int MODE>
+static void run_one(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
+  const int n = p.T * p.M;
+  std::vector<double> buf(7 * n + XB_SLOTS * p.T + (p.nxi > 0 ? p.nxi : 1), 0.0);
+  Shared sh;
+  sh.U0 = &buf[0]; sh.U1 = &buf[n]; sh.F = &buf[2 * n]; sh.G = &buf[3 * n];
+  sh.X = &buf[4 * n]; sh.Xx = &buf[5 * n]; sh.Xxx = &buf[6 * n];
+  sh.xb = &buf[7 * n]; sh.dW = &buf[7 * n + XB_SLOTS * p.T];
+  const long long off = (long long)io.r * p.ne;
+  for (int i = 0; i < p.ne; ++i) {
+    const int sl = row_slot(p, i);
+    sh.U0[sl] = u[off + i]; sh.U1[sl] = u1[off + i]; sh.F[sl] = dF[off + i];
+    sh.G[sl] = (MODE == NOISE_FULL) ? dG[off + i] : 0.0;
+  }
+  EmuExec<M, MODE> ex(p, order);
+  run_steps<EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  for (int i = 0; i < p.ne; ++i) {
+    const int sl = row_slot(p, i);
+    u[off + i] = sh.U0[sl]; u1[off + i] = sh.U1[sl]; dF[off + i] = sh.F[sl];
+    if (MODE == NOISE_FULL) dG[off + i] = sh.G[sl];
+  }
+}
+
+template <int M>
+static void run_mode(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
+  switch (p.mode) {
+    case NOISE_SCALAR: run_one<M, NOISE_SCALAR>(p, io, u, u1, dF, dG, order); break;
+    case NOISE_X: run_one<M, NOISE_X>(p, io, u, u1, dF, dG, order); break;
+    default: run_one<M, NOISE_FULL>(p, io, u, u1, dF, dG, order); break;
+  }
+}
+
+extern "C" int pk_emu_layout(int ne, int* T, int* M, int* rem) { return choose_layout(ne, T, M, rem) ? 0 : -1; }
+
+extern "C" double pk_emu_philox_normal(unsigned long long seed, unsigned rid, unsigned step, unsigned mode, unsigned sub) {
+  return philox_normal(seed, rid, step, mode, sub);
+}
+
+// Same argument meaning as pk_step() in include/peakon_b200.h, host pointers.
+extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mode, int nxi, int nupd,
+                           double xi_const, int R, int nsteps, int step0,
+                           double* u, double* u1, double* dF, double* dG,
+                           const double* xi, const double* xi_x, const double* xi_xx,
+                           const double* dW_in, double* dW_out, unsigned long long seed, unsigned rid0,
+                           int* fail_step, int* its_last, int* its_total, int* fail_reason,
+                           int order, int forceT, int forceM) {
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.ne = ne; p.h = Ld / ne; p.dt = dt; p.alphasq = alphasq; p.mode = mode; p.nxi = nxi; p.nupd = nupd;
+  p.max_it = 50; p.rtol = 1e-8; p.atol = 1e-50; p.stol = 1e-8; p.divtol = 1e4; p.xi_const = xi_const;
+  if (forceT > 0) { p.T = forceT; p.M = forceM; p.rem = ne - forceT * (forceM - 1); if (p.rem < 0 || p.rem > p.T) return -2; }
+  else if (!choose_layout(ne, &p.T, &p.M, &p.rem)) return -1;
+  fill_constants(p);
+  for (int r = 0; r < R; ++r) {
+    StepIO io;
+    io.dW_in = dW_in; io.dW_out = dW_out; io.xi = xi; io.xi_x = xi_x; io.xi_xx = xi_xx;
+    io.R = R; io.r = r; io.rid = rid0 + r; io.seed = seed; io.step0 = step0; io.nsteps = nsteps;
+    io.fail_step = fail_step; io.its_last = its_last; io.its_total = its_total; io.fail_reason = fail_reason;
+    switch (p.M) {
+      case 5: run_mode<5>(p, io, u, u1, dF, dG, order); break;
+      case 6: run_mode<6>(p, io, u, u1, dF, dG, order); break;
+      case 7: run_mode<7>(p, io, u, u1, dF, dG, order); break;
+      case 8: run_mode<8>(p, io, u, u1, dF, dG, order); break;
+      default: return -3;
+    }
+  }
+  return 0;
+}
