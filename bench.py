@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark: realisation*steps/s of the batched stochastic Camassa-Holm
+timestep (BASELINE.json metric), workload = BASELINE config 2 per GPU:
+  hydrodynamic/midpoint, ne=1000, Ld=40, dt=1e-3, 4 'sines' noise modes sigma=0.2, ic 'proper_peak',
+  1024 realisations per GPU (weak scaling), Brownian increments drawn in-kernel (Philox).
+
+A bench "step" is ONE pass of the hot path over the batch: one kernel launch that advances every
+realisation of the shard by STEPS_PER_LAUNCH timesteps (the reference's dump cadence, ndump=50).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            own arm (GPU)
+  python bench.py --impl reference ...                            CPU arm: the oracle port of the
+                                                                  reference's Firedrake path on all host cores
+Under torchrun (N>1) every rank drives one GPU; NCCL is used for the barrier, the max-over-ranks
+timing and the per-launch ensemble statistics all-reduce (the only exchange this path has).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NE, LD, DT, NXI, SIGMA, IC = 1000, 40.0, 1e-3, 4, 0.2, 'proper_peak'
+R_PER_GPU = 1024
+STEPS_PER_LAUNCH = 50
+B_ALG = 16 * NE + 8 * NXI      # algorithmic bytes per realisation-step
+METRIC = 'realisation_steps_per_sec'
+UNIT = 'realisation*steps/s'
+WORKLOAD = ('C2: stochastic CH hydrodynamic/midpoint, ne=1000, Ld=40, dt=1e-3, 4 sines sigma=0.2, '
+            'ic proper_peak, %d realisations/GPU, %d timesteps per launch' % (R_PER_GPU, STEPS_PER_LAUNCH))
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            f = [x.strip() for x in s.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, one worker per core, whole realisations each
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, nsteps = args
+    from oracle import ch_oracle as O
+    mesh = O.Mesh1D(NE, LD)
+    u0 = O.initial_u(mesh, IC)
+    tabs = O.noise_tables(mesh, 'sines', NXI, SIGMA)
+    dW = O.reference_dW(seed, nsteps + 1, NXI, DT)
+    orc = O.CHOracle(NE, LD, DT)
+    u = orc.solve(u0, dW[0] @ tabs[0], dW[0] @ tabs[1], dW[0] @ tabs[2])      # warm-up step (untimed)
+    t0 = time.perf_counter()
+    for n in range(1, nsteps + 1):
+        u = orc.solve(u, dW[n] @ tabs[0], dW[n] @ tabs[1], dW[n] @ tabs[2])
+    return time.perf_counter() - t0
+
+
+def cpu_rate(nsteps, workers=None, rounds=1):
+    """realisation*steps/s of the oracle on this host: `workers` processes, each integrating one
+    realisation of the bench workload for `nsteps` steps; returns (rate, workers, sample string)."""
+    import multiprocessing as mp
+    workers = workers or (os.cpu_count() or 1)
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    ctx = mp.get_context('fork')
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        for _ in range(rounds):
+            pool.map(_cpu_worker, [(s, nsteps) for s in range(workers)])
+    wall = time.perf_counter() - t0
+    # wall includes per-worker set-up (IC, tables, first step); the rate uses wall -> conservative
+    rate = workers * nsteps * rounds / wall
+    return rate, workers, ('%d realisations (one per core) x %d steps of the bench workload, oracle '
+                           '(NumPy/SciPy monolithic sparse-LU Newton), wall %.1f s' % (workers * rounds, nsteps, wall))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    nsteps = 40
+    # calibrate so that the whole run (W + K bench steps) stays within a few minutes
+    t0 = time.perf_counter()
+    rates = []
+    for _ in range(args.warmup):
+        cpu_rate(max(4, nsteps // 4), workers)
+    for _ in range(args.steps):
+        r, w, sample = cpu_rate(nsteps, workers)
+        rates.append(r)
+        if time.perf_counter() - t0 > 240:
+            break
+    rate = float(np.mean(rates))
+    units = workers * nsteps
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': len(rates), 'warmup': args.warmup, 'ms_per_step': 1e3 * units / rate,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'note': 'CPU arm: Firedrake is not installable offline; this is the '
+                   'oracle port of the same weak form (BASELINE.md section 4), each step a bounded sample'},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': workers, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    from peakondrake_b200 import ensemble as ens
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    R = R_PER_GPU
+    u0 = build_initial_u(NE, LD, IC)
+    eng = EnsembleIntegrator(NE, LD, DT, R, num_Xis=NXI, Xi_family='sines', sigma=SIGMA, seed=2026,
+                             rid_offset=rank * R, device=local)
+    eng.set_state(u0)
+    stats = ens.EnsembleStatistics(eng, nbins=64, lo=0.0, hi=LD)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > L2 (126 MB)
+    side = torch.cuda.Stream(device=dev)
+
+    def one_step():
+        flush.zero_()                         # L2 flush between timed iterations
+        eng.step(STEPS_PER_LAUNCH)
+        ms = eng.last_kernel_ms()             # CUDA events on the launching stream (synchronises)
+        # ensemble statistics: local fused reduction + ONE packed all-reduce on a side stream
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            stats.update(world > 1)
+        return ms
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kms = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        kms.append(one_step())
+    torch.cuda.current_stream(dev).wait_stream(side)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: the host-buffer C-ABI call, pinned host arrays, H2D + kernel + D2H every step ----
+    pin = lambda shape, dt_: torch.zeros(shape, dtype=dt_).pin_memory().numpy()
+    hu = pin((R, NE), torch.float64); hu[:] = u0
+    hu1, hdF, hdG = pin((R, NE), torch.float64), pin((R, NE), torch.float64), pin((R, NE), torch.float64)
+    hfs = pin((R,), torch.int32); hfs[:] = -1
+    hil, hit = pin((R,), torch.int32), pin((R,), torch.int32)
+    for _ in range(min(2, args.warmup)):
+        eng.step_host(STEPS_PER_LAUNCH, hu, hu1, hdF, hdG, None, hfs, hil, hit)
+    if world > 1:
+        dist.barrier()
+    te0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        eng.step_host(STEPS_PER_LAUNCH, hu, hu1, hdF, hdG, None, hfs, hil, hit)
+        energy_check = float(hu[0].max())       # the host reads the step's result
+    e2e_wall = time.perf_counter() - te0
+    h2d = 4 * R * NE * 8 + 2 * R * 4
+    d2h = 4 * R * NE * 8 + 3 * R * 4
+
+    tm = torch.tensor([dev_ms, e2e_wall * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in tm.cpu()]
+    units_per_step = world * R * STEPS_PER_LAUNCH
+    value = units_per_step * args.steps / (dev_ms * 1e-3)
+    e2e_value = units_per_step * e2e_steps / (e2e_ms * 1e-3)
+    failed = int((eng.fail_step >= 0).sum().item())
+    its_per_step = float(eng.its_total.double().mean().item()) / ((args.warmup + args.steps) * STEPS_PER_LAUNCH)
+
+    if rank == 0:
+        peak, which = measured_peak()
+        k_ms = float(np.mean(kms))
+        achieved = R * STEPS_PER_LAUNCH * B_ALG / (k_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'realisations_total': world * R, 'ne': NE, 'dt': DT,
+                       'timesteps_per_launch': STEPS_PER_LAUNCH, 'noise': 'Philox4x32-10 in-kernel',
+                       'l2': 'flushed between timed iterations (256 MB memset)',
+                       'layout': eng.layout, 'failed_realisations': failed,
+                       'mean_newton_its_per_step': its_per_step},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'steps': e2e_steps, 'api': 'pk_step_host (pinned host buffers)'},
+            'gpu_launches': args.steps * 4,   # per step: pk_step_kernel, pk_diag_kernel, pk_moments_partial, pk_moments_final
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': None, 'peak_source': which,
+                         'kernel': 'pk_step_kernel', 'kernel_ms': k_ms,
+                         'algorithmic_bytes_per_realisation_step': B_ALG,
+                         'note': 'fp64-pipe/latency bound by construction (SURVEY.md 8d): ~600 fp64 flop per '
+                                 'node-step against 16 algorithmic bytes; see DESIGN.md'},
+            'wall_ms_per_step': wall_ms / args.steps,
+        }
+        if args.cpu_baseline:
+            rate, cores, sample = cpu_rate(40)
+            line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            args.cpu_baseline = False     # cpu_baseline is reported at N=1 only
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,157 @@
+/*
+ * peakon_b200.h -- C ABI of the B200 ensemble integrator for peakondrake's stochastic
+ * Camassa-Holm timestep.
+ *
+ * The reference (tommbendall/peakondrake) has no FFI layer: its hot path is reached through the
+ * per-step operator protocol of its Python classes.  Each entry point
+ * below names the reference interface it replaces (file:line into /root/reference/peakondrake/).
+ * The Python binding a maintainer would add is shown in INTEGRATION.md and implemented in
+ * peakondrake_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C, no exceptions across the ABI: every function returns 0 on success, <0 on error;
+ *     pk_last_error() gives the message.
+ *   - all arrays are CALLER-OWNED.  Unless a function says "host", pointers are DEVICE pointers
+ *     on the context's device; fp64, realisation-major: u[r*ne + i] is CG1 dof i of realisation r
+ *     in the natural mesh order (node i at x = i*Ld/ne), i.e. u[r] equals the reference's
+ *     `u.dat.data` for that seed.
+ *   - work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL = default
+ *     stream); no hidden synchronisation except in the *_host functions.
+ *   - a context is not thread-safe; use one per host thread / device.
+ */
+#ifndef PEAKON_B200_H
+#define PEAKON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pk_ctx pk_ctx;
+
+/* noise_mode */
+#define PK_NOISE_SCALAR 0 /* num_Xis == 0, or Xi_family 'constant': dXi is a number, dXi_x = dXi_xx = 0 */
+#define PK_NOISE_X 1      /* scheme 'no_gradient': dXi varies in x, dXi_x = dXi_xx = 0 (stochastic_functions.py:121,189,232) */
+#define PK_NOISE_FULL 2   /* scheme 'hydrodynamic': dXi, dXi_x, dXi_xx from the tables */
+
+/* diagnostics computed by pk_diagnostics(): column index in out[r*PK_NDIAG + k] */
+enum {
+  PK_D_ENERGY = 0,      /* outputting.py:110 */
+  PK_D_L2U2,            /* ||u||_L2^2        (l2_u = sqrt, outputting.py:114) */
+  PK_D_H1SEMI2,         /* |u|_H1^2 = u^T K u (h1_u = sqrt(L2^2 + this), :116) */
+  PK_D_MASS_U,          /* :124 */
+  PK_D_MAX_DU,          /* :140 */
+  PK_D_MIN_DU,          /* :142 */
+  PK_D_MAX_JUMP_LOCAL,  /* :128 */
+  PK_D_MAX_U,           /* np.max(u), :158-160 (p_pde before the periodic factor) */
+  PK_D_L2M2,            /* ||m||_L2^2, m from M m = H u (diagnostic_equations.py:236-243) */
+  PK_D_H1SEMI_M2,       /* m^T K m */
+  PK_D_MASS_M,          /* :120 */
+  PK_D_M_MAX,           /* :164 */
+  PK_D_UMU,             /* u^T M m   (E_2 = 1/2 of it, :174) */
+  PK_D_ERR_SDE2,        /* ||u - u_sde||_L2^2 (:181), only if usde != NULL */
+  PK_NDIAG
+};
+/* integer outputs of pk_diagnostics(): idx[r*PK_NIDX + k]; ties -> lowest index (NumPy argmax/argmin) */
+enum {
+  PK_I_ARGMAX_DU = 0,   /* find_max(du)  outputting.py:254-258 */
+  PK_I_ARGMIN_DU,       /* find_min(du)  :248-252 */
+  PK_I_ARGMAX_U,        /* np.argmax(u)  :162, :388 */
+  PK_I_ARGMAX_JUMP,
+  PK_NIDX
+};
+
+typedef struct pk_config {
+  int32_t ne;            /* resolution: cells = CG1 dofs (experiment.py:171) */
+  int32_t R;             /* realisations held by this context (this GPU's shard) */
+  double Ld;             /* domain length */
+  double dt;             /* time step */
+  double alphasq;        /* alpha^2 > 0 (Camassa-Holm set-up, equations.py:26) */
+  int32_t noise_mode;    /* PK_NOISE_* */
+  int32_t num_xis;       /* number of noise modes (0 allowed) */
+  int32_t nxi_updates;   /* nXi_updates, >= 1 (stochastic_functions.py:213-217); used by the Philox path */
+  int32_t device;        /* CUDA device ordinal */
+  uint64_t seed;         /* Philox key */
+  uint32_t rid_offset;   /* global id of realisation 0 of this shard (Philox counter) */
+  int32_t max_it;        /* SNES max_it   (0 -> PETSc default 50) */
+  double rtol, atol, stol, divtol; /* SNES tolerances (0 -> PETSc defaults 1e-8, 1e-50, 1e-8, 1e4) */
+  double xi_const;       /* PK_NOISE_SCALAR: the constant value of xi_0 (sigma for 'constant') */
+} pk_config;
+
+/* Replaces Equations.__init__ (equations.py:63-95) + PrognosticVariables (simulation.py:227-249)
+ * for R realisations: validates the set-up, chooses the thread layout, allocates scratch. */
+int pk_create(const pk_config* cfg, pk_ctx** out);
+void pk_destroy(pk_ctx* ctx);
+const char* pk_last_error(const pk_ctx* ctx);  /* ctx may be NULL: last create error */
+
+/* Replaces StochasticFunctions.__init__'s tables (stochastic_functions.py:66-201):
+ * xi, xi_x, xi_xx are [num_xis, ne] device arrays shared by all realisations (xi_x/xi_xx may be
+ * NULL unless noise_mode == PK_NOISE_FULL).  Pointers are retained, not copied. */
+int pk_set_tables(pk_ctx* ctx, const double* xi, const double* xi_x, const double* xi_xx);
+
+/* Replaces `nsteps` passes of  Xis.update(t); equations.solve()  (simulation.py:96-108;
+ * stochastic_functions.py:204-236; equations.py:193-199) for every realisation.
+ *   u      [R, ne]  in/out  prognostic u
+ *   u1,dF,dG [R, ne] in/out the Newton unknown w1 = (u1, dF, dG) the reference carries between
+ *                   steps as warm start (equations.py:71,89); zero before the first step.
+ *                   dG may be NULL unless noise_mode == PK_NOISE_FULL (it is identically zero).
+ *   dW_in  [nsteps, R, num_xis] Brownian increments already scaled by sqrt(dt), or NULL to draw
+ *                   them in-kernel (Philox4x32-10 + Box-Muller, counter = (global realisation id,
+ *                   global step, mode, sub-update))
+ *   dW_out [nsteps, R, num_xis] or NULL: the increments actually used (for path-wise comparison)
+ *   fail_step [R] in/out  -1 = healthy; otherwise the global step index at which SNES diverged.
+ *                   A failed realisation is frozen (simulation.py:99-106) but its increments are
+ *                   still drawn (simulation.py:96).
+ *   its_last [R] out, its_total [R] in/out  Newton iteration counts.
+ * The context's global step counter advances by nsteps. */
+int pk_step(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+            const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+            int32_t* its_total, void* stream);
+
+/* Same, with HOST buffers: copies state (and dW_in) to internal device buffers, steps, copies the
+ * state, dW_out and the counters back, and synchronises.  This is the call a host application
+ * without device arrays makes; bench.py's "e2e" times it. */
+int pk_step_host(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                 const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                 int32_t* its_total);
+
+int pk_set_step_counter(pk_ctx* ctx, int64_t step);
+int64_t pk_get_step_counter(const pk_ctx* ctx);
+
+/* Replaces DiagnosticEquations.solve() for du, jump_du, m, u_sde (diagnostic_equations.py:94-113,
+ * 236-243,254-279,373-378) and the reductions of Outputting.dump_diagnostics (outputting.py:106-196)
+ * + find_min/find_max (:248-258), for every realisation.
+ *   u [R, ne] in
+ *   pq [R, 2] in or NULL: (p, q) of the "true" peakon for this dump (what update_constants reads from
+ *       the true-peakon file, diagnostic_equations.py:377-378); enables PK_D_ERR_SDE2
+ *   periodic: the `periodic` option (selects the u_sde formula)
+ *   want_m: compute the m-based columns (costs two more passes); otherwise they are NaN
+ *   out [R, PK_NDIAG] doubles, idx [R, PK_NIDX] int32
+ *   du_out [R, ne] or NULL: the DG0 field du (cell i = [node i, node i+1]) for host-side find_mus
+ *   fail_step [R] or NULL: rows of failed realisations are filled with NaN (outputting.py:107-108) */
+int pk_diagnostics(pk_ctx* ctx, const double* u, const double* pq, int32_t periodic, int32_t want_m,
+                   double* out, int32_t* idx, double* du_out, const int32_t* fail_step, void* stream);
+
+/* Ensemble statistics for one dump (the quantities the reference accumulates across seeds off-line:
+ * running mean of u, experiment.py:224-227; histograms plotted by plotting/plot_stochastic_histograms.py:61-67).
+ *   diag/idx: outputs of pk_diagnostics for the same state
+ *   packed [2*ne + 1 + 2*nbins] doubles out:
+ *     sum_r u | sum_r u^2 | number of healthy realisations | histogram of q_pde on [q_lo,q_hi) |
+ *     histogram of min_du on [d_lo,d_hi)      (integer counts stored as doubles; out-of-range -> end bins)
+ * Sums are order-fixed (deterministic); a multi-GPU caller all-reduces `packed` once (ncclSum). */
+int pk_ensemble_stats(pk_ctx* ctx, const double* u, const int32_t* fail_step, const double* diag,
+                      const int32_t* idx, int32_t nbins, double q_lo, double q_hi, double d_lo,
+                      double d_hi, double* packed, void* stream);
+
+/* layout query (for tests / documentation): threads per realisation, rows per thread, remainder */
+int pk_get_layout(const pk_ctx* ctx, int32_t* T, int32_t* M, int32_t* rem, int32_t* smem_bytes);
+
+/* measured duration (ms) of the kernels launched by the last pk_step(_host) call, from CUDA events
+ * recorded on the launching stream; synchronises on the second event. */
+double pk_last_step_kernel_ms(pk_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEAKON_B200_H */

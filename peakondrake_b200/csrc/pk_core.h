@@ -25,14 +25,6 @@
 #pragma once
 #include "pk_params.h"
 
-#if defined(__CUDACC__)
-#define PK_HD __host__ __device__ __forceinline__
-#define PK_UNROLL _Pragma("unroll")
-#else
-#define PK_HD inline __attribute__((always_inline))
-#define PK_UNROLL
-#endif
-
 namespace pk {
 
 // Shared (per-realisation) storage. Field arrays are [M*T] doubles, interleaved: row j of chunk t

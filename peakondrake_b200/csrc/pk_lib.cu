@@ -1,0 +1,630 @@
+// pk_lib.cu -- CUDA kernels (sm_100a) and the C ABI declared in include/peakon_b200.h.
+//
+// Build (see __graft_entry__.build):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared
+//        -o peakondrake_b200/libpeakon_b200.so peakondrake_b200/csrc/pk_lib.cu
+//
+// One CTA integrates one realisation for `nsteps` timesteps with its whole state resident in
+// shared memory (pk_core.h holds the thread-level phases, shared with the CPU emulation harness).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <cmath>
+#include "pk_core.h"
+#include "../../include/peakon_b200.h"
+
+using namespace pk;
+
+// ------------------------------------------------------------------------------------------------
+// device-side executor: one CUDA thread per chunk
+// ------------------------------------------------------------------------------------------------
+template <int M, int MODE>
+struct GpuExec {
+  typedef Thread<M, MODE> Th;
+  Th& th;
+  double* red;        // [3*32] reduction / scan scratch in shared memory
+  double rA, rc0, rc1;  // maps of the pending reverse scan
+  __device__ __forceinline__ GpuExec(Th& t, double* scratch) : th(t), red(scratch) {}
+
+  template <class F> __device__ __forceinline__ void each(F f) { if (th.active) f(th); }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+  template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
+
+  template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
+    double v[3] = {0.0, 0.0, 0.0};
+    if (th.active) f(th, v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+      v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
+      v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) { red[w] = v[0]; red[32 + w] = v[1]; red[64 + w] = v[2]; }
+    __syncthreads();
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < nw; ++i) { s0 += red[i]; s1 += red[32 + i]; s2 += red[64 + i]; }
+    out[0] = s0; out[1] = s1; out[2] = s2;
+    __syncthreads();
+  }
+
+  // Cyclic exclusive scan of affine maps over the block. DIR=+1: thread order 0..T-1, value
+  // entering thread t comes from t-1; DIR=-1: order T-1..0. Inactive threads carry the identity.
+  template <int DIR>
+  __device__ __forceinline__ void cyc_scan(double A, double c0, double c1, double& in0, double& in1) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // inclusive scan inside the warp (Kogge-Stone); "earlier" = lower lane for DIR=+1, higher for -1
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double Ao, c0o, c1o;
+      if (DIR > 0) {
+        Ao = __shfl_up_sync(0xffffffffu, A, o); c0o = __shfl_up_sync(0xffffffffu, c0, o); c1o = __shfl_up_sync(0xffffffffu, c1, o);
+      } else {
+        Ao = __shfl_down_sync(0xffffffffu, A, o); c0o = __shfl_down_sync(0xffffffffu, c0, o); c1o = __shfl_down_sync(0xffffffffu, c1, o);
+      }
+      const bool ok = (DIR > 0) ? (lane >= o) : (lane + o < 32);
+      if (ok) { c0 = A * c0o + c0; c1 = A * c1o + c1; A = A * Ao; }
+    }
+    const int last = (DIR > 0) ? 31 : 0;
+    if (lane == last) { red[w] = A; red[32 + w] = c0; red[64 + w] = c1; }
+    __syncthreads();
+    // compose the warp aggregates in scan order; remember the prefix in front of my warp
+    double tA = 1.0, t0 = 0.0, t1 = 0.0, eA = 1.0, e0 = 0.0, e1 = 0.0;
+    for (int k = 0; k < nw; ++k) {
+      const int ww = (DIR > 0) ? k : nw - 1 - k;
+      if (ww == w) { eA = tA; e0 = t0; e1 = t1; }
+      const double a = red[ww];
+      t0 = a * t0 + red[32 + ww]; t1 = a * t1 + red[64 + ww]; tA = a * tA;
+    }
+    const double inv = 1.0 / (1.0 - tA);
+    const double x0 = t0 * inv, x1 = t1 * inv;          // value entering the first thread (cyclic closure)
+    const double w0 = eA * x0 + e0, w1 = eA * x1 + e1;  // value entering my warp
+    const double o0 = A * w0 + c0, o1 = A * w1 + c1;    // value leaving my thread
+    double p0, p1;
+    if (DIR > 0) { p0 = __shfl_up_sync(0xffffffffu, o0, 1); p1 = __shfl_up_sync(0xffffffffu, o1, 1); }
+    else { p0 = __shfl_down_sync(0xffffffffu, o0, 1); p1 = __shfl_down_sync(0xffffffffu, o1, 1); }
+    const bool first = (DIR > 0) ? (lane == 0) : (lane == 31);
+    in0 = first ? w0 : p0; in1 = first ? w1 : p1;
+    __syncthreads();
+  }
+
+  template <class G, class P> __device__ __forceinline__ void scan_fwd(G get, P put) {
+    double A = 1.0, c0 = 0.0, c1 = 0.0, in0, in1;
+    if (th.active) get(th, A, c0, c1);
+    cyc_scan<+1>(A, c0, c1, in0, in1);
+    rA = 1.0; rc0 = 0.0; rc1 = 0.0;
+    if (th.active) put(th, in0, in1, rA, rc0, rc1);
+  }
+  template <class F> __device__ __forceinline__ void scan_rev(F fin) {
+    double in0, in1;
+    cyc_scan<-1>(rA, rc0, rc1, in0, in1);
+    if (th.active) fin(th, in0, in1);
+  }
+};
+
+struct StepArgs {
+  double *u, *u1, *dF, *dG;
+  const double *xi, *xi_x, *xi_xx;
+  const double* dW_in;
+  double* dW_out;
+  int *fail_step, *its_last, *its_total;
+  int R, step0, nsteps;
+  unsigned rid0;
+  unsigned long long seed;
+};
+
+template <int MODE> struct NArr { enum { n = (MODE == NOISE_FULL) ? 7 : (MODE == NOISE_X ? 4 : 3) }; };
+
+template <int M, int MODE, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int n = p.T * M;
+  Shared sh;
+  sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
+  double* nxt = smem + 3 * n;
+  if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
+  else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
+  else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
+  sh.xb = nxt; nxt += XB_SLOTS * p.T;
+  double* red = nxt; nxt += 96;
+  sh.dW = nxt;
+
+  const int r = blockIdx.x;
+  const long long off = (long long)r * p.ne;
+  // coalesced global reads, scattered into the chunk-interleaved shared layout
+  for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
+    const int sl = row_slot(p, i);
+    sh.U0[sl] = a.u[off + i]; sh.U1[sl] = a.u1[off + i]; sh.F[sl] = a.dF[off + i];
+    if (MODE == NOISE_FULL) sh.G[sl] = a.dG[off + i];
+  }
+  __syncthreads();
+
+  Thread<M, MODE> th;
+  th.init(p, threadIdx.x);
+  GpuExec<M, MODE> ex(th, red);
+  StepIO io;
+  io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
+  io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
+  io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
+  run_steps<GpuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  __syncthreads();
+
+  for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
+    const int sl = row_slot(p, i);
+    a.u[off + i] = sh.U0[sl]; a.u1[off + i] = sh.U1[sl]; a.dF[off + i] = sh.F[sl];
+    if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[sl];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics kernel: one CTA per realisation, natural order, coalesced
+// ------------------------------------------------------------------------------------------------
+struct DiagArgs {
+  const double* u;
+  const double* pq;        // [R,2] (p_true, q) of the peakon SDE or null
+  double* out;             // [R, PK_NDIAG]
+  int* idx;                // [R, PK_NIDX]
+  double* du_out;          // [R, ne] or null
+  double* scratch;         // [R, 2, ne] (b = H u, m) or null -> skip the m diagnostics
+  const int* fail_step;
+  int ne, periodic;
+  double h, alphasq, Ld;
+  double rhoM, gscale;     // mass-matrix inverse: m_i = gscale * sum_k g_k b_{i+k}
+  int K;                   // truncation radius of the (exponentially decaying) inverse stencil, or -1: full cyclic sum
+};
+
+struct ArgV { double v; int i; };
+__device__ __forceinline__ void amax(ArgV& a, double v, int i) { if (v > a.v || (v == a.v && i < a.i)) { a.v = v; a.i = i; } }
+__device__ __forceinline__ void amin(ArgV& a, double v, int i) { if (v < a.v || (v == a.v && i < a.i)) { a.v = v; a.i = i; } }
+
+template <bool IS_MAX>
+__device__ __forceinline__ ArgV block_arg(ArgV a, ArgV* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgV b; b.v = __shfl_xor_sync(0xffffffffu, a.v, o); b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    if (IS_MAX) amax(a, b.v, b.i); else amin(a, b.v, b.i);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) sm[w] = a;
+  __syncthreads();
+  ArgV r = sm[0];
+  for (int k = 1; k < nw; ++k) { if (IS_MAX) amax(r, sm[k].v, sm[k].i); else amin(r, sm[k].v, sm[k].i); }
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int k = 0; k < nw; ++k) s += sm[k];
+  __syncthreads();
+  return s;
+}
+
+// u_sde nodal value, diagnostic_equations.py:254-279 with the amplitude of :377 (third periodic
+// branch reproduces the reference's parenthesis at :270).
+__device__ __forceinline__ double usde_at(double x, double p_true, double q, double Ld, double alphasq, int periodic) {
+  const double al = sqrt(alphasq);
+  const double E = exp(-Ld / al);
+  const double p = p_true * 0.5 * (1.0 + E) / (1.0 - E);
+  if (periodic) {
+    if (x < q - 0.5 * Ld) return p * ((exp(-(x - q + Ld) / al) + E * exp((x - q + Ld) / al)) / (1.0 - E));
+    if (x < q + 0.5 * Ld) { const double d = sqrt((q - x) * (q - x) / alphasq); return p * ((exp(-d) + E * exp(d)) / (1.0 - E)); }
+    return p * ((exp(-(q + Ld - x) / al) + exp(-Ld / al * exp((q + Ld - x) / al))) / (1.0 - E));
+  }
+  if (x < q - 0.5 * Ld) return p * exp(-(x - q + Ld) / al);
+  if (x < q + 0.5 * Ld) return p * exp(-sqrt((q - x) * (q - x) / alphasq));
+  return p * exp(-(q + Ld - x) / al);
+}
+
+__global__ void __launch_bounds__(256) pk_diag_kernel(const __grid_constant__ DiagArgs a) {
+  __shared__ double ssum[32];
+  __shared__ ArgV sarg[32];
+  const int r = blockIdx.x, ne = a.ne;
+  const double* u = a.u + (long long)r * ne;
+  double* out = a.out + (long long)r * PK_NDIAG;
+  int* idx = a.idx + (long long)r * PK_NIDX;
+  if (a.fail_step && a.fail_step[r] >= 0) {   // outputting.py:107-108
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int k = threadIdx.x; k < PK_NDIAG; k += blockDim.x) out[k] = qnan;
+    for (int k = threadIdx.x; k < PK_NIDX; k += blockDim.x) idx[k] = -1;
+    return;
+  }
+  const double h = a.h, ih = 1.0 / a.h, a2 = a.alphasq;
+  double sM = 0.0, sK = 0.0, sU = 0.0, sE = 0.0;
+  ArgV mxdu = {-INFINITY, 0x7fffffff}, mndu = {INFINITY, 0x7fffffff}, mxu = {-INFINITY, 0x7fffffff}, mxj = {-INFINITY, 0x7fffffff};
+  double* b = a.scratch ? a.scratch + (long long)r * 2 * ne : nullptr;
+  double* mm = b ? b + ne : nullptr;
+  const double pt = a.pq ? a.pq[2 * r] : 0.0, qq = a.pq ? a.pq[2 * r + 1] : 0.0;
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    const int im = (i == 0) ? ne - 1 : i - 1, ip = (i == ne - 1) ? 0 : i + 1;
+    const double um = u[im], u0 = u[i], up = u[ip];
+    const double du = (up - u0) * ih;          // DG0 cell i          (diagnostic_equations.py:94-101)
+    const double dum = (u0 - um) * ih;         // DG0 cell i-1
+    const double jmp = fabs(du - dum);         // |jump(du)| at vertex i (:103-113)
+    sM += (h * (1.0 / 3.0)) * (u0 * u0 + u0 * up + up * up);   // cell integral of u^2
+    sK += (up - u0) * (up - u0) * ih;                          // cell integral of u_x^2
+    sU += h * u0;
+    amax(mxdu, du, i); amin(mndu, du, i); amax(mxu, u0, i); amax(mxj, jmp, i);
+    if (a.du_out) a.du_out[(long long)r * ne + i] = du;
+    if (b) b[i] = a.h / 6.0 * (um + 4.0 * u0 + up) + a2 * ih * (2.0 * u0 - um - up);
+    if (a.pq) {
+      const double e0 = u0 - usde_at(i * h, pt, qq, a.Ld, a2, a.periodic);
+      const double e1 = up - usde_at(ip * h, pt, qq, a.Ld, a2, a.periodic);
+      sE += (h * (1.0 / 3.0)) * (e0 * e0 + e0 * e1 + e1 * e1);
+    }
+  }
+  sM = block_sum(sM, ssum); sK = block_sum(sK, ssum); sU = block_sum(sU, ssum);
+  if (a.pq) sE = block_sum(sE, ssum);
+  mxdu = block_arg<true>(mxdu, sarg); mndu = block_arg<false>(mndu, sarg);
+  mxu = block_arg<true>(mxu, sarg); mxj = block_arg<true>(mxj, sarg);
+  double sMm = 0.0, sKm = 0.0, sm1 = 0.0, sUm = 0.0, mmax = -INFINITY;
+  if (b) {
+    __syncthreads();
+    // m = M^-1 b by the explicit (exponentially decaying) circulant inverse
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+      double acc = 0.0;
+      if (a.K < 0) {
+        const double rn = pow(a.rhoM, (double)ne);
+        double pk_ = 1.0, pnk = rn;     // rho^k, rho^(n-k)
+        const double irho = 1.0 / a.rhoM;
+        for (int k = 0; k < ne; ++k) {
+          int j = i + k; if (j >= ne) j -= ne;
+          acc += (pk_ + pnk) * b[j];
+          pk_ *= a.rhoM; pnk *= irho;
+        }
+      } else {
+        double pk_ = 1.0;
+        acc = b[i];
+        for (int k = 1; k <= a.K; ++k) {
+          pk_ *= a.rhoM;
+          int jp = i + k; if (jp >= ne) jp -= ne;
+          int jm = i - k; if (jm < 0) jm += ne;
+          acc += pk_ * (b[jp] + b[jm]);
+        }
+      }
+      mm[i] = acc * a.gscale;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+      const int ip = (i == ne - 1) ? 0 : i + 1;
+      const double m0 = mm[i], mp = mm[ip], u0 = u[i], up = u[ip];
+      sMm += (h * (1.0 / 3.0)) * (m0 * m0 + m0 * mp + mp * mp);
+      sKm += (mp - m0) * (mp - m0) * ih;
+      sm1 += h * m0;
+      sUm += (h * (1.0 / 6.0)) * (2.0 * u0 * m0 + u0 * mp + up * m0 + 2.0 * up * mp);
+      mmax = fmax(mmax, m0);
+    }
+    sMm = block_sum(sMm, ssum); sKm = block_sum(sKm, ssum); sm1 = block_sum(sm1, ssum); sUm = block_sum(sUm, ssum);
+    ArgV t = {mmax, 0}; t = block_arg<true>(t, sarg); mmax = t.v;
+  }
+  if (threadIdx.x == 0) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    out[PK_D_ENERGY] = sM + a2 * sK;
+    out[PK_D_L2U2] = sM; out[PK_D_H1SEMI2] = sK; out[PK_D_MASS_U] = sU;
+    out[PK_D_MAX_DU] = mxdu.v; out[PK_D_MIN_DU] = mndu.v; out[PK_D_MAX_JUMP_LOCAL] = mxj.v; out[PK_D_MAX_U] = mxu.v;
+    out[PK_D_L2M2] = b ? sMm : qnan; out[PK_D_H1SEMI_M2] = b ? sKm : qnan; out[PK_D_MASS_M] = b ? sm1 : qnan;
+    out[PK_D_M_MAX] = b ? mmax : qnan; out[PK_D_UMU] = b ? sUm : qnan;
+    out[PK_D_ERR_SDE2] = a.pq ? sE : qnan;
+    idx[PK_I_ARGMAX_DU] = mxdu.i; idx[PK_I_ARGMIN_DU] = mndu.i; idx[PK_I_ARGMAX_U] = mxu.i; idx[PK_I_ARGMAX_JUMP] = mxj.i;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// ensemble statistics: per-x moments of u over the healthy realisations + histograms of two scalar
+// diagnostics, packed into ONE fp64 buffer so that a multi-GPU run needs a single all-reduce
+// (SURVEY.md 8e). Deterministic: fixed-order partial sums, integer histogram counts.
+//   packed = [ sum_r u (ne) | sum_r u^2 (ne) | n_healthy (1) | hist q_pde (nbins) | hist min_du (nbins) ]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pk_moments_partial(const double* __restrict__ u, const int* __restrict__ fail_step,
+                                                          int R, int ne, int rows_per_tile, double* __restrict__ scratch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tile = blockIdx.y;
+  const int r0 = tile * rows_per_tile, r1 = min(R, r0 + rows_per_tile);
+  double s1 = 0.0, s2 = 0.0;
+  if (i < ne) {
+    for (int r = r0; r < r1; ++r) {
+      if (fail_step[r] >= 0) continue;
+      const double v = u[(long long)r * ne + i];
+      s1 += v; s2 += v * v;
+    }
+    scratch[(long long)tile * 2 * ne + i] = s1;
+    scratch[(long long)tile * 2 * ne + ne + i] = s2;
+  }
+}
+
+__global__ void __launch_bounds__(256) pk_moments_final(const double* __restrict__ scratch, int ntile, int ne,
+                                                        const int* __restrict__ fail_step, const double* __restrict__ diag,
+                                                        const int* __restrict__ idx, int R, int nbins, double h,
+                                                        double q_lo, double q_hi, double d_lo, double d_hi,
+                                                        double* __restrict__ packed) {
+  extern __shared__ int hist[];   // [2*nbins + 1]
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = tid; i < 2 * ne; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int t = 0; t < ntile; ++t) s += scratch[(long long)t * 2 * ne + i];
+    packed[i] = s;
+  }
+  if (blockIdx.x == 0) {
+    for (int k = threadIdx.x; k < 2 * nbins + 1; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+      if (fail_step[r] >= 0) continue;
+      atomicAdd(&hist[2 * nbins], 1);
+      const double q = (idx[r * PK_NIDX + PK_I_ARGMAX_U] + 0.5) * h;
+      int b = (int)floor((q - q_lo) / (q_hi - q_lo) * nbins);
+      b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);
+      atomicAdd(&hist[b], 1);
+      const double d = diag[r * PK_NDIAG + PK_D_MIN_DU];
+      int c = (int)floor((d - d_lo) / (d_hi - d_lo) * nbins);
+      c = c < 0 ? 0 : (c >= nbins ? nbins - 1 : c);
+      atomicAdd(&hist[nbins + c], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * nbins + 1; k += blockDim.x) {
+      const int dst = (k == 2 * nbins) ? 2 * ne : 2 * ne + 1 + k;
+      packed[dst] = (double)hist[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct pk_ctx {
+  pk_config cfg;
+  Params p;
+  const double *xi, *xi_x, *xi_xx;
+  long long step;
+  size_t smem;
+  int block;
+  std::string err;
+  // internal device buffers for the *_host entry points
+  double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;
+  double* d_scratch;   // diagnostics scratch [R,2,ne]
+  double* d_mom;       // moments partial sums [32, 2*ne]
+  cudaEvent_t ev0, ev1;
+  bool timed;
+};
+
+static std::string g_create_err;
+
+static int fail(pk_ctx* c, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (c) c->err = buf; else g_create_err = buf;
+  return -1;
+}
+#define CK(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+typedef void (*kern_t)(const Params, const StepArgs);
+
+template <int M, int MODE> static kern_t pick_tb(int block) {
+  if (block <= 128) return pk_step_kernel<M, MODE, 128, 2>;
+  if (block <= 256) return pk_step_kernel<M, MODE, 256, 1>;
+  return pk_step_kernel<M, MODE, 512, 1>;
+}
+template <int M> static kern_t pick_mode(int mode, int block) {
+  switch (mode) {
+    case NOISE_SCALAR: return pick_tb<M, NOISE_SCALAR>(block);
+    case NOISE_X: return pick_tb<M, NOISE_X>(block);
+    default: return pick_tb<M, NOISE_FULL>(block);
+  }
+}
+static kern_t pick_kernel(const Params& p, int block) {
+  switch (p.M) {
+    case 5: return pick_mode<5>(p.mode, block);
+    case 6: return pick_mode<6>(p.mode, block);
+    case 7: return pick_mode<7>(p.mode, block);
+    case 8: return pick_mode<8>(p.mode, block);
+  }
+  return nullptr;
+}
+
+extern "C" const char* pk_last_error(const pk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, "pk_create: null argument");
+  *out = nullptr;
+  if (!(cfg->alphasq > 0.0)) return fail(nullptr, "Schemes for alphasq <= 0 are not implemented (reference equations.py:166-167)");
+  if (cfg->ne < 8) return fail(nullptr, "pk_create: resolution ne=%d too small (need >= 8)", cfg->ne);
+  if (cfg->R < 1) return fail(nullptr, "pk_create: R must be >= 1");
+  if (cfg->noise_mode < 0 || cfg->noise_mode > 2) return fail(nullptr, "pk_create: bad noise_mode %d", cfg->noise_mode);
+  if (cfg->num_xis < 0) return fail(nullptr, "pk_create: num_xis < 0");
+  if (cfg->noise_mode == PK_NOISE_SCALAR && cfg->num_xis > 1)
+    return fail(nullptr, "pk_create: scalar noise supports one Xi only (reference stochastic_functions.py:111-112)");
+  pk_ctx* c = new pk_ctx();
+  c->cfg = *cfg;
+  Params& p = c->p;
+  memset(&p, 0, sizeof(p));
+  p.ne = cfg->ne; p.h = cfg->Ld / cfg->ne; p.dt = cfg->dt; p.alphasq = cfg->alphasq;
+  p.mode = cfg->noise_mode; p.nxi = cfg->num_xis; p.nupd = cfg->nxi_updates > 0 ? cfg->nxi_updates : 1;
+  p.max_it = cfg->max_it > 0 ? cfg->max_it : 50;
+  p.rtol = cfg->rtol > 0 ? cfg->rtol : 1e-8; p.atol = cfg->atol > 0 ? cfg->atol : 1e-50;
+  p.stol = cfg->stol > 0 ? cfg->stol : 1e-8; p.divtol = cfg->divtol > 0 ? cfg->divtol : 1e4;
+  p.xi_const = cfg->xi_const;
+  if (!choose_layout(p.ne, &p.T, &p.M, &p.rem)) { delete c; return fail(nullptr, "pk_create: no thread layout for ne=%d", cfg->ne); }
+  fill_constants(p);
+  const int narr = p.mode == NOISE_FULL ? 7 : (p.mode == NOISE_X ? 4 : 3);
+  c->smem = sizeof(double) * ((size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 96 + (p.nxi > 0 ? p.nxi : 1));
+  c->block = p.T < 32 ? 32 : p.T;
+  if (c->block > 512 || c->smem > 227 * 1024) {
+    const int ne = p.ne; delete c;
+    return fail(nullptr, "pk_create: ne=%d needs a thread-block cluster per realisation (state does not fit one SM); not built yet", ne);
+  }
+  c->xi = c->xi_x = c->xi_xx = nullptr;
+  c->step = 0; c->d_state = nullptr; c->d_dWin = c->d_dWout = nullptr; c->d_cnt = nullptr; c->dW_cap = 0; c->d_scratch = nullptr; c->d_mom = nullptr;
+  c->timed = false;
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
+  kern_t k = pick_kernel(p, c->block);
+  e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+  if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaFuncSetAttribute(smem=%zu): %s", c->smem, m.c_str()); }
+  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  *out = c;
+  return 0;
+}
+
+extern "C" void pk_destroy(pk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->d_state) cudaFree(c->d_state);
+  if (c->d_dWin) cudaFree(c->d_dWin);
+  if (c->d_dWout) cudaFree(c->d_dWout);
+  if (c->d_cnt) cudaFree(c->d_cnt);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->d_mom) cudaFree(c->d_mom);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+extern "C" int pk_set_tables(pk_ctx* c, const double* xi, const double* xi_x, const double* xi_xx) {
+  if (!c) return -1;
+  if (c->p.mode != NOISE_SCALAR && c->p.nxi > 0 && !xi) return fail(c, "pk_set_tables: xi is required");
+  if (c->p.mode == NOISE_FULL && c->p.nxi > 0 && (!xi_x || !xi_xx)) return fail(c, "pk_set_tables: xi_x and xi_xx are required for PK_NOISE_FULL");
+  c->xi = xi; c->xi_x = xi_x; c->xi_xx = xi_xx;
+  return 0;
+}
+
+extern "C" int pk_set_step_counter(pk_ctx* c, int64_t s) { if (!c) return -1; c->step = s; return 0; }
+extern "C" int64_t pk_get_step_counter(const pk_ctx* c) { return c ? c->step : -1; }
+
+extern "C" int pk_get_layout(const pk_ctx* c, int32_t* T, int32_t* M, int32_t* rem, int32_t* smem) {
+  if (!c) return -1;
+  if (T) *T = c->p.T; if (M) *M = c->p.M; if (rem) *rem = c->p.rem; if (smem) *smem = (int32_t)c->smem;
+  return 0;
+}
+
+extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                       const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                       int32_t* its_total, void* stream) {
+  if (!c) return -1;
+  if (nsteps < 0) return fail(c, "pk_step: nsteps < 0");
+  if (!u || !u1 || !dF || !fail_step || !its_last || !its_total) return fail(c, "pk_step: null state/counter pointer");
+  if (c->p.mode == NOISE_FULL && !dG) return fail(c, "pk_step: dG is required for PK_NOISE_FULL");
+  if (c->p.mode != NOISE_SCALAR && c->p.nxi > 0 && !c->xi) return fail(c, "pk_step: noise tables not set (pk_set_tables)");
+  if (nsteps == 0) return 0;
+  CK(c, cudaSetDevice(c->cfg.device));
+  StepArgs a;
+  a.u = u; a.u1 = u1; a.dF = dF; a.dG = dG; a.xi = c->xi; a.xi_x = c->xi_x; a.xi_xx = c->xi_xx;
+  a.dW_in = dW_in; a.dW_out = dW_out; a.fail_step = fail_step; a.its_last = its_last; a.its_total = its_total;
+  a.R = c->cfg.R; a.step0 = (int)c->step; a.nsteps = nsteps; a.rid0 = c->cfg.rid_offset; a.seed = c->cfg.seed;
+  cudaStream_t st = (cudaStream_t)stream;
+  kern_t k = pick_kernel(c->p, c->block);
+  CK(c, cudaEventRecord(c->ev0, st));
+  k<<<c->cfg.R, c->block, c->smem, st>>>(c->p, a);
+  CK(c, cudaGetLastError());
+  CK(c, cudaEventRecord(c->ev1, st));
+  c->timed = true;
+  c->step += nsteps;
+  return 0;
+}
+
+extern "C" double pk_last_step_kernel_ms(pk_ctx* c) {
+  if (!c || !c->timed) return -1.0;
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                            const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                            int32_t* its_total) {
+  if (!c) return -1;
+  if (!u || !u1 || !dF || !fail_step || !its_last || !its_total) return fail(c, "pk_step_host: null state/counter pointer");
+  CK(c, cudaSetDevice(c->cfg.device));
+  const size_t R = c->cfg.R, ne = c->p.ne, fld = R * ne;
+  const bool hasG = (c->p.mode == NOISE_FULL);
+  if (hasG && !dG) return fail(c, "pk_step_host: dG is required for PK_NOISE_FULL");
+  if (!c->d_state) {
+    CK(c, cudaMalloc(&c->d_state, sizeof(double) * 4 * fld));
+    CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * 3 * R));
+  }
+  const size_t ndw = (size_t)nsteps * R * (size_t)c->p.nxi;
+  if (ndw > c->dW_cap) {
+    if (c->d_dWin) cudaFree(c->d_dWin);
+    if (c->d_dWout) cudaFree(c->d_dWout);
+    CK(c, cudaMalloc(&c->d_dWin, sizeof(double) * ndw));
+    CK(c, cudaMalloc(&c->d_dWout, sizeof(double) * ndw));
+    c->dW_cap = ndw;
+  }
+  double *du = c->d_state, *du1 = du + fld, *ddF = du + 2 * fld, *ddG = du + 3 * fld;
+  int *dfs = c->d_cnt, *dil = dfs + R, *dit = dfs + 2 * R;
+  cudaStream_t st = 0;
+  CK(c, cudaMemcpyAsync(du, u, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpyAsync(du1, u1, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpyAsync(ddF, dF, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
+  if (hasG) CK(c, cudaMemcpyAsync(ddG, dG, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpyAsync(dfs, fail_step, sizeof(int) * R, cudaMemcpyHostToDevice, st));
+  CK(c, cudaMemcpyAsync(dit, its_total, sizeof(int) * R, cudaMemcpyHostToDevice, st));
+  if (dW_in && ndw) CK(c, cudaMemcpyAsync(c->d_dWin, dW_in, sizeof(double) * ndw, cudaMemcpyHostToDevice, st));
+  int rc = pk_step(c, nsteps, du, du1, ddF, hasG ? ddG : nullptr, (dW_in && ndw) ? c->d_dWin : nullptr,
+                   (dW_out && ndw) ? c->d_dWout : nullptr, dfs, dil, dit, (void*)st);
+  if (rc) return rc;
+  CK(c, cudaMemcpyAsync(u, du, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(u1, du1, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(dF, ddF, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
+  if (hasG) CK(c, cudaMemcpyAsync(dG, ddG, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(fail_step, dfs, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(its_last, dil, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaMemcpyAsync(its_total, dit, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
+  if (dW_out && ndw) CK(c, cudaMemcpyAsync(dW_out, c->d_dWout, sizeof(double) * ndw, cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int pk_diagnostics(pk_ctx* c, const double* u, const double* pq, int32_t periodic, int32_t want_m,
+                              double* out, int32_t* idx, double* du_out, const int32_t* fail_step, void* stream) {
+  if (!c) return -1;
+  if (!u || !out || !idx) return fail(c, "pk_diagnostics: null pointer");
+  CK(c, cudaSetDevice(c->cfg.device));
+  DiagArgs a;
+  a.u = u; a.pq = pq; a.out = out; a.idx = idx; a.du_out = du_out; a.fail_step = fail_step;
+  a.ne = c->p.ne; a.periodic = periodic; a.h = c->p.h; a.alphasq = c->p.alphasq; a.Ld = c->cfg.Ld;
+  a.scratch = nullptr;
+  if (want_m) {
+    if (!c->d_scratch) CK(c, cudaMalloc(&c->d_scratch, sizeof(double) * 2 * (size_t)c->cfg.R * c->p.ne));
+    a.scratch = c->d_scratch;
+  }
+  // M = kappa (1 - rho S)(1 - rho S^-1), rho = -(2 - sqrt 3); circulant inverse entries
+  // g_k = (rho^k + rho^(n-k)) / (kappa (1-rho^2)(1-rho^n))
+  const double ma = c->p.ma, mb = c->p.mb;
+  const double kappa = 0.5 * (ma + sqrt(ma * ma - 4.0 * mb * mb));
+  const double rho = -mb / kappa;
+  a.rhoM = rho;
+  const double rn = pow(rho, (double)c->p.ne);
+  if (c->p.ne >= 160) { a.K = 64; a.gscale = 1.0 / (kappa * (1.0 - rho * rho)); }   // |rho|^64 ~ 2e-37
+  else { a.K = -1; a.gscale = 1.0 / (kappa * (1.0 - rho * rho) * (1.0 - rn)); }
+  pk_diag_kernel<<<c->cfg.R, 256, 0, (cudaStream_t)stream>>>(a);
+  CK(c, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pk_ensemble_stats(pk_ctx* c, const double* u, const int32_t* fail_step, const double* diag,
+                                 const int32_t* idx, int32_t nbins, double q_lo, double q_hi, double d_lo,
+                                 double d_hi, double* packed, void* stream) {
+  if (!c) return -1;
+  if (!u || !fail_step || !diag || !idx || !packed || nbins < 1) return fail(c, "pk_ensemble_stats: bad argument");
+  CK(c, cudaSetDevice(c->cfg.device));
+  const int R = c->cfg.R, ne = c->p.ne;
+  const int ntile = R < 32 ? 1 : 32;
+  const int rows = (R + ntile - 1) / ntile;
+  if (!c->d_mom) CK(c, cudaMalloc(&c->d_mom, sizeof(double) * 2 * (size_t)ne * 32));
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g((ne + 127) / 128, ntile);
+  pk_moments_partial<<<g, 128, 0, st>>>(u, fail_step, R, ne, rows, c->d_mom);
+  CK(c, cudaGetLastError());
+  int nb = (2 * ne + 255) / 256; if (nb > 64) nb = 64;
+  pk_moments_final<<<nb, 256, sizeof(int) * (2 * nbins + 1), st>>>(c->d_mom, ntile, ne, fail_step, diag, idx, R, nbins,
+                                                                c->p.h, q_lo, q_hi, d_lo, d_hi, packed);
+  CK(c, cudaGetLastError());
+  return 0;
+}

@@ -7,6 +7,14 @@
 #pragma once
 #include <cmath>
 
+#if defined(__CUDACC__)
+#define PK_HD __host__ __device__ __forceinline__
+#define PK_UNROLL _Pragma("unroll")
+#else
+#define PK_HD inline __attribute__((always_inline))
+#define PK_UNROLL
+#endif
+
 namespace pk {
 
 enum NoiseMode {
@@ -37,8 +45,8 @@ struct Params {
 };
 
 // chunk geometry
-static inline int chunk_rows(const Params& p, int t) { return t < p.rem ? p.M : p.M - 1; }
-static inline int chunk_start(const Params& p, int t) { return t * (p.M - 1) + (t < p.rem ? t : p.rem); }
+PK_HD int chunk_rows(const Params& p, int t) { return t < p.rem ? p.M : p.M - 1; }
+PK_HD int chunk_start(const Params& p, int t) { return t * (p.M - 1) + (t < p.rem ? t : p.rem); }
 
 // Choose (T, M, rem) for a given ne: T = smallest power of two with 8T >= ne, chunks of
 // ceil/floor(ne/T) rows, which is then in [4, 8].  Returns false if ne < 8.

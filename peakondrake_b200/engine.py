@@ -1,0 +1,188 @@
+"""
+EnsembleIntegrator -- the batched replacement of the reference's per-step operator protocol
+
+    Xis.update(t); equations.solve()                       (simulation.py:96-108)
+    diagnostic_equations.solve(); outputting.dump_diagnostics(t, failed)   (simulation.py:118-125)
+
+for R independent realisations on one GPU.  PyTorch is used only to own device memory and the
+CUDA stream; every numerical kernel is in libpeakon_b200.so (include/peakon_b200.h).
+"""
+import ctypes
+import numpy as np
+import torch
+
+from peakondrake_b200 import _lib
+from peakondrake_b200.stochastic_functions import build_tables
+
+CG1_MIDPOINT_SCHEMES = ('hydrodynamic', 'no_gradient')
+
+
+def validate_scheme(scheme, timestepping, alphasq=1.0, gamma=0.0):
+    """The checks of Equations.__init__ (equations.py:26-28,63,97,147-167), same exceptions."""
+    if alphasq > 0.0 and gamma == 0.0:
+        if scheme in CG1_MIDPOINT_SCHEMES and timestepping == 'midpoint':
+            return
+        if (scheme, timestepping) in (('upwind', 'ssprk3'), ('test', 'midpoint')):
+            raise NotImplementedError('Scheme %s with %s exists in the reference but is outside the '
+                                      'B200 hot path built so far (DESIGN.md, "out of scope").'
+                                      % (scheme, timestepping))
+        raise ValueError('Scheme %s and timestepping %s either not compatible or not recognised.'
+                         % (scheme, timestepping))
+    elif alphasq == 0.0 and gamma > 0.0:
+        if scheme in ('upwind', 'hydrodynamic') and timestepping in ('ssprk3', 'midpoint') \
+                and (scheme, timestepping) != ('hydrodynamic', 'ssprk3'):
+            raise NotImplementedError('Scheme %s and timestepping %s not yet implemented.' % (scheme, timestepping))
+        raise ValueError('Scheme %s and timestepping %s either not compatible or not recognised.'
+                         % (scheme, timestepping))
+    raise NotImplementedError('Schemes for your values of alpha squared %.3f and gamma %.3f are not yet implemented.'
+                              % (alphasq, gamma))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class EnsembleIntegrator(object):
+    """
+    R realisations of the stochastic Camassa-Holm equation on PeriodicIntervalMesh(ne, Ld).
+
+    State (device, fp64, [R, ne], natural node order): u and the Newton unknown (u1, dF, dG) the
+    reference carries as warm start (equations.py:71,89).
+    """
+
+    def __init__(self, ne, Ld, dt, R, alphasq=1.0, scheme='hydrodynamic', timestepping='midpoint',
+                 num_Xis=0, Xi_family='sines', sigma=0.0, nXi_updates=1, seed=0, rid_offset=0,
+                 device=None, tables=None, c0=0.0, gamma=0.0):
+        validate_scheme(scheme, timestepping, alphasq, gamma)
+        if not torch.cuda.is_available():
+            raise RuntimeError('peakondrake_b200 needs a CUDA device (B200); there is no CPU fallback.')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self.ne, self.Ld, self.dt, self.R = int(ne), float(Ld), float(dt), int(R)
+        self.alphasq, self.scheme = float(alphasq), scheme
+        self.num_Xis, self.Xi_family, self.sigma = int(num_Xis), Xi_family, float(sigma)
+        self.nXi_updates = int(nXi_updates)
+        if tables is None:
+            tables = build_tables(self.ne, self.Ld, Xi_family, self.num_Xis, self.sigma, scheme)
+        xi, xi_x, xi_xx = [np.ascontiguousarray(t, dtype=np.float64) for t in tables]
+        self.tables_host = (xi, xi_x, xi_xx)
+        spatially_constant = self.num_Xis == 0 or (self.num_Xis == 1 and np.all(xi[0] == xi[0, 0])
+                                                   and not xi_x.any() and not xi_xx.any())
+        if spatially_constant:
+            mode = _lib.PK_NOISE_SCALAR
+        elif not xi_x.any() and not xi_xx.any():
+            mode = _lib.PK_NOISE_X
+        else:
+            mode = _lib.PK_NOISE_FULL
+        self.noise_mode = mode
+        cfg = _lib.PkConfig(ne=self.ne, R=self.R, Ld=self.Ld, dt=self.dt, alphasq=self.alphasq,
+                            noise_mode=mode, num_xis=self.num_Xis, nxi_updates=self.nXi_updates,
+                            device=self.device.index, seed=int(seed), rid_offset=int(rid_offset), max_it=0,
+                            rtol=0.0, atol=0.0, stol=0.0, divtol=0.0,
+                            xi_const=float(xi[0, 0]) if (spatially_constant and self.num_Xis) else 0.0)
+        ctx = ctypes.c_void_p()
+        rc = self.lib.pk_create(ctypes.byref(cfg), ctypes.byref(ctx))
+        if rc != 0:
+            raise _lib.PkError(self.lib.pk_last_error(None).decode())
+        self.ctx = ctx
+        dev = self.device
+        self.xi = torch.from_numpy(xi).to(dev)
+        self.xi_x = torch.from_numpy(xi_x).to(dev)
+        self.xi_xx = torch.from_numpy(xi_xx).to(dev)
+        if self.num_Xis > 0 and mode != _lib.PK_NOISE_SCALAR:
+            _lib.check(self.lib, ctx, self.lib.pk_set_tables(ctx, _ptr(self.xi), _ptr(self.xi_x), _ptr(self.xi_xx)))
+        z = lambda: torch.zeros(self.R, self.ne, dtype=torch.float64, device=dev)
+        self.u, self.u1, self.dF, self.dG = z(), z(), z(), z()
+        self.fail_step = torch.full((self.R,), -1, dtype=torch.int32, device=dev)
+        self.its_last = torch.zeros(self.R, dtype=torch.int32, device=dev)
+        self.its_total = torch.zeros(self.R, dtype=torch.int32, device=dev)
+        self.diag = torch.zeros(self.R, _lib.NDIAG, dtype=torch.float64, device=dev)
+        self.didx = torch.zeros(self.R, _lib.NIDX, dtype=torch.int32, device=dev)
+
+    # -- life cycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, 'ctx', None) is not None:
+            self.lib.pk_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def layout(self):
+        T, M, rem, smem = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32())
+        self.lib.pk_get_layout(self.ctx, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem), ctypes.byref(smem))
+        return dict(threads=T.value, rows_per_thread=M.value, rem=rem.value, smem_bytes=smem.value)
+
+    @property
+    def step_counter(self):
+        return int(self.lib.pk_get_step_counter(self.ctx))
+
+    # -- state --------------------------------------------------------------------------------
+    def set_state(self, u0, w1=None):
+        """u0: [ne] (broadcast over realisations) or [R, ne]; w1 = (u1, dF, dG) or None for the
+        reference's zero start (equations.py:71)."""
+        u0 = torch.as_tensor(np.asarray(u0), dtype=torch.float64)
+        self.u.copy_(u0.to(self.device).expand(self.R, self.ne))
+        if w1 is None:
+            self.u1.zero_(); self.dF.zero_(); self.dG.zero_()
+        else:
+            for dst, src in zip((self.u1, self.dF, self.dG), w1):
+                dst.copy_(torch.as_tensor(np.asarray(src), dtype=torch.float64).to(self.device).expand(self.R, self.ne))
+        self.fail_step.fill_(-1); self.its_last.zero_(); self.its_total.zero_()
+        self.lib.pk_set_step_counter(self.ctx, 0)
+
+    # -- the hot path -------------------------------------------------------------------------
+    def step(self, nsteps, dW=None, export_dW=False):
+        """
+        Advance every realisation `nsteps` steps in ONE kernel launch.
+        dW: None (draw in-kernel with Philox) or array/tensor [nsteps, R, num_Xis] of increments
+        already scaled by sqrt(dt).  Returns the exported increments (device tensor) if asked.
+        """
+        dW_dev = None
+        if dW is not None and self.num_Xis > 0:
+            dW_dev = torch.as_tensor(dW, dtype=torch.float64).to(self.device).contiguous()
+            if tuple(dW_dev.shape) != (nsteps, self.R, self.num_Xis):
+                raise ValueError('dW must have shape (nsteps, R, num_Xis) = %s, got %s'
+                                 % ((nsteps, self.R, self.num_Xis), tuple(dW_dev.shape)))
+        out = None
+        if export_dW and self.num_Xis > 0:
+            out = torch.empty(nsteps, self.R, self.num_Xis, dtype=torch.float64, device=self.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.pk_step(self.ctx, int(nsteps), _ptr(self.u), _ptr(self.u1), _ptr(self.dF), _ptr(self.dG),
+                              _ptr(dW_dev), _ptr(out), _ptr(self.fail_step), _ptr(self.its_last),
+                              _ptr(self.its_total), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        self._keep = (dW_dev, out)      # keep inputs alive until the stream has consumed them
+        return out
+
+    def last_kernel_ms(self):
+        return float(self.lib.pk_last_step_kernel_ms(self.ctx))
+
+    def step_host(self, nsteps, u, u1, dF, dG, dW, fail_step, its_last, its_total, dW_out=None):
+        """pk_step_host on (pinned or pageable) host NumPy arrays, in place. Synchronous."""
+        p = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
+        rc = self.lib.pk_step_host(self.ctx, int(nsteps), p(u), p(u1), p(dF), p(dG), p(dW), p(dW_out),
+                                   p(fail_step), p(its_last), p(its_total))
+        _lib.check(self.lib, self.ctx, rc)
+
+    # -- diagnostics --------------------------------------------------------------------------
+    def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False):
+        """
+        Fused per-realisation reductions. Returns (vals [R, NDIAG] float64, idx [R, NIDX] int32,
+        du [R, ne] or None) as device tensors; columns are _lib.D_* / _lib.I_*.
+        Failed realisations give NaN rows (outputting.py:107-108).
+        """
+        pq_dev = None
+        if pq is not None:
+            pq_dev = torch.as_tensor(pq, dtype=torch.float64).to(self.device).contiguous()
+        du = torch.empty(self.R, self.ne, dtype=torch.float64, device=self.device) if want_du else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.pk_diagnostics(self.ctx, _ptr(self.u), _ptr(pq_dev), int(bool(periodic)), int(bool(want_m)),
+                                     _ptr(self.diag), _ptr(self.didx), _ptr(du), _ptr(self.fail_step), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        self._keep_d = pq_dev
+        return self.diag, self.didx, du

@@ -1,0 +1,243 @@
+"""
+GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libpeakon_b200.so), against
+the NumPy/SciPy oracle on the same inputs and the same Brownian increments.
+
+Tolerance (BASELINE.json north_star): relative L2 error of u per realisation <= 1e-10 in fp64;
+Newton iteration counts and integer indices identical.
+"""
+import numpy as np
+import pytest
+
+from oracle import ch_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def run_case(ne, R, nsteps, ic='proper_peak', fam='sines', nxi=4, sigma=0.2, scheme='hydrodynamic',
+             Ld=40.0, dt=1e-3, peak_width=1.0, chunks=None):
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, draw_dW
+    u0 = build_initial_u(ne, Ld, ic, peak_width=peak_width)
+    u0_or = O.initial_u(O.Mesh1D(ne, Ld), ic, peak_width=peak_width)
+    assert rel(u0, u0_or) < 1e-12
+    eng = EnsembleIntegrator(ne, Ld, dt, R, scheme=scheme, num_Xis=nxi, Xi_family=fam, sigma=sigma)
+    eng.set_state(u0)
+    dW = None
+    if nxi > 0:
+        dW = np.stack([draw_dW(r, nsteps, nxi, dt) for r in range(R)], axis=1)
+    chunks = chunks or [nsteps]
+    assert sum(chunks) == nsteps
+    n0 = 0
+    for c in chunks:           # several launches must equal one launch
+        eng.step(c, dW=None if dW is None else dW[n0:n0 + c])
+        n0 += c
+    torch.cuda.synchronize()
+    tabs = O.noise_tables(O.Mesh1D(ne, Ld), fam, nxi, sigma, scheme=scheme) if nxi else None
+    u, u1, dF, dG = [t.cpu().numpy() for t in (eng.u, eng.u1, eng.dF, eng.dG)]
+    its = eng.its_total.cpu().numpy()
+    fs = eng.fail_step.cpu().numpy()
+    worst = 0.0
+    for r in range(R):
+        ref = O.run(ne, Ld, dt, nsteps, u0, None if dW is None else dW[:, r, :], tabs, scheme=scheme)
+        assert fs[r] == -1 and ref['fail_step'] == -1
+        assert its[r] == ref['its'].sum(), (r, its[r], ref['its'].sum())
+        worst = max(worst, rel(u[r], ref['u']))
+        assert rel(u[r], ref['u']) <= TOL
+        assert rel(u1[r], ref['w1'][:ne]) <= TOL
+        assert rel(dF[r], ref['w1'][ne:2 * ne]) <= 1e-8
+        if np.linalg.norm(ref['w1'][2 * ne:]) > 0:
+            assert rel(dG[r], ref['w1'][2 * ne:]) <= 1e-8
+        else:
+            assert not dG[r].any()
+    eng.close()
+    return worst
+
+
+def test_c1_deterministic_single_peak():
+    # BASELINE config 1 (shortened): CG1 ne=1000 L=40 dt=1e-3, one_peak, sigma=0
+    assert run_case(1000, 2, 20, ic='one_peak', nxi=1, sigma=0.0) <= TOL
+
+
+def test_c2_stochastic_pathwise():
+    # BASELINE config 2 (shortened): 4 sines, sigma=0.2, proper_peak, shared dW per seed
+    assert run_case(1000, 8, 20, chunks=[7, 13]) <= TOL
+
+
+@pytest.mark.parametrize('ne', [8, 20, 37, 200, 1001, 1500, 2000])
+def test_mesh_sizes(ne):
+    assert run_case(ne, 3, 6, nxi=2) <= TOL
+
+
+def test_constant_noise_family():
+    # Xi_family 'constant': dXi_x = dXi_xx = 0 and dG stays identically zero
+    assert run_case(1000, 4, 10, ic='new_peak', fam='constant', nxi=1, sigma=0.2, dt=5e-4, peak_width=1 / 6) <= TOL
+
+
+def test_large_single_cta_mesh_scalar_noise():
+    # ne=4000 fits one CTA only with scalar noise (3 resident fields): T=512, M=8
+    assert run_case(4000, 2, 4, ic='periodic_peakon', fam='constant', nxi=1, sigma=0.5) <= TOL
+
+
+def test_unsupported_mesh_raises_cleanly():
+    from peakondrake_b200 import EnsembleIntegrator, _lib
+    with pytest.raises(_lib.PkError):
+        EnsembleIntegrator(16384, 40.0, 1e-3, 2, num_Xis=4, sigma=0.1)     # needs the cluster path
+    with pytest.raises(ValueError):
+        EnsembleIntegrator(100, 40.0, 1e-3, 2, scheme='conforming')         # equations.py:147-148
+    with pytest.raises(NotImplementedError):
+        EnsembleIntegrator(100, 40.0, 1e-3, 2, alphasq=0.0, gamma=1.0)      # equations.py:160-161
+
+
+def test_no_gradient_scheme():
+    assert run_case(400, 3, 8, scheme='no_gradient', nxi=3) <= TOL
+
+
+def test_no_noise_modes():
+    assert run_case(300, 2, 8, nxi=0) <= TOL
+
+
+def test_periodic_peakon_large_sigma():
+    assert run_case(2000, 3, 6, ic='periodic_peakon', fam='constant', nxi=1, sigma=1.0, dt=1e-3) <= TOL
+
+
+def test_philox_export_roundtrip_and_sharding():
+    """In-kernel Philox increments: exported dW fed to the oracle reproduces the path, and the
+    numbers depend only on the global realisation id (sharding-invariant)."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    ne, Ld, dt, R, nsteps, nxi, sigma = 200, 40.0, 1e-3, 6, 8, 3, 0.3
+    u0 = build_initial_u(ne, Ld, 'proper_peak')
+    eng = EnsembleIntegrator(ne, Ld, dt, R, num_Xis=nxi, sigma=sigma, seed=1234)
+    eng.set_state(u0)
+    dW = eng.step(nsteps, export_dW=True).cpu().numpy()
+    u = eng.u.cpu().numpy()
+    assert abs(dW.std() / np.sqrt(dt) - 1.0) < 0.25 and abs(dW.mean()) < 0.02
+    tabs = O.noise_tables(O.Mesh1D(ne, Ld), 'sines', nxi, sigma)
+    for r in range(R):
+        ref = O.run(ne, Ld, dt, nsteps, u0, dW[:, r, :], tabs)
+        assert rel(u[r], ref['u']) <= TOL
+    # second shard holding realisations 3..5 only
+    eng2 = EnsembleIntegrator(ne, Ld, dt, 3, num_Xis=nxi, sigma=sigma, seed=1234, rid_offset=3)
+    eng2.set_state(u0)
+    dW2 = eng2.step(nsteps, export_dW=True).cpu().numpy()
+    assert np.array_equal(dW2, dW[:, 3:, :])
+    assert np.array_equal(eng2.u.cpu().numpy(), u[3:])
+    # nXi_updates: sum of sub-draws has the right variance
+    eng3 = EnsembleIntegrator(ne, Ld, dt, 64, num_Xis=1, Xi_family='constant', sigma=0.1, seed=7, nXi_updates=16)
+    eng3.set_state(u0)
+    d3 = eng3.step(16, export_dW=True).cpu().numpy()
+    assert abs(d3.std() / np.sqrt(dt) - 1.0) < 0.15
+    torch.cuda.synchronize()
+
+
+def test_host_buffer_entry_point_equals_device_path():
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, draw_dW
+    ne, Ld, dt, R, nsteps, nxi = 200, 40.0, 1e-3, 5, 6, 2
+    u0 = build_initial_u(ne, Ld, 'one_peak')
+    dW = np.stack([draw_dW(r, nsteps, nxi, dt) for r in range(R)], axis=1)
+    eng = EnsembleIntegrator(ne, Ld, dt, R, num_Xis=nxi, sigma=0.2)
+    eng.set_state(u0)
+    eng.step(nsteps, dW=dW)
+    u_dev = eng.u.cpu().numpy()
+    its_dev = eng.its_total.cpu().numpy().copy()
+    eng.set_state(u0)
+    u = np.tile(u0, (R, 1)); u1 = np.zeros_like(u); dF = np.zeros_like(u); dG = np.zeros_like(u)
+    fs = np.full(R, -1, np.int32); il = np.zeros(R, np.int32); it = np.zeros(R, np.int32)
+    eng.step_host(nsteps, u, u1, dF, dG, np.ascontiguousarray(dW), fs, il, it)
+    assert np.array_equal(u, u_dev)
+    assert (fs == -1).all() and (it == its_dev).all()
+
+
+def test_failure_latch():
+    """A step SNES cannot solve latches the realisation (simulation.py:99-106): u frozen at the last
+    accepted value, fail_step recorded, diagnostics NaN (outputting.py:107-108); healthy
+    realisations of the same batch are unaffected."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, _lib
+    ne, Ld, dt, R, nsteps = 200, 40.0, 1e-3, 3, 4
+    u0 = build_initial_u(ne, Ld, 'proper_peak')
+    eng = EnsembleIntegrator(ne, Ld, dt, R, num_Xis=1, Xi_family='sines', sigma=1.0)
+    eng.set_state(u0)
+    dW = np.zeros((nsteps, R, 1))
+    dW[:, 0, 0] = 0.01
+    dW[:, 2, 0] = 0.01
+    dW[2, 1, 0] = np.nan          # realisation 1 receives a non-finite increment at step 2
+    eng.step(nsteps, dW=dW)
+    vals, idx, _ = eng.diagnostics()
+    torch.cuda.synchronize()
+    fs = eng.fail_step.cpu().numpy()
+    assert list(fs) == [-1, 2, -1]
+    tabs = O.noise_tables(O.Mesh1D(ne, Ld), 'sines', 1, 1.0)
+    ref1 = O.run(ne, Ld, dt, 2, u0, dW[:2, 1, :], tabs)     # state after the two good steps
+    assert rel(eng.u[1].cpu().numpy(), ref1['u']) <= TOL
+    ref0 = O.run(ne, Ld, dt, nsteps, u0, dW[:, 0, :], tabs)
+    assert rel(eng.u[0].cpu().numpy(), ref0['u']) <= TOL
+    v = vals.cpu().numpy()
+    assert np.isnan(v[1]).all() and np.isfinite(v[0, _lib.D_ENERGY]) and np.isfinite(v[2, _lib.D_ENERGY])
+
+
+def test_diagnostics_against_oracle():
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, draw_dW, _lib
+    ne, Ld, dt, R, nsteps, nxi = 500, 40.0, 1e-3, 4, 10, 4
+    u0 = build_initial_u(ne, Ld, 'proper_peak')
+    dW = np.stack([draw_dW(r, nsteps, nxi, dt) for r in range(R)], axis=1)
+    eng = EnsembleIntegrator(ne, Ld, dt, R, num_Xis=nxi, sigma=0.2)
+    eng.set_state(u0)
+    eng.step(nsteps, dW=dW)
+    pq = np.array([[1.0, 10.0 + 0.1 * r] for r in range(R)])
+    vals, idx, du = eng.diagnostics(pq=pq, periodic=True, want_m=True, want_du=True)
+    torch.cuda.synchronize()
+    vals, idx, du, u = vals.cpu().numpy(), idx.cpu().numpy(), du.cpu().numpy(), eng.u.cpu().numpy()
+    orc = O.CHOracle(ne, Ld, dt)
+    mesh = orc.mesh
+    names = ['energy', 'l2_u', 'h1_u', 'mass_u', 'max_du', 'min_du', 'max_jump_local', 'p_pde', 'l2_m',
+             'h1_m', 'mass_m', 'm_max', 'E_2', 'u_error_with_sde']
+    for r in range(R):
+        m = O.m_field(orc, u[r])
+        usde = O.u_sde_field(mesh, pq[r, 0], pq[r, 1], 1.0, True)
+        d = O.scalar_diagnostics(orc, u[r], names, m=m, u_sde=usde)
+        v = vals[r]
+        close = lambda a, b: abs(a - b) <= 1e-11 * max(1.0, abs(b))
+        assert close(v[_lib.D_ENERGY], d['energy'])
+        assert close(np.sqrt(v[_lib.D_L2U2]), d['l2_u'])
+        assert close(np.sqrt(v[_lib.D_L2U2] + v[_lib.D_H1SEMI2]), d['h1_u'])
+        assert close(v[_lib.D_MASS_U], d['mass_u'])
+        assert v[_lib.D_MAX_U] == u[r].max()
+        assert close(np.sqrt(v[_lib.D_L2M2]), d['l2_m'])
+        assert close(np.sqrt(v[_lib.D_L2M2] + v[_lib.D_H1SEMI_M2]), d['h1_m'])
+        assert close(v[_lib.D_MASS_M], d['mass_m'])
+        assert close(v[_lib.D_M_MAX], d['m_max'])
+        assert close(0.5 * v[_lib.D_UMU], d['E_2'])
+        assert close(np.sqrt(v[_lib.D_ERR_SDE2]), d['u_error_with_sde'])
+        # du on the device is (u[i+1]-u[i])*(1/h); indices are exact argmax/argmin of that field
+        assert np.allclose(du[r], O.du_field(mesh, u[r]), rtol=1e-14, atol=0)
+        assert v[_lib.D_MAX_DU] == du[r].max() and v[_lib.D_MIN_DU] == du[r].min()
+        assert idx[r, _lib.I_ARGMAX_DU] == np.argmax(du[r])
+        assert idx[r, _lib.I_ARGMIN_DU] == np.argmin(du[r])
+        assert idx[r, _lib.I_ARGMAX_U] == np.argmax(u[r])
+        jmp = np.abs(du[r] - np.roll(du[r], 1))
+        assert v[_lib.D_MAX_JUMP_LOCAL] == jmp.max() and idx[r, _lib.I_ARGMAX_JUMP] == np.argmax(jmp)
+
+
+def test_argmax_ties_take_lowest_index():
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, _lib
+    ne = 64
+    eng = EnsembleIntegrator(ne, 40.0, 1e-3, 2)
+    u = np.zeros((2, ne))
+    u[0, [5, 40, 41]] = 1.0          # three equal maxima
+    u[1, [63, 0]] = 2.0              # maxima at both ends of the array
+    eng.u.copy_(torch.from_numpy(u))
+    vals, idx, du = eng.diagnostics(want_du=True)
+    torch.cuda.synchronize()
+    idx = idx.cpu().numpy(); du = du.cpu().numpy()
+    assert idx[0, _lib.I_ARGMAX_U] == 5 and idx[1, _lib.I_ARGMAX_U] == 0
+    for r in range(2):
+        assert idx[r, _lib.I_ARGMAX_DU] == np.argmax(du[r]) and idx[r, _lib.I_ARGMIN_DU] == np.argmin(du[r])
