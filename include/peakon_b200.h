@@ -133,6 +133,15 @@ int64_t pk_get_step_counter(const pk_ctx* ctx);
 int pk_diagnostics(pk_ctx* ctx, const double* u, const double* pq, int32_t periodic, int32_t want_m,
                    double* out, int32_t* idx, double* du_out, const int32_t* fail_step, void* stream);
 
+/* Replaces the two sequential scans of peakon_diagnostics (outputting.py:401-435) for every
+ * realisation: idx = output of pk_diagnostics for the same u.
+ *   vals [R,2] = (peakon_min_du, peakon_max_du), NaN when the scan finds nothing within ne/2 cells
+ *   ids  [R,3] = (argmax u, min_du_idx, max_du_idx): array positions as the reference's (possibly
+ *               negative, Python-wrapped) indices resolve; -1 = not found.  The host turns them into
+ *               peakon_loc / *_loc / mu / nu with its own coordinate array (bit-exact look-ups). */
+int pk_peakon_suite(pk_ctx* ctx, const double* u, const int32_t* idx, const int32_t* fail_step,
+                    double* vals, int32_t* ids, void* stream);
+
 /* Ensemble statistics for one dump (the quantities the reference accumulates across seeds off-line:
  * running mean of u, experiment.py:224-227; histograms plotted by plotting/plot_stochastic_histograms.py:61-67).
  *   diag/idx: outputs of pk_diagnostics for the same state

@@ -19,7 +19,7 @@ I_ARGMAX_DU, I_ARGMIN_DU, I_ARGMAX_U, I_ARGMAX_JUMP, NIDX = range(5)
 
 EXPORTS = ['pk_create', 'pk_destroy', 'pk_last_error', 'pk_set_tables', 'pk_step', 'pk_step_host',
            'pk_set_step_counter', 'pk_get_step_counter', 'pk_diagnostics', 'pk_get_layout',
-           'pk_last_step_kernel_ms', 'pk_ensemble_stats']
+           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite']
 
 
 class PkConfig(ctypes.Structure):
@@ -70,6 +70,8 @@ def load():
     lib.pk_last_step_kernel_ms.argtypes = [vp]
     lib.pk_ensemble_stats.restype = ctypes.c_int
     lib.pk_ensemble_stats.argtypes = [vp, dp, ip, dp, ip, ctypes.c_int32] + [ctypes.c_double] * 4 + [dp, vp]
+    lib.pk_peakon_suite.restype = ctypes.c_int
+    lib.pk_peakon_suite.argtypes = [vp, dp, ip, ip, dp, ip, vp]
     _lib = lib
     return lib
 

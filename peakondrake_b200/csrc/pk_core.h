@@ -25,6 +25,12 @@
 #pragma once
 #include "pk_params.h"
 
+#if defined(__CUDA_ARCH__)
+#define PK_RCP(x) __drcp_rn(x)     // IEEE round-to-nearest reciprocal == 1.0/x
+#else
+#define PK_RCP(x) (1.0 / (x))
+#endif
+
 namespace pk {
 
 // Shared (per-realisation) storage. Field arrays are [M*T] doubles, interleaved: row j of chunk t
@@ -43,6 +49,16 @@ PK_HD int row_slot(const Params& p, int i) {
   int t, j;
   if (i < big) { t = i / p.M; j = i - t * p.M; }
   else { const int k = i - big; const int q = k / (p.M - 1); t = p.rem + q; j = k - q * (p.M - 1); }
+  return j * p.T + t;
+}
+
+// same with a compile-time M (constant divisions)
+template <int M>
+PK_HD int row_slot_c(const Params& p, int i) {
+  const int big = p.rem * M;
+  int t, j;
+  if (i < big) { t = i / M; j = i - t * M; }
+  else { const int k = i - big; const int q = k / (M - 1); t = p.rem + q; j = k - q * (M - 1); }
   return j * p.T + t;
 }
 
@@ -92,7 +108,7 @@ struct Packet { double Cm[3], C0[3], Cp[3], Qm, Q0, Qp; };
 
 PK_HD void inv2(const double* D, double* Di) {
   const double det = D[0] * D[3] - D[1] * D[2];
-  const double id = 1.0 / det;
+  const double id = PK_RCP(det);
   Di[0] = D[3] * id; Di[1] = -D[1] * id; Di[2] = -D[2] * id; Di[3] = D[0] * id;
 }
 // C = A*B (2x2 row-major)
@@ -209,7 +225,7 @@ struct Thread {
       w1 = -l2 * zw1[k - 2] - l1 * zw1[k - 1];
       w2 = -l2 * zw2[k - 2] - l1 * zw2[k - 1];
     }
-    r[k] = 1.0 / d; e[k] = ee; f[k] = ff; zb[k] = z; zw1[k] = w1; zw2[k] = w2;
+    r[k] = PK_RCP(d); e[k] = ee; f[k] = ff; zb[k] = z; zw1[k] = w1; zw2[k] = w2;
   }
 
   // Row (n-1) is complete once packet n is known: separator rows are stored, interior rows eliminated.
@@ -256,6 +272,29 @@ struct Thread {
     }
     push_packet(k);
     nm = n0; n0 = np; pc = cc;
+  }
+
+  // ---- residual norm only (no Jacobian, no elimination): used when convergence is expected -----
+  PK_HD void residual_only(const Params& p, const Shared& sh) {
+    fn2 = 0.0;
+    NodeS a_, b_, c_;
+    load_node(p, sh, -1, a_);
+    load_node(p, sh, 0, b_);
+    CellC<MODE> c0; c0.compute(p, a_, b_);
+    PK_UNROLL
+    for (int q = 1; q <= M; ++q) {
+      if (q <= m) {
+        load_node(p, sh, q, c_);
+        CellC<MODE> c1; c1.compute(p, b_, c_);
+        const double Rpsi = p.mb * (a_.w + c_.w) + p.ma * b_.w + (c0.N1R + c1.N1L) - 0.5 * (a_.F - c_.F)
+                            + ((MODE == NOISE_FULL) ? (p.mb * (a_.G + c_.G) + p.ma * b_.G) : 0.0);
+        const double Rphi = p.hb * (a_.F + c_.F) + p.ha * b_.F - (c0.fR + c1.fL);
+        double Rzeta = 0.0;
+        if (MODE == NOISE_FULL) Rzeta = p.hb * (a_.G + c_.G) + p.ha * b_.G - (c0.gR + c1.gL);
+        fn2 += Rpsi * Rpsi + Rphi * Rphi + Rzeta * Rzeta;
+        a_ = b_; b_ = c_; c0 = c1;
+      }
+    }
   }
 
   // ---- phase A1: first two cells, publish first-node packet --------------------------------
@@ -515,29 +554,30 @@ struct Thread {
       if (j < m) { const int i = idx(p, j); sh.U0[i] = sh.U1[i]; }
   }
 
-  // ---- noise fields of this step: dXi = sum_k dW_k xi_k (stochastic_functions.py:229-234) -------
-  PK_HD void fill_noise(const Params& p, const Shared& sh, const double* xi, const double* xi_x, const double* xi_xx) {
-    if (MODE == NOISE_SCALAR) {
-      Xs = (p.nxi > 0) ? sh.dW[0] * p.xi_const : 0.0;
-      return;
-    }
-    PK_UNROLL
-    for (int j = 0; j < M; ++j) {
-      if (j < m) {
-        const int g = s + j;
-        double X = 0.0, Xx = 0.0, Xxx = 0.0;
-        for (int k = 0; k < p.nxi; ++k) {
-          const double w = sh.dW[k];
-          X += w * xi[k * p.ne + g];
-          if (MODE == NOISE_FULL) { Xx += w * xi_x[k * p.ne + g]; Xxx += w * xi_xx[k * p.ne + g]; }
-        }
-        const int i = idx(p, j);
-        sh.X[i] = X;
-        if (MODE == NOISE_FULL) { sh.Xx[i] = Xx; sh.Xxx[i] = Xxx; }
-      }
-    }
+  // ---- NOISE_SCALAR: the dXi value of this step ------------------------------------------------
+  PK_HD void set_scalar_noise(const Params& p, const Shared& sh) {
+    Xs = (p.nxi > 0) ? sh.dW[0] * p.xi_const : 0.0;
   }
 };
+
+// Noise fields of this step: dXi = sum_k dW_k xi_k etc. (stochastic_functions.py:229-234).
+// Block-wide loop in natural node order: coalesced table reads, scattered into the chunk layout.
+template <int M, int MODE>
+PK_HD void fill_noise_rows(const Params& p, const Shared& sh, const double* xi, const double* xi_x,
+                           const double* xi_xx, int tid, int nth) {
+  if (MODE == NOISE_SCALAR) return;
+  for (int g = tid; g < p.ne; g += nth) {
+    double X = 0.0, Xx = 0.0, Xxx = 0.0;
+    for (int k = 0; k < p.nxi; ++k) {
+      const double w = sh.dW[k];
+      X += w * xi[k * p.ne + g];
+      if (MODE == NOISE_FULL) { Xx += w * xi_x[k * p.ne + g]; Xxx += w * xi_xx[k * p.ne + g]; }
+    }
+    const int i = row_slot_c<M>(p, g);
+    sh.X[i] = X;
+    if (MODE == NOISE_FULL) { sh.Xx[i] = Xx; sh.Xxx[i] = Xxx; }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator + Box-Muller. Counter =
@@ -577,6 +617,7 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 //                      that get() returns, in thread order 0..T-1; put() receives the value entering
 //                      its thread and returns the maps of the following reverse scan
 //   scan_rev(fin)      the reverse cyclic scan (order T-1..0); fin() receives the entering value
+//   each_tid(f)        run f(tid, nthreads) on every thread of the block (also the idle ones)
 //   one(f)             run f() once (thread 0)
 // ------------------------------------------------------------------------------------------------
 struct StepIO {
@@ -595,10 +636,28 @@ struct StepIO {
   int* fail_reason;       // [R] out: 0 ok, 1 max_it, 2 nan, 3 dtol
 };
 
-template <class Exec, class Th>
+// SNES convergence test (SNESConvergedDefault + divergence tolerance).
+// returns 0 = keep iterating, 1 = converged, 2 = diverged (reason set)
+PK_HD int snes_test(const Params& p, int it, const double* nrm, double& fnorm0, int& reason) {
+  const double fnorm = sqrt(nrm[0]);
+  if (!(fnorm == fnorm) || fnorm > 1.7e308) { reason = 2; return 2; }
+  if (it == 0) {
+    fnorm0 = fnorm;
+    if (fnorm < p.atol) return 1;
+  } else {
+    if (fnorm < p.atol || fnorm <= p.rtol * fnorm0) return 1;
+    if (sqrt(nrm[1]) < p.stol * sqrt(nrm[2])) return 1;
+    if (fnorm > p.divtol * fnorm0) { reason = 3; return 2; }
+  }
+  if (it >= p.max_it) { reason = 1; return 2; }
+  return 0;
+}
+
+template <int M, int MODE, class Exec, class Th>
 PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& io) {
   int failed = io.fail_step[io.r];
   int its_last = 0, its_total = io.its_total[io.r], reason = 0;
+  int expect = 2;     // iteration at which convergence is expected: there only the residual is evaluated first
   for (int n = 0; n < io.nsteps; ++n) {
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
     ex.each([&](Th& th) {
@@ -616,32 +675,30 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
         if (io.dW_out) io.dW_out[o] = w;
       }
     });
-    if (failed >= 0) { ex.sync(); continue; }
     ex.sync();
-    ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
+    if (failed >= 0) continue;
+    if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
+    else ex.each_tid([&](int tid, int nth) { fill_noise_rows<M, MODE>(p, sh, io.xi, io.xi_x, io.xi_xx, tid, nth); });
     ex.sync();
 
     // ---- SNES newtonls, basic line search ----
-    int it = 0;
-    double fnorm0 = 0.0;
-    bool converged = false, fail = false;
+    int it = 0, status = 0;
+    double fnorm0 = 0.0, nrm[3];
     while (true) {
+      if (it > 0 && it >= expect) {
+        // convergence is expected here: evaluate the residual only; fall through to the full
+        // assembly (which recomputes it) in the rare case it is not
+        ex.each([&](Th& th) { th.residual_only(p, sh); });
+        ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
+        status = snes_test(p, it, nrm, fnorm0, reason);
+        if (status) break;
+      }
       ex.each([&](Th& th) { th.assemble_begin(p, sh); });
       ex.sync();
       ex.each([&](Th& th) { th.assemble_finish(p, sh); });
-      double nrm[3];
-      ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);  // includes barriers
-      const double fnorm = sqrt(nrm[0]);
-      if (!(fnorm == fnorm) || fnorm > 1.7e308) { fail = true; reason = 2; break; }
-      if (it == 0) {
-        fnorm0 = fnorm;
-        if (fnorm < p.atol) { converged = true; break; }
-      } else {
-        if (fnorm < p.atol || fnorm <= p.rtol * fnorm0) { converged = true; break; }
-        if (sqrt(nrm[1]) < p.stol * sqrt(nrm[2])) { converged = true; break; }
-        if (fnorm > p.divtol * fnorm0) { fail = true; reason = 3; break; }
-      }
-      if (it >= p.max_it) { fail = true; reason = 1; break; }
+      ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
+      status = snes_test(p, it, nrm, fnorm0, reason);
+      if (status) break;
       // ---- linear solve + update ----
       ex.each([&](Th& th) { th.reduce_build(p, sh); });
       ex.sync();
@@ -667,9 +724,10 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
       ++it;
     }
     its_last = it; its_total += it;
-    if (converged) {
+    if (status == 1) {
       ex.each([&](Th& th) { th.accept(p, sh); });
-    } else if (fail) {
+      expect = it > 1 ? it : 1;
+    } else {
       failed = io.step0 + n;
     }
     ex.sync();

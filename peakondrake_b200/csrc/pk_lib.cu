@@ -8,6 +8,7 @@
 // shared memory (pk_core.h holds the thread-level phases, shared with the CPU emulation harness).
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdarg>
 #include <string>
@@ -24,13 +25,22 @@ template <int M, int MODE>
 struct GpuExec {
   typedef Thread<M, MODE> Th;
   Th& th;
-  double* red;        // [3*32] reduction / scan scratch in shared memory
+  double* red;          // [2][3*nw] reduction / scan scratch in shared memory, used alternately (ping-pong)
+  int flip;             // so that a collective needs one barrier only: the area written by collective k
+                        // is next written by collective k+2, i.e. after the barrier of collective k+1
   double rA, rc0, rc1;  // maps of the pending reverse scan
-  __device__ __forceinline__ GpuExec(Th& t, double* scratch) : th(t), red(scratch) {}
+  __device__ __forceinline__ GpuExec(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
 
   template <class F> __device__ __forceinline__ void each(F f) { if (th.active) f(th); }
+  template <class F> __device__ __forceinline__ void each_tid(F f) { f((int)threadIdx.x, (int)blockDim.x); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
+  __device__ __forceinline__ double* area() {
+    const int nw = blockDim.x >> 5;
+    double* a = red + flip * 3 * nw;
+    flip ^= 1;
+    return a;
+  }
 
   template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
     double v[3] = {0.0, 0.0, 0.0};
@@ -42,12 +52,12 @@ struct GpuExec {
       v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (lane == 0) { red[w] = v[0]; red[32 + w] = v[1]; red[64 + w] = v[2]; }
+    double* sc = area();
+    if (lane == 0) { sc[w] = v[0]; sc[nw + w] = v[1]; sc[2 * nw + w] = v[2]; }
     __syncthreads();
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < nw; ++i) { s0 += red[i]; s1 += red[32 + i]; s2 += red[64 + i]; }
+    for (int i = 0; i < nw; ++i) { s0 += sc[i]; s1 += sc[nw + i]; s2 += sc[2 * nw + i]; }
     out[0] = s0; out[1] = s1; out[2] = s2;
-    __syncthreads();
   }
 
   // Cyclic exclusive scan of affine maps over the block. DIR=+1: thread order 0..T-1, value
@@ -68,17 +78,18 @@ struct GpuExec {
       if (ok) { c0 = A * c0o + c0; c1 = A * c1o + c1; A = A * Ao; }
     }
     const int last = (DIR > 0) ? 31 : 0;
-    if (lane == last) { red[w] = A; red[32 + w] = c0; red[64 + w] = c1; }
+    double* sc = area();
+    if (lane == last) { sc[w] = A; sc[nw + w] = c0; sc[2 * nw + w] = c1; }
     __syncthreads();
     // compose the warp aggregates in scan order; remember the prefix in front of my warp
     double tA = 1.0, t0 = 0.0, t1 = 0.0, eA = 1.0, e0 = 0.0, e1 = 0.0;
     for (int k = 0; k < nw; ++k) {
       const int ww = (DIR > 0) ? k : nw - 1 - k;
       if (ww == w) { eA = tA; e0 = t0; e1 = t1; }
-      const double a = red[ww];
-      t0 = a * t0 + red[32 + ww]; t1 = a * t1 + red[64 + ww]; tA = a * tA;
+      const double a = sc[ww];
+      t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
     }
-    const double inv = 1.0 / (1.0 - tA);
+    const double inv = PK_RCP(1.0 - tA);
     const double x0 = t0 * inv, x1 = t1 * inv;          // value entering the first thread (cyclic closure)
     const double w0 = eA * x0 + e0, w1 = eA * x1 + e1;  // value entering my warp
     const double o0 = A * w0 + c0, o1 = A * w1 + c1;    // value leaving my thread
@@ -87,7 +98,6 @@ struct GpuExec {
     else { p0 = __shfl_down_sync(0xffffffffu, o0, 1); p1 = __shfl_down_sync(0xffffffffu, o1, 1); }
     const bool first = (DIR > 0) ? (lane == 0) : (lane == 31);
     in0 = first ? w0 : p0; in1 = first ? w1 : p1;
-    __syncthreads();
   }
 
   template <class G, class P> __device__ __forceinline__ void scan_fwd(G get, P put) {
@@ -128,14 +138,14 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
   sh.xb = nxt; nxt += XB_SLOTS * p.T;
-  double* red = nxt; nxt += 96;
+  double* red = nxt; nxt += 6 * (blockDim.x >> 5);
   sh.dW = nxt;
 
   const int r = blockIdx.x;
   const long long off = (long long)r * p.ne;
   // coalesced global reads, scattered into the chunk-interleaved shared layout
   for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
-    const int sl = row_slot(p, i);
+    const int sl = row_slot_c<M>(p, i);
     sh.U0[sl] = a.u[off + i]; sh.U1[sl] = a.u1[off + i]; sh.F[sl] = a.dF[off + i];
     if (MODE == NOISE_FULL) sh.G[sl] = a.dG[off + i];
   }
@@ -148,11 +158,11 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
   io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
-  run_steps<GpuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  run_steps<M, MODE, GpuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
   __syncthreads();
 
   for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
-    const int sl = row_slot(p, i);
+    const int sl = row_slot_c<M>(p, i);
     a.u[off + i] = sh.U0[sl]; a.u1[off + i] = sh.U1[sl]; a.dF[off + i] = sh.F[sl];
     if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[sl];
   }
@@ -245,8 +255,8 @@ __global__ void __launch_bounds__(256) pk_diag_kernel(const __grid_constant__ Di
   for (int i = threadIdx.x; i < ne; i += blockDim.x) {
     const int im = (i == 0) ? ne - 1 : i - 1, ip = (i == ne - 1) ? 0 : i + 1;
     const double um = u[im], u0 = u[i], up = u[ip];
-    const double du = (up - u0) * ih;          // DG0 cell i          (diagnostic_equations.py:94-101)
-    const double dum = (u0 - um) * ih;         // DG0 cell i-1
+    const double du = (up - u0) / h;           // DG0 cell i          (diagnostic_equations.py:94-101)
+    const double dum = (u0 - um) / h;          // DG0 cell i-1
     const double jmp = fabs(du - dum);         // |jump(du)| at vertex i (:103-113)
     sM += (h * (1.0 / 3.0)) * (u0 * u0 + u0 * up + up * up);   // cell integral of u^2
     sK += (up - u0) * (up - u0) * ih;                          // cell integral of u_x^2
@@ -316,6 +326,56 @@ __global__ void __launch_bounds__(256) pk_diag_kernel(const __grid_constant__ Di
   }
 }
 
+
+
+// ------------------------------------------------------------------------------------------------
+// peakon suite (outputting.py:373-450): the two sequential scans around the highest peak as
+// block-parallel "first index satisfying" searches. One CTA per realisation.
+//   right scan: first k in [0,S): D=(pc+k) mod n with du[D] > du[D-1]  -> min_du = du[D-1], index D-1
+//   left  scan: first k in [0,S): D=(pc-1-k) mod n with du[D] < du[D+1] -> max_du = du[D+1], index D-1
+// (the "D-1" of the left scan is the reference's own indexing, :430, reproduced)
+// outputs per realisation: vals[2] = (min_du, max_du) (NaN if not found), ids[3] = (argmax u,
+// min_du_idx, max_du_idx) as the NON-NEGATIVE array positions Python's negative indexing resolves to
+// (-1 if not found).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pk_peakon_suite_kernel(const double* __restrict__ uall, const int* __restrict__ didx,
+                                                              const int* __restrict__ fail_step, int ne, double h,
+                                                              double* __restrict__ vals, int* __restrict__ ids) {
+  __shared__ int found[2];
+  const int r = blockIdx.x;
+  const double* u = uall + (long long)r * ne;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  if (fail_step && fail_step[r] >= 0) {
+    if (threadIdx.x == 0) { vals[2 * r] = qnan; vals[2 * r + 1] = qnan; ids[3 * r] = -1; ids[3 * r + 1] = -1; ids[3 * r + 2] = -1; }
+    return;
+  }
+  const int pc = didx[r * PK_NIDX + PK_I_ARGMAX_U];
+  const int S = ne / 2;
+  auto du = [&](int i) { i %= ne; if (i < 0) i += ne; const int ip = (i + 1 == ne) ? 0 : i + 1; return (u[ip] - u[i]) / h; };
+  if (threadIdx.x == 0) { found[0] = 0x7fffffff; found[1] = 0x7fffffff; }
+  __syncthreads();
+  for (int base = 0; base < S; base += blockDim.x) {
+    const int k = base + threadIdx.x;
+    if (k < S) {
+      if (found[0] == 0x7fffffff) { const int D = pc + k; if (du(D) > du(D - 1)) atomicMin(&found[0], k); }
+      if (found[1] == 0x7fffffff) { const int D = pc - 1 - k; if (du(D) < du(D + 1)) atomicMin(&found[1], k); }
+    }
+    __syncthreads();
+    if (found[0] != 0x7fffffff && found[1] != 0x7fffffff) break;
+  }
+  if (threadIdx.x == 0) {
+    ids[3 * r] = pc;
+    if (found[0] != 0x7fffffff) {
+      int D = (pc + found[0]) % ne; int j = D - 1; if (j < 0) j += ne;
+      vals[2 * r] = du(j); ids[3 * r + 1] = j;
+    } else { vals[2 * r] = qnan; ids[3 * r + 1] = -1; }
+    if (found[1] != 0x7fffffff) {
+      int D = (pc - 1 - found[1]) % ne; if (D < 0) D += ne;
+      int j = D - 1; if (j < 0) j += ne;
+      vals[2 * r + 1] = du(D + 1); ids[3 * r + 2] = j;
+    } else { vals[2 * r + 1] = qnan; ids[3 * r + 2] = -1; }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // ensemble statistics: per-x moments of u over the healthy realisations + histograms of two scalar
@@ -406,8 +466,13 @@ static int fail(pk_ctx* c, const char* fmt, ...) {
 
 typedef void (*kern_t)(const Params, const StepArgs);
 
+static int g_minb = 0;   // PK_MINB env: resident CTAs/SM the 128-thread kernel is compiled for (2, 3 or 4)
 template <int M, int MODE> static kern_t pick_tb(int block) {
-  if (block <= 128) return pk_step_kernel<M, MODE, 128, 2>;
+  if (block <= 128) {
+    if (g_minb == 3) return pk_step_kernel<M, MODE, 128, 3>;
+    if (g_minb == 4) return pk_step_kernel<M, MODE, 128, 4>;
+    return pk_step_kernel<M, MODE, 128, 2>;
+  }
   if (block <= 256) return pk_step_kernel<M, MODE, 256, 1>;
   return pk_step_kernel<M, MODE, 512, 1>;
 }
@@ -440,6 +505,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (cfg->num_xis < 0) return fail(nullptr, "pk_create: num_xis < 0");
   if (cfg->noise_mode == PK_NOISE_SCALAR && cfg->num_xis > 1)
     return fail(nullptr, "pk_create: scalar noise supports one Xi only (reference stochastic_functions.py:111-112)");
+  { const char* e = getenv("PK_MINB"); g_minb = e ? atoi(e) : 0; }
   pk_ctx* c = new pk_ctx();
   c->cfg = *cfg;
   Params& p = c->p;
@@ -453,8 +519,8 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (!choose_layout(p.ne, &p.T, &p.M, &p.rem)) { delete c; return fail(nullptr, "pk_create: no thread layout for ne=%d", cfg->ne); }
   fill_constants(p);
   const int narr = p.mode == NOISE_FULL ? 7 : (p.mode == NOISE_X ? 4 : 3);
-  c->smem = sizeof(double) * ((size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 96 + (p.nxi > 0 ? p.nxi : 1));
   c->block = p.T < 32 ? 32 : p.T;
+  c->smem = sizeof(double) * ((size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1));
   if (c->block > 512 || c->smem > 227 * 1024) {
     const int ne = p.ne; delete c;
     return fail(nullptr, "pk_create: ne=%d needs a thread-block cluster per realisation (state does not fit one SM); not built yet", ne);
@@ -625,6 +691,16 @@ extern "C" int pk_ensemble_stats(pk_ctx* c, const double* u, const int32_t* fail
   int nb = (2 * ne + 255) / 256; if (nb > 64) nb = 64;
   pk_moments_final<<<nb, 256, sizeof(int) * (2 * nbins + 1), st>>>(c->d_mom, ntile, ne, fail_step, diag, idx, R, nbins,
                                                                 c->p.h, q_lo, q_hi, d_lo, d_hi, packed);
+  CK(c, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pk_peakon_suite(pk_ctx* c, const double* u, const int32_t* idx, const int32_t* fail_step,
+                               double* vals, int32_t* ids, void* stream) {
+  if (!c) return -1;
+  if (!u || !idx || !vals || !ids) return fail(c, "pk_peakon_suite: null pointer");
+  CK(c, cudaSetDevice(c->cfg.device));
+  pk_peakon_suite_kernel<<<c->cfg.R, 128, 0, (cudaStream_t)stream>>>(u, idx, fail_step, c->p.ne, c->p.h, vals, ids);
   CK(c, cudaGetLastError());
   return 0;
 }

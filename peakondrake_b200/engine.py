@@ -186,3 +186,15 @@ class EnsembleIntegrator(object):
         _lib.check(self.lib, self.ctx, rc)
         self._keep_d = pq_dev
         return self.diag, self.didx, du
+
+    def peakon_suite(self):
+        """Device part of peakon_diagnostics (outputting.py:373-450); call after diagnostics().
+        Returns (vals [R,2] = (min_du, max_du), ids [R,3] = (argmax u, min_du_idx, max_du_idx))."""
+        if not hasattr(self, 'pk_vals'):
+            self.pk_vals = torch.zeros(self.R, 2, dtype=torch.float64, device=self.device)
+            self.pk_ids = torch.zeros(self.R, 3, dtype=torch.int32, device=self.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.pk_peakon_suite(self.ctx, _ptr(self.u), _ptr(self.didx), _ptr(self.fail_step),
+                                      _ptr(self.pk_vals), _ptr(self.pk_ids), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        return self.pk_vals, self.pk_ids

@@ -13,6 +13,23 @@ import torch
 from peakondrake_b200 import _lib
 
 
+def partition(R_total, world_size, rank):
+    """Contiguous block of global realisation ids owned by `rank`: (offset, count).
+    Philox counters are keyed by the GLOBAL id, so results do not depend on world_size."""
+    base, extra = divmod(int(R_total), int(world_size))
+    count = base + (1 if rank < extra else 0)
+    offset = rank * base + min(rank, extra)
+    return offset, count
+
+
+def allreduce_packed(packed, group=None):
+    """The one collective of this path: sum the packed statistics buffer over ranks (NCCL on GPU
+    tensors, gloo on CPU tensors in the tests)."""
+    import torch.distributed as dist
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
 class EnsembleStatistics(object):
     def __init__(self, engine, nbins=64, lo=0.0, hi=None, du_lo=-10.0, du_hi=0.0):
         self.eng = engine
@@ -33,8 +50,7 @@ class EnsembleStatistics(object):
         _lib.check(eng.lib, eng.ctx, rc)
         self.launches += 3      # pk_diag_kernel + pk_moments_partial + pk_moments_final
         if allreduce:
-            import torch.distributed as dist
-            dist.all_reduce(self.packed, op=dist.ReduceOp.SUM)
+            allreduce_packed(self.packed)
         return self.packed
 
     # views into the packed buffer

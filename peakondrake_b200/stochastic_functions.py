@@ -66,6 +66,39 @@ def xi_functions(Xi_family, num_Xis, sigma, Ld):
     return fs
 
 
+def xi_derivative_functions(Xi_family, num_Xis, sigma, Ld):
+    """Analytic d/dx of the xi_n (what UFL's Xi_function.dx(0) evaluates, stochastic_functions.py:179)."""
+    ds = []
+    if Xi_family in ('sines', 'double_sines', 'high_freq_sines'):
+        for n in range(num_Xis):
+            k = {'sines': 2 * (n + 1), 'double_sines': 4 * (n + 1), 'high_freq_sines': 2 * (n + 1) + 10}[Xi_family] * np.pi / Ld
+            ds.append((lambda x, k=k: sigma * k * np.cos(k * x)) if (n + 1) % 2 == 1
+                      else (lambda x, k=k: -sigma * k * np.sin(k * x)))
+    elif Xi_family == 'gaussians':
+        for n in range(num_Xis):
+            c = Ld * (n + 1) / (num_Xis + 1.0)
+            ds.append(lambda x, c=c: sigma * 0.5 * num_Xis * np.exp(-((x - c) / 2.) ** 2) * (-(x - c) / 2.))
+    elif Xi_family == 'proper_peak':
+        ds.append(lambda x: -sigma * (np.exp(x - Ld / 2) - np.exp(-x + Ld / 2)) / (np.exp(x - Ld / 2) + np.exp(-x + Ld / 2)) ** 2)
+    elif Xi_family == 'quadratic':
+        def dquad(x):
+            x = np.asarray(x, dtype=float)
+            v = np.zeros_like(x)
+            s1 = (x > Ld / 4) & ~(x > 3 * Ld / 8)
+            s2 = (x > 3 * Ld / 8) & ~(x > 5 * Ld / 8)
+            s3 = (x > 5 * Ld / 8) & (x < 3 * Ld / 4)
+            v[s1] = 2 * (x[s1] - Ld / 4)
+            v[s2] = 2 * (x[s2] - Ld / 2)
+            v[s3] = sigma * 2 * (x[s3] - 3 * Ld / 4)
+            return 32 / (Ld * Ld) * v
+        ds.append(dquad)
+    elif Xi_family == 'constant':
+        ds.append(lambda x: np.zeros_like(np.asarray(x, dtype=float)))
+    else:
+        raise NotImplementedError('Xi_family %s not implemented' % Xi_family)
+    return ds
+
+
 _G2 = (0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0))   # 2-point Gauss on [0,1], weights 1/2
 
 

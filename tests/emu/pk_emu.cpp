@@ -27,6 +27,10 @@ struct EmuExec {
     if (order == 0) for (int t = 0; t < T; ++t) f(th[t]);
     else for (int t = T - 1; t >= 0; --t) f(th[t]);
   }
+  template <class F> void each_tid(F f) {
+    if (order == 0) for (int t = 0; t < T; ++t) f(t, T);
+    else for (int t = T - 1; t >= 0; --t) f(t, T);
+  }
   void sync() {}
   template <class F> void one(F f) { f(); }
   template <class F> void allreduce3(F f, double* out) {
@@ -75,7 +79,7 @@ static void run_one(const Params& p, StepIO io, double* u, double* u1, double* d
     sh.G[sl] = (MODE == NOISE_FULL) ? dG[off + i] : 0.0;
   }
   EmuExec<M, MODE> ex(p, order);
-  run_steps<EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  run_steps<M, MODE, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
   for (int i = 0; i < p.ne; ++i) {
     const int sl = row_slot(p, i);
     u[off + i] = sh.U0[sl]; u1[off + i] = sh.U1[sl]; dF[off + i] = sh.F[sl];

@@ -1,0 +1,103 @@
+"""
+The CUDA kernel's algorithm, executed on the CPU by the emulation harness (tests/emu/pk_emu.cpp runs
+the identical `pk_core.h` phases with the threads of a CTA serialised), against the oracle.
+This is what keeps the kernel logic under test in the GPU-less container; the GPU tests
+(test_gpu_parity.py) repeat the comparison on the real device.
+"""
+import numpy as np
+import pytest
+
+from oracle import ch_oracle as O
+from emu_util import emu_step, lib
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def compare(ne, nsteps=5, ic='proper_peak', fam='sines', nxi=4, sigma=0.2, scheme='hydrodynamic', dt=1e-3,
+            Ld=40.0, T=0, M=0, seed=3, order=0):
+    mesh = O.Mesh1D(ne, Ld)
+    u0 = O.initial_u(mesh, ic)
+    tabs = O.noise_tables(mesh, fam, nxi, sigma, scheme=scheme) if nxi else None
+    dW = O.reference_dW(seed, nsteps, nxi, dt) if nxi else None
+    ref = O.run(ne, Ld, dt, nsteps, u0, dW, tabs, scheme=scheme)
+    u = u0[None].copy(); u1 = np.zeros_like(u); dF = np.zeros_like(u); dG = np.zeros_like(u)
+    if nxi == 0 or fam == 'constant':
+        mode, xc = 0, (tabs[0][0, 1] if nxi else 0.0)
+    elif scheme == 'no_gradient':
+        mode, xc = 1, 0.0
+    else:
+        mode, xc = 2, 0.0
+    tabs_c = [np.ascontiguousarray(t) for t in tabs] if tabs is not None else None
+    r = emu_step(ne, Ld, dt, mode, u, u1, dF, dG, tabs_c, None if dW is None else np.ascontiguousarray(dW[:, None, :]),
+                 nsteps, xi_const=xc, T=T, M=M, order=order, nxi=nxi)
+    assert r['fail_step'][0] == -1
+    assert r['its_total'][0] == ref['its'].sum()
+    assert rel(u[0], ref['u']) <= TOL and rel(u1[0], ref['w1'][:ne]) <= TOL
+    assert rel(dF[0], ref['w1'][ne:2 * ne]) <= 1e-9
+    return u[0], u1[0], dF[0], dG[0]
+
+
+@pytest.mark.parametrize('ne', [8, 9, 16, 20, 37, 64, 200, 1000, 1001, 1500])
+def test_mesh_sizes(ne):
+    compare(ne, nsteps=4, nxi=2)
+
+
+@pytest.mark.parametrize('T,M,ne', [(4, 5, 20), (4, 6, 22), (8, 7, 50), (16, 8, 128), (32, 8, 250), (2, 5, 9)])
+def test_forced_layouts(T, M, ne):
+    compare(ne, nsteps=3, nxi=3, T=T, M=M)
+
+
+def test_constant_noise_and_no_noise_and_no_gradient():
+    compare(400, fam='constant', nxi=1, ic='periodic_peakon', sigma=1.0)
+    compare(300, nxi=0)
+    compare(300, scheme='no_gradient', nxi=3)
+
+
+def test_thread_order_independence():
+    """Running the threads of a phase in ascending or descending order must give bit-identical
+    results: there is no intra-phase communication (race-freedom of the barrier structure)."""
+    a = compare(250, nsteps=4, order=0)
+    b = compare(250, nsteps=4, order=1)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_fine_mesh_large_noise():
+    # C5-like spacing h = 40/2000 with sigma = 1: P is strongly non diagonally dominant here
+    compare(2000, nsteps=3, ic='periodic_peakon', fam='constant', nxi=1, sigma=1.0, dt=1e-2)
+
+
+def test_failure_latch_and_reason():
+    ne, Ld, dt = 64, 40.0, 1e-3
+    u0 = O.initial_u(O.Mesh1D(ne, Ld), 'proper_peak')
+    tabs = [np.ascontiguousarray(t) for t in O.noise_tables(O.Mesh1D(ne, Ld), 'sines', 1, 1.0)]
+    dW = np.zeros((4, 1, 1)); dW[2] = np.nan
+    u = u0[None].copy(); u1 = np.zeros_like(u); dF = np.zeros_like(u); dG = np.zeros_like(u)
+    r = emu_step(ne, Ld, dt, 2, u, u1, dF, dG, tabs, dW, 4)
+    assert r['fail_step'][0] == 2 and r['reason'][0] == 2          # DIVERGED_FNORM_NAN at step 2
+    ref = O.run(ne, Ld, dt, 2, u0, dW[:2, 0, :], tabs)
+    assert rel(u[0], ref['u']) <= TOL                               # frozen at the last accepted state
+
+
+def test_philox_generator_statistics_and_reproducibility():
+    L = lib()
+    z = np.array([L.pk_emu_philox_normal(42, r, s, 0, 0) for r in range(200) for s in range(50)])
+    assert abs(z.mean()) < 0.03 and abs(z.std() - 1) < 0.03
+    assert abs((z ** 3).mean()) < 0.1 and abs((z ** 4).mean() - 3) < 0.2
+    assert L.pk_emu_philox_normal(42, 5, 7, 1, 0) == L.pk_emu_philox_normal(42, 5, 7, 1, 0)
+    assert L.pk_emu_philox_normal(42, 5, 7, 1, 0) != L.pk_emu_philox_normal(43, 5, 7, 1, 0)
+    # exported in-kernel increments reproduce the path through the oracle; sub-updates sum
+    ne, Ld, dt, n = 64, 40.0, 1e-3, 5
+    u0 = O.initial_u(O.Mesh1D(ne, Ld), 'proper_peak')
+    tabs = [np.ascontiguousarray(t) for t in O.noise_tables(O.Mesh1D(ne, Ld), 'sines', 2, 0.3)]
+    u = np.tile(u0, (2, 1)); u1 = np.zeros_like(u); dF = np.zeros_like(u); dG = np.zeros_like(u)
+    r = emu_step(ne, Ld, dt, 2, u, u1, dF, dG, tabs, None, n, nxi=2, seed=9, rid0=100, export=True, nupd=4)
+    for k in range(2):
+        ref = O.run(ne, Ld, dt, n, u0, r['dW'][:, k, :], tabs)
+        assert rel(u[k], ref['u']) <= TOL
+    w = sum(L.pk_emu_philox_normal(9, 101, 3, 1, j) for j in range(4)) * np.sqrt(dt / 4)
+    assert abs(r['dW'][3, 1, 1] - w) < 1e-16          # kernel scales each sub-draw, then sums

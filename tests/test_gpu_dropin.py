@@ -1,0 +1,142 @@
+"""
+GPU tests of the drop-in surface: experiment()/simulation() with the reference's keyword arguments,
+the data.nc schema, the device peakon-suite and ensemble-statistics kernels.
+"""
+import os
+import numpy as np
+import pytest
+
+from oracle import ch_oracle as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, 'golden', 'reference_helpers.npz'))
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_experiment_seed_ensemble_matches_oracle_per_seed(tmp_path, monkeypatch):
+    """The reference's runnable test parameters (tests/test_dumping.py: 10 steps, dumps every step, 7 sines)
+    transplanted to the hydrodynamic scheme, with a seed sweep batched on the GPU."""
+    from peakondrake_b200 import experiment, outputting as out
+    monkeypatch.chdir(tmp_path)
+    Ld, dt, tmax, ne, nxi, sigma = 40., 0.001, 0.01, 200, 7, 0.25
+    seeds = [0, 1, 2, 5]
+    experiment('test_one_run', Ld, tmax, resolutions=ne, dts=dt, sigmas=sigma, seeds=seeds, schemes='hydrodynamic',
+               timesteppings='midpoint', ics='one_peak', num_Xis=nxi, Xi_family='sines', alphasq=1.0, c0=0.,
+               gamma=0., diagnostics=['h1_u', 'l2_u', 'energy', 'max_du', 'min_du', 'min_du_loc', 'q_pde', 'u_field',
+                                      'mu', 'peakon_suite', 'l2_m', 'E_2'],
+               fields_to_output=['du'], ndump=1, field_ndump=1, allow_fail=True)
+    d = out.read_data_file('results/test_one_run/data.nc')
+    assert d['time'].shape == (11,) and np.allclose(d['time'], np.arange(11) * dt)
+    assert d['energy'].shape == (11, 4) and d['u_field'].shape == (11, 4, ne) and list(d['seed']) == seeds
+    assert np.allclose(d['x'], (np.arange(ne) + 0.5) * Ld / ne)
+    assert np.isnan(d['failed_time']).all() and (d['wallclock_time'][1] >= d['wallclock_time'][0]).all()
+    mesh = O.Mesh1D(ne, Ld)
+    u0 = O.initial_u(mesh, 'one_peak')
+    tabs = O.noise_tables(mesh, 'sines', nxi, sigma)
+    orc = O.CHOracle(ne, Ld, dt)
+    for k, s in enumerate(seeds):
+        dW = O.reference_dW(s, 10, nxi, dt)               # the reference's own stream for this seed
+        ref = O.run(ne, Ld, dt, 10, u0, dW, tabs, dump_every=1)
+        for t in range(1, 11):
+            u = ref['dumps'][t - 1]
+            assert rel(d['u_field'][t, k], u) <= 1e-10
+            sd = O.scalar_diagnostics(orc, u, ['energy', 'l2_u', 'h1_u', 'max_du', 'min_du', 'min_du_loc', 'q_pde',
+                                               'l2_m', 'E_2'], m=O.m_field(orc, u))
+            for name, v in sd.items():
+                assert abs(d[name][t, k] - v) <= 1e-9 * max(1.0, abs(v)), (name, t, k)
+        assert abs(d['energy'][0, k] - (u0 @ (orc.M @ u0) + u0 @ (orc.K @ u0))) < 1e-12
+    assert np.isfinite(d['mu_0']).all() and np.isnan(d['mu_1']).all()        # single peak
+    assert np.isfinite(d['peakon_mu']).all() and (d['peakon_max_u'] > 0.4).all()
+
+
+def test_simulation_single_realisation_and_convergence_error(tmp_path, monkeypatch):
+    from peakondrake_b200 import simulation, ConvergenceError, PeriodicIntervalMesh
+    monkeypatch.chdir(tmp_path)
+    p = dict(dt=(1e-3,), resolution=(100,), seed=(3,), sigma=(0.2,), scheme=('hydrodynamic',), timestepping=('midpoint',),
+             alphasq=(1.0,), c0=(0.,), gamma=(0.,), ic=('proper_peak',), num_Xis=(2,), Xi_family=('sines',),
+             dirname=('results/x',), Ld=(40.,), tmax=(0.005,), ndump=(-1,), field_ndump=(-1,), nXi_updates=(1,),
+             allow_fail=(False,), smooth_t=(None,), peakon_equations=(False,), only_peakons=(False,),
+             true_peakon_data=(None,), true_mean_peakon_data=(None,), peakon_speed=(None,), periodic=(False,),
+             fixed_dW=(None,), peak_width=(1.0,), peakon_method=('ito_euler',), store_coordinates=[True],
+             mesh=(PeriodicIntervalMesh(100, 40.),), file_name=('none',))
+    u = simulation(p, diagnostic_values=None, expected_u=True)
+    mesh = O.Mesh1D(100, 40.)
+    ref = O.run(100, 40., 1e-3, 5, O.initial_u(mesh, 'proper_peak'), O.reference_dW(3, 5, 2, 1e-3),
+                O.noise_tables(mesh, 'sines', 2, 0.2))
+    assert rel(u, ref['u']) <= 1e-10
+    # a forcing SNES cannot handle: without allow_fail the failure propagates (simulation.py:107-108)
+    p2 = dict(p); p2['smooth_t'] = (lambda t: float('nan'),)
+    with pytest.raises(ConvergenceError):
+        simulation(p2, diagnostic_values=None)
+    p3 = dict(p); p3['peakon_equations'] = ('yes',)
+    with pytest.raises(ValueError):
+        simulation(p3)                                                     # simulation.py:68-69
+
+
+def test_true_peakon_workflow(tmp_path, monkeypatch):
+    """The strong-convergence design of experiments/publication/stochastic (true_peakon_sde.py then
+    peakon_strong_dt.py), scaled down: SDE-only 'true' run, then PDE runs measured against it."""
+    from peakondrake_b200 import experiment, outputting as out
+    monkeypatch.chdir(tmp_path)
+    common = dict(resolutions=400, sigmas=1.0, seeds=0, schemes='hydrodynamic', timesteppings='midpoint',
+                  ics='periodic_peakon', num_Xis=1, Xi_family='constant', alphasq=1.0, c0=0., gamma=0.,
+                  allow_fail=True, periodic=True)
+    tmax, dt_true, dt = 0.02, 1e-4, 2e-3
+    experiment('true_peakon_data', 40., tmax, dts=dt_true, diagnostics=['l2_u'], fields_to_output=[],
+               ndump=int(round(tmax / dt_true)), field_ndump=int(round(tmax / dt_true)), peakon_equations=True, only_peakons=True, **common)
+    t = out.read_data_file('results/true_peakon_data/data.nc')
+    assert t['p'].shape == (2,) and np.isnan(t['l2_u'][1]) and not np.isnan(t['p'][1])
+    # q moves with speed p/2 * coth-like factor plus sigma*W: with sigma=1 the displacement is O(sqrt(tmax))
+    assert abs(t['q'][1] - t['q'][0]) < 1.0 and t['p'][1] == t['p'][0]      # constant Xi: dp = 0
+    experiment('strong', 40., tmax, dts=dt, diagnostics=['u_error_with_sde', 'u_error_weak', 'p_pde', 'q_pde'],
+               fields_to_output=['u_sde', 'u_sde_weak'], ndump=int(round(tmax / dt)), field_ndump=int(round(tmax / dt)),
+               true_peakon_data='true_peakon_data', nXi_updates=int(round(dt / dt_true)), **common)
+    s = out.read_data_file('results/strong/data.nc')
+    assert s['u_error_with_sde'].shape == (2,) and s['u_error_with_sde'][1] < 0.05
+    assert s['u_error_with_sde'][1] == s['u_error_weak'][1]
+    # same Brownian path: the PDE peak follows the SDE peakon to within a few cells
+    assert abs(s['q_pde'][1] - t['q'][1]) < 0.5
+
+
+@pytest.mark.parametrize('name', [str(n) for n in GOLD['names']])
+def test_device_peakon_suite_against_reference_helper(name):
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, outputting as out, _lib
+    u = GOLD[name + '/u']; ne = len(u); Ld = 40.0
+    eng = EnsembleIntegrator(ne, Ld, 1e-3, 2)
+    eng.u.copy_(torch.from_numpy(np.stack([u, np.roll(u, 17)])))
+    vals, idx, _ = eng.diagnostics()
+    pv, pi = eng.peakon_suite()
+    torch.cuda.synchronize()
+    x = (np.arange(ne) + 0.5) * Ld / ne
+    res = out.peakon_suite_from_indices(x, vals[0, _lib.D_MAX_U].item(), pv[0].cpu().numpy(), pi[0].cpu().numpy())
+    got = np.array([res[k] for k in out.PEAKON_DIAGNOSTICS])
+    assert np.array_equal(got, GOLD[name + '/peakon'], equal_nan=True)      # bit-exact incl. locations
+
+
+def test_ensemble_statistics_kernels():
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, EnsembleStatistics, build_initial_u
+    ne, Ld, R = 300, 40.0, 70
+    eng = EnsembleIntegrator(ne, Ld, 1e-3, R, num_Xis=2, sigma=0.3, seed=5)
+    eng.set_state(build_initial_u(ne, Ld, 'proper_peak'))
+    eng.step(5)
+    eng.fail_step[3] = 2                     # a failed realisation is excluded from the statistics
+    st = EnsembleStatistics(eng, nbins=16, lo=0.0, hi=Ld, du_lo=-2.0, du_hi=0.0)
+    st.update()
+    torch.cuda.synchronize()
+    u = eng.u.cpu().numpy(); ok = np.ones(R, bool); ok[3] = False
+    assert st.count.item() == R - 1
+    assert np.allclose(st.mean_u.cpu().numpy(), u[ok].mean(0), rtol=1e-13, atol=1e-15)
+    assert np.allclose(st.packed[ne:2 * ne].cpu().numpy(), (u[ok] ** 2).sum(0), rtol=1e-13)
+    du = (np.roll(u, -1, axis=1) - u) / (Ld / ne)
+    q = (np.argmax(u[ok], axis=1) + 0.5) * Ld / ne
+    hq = np.histogram(q, bins=16, range=(0, Ld))[0]
+    hd = np.histogram(np.clip(du[ok].min(1), -2.0, -1e-12), bins=16, range=(-2.0, 0.0))[0]
+    assert np.array_equal(st.hist_q.cpu().numpy(), hq) and np.array_equal(st.hist_min_du.cpu().numpy(), hd)
+    a = st.packed.clone(); st.update(); torch.cuda.synchronize()
+    assert torch.equal(a, st.packed)         # deterministic (fixed-order sums, integer histograms)
