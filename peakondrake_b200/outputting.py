@@ -33,6 +33,13 @@ class DataFile(object):
 
     def createVariable(self, name, typ, dims):
         tc = _NC_TYPES.get(typ, 'd')
+        if len(tuple(dims)) == 0:
+            # scipy's NetCDF-3 writer corrupts record variables when a 0-d variable is present;
+            # scalars are stored with a length-1 dimension instead (read as var[0], like the
+            # reference's own `data_file['failed_time'][0]`, outputting.py:241)
+            if 'scalar' not in self.dims:
+                self.createDimension('scalar', 1)
+            dims = ('scalar',)
         self.vars[name] = (tc, tuple(dims))
         shape = tuple(0 if self.dims[d] is None else self.dims[d] for d in dims)
         if tc == 'c':
@@ -71,10 +78,8 @@ class DataFile(object):
                 a = self.data[name]
                 for t in range(nrec):
                     handles[name][t] = a[t]
-            elif dims:
-                handles[name][:] = a
             else:
-                handles[name].assignValue(a)
+                handles[name][:] = a
         f.close()
 
 

@@ -286,10 +286,7 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
             ix = index_of(si)
             data_file.put('wallclock_time', (1,) + ix, wall1)
             ft = np.nan if (fs[k] < 0 or only_peakons) else (fs[k] + 1) * dt      # simulation.py:105
-            if len(ix) == 0:
-                data_file.data['failed_time'] = np.array(ft)
-            else:
-                data_file.put('failed_time', ix, ft)
+            data_file.put('failed_time', ix if len(ix) else (0,), ft)
     result = dict(fail_step=fs, its_total=eng.its_total.cpu().numpy(), nsteps=nsteps)
     if return_state:
         result['u'] = eng.u.cpu().numpy()
