@@ -112,7 +112,7 @@ def test_device_peakon_suite_against_reference_helper(name):
     vals, idx, _ = eng.diagnostics()
     pv, pi = eng.peakon_suite()
     torch.cuda.synchronize()
-    x = (np.arange(ne) + 0.5) * Ld / ne
+    x = (np.arange(ne) + 0.5) * (Ld / ne)      # the coordinate array the fixtures were made with
     res = out.peakon_suite_from_indices(x, vals[0, _lib.D_MAX_U].item(), pv[0].cpu().numpy(), pi[0].cpu().numpy())
     got = np.array([res[k] for k in out.PEAKON_DIAGNOSTICS])
     assert np.array_equal(got, GOLD[name + '/peakon'], equal_nan=True)      # bit-exact incl. locations
