@@ -161,6 +161,33 @@ struct Thread {
     fn2 = sn2 = xn2 = 0.0; Xs = 0.0;
   }
 
+  // ---- liveness helpers ---------------------------------------------------------------------
+  // Several per-thread arrays are written under predicates (optional last row, k < nI).  Without an
+  // unconditional definition the compiler must keep their previous values alive around the Newton
+  // and time-step loops (~190 registers); these "kills" end those live ranges explicitly.
+  PK_HD void kill_factors() {
+    PK_UNROLL
+    for (int k = 0; k < NI; ++k) { r[k] = 0.0; e[k] = 0.0; f[k] = 0.0; zb[k] = 0.0; zw1[k] = 0.0; zw2[k] = 0.0; }
+  }
+  PK_HD void kill_all() {
+    kill_factors();
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) { du[j] = 0.0; hF[j] = 0.0; hG[j] = 0.0; }
+    PK_UNROLL
+    for (int c = 0; c < 5; ++c) { sp0[c] = 0.0; sp1[c] = 0.0; F2a[c] = 0.0; F2b[c] = 0.0; }
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { Lb[c] = 0.0; Db[c] = 0.0; Ub[c] = 0.0; }
+    PK_UNROLL
+    for (int c = 0; c < 3; ++c) { wCm2[c] = 0.0; wCm1[c] = 0.0; wC01[c] = 0.0; }
+    rb[0] = rb[1] = 0.0; sb0 = sb1 = 0.0; xs0 = xs1 = 0.0; wQm2 = wQm1 = wQ01 = 0.0;
+    NodeS z; z.a = z.v = z.w = z.F = z.G = z.x = z.y = 0.0;
+    nm = z; n0 = z; np = z;
+    pc.N1L = pc.N1R = pc.fL = pc.fR = pc.gL = pc.gR = 0.0;
+    pc.dN1L0 = pc.dN1L1 = pc.dN1R0 = pc.dN1R1 = 0.0;
+    pc.dfL0 = pc.dfL1 = pc.dfR0 = pc.dfR1 = 0.0;
+    pc.dgL0 = pc.dgL1 = pc.dgR0 = pc.dgR1 = 0.0;
+  }
+
   // ---- smem index helpers -------------------------------------------------------------
   PK_HD int idx(const Params& p, int j) const { return j * p.T + t; }
   // node with local index j in [-1, m]: own rows, last row of the left chunk, first row of the right chunk
@@ -300,6 +327,7 @@ struct Thread {
   // ---- phase A1: first two cells, publish first-node packet --------------------------------
   PK_HD void assemble_begin(const Params& p, const Shared& sh) {
     fn2 = 0.0;
+    kill_factors();
     load_node(p, sh, -1, nm);
     load_node(p, sh, 0, n0);
     pc.compute(p, nm, n0);
@@ -458,27 +486,45 @@ struct Thread {
   // ---- phase D1: Helmholtz right-hand sides f + f'/2 du, g + g'/2 du; causal local pass ------
   // returns the chunk aggregate (value with zero carry-in) in cF, cG and the multiplier A = rho^m
   PK_HD void helm_causal_local(const Params& p, const Shared& sh, double& A, double& cF, double& cG) {
+    // Right-hand sides  f(uh) + f'(uh) e  and  g(uh) + g'(uh) e  with e = du/2 (the change of uh).
+    // f is a homogeneous quadratic form in uh, g is linear in uh, hence exactly
+    //    f(uh) + f'(uh) e = f(uh + e) - f(e),        g(uh) + g'(uh) e = g(uh + e).
     const int T = p.T;
-    NodeS A0, B0;
-    load_node(p, sh, -1, A0);
-    double ea = 0.5 * sh.xb[16 * T + tl];      // half the increment of the left neighbour's last row
+    double a0, x0 = 0.0, y0 = 0.0, e0;
+    {
+      const int i = nidx(p, -1);
+      a0 = 0.5 * (sh.U0[i] + sh.U1[i]);
+      if (MODE == NOISE_FULL) { x0 = sh.Xx[i]; y0 = sh.Xxx[i]; }
+      e0 = 0.5 * sh.xb[16 * T + tl];           // half the increment of the left neighbour's last row
+    }
     double prevFR = 0.0, prevGR = 0.0;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) { hF[j] = 0.0; hG[j] = 0.0; }
     PK_UNROLL
     for (int q = 0; q <= M; ++q) {
       if (q <= m) {
-        load_node(p, sh, q, B0);
-        const double eb = 0.5 * ((q < m) ? du[q < M ? q : M - 1] : sh.xb[14 * T + tr]);
-        CellC<MODE> cc; cc.compute(p, A0, B0);
-        const double fLv = cc.fL + cc.dfL0 * ea + cc.dfL1 * eb;
-        const double fRv = cc.fR + cc.dfR0 * ea + cc.dfR1 * eb;
+        const int i = nidx(p, q);
+        const double a1 = 0.5 * (sh.U0[i] + sh.U1[i]);
+        double x1 = 0.0, y1 = 0.0;
+        if (MODE == NOISE_FULL) { x1 = sh.Xx[i]; y1 = sh.Xxx[i]; }
+        const double e1 = 0.5 * ((q < m) ? du[q < M ? q : M - 1] : sh.xb[14 * T + tr]);
+        const double b0 = a0 + e0, b1 = a1 + e1;            // uh + e at the two nodes of the cell
+        const double db = b1 - b0, de = e1 - e0;
+        const double qb = b0 * b0 + b1 * b1, pb = b0 * b1, qe = e0 * e0 + e1 * e1, pe = e0 * e1;
+        // fL = c1 (3 b0^2 + 2 b0 b1 + b1^2) + c2 db^2 ;  fR = c1 (b0^2 + 2 b0 b1 + 3 b1^2) + c2 db^2
+        const double sb = p.c1 * (qb + 2.0 * pb) + p.c2 * db * db;
+        const double se = p.c1 * (qe + 2.0 * pe) + p.c2 * de * de;
+        const double fLv = (sb + 2.0 * p.c1 * b0 * b0) - (se + 2.0 * p.c1 * e0 * e0);
+        const double fRv = (sb + 2.0 * p.c1 * b1 * b1) - (se + 2.0 * p.c1 * e1 * e1);
         double gLv = 0.0, gRv = 0.0;
         if (MODE == NOISE_FULL) {
-          gLv = cc.gL + cc.dgL0 * ea + cc.dgL1 * eb;
-          gRv = cc.gR + cc.dgR0 * ea + cc.dgR1 * eb;
+          const double xs = x0 + x1;
+          gLv = p.h6 * (b0 * (3.0 * x0 + x1) + b1 * xs) + p.a26 * db * (2.0 * y0 + y1);
+          gRv = p.h6 * (b0 * xs + b1 * (x0 + 3.0 * x1)) + p.a26 * db * (y0 + 2.0 * y1);
         }
         if (q >= 1) { hF[q - 1] = (prevFR + fLv) * p.ikappa; hG[q - 1] = (prevGR + gLv) * p.ikappa; }
         prevFR = fRv; prevGR = gRv;
-        A0 = B0; ea = eb;
+        a0 = a1; x0 = x1; y0 = y1; e0 = e1;
       }
     }
     // causal recurrence with zero carry-in
@@ -566,16 +612,34 @@ template <int M, int MODE>
 PK_HD void fill_noise_rows(const Params& p, const Shared& sh, const double* xi, const double* xi_x,
                            const double* xi_xx, int tid, int nth) {
   if (MODE == NOISE_SCALAR) return;
-  for (int g = tid; g < p.ne; g += nth) {
-    double X = 0.0, Xx = 0.0, Xxx = 0.0;
+  enum { NB = 4 };     // nodes in flight per thread: NB x 3 tables x (unrolled modes) independent loads
+  for (int base = tid; base < p.ne; base += NB * nth) {
+    double X[NB], Xx[NB], Xxx[NB];
+    PK_UNROLL
+    for (int j = 0; j < NB; ++j) { X[j] = 0.0; Xx[j] = 0.0; Xxx[j] = 0.0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
     for (int k = 0; k < p.nxi; ++k) {
       const double w = sh.dW[k];
-      X += w * xi[k * p.ne + g];
-      if (MODE == NOISE_FULL) { Xx += w * xi_x[k * p.ne + g]; Xxx += w * xi_xx[k * p.ne + g]; }
+      PK_UNROLL
+      for (int j = 0; j < NB; ++j) {
+        const int g = base + j * nth;
+        if (g < p.ne) {
+          X[j] += w * xi[k * p.ne + g];
+          if (MODE == NOISE_FULL) { Xx[j] += w * xi_x[k * p.ne + g]; Xxx[j] += w * xi_xx[k * p.ne + g]; }
+        }
+      }
     }
-    const int i = row_slot_c<M>(p, g);
-    sh.X[i] = X;
-    if (MODE == NOISE_FULL) { sh.Xx[i] = Xx; sh.Xxx[i] = Xxx; }
+    PK_UNROLL
+    for (int j = 0; j < NB; ++j) {
+      const int g = base + j * nth;
+      if (g < p.ne) {
+        const int i = row_slot_c<M>(p, g);
+        sh.X[i] = X[j];
+        if (MODE == NOISE_FULL) { sh.Xx[i] = Xx[j]; sh.Xxx[i] = Xxx[j]; }
+      }
+    }
   }
 }
 
@@ -619,6 +683,7 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 //   scan_rev(fin)      the reverse cyclic scan (order T-1..0); fin() receives the entering value
 //   each_tid(f)        run f(tid, nthreads) on every thread of the block (also the idle ones)
 //   one(f)             run f() once (thread 0)
+//   tick(id)           profiling hook (no-op unless built with -DPK_PROFILE): time since the last tick -> bucket id
 // ------------------------------------------------------------------------------------------------
 struct StepIO {
   const double* dW_in;    // [nsteps, R, nxi] or null -> Philox
@@ -659,6 +724,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
   int its_last = 0, its_total = io.its_total[io.r], reason = 0;
   int expect = 2;     // iteration at which convergence is expected: there only the residual is evaluated first
   for (int n = 0; n < io.nsteps; ++n) {
+    ex.each([&](Th& th) { th.kill_all(); });
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
     ex.each([&](Th& th) {
       for (int k = th.t; k < p.nxi; k += p.T) {
@@ -676,10 +742,12 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
       }
     });
     ex.sync();
+    ex.tick(0);
     if (failed >= 0) continue;
     if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
     else ex.each_tid([&](int tid, int nth) { fill_noise_rows<M, MODE>(p, sh, io.xi, io.xi_x, io.xi_xx, tid, nth); });
     ex.sync();
+    ex.tick(1);
 
     // ---- SNES newtonls, basic line search ----
     int it = 0, status = 0;
@@ -691,36 +759,46 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
         ex.each([&](Th& th) { th.residual_only(p, sh); });
         ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
         status = snes_test(p, it, nrm, fnorm0, reason);
+        ex.tick(2);
         if (status) break;
       }
       ex.each([&](Th& th) { th.assemble_begin(p, sh); });
       ex.sync();
+      ex.tick(3);
       ex.each([&](Th& th) { th.assemble_finish(p, sh); });
+      ex.tick(4);
       ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
       status = snes_test(p, it, nrm, fnorm0, reason);
+      ex.tick(5);
       if (status) break;
       // ---- linear solve + update ----
       ex.each([&](Th& th) { th.reduce_build(p, sh); });
       ex.sync();
       ex.each([&](Th& th) { th.reduce_publish(p, sh); });
       ex.sync();
+      ex.tick(6);
       for (int d = 1; d < p.T / 2; d *= 2) {
         ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
         ex.sync();
         ex.each([&](Th& th) { th.reduce_publish(p, sh); });
         ex.sync();
       }
+      ex.tick(7);
       ex.each([&](Th& th) { th.pcr_final(p, sh); });
       ex.sync();
+      ex.tick(8);
       ex.each([&](Th& th) { th.interior_solve(p, sh); });
       ex.sync();
+      ex.tick(9);
       // forward cyclic scan (causal filter); its carries feed the anticausal local pass, whose maps
       // are scanned in reverse; the reverse carries finish the update.
       ex.scan_fwd([&](Th& th, double& A, double& c0, double& c1) { th.helm_causal_local(p, sh, A, c0, c1); },
                   [&](Th& th, double in0, double in1, double& A, double& c0, double& c1) {
                     th.helm_anticausal_local(p, in0, in1, A, c0, c1); });
+      ex.tick(10);
       ex.scan_rev([&](Th& th, double in0, double in1) { th.helm_finish_update(p, sh, in0, in1); });
       ex.sync();
+      ex.tick(11);
       ++it;
     }
     its_last = it; its_total += it;
@@ -731,6 +809,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
       failed = io.step0 + n;
     }
     ex.sync();
+    ex.tick(12);
   }
   ex.one([&]() {
     io.fail_step[io.r] = failed; io.its_last[io.r] = its_last; io.its_total[io.r] = its_total;

@@ -21,7 +21,9 @@ using namespace pk;
 // ------------------------------------------------------------------------------------------------
 // device-side executor: one CUDA thread per chunk
 // ------------------------------------------------------------------------------------------------
-template <int M, int MODE>
+// AA ("all active") is true for every launch with T >= 32 chunks: then no thread of the block is idle and
+// the phase calls are unconditional, which lets the compiler see the per-thread arrays die between phases.
+template <int M, int MODE, bool AA>
 struct GpuExec {
   typedef Thread<M, MODE> Th;
   Th& th;
@@ -31,9 +33,17 @@ struct GpuExec {
   double rA, rc0, rc1;  // maps of the pending reverse scan
   __device__ __forceinline__ GpuExec(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
 
-  template <class F> __device__ __forceinline__ void each(F f) { if (th.active) f(th); }
+  template <class F> __device__ __forceinline__ void each(F f) { if (AA || th.active) f(th); }
   template <class F> __device__ __forceinline__ void each_tid(F f) { f((int)threadIdx.x, (int)blockDim.x); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
+#ifdef PK_PROFILE
+  long long tlast; long long* tbuf;   // per-phase cycle buckets (thread 0 of each CTA), profiling builds only
+  __device__ __forceinline__ void tick(int id) {
+    if (threadIdx.x == 0) { const long long c = clock64(); tbuf[id] += c - tlast; tlast = c; }
+  }
+#else
+  __device__ __forceinline__ void tick(int) {}
+#endif
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
   __device__ __forceinline__ double* area() {
     const int nw = blockDim.x >> 5;
@@ -44,7 +54,7 @@ struct GpuExec {
 
   template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
     double v[3] = {0.0, 0.0, 0.0};
-    if (th.active) f(th, v);
+    if (AA || th.active) f(th, v);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
@@ -102,15 +112,15 @@ struct GpuExec {
 
   template <class G, class P> __device__ __forceinline__ void scan_fwd(G get, P put) {
     double A = 1.0, c0 = 0.0, c1 = 0.0, in0, in1;
-    if (th.active) get(th, A, c0, c1);
+    if (AA || th.active) get(th, A, c0, c1);
     cyc_scan<+1>(A, c0, c1, in0, in1);
     rA = 1.0; rc0 = 0.0; rc1 = 0.0;
-    if (th.active) put(th, in0, in1, rA, rc0, rc1);
+    if (AA || th.active) put(th, in0, in1, rA, rc0, rc1);
   }
   template <class F> __device__ __forceinline__ void scan_rev(F fin) {
     double in0, in1;
     cyc_scan<-1>(rA, rc0, rc1, in0, in1);
-    if (th.active) fin(th, in0, in1);
+    if (AA || th.active) fin(th, in0, in1);
   }
 };
 
@@ -121,6 +131,7 @@ struct StepArgs {
   double* dW_out;
   int *fail_step, *its_last, *its_total;
   int R, step0, nsteps;
+  long long* prof;    // [R,16] cycle buckets, PK_PROFILE builds only
   unsigned rid0;
   unsigned long long seed;
 };
@@ -153,13 +164,22 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
 
   Thread<M, MODE> th;
   th.init(p, threadIdx.x);
-  GpuExec<M, MODE> ex(th, red);
+  GpuExec<M, MODE, (TB > 32)> ex(th, red);
+#ifdef PK_PROFILE
+  __shared__ long long tb[16];
+  if (threadIdx.x < 16) tb[threadIdx.x] = 0;
+  __syncthreads();
+  ex.tbuf = tb; ex.tlast = clock64();
+#endif
   StepIO io;
   io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
   io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
-  run_steps<M, MODE, GpuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  run_steps<M, MODE, GpuExec<M, MODE, (TB > 32)>, Thread<M, MODE> >(ex, p, sh, io);
   __syncthreads();
+#ifdef PK_PROFILE
+  if (a.prof && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];
+#endif
 
   for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
     const int sl = row_slot_c<M>(p, i);
@@ -450,6 +470,7 @@ struct pk_ctx {
   double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;
   double* d_scratch;   // diagnostics scratch [R,2,ne]
   double* d_mom;       // moments partial sums [32, 2*ne]
+  long long* d_prof;   // PK_PROFILE: [R,16] cycle buckets
   cudaEvent_t ev0, ev1;
   bool timed;
 };
@@ -467,7 +488,8 @@ static int fail(pk_ctx* c, const char* fmt, ...) {
 typedef void (*kern_t)(const Params, const StepArgs);
 
 static int g_minb = 0;   // PK_MINB env: resident CTAs/SM the 128-thread kernel is compiled for (2, 3 or 4)
-template <int M, int MODE> static kern_t pick_tb(int block) {
+template <int M, int MODE> static kern_t pick_tb(int block, int T) {
+  if (T < 32) return pk_step_kernel<M, MODE, 32, 1>;      // tiny meshes: some lanes of the single warp idle
   if (block <= 128) {
     if (g_minb == 3) return pk_step_kernel<M, MODE, 128, 3>;
     if (g_minb == 4) return pk_step_kernel<M, MODE, 128, 4>;
@@ -476,19 +498,19 @@ template <int M, int MODE> static kern_t pick_tb(int block) {
   if (block <= 256) return pk_step_kernel<M, MODE, 256, 1>;
   return pk_step_kernel<M, MODE, 512, 1>;
 }
-template <int M> static kern_t pick_mode(int mode, int block) {
+template <int M> static kern_t pick_mode(int mode, int block, int T) {
   switch (mode) {
-    case NOISE_SCALAR: return pick_tb<M, NOISE_SCALAR>(block);
-    case NOISE_X: return pick_tb<M, NOISE_X>(block);
-    default: return pick_tb<M, NOISE_FULL>(block);
+    case NOISE_SCALAR: return pick_tb<M, NOISE_SCALAR>(block, T);
+    case NOISE_X: return pick_tb<M, NOISE_X>(block, T);
+    default: return pick_tb<M, NOISE_FULL>(block, T);
   }
 }
 static kern_t pick_kernel(const Params& p, int block) {
   switch (p.M) {
-    case 5: return pick_mode<5>(p.mode, block);
-    case 6: return pick_mode<6>(p.mode, block);
-    case 7: return pick_mode<7>(p.mode, block);
-    case 8: return pick_mode<8>(p.mode, block);
+    case 5: return pick_mode<5>(p.mode, block, p.T);
+    case 6: return pick_mode<6>(p.mode, block, p.T);
+    case 7: return pick_mode<7>(p.mode, block, p.T);
+    case 8: return pick_mode<8>(p.mode, block, p.T);
   }
   return nullptr;
 }
@@ -526,7 +548,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     return fail(nullptr, "pk_create: ne=%d needs a thread-block cluster per realisation (state does not fit one SM); not built yet", ne);
   }
   c->xi = c->xi_x = c->xi_xx = nullptr;
-  c->step = 0; c->d_state = nullptr; c->d_dWin = c->d_dWout = nullptr; c->d_cnt = nullptr; c->dW_cap = 0; c->d_scratch = nullptr; c->d_mom = nullptr;
+  c->step = 0; c->d_state = nullptr; c->d_dWin = c->d_dWout = nullptr; c->d_cnt = nullptr; c->dW_cap = 0; c->d_scratch = nullptr; c->d_mom = nullptr; c->d_prof = nullptr;
   c->timed = false;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
@@ -581,6 +603,7 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
   StepArgs a;
   a.u = u; a.u1 = u1; a.dF = dF; a.dG = dG; a.xi = c->xi; a.xi_x = c->xi_x; a.xi_xx = c->xi_xx;
   a.dW_in = dW_in; a.dW_out = dW_out; a.fail_step = fail_step; a.its_last = its_last; a.its_total = its_total;
+  a.prof = c->d_prof;
   a.R = c->cfg.R; a.step0 = (int)c->step; a.nsteps = nsteps; a.rid0 = c->cfg.rid_offset; a.seed = c->cfg.seed;
   cudaStream_t st = (cudaStream_t)stream;
   kern_t k = pick_kernel(c->p, c->block);
@@ -703,4 +726,27 @@ extern "C" int pk_peakon_suite(pk_ctx* c, const double* u, const int32_t* idx, c
   pk_peakon_suite_kernel<<<c->cfg.R, 128, 0, (cudaStream_t)stream>>>(u, idx, fail_step, c->p.ne, c->p.h, vals, ids);
   CK(c, cudaGetLastError());
   return 0;
+}
+
+// Profiling builds (-DPK_PROFILE) only: per-phase cycle buckets of the last launches, [R,16] host copy.
+extern "C" int pk_profile_read(pk_ctx* c, long long* host_out) {
+  if (!c) return -1;
+#ifdef PK_PROFILE
+  if (!c->d_prof) return fail(c, "no profile yet");
+  CK(c, cudaMemcpy(host_out, c->d_prof, sizeof(long long) * 16 * c->cfg.R, cudaMemcpyDeviceToHost));
+  return 0;
+#else
+  (void)host_out;
+  return fail(c, "library built without PK_PROFILE");
+#endif
+}
+extern "C" int pk_profile_enable(pk_ctx* c) {
+  if (!c) return -1;
+#ifdef PK_PROFILE
+  if (!c->d_prof) { CK(c, cudaMalloc(&c->d_prof, sizeof(long long) * 16 * c->cfg.R)); }
+  CK(c, cudaMemset(c->d_prof, 0, sizeof(long long) * 16 * c->cfg.R));
+  return 0;
+#else
+  return fail(c, "library built without PK_PROFILE");
+#endif
 }

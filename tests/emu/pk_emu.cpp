@@ -32,6 +32,7 @@ struct EmuExec {
     else for (int t = T - 1; t >= 0; --t) f(t, T);
   }
   void sync() {}
+  void tick(int) {}
   template <class F> void one(F f) { f(); }
   template <class F> void allreduce3(F f, double* out) {
     out[0] = out[1] = out[2] = 0.0;
