@@ -53,13 +53,13 @@ PK_HD int row_slot(const Params& p, int i) {
 }
 
 // same with a compile-time M (constant divisions)
-template <int M>
+template <int M, int TT = 0>
 PK_HD int row_slot_c(const Params& p, int i) {
   const int big = p.rem * M;
   int t, j;
   if (i < big) { t = i / M; j = i - t * M; }
   else { const int k = i - big; const int q = k / (M - 1); t = p.rem + q; j = k - q * (M - 1); }
-  return j * p.T + t;
+  return j * (TT > 0 ? TT : p.T) + t;
 }
 
 struct NodeS { double a, v, w, F, G, x, y; };
@@ -126,9 +126,12 @@ PK_HD void mva2(const double* A, const double* x, double* y) {
   y[0] += A[0] * x[0] + A[1] * x[1]; y[1] += A[2] * x[0] + A[3] * x[1];
 }
 
-template <int M, int MODE>
+// TT > 0: number of threads per realisation known at compile time (constant-folds the shared-memory
+// address arithmetic); TT == 0: read it from Params.
+template <int M, int MODE, int TT = 0>
 struct Thread {
   enum { NI = M - 2 };
+  static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
   // geometry
   int t, m, s, ext, tl, tr, ml, active;
   // level-1 factors of the interior block (interior row k <-> chunk row k+2)
@@ -153,10 +156,10 @@ struct Thread {
   double Xs;                      // NOISE_SCALAR: dXi value of this step
 
   PK_HD void init(const Params& p, int tid) {
-    t = tid; active = (tid < p.T);
+    t = tid; active = (tid < TN(p));
     const int tt = active ? tid : 0;
     m = chunk_rows(p, tt); s = chunk_start(p, tt); ext = (m == M);
-    tl = (tt + p.T - 1) & (p.T - 1); tr = (tt + 1) & (p.T - 1);
+    tl = (tt + TN(p) - 1) & (TN(p) - 1); tr = (tt + 1) & (TN(p) - 1);
     ml = chunk_rows(p, tl);
     fn2 = sn2 = xn2 = 0.0; Xs = 0.0;
   }
@@ -189,10 +192,10 @@ struct Thread {
   }
 
   // ---- smem index helpers -------------------------------------------------------------
-  PK_HD int idx(const Params& p, int j) const { return j * p.T + t; }
+  PK_HD int idx(const Params& p, int j) const { return j * TN(p) + t; }
   // node with local index j in [-1, m]: own rows, last row of the left chunk, first row of the right chunk
   PK_HD int nidx(const Params& p, int j) const {
-    return j < 0 ? (ml - 1) * p.T + tl : (j < m ? j * p.T + t : tr);
+    return j < 0 ? (ml - 1) * TN(p) + tl : (j < m ? j * TN(p) + t : tr);
   }
 
   PK_HD void load_node(const Params& p, const Shared& sh, int j, NodeS& n) const {
@@ -292,8 +295,8 @@ struct Thread {
       sp0[0] = p.hm2; sp0[1] = p.hm1 + k.C0[0]; sp0[2] = p.hm0 + k.C0[1]; sp0[3] = p.hm1 + k.C0[2]; sp0[4] = p.hm2;
       sb0 = -k.Q0;
       // publish what the left neighbour's last row needs from my first node
-      sh.xb[14 * p.T + t] = k.Cp[0]; sh.xb[15 * p.T + t] = k.Cp[1]; sh.xb[16 * p.T + t] = k.Cp[2];
-      sh.xb[17 * p.T + t] = k.Qp;
+      sh.xb[14 * TN(p) + t] = k.Cp[0]; sh.xb[15 * TN(p) + t] = k.Cp[1]; sh.xb[16 * TN(p) + t] = k.Cp[2];
+      sh.xb[17 * TN(p) + t] = k.Qp;
     } else {
       finish_row(p, n - 1, k.Cp, k.Qp);
     }
@@ -344,12 +347,12 @@ struct Thread {
     if (ext) stream(p, sh, M);
     // last row (m-1): Cp,Qp come from the right neighbour's first node
     double cp[3];
-    cp[0] = sh.xb[14 * p.T + tr]; cp[1] = sh.xb[15 * p.T + tr]; cp[2] = sh.xb[16 * p.T + tr];
-    const double qp = sh.xb[17 * p.T + tr];
+    cp[0] = sh.xb[14 * TN(p) + tr]; cp[1] = sh.xb[15 * TN(p) + tr]; cp[2] = sh.xb[16 * TN(p) + tr];
+    const double qp = sh.xb[17 * TN(p) + tr];
     if (ext) finish_row(p, M - 1, cp, qp); else finish_row(p, M - 2, cp, qp);
     // publish my last node's Cm,Qm for the right neighbour's separator row 0
-    sh.xb[10 * p.T + t] = wCm1[0]; sh.xb[11 * p.T + t] = wCm1[1]; sh.xb[12 * p.T + t] = wCm1[2];
-    sh.xb[13 * p.T + t] = wQm1;
+    sh.xb[10 * TN(p) + t] = wCm1[0]; sh.xb[11 * TN(p) + t] = wCm1[1]; sh.xb[12 * TN(p) + t] = wCm1[2];
+    sh.xb[13 * TN(p) + t] = wQm1;
 
     // back-substitute the five columns  x_I = y + Wn1 xs0 + Wn2 xs1 + Vn1 xR0 + Vn2 xR1
     const int nI = m - 2;
@@ -374,16 +377,16 @@ struct Thread {
       }
     }
     // slots 0..9: tips at the LAST two interior rows, read by the right neighbour
-    sh.xb[0 * p.T + t] = L2a[0]; sh.xb[1 * p.T + t] = L2b[0];
-    sh.xb[2 * p.T + t] = L2a[1]; sh.xb[3 * p.T + t] = L2a[2];
-    sh.xb[4 * p.T + t] = L2b[1]; sh.xb[5 * p.T + t] = L2b[2];
-    sh.xb[6 * p.T + t] = L2a[3]; sh.xb[7 * p.T + t] = L2a[4];
-    sh.xb[8 * p.T + t] = L2b[3]; sh.xb[9 * p.T + t] = L2b[4];
+    sh.xb[0 * TN(p) + t] = L2a[0]; sh.xb[1 * TN(p) + t] = L2b[0];
+    sh.xb[2 * TN(p) + t] = L2a[1]; sh.xb[3 * TN(p) + t] = L2a[2];
+    sh.xb[4 * TN(p) + t] = L2b[1]; sh.xb[5 * TN(p) + t] = L2b[2];
+    sh.xb[6 * TN(p) + t] = L2a[3]; sh.xb[7 * TN(p) + t] = L2a[4];
+    sh.xb[8 * TN(p) + t] = L2b[3]; sh.xb[9 * TN(p) + t] = L2b[4];
   }
 
   // ---- phase B1: build the reduced (Schur) block row of my separator pair -------------------
   PK_HD void reduce_build(const Params& p, const Shared& sh) {
-    const int T = p.T;
+    const int T = TN(p);
     const double yL[2] = {sh.xb[0 * T + tl], sh.xb[1 * T + tl]};
     const double WL[4] = {sh.xb[2 * T + tl], sh.xb[3 * T + tl], sh.xb[4 * T + tl], sh.xb[5 * T + tl]};
     const double VL[4] = {sh.xb[6 * T + tl], sh.xb[7 * T + tl], sh.xb[8 * T + tl], sh.xb[9 * T + tl]};
@@ -407,7 +410,7 @@ struct Thread {
 
   // write my block row (L, U, D^-1, r) to the exchange slots 0..13
   PK_HD void reduce_publish(const Params& p, const Shared& sh) {
-    const int T = p.T;
+    const int T = TN(p);
     double Di[4]; inv2(Db, Di);
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
@@ -418,7 +421,7 @@ struct Thread {
 
   // one parallel-cyclic-reduction step with stride d (reads only)
   PK_HD void pcr_step(const Params& p, const Shared& sh, int d) {
-    const int T = p.T;
+    const int T = TN(p);
     const int ql = (t + T - d) & (T - 1), qr = (t + d) & (T - 1);
     double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
     PK_UNROLL
@@ -440,7 +443,7 @@ struct Thread {
 
   // last level: rows t and t+T/2 form a closed 2-block system
   PK_HD void pcr_final(const Params& p, const Shared& sh) {
-    const int T = p.T;
+    const int T = TN(p);
     const int q = (t + T / 2) & (T - 1);
     double Lq[4], Uq[4], Dq[4], rq[2];
     PK_UNROLL
@@ -465,7 +468,7 @@ struct Thread {
 
   // ---- phase C: interior solution with known separators --------------------------------------
   PK_HD void interior_solve(const Params& p, const Shared& sh) {
-    const int T = p.T;
+    const int T = TN(p);
     const int nI = m - 2;
     double xp1 = sh.xb[14 * T + tr], xp2 = sh.xb[15 * T + tr];
     du[0] = xs0; du[1] = xs1;
@@ -489,7 +492,7 @@ struct Thread {
     // Right-hand sides  f(uh) + f'(uh) e  and  g(uh) + g'(uh) e  with e = du/2 (the change of uh).
     // f is a homogeneous quadratic form in uh, g is linear in uh, hence exactly
     //    f(uh) + f'(uh) e = f(uh + e) - f(e),        g(uh) + g'(uh) e = g(uh + e).
-    const int T = p.T;
+    const int T = TN(p);
     double a0, x0 = 0.0, y0 = 0.0, e0;
     {
       const int i = nidx(p, -1);
@@ -608,7 +611,7 @@ struct Thread {
 
 // Noise fields of this step: dXi = sum_k dW_k xi_k etc. (stochastic_functions.py:229-234).
 // Block-wide loop in natural node order: coalesced table reads, scattered into the chunk layout.
-template <int M, int MODE>
+template <int M, int MODE, int TT = 0>
 PK_HD void fill_noise_rows(const Params& p, const Shared& sh, const double* xi, const double* xi_x,
                            const double* xi_xx, int tid, int nth) {
   if (MODE == NOISE_SCALAR) return;
@@ -635,7 +638,7 @@ PK_HD void fill_noise_rows(const Params& p, const Shared& sh, const double* xi, 
     for (int j = 0; j < NB; ++j) {
       const int g = base + j * nth;
       if (g < p.ne) {
-        const int i = row_slot_c<M>(p, g);
+        const int i = row_slot_c<M, TT>(p, g);
         sh.X[i] = X[j];
         if (MODE == NOISE_FULL) { sh.Xx[i] = Xx[j]; sh.Xxx[i] = Xxx[j]; }
       }
@@ -718,7 +721,7 @@ PK_HD int snes_test(const Params& p, int it, const double* nrm, double& fnorm0, 
   return 0;
 }
 
-template <int M, int MODE, class Exec, class Th>
+template <int M, int MODE, int TT, class Exec, class Th>
 PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& io) {
   int failed = io.fail_step[io.r];
   int its_last = 0, its_total = io.its_total[io.r], reason = 0;
@@ -727,7 +730,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
     ex.each([&](Th& th) { th.kill_all(); });
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
     ex.each([&](Th& th) {
-      for (int k = th.t; k < p.nxi; k += p.T) {
+      for (int k = th.t; k < p.nxi; k += (TT > 0 ? TT : p.T)) {
         const long long o = ((long long)n * io.R + io.r) * p.nxi + k;
         double w;
         if (io.dW_in) {
@@ -745,7 +748,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
     ex.tick(0);
     if (failed >= 0) continue;
     if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
-    else ex.each_tid([&](int tid, int nth) { fill_noise_rows<M, MODE>(p, sh, io.xi, io.xi_x, io.xi_xx, tid, nth); });
+    else ex.each_tid([&](int tid, int nth) { fill_noise_rows<M, MODE, TT>(p, sh, io.xi, io.xi_x, io.xi_xx, tid, nth); });
     ex.sync();
     ex.tick(1);
 
@@ -777,7 +780,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
       ex.each([&](Th& th) { th.reduce_publish(p, sh); });
       ex.sync();
       ex.tick(6);
-      for (int d = 1; d < p.T / 2; d *= 2) {
+      for (int d = 1; d < (TT > 0 ? TT : p.T) / 2; d *= 2) {
         ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
         ex.sync();
         ex.each([&](Th& th) { th.reduce_publish(p, sh); });

@@ -23,9 +23,9 @@ using namespace pk;
 // ------------------------------------------------------------------------------------------------
 // AA ("all active") is true for every launch with T >= 32 chunks: then no thread of the block is idle and
 // the phase calls are unconditional, which lets the compiler see the per-thread arrays die between phases.
-template <int M, int MODE, bool AA>
+template <int M, int MODE, bool AA, int TT>
 struct GpuExec {
-  typedef Thread<M, MODE> Th;
+  typedef Thread<M, MODE, TT> Th;
   Th& th;
   double* red;          // [2][3*nw] reduction / scan scratch in shared memory, used alternately (ping-pong)
   int flip;             // so that a collective needs one barrier only: the area written by collective k
@@ -138,17 +138,18 @@ struct StepArgs {
 
 template <int MODE> struct NArr { enum { n = (MODE == NOISE_FULL) ? 7 : (MODE == NOISE_X ? 4 : 3) }; };
 
-template <int M, int MODE, int TB, int MINB>
+template <int M, int MODE, int TB, int MINB, int TT>
 __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int n = p.T * M;
+  const int Tn = TT > 0 ? TT : p.T;
+  const int n = Tn * M;
   Shared sh;
   sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
   double* nxt = smem + 3 * n;
   if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
   else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
-  sh.xb = nxt; nxt += XB_SLOTS * p.T;
+  sh.xb = nxt; nxt += XB_SLOTS * Tn;
   double* red = nxt; nxt += 6 * (blockDim.x >> 5);
   sh.dW = nxt;
 
@@ -156,15 +157,15 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   const long long off = (long long)r * p.ne;
   // coalesced global reads, scattered into the chunk-interleaved shared layout
   for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
-    const int sl = row_slot_c<M>(p, i);
+    const int sl = row_slot_c<M, TT>(p, i);
     sh.U0[sl] = a.u[off + i]; sh.U1[sl] = a.u1[off + i]; sh.F[sl] = a.dF[off + i];
     if (MODE == NOISE_FULL) sh.G[sl] = a.dG[off + i];
   }
   __syncthreads();
 
-  Thread<M, MODE> th;
+  Thread<M, MODE, TT> th;
   th.init(p, threadIdx.x);
-  GpuExec<M, MODE, (TB > 32)> ex(th, red);
+  GpuExec<M, MODE, (TB > 32), TT> ex(th, red);
 #ifdef PK_PROFILE
   __shared__ long long tb[16];
   if (threadIdx.x < 16) tb[threadIdx.x] = 0;
@@ -175,14 +176,14 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
   io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
-  run_steps<M, MODE, GpuExec<M, MODE, (TB > 32)>, Thread<M, MODE> >(ex, p, sh, io);
+  run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT>, Thread<M, MODE, TT> >(ex, p, sh, io);
   __syncthreads();
 #ifdef PK_PROFILE
   if (a.prof && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];
 #endif
 
   for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
-    const int sl = row_slot_c<M>(p, i);
+    const int sl = row_slot_c<M, TT>(p, i);
     a.u[off + i] = sh.U0[sl]; a.u1[off + i] = sh.U1[sl]; a.dF[off + i] = sh.F[sl];
     if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[sl];
   }
@@ -489,14 +490,15 @@ typedef void (*kern_t)(const Params, const StepArgs);
 
 static int g_minb = 0;   // PK_MINB env: resident CTAs/SM the 128-thread kernel is compiled for (2, 3 or 4)
 template <int M, int MODE> static kern_t pick_tb(int block, int T) {
-  if (T < 32) return pk_step_kernel<M, MODE, 32, 1>;      // tiny meshes: some lanes of the single warp idle
-  if (block <= 128) {
-    if (g_minb == 3) return pk_step_kernel<M, MODE, 128, 3>;
-    if (g_minb == 4) return pk_step_kernel<M, MODE, 128, 4>;
-    return pk_step_kernel<M, MODE, 128, 2>;
+  if (T < 32) return pk_step_kernel<M, MODE, 32, 1, 0>;    // tiny meshes: some lanes of the single warp idle
+  if (T == 128) {
+    if (g_minb == 2) return pk_step_kernel<M, MODE, 128, 2, 128>;
+    if (g_minb == 4) return pk_step_kernel<M, MODE, 128, 4, 128>;
+    return pk_step_kernel<M, MODE, 128, 3, 128>;
   }
-  if (block <= 256) return pk_step_kernel<M, MODE, 256, 1>;
-  return pk_step_kernel<M, MODE, 512, 1>;
+  if (block <= 128) return pk_step_kernel<M, MODE, 128, 2, 0>;
+  if (block <= 256) return pk_step_kernel<M, MODE, 256, 1, 256>;
+  return pk_step_kernel<M, MODE, 512, 1, 512>;
 }
 template <int M> static kern_t pick_mode(int mode, int block, int T) {
   switch (mode) {

@@ -80,7 +80,7 @@ static void run_one(const Params& p, StepIO io, double* u, double* u1, double* d
     sh.G[sl] = (MODE == NOISE_FULL) ? dG[off + i] : 0.0;
   }
   EmuExec<M, MODE> ex(p, order);
-  run_steps<M, MODE, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  run_steps<M, MODE, 0, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
   for (int i = 0; i < p.ne; ++i) {
     const int sl = row_slot(p, i);
     u[off + i] = sh.U0[sl]; u1[off + i] = sh.U1[sl]; dF[off + i] = sh.F[sl];
