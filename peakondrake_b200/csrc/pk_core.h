@@ -39,6 +39,11 @@ struct Shared {
   double *U0, *U1, *F, *G, *X, *Xx, *Xxx;
   double *xb;   // [18*T] exchange slots / PCR rows: slot c of thread t at c*T + t
   double *dW;   // [max(nxi,1)]
+  // flat index i = j*T + t (row j of chunk t).  One CTA per realisation: plain shared memory.
+  PK_HD double ld(const double* a, int i) const { return a[i]; }
+  PK_HD void st(double* a, int i, double v) const { a[i] = v; }
+  PK_HD double dw(int k) const { return dW[k]; }
+  PK_HD void set_dw(int k, double v) const { dW[k] = v; }
 };
 
 enum { XB_SLOTS = 18 };
@@ -198,15 +203,16 @@ struct Thread {
     return j < 0 ? (ml - 1) * TN(p) + tl : (j < m ? j * TN(p) + t : tr);
   }
 
-  PK_HD void load_node(const Params& p, const Shared& sh, int j, NodeS& n) const {
+  template <class SH>
+  PK_HD void load_node(const Params& p, const SH& sh, int j, NodeS& n) const {
     const int i = nidx(p, j);
-    const double u0 = sh.U0[i], u1 = sh.U1[i];
+    const double u0 = sh.ld(sh.U0, i), u1 = sh.ld(sh.U1, i);
     n.a = 0.5 * (u1 + u0);
     n.w = u1 - u0;
-    n.F = sh.F[i];
-    if (MODE == NOISE_FULL) { n.G = sh.G[i]; n.x = sh.Xx[i]; n.y = sh.Xxx[i]; }
+    n.F = sh.ld(sh.F, i);
+    if (MODE == NOISE_FULL) { n.G = sh.ld(sh.G, i); n.x = sh.ld(sh.Xx, i); n.y = sh.ld(sh.Xxx, i); }
     else { n.G = 0.0; n.x = 0.0; n.y = 0.0; }
-    const double X = (MODE == NOISE_SCALAR) ? Xs : sh.X[i];
+    const double X = (MODE == NOISE_SCALAR) ? Xs : sh.ld(sh.X, i);
     n.v = p.dt * n.a + X;
   }
 
@@ -285,7 +291,8 @@ struct Thread {
   }
 
   // One streaming iteration q >= 1: cell (q-1, q); finalises node q-1 and row q-2.
-  PK_HD void stream(const Params& p, const Shared& sh, int q) {
+  template <class SH>
+  PK_HD void stream(const Params& p, const SH& sh, int q) {
     load_node(p, sh, q, np);
     CellC<MODE> cc; cc.compute(p, n0, np);
     Packet k; node_packet(p, cc, k);           // node q-1
@@ -295,8 +302,8 @@ struct Thread {
       sp0[0] = p.hm2; sp0[1] = p.hm1 + k.C0[0]; sp0[2] = p.hm0 + k.C0[1]; sp0[3] = p.hm1 + k.C0[2]; sp0[4] = p.hm2;
       sb0 = -k.Q0;
       // publish what the left neighbour's last row needs from my first node
-      sh.xb[14 * TN(p) + t] = k.Cp[0]; sh.xb[15 * TN(p) + t] = k.Cp[1]; sh.xb[16 * TN(p) + t] = k.Cp[2];
-      sh.xb[17 * TN(p) + t] = k.Qp;
+      sh.st(sh.xb, 14 * TN(p) + t, k.Cp[0]); sh.st(sh.xb, 15 * TN(p) + t, k.Cp[1]); sh.st(sh.xb, 16 * TN(p) + t, k.Cp[2]);
+      sh.st(sh.xb, 17 * TN(p) + t, k.Qp);
     } else {
       finish_row(p, n - 1, k.Cp, k.Qp);
     }
@@ -305,7 +312,8 @@ struct Thread {
   }
 
   // ---- residual norm only (no Jacobian, no elimination): used when convergence is expected -----
-  PK_HD void residual_only(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void residual_only(const Params& p, const SH& sh) {
     fn2 = 0.0;
     NodeS a_, b_, c_;
     load_node(p, sh, -1, a_);
@@ -328,7 +336,8 @@ struct Thread {
   }
 
   // ---- phase A1: first two cells, publish first-node packet --------------------------------
-  PK_HD void assemble_begin(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void assemble_begin(const Params& p, const SH& sh) {
     fn2 = 0.0;
     kill_factors();
     load_node(p, sh, -1, nm);
@@ -341,18 +350,19 @@ struct Thread {
   }
 
   // ---- phase A2: rest of the chunk, interior LU, tips; publishes tips + last packet --------
-  PK_HD void assemble_finish(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void assemble_finish(const Params& p, const SH& sh) {
     PK_UNROLL
     for (int q = 2; q <= M - 1; ++q) stream(p, sh, q);
     if (ext) stream(p, sh, M);
     // last row (m-1): Cp,Qp come from the right neighbour's first node
     double cp[3];
-    cp[0] = sh.xb[14 * TN(p) + tr]; cp[1] = sh.xb[15 * TN(p) + tr]; cp[2] = sh.xb[16 * TN(p) + tr];
-    const double qp = sh.xb[17 * TN(p) + tr];
+    cp[0] = sh.ld(sh.xb, 14 * TN(p) + tr); cp[1] = sh.ld(sh.xb, 15 * TN(p) + tr); cp[2] = sh.ld(sh.xb, 16 * TN(p) + tr);
+    const double qp = sh.ld(sh.xb, 17 * TN(p) + tr);
     if (ext) finish_row(p, M - 1, cp, qp); else finish_row(p, M - 2, cp, qp);
     // publish my last node's Cm,Qm for the right neighbour's separator row 0
-    sh.xb[10 * TN(p) + t] = wCm1[0]; sh.xb[11 * TN(p) + t] = wCm1[1]; sh.xb[12 * TN(p) + t] = wCm1[2];
-    sh.xb[13 * TN(p) + t] = wQm1;
+    sh.st(sh.xb, 10 * TN(p) + t, wCm1[0]); sh.st(sh.xb, 11 * TN(p) + t, wCm1[1]); sh.st(sh.xb, 12 * TN(p) + t, wCm1[2]);
+    sh.st(sh.xb, 13 * TN(p) + t, wQm1);
 
     // back-substitute the five columns  x_I = y + Wn1 xs0 + Wn2 xs1 + Vn1 xR0 + Vn2 xR1
     const int nI = m - 2;
@@ -377,21 +387,22 @@ struct Thread {
       }
     }
     // slots 0..9: tips at the LAST two interior rows, read by the right neighbour
-    sh.xb[0 * TN(p) + t] = L2a[0]; sh.xb[1 * TN(p) + t] = L2b[0];
-    sh.xb[2 * TN(p) + t] = L2a[1]; sh.xb[3 * TN(p) + t] = L2a[2];
-    sh.xb[4 * TN(p) + t] = L2b[1]; sh.xb[5 * TN(p) + t] = L2b[2];
-    sh.xb[6 * TN(p) + t] = L2a[3]; sh.xb[7 * TN(p) + t] = L2a[4];
-    sh.xb[8 * TN(p) + t] = L2b[3]; sh.xb[9 * TN(p) + t] = L2b[4];
+    sh.st(sh.xb, 0 * TN(p) + t, L2a[0]); sh.st(sh.xb, 1 * TN(p) + t, L2b[0]);
+    sh.st(sh.xb, 2 * TN(p) + t, L2a[1]); sh.st(sh.xb, 3 * TN(p) + t, L2a[2]);
+    sh.st(sh.xb, 4 * TN(p) + t, L2b[1]); sh.st(sh.xb, 5 * TN(p) + t, L2b[2]);
+    sh.st(sh.xb, 6 * TN(p) + t, L2a[3]); sh.st(sh.xb, 7 * TN(p) + t, L2a[4]);
+    sh.st(sh.xb, 8 * TN(p) + t, L2b[3]); sh.st(sh.xb, 9 * TN(p) + t, L2b[4]);
   }
 
   // ---- phase B1: build the reduced (Schur) block row of my separator pair -------------------
-  PK_HD void reduce_build(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void reduce_build(const Params& p, const SH& sh) {
     const int T = TN(p);
-    const double yL[2] = {sh.xb[0 * T + tl], sh.xb[1 * T + tl]};
-    const double WL[4] = {sh.xb[2 * T + tl], sh.xb[3 * T + tl], sh.xb[4 * T + tl], sh.xb[5 * T + tl]};
-    const double VL[4] = {sh.xb[6 * T + tl], sh.xb[7 * T + tl], sh.xb[8 * T + tl], sh.xb[9 * T + tl]};
-    sp0[0] += sh.xb[10 * T + tl]; sp0[1] += sh.xb[11 * T + tl]; sp0[2] += sh.xb[12 * T + tl];
-    sb0 -= sh.xb[13 * T + tl];
+    const double yL[2] = {sh.ld(sh.xb, 0 * T + tl), sh.ld(sh.xb, 1 * T + tl)};
+    const double WL[4] = {sh.ld(sh.xb, 2 * T + tl), sh.ld(sh.xb, 3 * T + tl), sh.ld(sh.xb, 4 * T + tl), sh.ld(sh.xb, 5 * T + tl)};
+    const double VL[4] = {sh.ld(sh.xb, 6 * T + tl), sh.ld(sh.xb, 7 * T + tl), sh.ld(sh.xb, 8 * T + tl), sh.ld(sh.xb, 9 * T + tl)};
+    sp0[0] += sh.ld(sh.xb, 10 * T + tl); sp0[1] += sh.ld(sh.xb, 11 * T + tl); sp0[2] += sh.ld(sh.xb, 12 * T + tl);
+    sb0 -= sh.ld(sh.xb, 13 * T + tl);
     const double E[4] = {sp0[0], sp0[1], 0.0, sp1[0]};
     const double C[4] = {sp0[2], sp0[3], sp1[1], sp1[2]};
     const double Gc[4] = {sp0[4], 0.0, sp1[3], sp1[4]};
@@ -409,28 +420,30 @@ struct Thread {
   }
 
   // write my block row (L, U, D^-1, r) to the exchange slots 0..13
-  PK_HD void reduce_publish(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void reduce_publish(const Params& p, const SH& sh) {
     const int T = TN(p);
     double Di[4]; inv2(Db, Di);
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
-      sh.xb[c * T + t] = Lb[c]; sh.xb[(4 + c) * T + t] = Ub[c]; sh.xb[(8 + c) * T + t] = Di[c];
+      sh.st(sh.xb, c * T + t, Lb[c]); sh.st(sh.xb, (4 + c) * T + t, Ub[c]); sh.st(sh.xb, (8 + c) * T + t, Di[c]);
     }
-    sh.xb[12 * T + t] = rb[0]; sh.xb[13 * T + t] = rb[1];
+    sh.st(sh.xb, 12 * T + t, rb[0]); sh.st(sh.xb, 13 * T + t, rb[1]);
   }
 
   // one parallel-cyclic-reduction step with stride d (reads only)
-  PK_HD void pcr_step(const Params& p, const Shared& sh, int d) {
+  template <class SH>
+  PK_HD void pcr_step(const Params& p, const SH& sh, int d) {
     const int T = TN(p);
     const int ql = (t + T - d) & (T - 1), qr = (t + d) & (T - 1);
     double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
-      Ll[c] = sh.xb[c * T + ql]; Ul[c] = sh.xb[(4 + c) * T + ql]; Dl[c] = sh.xb[(8 + c) * T + ql];
-      Lr[c] = sh.xb[c * T + qr]; Ur[c] = sh.xb[(4 + c) * T + qr]; Dr[c] = sh.xb[(8 + c) * T + qr];
+      Ll[c] = sh.ld(sh.xb, c * T + ql); Ul[c] = sh.ld(sh.xb, (4 + c) * T + ql); Dl[c] = sh.ld(sh.xb, (8 + c) * T + ql);
+      Lr[c] = sh.ld(sh.xb, c * T + qr); Ur[c] = sh.ld(sh.xb, (4 + c) * T + qr); Dr[c] = sh.ld(sh.xb, (8 + c) * T + qr);
     }
-    rl[0] = sh.xb[12 * T + ql]; rl[1] = sh.xb[13 * T + ql];
-    rr[0] = sh.xb[12 * T + qr]; rr[1] = sh.xb[13 * T + qr];
+    rl[0] = sh.ld(sh.xb, 12 * T + ql); rl[1] = sh.ld(sh.xb, 13 * T + ql);
+    rr[0] = sh.ld(sh.xb, 12 * T + qr); rr[1] = sh.ld(sh.xb, 13 * T + qr);
     double al[4], ga[4];
     mm2(Lb, Dl, al); mm2(Ub, Dr, ga);
     PK_UNROLL
@@ -442,15 +455,16 @@ struct Thread {
   }
 
   // last level: rows t and t+T/2 form a closed 2-block system
-  PK_HD void pcr_final(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void pcr_final(const Params& p, const SH& sh) {
     const int T = TN(p);
     const int q = (t + T / 2) & (T - 1);
     double Lq[4], Uq[4], Dq[4], rq[2];
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
-      Lq[c] = sh.xb[c * T + q]; Uq[c] = sh.xb[(4 + c) * T + q]; Dq[c] = sh.xb[(8 + c) * T + q];
+      Lq[c] = sh.ld(sh.xb, c * T + q); Uq[c] = sh.ld(sh.xb, (4 + c) * T + q); Dq[c] = sh.ld(sh.xb, (8 + c) * T + q);
     }
-    rq[0] = sh.xb[12 * T + q]; rq[1] = sh.xb[13 * T + q];
+    rq[0] = sh.ld(sh.xb, 12 * T + q); rq[1] = sh.ld(sh.xb, 13 * T + q);
     double S[4], Sq[4], SD[4], A[4], Ai[4], rhs[2];
     PK_UNROLL
     for (int c = 0; c < 4; ++c) { S[c] = Lb[c] + Ub[c]; Sq[c] = Lq[c] + Uq[c]; A[c] = Db[c]; }
@@ -463,14 +477,15 @@ struct Thread {
     inv2(A, Ai);
     xs0 = Ai[0] * rhs[0] + Ai[1] * rhs[1];
     xs1 = Ai[2] * rhs[0] + Ai[3] * rhs[1];
-    sh.xb[14 * T + t] = xs0; sh.xb[15 * T + t] = xs1;
+    sh.st(sh.xb, 14 * T + t, xs0); sh.st(sh.xb, 15 * T + t, xs1);
   }
 
   // ---- phase C: interior solution with known separators --------------------------------------
-  PK_HD void interior_solve(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void interior_solve(const Params& p, const SH& sh) {
     const int T = TN(p);
     const int nI = m - 2;
-    double xp1 = sh.xb[14 * T + tr], xp2 = sh.xb[15 * T + tr];
+    double xp1 = sh.ld(sh.xb, 14 * T + tr), xp2 = sh.ld(sh.xb, 15 * T + tr);
     du[0] = xs0; du[1] = xs1;
     PK_UNROLL
     for (int k = NI - 1; k >= 0; --k) {
@@ -483,12 +498,13 @@ struct Thread {
         du[k + 2] = 0.0;
       }
     }
-    sh.xb[16 * T + t] = ext ? du[M - 1] : du[M - 2];   // my last row, for the right neighbour
+    sh.st(sh.xb, 16 * T + t, ext ? du[M - 1] : du[M - 2]);   // my last row, for the right neighbour
   }
 
   // ---- phase D1: Helmholtz right-hand sides f + f'/2 du, g + g'/2 du; causal local pass ------
   // returns the chunk aggregate (value with zero carry-in) in cF, cG and the multiplier A = rho^m
-  PK_HD void helm_causal_local(const Params& p, const Shared& sh, double& A, double& cF, double& cG) {
+  template <class SH>
+  PK_HD void helm_causal_local(const Params& p, const SH& sh, double& A, double& cF, double& cG) {
     // Right-hand sides  f(uh) + f'(uh) e  and  g(uh) + g'(uh) e  with e = du/2 (the change of uh).
     // f is a homogeneous quadratic form in uh, g is linear in uh, hence exactly
     //    f(uh) + f'(uh) e = f(uh + e) - f(e),        g(uh) + g'(uh) e = g(uh + e).
@@ -496,9 +512,9 @@ struct Thread {
     double a0, x0 = 0.0, y0 = 0.0, e0;
     {
       const int i = nidx(p, -1);
-      a0 = 0.5 * (sh.U0[i] + sh.U1[i]);
-      if (MODE == NOISE_FULL) { x0 = sh.Xx[i]; y0 = sh.Xxx[i]; }
-      e0 = 0.5 * sh.xb[16 * T + tl];           // half the increment of the left neighbour's last row
+      a0 = 0.5 * (sh.ld(sh.U0, i) + sh.ld(sh.U1, i));
+      if (MODE == NOISE_FULL) { x0 = sh.ld(sh.Xx, i); y0 = sh.ld(sh.Xxx, i); }
+      e0 = 0.5 * sh.ld(sh.xb, 16 * T + tl);           // half the increment of the left neighbour's last row
     }
     double prevFR = 0.0, prevGR = 0.0;
     PK_UNROLL
@@ -507,10 +523,10 @@ struct Thread {
     for (int q = 0; q <= M; ++q) {
       if (q <= m) {
         const int i = nidx(p, q);
-        const double a1 = 0.5 * (sh.U0[i] + sh.U1[i]);
+        const double a1 = 0.5 * (sh.ld(sh.U0, i) + sh.ld(sh.U1, i));
         double x1 = 0.0, y1 = 0.0;
-        if (MODE == NOISE_FULL) { x1 = sh.Xx[i]; y1 = sh.Xxx[i]; }
-        const double e1 = 0.5 * ((q < m) ? du[q < M ? q : M - 1] : sh.xb[14 * T + tr]);
+        if (MODE == NOISE_FULL) { x1 = sh.ld(sh.Xx, i); y1 = sh.ld(sh.Xxx, i); }
+        const double e1 = 0.5 * ((q < m) ? du[q < M ? q : M - 1] : sh.ld(sh.xb, 14 * T + tr));
         const double b0 = a0 + e0, b1 = a1 + e1;            // uh + e at the two nodes of the cell
         const double db = b1 - b0, de = e1 - e0;
         const double qb = b0 * b0 + b1 * b1, pb = b0 * b1, qe = e0 * e0 + e1 * e1, pe = e0 * e1;
@@ -567,7 +583,8 @@ struct Thread {
   }
 
   // ---- phase D3: apply anticausal carry, write the new iterate, accumulate |delta|^2, |w1|^2 ---
-  PK_HD void helm_finish_update(const Params& p, const Shared& sh, double inF, double inG) {
+  template <class SH>
+  PK_HD void helm_finish_update(const Params& p, const SH& sh, double inF, double inG) {
     sn2 = 0.0; xn2 = 0.0;
     // x_j = xl_j + rho^(m-j) * carry
     double pwv[M];
@@ -580,15 +597,15 @@ struct Thread {
     for (int j = 0; j < M; ++j) {
       if (j < m) {
         const int i = idx(p, j);
-        const double u1n = sh.U1[i] + du[j];
+        const double u1n = sh.ld(sh.U1, i) + du[j];
         const double Fn = hF[j] + pwv[j] * inF;
-        const double dFv = Fn - sh.F[i];
-        sh.U1[i] = u1n; sh.F[i] = Fn;
+        const double dFv = Fn - sh.ld(sh.F, i);
+        sh.st(sh.U1, i, u1n); sh.st(sh.F, i, Fn);
         double s2 = du[j] * du[j] + dFv * dFv, x2 = u1n * u1n + Fn * Fn;
         if (MODE == NOISE_FULL) {
           const double Gn = hG[j] + pwv[j] * inG;
-          const double dGv = Gn - sh.G[i];
-          sh.G[i] = Gn;
+          const double dGv = Gn - sh.ld(sh.G, i);
+          sh.st(sh.G, i, Gn);
           s2 += dGv * dGv; x2 += Gn * Gn;
         }
         sn2 += s2; xn2 += x2;
@@ -597,26 +614,29 @@ struct Thread {
   }
 
   // ---- accept the step: u <- u1 (equations.py:195) ----------------------------------------------
-  PK_HD void accept(const Params& p, const Shared& sh) {
+  template <class SH>
+  PK_HD void accept(const Params& p, const SH& sh) {
     PK_UNROLL
     for (int j = 0; j < M; ++j)
-      if (j < m) { const int i = idx(p, j); sh.U0[i] = sh.U1[i]; }
+      if (j < m) { const int i = idx(p, j); sh.st(sh.U0, i, sh.ld(sh.U1, i)); }
   }
 
   // ---- NOISE_SCALAR: the dXi value of this step ------------------------------------------------
-  PK_HD void set_scalar_noise(const Params& p, const Shared& sh) {
-    Xs = (p.nxi > 0) ? sh.dW[0] * p.xi_const : 0.0;
+  template <class SH>
+  PK_HD void set_scalar_noise(const Params& p, const SH& sh) {
+    Xs = (p.nxi > 0) ? sh.dw(0) * p.xi_const : 0.0;
   }
 };
 
 // Noise fields of this step: dXi = sum_k dW_k xi_k etc. (stochastic_functions.py:229-234).
 // Block-wide loop in natural node order: coalesced table reads, scattered into the chunk layout.
-template <int M, int MODE, int TT = 0>
-PK_HD void fill_noise_rows(const Params& p, const Shared& sh, const double* xi, const double* xi_x,
-                           const double* xi_xx, int tid, int nth) {
+template <int M, int MODE, int TT, class SH>
+PK_HD void fill_noise_rows(const Params& p, const SH& sh, const double* xi, const double* xi_x,
+                           const double* xi_xx, int tid, int nth, int g0, int g1) {
+  // rows [g0, g1) are the ones this block owns (the whole mesh unless a cluster shares the realisation)
   if (MODE == NOISE_SCALAR) return;
   enum { NB = 4 };     // nodes in flight per thread: NB x 3 tables x (unrolled modes) independent loads
-  for (int base = tid; base < p.ne; base += NB * nth) {
+  for (int base = g0 + tid; base < g1; base += NB * nth) {
     double X[NB], Xx[NB], Xxx[NB];
     PK_UNROLL
     for (int j = 0; j < NB; ++j) { X[j] = 0.0; Xx[j] = 0.0; Xxx[j] = 0.0; }
@@ -624,11 +644,11 @@ PK_HD void fill_noise_rows(const Params& p, const Shared& sh, const double* xi, 
 #pragma unroll 4
 #endif
     for (int k = 0; k < p.nxi; ++k) {
-      const double w = sh.dW[k];
+      const double w = sh.dw(k);
       PK_UNROLL
       for (int j = 0; j < NB; ++j) {
         const int g = base + j * nth;
-        if (g < p.ne) {
+        if (g < g1) {
           X[j] += w * xi[k * p.ne + g];
           if (MODE == NOISE_FULL) { Xx[j] += w * xi_x[k * p.ne + g]; Xxx[j] += w * xi_xx[k * p.ne + g]; }
         }
@@ -637,10 +657,10 @@ PK_HD void fill_noise_rows(const Params& p, const Shared& sh, const double* xi, 
     PK_UNROLL
     for (int j = 0; j < NB; ++j) {
       const int g = base + j * nth;
-      if (g < p.ne) {
+      if (g < g1) {
         const int i = row_slot_c<M, TT>(p, g);
-        sh.X[i] = X[j];
-        if (MODE == NOISE_FULL) { sh.Xx[i] = Xx[j]; sh.Xxx[i] = Xxx[j]; }
+        sh.st(sh.X, i, X[j]);
+        if (MODE == NOISE_FULL) { sh.st(sh.Xx, i, Xx[j]); sh.st(sh.Xxx, i, Xxx[j]); }
       }
     }
   }
@@ -684,7 +704,9 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 //                      that get() returns, in thread order 0..T-1; put() receives the value entering
 //                      its thread and returns the maps of the following reverse scan
 //   scan_rev(fin)      the reverse cyclic scan (order T-1..0); fin() receives the entering value
-//   each_tid(f)        run f(tid, nthreads) on every thread of the block (also the idle ones)
+//   each_tid(f)        run f(tid, nthreads, leader, g0, g1) on every thread of every block working on the
+//                      realisation: block-local thread id / count, whether the block is the cluster
+//                      leader, and the range of mesh rows the block owns
 //   one(f)             run f() once (thread 0)
 //   tick(id)           profiling hook (no-op unless built with -DPK_PROFILE): time since the last tick -> bucket id
 // ------------------------------------------------------------------------------------------------
@@ -721,16 +743,16 @@ PK_HD int snes_test(const Params& p, int it, const double* nrm, double& fnorm0, 
   return 0;
 }
 
-template <int M, int MODE, int TT, class Exec, class Th>
-PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& io) {
+template <int M, int MODE, int TT, class Exec, class Th, class SH>
+PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) {
   int failed = io.fail_step[io.r];
   int its_last = 0, its_total = io.its_total[io.r], reason = 0;
   int expect = 2;     // iteration at which convergence is expected: there only the residual is evaluated first
   for (int n = 0; n < io.nsteps; ++n) {
     ex.each([&](Th& th) { th.kill_all(); });
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
-    ex.each([&](Th& th) {
-      for (int k = th.t; k < p.nxi; k += (TT > 0 ? TT : p.T)) {
+    ex.each_tid([&](int tid, int nth, bool leader, int, int) {
+      for (int k = tid; k < p.nxi; k += nth) {
         const long long o = ((long long)n * io.R + io.r) * p.nxi + k;
         double w;
         if (io.dW_in) {
@@ -740,15 +762,16 @@ PK_HD void run_steps(Exec& ex, const Params& p, const Shared& sh, const StepIO& 
           for (int j = 0; j < p.nupd; ++j)
             w += philox_normal(io.seed, io.rid, (unsigned)(io.step0 + n), (unsigned)k, (unsigned)j) * p.sdt;
         }
-        sh.dW[k] = w;
-        if (io.dW_out) io.dW_out[o] = w;
+        sh.set_dw(k, w);
+        if (leader && io.dW_out) io.dW_out[o] = w;
       }
     });
     ex.sync();
     ex.tick(0);
     if (failed >= 0) continue;
     if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
-    else ex.each_tid([&](int tid, int nth) { fill_noise_rows<M, MODE, TT>(p, sh, io.xi, io.xi_x, io.xi_xx, tid, nth); });
+    else ex.each_tid([&](int tid, int nth, bool, int g0, int g1) {
+      fill_noise_rows<M, MODE, TT>(p, sh, io.xi, io.xi_x, io.xi_xx, tid, nth, g0, g1); });
     ex.sync();
     ex.tick(1);
 

@@ -114,8 +114,9 @@ class EnsembleIntegrator(object):
     @property
     def layout(self):
         T, M, rem, smem = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32())
-        self.lib.pk_get_layout(self.ctx, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem), ctypes.byref(smem))
-        return dict(threads=T.value, rows_per_thread=M.value, rem=rem.value, smem_bytes=smem.value)
+        c = self.lib.pk_get_layout(self.ctx, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem), ctypes.byref(smem))
+        return dict(threads=T.value, rows_per_thread=M.value, rem=rem.value, smem_bytes=smem.value,
+                    ctas_per_realisation=max(1, c))
 
     @property
     def step_counter(self):

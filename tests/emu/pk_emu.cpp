@@ -14,22 +14,47 @@
 
 using namespace pk;
 
+// Emulated thread-block cluster: the flat index space j*T + t is split over C "CTAs" of Tc threads
+// exactly like SharedCluster in pk_lib.cu (same decode); `cur` is the CTA of the running thread and
+// every store is checked to be local.
+struct EmuSharedCluster {
+  double *U0, *U1, *F, *G, *X, *Xx, *Xxx, *xb, *dW;    // array ids: offsets into every CTA's private buffer
+  std::vector<std::vector<double> >* bufs;
+  int Tc, lgTc, lgT, nxi_;
+  int* cur;
+  int* bad;
+  double* at(const double* a, int i, bool store) const {
+    const int tg = i & ((1 << lgT) - 1), j = i >> lgT;
+    const int owner = tg >> lgTc;
+    if (store && owner != *cur) ++*bad;
+    return &(*bufs)[owner][(a - (const double*)0) + (size_t)(j << lgTc) + (tg & (Tc - 1))];
+  }
+  double ld(const double* a, int i) const { return *at(a, i, false); }
+  void st(double* a, int i, double v) const { *at(a, i, true) = v; }
+  double dw(int k) const { return (*bufs)[*cur][(dW - (double*)0) + k]; }
+  void set_dw(int k, double v) const { (*bufs)[*cur][(dW - (double*)0) + k] = v; }
+};
+
 template <int M, int MODE>
 struct EmuExec {
   typedef Thread<M, MODE> Th;
   std::vector<Th> th;
   int T, order;
   std::vector<double> A, c0, c1;
-  EmuExec(const Params& p, int order_) : th(p.T), T(p.T), order(order_), A(p.T), c0(p.T), c1(p.T) {
+  EmuExec(const Params& p, int order_, int C_ = 1) : th(p.T), T(p.T), order(order_), A(p.T), c0(p.T), c1(p.T), ne(p.ne), C(C_), Tc(p.T / C_), cur(0), pp(p) {
     for (int t = 0; t < T; ++t) th[t].init(p, t);
   }
   template <class F> void each(F f) {
-    if (order == 0) for (int t = 0; t < T; ++t) f(th[t]);
-    else for (int t = T - 1; t >= 0; --t) f(th[t]);
+    for (int k = 0; k < T; ++k) { const int t = order == 0 ? k : T - 1 - k; cur = t / Tc; f(th[t]); }
   }
+  int ne, C, Tc; int cur; Params pp;
   template <class F> void each_tid(F f) {
-    if (order == 0) for (int t = 0; t < T; ++t) f(t, T);
-    else for (int t = T - 1; t >= 0; --t) f(t, T);
+    for (int k = 0; k < T; ++k) {
+      const int t = order == 0 ? k : T - 1 - k;
+      const int c = t / Tc; cur = c;
+      const int g0 = chunk_start(pp, c * Tc), g1 = (c == C - 1) ? ne : chunk_start(pp, (c + 1) * Tc);
+      f(t % Tc, Tc, c == 0, g0, g1);
+    }
   }
   void sync() {}
   void tick(int) {}
@@ -66,6 +91,35 @@ struct EmuExec {
 };
 
 template <int M, int MODE>
+static int run_one_cluster(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order, int C) {
+  const int Tc = p.T / C, n = Tc * p.M;
+  std::vector<std::vector<double> > bufs(C, std::vector<double>(7 * n + XB_SLOTS * Tc + (p.nxi > 0 ? p.nxi : 1), 0.0));
+  EmuExec<M, MODE> ex(p, order, C);
+  int bad = 0;
+  EmuSharedCluster sh;
+  double* z = (double*)0;
+  sh.U0 = z; sh.U1 = z + n; sh.F = z + 2 * n; sh.G = z + 3 * n; sh.X = z + 4 * n; sh.Xx = z + 5 * n; sh.Xxx = z + 6 * n;
+  sh.xb = z + 7 * n; sh.dW = z + 7 * n + XB_SLOTS * Tc;
+  sh.bufs = &bufs; sh.Tc = Tc; sh.nxi_ = p.nxi; sh.cur = &ex.cur; sh.bad = &bad;
+  sh.lgTc = 0; while ((1 << sh.lgTc) < Tc) ++sh.lgTc;
+  sh.lgT = 0; while ((1 << sh.lgT) < p.T) ++sh.lgT;
+  const long long off = (long long)io.r * p.ne;
+  for (int i = 0; i < p.ne; ++i) {
+    const int sl = row_slot(p, i);
+    ex.cur = (sl & (p.T - 1)) / Tc;
+    sh.st(sh.U0, sl, u[off + i]); sh.st(sh.U1, sl, u1[off + i]); sh.st(sh.F, sl, dF[off + i]);
+    sh.st(sh.G, sl, (MODE == NOISE_FULL) ? dG[off + i] : 0.0);
+  }
+  run_steps<M, MODE, 0, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  for (int i = 0; i < p.ne; ++i) {
+    const int sl = row_slot(p, i);
+    u[off + i] = sh.ld(sh.U0, sl); u1[off + i] = sh.ld(sh.U1, sl); dF[off + i] = sh.ld(sh.F, sl);
+    if (MODE == NOISE_FULL) dG[off + i] = sh.ld(sh.G, sl);
+  }
+  return bad;
+}
+
+template <int M, int MODE>
 static void run_one(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
   const int n = p.T * p.M;
   std::vector<double> buf(7 * n + XB_SLOTS * p.T + (p.nxi > 0 ? p.nxi : 1), 0.0);
@@ -88,14 +142,26 @@ static void run_one(const Params& p, StepIO io, double* u, double* u1, double* d
   }
 }
 
+static int g_emuC = 1, g_bad = 0;
 template <int M>
 static void run_mode(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
+  if (g_emuC > 1) {
+    switch (p.mode) {
+      case NOISE_SCALAR: g_bad += run_one_cluster<M, NOISE_SCALAR>(p, io, u, u1, dF, dG, order, g_emuC); break;
+      case NOISE_X: g_bad += run_one_cluster<M, NOISE_X>(p, io, u, u1, dF, dG, order, g_emuC); break;
+      default: g_bad += run_one_cluster<M, NOISE_FULL>(p, io, u, u1, dF, dG, order, g_emuC); break;
+    }
+    return;
+  }
   switch (p.mode) {
     case NOISE_SCALAR: run_one<M, NOISE_SCALAR>(p, io, u, u1, dF, dG, order); break;
     case NOISE_X: run_one<M, NOISE_X>(p, io, u, u1, dF, dG, order); break;
     default: run_one<M, NOISE_FULL>(p, io, u, u1, dF, dG, order); break;
   }
 }
+// emulate a thread-block cluster of C CTAs per realisation (1 = off); returns the number of
+// non-local stores seen so far (must stay 0)
+extern "C" int pk_emu_set_cluster(int C) { g_emuC = C; return g_bad; }
 
 extern "C" int pk_emu_layout(int ne, int* T, int* M, int* rem) { return choose_layout(ne, T, M, rem) ? 0 : -1; }
 

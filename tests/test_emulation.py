@@ -101,3 +101,17 @@ def test_philox_generator_statistics_and_reproducibility():
         assert rel(u[k], ref['u']) <= TOL
     w = sum(L.pk_emu_philox_normal(9, 101, 3, 1, j) for j in range(4)) * np.sqrt(dt / 4)
     assert abs(r['dW'][3, 1, 1] - w) < 1e-16          # kernel scales each sub-draw, then sums
+
+
+@pytest.mark.parametrize('ne,C', [(1000, 2), (1000, 4), (250, 2), (2000, 8)])
+def test_cluster_layout_emulated(ne, C):
+    """Thread-block-cluster variant (large meshes): shared arrays distributed over C CTAs, foreign
+    rows read remotely, every store local -- same decode as SharedCluster in pk_lib.cu."""
+    L = lib()
+    try:
+        assert L.pk_emu_set_cluster(C) == 0
+        compare(ne, nsteps=3, nxi=2)
+        compare(ne, nsteps=2, fam='constant', nxi=1, ic='periodic_peakon', sigma=0.5)
+        assert L.pk_emu_set_cluster(1) == 0          # no non-local stores happened
+    finally:
+        L.pk_emu_set_cluster(1)

@@ -87,7 +87,9 @@ def test_large_single_cta_mesh_scalar_noise():
 def test_unsupported_mesh_raises_cleanly():
     from peakondrake_b200 import EnsembleIntegrator, _lib
     with pytest.raises(_lib.PkError):
-        EnsembleIntegrator(16384, 40.0, 1e-3, 2, num_Xis=4, sigma=0.1)     # needs the cluster path
+        EnsembleIntegrator(200000, 40.0, 1e-3, 2, num_Xis=4, sigma=0.1)    # beyond the largest cluster layout
+    with pytest.raises(_lib.PkError):
+        EnsembleIntegrator(6, 40.0, 1e-3, 2)                               # fewer than 8 cells
     with pytest.raises(ValueError):
         EnsembleIntegrator(100, 40.0, 1e-3, 2, scheme='conforming')         # equations.py:147-148
     with pytest.raises(NotImplementedError):
@@ -241,3 +243,29 @@ def test_argmax_ties_take_lowest_index():
     assert idx[0, _lib.I_ARGMAX_U] == 5 and idx[1, _lib.I_ARGMAX_U] == 0
     for r in range(2):
         assert idx[r, _lib.I_ARGMAX_DU] == np.argmax(du[r]) and idx[r, _lib.I_ARGMIN_DU] == np.argmin(du[r])
+
+
+# ---- thread-block-cluster variant (one realisation per cluster of CTAs, DSMEM) -------------------
+@pytest.mark.parametrize('ne,C', [(1000, 2), (1000, 4), (2000, 8), (500, 2)])
+def test_cluster_variant_forced_on_small_meshes(ne, C, monkeypatch):
+    monkeypatch.setenv('PK_FORCE_CLUSTER', str(C))
+    assert run_case(ne, 3, 6, nxi=2) <= TOL
+    assert run_case(ne, 2, 4, ic='periodic_peakon', fam='constant', nxi=1, sigma=0.5) <= TOL
+
+
+def test_c4_fine_mesh_16384():
+    # BASELINE config 4 (shortened): steep front, ne=16384, constant noise, dt=5e-4
+    from peakondrake_b200 import EnsembleIntegrator
+    eng = EnsembleIntegrator(16384, 40.0, 5e-4, 2, num_Xis=1, Xi_family='constant', sigma=0.2)
+    assert eng.layout['ctas_per_realisation'] == 8 and eng.layout['threads'] == 2048
+    eng.close()
+    assert run_case(16384, 2, 4, ic='new_peak', fam='constant', nxi=1, sigma=0.2, dt=5e-4, peak_width=1 / 6) <= TOL
+
+
+def test_c5_fine_mesh_20000_large_noise():
+    # BASELINE config 5 (shortened): periodic peakon, ne=20000, sigma=1, dt=1e-2 (3 Newton iterations/step)
+    assert run_case(20000, 2, 3, ic='periodic_peakon', fam='constant', nxi=1, sigma=1.0, dt=1e-2) <= TOL
+
+
+def test_cluster_with_noise_tables_4096():
+    assert run_case(4096, 2, 4, nxi=4) <= TOL
