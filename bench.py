@@ -31,6 +31,7 @@ NE, LD, DT, NXI, SIGMA, IC = 1000, 40.0, 1e-3, 4, 0.2, 'proper_peak'
 R_PER_GPU = 1024
 STEPS_PER_LAUNCH = 50
 B_ALG = 16 * NE + 8 * NXI      # algorithmic bytes per realisation-step
+DRAM_TRAFFIC_PER_LAUNCH = 35.36e6   # bytes, ncu capture profiles/r1a_ncu_full_pk_step_kernel.csv
 METRIC = 'realisation_steps_per_sec'
 UNIT = 'realisation*steps/s'
 WORKLOAD = ('C2: stochastic CH hydrodynamic/midpoint, ne=1000, Ld=40, dt=1e-3, 4 sines sigma=0.2, '
@@ -55,6 +56,13 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index, self.samples, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -68,7 +76,7 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -80,7 +88,11 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for s in self.samples:
+        inside = [s for (ts, s) in self.samples
+                  if (self.t0 is None or ts >= self.t0) and (self.t1 is None or ts <= self.t1 + 0.05)]
+        if not inside:      # region shorter than the sampling period: fall back to every sample taken under load
+            inside = [s for (_, s) in self.samples]
+        for s in inside:
             f = [x.strip() for x in s.split(',')]
             if len(f) < 7:
                 continue
@@ -136,7 +148,7 @@ def run_reference(args):
     if rank != 0:
         return
     workers = os.cpu_count() or 1
-    nsteps = 40
+    nsteps = 300
     # calibrate so that the whole run (W + K bench steps) stays within a few minutes
     t0 = time.perf_counter()
     rates = []
@@ -198,15 +210,16 @@ def run_gpu(args):
             stats.update(world > 1)
         return ms
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     kms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -219,6 +232,7 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark_end()
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
@@ -270,7 +284,9 @@ def run_gpu(args):
                     'steps': e2e_steps, 'api': 'pk_step_host (pinned host buffers)'},
             'gpu_launches': args.steps * 4,   # per step: pk_step_kernel, pk_diag_kernel, pk_moments_partial, pk_moments_final
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'peak_source': which,
+                         'frac': achieved / peak, 'traffic': DRAM_TRAFFIC_PER_LAUNCH, 'peak_source': which,
+                         'traffic_note': 'dram__bytes_read+write per launch from the ncu --set full capture in profiles/ '
+                                         '(state is loaded once per launch and stepped on-chip for 50 timesteps)',
                          'kernel': 'pk_step_kernel', 'kernel_ms': k_ms,
                          'algorithmic_bytes_per_realisation_step': B_ALG,
                          'note': 'fp64-pipe/latency bound by construction (SURVEY.md 8d): ~600 fp64 flop per '
@@ -278,7 +294,7 @@ def run_gpu(args):
             'wall_ms_per_step': wall_ms / args.steps,
         }
         if args.cpu_baseline:
-            rate, cores, sample = cpu_rate(40)
+            rate, cores, sample = cpu_rate(500)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -288,7 +304,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')

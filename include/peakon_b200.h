@@ -77,6 +77,8 @@ typedef struct pk_config {
   int32_t max_it;        /* SNES max_it   (0 -> PETSc default 50) */
   double rtol, atol, stol, divtol; /* SNES tolerances (0 -> PETSc defaults 1e-8, 1e-50, 1e-8, 1e4) */
   double xi_const;       /* PK_NOISE_SCALAR: the constant value of xi_0 (sigma for 'constant') */
+  int32_t scheme;        /* 0: 'hydrodynamic' / 'no_gradient' with 'midpoint' (equations.py:63-130);
+                            1: 'upwind' with 'ssprk3' (equations.py:28-61) -> pk_step_upwind */
 } pk_config;
 
 /* Replaces Equations.__init__ (equations.py:63-95) + PrognosticVariables (simulation.py:227-249)
@@ -115,6 +117,22 @@ int pk_step(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, doub
 int pk_step_host(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
                  const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
                  int32_t* its_total);
+
+/* Replaces `nsteps` passes of  Xis.update(t); equations.solve()  for scheme 'upwind', timestepping
+ * 'ssprk3' (equations.py:172-185): three SSPRK3 stages of the DG1 upwind transport of m with the
+ * frozen velocity us = Dt*u + dXi, then the Helmholtz solve (M + alphasq K) u = P m.
+ *   m [R, ne, 2] in/out: DG1 m, (left-node value, right-node value) of every cell
+ *   u [R, ne]    in/out: CG1 u (the reference's vector-valued u, scalar on the interval)
+ *   dW_in / dW_out / fail_step: as for pk_step.  The scheme is explicit: a realisation fails only on
+ *   a non-finite increment (before the state is touched) or when its state has blown up. */
+int pk_step_upwind(pk_ctx* ctx, int32_t nsteps, double* m, double* u, const double* dW_in,
+                   double* dW_out, int32_t* fail_step, void* stream);
+
+/* Diagnostics of the prognostic DG1 field m of the upwind scheme (outputting.py:112,118,120,164,174):
+ * fills the columns PK_D_L2M2, PK_D_H1SEMI_M2, PK_D_MASS_M, PK_D_M_MAX, PK_D_UMU of `out`
+ * ([R, PK_NDIAG], the table pk_diagnostics writes; call it afterwards on the same stream). */
+int pk_diagnostics_dg1(pk_ctx* ctx, const double* m, const double* u, const int32_t* fail_step,
+                       double* out, void* stream);
 
 int pk_set_step_counter(pk_ctx* ctx, int64_t step);
 int64_t pk_get_step_counter(const pk_ctx* ctx);

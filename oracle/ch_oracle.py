@@ -622,3 +622,85 @@ def run(ne, Ld, dt, nsteps, u0, dW=None, tables=None, alphasq=1.0, scheme='hydro
         if dump_every and (n + 1) % dump_every == 0:
             dumps.append(u.copy())
     return dict(u=u, w1=orc.w1.copy(), its=its, fail_step=fail_step, dumps=dumps, oracle=orc)
+
+
+# ----------------------------------------------------------------------------
+# upwind / ssprk3: equations.py:28-61, 172-185
+# ----------------------------------------------------------------------------
+
+class UpwindOracle(object):
+    """
+    DG1 upwind transport of m with the CG1 velocity us = Dt*u + Xi frozen over three SSPRK3 stages,
+    then the Helmholtz solve (M + a2 K) u = P m.  m is stored [ne, 2] = (value at the left node,
+    value at the right node) of every cell -- Firedrake's DG1 dof order on an interval.
+    Assembled by 2-point Gauss quadrature on cells (integrands are quadratic) and explicit facet terms.
+    """
+
+    def __init__(self, ne, Ld, dt, alphasq=1.0):
+        self.mesh = Mesh1D(ne, Ld)
+        self.ne, self.h, self.dt, self.alphasq = self.mesh.ne, self.mesh.h, float(dt), float(alphasq)
+        self.M = self.mesh.mass()
+        self.K = self.mesh.stiffness()
+        self.H = sp.csc_matrix(self.M + self.alphasq * self.K)
+        self.Hlu = spla.splu(self.H)
+        self.Me_inv = np.linalg.inv(self.h / 6.0 * np.array([[2.0, 1.0], [1.0, 2.0]]))
+        self.qx, self.qw = gauss(2)
+
+    def initial_m(self, u):
+        """initial_conditions.py:65-77: M m_CG = (M + a2 K) u in CG1, then interpolate into DG1."""
+        m_cg = spla.splu(sp.csc_matrix(self.M)).solve(self.H @ u)
+        return np.stack([m_cg, m_cg[self.mesh.right]], axis=1)
+
+    def dm(self, m, s):
+        """Solve  psi*dm dx = psi_x*m*us dx - psi*m*us_x dx - jump(psi)*(un+ m+ - un- m-) dS  (:48-51)."""
+        h = self.h
+        mL, mR = m[:, 0], m[:, 1]
+        s0, s1 = s, s[self.mesh.right]
+        sx = (s1 - s0) / h
+        r = np.zeros((self.ne, 2))
+        for q, w in zip(self.qx, self.qw):
+            mq = (1 - q) * mL + q * mR
+            sq = (1 - q) * s0 + q * s1
+            wt = w * h
+            r[:, 0] += wt * ((-1.0 / h) * mq * sq - (1 - q) * mq * sx)
+            r[:, 1] += wt * ((1.0 / h) * mq * sq - q * mq * sx)
+        # upwind flux through vertex v (between cells v-1 and v): un = max(us.n, 0) on either side
+        up_left = np.roll(mR, 1)                   # value of m just left of vertex v (cell v-1, right end)
+        phi = np.maximum(s, 0.0) * up_left - np.maximum(-s, 0.0) * mL
+        r[:, 0] += phi                              # cell v is the right-hand cell of vertex v
+        r[:, 1] -= np.roll(phi, -1)                 # and the left-hand cell of vertex v+1
+        return r @ self.Me_inv.T
+
+    def solve(self, m, u, dXi):
+        """One step (equations.py:172-185). Returns (m_new, u_new)."""
+        s = self.dt * u + dXi                       # :42
+        m0 = m
+        d1 = self.dm(m0, s)
+        t1 = m0 + d1                                # :177
+        d2 = self.dm(t1, s)
+        t2 = 0.75 * m0 + 0.25 * (t1 + d2)           # :179
+        d3 = self.dm(t2, s)
+        mn = (1.0 / 3.0) * m0 + (2.0 / 3.0) * (t2 + d3)   # :181
+        b = self.h / 6.0 * (2 * mn[:, 0] + mn[:, 1]) + np.roll(self.h / 6.0 * (mn[:, 0] + 2 * mn[:, 1]), 1)
+        un = self.Hlu.solve(b)                      # :58-61,185
+        return mn, un
+
+
+def run_upwind(ne, Ld, dt, nsteps, u0, dW=None, xi=None, alphasq=1.0, m0=None):
+    orc = UpwindOracle(ne, Ld, dt, alphasq)
+    u = np.array(u0, dtype=float).copy()
+    m = orc.initial_m(u) if m0 is None else np.array(m0, dtype=float).copy()
+    for n in range(nsteps):
+        dXi = dW[n] @ xi if dW is not None and dW.shape[1] else np.zeros(ne)
+        m, u = orc.solve(m, u, dXi)
+    return dict(u=u, m=m, oracle=orc)
+
+
+def dg1_norms(orc, m):
+    """L2 / H1 norms and mass of a DG1 field [ne,2] (outputting.py:112,118,120 with m prognostic)."""
+    h = orc.h
+    mL, mR = m[:, 0], m[:, 1]
+    l2sq = np.sum(h / 3.0 * (mL * mL + mL * mR + mR * mR))
+    semi = np.sum((mR - mL) ** 2 / h)
+    return dict(l2_m=float(np.sqrt(l2sq)), h1_m=float(np.sqrt(l2sq + semi)), mass_m=float(np.sum(h / 2.0 * (mL + mR))),
+                m_max=float(max(mL.max(), mR.max())))

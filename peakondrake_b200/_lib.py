@@ -19,7 +19,7 @@ I_ARGMAX_DU, I_ARGMIN_DU, I_ARGMAX_U, I_ARGMAX_JUMP, NIDX = range(5)
 
 EXPORTS = ['pk_create', 'pk_destroy', 'pk_last_error', 'pk_set_tables', 'pk_step', 'pk_step_host',
            'pk_set_step_counter', 'pk_get_step_counter', 'pk_diagnostics', 'pk_get_layout',
-           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite']
+           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite', 'pk_step_upwind', 'pk_diagnostics_dg1']
 
 
 class PkConfig(ctypes.Structure):
@@ -29,7 +29,7 @@ class PkConfig(ctypes.Structure):
                 ('nxi_updates', ctypes.c_int32), ('device', ctypes.c_int32),
                 ('seed', ctypes.c_uint64), ('rid_offset', ctypes.c_uint32), ('max_it', ctypes.c_int32),
                 ('rtol', ctypes.c_double), ('atol', ctypes.c_double), ('stol', ctypes.c_double),
-                ('divtol', ctypes.c_double), ('xi_const', ctypes.c_double)]
+                ('divtol', ctypes.c_double), ('xi_const', ctypes.c_double), ('scheme', ctypes.c_int32)]
 
 
 _lib = None
@@ -72,6 +72,10 @@ def load():
     lib.pk_ensemble_stats.argtypes = [vp, dp, ip, dp, ip, ctypes.c_int32] + [ctypes.c_double] * 4 + [dp, vp]
     lib.pk_peakon_suite.restype = ctypes.c_int
     lib.pk_peakon_suite.argtypes = [vp, dp, ip, ip, dp, ip, vp]
+    lib.pk_step_upwind.restype = ctypes.c_int
+    lib.pk_step_upwind.argtypes = [vp, ctypes.c_int32, dp, dp, dp, dp, ip, vp]
+    lib.pk_diagnostics_dg1.restype = ctypes.c_int
+    lib.pk_diagnostics_dg1.argtypes = [vp, dp, dp, ip, dp, vp]
     _lib = lib
     return lib
 

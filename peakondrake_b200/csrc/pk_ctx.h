@@ -1,0 +1,34 @@
+// pk_ctx.h -- the context object behind the C ABI (internal; shared by the translation units).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <cstdio>
+#include <cstdarg>
+#include "pk_params.h"
+#include "../../include/peakon_b200.h"
+
+struct pk_ctx {
+  pk_config cfg;
+  pk::Params p;
+  const double *xi, *xi_x, *xi_xx;
+  long long step;
+  size_t smem;
+  int block;
+  int cluster;         // CTAs per realisation (1 = single-CTA kernel)
+  int lgTc;
+  std::string err;
+  // internal device buffers for the *_host entry points
+  double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;
+  double* d_scratch;   // diagnostics scratch [R,2,ne]
+  double* d_mom;       // moments partial sums [32, 2*ne]
+  long long* d_prof;   // PK_PROFILE: [R,16] cycle buckets
+  cudaEvent_t ev0, ev1;
+  bool timed;
+};
+
+extern std::string g_create_err;
+
+int pk_fail(pk_ctx* c, const char* fmt, ...);
+#define fail pk_fail
+#define CK(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cooperative_groups.h>
 #include "pk_core.h"
+#include "pk_upwind.h"
 #include "../../include/peakon_b200.h"
 
 using namespace pk;
@@ -25,15 +26,15 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 // AA ("all active") is true for every launch with T >= 32 chunks: then no thread of the block is idle and
 // the phase calls are unconditional, which lets the compiler see the per-thread arrays die between phases.
-template <int M, int MODE, bool AA, int TT>
-struct GpuExec {
-  typedef Thread<M, MODE, TT> Th;
+template <class ThT, bool AA>
+struct GpuExecT {
+  typedef ThT Th;
   Th& th;
   double* red;          // [2][3*nw] reduction / scan scratch in shared memory, used alternately (ping-pong)
   int flip;             // so that a collective needs one barrier only: the area written by collective k
                         // is next written by collective k+2, i.e. after the barrier of collective k+1
   double rA, rc0, rc1;  // maps of the pending reverse scan
-  __device__ __forceinline__ GpuExec(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
+  __device__ __forceinline__ GpuExecT(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
 
   template <class F> __device__ __forceinline__ void each(F f) { if (AA || th.active) f(th); }
   int ne_;
@@ -126,6 +127,8 @@ struct GpuExec {
     if (AA || th.active) fin(th, in0, in1);
   }
 };
+
+template <int M, int MODE, bool AA, int TT> using GpuExec = GpuExecT<Thread<M, MODE, TT>, AA>;
 
 struct StepArgs {
   double *u, *u1, *dF, *dG;
@@ -648,34 +651,15 @@ __global__ void __launch_bounds__(256) pk_moments_final(const double* __restrict
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-struct pk_ctx {
-  pk_config cfg;
-  Params p;
-  const double *xi, *xi_x, *xi_xx;
-  long long step;
-  size_t smem;
-  int block;
-  int cluster;         // CTAs per realisation (1 = single-CTA kernel)
-  int lgTc;
-  std::string err;
-  // internal device buffers for the *_host entry points
-  double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;
-  double* d_scratch;   // diagnostics scratch [R,2,ne]
-  double* d_mom;       // moments partial sums [32, 2*ne]
-  long long* d_prof;   // PK_PROFILE: [R,16] cycle buckets
-  cudaEvent_t ev0, ev1;
-  bool timed;
-};
+#include "pk_ctx.h"
 
-static std::string g_create_err;
-
-static int fail(pk_ctx* c, const char* fmt, ...) {
+std::string g_create_err;
+int pk_fail(pk_ctx* c, const char* fmt, ...) {
   char buf[512];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
   if (c) c->err = buf; else g_create_err = buf;
   return -1;
 }
-#define CK(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 typedef void (*kern_t)(const Params, const StepArgs);
 typedef void (*ckern_t)(const Params, const StepArgs, int);
@@ -743,6 +727,9 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (cfg->R < 1) return fail(nullptr, "pk_create: R must be >= 1");
   if (cfg->noise_mode < 0 || cfg->noise_mode > 2) return fail(nullptr, "pk_create: bad noise_mode %d", cfg->noise_mode);
   if (cfg->num_xis < 0) return fail(nullptr, "pk_create: num_xis < 0");
+  if (cfg->scheme != 0 && cfg->scheme != 1) return fail(nullptr, "pk_create: bad scheme %d", cfg->scheme);
+  if (cfg->scheme == 1 && cfg->noise_mode == PK_NOISE_FULL)
+    return fail(nullptr, "pk_create: the upwind scheme takes dXi only (noise_mode SCALAR or X)");
   if (cfg->noise_mode == PK_NOISE_SCALAR && cfg->num_xis > 1)
     return fail(nullptr, "pk_create: scalar noise supports one Xi only (reference stochastic_functions.py:111-112)");
   { const char* e = getenv("PK_MINB"); g_minb = e ? atoi(e) : 0; }
@@ -762,9 +749,14 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->block = p.T < 32 ? 32 : p.T;
   c->cluster = 1; c->lgTc = 0;
   c->smem = sizeof(double) * ((size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1));
+  if (cfg->scheme == 1) {
+    // upwind/ssprk3: state in registers, only exchange slots in shared memory (pk_upwind_lib.cu)
+    c->smem = sizeof(double) * ((size_t)UW_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1) + 2);
+    if (c->block > 512) { const int ne = p.ne; delete c; return fail(nullptr, "pk_create: upwind scheme supports ne <= 4096 (ne=%d)", ne); }
+  }
   int force = 0;
   { const char* e = getenv("PK_FORCE_CLUSTER"); force = e ? atoi(e) : 0; }   // testing: split small meshes too
-  if (force > 1 || c->block > 512 || c->smem > 227 * 1024) {
+  if (cfg->scheme == 0 && (force > 1 || c->block > 512 || c->smem > 227 * 1024)) {
     // one realisation per thread-block cluster: C CTAs of Tc threads
     int Tc = 256, C = p.T / Tc;
     if (force > 1) { C = force; Tc = p.T / C; }
@@ -784,7 +776,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
   const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block) : (const void*)pick_kernel(p, c->block);
   if (c->cluster > 8) cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+  e = cfg->scheme == 1 ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaFuncSetAttribute(smem=%zu): %s", c->smem, m.c_str()); }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
   *out = c;
@@ -826,6 +818,7 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
                        int32_t* its_total, void* stream) {
   if (!c) return -1;
   if (nsteps < 0) return fail(c, "pk_step: nsteps < 0");
+  if (c->cfg.scheme != 0) return fail(c, "pk_step: context was created for the upwind scheme; use pk_step_upwind");
   if (!u || !u1 || !dF || !fail_step || !its_last || !its_total) return fail(c, "pk_step: null state/counter pointer");
   if (c->p.mode == NOISE_FULL && !dG) return fail(c, "pk_step: dG is required for PK_NOISE_FULL");
   if (c->p.mode != NOISE_SCALAR && c->p.nxi > 0 && !c->xi) return fail(c, "pk_step: noise tables not set (pk_set_tables)");

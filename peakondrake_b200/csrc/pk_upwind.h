@@ -1,0 +1,221 @@
+// pk_upwind.h -- thread-level phases of the 'upwind'/'ssprk3' timestep for an ensemble.
+//
+// Replaces Equations.solve() of the reference for scheme 'upwind', timestepping 'ssprk3'
+// (/root/reference/peakondrake/equations.py:28-61 set-up, :172-185 step):
+//   m in DG1, u in CG1;  us = Dt*u + Xi frozen over the step (:42)
+//   three SSPRK3 stages of  dm = -M_e^-1 r(m_trial)  (:48-55, block-Jacobi+ILU is exact for DG)
+//   then  (M + a2 K) u = P m  (:58-61,185).
+// Per cell (nodes s0,s1 of us; mL,mR of m):
+//   Q  = (2 mL s0 + mL s1 + mR s0 + 2 mR s1)/6,   sx = (s1-s0)/h,
+//   Phi_v = s_v * (s_v > 0 ? mR_{v-1} : mL_v)                       (upwind flux at vertex v)
+//   rhs0 = -Q - sx h/6 (2mL+mR) + Phi_i ,  rhs1 = +Q - sx h/6 (mL+2mR) - Phi_{i+1},  dm = M_e^-1 rhs.
+//
+// Layout: one CTA per realisation, the same chunk geometry as the midpoint kernel (thread t owns
+// cells/nodes [s_t, s_t+m_t)), but the scheme is explicit and local, so the WHOLE state of a thread
+// (m of its cells, u of its nodes) lives in registers for all timesteps of a launch; only the
+// chunk-edge values travel through a handful of shared-memory exchange slots.  The Helmholtz solve
+// reuses the recursive-filter + cyclic affine scan of pk_core.h.
+#pragma once
+#include "pk_core.h"
+
+namespace pk {
+
+// exchange slots (of Shared::xb, slot c of thread t at c*T + t)
+enum { UW_S0 = 0, UW_A_L = 1, UW_A_R = 2, UW_B_L = 3, UW_B_R = 4, UW_H_L = 5, UW_H_R = 6, UW_SLOTS = 7 };
+
+struct UpwindIO {
+  double* m;              // [R, ne, 2]  DG1 m: (left-node value, right-node value) per cell
+  double* u;              // [R, ne]
+  const double* dW_in;    // [nsteps, R, nxi] or null -> Philox
+  double* dW_out;
+  const double* xi;       // [nxi, ne]
+  int R, r;
+  unsigned rid;
+  unsigned long long seed;
+  int step0, nsteps;
+  int* fail_step;         // [R] in/out
+};
+
+template <int M, int XARR, int TT = 0>
+struct UpwindThread {
+  int t, m, s, tl, tr, active;
+  double mL[M], mR[M];       // m0: the state
+  double aL[M], aR[M];       // trial
+  double u[M];               // nodal u of my nodes
+  double sv[M];              // us at my nodes
+  double sR;                 // us at the first node of the right neighbour
+  double hh[M];              // Helmholtz work
+  static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
+
+  PK_HD void init(const Params& p, int tid) {
+    t = tid; active = (tid < p.T);
+    const int tt = active ? tid : 0;
+    t = tt;
+    m = chunk_rows(p, tt); s = chunk_start(p, tt);
+    tl = (tt + p.T - 1) & (p.T - 1); tr = (tt + 1) & (p.T - 1);
+  }
+
+  PK_HD void load(const Params& p, const UpwindIO& io) {
+    const long long off = (long long)io.r * p.ne;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      mL[j] = mR[j] = u[j] = 0.0; aL[j] = aR[j] = 0.0; hh[j] = 0.0; sv[j] = 0.0;
+      if (j < m) { mL[j] = io.m[2 * (off + s + j)]; mR[j] = io.m[2 * (off + s + j) + 1]; u[j] = io.u[off + s + j]; }
+    }
+    sR = 0.0;
+  }
+  PK_HD void store(const Params& p, const UpwindIO& io) const {
+    const long long off = (long long)io.r * p.ne;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j)
+      if (j < m) { io.m[2 * (off + s + j)] = mL[j]; io.m[2 * (off + s + j) + 1] = mR[j]; io.u[off + s + j] = u[j]; }
+  }
+
+  // us = Dt*u + Xi at my nodes; publish my first node's us and the edges of m0 (trial of stage 1)
+  template <class SH>
+  PK_HD void begin_step(const Params& p, const SH& sh, const double* xi) {
+    const int T = TN(p);
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      double X = 0.0;
+      if (j < m) {
+        if (XARR) { for (int k = 0; k < p.nxi; ++k) X += sh.dw(k) * xi[k * p.ne + s + j]; }
+        else X = (p.nxi > 0) ? sh.dw(0) * p.xi_const : 0.0;
+      }
+      sv[j] = p.dt * u[j] + X;
+      aL[j] = mL[j]; aR[j] = mR[j];
+    }
+    sh.st(sh.xb, UW_S0 * T + t, sv[0]);
+    sh.st(sh.xb, UW_A_L * T + t, aL[0]);
+    sh.st(sh.xb, UW_A_R * T + t, (m == M) ? aR[M - 1] : aR[M - 2]);
+  }
+
+  // one SSPRK3 stage: d = dm(trial) and the stage combination, edges published to the other slot set
+  template <class SH>
+  PK_HD void stage(const Params& p, const SH& sh, int k) {
+    const int T = TN(p);
+    const int inL = (k == 2) ? UW_B_L : UW_A_L, inR = (k == 2) ? UW_B_R : UW_A_R;
+    if (k == 1) sR = sh.ld(sh.xb, UW_S0 * T + tr);     // us at the node right of my last cell
+    const double upL = sh.ld(sh.xb, inR * T + tl);   // trial value just left of my first vertex
+    const double dnR = sh.ld(sh.xb, inL * T + tr);   // trial value just right of my last vertex
+    const double ih = 1.0 / p.h, h6 = p.h6;
+    double nL[M], nR[M];
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      nL[j] = aL[j]; nR[j] = aR[j];
+      if (j < m) {
+        const double s0 = sv[j], s1 = (j == m - 1) ? sR : sv[j + 1 < M ? j + 1 : M - 1];
+        const double a = aL[j], b = aR[j];
+        const double left = (j == 0) ? upL : aR[j > 0 ? j - 1 : 0];
+        const double right = (j == m - 1) ? dnR : aL[j + 1 < M ? j + 1 : M - 1];
+        const double phi0 = s0 * (s0 > 0.0 ? left : a);
+        const double phi1 = s1 * (s1 > 0.0 ? b : right);
+        const double Q = (1.0 / 6.0) * (a * (2.0 * s0 + s1) + b * (s0 + 2.0 * s1));
+        const double sx = (s1 - s0) * ih;
+        const double r0 = -Q - sx * h6 * (2.0 * a + b) + phi0;
+        const double r1 = Q - sx * h6 * (a + 2.0 * b) - phi1;
+        const double d0 = (2.0 * ih) * (2.0 * r0 - r1), d1 = (2.0 * ih) * (2.0 * r1 - r0);   // M_e^-1
+        if (k == 1) { nL[j] = mL[j] + d0; nR[j] = mR[j] + d1; }
+        else if (k == 2) { nL[j] = 0.75 * mL[j] + 0.25 * (a + d0); nR[j] = 0.75 * mR[j] + 0.25 * (b + d1); }
+        else { nL[j] = (1.0 / 3.0) * mL[j] + (2.0 / 3.0) * (a + d0); nR[j] = (1.0 / 3.0) * mR[j] + (2.0 / 3.0) * (b + d1); }
+      }
+    }
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) { aL[j] = nL[j]; aR[j] = nR[j]; }
+    const double lastL = (m == M) ? aL[M - 1] : aL[M - 2], lastR = (m == M) ? aR[M - 1] : aR[M - 2];
+    if (k == 1) { sh.st(sh.xb, UW_B_L * T + t, aL[0]); sh.st(sh.xb, UW_B_R * T + t, lastR); }
+    else if (k == 2) { sh.st(sh.xb, UW_A_L * T + t, aL[0]); sh.st(sh.xb, UW_A_R * T + t, lastR); }
+    else {
+      PK_UNROLL
+      for (int j = 0; j < M; ++j) { mL[j] = aL[j]; mR[j] = aR[j]; }            // m0 <- m  (:181-182)
+      sh.st(sh.xb, UW_H_L * T + t, lastL); sh.st(sh.xb, UW_H_R * T + t, lastR);
+    }
+  }
+
+  // Helmholtz right-hand side b = P m and the causal local pass
+  template <class SH>
+  PK_HD void helm_causal(const Params& p, const SH& sh, double& A, double& c0, double& c1) {
+    const int T = TN(p);
+    double pL = sh.ld(sh.xb, UW_H_L * T + tl), pR = sh.ld(sh.xb, UW_H_R * T + tl);
+    double y = 0.0, pw = 1.0;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      hh[j] = 0.0;
+      if (j < m) {
+        const double b = p.h6 * ((pL + 2.0 * pR) + (2.0 * mL[j] + mR[j]));
+        y = b * p.ikappa + p.rho * y; hh[j] = y; pw *= p.rho;
+        pL = mL[j]; pR = mR[j];
+      }
+    }
+    A = pw; c0 = y; c1 = 0.0;
+  }
+  PK_HD void helm_anticausal(const Params& p, double in0, double& A, double& c0, double& c1) {
+    double pw = p.rho;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) if (j < m) { hh[j] += pw * in0; pw *= p.rho; }
+    double x = 0.0; pw = 1.0;
+    PK_UNROLL
+    for (int j = M - 1; j >= 0; --j) if (j < m) { x = hh[j] + p.rho * x; hh[j] = x; pw *= p.rho; }
+    A = pw; c0 = x; c1 = 0.0;
+  }
+  // returns true if every new u of this thread is finite
+  PK_HD bool helm_finish(const Params& p, double in0) {
+    double pw = p.rho;
+    bool ok = true;
+    PK_UNROLL
+    for (int j = M - 1; j >= 0; --j) {
+      if (j < m) {
+        u[j] = hh[j] + pw * in0; pw *= p.rho;
+        ok = ok && (u[j] - u[j] == 0.0);
+      }
+    }
+    return ok;
+  }
+};
+
+template <int M, int XARR, int TT, class Exec, class Th, class SH>
+PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const UpwindIO& io, int* flag) {
+  int failed = io.fail_step[io.r];
+  ex.each([&](Th& th) { th.load(p, io); });
+  ex.one([&]() { *flag = 0; });
+  for (int n = 0; n < io.nsteps; ++n) {
+    ex.each_tid([&](int tid, int nth, bool leader, int, int) {
+      for (int k = tid; k < p.nxi; k += nth) {
+        const long long o = ((long long)n * io.R + io.r) * p.nxi + k;
+        double w;
+        if (io.dW_in) w = io.dW_in[o];
+        else {
+          w = 0.0;
+          for (int j = 0; j < p.nupd; ++j)
+            w += philox_normal(io.seed, io.rid, (unsigned)(io.step0 + n), (unsigned)k, (unsigned)j) * p.sdt;
+        }
+        sh.set_dw(k, w);
+        if (leader && io.dW_out) io.dW_out[o] = w;
+      }
+    });
+    ex.sync();
+    if (failed >= 0) continue;
+    // the reference's linear solves raise on a non-finite residual: a non-finite increment fails the
+    // step before the state is touched; a blow-up of the state is caught one step after it happened
+    bool bad = (*flag != 0);
+    for (int k = 0; k < p.nxi; ++k) { const double w = sh.dw(k); bad = bad || !(w - w == 0.0); }
+    if (bad) { failed = (*flag != 0) ? io.step0 + n - 1 : io.step0 + n; continue; }
+    ex.each([&](Th& th) { th.begin_step(p, sh, io.xi); });
+    ex.sync();
+    ex.each([&](Th& th) { th.stage(p, sh, 1); });
+    ex.sync();
+    ex.each([&](Th& th) { th.stage(p, sh, 2); });
+    ex.sync();
+    ex.each([&](Th& th) { th.stage(p, sh, 3); });
+    ex.sync();
+    ex.scan_fwd([&](Th& th, double& A, double& c0, double& c1) { th.helm_causal(p, sh, A, c0, c1); },
+                [&](Th& th, double in0, double, double& A, double& c0, double& c1) { th.helm_anticausal(p, in0, A, c0, c1); });
+    ex.scan_rev([&](Th& th, double in0, double) { if (!th.helm_finish(p, in0)) *flag = 1; });
+  }
+  ex.sync();
+  if (failed < 0 && *flag != 0) failed = io.step0 + io.nsteps - 1;
+  ex.each([&](Th& th) { th.store(p, io); });
+  ex.one([&]() { io.fail_step[io.r] = failed; });
+}
+
+}  // namespace pk

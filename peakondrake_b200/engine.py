@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from peakondrake_b200 import _lib
-from peakondrake_b200.stochastic_functions import build_tables
+from peakondrake_b200.stochastic_functions import build_tables, circulant_tridiag_solve
 
 CG1_MIDPOINT_SCHEMES = ('hydrodynamic', 'no_gradient')
 
@@ -22,7 +22,9 @@ def validate_scheme(scheme, timestepping, alphasq=1.0, gamma=0.0):
     if alphasq > 0.0 and gamma == 0.0:
         if scheme in CG1_MIDPOINT_SCHEMES and timestepping == 'midpoint':
             return
-        if (scheme, timestepping) in (('upwind', 'ssprk3'), ('test', 'midpoint')):
+        if scheme == 'upwind' and timestepping == 'ssprk3':
+            return
+        if (scheme, timestepping) in (('test', 'midpoint'),):
             raise NotImplementedError('Scheme %s with %s exists in the reference but is outside the '
                                       'B200 hot path built so far (DESIGN.md, "out of scope").'
                                       % (scheme, timestepping))
@@ -60,6 +62,7 @@ class EnsembleIntegrator(object):
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         self.ne, self.Ld, self.dt, self.R = int(ne), float(Ld), float(dt), int(R)
         self.alphasq, self.scheme = float(alphasq), scheme
+        self.upwind = (scheme == 'upwind')
         self.num_Xis, self.Xi_family, self.sigma = int(num_Xis), Xi_family, float(sigma)
         self.nXi_updates = int(nXi_updates)
         if tables is None:
@@ -79,7 +82,8 @@ class EnsembleIntegrator(object):
                             noise_mode=mode, num_xis=self.num_Xis, nxi_updates=self.nXi_updates,
                             device=self.device.index, seed=int(seed), rid_offset=int(rid_offset), max_it=0,
                             rtol=0.0, atol=0.0, stol=0.0, divtol=0.0,
-                            xi_const=float(xi[0, 0]) if (spatially_constant and self.num_Xis) else 0.0)
+                            xi_const=float(xi[0, 0]) if (spatially_constant and self.num_Xis) else 0.0,
+                            scheme=1 if self.upwind else 0)
         ctx = ctypes.c_void_p()
         rc = self.lib.pk_create(ctypes.byref(cfg), ctypes.byref(ctx))
         if rc != 0:
@@ -93,6 +97,8 @@ class EnsembleIntegrator(object):
             _lib.check(self.lib, ctx, self.lib.pk_set_tables(ctx, _ptr(self.xi), _ptr(self.xi_x), _ptr(self.xi_xx)))
         z = lambda: torch.zeros(self.R, self.ne, dtype=torch.float64, device=dev)
         self.u, self.u1, self.dF, self.dG = z(), z(), z(), z()
+        # upwind scheme: prognostic DG1 m, (left-node, right-node) value per cell (simulation.py:154-160)
+        self.m = torch.zeros(self.R, self.ne, 2, dtype=torch.float64, device=dev) if self.upwind else None
         self.fail_step = torch.full((self.R,), -1, dtype=torch.int32, device=dev)
         self.its_last = torch.zeros(self.R, dtype=torch.int32, device=dev)
         self.its_total = torch.zeros(self.R, dtype=torch.int32, device=dev)
@@ -135,6 +141,15 @@ class EnsembleIntegrator(object):
                 dst.copy_(torch.as_tensor(np.asarray(src), dtype=torch.float64).to(self.device).expand(self.R, self.ne))
         self.fail_step.fill_(-1); self.its_last.zero_(); self.its_total.zero_()
         self.lib.pk_set_step_counter(self.ctx, 0)
+        if self.upwind:
+            # initial m: M m_CG = (M + alphasq K) u in CG1, interpolated into DG1 (initial_conditions.py:65-77)
+            h = self.Ld / self.ne
+            uu = self.u.cpu().numpy()
+            b = (h / 6.0 - self.alphasq / h) * (np.roll(uu, 1, axis=1) + np.roll(uu, -1, axis=1)) \
+                + (2.0 * h / 3.0 + 2.0 * self.alphasq / h) * uu
+            m_cg = circulant_tridiag_solve(h / 6.0, 2.0 * h / 3.0, b)
+            m = np.stack([m_cg, np.roll(m_cg, -1, axis=1)], axis=2)
+            self.m.copy_(torch.from_numpy(np.ascontiguousarray(m)))
 
     # -- the hot path -------------------------------------------------------------------------
     def step(self, nsteps, dW=None, export_dW=False):
@@ -153,9 +168,13 @@ class EnsembleIntegrator(object):
         if export_dW and self.num_Xis > 0:
             out = torch.empty(nsteps, self.R, self.num_Xis, dtype=torch.float64, device=self.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.lib.pk_step(self.ctx, int(nsteps), _ptr(self.u), _ptr(self.u1), _ptr(self.dF), _ptr(self.dG),
-                              _ptr(dW_dev), _ptr(out), _ptr(self.fail_step), _ptr(self.its_last),
-                              _ptr(self.its_total), stream)
+        if self.upwind:
+            rc = self.lib.pk_step_upwind(self.ctx, int(nsteps), _ptr(self.m), _ptr(self.u), _ptr(dW_dev), _ptr(out),
+                                         _ptr(self.fail_step), stream)
+        else:
+            rc = self.lib.pk_step(self.ctx, int(nsteps), _ptr(self.u), _ptr(self.u1), _ptr(self.dF), _ptr(self.dG),
+                                  _ptr(dW_dev), _ptr(out), _ptr(self.fail_step), _ptr(self.its_last),
+                                  _ptr(self.its_total), stream)
         _lib.check(self.lib, self.ctx, rc)
         self._keep = (dW_dev, out)      # keep inputs alive until the stream has consumed them
         return out
@@ -165,6 +184,8 @@ class EnsembleIntegrator(object):
 
     def step_host(self, nsteps, u, u1, dF, dG, dW, fail_step, its_last, its_total, dW_out=None):
         """pk_step_host on (pinned or pageable) host NumPy arrays, in place. Synchronous."""
+        if self.upwind:
+            raise NotImplementedError('step_host is provided for the midpoint schemes')
         p = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
         rc = self.lib.pk_step_host(self.ctx, int(nsteps), p(u), p(u1), p(dF), p(dG), p(dW), p(dW_out),
                                    p(fail_step), p(its_last), p(its_total))
@@ -182,9 +203,14 @@ class EnsembleIntegrator(object):
             pq_dev = torch.as_tensor(pq, dtype=torch.float64).to(self.device).contiguous()
         du = torch.empty(self.R, self.ne, dtype=torch.float64, device=self.device) if want_du else None
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.lib.pk_diagnostics(self.ctx, _ptr(self.u), _ptr(pq_dev), int(bool(periodic)), int(bool(want_m)),
+        rc = self.lib.pk_diagnostics(self.ctx, _ptr(self.u), _ptr(pq_dev), int(bool(periodic)),
+                                     int(bool(want_m) and not self.upwind),
                                      _ptr(self.diag), _ptr(self.didx), _ptr(du), _ptr(self.fail_step), stream)
         _lib.check(self.lib, self.ctx, rc)
+        if self.upwind:      # m is prognostic (DG1): its norms come from the state, not from a Helmholtz solve
+            rc = self.lib.pk_diagnostics_dg1(self.ctx, _ptr(self.m), _ptr(self.u), _ptr(self.fail_step),
+                                             _ptr(self.diag), stream)
+            _lib.check(self.lib, self.ctx, rc)
         self._keep_d = pq_dev
         return self.diag, self.didx, du
 

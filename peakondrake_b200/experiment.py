@@ -48,6 +48,10 @@ def experiment(code, Ld, tmax, resolutions=[],
     for field in fields_to_output or []:
         if field not in KNOWN_FIELDS:
             raise ValueError('Output field %s not recognised.' % field)          # simulation.py:295
+        if field in ('uscalar', 'Xiscalar'):
+            for sch in ([schemes] if isinstance(schemes, str) else list(schemes)):
+                if sch not in ('upwind', 'LASCH'):                                  # simulation.py:272-276
+                    raise ValueError('Output field %s only usable with upwind scheme, not %s' % (field, sch))
     check_diagnostics(diagnostics)
 
     expmt = OrderedDict([('dt', (float, dts)), ('resolution', (float, resolutions)), ('seed', (int, seeds)),

@@ -115,6 +115,8 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
     x_cells, x_nodes = mesh.x_cells(), mesh.x_nodes()
     u0 = build_initial_u(ne, Ld, ic, alphasq, float(_val(params, 'peak_width')))
     tables = build_tables(ne, Ld, fam, num_Xis, sigma, scheme)
+    if scheme == 'upwind' and peakon_flag:
+        raise NotImplementedError('peakon_equations with the upwind scheme is outside the B200 hot path')
     eng = EnsembleIntegrator(ne, Ld, dt, R, alphasq=alphasq, scheme=scheme, timestepping=timestepping,
                              num_Xis=num_Xis, Xi_family=fam, sigma=sigma, nXi_updates=nupd,
                              seed=philox_seed, device=device, tables=tables)

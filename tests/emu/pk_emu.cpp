@@ -11,8 +11,12 @@
 #include <vector>
 #include <cmath>
 #include "../../peakondrake_b200/csrc/pk_core.h"
+#include "../../peakondrake_b200/csrc/pk_upwind.h"
 
 using namespace pk;
+
+template <class ThT> struct EmuExecT;
+template <int M, int MODE> using EmuExec = EmuExecT<Thread<M, MODE> >;
 
 // Emulated thread-block cluster: the flat index space j*T + t is split over C "CTAs" of Tc threads
 // exactly like SharedCluster in pk_lib.cu (same decode); `cur` is the CTA of the running thread and
@@ -35,13 +39,13 @@ struct EmuSharedCluster {
   void set_dw(int k, double v) const { (*bufs)[*cur][(dW - (double*)0) + k] = v; }
 };
 
-template <int M, int MODE>
-struct EmuExec {
-  typedef Thread<M, MODE> Th;
+template <class ThT>
+struct EmuExecT {
+  typedef ThT Th;
   std::vector<Th> th;
   int T, order;
   std::vector<double> A, c0, c1;
-  EmuExec(const Params& p, int order_, int C_ = 1) : th(p.T), T(p.T), order(order_), A(p.T), c0(p.T), c1(p.T), ne(p.ne), C(C_), Tc(p.T / C_), cur(0), pp(p) {
+  EmuExecT(const Params& p, int order_, int C_ = 1) : th(p.T), T(p.T), order(order_), A(p.T), c0(p.T), c1(p.T), ne(p.ne), C(C_), Tc(p.T / C_), cur(0), pp(p) {
     for (int t = 0; t < T; ++t) th[t].init(p, t);
   }
   template <class F> void each(F f) {
@@ -196,6 +200,40 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
       case 8: run_mode<8>(p, io, u, u1, dF, dG, order); break;
       default: return -3;
     }
+  }
+  return 0;
+}
+
+// ---- upwind / ssprk3 ---------------------------------------------------------------------------
+template <int M, int XARR>
+static void run_upwind_one(const Params& p, UpwindIO io, int order) {
+  std::vector<double> buf(UW_SLOTS * p.T + (p.nxi > 0 ? p.nxi : 1), 0.0);
+  Shared sh;
+  sh.U0 = sh.U1 = sh.F = sh.G = sh.X = sh.Xx = sh.Xxx = nullptr;
+  sh.xb = &buf[0]; sh.dW = &buf[UW_SLOTS * p.T];
+  typedef UpwindThread<M, XARR, 0> Th;
+  EmuExecT<Th> ex(p, order);
+  int flag = 0;
+  run_upwind_steps<M, XARR, 0, EmuExecT<Th>, Th>(ex, p, sh, io, &flag);
+}
+
+extern "C" int pk_emu_step_upwind(int ne, double Ld, double dt, double alphasq, int xarr, int nxi, int nupd,
+                                  double xi_const, int R, int nsteps, int step0, double* m, double* u,
+                                  const double* xi, const double* dW_in, double* dW_out,
+                                  unsigned long long seed, unsigned rid0, int* fail_step, int order) {
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.ne = ne; p.h = Ld / ne; p.dt = dt; p.alphasq = alphasq; p.mode = xarr ? NOISE_X : NOISE_SCALAR; p.nxi = nxi; p.nupd = nupd;
+  p.max_it = 50; p.rtol = 1e-8; p.atol = 1e-50; p.stol = 1e-8; p.divtol = 1e4; p.xi_const = xi_const;
+  if (!choose_layout(ne, &p.T, &p.M, &p.rem)) return -1;
+  fill_constants(p);
+  for (int r = 0; r < R; ++r) {
+    UpwindIO io;
+    io.m = m; io.u = u; io.dW_in = dW_in; io.dW_out = dW_out; io.xi = xi; io.R = R; io.r = r; io.rid = rid0 + r;
+    io.seed = seed; io.step0 = step0; io.nsteps = nsteps; io.fail_step = fail_step;
+#define UW_CASE(MM) case MM: if (xarr) run_upwind_one<MM, 1>(p, io, order); else run_upwind_one<MM, 0>(p, io, order); break;
+    switch (p.M) { UW_CASE(5) UW_CASE(6) UW_CASE(7) UW_CASE(8) default: return -3; }
+#undef UW_CASE
   }
   return 0;
 }

@@ -35,3 +35,20 @@ def emu_step(ne, Ld, dt, mode, u, u1, dF, dG, tabs, dW, nsteps, xi_const=0.0, or
                            order, T, M)
     assert rc == 0, rc
     return dict(fail_step=fs, its_last=il, its_total=itot, reason=fr, dW=dWo)
+
+
+def emu_step_upwind(ne, Ld, dt, m, u, xi, dW, nsteps, xi_const=0.0, order=0, alphasq=1.0, nupd=1, seed=0, rid0=0,
+                    nxi=None, export=False):
+    R = u.shape[0]
+    if nxi is None:
+        nxi = 0 if dW is None else dW.shape[2]
+    xarr = 1 if (xi is not None and nxi > 0) else 0
+    fs = -np.ones(R, np.int32)
+    dWo = np.zeros((nsteps, R, nxi)) if export else None
+    L = lib()
+    L.pk_emu_step_upwind.restype = ctypes.c_int
+    rc = L.pk_emu_step_upwind(ctypes.c_int(ne), ctypes.c_double(Ld), ctypes.c_double(dt), ctypes.c_double(alphasq),
+                              xarr, nxi, nupd, ctypes.c_double(xi_const), R, nsteps, 0, _p(m), _p(u), _p(xi), _p(dW), _p(dWo),
+                              ctypes.c_ulonglong(seed), rid0, _p(fs, ctypes.c_int), order)
+    assert rc == 0, rc
+    return dict(fail_step=fs, dW=dWo)

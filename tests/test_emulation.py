@@ -115,3 +115,36 @@ def test_cluster_layout_emulated(ne, C):
         assert L.pk_emu_set_cluster(1) == 0          # no non-local stores happened
     finally:
         L.pk_emu_set_cluster(1)
+
+
+# ---- upwind / ssprk3 ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('ne,nxi,fam', [(20, 7, 'sines'), (1000, 7, 'sines'), (200, 1, 'constant'), (333, 0, 'sines'), (9, 2, 'sines')])
+def test_upwind_kernel_emulated(ne, nxi, fam):
+    from emu_util import emu_step_upwind
+    Ld, dt, n = 40., 1e-3, 10
+    mesh = O.Mesh1D(ne, Ld); u0 = O.initial_u(mesh, 'one_peak')
+    xi = O.noise_tables(mesh, fam, nxi, 0.25, scheme='upwind')[0] if nxi else None
+    dW = O.reference_dW(0, n, nxi, dt) if nxi else None
+    ref = O.run_upwind(ne, Ld, dt, n, u0, dW, xi)
+    res = []
+    for order in (0, 1):
+        m = ref['oracle'].initial_m(u0)[None].copy(); u = u0[None].copy()
+        xc = xi[0, 1] if fam == 'constant' else 0.0
+        emu_step_upwind(ne, Ld, dt, m, u, None if (fam == 'constant' or not nxi) else np.ascontiguousarray(xi),
+                        None if dW is None else np.ascontiguousarray(dW[:, None, :]), n, xi_const=xc, nxi=nxi, order=order)
+        assert rel(u[0], ref['u']) <= TOL and rel(m[0], ref['m']) <= TOL
+        res.append((u.copy(), m.copy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_upwind_oracle_properties():
+    # constants are preserved; int m drifts only weakly; energy drift ~5e-4 over t=2 at ne=1000
+    ne, Ld, dt = 200, 40.0, 1e-3
+    orc = O.UpwindOracle(ne, Ld, dt)
+    m, u = orc.solve(np.full((ne, 2), 0.7), np.full(ne, 0.7), np.zeros(ne))
+    assert abs(m - 0.7).max() < 1e-14 and abs(u - 0.7).max() < 1e-12
+    u0 = O.initial_u(orc.mesh, 'one_peak')
+    r = O.run_upwind(ne, Ld, dt, 200, u0)
+    E0 = u0 @ (orc.M @ u0) + u0 @ (orc.K @ u0); E1 = r['u'] @ (orc.M @ r['u']) + r['u'] @ (orc.K @ r['u'])
+    assert abs(E1 - E0) / E0 < 5e-3
+    assert abs(O.dg1_norms(orc, r['m'])['mass_m'] - O.dg1_norms(orc, orc.initial_m(u0))['mass_m']) < 1e-3

@@ -140,3 +140,35 @@ def test_ensemble_statistics_kernels():
     assert np.array_equal(st.hist_q.cpu().numpy(), hq) and np.array_equal(st.hist_min_du.cpu().numpy(), hd)
     a = st.packed.clone(); st.update(); torch.cuda.synchronize()
     assert torch.equal(a, st.packed)         # deterministic (fixed-order sums, integer histograms)
+
+
+def test_reference_test_dumping_script_parameters(tmp_path, monkeypatch):
+    """The reference's one runnable test, verbatim parameters (tests/test_dumping.py): upwind/ssprk3,
+    20 cells, 10 steps, 7 sines, sigma 0.25, the five norms, uscalar/Xiscalar fields."""
+    from peakondrake_b200 import experiment, outputting as out
+    monkeypatch.chdir(tmp_path)
+    code, Ld, dt, tmax = 'test_one_run', 40., 0.001, 0.01
+    experiment(code, Ld, tmax, resolutions=20, dts=dt, sigmas=0.25, seeds=0, schemes='upwind', timesteppings='ssprk3',
+               ics='one_peak', num_Xis=7, Xi_family='sines', alphasq=1.0, c0=0., gamma=0.,
+               diagnostics=['h1_u', 'h1_m', 'l2_u', 'l2_m', 'energy'], fields_to_output=['uscalar', 'Xiscalar'],
+               ndump=int(tmax / (10 * dt)), field_ndump=int(tmax / (10 * dt)))
+    d = out.read_data_file('results/test_one_run/data.nc')
+    assert d['time'].shape == (11,) and d['energy'].shape == (11,)
+    mesh = O.Mesh1D(20, Ld)
+    u0 = O.initial_u(mesh, 'one_peak')
+    xi = O.noise_tables(mesh, 'sines', 7, 0.25, scheme='upwind')[0]
+    dW = O.reference_dW(0, 10, 7, dt)
+    orc = O.UpwindOracle(20, Ld, dt)
+    m, u = orc.initial_m(u0), u0.copy()
+    for n in range(11):
+        if n > 0:
+            m, u = orc.solve(m, u, dW[n - 1] @ xi)
+        nm = O.dg1_norms(orc, m)
+        l2u = np.sqrt(u @ (orc.M @ u)); h1u = np.sqrt(u @ (orc.M @ u) + u @ (orc.K @ u))
+        for name, v in (('l2_u', l2u), ('h1_u', h1u), ('energy', u @ (orc.M @ u) + u @ (orc.K @ u)),
+                        ('l2_m', nm['l2_m']), ('h1_m', nm['h1_m'])):
+            assert abs(d[name][n] - v) <= 1e-10 * max(1.0, abs(v)), (name, n)
+    with pytest.raises(IOError):          # re-running needs a fresh results directory (experiment.py:25-27)
+        experiment(code, Ld, tmax, resolutions=20, dts=dt, sigmas=0.25, seeds=0, schemes='upwind',
+                   timesteppings='ssprk3', ics='one_peak', num_Xis=7, Xi_family='sines', alphasq=1.0, c0=0., gamma=0.,
+                   diagnostics=['energy'])

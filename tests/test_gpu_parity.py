@@ -269,3 +269,65 @@ def test_c5_fine_mesh_20000_large_noise():
 
 def test_cluster_with_noise_tables_4096():
     assert run_case(4096, 2, 4, nxi=4) <= TOL
+
+
+# ---- upwind / ssprk3 (equations.py:28-61,172-185) ---------------------------------------------------
+def run_upwind_case(ne, R, nsteps, ic='one_peak', fam='sines', nxi=7, sigma=0.25, dt=1e-3, Ld=40.0):
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, draw_dW, _lib
+    u0 = build_initial_u(ne, Ld, ic)
+    eng = EnsembleIntegrator(ne, Ld, dt, R, scheme='upwind', timestepping='ssprk3', num_Xis=nxi, Xi_family=fam, sigma=sigma)
+    eng.set_state(u0)
+    orc = O.UpwindOracle(ne, Ld, dt)
+    m_init = eng.m[0].cpu().numpy().copy()
+    # m = u - a2 u_xx amplifies rounding by ~4 a2/h^2: the two set-up solves agree to cond * eps
+    assert rel(m_init, orc.initial_m(u0)) <= 1e-15 * max(1e3, 4.0 / (Ld / ne) ** 2)
+    dW = np.stack([draw_dW(r, nsteps, nxi, dt) for r in range(R)], axis=1) if nxi else None
+    eng.step(nsteps // 2, dW=None if dW is None else dW[:nsteps // 2])
+    eng.step(nsteps - nsteps // 2, dW=None if dW is None else dW[nsteps // 2:])
+    vals, idx, _ = eng.diagnostics(want_m=True)
+    torch.cuda.synchronize()
+    xi = O.noise_tables(O.Mesh1D(ne, Ld), fam, nxi, sigma, scheme='upwind')[0] if nxi else None
+    u, m, vals = eng.u.cpu().numpy(), eng.m.cpu().numpy(), vals.cpu().numpy()
+    assert (eng.fail_step.cpu().numpy() == -1).all()
+    for r in range(R):
+        ref = O.run_upwind(ne, Ld, dt, nsteps, u0, None if dW is None else dW[:, r, :], xi, m0=m_init)
+        assert rel(u[r], ref['u']) <= TOL and rel(m[r], ref['m']) <= TOL
+        d = O.dg1_norms(orc, ref['m'])
+        assert abs(np.sqrt(vals[r, _lib.D_L2M2]) - d['l2_m']) <= 1e-10 * d['l2_m']
+        assert abs(np.sqrt(vals[r, _lib.D_L2M2] + vals[r, _lib.D_H1SEMI_M2]) - d['h1_m']) <= 1e-10 * d['h1_m']
+        assert abs(vals[r, _lib.D_MASS_M] - d['mass_m']) <= 1e-10 and abs(vals[r, _lib.D_M_MAX] - d['m_max']) <= 1e-10
+    eng.close()
+
+
+def test_upwind_ssprk3_reference_test_parameters():
+    # the reference's only runnable test (tests/test_dumping.py): 20 cells, 10 steps, 7 sines, sigma 0.25
+    run_upwind_case(20, 2, 10)
+
+
+@pytest.mark.parametrize('ne', [8, 37, 200, 1000, 2000, 4000])
+def test_upwind_mesh_sizes(ne):
+    # the explicit scheme is only stable for |us|/h well below 1: scale the noise with the mesh width,
+    # otherwise rounding differences are amplified step by step and path-wise comparison is meaningless
+    run_upwind_case(ne, 3, 8, nxi=3, sigma=0.25 * min(1.0, 200.0 / ne))
+
+
+def test_upwind_constant_and_no_noise():
+    run_upwind_case(500, 2, 8, fam='constant', nxi=1, sigma=0.3, ic='proper_peak')
+    run_upwind_case(500, 2, 8, nxi=0)
+
+
+def test_upwind_failure_on_nonfinite_increment():
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    ne = 100
+    u0 = build_initial_u(ne, 40.0, 'one_peak')
+    eng = EnsembleIntegrator(ne, 40.0, 1e-3, 2, scheme='upwind', timestepping='ssprk3', num_Xis=1, sigma=0.5)
+    eng.set_state(u0)
+    dW = np.full((4, 2, 1), 0.01); dW[2, 1, 0] = np.inf
+    eng.step(4, dW=dW)
+    torch.cuda.synchronize()
+    assert list(eng.fail_step.cpu().numpy()) == [-1, 2]
+    xi = O.noise_tables(O.Mesh1D(ne, 40.0), 'sines', 1, 0.5, scheme='upwind')[0]
+    ref = O.run_upwind(ne, 40.0, 1e-3, 2, u0, dW[:2, 1, :], xi)
+    assert rel(eng.u[1].cpu().numpy(), ref['u']) <= TOL          # frozen at the last good step
