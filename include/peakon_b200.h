@@ -89,7 +89,8 @@ const char* pk_last_error(const pk_ctx* ctx);  /* ctx may be NULL: last create e
 
 /* Replaces StochasticFunctions.__init__'s tables (stochastic_functions.py:66-201):
  * xi, xi_x, xi_xx are [num_xis, ne] device arrays shared by all realisations (xi_x/xi_xx may be
- * NULL unless noise_mode == PK_NOISE_FULL).  Pointers are retained, not copied. */
+ * NULL unless noise_mode == PK_NOISE_FULL).  The tables are copied (into the kernel's chunk-interleaved
+ * order); the caller may free them afterwards.  Synchronises the device. */
 int pk_set_tables(pk_ctx* ctx, const double* xi, const double* xi_x, const double* xi_xx);
 
 /* Replaces `nsteps` passes of  Xis.update(t); equations.solve()  (simulation.py:96-108;

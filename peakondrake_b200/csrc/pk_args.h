@@ -1,0 +1,13 @@
+// pk_args.h -- argument block of the step kernels.
+#pragma once
+struct StepArgs {
+  double *u, *u1, *dF, *dG;
+  const double *xi, *xi_x, *xi_xx;
+  const double* dW_in;
+  double* dW_out;
+  int *fail_step, *its_last, *its_total;
+  int R, step0, nsteps;
+  long long* prof;    // [R,16] cycle buckets, PK_PROFILE builds only
+  unsigned rid0;
+  unsigned long long seed;
+};

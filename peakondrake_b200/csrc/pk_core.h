@@ -67,6 +67,15 @@ PK_HD int row_slot_c(const Params& p, int i) {
   return j * (TT > 0 ? TT : p.T) + t;
 }
 
+// chunk-interleaved copy of a [nxi, ne] table: dst[k*T*M + row_slot(i)] = src[k*ne + i], padding rows 0
+inline void permute_table_host(const Params& p, const double* src, double* dst) {
+  const int TM = p.T * p.M;
+  for (int k = 0; k < p.nxi; ++k) {
+    for (int i = 0; i < TM; ++i) dst[k * TM + i] = 0.0;
+    for (int i = 0; i < p.ne; ++i) dst[k * TM + row_slot(p, i)] = src[k * p.ne + i];
+  }
+}
+
 struct NodeS { double a, v, w, F, G, x, y; };
 
 // Contributions of one cell (left node A, right node B) to its two nodes, and their derivatives
@@ -621,50 +630,44 @@ struct Thread {
       if (j < m) { const int i = idx(p, j); sh.st(sh.U0, i, sh.ld(sh.U1, i)); }
   }
 
+  // ---- noise fields of this step: dXi = sum_k dW_k xi_k etc. (stochastic_functions.py:229-234) ----
+  // The tables arrive in the chunk-interleaved order of the shared arrays (pk_set_tables permutes
+  // them once): table k holds row j of chunk t at k*(T*M) + j*T + t, so the loads of a warp are
+  // contiguous and every thread fills exactly its own rows.
+  template <class SH>
+  PK_HD void fill_noise(const Params& p, const SH& sh, const double* xi, const double* xi_x, const double* xi_xx) {
+    if (MODE == NOISE_SCALAR) return;
+    const int T = TN(p), TM = T * M;
+    double X[M], Xx[M], Xxx[M];
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) { X[j] = 0.0; Xx[j] = 0.0; Xxx[j] = 0.0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+    for (int k = 0; k < p.nxi; ++k) {
+      const double w = sh.dw(k);
+      PK_UNROLL
+      for (int j = 0; j < M; ++j) {
+        const int i = k * TM + j * T + t;
+        X[j] += w * xi[i];
+        if (MODE == NOISE_FULL) { Xx[j] += w * xi_x[i]; Xxx[j] += w * xi_xx[i]; }
+      }
+    }
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (j < m) {
+        sh.st(sh.X, j * T + t, X[j]);
+        if (MODE == NOISE_FULL) { sh.st(sh.Xx, j * T + t, Xx[j]); sh.st(sh.Xxx, j * T + t, Xxx[j]); }
+      }
+    }
+  }
+
   // ---- NOISE_SCALAR: the dXi value of this step ------------------------------------------------
   template <class SH>
   PK_HD void set_scalar_noise(const Params& p, const SH& sh) {
     Xs = (p.nxi > 0) ? sh.dw(0) * p.xi_const : 0.0;
   }
 };
-
-// Noise fields of this step: dXi = sum_k dW_k xi_k etc. (stochastic_functions.py:229-234).
-// Block-wide loop in natural node order: coalesced table reads, scattered into the chunk layout.
-template <int M, int MODE, int TT, class SH>
-PK_HD void fill_noise_rows(const Params& p, const SH& sh, const double* xi, const double* xi_x,
-                           const double* xi_xx, int tid, int nth, int g0, int g1) {
-  // rows [g0, g1) are the ones this block owns (the whole mesh unless a cluster shares the realisation)
-  if (MODE == NOISE_SCALAR) return;
-  enum { NB = 4 };     // nodes in flight per thread: NB x 3 tables x (unrolled modes) independent loads
-  for (int base = g0 + tid; base < g1; base += NB * nth) {
-    double X[NB], Xx[NB], Xxx[NB];
-    PK_UNROLL
-    for (int j = 0; j < NB; ++j) { X[j] = 0.0; Xx[j] = 0.0; Xxx[j] = 0.0; }
-#if defined(__CUDA_ARCH__)
-#pragma unroll 4
-#endif
-    for (int k = 0; k < p.nxi; ++k) {
-      const double w = sh.dw(k);
-      PK_UNROLL
-      for (int j = 0; j < NB; ++j) {
-        const int g = base + j * nth;
-        if (g < g1) {
-          X[j] += w * xi[k * p.ne + g];
-          if (MODE == NOISE_FULL) { Xx[j] += w * xi_x[k * p.ne + g]; Xxx[j] += w * xi_xx[k * p.ne + g]; }
-        }
-      }
-    }
-    PK_UNROLL
-    for (int j = 0; j < NB; ++j) {
-      const int g = base + j * nth;
-      if (g < g1) {
-        const int i = row_slot_c<M, TT>(p, g);
-        sh.st(sh.X, i, X[j]);
-        if (MODE == NOISE_FULL) { sh.st(sh.Xx, i, Xx[j]); sh.st(sh.Xxx, i, Xxx[j]); }
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator + Box-Muller. Counter =
@@ -713,7 +716,7 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 struct StepIO {
   const double* dW_in;    // [nsteps, R, nxi] or null -> Philox
   double* dW_out;         // [nsteps, R, nxi] or null
-  const double *xi, *xi_x, *xi_xx;   // [nxi, ne]
+  const double *xi, *xi_x, *xi_xx;   // [nxi, T*M] chunk-interleaved copies of the [nxi, ne] tables (permute_table)
   int R;                  // realisations in this launch (stride of dW_in/out)
   int r;                  // this realisation (local index)
   unsigned rid;           // global realisation id (Philox counter)
@@ -770,8 +773,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     ex.tick(0);
     if (failed >= 0) continue;
     if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
-    else ex.each_tid([&](int tid, int nth, bool, int g0, int g1) {
-      fill_noise_rows<M, MODE, TT>(p, sh, io.xi, io.xi_x, io.xi_xx, tid, nth, g0, g1); });
+    else ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
     ex.sync();
     ex.tick(1);
 

@@ -22,6 +22,7 @@ struct pk_ctx {
   double* d_scratch;   // diagnostics scratch [R,2,ne]
   double* d_mom;       // moments partial sums [32, 2*ne]
   long long* d_prof;   // PK_PROFILE: [R,16] cycle buckets
+  double* d_tab[3];    // chunk-interleaved copies of the noise tables [nxi, T*M]
   cudaEvent_t ev0, ev1;
   bool timed;
 };

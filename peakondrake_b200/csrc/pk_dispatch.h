@@ -1,0 +1,14 @@
+// pk_dispatch.h -- kernel pickers exported by the per-M translation units (pk_kernels_m.cu).
+#pragma once
+#include "pk_params.h"
+struct StepArgs;
+typedef void (*kern_t)(const pk::Params, const StepArgs);
+typedef void (*ckern_t)(const pk::Params, const StepArgs, int);
+kern_t pk_pick_kernel_m5(int mode, int block, int T, int minb);
+kern_t pk_pick_kernel_m6(int mode, int block, int T, int minb);
+kern_t pk_pick_kernel_m7(int mode, int block, int T, int minb);
+kern_t pk_pick_kernel_m8(int mode, int block, int T, int minb);
+ckern_t pk_pick_cluster_kernel_m5(int mode, int Tc);
+ckern_t pk_pick_cluster_kernel_m6(int mode, int Tc);
+ckern_t pk_pick_cluster_kernel_m7(int mode, int Tc);
+ckern_t pk_pick_cluster_kernel_m8(int mode, int Tc);

@@ -1,0 +1,362 @@
+// pk_kernels.cuh -- device executors and the step kernels (single-CTA and thread-block-cluster
+// variants).  Included by pk_kernels_m.cu, which is compiled once per chunk size M (parallel build).
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include "pk_core.h"
+
+using namespace pk;
+namespace cg = cooperative_groups;
+
+// ------------------------------------------------------------------------------------------------
+// device-side executor: one CUDA thread per chunk
+// ------------------------------------------------------------------------------------------------
+// AA ("all active") is true for every launch with T >= 32 chunks: then no thread of the block is idle and
+// the phase calls are unconditional, which lets the compiler see the per-thread arrays die between phases.
+template <class ThT, bool AA>
+struct GpuExecT {
+  typedef ThT Th;
+  Th& th;
+  double* red;          // [2][3*nw] reduction / scan scratch in shared memory, used alternately (ping-pong)
+  int flip;             // so that a collective needs one barrier only: the area written by collective k
+                        // is next written by collective k+2, i.e. after the barrier of collective k+1
+  double rA, rc0, rc1;  // maps of the pending reverse scan
+  __device__ __forceinline__ GpuExecT(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
+
+  template <class F> __device__ __forceinline__ void each(F f) { if (AA || th.active) f(th); }
+  int ne_;
+  template <class F> __device__ __forceinline__ void each_tid(F f) { f((int)threadIdx.x, (int)blockDim.x, true, 0, ne_); }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+#ifdef PK_PROFILE
+  long long tlast; long long* tbuf;   // per-phase cycle buckets (thread 0 of each CTA), profiling builds only
+  __device__ __forceinline__ void tick(int id) {
+    if (threadIdx.x == 0) { const long long c = clock64(); tbuf[id] += c - tlast; tlast = c; }
+  }
+#else
+  __device__ __forceinline__ void tick(int) {}
+#endif
+  template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
+  __device__ __forceinline__ double* area() {
+    const int nw = blockDim.x >> 5;
+    double* a = red + flip * 3 * nw;
+    flip ^= 1;
+    return a;
+  }
+
+  template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
+    double v[3] = {0.0, 0.0, 0.0};
+    if (AA || th.active) f(th, v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+      v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
+      v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* sc = area();
+    if (lane == 0) { sc[w] = v[0]; sc[nw + w] = v[1]; sc[2 * nw + w] = v[2]; }
+    __syncthreads();
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < nw; ++i) { s0 += sc[i]; s1 += sc[nw + i]; s2 += sc[2 * nw + i]; }
+    out[0] = s0; out[1] = s1; out[2] = s2;
+  }
+
+  // Cyclic exclusive scan of affine maps over the block. DIR=+1: thread order 0..T-1, value
+  // entering thread t comes from t-1; DIR=-1: order T-1..0. Inactive threads carry the identity.
+  template <int DIR>
+  __device__ __forceinline__ void cyc_scan(double A, double c0, double c1, double& in0, double& in1) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // inclusive scan inside the warp (Kogge-Stone); "earlier" = lower lane for DIR=+1, higher for -1
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double Ao, c0o, c1o;
+      if (DIR > 0) {
+        Ao = __shfl_up_sync(0xffffffffu, A, o); c0o = __shfl_up_sync(0xffffffffu, c0, o); c1o = __shfl_up_sync(0xffffffffu, c1, o);
+      } else {
+        Ao = __shfl_down_sync(0xffffffffu, A, o); c0o = __shfl_down_sync(0xffffffffu, c0, o); c1o = __shfl_down_sync(0xffffffffu, c1, o);
+      }
+      const bool ok = (DIR > 0) ? (lane >= o) : (lane + o < 32);
+      if (ok) { c0 = A * c0o + c0; c1 = A * c1o + c1; A = A * Ao; }
+    }
+    const int last = (DIR > 0) ? 31 : 0;
+    double* sc = area();
+    if (lane == last) { sc[w] = A; sc[nw + w] = c0; sc[2 * nw + w] = c1; }
+    __syncthreads();
+    // compose the warp aggregates in scan order; remember the prefix in front of my warp
+    double tA = 1.0, t0 = 0.0, t1 = 0.0, eA = 1.0, e0 = 0.0, e1 = 0.0;
+    for (int k = 0; k < nw; ++k) {
+      const int ww = (DIR > 0) ? k : nw - 1 - k;
+      if (ww == w) { eA = tA; e0 = t0; e1 = t1; }
+      const double a = sc[ww];
+      t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
+    }
+    const double inv = PK_RCP(1.0 - tA);
+    const double x0 = t0 * inv, x1 = t1 * inv;          // value entering the first thread (cyclic closure)
+    const double w0 = eA * x0 + e0, w1 = eA * x1 + e1;  // value entering my warp
+    const double o0 = A * w0 + c0, o1 = A * w1 + c1;    // value leaving my thread
+    double p0, p1;
+    if (DIR > 0) { p0 = __shfl_up_sync(0xffffffffu, o0, 1); p1 = __shfl_up_sync(0xffffffffu, o1, 1); }
+    else { p0 = __shfl_down_sync(0xffffffffu, o0, 1); p1 = __shfl_down_sync(0xffffffffu, o1, 1); }
+    const bool first = (DIR > 0) ? (lane == 0) : (lane == 31);
+    in0 = first ? w0 : p0; in1 = first ? w1 : p1;
+  }
+
+  template <class G, class P> __device__ __forceinline__ void scan_fwd(G get, P put) {
+    double A = 1.0, c0 = 0.0, c1 = 0.0, in0, in1;
+    if (AA || th.active) get(th, A, c0, c1);
+    cyc_scan<+1>(A, c0, c1, in0, in1);
+    rA = 1.0; rc0 = 0.0; rc1 = 0.0;
+    if (AA || th.active) put(th, in0, in1, rA, rc0, rc1);
+  }
+  template <class F> __device__ __forceinline__ void scan_rev(F fin) {
+    double in0, in1;
+    cyc_scan<-1>(rA, rc0, rc1, in0, in1);
+    if (AA || th.active) fin(th, in0, in1);
+  }
+};
+
+template <int M, int MODE, bool AA, int TT> using GpuExec = GpuExecT<Thread<M, MODE, TT>, AA>;
+
+#include "pk_args.h"
+
+
+template <int MODE> struct NArr { enum { n = (MODE == NOISE_FULL) ? 7 : (MODE == NOISE_X ? 4 : 3) }; };
+
+template <int M, int MODE, int TB, int MINB, int TT>
+__global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int Tn = TT > 0 ? TT : p.T;
+  const int n = Tn * M;
+  Shared sh;
+  sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
+  double* nxt = smem + 3 * n;
+  if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
+  else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
+  else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
+  sh.xb = nxt; nxt += XB_SLOTS * Tn;
+  double* red = nxt; nxt += 6 * (blockDim.x >> 5);
+  sh.dW = nxt;
+
+  const int r = blockIdx.x;
+  const long long off = (long long)r * p.ne;
+  // coalesced global reads, scattered into the chunk-interleaved shared layout
+  for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
+    const int sl = row_slot_c<M, TT>(p, i);
+    sh.U0[sl] = a.u[off + i]; sh.U1[sl] = a.u1[off + i]; sh.F[sl] = a.dF[off + i];
+    if (MODE == NOISE_FULL) sh.G[sl] = a.dG[off + i];
+  }
+  __syncthreads();
+
+  Thread<M, MODE, TT> th;
+  th.init(p, threadIdx.x);
+  GpuExec<M, MODE, (TB > 32), TT> ex(th, red);
+  ex.ne_ = p.ne;
+#ifdef PK_PROFILE
+  __shared__ long long tb[16];
+  if (threadIdx.x < 16) tb[threadIdx.x] = 0;
+  __syncthreads();
+  ex.tbuf = tb; ex.tlast = clock64();
+#endif
+  StepIO io;
+  io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
+  io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
+  io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
+  run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT>, Thread<M, MODE, TT> >(ex, p, sh, io);
+  __syncthreads();
+#ifdef PK_PROFILE
+  if (a.prof && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];
+#endif
+
+  for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
+    const int sl = row_slot_c<M, TT>(p, i);
+    a.u[off + i] = sh.U0[sl]; a.u1[off + i] = sh.U1[sl]; a.dF[off + i] = sh.F[sl];
+    if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[sl];
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Thread-block-cluster variant: one realisation per CLUSTER of C CTAs (meshes whose state does not
+// fit one SM: ne = 16 384 / 20 000 of BASELINE configs 4 and 5).  Every CTA keeps the rows of its own
+// Tc threads in its shared memory; the flat index space j*T + t (T = C*Tc threads) is decoded to
+// (owner CTA, local offset) and foreign rows are read through distributed shared memory.  All writes
+// are to own rows.  Barriers are cluster barriers.
+// ------------------------------------------------------------------------------------------------
+struct SharedCluster {
+  double *U0, *U1, *F, *G, *X, *Xx, *Xxx, *xb, *dW;
+  int Tc, lgTc, lgT;
+  unsigned rank;
+  __device__ __forceinline__ double ld(const double* a, int i) const {
+    const int tg = i & ((1 << lgT) - 1), j = i >> lgT;
+    const unsigned owner = (unsigned)tg >> lgTc;
+    double* pl = const_cast<double*>(a) + (j << lgTc) + (tg & (Tc - 1));
+    if (owner == rank) return *pl;
+    return *cg::this_cluster().map_shared_rank(pl, owner);
+  }
+  __device__ __forceinline__ void st(double* a, int i, double v) const {
+    const int tg = i & ((1 << lgT) - 1), j = i >> lgT;
+    a[(j << lgTc) + (tg & (Tc - 1))] = v;
+  }
+  __device__ __forceinline__ double dw(int k) const { return dW[k]; }
+  __device__ __forceinline__ void set_dw(int k, double v) const { dW[k] = v; }
+};
+
+template <int M, int MODE>
+struct GpuExecCluster {
+  typedef Thread<M, MODE, 0> Th;
+  Th& th;
+  double* red;          // [2][3*nw + 3]: warp partials + this CTA's aggregate, ping-pong
+  int flip, g0, g1;
+  unsigned rank, C;
+  double rA, rc0, rc1;
+  __device__ __forceinline__ GpuExecCluster(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
+  template <class F> __device__ __forceinline__ void each(F f) { f(th); }
+  template <class F> __device__ __forceinline__ void each_tid(F f) { f((int)threadIdx.x, (int)blockDim.x, rank == 0, g0, g1); }
+  __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+  __device__ __forceinline__ void tick(int) {}
+  template <class F> __device__ __forceinline__ void one(F f) { if (rank == 0 && threadIdx.x == 0) f(); }
+  __device__ __forceinline__ double* area() {
+    const int nw = blockDim.x >> 5;
+    double* a = red + flip * (3 * nw + 3);
+    flip ^= 1;
+    return a;
+  }
+  template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
+    double v[3] = {0.0, 0.0, 0.0};
+    f(th, v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+      v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
+      v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* sc = area();
+    if (lane == 0) { sc[w] = v[0]; sc[nw + w] = v[1]; sc[2 * nw + w] = v[2]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int i = 0; i < nw; ++i) { s0 += sc[i]; s1 += sc[nw + i]; s2 += sc[2 * nw + i]; }
+      sc[3 * nw] = s0; sc[3 * nw + 1] = s1; sc[3 * nw + 2] = s2;
+    }
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (unsigned c = 0; c < C; ++c) {
+      const double* q = cl.map_shared_rank(sc + 3 * nw, c);
+      s0 += q[0]; s1 += q[1]; s2 += q[2];
+    }
+    out[0] = s0; out[1] = s1; out[2] = s2;
+  }
+  template <int DIR>
+  __device__ __forceinline__ void cyc_scan(double A, double c0, double c1, double& in0, double& in1) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double Ao, c0o, c1o;
+      if (DIR > 0) {
+        Ao = __shfl_up_sync(0xffffffffu, A, o); c0o = __shfl_up_sync(0xffffffffu, c0, o); c1o = __shfl_up_sync(0xffffffffu, c1, o);
+      } else {
+        Ao = __shfl_down_sync(0xffffffffu, A, o); c0o = __shfl_down_sync(0xffffffffu, c0, o); c1o = __shfl_down_sync(0xffffffffu, c1, o);
+      }
+      const bool ok = (DIR > 0) ? (lane >= o) : (lane + o < 32);
+      if (ok) { c0 = A * c0o + c0; c1 = A * c1o + c1; A = A * Ao; }
+    }
+    const int last = (DIR > 0) ? 31 : 0;
+    double* sc = area();
+    if (lane == last) { sc[w] = A; sc[nw + w] = c0; sc[2 * nw + w] = c1; }
+    __syncthreads();
+    // prefix of the warps in front of mine inside this CTA, and the CTA aggregate
+    double tA = 1.0, t0 = 0.0, t1 = 0.0, eA = 1.0, e0 = 0.0, e1 = 0.0;
+    for (int k = 0; k < nw; ++k) {
+      const int ww = (DIR > 0) ? k : nw - 1 - k;
+      if (ww == w) { eA = tA; e0 = t0; e1 = t1; }
+      const double a = sc[ww];
+      t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
+    }
+    if (threadIdx.x == 0) { sc[3 * nw] = tA; sc[3 * nw + 1] = t0; sc[3 * nw + 2] = t1; }
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    // compose the CTA aggregates in scan order
+    double gA = 1.0, g0_ = 0.0, g1_ = 0.0, pA = 1.0, p0 = 0.0, p1 = 0.0;
+    for (unsigned k = 0; k < C; ++k) {
+      const unsigned cc = (DIR > 0) ? k : C - 1 - k;
+      if (cc == rank) { pA = gA; p0 = g0_; p1 = g1_; }
+      const double* q = cl.map_shared_rank(sc + 3 * nw, cc);
+      const double a = q[0];
+      g0_ = a * g0_ + q[1]; g1_ = a * g1_ + q[2]; gA = a * gA;
+    }
+    const double inv = PK_RCP(1.0 - gA);
+    const double x0 = g0_ * inv, x1 = g1_ * inv;          // entering the first thread of the ring
+    const double y0 = pA * x0 + p0, y1 = pA * x1 + p1;    // entering my CTA
+    const double w0 = eA * y0 + e0, w1 = eA * y1 + e1;    // entering my warp
+    const double o0 = A * w0 + c0, o1 = A * w1 + c1;      // leaving my thread
+    double q0, q1;
+    if (DIR > 0) { q0 = __shfl_up_sync(0xffffffffu, o0, 1); q1 = __shfl_up_sync(0xffffffffu, o1, 1); }
+    else { q0 = __shfl_down_sync(0xffffffffu, o0, 1); q1 = __shfl_down_sync(0xffffffffu, o1, 1); }
+    const bool first = (DIR > 0) ? (lane == 0) : (lane == 31);
+    in0 = first ? w0 : q0; in1 = first ? w1 : q1;
+  }
+  template <class G, class P> __device__ __forceinline__ void scan_fwd(G get, P put) {
+    double A = 1.0, c0 = 0.0, c1 = 0.0, in0, in1;
+    get(th, A, c0, c1);
+    cyc_scan<+1>(A, c0, c1, in0, in1);
+    rA = 1.0; rc0 = 0.0; rc1 = 0.0;
+    put(th, in0, in1, rA, rc0, rc1);
+  }
+  template <class F> __device__ __forceinline__ void scan_rev(F fin) {
+    double in0, in1;
+    cyc_scan<-1>(rA, rc0, rc1, in0, in1);
+    fin(th, in0, in1);
+  }
+};
+
+template <int M, int MODE, int TB>
+__global__ void __launch_bounds__(TB, 1) pk_step_cluster_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a, int lgTc) {
+  extern __shared__ __align__(16) double smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), C = cluster.num_blocks();
+  const int Tc = blockDim.x, n = Tc * M;
+  SharedCluster sh;
+  sh.Tc = Tc; sh.lgTc = lgTc; sh.rank = rank;
+  { int lg = 0; while ((1 << lg) < p.T) ++lg; sh.lgT = lg; }
+  sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
+  double* nxt = smem + 3 * n;
+  if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
+  else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
+  else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
+  sh.xb = nxt; nxt += XB_SLOTS * Tc;
+  double* red = nxt; nxt += 2 * (3 * (Tc >> 5) + 3);
+  sh.dW = nxt;
+
+  const int r = blockIdx.x / C;
+  const long long off = (long long)r * p.ne;
+  const int t0 = (int)rank * Tc;
+  const int g0 = chunk_start(p, t0);
+  const int g1 = (rank == C - 1) ? p.ne : chunk_start(p, t0 + Tc);
+  for (int i = g0 + threadIdx.x; i < g1; i += blockDim.x) {
+    const int sl = row_slot_c<M, 0>(p, i);
+    sh.st(sh.U0, sl, a.u[off + i]); sh.st(sh.U1, sl, a.u1[off + i]); sh.st(sh.F, sl, a.dF[off + i]);
+    if (MODE == NOISE_FULL) sh.st(sh.G, sl, a.dG[off + i]);
+  }
+  cluster.sync();
+
+  Thread<M, MODE, 0> th;
+  th.init(p, t0 + (int)threadIdx.x);
+  GpuExecCluster<M, MODE> ex(th, red);
+  ex.rank = rank; ex.C = C; ex.g0 = g0; ex.g1 = g1;
+  StepIO io;
+  io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
+  io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
+  io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
+  run_steps<M, MODE, 0, GpuExecCluster<M, MODE>, Thread<M, MODE, 0> >(ex, p, sh, io);
+  cluster.sync();     // nobody leaves while a peer may still read its shared memory
+
+  for (int i = g0 + threadIdx.x; i < g1; i += blockDim.x) {
+    const int sl = row_slot_c<M, 0>(p, i);
+    a.u[off + i] = sh.ld(sh.U0, sl); a.u1[off + i] = sh.ld(sh.U1, sl); a.dF[off + i] = sh.ld(sh.F, sl);
+    if (MODE == NOISE_FULL) a.dG[off + i] = sh.ld(sh.G, sl);
+  }
+}
+

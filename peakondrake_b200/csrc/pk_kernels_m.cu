@@ -1,0 +1,47 @@
+// pk_kernels_m.cu -- instantiates the step kernels for ONE chunk size PK_M (5..8); compiled four times.
+#include "pk_kernels.cuh"
+#include "pk_dispatch.h"
+
+#ifndef PK_M
+#error "compile with -DPK_M=5|6|7|8"
+#endif
+
+
+template <int M> static ckern_t pick_cmode(int mode, int Tc) {
+  if (Tc <= 256) {
+    switch (mode) {
+      case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 256>;
+      case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 256>;
+      default: return pk_step_cluster_kernel<M, NOISE_FULL, 256>;
+    }
+  }
+  switch (mode) {
+    case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 512>;
+    case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 512>;
+    default: return pk_step_cluster_kernel<M, NOISE_FULL, 512>;
+  }
+}
+
+template <int M, int MODE> static kern_t pick_tb(int block, int T, int minb) {
+  if (T < 32) return pk_step_kernel<M, MODE, 32, 1, 0>;    // tiny meshes: some lanes of the single warp idle
+  if (T == 128) {
+    if (minb == 2) return pk_step_kernel<M, MODE, 128, 2, 128>;
+    if (minb == 4) return pk_step_kernel<M, MODE, 128, 4, 128>;
+    return pk_step_kernel<M, MODE, 128, 3, 128>;
+  }
+  if (block <= 128) return pk_step_kernel<M, MODE, 128, 2, 0>;
+  if (block <= 256) return pk_step_kernel<M, MODE, 256, 1, 256>;
+  return pk_step_kernel<M, MODE, 512, 1, 512>;
+}
+template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {
+  switch (mode) {
+    case NOISE_SCALAR: return pick_tb<M, NOISE_SCALAR>(block, T, minb);
+    case NOISE_X: return pick_tb<M, NOISE_X>(block, T, minb);
+    default: return pick_tb<M, NOISE_FULL>(block, T, minb);
+  }
+}
+
+#define PK_CAT2(a, b) a##b
+#define PK_CAT(a, b) PK_CAT2(a, b)
+kern_t PK_CAT(pk_pick_kernel_m, PK_M)(int mode, int block, int T, int minb) { return pick_mode<PK_M>(mode, block, T, minb); }
+ckern_t PK_CAT(pk_pick_cluster_kernel_m, PK_M)(int mode, int Tc) { return pick_cmode<PK_M>(mode, Tc); }

@@ -28,7 +28,7 @@ struct UpwindIO {
   double* u;              // [R, ne]
   const double* dW_in;    // [nsteps, R, nxi] or null -> Philox
   double* dW_out;
-  const double* xi;       // [nxi, ne]
+  const double* xi;       // [nxi, T*M] chunk-interleaved table (permute_table)
   int R, r;
   unsigned rid;
   unsigned long long seed;
@@ -79,7 +79,7 @@ struct UpwindThread {
     for (int j = 0; j < M; ++j) {
       double X = 0.0;
       if (j < m) {
-        if (XARR) { for (int k = 0; k < p.nxi; ++k) X += sh.dw(k) * xi[k * p.ne + s + j]; }
+        if (XARR) { for (int k = 0; k < p.nxi; ++k) X += sh.dw(k) * xi[k * T * M + j * T + t]; }
         else X = (p.nxi > 0) ? sh.dw(0) * p.xi_const : 0.0;
       }
       sv[j] = p.dt * u[j] + X;

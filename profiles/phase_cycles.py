@@ -10,8 +10,10 @@ sys.path.insert(0, ROOT)
 lib_path = os.path.join(ROOT, 'peakondrake_b200', 'libpeakon_b200_prof.so')
 subprocess.check_call(['/usr/local/cuda/bin/nvcc', '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a',
                        '-lineinfo', '-Xcompiler', '-fPIC', '-shared', '-diag-suppress', '128', '-DPK_PROFILE',
-                       '-o', lib_path, os.path.join(ROOT, 'peakondrake_b200', 'csrc', 'pk_lib.cu'),
-                       os.path.join(ROOT, 'peakondrake_b200', 'csrc', 'pk_upwind_lib.cu')])
+                       '-DPK_M=8', '-DPK_PROFILE_SINGLE_M', '-o', lib_path,
+                       os.path.join(ROOT, 'peakondrake_b200', 'csrc', 'pk_lib.cu'),
+                       os.path.join(ROOT, 'peakondrake_b200', 'csrc', 'pk_upwind_lib.cu'),
+                       os.path.join(ROOT, 'peakondrake_b200', 'csrc', 'pk_kernels_m.cu')])
 from peakondrake_b200 import _lib
 _lib.LIB_PATH = lib_path
 import torch

@@ -188,9 +188,13 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
   if (forceT > 0) { p.T = forceT; p.M = forceM; p.rem = ne - forceT * (forceM - 1); if (p.rem < 0 || p.rem > p.T) return -2; }
   else if (!choose_layout(ne, &p.T, &p.M, &p.rem)) return -1;
   fill_constants(p);
+  std::vector<double> pt[3];
+  const double* src[3] = {xi, xi_x, xi_xx};
+  const double* tab[3] = {nullptr, nullptr, nullptr};
+  for (int q = 0; q < 3; ++q) if (src[q] && nxi > 0) { pt[q].resize((size_t)nxi * p.T * p.M); permute_table_host(p, src[q], pt[q].data()); tab[q] = pt[q].data(); }
   for (int r = 0; r < R; ++r) {
     StepIO io;
-    io.dW_in = dW_in; io.dW_out = dW_out; io.xi = xi; io.xi_x = xi_x; io.xi_xx = xi_xx;
+    io.dW_in = dW_in; io.dW_out = dW_out; io.xi = tab[0]; io.xi_x = tab[1]; io.xi_xx = tab[2];
     io.R = R; io.r = r; io.rid = rid0 + r; io.seed = seed; io.step0 = step0; io.nsteps = nsteps;
     io.fail_step = fail_step; io.its_last = its_last; io.its_total = its_total; io.fail_reason = fail_reason;
     switch (p.M) {
@@ -227,9 +231,11 @@ extern "C" int pk_emu_step_upwind(int ne, double Ld, double dt, double alphasq, 
   p.max_it = 50; p.rtol = 1e-8; p.atol = 1e-50; p.stol = 1e-8; p.divtol = 1e4; p.xi_const = xi_const;
   if (!choose_layout(ne, &p.T, &p.M, &p.rem)) return -1;
   fill_constants(p);
+  std::vector<double> pt;
+  if (xi && nxi > 0) { pt.resize((size_t)nxi * p.T * p.M); permute_table_host(p, xi, pt.data()); }
   for (int r = 0; r < R; ++r) {
     UpwindIO io;
-    io.m = m; io.u = u; io.dW_in = dW_in; io.dW_out = dW_out; io.xi = xi; io.R = R; io.r = r; io.rid = rid0 + r;
+    io.m = m; io.u = u; io.dW_in = dW_in; io.dW_out = dW_out; io.xi = pt.empty() ? nullptr : pt.data(); io.R = R; io.r = r; io.rid = rid0 + r;
     io.seed = seed; io.step0 = step0; io.nsteps = nsteps; io.fail_step = fail_step;
 #define UW_CASE(MM) case MM: if (xarr) run_upwind_one<MM, 1>(p, io, order); else run_upwind_one<MM, 0>(p, io, order); break;
     switch (p.M) { UW_CASE(5) UW_CASE(6) UW_CASE(7) UW_CASE(8) default: return -3; }
