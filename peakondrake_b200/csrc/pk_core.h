@@ -168,6 +168,7 @@ struct Thread {
   double hF[M], hG[M];            // Helmholtz work (rhs -> y -> x)
   double fn2, sn2, xn2;           // partial sums: |R|^2, |delta|^2, |w1|^2
   double Xs;                      // NOISE_SCALAR: dXi value of this step
+  double dw_hold;                 // my pre-drawn Brownian increment (draw_step)
 
   PK_HD void init(const Params& p, int tid) {
     t = tid; active = (tid < TN(p));
@@ -175,7 +176,7 @@ struct Thread {
     m = chunk_rows(p, tt); s = chunk_start(p, tt); ext = (m == M);
     tl = (tt + TN(p) - 1) & (TN(p) - 1); tr = (tt + 1) & (TN(p) - 1);
     ml = chunk_rows(p, tl);
-    fn2 = sn2 = xn2 = 0.0; Xs = 0.0;
+    fn2 = sn2 = xn2 = 0.0; Xs = 0.0; dw_hold = 0.0;
   }
 
   // ---- liveness helpers ---------------------------------------------------------------------
@@ -698,6 +699,48 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
   return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Brownian increments of step n into sh.dW[0..nxi): read from dW_in or drawn with Philox.  With
+// nxi <= nth every thread of a block owns one (step, mode) pair of a window of nth/nxi steps and keeps
+// its value in a register (`hold`), so the generator runs once per window on all threads instead of
+// once per step on nxi threads.  Every block of a cluster draws the same numbers; the leader exports.
+// ------------------------------------------------------------------------------------------------
+struct DrawIO {
+  const double* dW_in; double* dW_out;
+  int R, r, step0, nsteps;
+  unsigned rid;
+  unsigned long long seed;
+};
+PK_HD double draw_one(const Params& p, const DrawIO& d, int n, int k) {
+  const long long o = ((long long)n * d.R + d.r) * p.nxi + k;
+  if (d.dW_in) return d.dW_in[o];
+  double w = 0.0;
+  for (int j = 0; j < p.nupd; ++j)
+    w += philox_normal(d.seed, d.rid, (unsigned)(d.step0 + n), (unsigned)k, (unsigned)j) * p.sdt;
+  return w;
+}
+template <class SH>
+PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int tid, int nth, bool leader, double& hold) {
+  if (p.nxi <= 0) return;
+  if (p.nxi > nth) {                       // more modes than threads: plain loop
+    for (int k = tid; k < p.nxi; k += nth) {
+      const double w = draw_one(p, d, n, k);
+      sh.set_dw(k, w);
+      if (leader && d.dW_out) d.dW_out[((long long)n * d.R + d.r) * p.nxi + k] = w;
+    }
+    return;
+  }
+  const int per = nth / p.nxi;             // steps per window
+  const int mine = tid / p.nxi, k = tid - mine * p.nxi;
+  const int w0 = n - (n % per);            // first step of the current window
+  if (n == w0 && mine < per && w0 + mine < d.nsteps) hold = draw_one(p, d, w0 + mine, k);
+  if (mine == n - w0 && mine < per) {
+    sh.set_dw(k, hold);
+    if (leader && d.dW_out) d.dW_out[((long long)n * d.R + d.r) * p.nxi + k] = hold;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block-level orchestration, templated on an executor that provides
 //   each(f)            run f(Thread&) on every thread of the realisation
@@ -707,7 +750,7 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 //                      that get() returns, in thread order 0..T-1; put() receives the value entering
 //                      its thread and returns the maps of the following reverse scan
 //   scan_rev(fin)      the reverse cyclic scan (order T-1..0); fin() receives the entering value
-//   each_tid(f)        run f(tid, nthreads, leader, g0, g1) on every thread of every block working on the
+//   each_tid(f)        run f(th, tid, nthreads, leader, g0, g1) on every thread of every block working on the
 //                      realisation: block-local thread id / count, whether the block is the cluster
 //                      leader, and the range of mesh rows the block owns
 //   one(f)             run f() once (thread 0)
@@ -750,24 +793,15 @@ template <int M, int MODE, int TT, class Exec, class Th, class SH>
 PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) {
   int failed = io.fail_step[io.r];
   int its_last = 0, its_total = io.its_total[io.r], reason = 0;
+  DrawIO dio;
+  dio.dW_in = io.dW_in; dio.dW_out = io.dW_out; dio.R = io.R; dio.r = io.r; dio.step0 = io.step0;
+  dio.nsteps = io.nsteps; dio.rid = io.rid; dio.seed = io.seed;
   int expect = 2;     // iteration at which convergence is expected: there only the residual is evaluated first
   for (int n = 0; n < io.nsteps; ++n) {
     ex.each([&](Th& th) { th.kill_all(); });
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
-    ex.each_tid([&](int tid, int nth, bool leader, int, int) {
-      for (int k = tid; k < p.nxi; k += nth) {
-        const long long o = ((long long)n * io.R + io.r) * p.nxi + k;
-        double w;
-        if (io.dW_in) {
-          w = io.dW_in[o];
-        } else {
-          w = 0.0;
-          for (int j = 0; j < p.nupd; ++j)
-            w += philox_normal(io.seed, io.rid, (unsigned)(io.step0 + n), (unsigned)k, (unsigned)j) * p.sdt;
-        }
-        sh.set_dw(k, w);
-        if (leader && io.dW_out) io.dW_out[o] = w;
-      }
+    ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
+      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold);
     });
     ex.sync();
     ex.tick(0);

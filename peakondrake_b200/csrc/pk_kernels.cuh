@@ -26,7 +26,7 @@ struct GpuExecT {
 
   template <class F> __device__ __forceinline__ void each(F f) { if (AA || th.active) f(th); }
   int ne_;
-  template <class F> __device__ __forceinline__ void each_tid(F f) { f((int)threadIdx.x, (int)blockDim.x, true, 0, ne_); }
+  template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, (int)blockDim.x, true, 0, ne_); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
 #ifdef PK_PROFILE
   long long tlast; long long* tbuf;   // per-phase cycle buckets (thread 0 of each CTA), profiling builds only
@@ -212,7 +212,7 @@ struct GpuExecCluster {
   double rA, rc0, rc1;
   __device__ __forceinline__ GpuExecCluster(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
   template <class F> __device__ __forceinline__ void each(F f) { f(th); }
-  template <class F> __device__ __forceinline__ void each_tid(F f) { f((int)threadIdx.x, (int)blockDim.x, rank == 0, g0, g1); }
+  template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, (int)blockDim.x, rank == 0, g0, g1); }
   __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
   __device__ __forceinline__ void tick(int) {}
   template <class F> __device__ __forceinline__ void one(F f) { if (rank == 0 && threadIdx.x == 0) f(); }

@@ -45,6 +45,7 @@ struct UpwindThread {
   double sv[M];              // us at my nodes
   double sR;                 // us at the first node of the right neighbour
   double hh[M];              // Helmholtz work
+  double dw_hold;            // my pre-drawn Brownian increment (draw_step)
   static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
 
   PK_HD void init(const Params& p, int tid) {
@@ -62,7 +63,7 @@ struct UpwindThread {
       mL[j] = mR[j] = u[j] = 0.0; aL[j] = aR[j] = 0.0; hh[j] = 0.0; sv[j] = 0.0;
       if (j < m) { mL[j] = io.m[2 * (off + s + j)]; mR[j] = io.m[2 * (off + s + j) + 1]; u[j] = io.u[off + s + j]; }
     }
-    sR = 0.0;
+    sR = 0.0; dw_hold = 0.0;
   }
   PK_HD void store(const Params& p, const UpwindIO& io) const {
     const long long off = (long long)io.r * p.ne;
@@ -176,22 +177,14 @@ struct UpwindThread {
 template <int M, int XARR, int TT, class Exec, class Th, class SH>
 PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const UpwindIO& io, int* flag) {
   int failed = io.fail_step[io.r];
+  DrawIO dio;
+  dio.dW_in = io.dW_in; dio.dW_out = io.dW_out; dio.R = io.R; dio.r = io.r; dio.step0 = io.step0;
+  dio.nsteps = io.nsteps; dio.rid = io.rid; dio.seed = io.seed;
   ex.each([&](Th& th) { th.load(p, io); });
   ex.one([&]() { *flag = 0; });
   for (int n = 0; n < io.nsteps; ++n) {
-    ex.each_tid([&](int tid, int nth, bool leader, int, int) {
-      for (int k = tid; k < p.nxi; k += nth) {
-        const long long o = ((long long)n * io.R + io.r) * p.nxi + k;
-        double w;
-        if (io.dW_in) w = io.dW_in[o];
-        else {
-          w = 0.0;
-          for (int j = 0; j < p.nupd; ++j)
-            w += philox_normal(io.seed, io.rid, (unsigned)(io.step0 + n), (unsigned)k, (unsigned)j) * p.sdt;
-        }
-        sh.set_dw(k, w);
-        if (leader && io.dW_out) io.dW_out[o] = w;
-      }
+    ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
+      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold);
     });
     ex.sync();
     if (failed >= 0) continue;

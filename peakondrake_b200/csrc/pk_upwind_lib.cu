@@ -18,7 +18,7 @@ struct UwExec {
   double rA, rc0, rc1;
   __device__ __forceinline__ UwExec(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
   template <class F> __device__ __forceinline__ void each(F f) { if (AA || th.active) f(th); }
-  template <class F> __device__ __forceinline__ void each_tid(F f) { f((int)threadIdx.x, (int)blockDim.x, true, 0, ne_); }
+  template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, (int)blockDim.x, true, 0, ne_); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void tick(int) {}
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }

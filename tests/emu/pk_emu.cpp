@@ -57,7 +57,7 @@ struct EmuExecT {
       const int t = order == 0 ? k : T - 1 - k;
       const int c = t / Tc; cur = c;
       const int g0 = chunk_start(pp, c * Tc), g1 = (c == C - 1) ? ne : chunk_start(pp, (c + 1) * Tc);
-      f(t % Tc, Tc, c == 0, g0, g1);
+      f(th[t], t % Tc, Tc, c == 0, g0, g1);
     }
   }
   void sync() {}
