@@ -86,19 +86,34 @@ struct CellC {
   double dN1L0, dN1L1, dN1R0, dN1R1;
   double dfL0, dfL1, dfR0, dfR1;
   double dgL0, dgL1, dgR0, dgR1;
-  PK_HD void compute(const Params& p, const NodeS& A, const NodeS& B) {
+  // values only (residual evaluation)
+  PK_HD void compute_res(const Params& p, const NodeS& A, const NodeS& B) {
     const double da = B.a - A.a;
     const double sL = 2.0 * A.v + B.v, sR = A.v + 2.0 * B.v;
     const double da6 = da * (1.0 / 6.0);
     N1L = da6 * sL; N1R = da6 * sR;
-    const double dd = da6 * p.dt;
-    dN1L0 = -sL * (1.0 / 6.0) + 2.0 * dd; dN1L1 = sL * (1.0 / 6.0) + dd;
-    dN1R0 = -sR * (1.0 / 6.0) + dd;       dN1R1 = sR * (1.0 / 6.0) + 2.0 * dd;
     const double a0 = A.a, a1 = B.a;
     const double a00 = a0 * a0, a01 = a0 * a1, a11 = a1 * a1;
     const double cda2 = p.c2 * da * da;
     fL = p.c1 * (3.0 * a00 + 2.0 * a01 + a11) + cda2;
     fR = p.c1 * (a00 + 2.0 * a01 + 3.0 * a11) + cda2;
+    if (MODE == NOISE_FULL) {
+      const double x0 = A.x, x1 = B.x, y0 = A.y, y1 = B.y;
+      const double xs = x0 + x1;
+      gL = p.h6 * (a0 * (3.0 * x0 + x1) + a1 * xs) + p.a26 * da * (2.0 * y0 + y1);
+      gR = p.h6 * (a0 * xs + a1 * (x0 + 3.0 * x1)) + p.a26 * da * (y0 + 2.0 * y1);
+    } else {
+      gL = gR = 0.0;
+    }
+  }
+  // derivatives with respect to the two nodal values of uh (Jacobian rows)
+  PK_HD void compute_jac(const Params& p, const NodeS& A, const NodeS& B) {
+    const double da = B.a - A.a;
+    const double sL = 2.0 * A.v + B.v, sR = A.v + 2.0 * B.v;
+    const double dd = da * (1.0 / 6.0) * p.dt;
+    dN1L0 = -sL * (1.0 / 6.0) + 2.0 * dd; dN1L1 = sL * (1.0 / 6.0) + dd;
+    dN1R0 = -sR * (1.0 / 6.0) + dd;       dN1R1 = sR * (1.0 / 6.0) + 2.0 * dd;
+    const double a0 = A.a, a1 = B.a;
     const double k = 2.0 * p.c2 * da;
     const double s2 = 2.0 * p.c1 * (a0 + a1);
     dfL0 = p.c1 * (6.0 * a0 + 2.0 * a1) - k; dfL1 = s2 + k;
@@ -107,14 +122,13 @@ struct CellC {
       const double x0 = A.x, x1 = B.x, y0 = A.y, y1 = B.y;
       const double yL = 2.0 * y0 + y1, yR = y0 + 2.0 * y1;
       const double xs = x0 + x1;
-      gL = p.h6 * (a0 * (3.0 * x0 + x1) + a1 * xs) + p.a26 * da * yL;
-      gR = p.h6 * (a0 * xs + a1 * (x0 + 3.0 * x1)) + p.a26 * da * yR;
       dgL0 = p.h6 * (3.0 * x0 + x1) - p.a26 * yL; dgL1 = p.h6 * xs + p.a26 * yL;
       dgR0 = p.h6 * xs - p.a26 * yR;              dgR1 = p.h6 * (x0 + 3.0 * x1) + p.a26 * yR;
     } else {
-      gL = gR = dgL0 = dgL1 = dgR0 = dgR1 = 0.0;
+      dgL0 = dgL1 = dgR0 = dgR1 = 0.0;
     }
   }
+  PK_HD void compute(const Params& p, const NodeS& A, const NodeS& B) { compute_res(p, A, B); compute_jac(p, A, B); }
 };
 
 // What node l contributes to pentadiagonal rows l-1 (Cp,Qp), l (C0,Q0) and l+1 (Cm,Qm).
@@ -227,7 +241,7 @@ struct Thread {
   }
 
   // Residual and Jacobian rows of node n0 (neighbours nm, np; cells pc = (nm,n0), cc = (n0,np)).
-  PK_HD void node_packet(const Params& p, const CellC<MODE>& cc, Packet& k) {
+  PK_HD void node_packet(const Params& p, const CellC<MODE>& cc, Packet& k, bool lite) {
     const double N1 = pc.N1R + cc.N1L, ff = pc.fR + cc.fL;
     const double Rpsi = p.mb * (nm.w + np.w) + p.ma * n0.w + N1 - 0.5 * (nm.F - np.F)
                         + ((MODE == NOISE_FULL) ? (p.mb * (nm.G + np.G) + p.ma * n0.G) : 0.0);
@@ -235,6 +249,7 @@ struct Thread {
     double Rzeta = 0.0;
     if (MODE == NOISE_FULL) Rzeta = p.hb * (nm.G + np.G) + p.ha * n0.G - (pc.gR + cc.gL);
     fn2 += Rpsi * Rpsi + Rphi * Rphi + Rzeta * Rzeta;
+    if (lite) return;                    // residual norm only (uniform across the block)
     const double B[3] = {0.5 * pc.dN1R0, 0.5 * (pc.dN1R1 + cc.dN1L0), 0.5 * cc.dN1L1};
     const double Fm[3] = {0.5 * pc.dfR0, 0.5 * (pc.dfR1 + cc.dfL0), 0.5 * cc.dfL1};
     double Gm[3] = {0.0, 0.0, 0.0};
@@ -302,10 +317,12 @@ struct Thread {
 
   // One streaming iteration q >= 1: cell (q-1, q); finalises node q-1 and row q-2.
   template <class SH>
-  PK_HD void stream(const Params& p, const SH& sh, int q) {
+  PK_HD void stream(const Params& p, const SH& sh, int q, bool lite) {
     load_node(p, sh, q, np);
-    CellC<MODE> cc; cc.compute(p, n0, np);
-    Packet k; node_packet(p, cc, k);           // node q-1
+    CellC<MODE> cc; cc.compute_res(p, n0, np);
+    if (!lite) cc.compute_jac(p, n0, np);
+    Packet k; node_packet(p, cc, k, lite);     // node q-1
+    if (lite) { nm = n0; n0 = np; pc.N1R = cc.N1R; pc.fR = cc.fR; pc.gR = cc.gR; return; }
     const int n = q - 1;
     if (n == 0) {
       // separator row 0 so far: H*M part, own C0/Q0 (Cm of the left neighbour is added in reduce_build)
@@ -321,50 +338,30 @@ struct Thread {
     nm = n0; n0 = np; pc = cc;
   }
 
-  // ---- residual norm only (no Jacobian, no elimination): used when convergence is expected -----
-  template <class SH>
-  PK_HD void residual_only(const Params& p, const SH& sh) {
-    fn2 = 0.0;
-    NodeS a_, b_, c_;
-    load_node(p, sh, -1, a_);
-    load_node(p, sh, 0, b_);
-    CellC<MODE> c0; c0.compute(p, a_, b_);
-    PK_UNROLL
-    for (int q = 1; q <= M; ++q) {
-      if (q <= m) {
-        load_node(p, sh, q, c_);
-        CellC<MODE> c1; c1.compute(p, b_, c_);
-        const double Rpsi = p.mb * (a_.w + c_.w) + p.ma * b_.w + (c0.N1R + c1.N1L) - 0.5 * (a_.F - c_.F)
-                            + ((MODE == NOISE_FULL) ? (p.mb * (a_.G + c_.G) + p.ma * b_.G) : 0.0);
-        const double Rphi = p.hb * (a_.F + c_.F) + p.ha * b_.F - (c0.fR + c1.fL);
-        double Rzeta = 0.0;
-        if (MODE == NOISE_FULL) Rzeta = p.hb * (a_.G + c_.G) + p.ha * b_.G - (c0.gR + c1.gL);
-        fn2 += Rpsi * Rpsi + Rphi * Rphi + Rzeta * Rzeta;
-        a_ = b_; b_ = c_; c0 = c1;
-      }
-    }
-  }
-
   // ---- phase A1: first two cells, publish first-node packet --------------------------------
   template <class SH>
-  PK_HD void assemble_begin(const Params& p, const SH& sh) {
+  // lite: evaluate the residual norm only (no Jacobian, no elimination) -- the same code, so that the
+  // convergence check does not cost a second copy of the assembly in the instruction cache
+  PK_HD void assemble_begin(const Params& p, const SH& sh, bool lite) {
     fn2 = 0.0;
     kill_factors();
     load_node(p, sh, -1, nm);
     load_node(p, sh, 0, n0);
-    pc.compute(p, nm, n0);
+    pc.compute_res(p, nm, n0);
+    if (!lite) pc.compute_jac(p, nm, n0);
     PK_UNROLL
     for (int c = 0; c < 3; ++c) { wCm1[c] = 0.0; wCm2[c] = 0.0; wC01[c] = 0.0; }
     wQm1 = wQm2 = wQ01 = 0.0;
-    stream(p, sh, 1);
+    stream(p, sh, 1, lite);
   }
 
   // ---- phase A2: rest of the chunk, interior LU, tips; publishes tips + last packet --------
   template <class SH>
-  PK_HD void assemble_finish(const Params& p, const SH& sh) {
+  PK_HD void assemble_finish(const Params& p, const SH& sh, bool lite) {
     PK_UNROLL
-    for (int q = 2; q <= M - 1; ++q) stream(p, sh, q);
-    if (ext) stream(p, sh, M);
+    for (int q = 2; q <= M - 1; ++q) stream(p, sh, q, lite);
+    if (ext) stream(p, sh, M, lite);
+    if (lite) return;
     // last row (m-1): Cp,Qp come from the right neighbour's first node
     double cp[3];
     cp[0] = sh.ld(sh.xb, 14 * TN(p) + tr); cp[1] = sh.ld(sh.xb, 15 * TN(p) + tr); cp[2] = sh.ld(sh.xb, 16 * TN(p) + tr);
@@ -818,16 +815,17 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       if (it > 0 && it >= expect) {
         // convergence is expected here: evaluate the residual only; fall through to the full
         // assembly (which recomputes it) in the rare case it is not
-        ex.each([&](Th& th) { th.residual_only(p, sh); });
+        ex.each([&](Th& th) { th.assemble_begin(p, sh, true); });
+        ex.each([&](Th& th) { th.assemble_finish(p, sh, true); });
         ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
         status = snes_test(p, it, nrm, fnorm0, reason);
         ex.tick(2);
         if (status) break;
       }
-      ex.each([&](Th& th) { th.assemble_begin(p, sh); });
+      ex.each([&](Th& th) { th.assemble_begin(p, sh, false); });
       ex.sync();
       ex.tick(3);
-      ex.each([&](Th& th) { th.assemble_finish(p, sh); });
+      ex.each([&](Th& th) { th.assemble_finish(p, sh, false); });
       ex.tick(4);
       ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
       status = snes_test(p, it, nrm, fnorm0, reason);

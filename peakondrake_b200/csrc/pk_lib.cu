@@ -338,6 +338,14 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (cfg->noise_mode == PK_NOISE_SCALAR && cfg->num_xis > 1)
     return fail(nullptr, "pk_create: scalar noise supports one Xi only (reference stochastic_functions.py:111-112)");
   { const char* e = getenv("PK_MINB"); g_minb = e ? atoi(e) : 0; }
+  if (g_minb == 0) {
+    // resident CTAs/SM of the 128-thread kernel: 3 (168 regs) has ~13 % more throughput per SM than 2
+    // (206 regs) but a CTA-step takes ~1.3x longer; pick whatever finishes the R realisations first
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    const double w2 = (double)((cfg->R + 2 * sms - 1) / (2 * sms)), w3 = 1.33 * (double)((cfg->R + 3 * sms - 1) / (3 * sms));
+    g_minb = (w3 < w2) ? 3 : 2;
+  }
   pk_ctx* c = new pk_ctx();
   c->cfg = *cfg;
   Params& p = c->p;
