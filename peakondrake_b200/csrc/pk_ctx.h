@@ -16,6 +16,7 @@ struct pk_ctx {
   int block;
   int cluster;         // CTAs per realisation (1 = single-CTA kernel)
   int lgTc;
+  int minb;            // resident CTAs/SM the 128-thread midpoint kernel is compiled for
   std::string err;
   // internal device buffers for the *_host entry points
   double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;

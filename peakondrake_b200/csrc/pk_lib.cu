@@ -302,8 +302,7 @@ int pk_fail(pk_ctx* c, const char* fmt, ...) {
   return -1;
 }
 
-static int g_minb = 0;   // PK_MINB env: resident CTAs/SM the 128-thread kernel is compiled for (2, 3 or 4)
-static kern_t pick_kernel(const Params& p, int block) {
+static kern_t pick_kernel(const Params& p, int block, int g_minb) {
   switch (p.M) {
     case 5: return pk_pick_kernel_m5(p.mode, block, p.T, g_minb);
     case 6: return pk_pick_kernel_m6(p.mode, block, p.T, g_minb);
@@ -337,6 +336,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     return fail(nullptr, "pk_create: the upwind scheme takes dXi only (noise_mode SCALAR or X)");
   if (cfg->noise_mode == PK_NOISE_SCALAR && cfg->num_xis > 1)
     return fail(nullptr, "pk_create: scalar noise supports one Xi only (reference stochastic_functions.py:111-112)");
+  int g_minb = 0;   // PK_MINB env: resident CTAs/SM the 128-thread kernel is compiled for (2, 3 or 4)
   { const char* e = getenv("PK_MINB"); g_minb = e ? atoi(e) : 0; }
   if (g_minb == 0) {
     // resident CTAs/SM of the 128-thread kernel: 3 (168 regs) has ~13 % more throughput per SM than 2
@@ -348,6 +348,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   }
   pk_ctx* c = new pk_ctx();
   c->cfg = *cfg;
+  c->minb = g_minb;
   Params& p = c->p;
   memset(&p, 0, sizeof(p));
   p.ne = cfg->ne; p.h = cfg->Ld / cfg->ne; p.dt = cfg->dt; p.alphasq = cfg->alphasq;
@@ -387,7 +388,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->timed = false;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
-  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block) : (const void*)pick_kernel(p, c->block);
+  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block) : (const void*)pick_kernel(p, c->block, c->minb);
   if (c->cluster > 8) cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   e = cfg->scheme == 1 ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaFuncSetAttribute(smem=%zu): %s", c->smem, m.c_str()); }
@@ -477,7 +478,7 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
     lc.attrs = at; lc.numAttrs = 1;
     CK(c, cudaLaunchKernelEx(&lc, pick_cluster_kernel(c->p, c->block), c->p, a, c->lgTc));
   } else {
-    kern_t k = pick_kernel(c->p, c->block);
+    kern_t k = pick_kernel(c->p, c->block, c->minb);
     k<<<c->cfg.R, c->block, c->smem, st>>>(c->p, a);
   }
   CK(c, cudaGetLastError());

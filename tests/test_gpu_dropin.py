@@ -172,3 +172,31 @@ def test_reference_test_dumping_script_parameters(tmp_path, monkeypatch):
         experiment(code, Ld, tmax, resolutions=20, dts=dt, sigmas=0.25, seeds=0, schemes='upwind',
                    timesteppings='ssprk3', ics='one_peak', num_Xis=7, Xi_family='sines', alphasq=1.0, c0=0., gamma=0.,
                    diagnostics=['energy'])
+
+
+def test_experiment_multi_parameter_sweep_schema(tmp_path, monkeypatch):
+    """Swept resolutions x seeds x sigmas: dimension order and indexing of data.nc (experiment.py:59-156:
+    'resolution' first, then the order of the parameter dictionary)."""
+    from peakondrake_b200 import experiment, outputting as out
+    monkeypatch.chdir(tmp_path)
+    res, seeds, sigmas = [100, 200], [3, 4, 5], [0.0, 0.2]
+    experiment('sweep', 40., 0.004, resolutions=res, dts=1e-3, sigmas=sigmas, seeds=seeds, schemes='hydrodynamic',
+               timesteppings='midpoint', ics='proper_peak', num_Xis=2, Xi_family='sines', alphasq=1.0, c0=0., gamma=0.,
+               diagnostics=['energy', 'max_du', 'q_pde'], ndump=2, allow_fail=True)
+    d = out.read_data_file('results/sweep/data.nc')
+    assert d['energy'].shape == (3, 2, 3, 2)            # (time, resolution, seed, sigma)
+    assert d['failed_time'].shape == (2, 3, 2) and d['wallclock_time'].shape == (2, 2, 3, 2)
+    assert np.allclose(d['deltax'], [0.4, 0.2]) and list(d['seed']) == seeds and np.allclose(d['sigma'], sigmas)
+    assert d['x'].shape == (100,)                       # swept resolution -> fixed 100-point x axis (:113-115)
+    # sigma = 0: every seed gives the same (deterministic) answer; sigma > 0: seeds differ
+    assert np.ptp(d['energy'][2, :, :, 0], axis=1).max() == 0.0
+    assert np.ptp(d['energy'][2, :, :, 1], axis=1).min() > 0.0
+    for ir, ne in enumerate(res):
+        mesh = O.Mesh1D(ne, 40.)
+        u0 = O.initial_u(mesh, 'proper_peak')
+        tabs = O.noise_tables(mesh, 'sines', 2, 0.2)
+        for js, s in enumerate(seeds):
+            ref = O.run(ne, 40., 1e-3, 4, u0, O.reference_dW(s, 4, 2, 1e-3), tabs)
+            orc = ref['oracle']
+            e = ref['u'] @ (orc.M @ ref['u']) + ref['u'] @ (orc.K @ ref['u'])
+            assert abs(d['energy'][2, ir, js, 1] - e) <= 1e-10 * e
