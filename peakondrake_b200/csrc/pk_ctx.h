@@ -16,7 +16,11 @@ struct pk_ctx {
   int block;
   int cluster;         // CTAs per realisation (1 = single-CTA kernel)
   int lgTc;
-  int minb;            // resident CTAs/SM the 128-thread midpoint kernel is compiled for
+  int group;           // realisations per CTA of the persistent lock-step kernel (0 = kernel not used)
+  int gdoubles;        // its shared-memory doubles per realisation
+  int sms;             // multiprocessors of the device
+  int* d_queue;        // [1 + R] work counter + per-realisation finished-block counters
+  int last_nb, last_nblk, last_grid;   // work split of the last pk_step launch (pk_get_work_split)
   std::string err;
   // internal device buffers for the *_host entry points
   double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;

@@ -121,8 +121,13 @@ class EnsembleIntegrator(object):
     def layout(self):
         T, M, rem, smem = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32())
         c = self.lib.pk_get_layout(self.ctx, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem), ctypes.byref(smem))
-        return dict(threads=T.value, rows_per_thread=M.value, rem=rem.value, smem_bytes=smem.value,
-                    ctas_per_realisation=max(1, c))
+        d = dict(threads=T.value, rows_per_thread=M.value, rem=rem.value, smem_bytes=smem.value,
+                 ctas_per_realisation=max(1, c))
+        g, nb, nblk, grid = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32())
+        self.lib.pk_get_work_split(self.ctx, ctypes.byref(g), ctypes.byref(nb), ctypes.byref(nblk), ctypes.byref(grid))
+        if g.value:     # persistent lock-step kernel: realisations per CTA and the work split of the last launch
+            d.update(realisations_per_cta=g.value, step_blocks=nb.value, steps_per_block=nblk.value, ctas=grid.value)
+        return d
 
     @property
     def step_counter(self):

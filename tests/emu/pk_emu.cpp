@@ -63,6 +63,7 @@ struct EmuExecT {
   void sync() {}
   void tick(int) {}
   template <class F> void one(F f) { f(); }
+  bool any(bool b) { return b; }
   template <class F> void allreduce3(F f, double* out) {
     out[0] = out[1] = out[2] = 0.0;
     for (int t = 0; t < T; ++t) { double v[3]; f(th[t], v); out[0] += v[0]; out[1] += v[1]; out[2] += v[2]; }
@@ -92,6 +93,8 @@ struct EmuExecT {
     cyc_scan(-1, in0, in1);
     each([&](Th& h) { fin(h, in0[h.t], in1[h.t]); });
   }
+  template <class G, class P> void scan_fwd(bool, G get, P put) { scan_fwd(get, put); }
+  template <class F> void scan_rev(bool, F fin) { scan_rev(fin); }
 };
 
 template <int M, int MODE>
@@ -123,6 +126,7 @@ static int run_one_cluster(const Params& p, StepIO io, double* u, double* u1, do
   return bad;
 }
 
+static int g_emu_nblk = 0;
 template <int M, int MODE>
 static void run_one(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
   const int n = p.T * p.M;
@@ -137,8 +141,16 @@ static void run_one(const Params& p, StepIO io, double* u, double* u1, double* d
     sh.U0[sl] = u[off + i]; sh.U1[sl] = u1[off + i]; sh.F[sl] = dF[off + i];
     sh.G[sl] = (MODE == NOISE_FULL) ? dG[off + i] : 0.0;
   }
-  EmuExec<M, MODE> ex(p, order);
-  run_steps<M, MODE, 0, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+  // g_emu_nblk > 0: advance in work items of g_emu_nblk steps, each with fresh per-thread state (what a
+  // different slot of the persistent lock-step kernel sees when it picks up the next block); the trip
+  // count is padded by one barrier-only iteration like an uneven last block
+  const int nblk = g_emu_nblk > 0 ? g_emu_nblk : io.nsteps;
+  for (int b0 = 0; b0 < io.nsteps || b0 == 0; b0 += nblk) {
+    EmuExec<M, MODE> ex(p, order);
+    io.n0 = b0; io.n1 = b0 + nblk < io.nsteps ? b0 + nblk : io.nsteps; io.nloop = nblk + (g_emu_nblk > 0 ? 1 : 0);
+    run_steps<M, MODE, 0, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+    if (nblk <= 0) break;
+  }
   for (int i = 0; i < p.ne; ++i) {
     const int sl = row_slot(p, i);
     u[off + i] = sh.U0[sl]; u1[off + i] = sh.U1[sl]; dF[off + i] = sh.F[sl];
@@ -166,6 +178,9 @@ static void run_mode(const Params& p, StepIO io, double* u, double* u1, double* 
 // emulate a thread-block cluster of C CTAs per realisation (1 = off); returns the number of
 // non-local stores seen so far (must stay 0)
 extern "C" int pk_emu_set_cluster(int C) { g_emuC = C; return g_bad; }
+
+// advance in step blocks of nblk steps (0 = whole launch at once), see run_one
+extern "C" int pk_emu_set_block(int nblk) { g_emu_nblk = nblk; return 0; }
 
 extern "C" int pk_emu_layout(int ne, int* T, int* M, int* rem) { return choose_layout(ne, T, M, rem) ? 0 : -1; }
 
@@ -196,6 +211,7 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
     StepIO io;
     io.dW_in = dW_in; io.dW_out = dW_out; io.xi = tab[0]; io.xi_x = tab[1]; io.xi_xx = tab[2];
     io.R = R; io.r = r; io.rid = rid0 + r; io.seed = seed; io.step0 = step0; io.nsteps = nsteps;
+    io.n0 = 0; io.n1 = nsteps; io.nloop = nsteps; io.present = true;
     io.fail_step = fail_step; io.its_last = its_last; io.its_total = its_total; io.fail_reason = fail_reason;
     switch (p.M) {
       case 5: run_mode<5>(p, io, u, u1, dF, dG, order); break;

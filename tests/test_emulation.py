@@ -148,3 +148,26 @@ def test_upwind_oracle_properties():
     E0 = u0 @ (orc.M @ u0) + u0 @ (orc.K @ u0); E1 = r['u'] @ (orc.M @ r['u']) + r['u'] @ (orc.K @ r['u'])
     assert abs(E1 - E0) / E0 < 5e-3
     assert abs(O.dg1_norms(orc, r['m'])['mass_m'] - O.dg1_norms(orc, orc.initial_m(u0))['mass_m']) < 1e-3
+
+
+def test_step_blocks_are_bit_identical_to_one_pass():
+    """The persistent lock-step kernel hands a launch out in work items of `nblk` steps that different
+    slots pick up with fresh per-thread state (pk_step_group_kernel): the Philox window is re-drawn at
+    a block start, counters continue, padded barrier-only iterations change nothing."""
+    ne, Ld, dt, nsteps, nxi = 200, 40.0, 1e-3, 11, 4
+    mesh = O.Mesh1D(ne, Ld)
+    u0 = O.initial_u(mesh, 'proper_peak')
+    tabs = [np.ascontiguousarray(t) for t in O.noise_tables(mesh, 'sines', nxi, 0.2)]
+    out = []
+    for nblk in (0, 1, 3, 4, 11, 20):
+        lib().pk_emu_set_block(nblk)
+        try:
+            u = np.tile(u0, (2, 1)); u1 = np.zeros_like(u); dF = np.zeros_like(u); dG = np.zeros_like(u)
+            r = emu_step(ne, Ld, dt, 2, u, u1, dF, dG, tabs, None, nsteps, seed=7, rid0=5, export=True, nxi=nxi)
+        finally:
+            lib().pk_emu_set_block(0)
+        out.append((u, u1, dF, dG, r['dW'], r['its_total'], r['its_last'], r['fail_step']))
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert np.array_equal(a, b)
+    assert out[0][5].min() >= 2 * nsteps and np.abs(out[0][4]).min() > 0
