@@ -175,10 +175,10 @@ int pk_ensemble_stats(pk_ctx* ctx, const double* u, const int32_t* fail_step, co
 /* layout query (for tests / documentation): threads per realisation, rows per thread, remainder */
 int pk_get_layout(const pk_ctx* ctx, int32_t* T, int32_t* M, int32_t* rem, int32_t* smem_bytes);
 
-/* work split of the last pk_step launch of the persistent lock-step kernel (meshes with 32..128 threads
- * per realisation): realisations per CTA, step blocks per realisation, steps per block, CTAs launched.
- * Returns 0 and zeros when another kernel variant serves this context. */
-int pk_get_work_split(const pk_ctx* ctx, int32_t* group, int32_t* nb, int32_t* nblk, int32_t* grid);
+/* work split of the last pk_step launch of the single-CTA step kernel (persistent CTAs that pull items of
+ * `nblk` consecutive steps of one realisation from a queue): resident CTA slots, step blocks per realisation,
+ * steps per block, CTAs launched.  slots = 0 when the cluster / upwind kernels serve this context. */
+int pk_get_work_split(const pk_ctx* ctx, int32_t* slots, int32_t* nb, int32_t* nblk, int32_t* grid);
 
 /* measured duration (ms) of the kernels launched by the last pk_step(_host) call, from CUDA events
  * recorded on the launching stream; synchronises on the second event. */

@@ -10,9 +10,8 @@ struct StepArgs {
   long long* prof;    // [R,16] cycle buckets, PK_PROFILE builds only
   unsigned rid0;
   unsigned long long seed;
-  // persistent lock-step kernel (pk_step_group_kernel) only
+  // single-CTA step kernel (persistent CTAs + work queue)
   int* queue;         // [1 + R]: work counter, then per realisation the number of finished step blocks
   int nblk;           // steps per work item
   int nb;             // step blocks per realisation: items = nb * R, item i = (block i / R, realisation i % R)
-  int gdoubles;       // doubles of shared memory per realisation group
 };

@@ -752,11 +752,6 @@ PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int 
 //                      realisation: block-local thread id / count, whether the block is the cluster
 //                      leader, and the range of mesh rows the block owns
 //   one(f)             run f() once (thread 0)
-//   any(b)             true if b holds for any of the realisations that share the executor's barriers
-//                      (b is uniform over the threads of one realisation; executors that serve a single
-//                      realisation return b).  All control flow that contains a barrier branches on any(.)
-//                      only, so several realisations can be advanced in lock-step by one thread block.
-//   tick(id)           profiling hook (no-op unless built with -DPK_PROFILE): time since the last tick -> bucket id
 // ------------------------------------------------------------------------------------------------
 struct StepIO {
   const double* dW_in;    // [nsteps, R, nxi] or null -> Philox
@@ -768,9 +763,7 @@ struct StepIO {
   unsigned long long seed;
   int step0;              // global index of the first step of this launch
   int nsteps;             // steps of the whole launch (extent of dW_in / dW_out)
-  int n0, n1;             // launch-local range [n0, n1) of steps this call advances
-  int nloop;              // barrier-uniform trip count (>= n1 - n0): iterations past n1 only keep the barriers
-  bool present;           // false: no realisation behind this executor (it only takes part in the barriers)
+  int n0, n1;             // launch-local range [n0, n1) of steps this call advances (one work item)
   int* fail_step;         // [R] in/out: -1 = healthy, else global step index at which SNES diverged
   int* its_last;          // [R] out: Newton iterations of the last attempted step
   int* its_total;         // [R] in/out: accumulated Newton iterations
@@ -802,104 +795,92 @@ PK_HD int snes_test(const Params& p, int it, const double* nrm, double& fnorm0, 
 
 template <int M, int MODE, int TT, class Exec, class Th, class SH>
 PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) {
-  const bool present = io.present;
-  int failed = present ? PK_LD_COHERENT(io.fail_step + io.r) : 0;
-  int its_last = (present && io.n0 > 0) ? PK_LD_COHERENT(io.its_last + io.r) : 0;   // later step blocks of a launch continue
-  int its_total = present ? PK_LD_COHERENT(io.its_total + io.r) : 0, reason = 0;
+  // counters may have been written by another SM earlier in this launch (previous step block)
+  int failed = PK_LD_COHERENT(io.fail_step + io.r);
+  int its_last = io.n0 > 0 ? PK_LD_COHERENT(io.its_last + io.r) : 0;   // later step blocks of a launch continue
+  int its_total = PK_LD_COHERENT(io.its_total + io.r), reason = 0;
   DrawIO dio;
   dio.dW_in = io.dW_in; dio.dW_out = io.dW_out; dio.R = io.R; dio.r = io.r; dio.step0 = io.step0;
   dio.nsteps = io.nsteps; dio.rid = io.rid; dio.seed = io.seed; dio.n0 = io.n0;
   int expect = 2;     // iteration at which convergence is expected: there only the residual is evaluated first
-  for (int s = 0; s < io.nloop; ++s) {
-    const int n = io.n0 + s;
-    const bool here = present && n < io.n1;
+  for (int n = io.n0; n < io.n1; ++n) {
     ex.each([&](Th& th) { th.kill_all(); });
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
-    if (here) ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
+    ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
       draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold);
     });
     ex.sync();
     ex.tick(0);
-    const bool run = here && failed < 0;
-    if (!ex.any(run)) continue;
-    if (run) {
-      if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
-      else ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
-    }
+    if (failed >= 0) continue;
+    if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
+    else ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
     ex.sync();
     ex.tick(1);
 
     // ---- SNES newtonls, basic line search ----
-    // status: 0 = iterating, 1 = converged, 2 = diverged, 3 = not taking part in this step
-    int it = 0, status = run ? 0 : 3;
+    int it = 0, status = 0;
     double fnorm0 = 0.0, nrm[3];
     while (true) {
-      const bool lite = (status == 0 && it > 0 && it >= expect);
-      if (ex.any(lite)) {
+      if (it > 0 && it >= expect) {
         // convergence is expected here: evaluate the residual only; fall through to the full
         // assembly (which recomputes it) in the rare case it is not
-        if (lite) {
-          ex.each([&](Th& th) { th.assemble_begin(p, sh, true); });
-          ex.each([&](Th& th) { th.assemble_finish(p, sh, true); });
-        }
+        ex.each([&](Th& th) { th.assemble_begin(p, sh, true); });
+        ex.each([&](Th& th) { th.assemble_finish(p, sh, true); });
         ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
-        if (lite) status = snes_test(p, it, nrm, fnorm0, reason);
+        status = snes_test(p, it, nrm, fnorm0, reason);
         ex.tick(2);
+        if (status) break;
       }
-      if (!ex.any(status == 0)) break;
-      if (status == 0) ex.each([&](Th& th) { th.assemble_begin(p, sh, false); });
+      ex.each([&](Th& th) { th.assemble_begin(p, sh, false); });
       ex.sync();
       ex.tick(3);
-      if (status == 0) ex.each([&](Th& th) { th.assemble_finish(p, sh, false); });
+      ex.each([&](Th& th) { th.assemble_finish(p, sh, false); });
       ex.tick(4);
       ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
-      if (status == 0) status = snes_test(p, it, nrm, fnorm0, reason);
+      status = snes_test(p, it, nrm, fnorm0, reason);
       ex.tick(5);
-      if (!ex.any(status == 0)) break;
-      const bool act = (status == 0);
+      if (status) break;
       // ---- linear solve + update ----
-      if (act) ex.each([&](Th& th) { th.reduce_build(p, sh); });
+      ex.each([&](Th& th) { th.reduce_build(p, sh); });
       ex.sync();
-      if (act) ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+      ex.each([&](Th& th) { th.reduce_publish(p, sh); });
       ex.sync();
       ex.tick(6);
       for (int d = 1; d < (TT > 0 ? TT : p.T) / 2; d *= 2) {
-        if (act) ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
+        ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
         ex.sync();
-        if (act) ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+        ex.each([&](Th& th) { th.reduce_publish(p, sh); });
         ex.sync();
       }
       ex.tick(7);
-      if (act) ex.each([&](Th& th) { th.pcr_final(p, sh); });
+      ex.each([&](Th& th) { th.pcr_final(p, sh); });
       ex.sync();
       ex.tick(8);
-      if (act) ex.each([&](Th& th) { th.interior_solve(p, sh); });
+      ex.each([&](Th& th) { th.interior_solve(p, sh); });
       ex.sync();
       ex.tick(9);
       // forward cyclic scan (causal filter); its carries feed the anticausal local pass, whose maps
       // are scanned in reverse; the reverse carries finish the update.
-      ex.scan_fwd(act, [&](Th& th, double& A, double& c0, double& c1) { th.helm_causal_local(p, sh, A, c0, c1); },
+      ex.scan_fwd([&](Th& th, double& A, double& c0, double& c1) { th.helm_causal_local(p, sh, A, c0, c1); },
                   [&](Th& th, double in0, double in1, double& A, double& c0, double& c1) {
                     th.helm_anticausal_local(p, in0, in1, A, c0, c1); });
       ex.tick(10);
-      ex.scan_rev(act, [&](Th& th, double in0, double in1) { th.helm_finish_update(p, sh, in0, in1); });
+      ex.scan_rev([&](Th& th, double in0, double in1) { th.helm_finish_update(p, sh, in0, in1); });
       ex.sync();
       ex.tick(11);
-      if (act) ++it;
+      ++it;
     }
-    if (run) {
-      its_last = it; its_total += it;
-      if (status == 1) {
-        ex.each([&](Th& th) { th.accept(p, sh); });
-        expect = it > 1 ? it : 1;
-      } else {
-        failed = io.step0 + n;
-      }
+    its_last = it; its_total += it;
+    if (status == 1) {
+      ex.each([&](Th& th) { th.accept(p, sh); });
+      expect = it > 1 ? it : 1;
+    } else {
+      failed = io.step0 + n;
     }
     ex.sync();
     ex.tick(12);
   }
-  if (present) ex.one([&]() {
+  ex.one([&]() {
     io.fail_step[io.r] = failed; io.its_last[io.r] = its_last; io.its_total[io.r] = its_total;
     if (io.fail_reason) io.fail_reason[io.r] = reason;
   });

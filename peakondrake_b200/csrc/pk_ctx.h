@@ -16,8 +16,7 @@ struct pk_ctx {
   int block;
   int cluster;         // CTAs per realisation (1 = single-CTA kernel)
   int lgTc;
-  int group;           // realisations per CTA of the persistent lock-step kernel (0 = kernel not used)
-  int gdoubles;        // its shared-memory doubles per realisation
+  int slots;           // CTAs of the single-CTA step kernel resident at once (persistent grid), 0 = other kernel
   int sms;             // multiprocessors of the device
   int* d_queue;        // [1 + R] work counter + per-realisation finished-block counters
   int last_nb, last_nblk, last_grid;   // work split of the last pk_step launch (pk_get_work_split)

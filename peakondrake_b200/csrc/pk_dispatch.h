@@ -8,10 +8,6 @@ kern_t pk_pick_kernel_m5(int mode, int block, int T, int minb);
 kern_t pk_pick_kernel_m6(int mode, int block, int T, int minb);
 kern_t pk_pick_kernel_m7(int mode, int block, int T, int minb);
 kern_t pk_pick_kernel_m8(int mode, int block, int T, int minb);
-kern_t pk_pick_group_kernel_m5(int mode, int T);
-kern_t pk_pick_group_kernel_m6(int mode, int T);
-kern_t pk_pick_group_kernel_m7(int mode, int T);
-kern_t pk_pick_group_kernel_m8(int mode, int T);
 ckern_t pk_pick_cluster_kernel_m5(int mode, int Tc);
 ckern_t pk_pick_cluster_kernel_m6(int mode, int Tc);
 ckern_t pk_pick_cluster_kernel_m7(int mode, int Tc);

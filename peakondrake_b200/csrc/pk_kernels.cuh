@@ -37,7 +37,6 @@ struct GpuExecT {
   __device__ __forceinline__ void tick(int) {}
 #endif
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
-  __device__ __forceinline__ bool any(bool b) { return b; }     // one realisation per block
   __device__ __forceinline__ double* area() {
     const int nw = blockDim.x >> 5;
     double* a = red + flip * 3 * nw;
@@ -103,14 +102,14 @@ struct GpuExecT {
     in0 = first ? w0 : p0; in1 = first ? w1 : p1;
   }
 
-  template <class G, class P> __device__ __forceinline__ void scan_fwd(bool, G get, P put) {
+  template <class G, class P> __device__ __forceinline__ void scan_fwd(G get, P put) {
     double A = 1.0, c0 = 0.0, c1 = 0.0, in0, in1;
     if (AA || th.active) get(th, A, c0, c1);
     cyc_scan<+1>(A, c0, c1, in0, in1);
     rA = 1.0; rc0 = 0.0; rc1 = 0.0;
     if (AA || th.active) put(th, in0, in1, rA, rc0, rc1);
   }
-  template <class F> __device__ __forceinline__ void scan_rev(bool, F fin) {
+  template <class F> __device__ __forceinline__ void scan_rev(F fin) {
     double in0, in1;
     cyc_scan<-1>(rA, rc0, rc1, in0, in1);
     if (AA || th.active) fin(th, in0, in1);
@@ -139,16 +138,6 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   double* red = nxt; nxt += 6 * (blockDim.x >> 5);
   sh.dW = nxt;
 
-  const int r = blockIdx.x;
-  const long long off = (long long)r * p.ne;
-  // coalesced global reads, scattered into the chunk-interleaved shared layout
-  for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
-    const int sl = row_slot_c<M, TT>(p, i);
-    sh.U0[sl] = a.u[off + i]; sh.U1[sl] = a.u1[off + i]; sh.F[sl] = a.dF[off + i];
-    if (MODE == NOISE_FULL) sh.G[sl] = a.dG[off + i];
-  }
-  __syncthreads();
-
   Thread<M, MODE, TT> th;
   th.init(p, threadIdx.x);
   GpuExec<M, MODE, (TB > 32), TT> ex(th, red);
@@ -161,212 +150,51 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
 #endif
   StepIO io;
   io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
-  io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
-  io.n0 = 0; io.n1 = a.nsteps; io.nloop = a.nsteps; io.present = true;
-  io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
-  run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT>, Thread<M, MODE, TT> >(ex, p, sh, io);
-  __syncthreads();
-#ifdef PK_PROFILE
-  if (a.prof && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];
-#endif
-
-  for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
-    const int sl = row_slot_c<M, TT>(p, i);
-    a.u[off + i] = sh.U0[sl]; a.u1[off + i] = sh.U1[sl]; a.dF[off + i] = sh.F[sl];
-    if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[sl];
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Persistent lock-step variant: G realisations per CTA (TT threads each, G*TT = 384 threads, one CTA
-// per SM), advanced through the SAME instruction stream between block-wide barriers.
-//
-// Why: the step kernel is ~115 KB of straight-line SASS that every warp walks once per Newton
-// iteration.  With independent CTAs the three resident realisations of an SM drift apart and each
-// streams the whole body through the instruction caches on its own: ncu shows the GPC-level
-// instruction cache at 90 % of its request peak (gcc__cache_requests_type_instruction) and
-// stall_no_instruction as the top stall, and 2 -> 3 resident CTAs/SM adds no throughput.  In lock-step
-// the 12 warps of an SM fetch every line once.
-//
-// Work is handed out from a global queue in items of `nblk` consecutive time steps of one realisation
-// (block-major order, so the previous block of the same realisation was handed out R items earlier and
-// is normally long finished; a per-realisation "blocks done" counter is awaited before loading).  That
-// removes the wave quantisation of R/(G*SMs) as well: all G*SMs slots stay busy until the queue is dry.
-// ------------------------------------------------------------------------------------------------
-template <class ThT, int TT, int G>
-struct GpuExecGroup {
-  typedef ThT Th;
-  enum { NW = TT / 32 };
-  Th& th;
-  double* red;          // this group's [2][3*NW] scratch, ping-pong like GpuExecT
-  int flip, tid, w, lane;
-  double rA, rc0, rc1;
-  __device__ __forceinline__ GpuExecGroup(Th& t, double* scratch, int tid_) : th(t), red(scratch), flip(0), tid(tid_) {
-    w = tid_ >> 5; lane = tid_ & 31;
-  }
-  template <class F> __device__ __forceinline__ void each(F f) { f(th); }
-  int ne_;
-  template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, tid, TT, true, 0, ne_); }
-  __device__ __forceinline__ void sync() { __syncthreads(); }
-  __device__ __forceinline__ bool any(bool b) { return G > 1 ? (__syncthreads_or(b ? 1 : 0) != 0) : b; }
-#ifdef PK_PROFILE
-  long long tlast; long long* tbuf;
-  __device__ __forceinline__ void tick(int id) {
-    if (threadIdx.x == 0) { const long long c = clock64(); tbuf[id] += c - tlast; tlast = c; }
-  }
-#else
-  __device__ __forceinline__ void tick(int) {}
-#endif
-  template <class F> __device__ __forceinline__ void one(F f) { if (tid == 0) f(); }
-  __device__ __forceinline__ double* area() {
-    double* a = red + flip * 3 * NW;
-    flip ^= 1;
-    return a;
-  }
-  template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
-    double v[3] = {0.0, 0.0, 0.0};
-    f(th, v);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-      v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
-      v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
-    }
-    double* sc = area();
-    if (lane == 0) { sc[w] = v[0]; sc[NW + w] = v[1]; sc[2 * NW + w] = v[2]; }
-    __syncthreads();
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) { s0 += sc[i]; s1 += sc[NW + i]; s2 += sc[2 * NW + i]; }
-    out[0] = s0; out[1] = s1; out[2] = s2;
-  }
-  template <int DIR>
-  __device__ __forceinline__ void cyc_scan(double A, double c0, double c1, double& in0, double& in1) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      double Ao, c0o, c1o;
-      if (DIR > 0) {
-        Ao = __shfl_up_sync(0xffffffffu, A, o); c0o = __shfl_up_sync(0xffffffffu, c0, o); c1o = __shfl_up_sync(0xffffffffu, c1, o);
-      } else {
-        Ao = __shfl_down_sync(0xffffffffu, A, o); c0o = __shfl_down_sync(0xffffffffu, c0, o); c1o = __shfl_down_sync(0xffffffffu, c1, o);
-      }
-      const bool ok = (DIR > 0) ? (lane >= o) : (lane + o < 32);
-      if (ok) { c0 = A * c0o + c0; c1 = A * c1o + c1; A = A * Ao; }
-    }
-    const int last = (DIR > 0) ? 31 : 0;
-    double* sc = area();
-    if (lane == last) { sc[w] = A; sc[NW + w] = c0; sc[2 * NW + w] = c1; }
-    __syncthreads();
-    double tA = 1.0, t0 = 0.0, t1 = 0.0, eA = 1.0, e0 = 0.0, e1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const int ww = (DIR > 0) ? k : NW - 1 - k;
-      if (ww == w) { eA = tA; e0 = t0; e1 = t1; }
-      const double a = sc[ww];
-      t0 = a * t0 + sc[NW + ww]; t1 = a * t1 + sc[2 * NW + ww]; tA = a * tA;
-    }
-    const double inv = PK_RCP(1.0 - tA);
-    const double x0 = t0 * inv, x1 = t1 * inv;
-    const double w0 = eA * x0 + e0, w1 = eA * x1 + e1;
-    const double o0 = A * w0 + c0, o1 = A * w1 + c1;
-    double p0, p1;
-    if (DIR > 0) { p0 = __shfl_up_sync(0xffffffffu, o0, 1); p1 = __shfl_up_sync(0xffffffffu, o1, 1); }
-    else { p0 = __shfl_down_sync(0xffffffffu, o0, 1); p1 = __shfl_down_sync(0xffffffffu, o1, 1); }
-    const bool first = (DIR > 0) ? (lane == 0) : (lane == 31);
-    in0 = first ? w0 : p0; in1 = first ? w1 : p1;
-  }
-  // act is uniform over the group: an idle group feeds identity maps through the scans (barriers only)
-  template <class GG, class P> __device__ __forceinline__ void scan_fwd(bool act, GG get, P put) {
-    double A = 0.5, c0 = 0.0, c1 = 0.0, in0, in1;
-    if (act) get(th, A, c0, c1);
-    cyc_scan<+1>(A, c0, c1, in0, in1);
-    rA = 0.5; rc0 = 0.0; rc1 = 0.0;
-    if (act) put(th, in0, in1, rA, rc0, rc1);
-  }
-  template <class F> __device__ __forceinline__ void scan_rev(bool act, F fin) {
-    double in0, in1;
-    cyc_scan<-1>(rA, rc0, rc1, in0, in1);
-    if (act) fin(th, in0, in1);
-  }
-};
-
-template <int M, int MODE, int TT, int G>
-__global__ void __launch_bounds__(TT * G, 1) pk_step_group_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ int s_item[G];
-  const int g = (int)threadIdx.x / TT, tid = (int)threadIdx.x - g * TT;
-  const int n = TT * M;
-  Shared sh;
-  double* base = smem + (size_t)g * a.gdoubles;
-  sh.U0 = base; sh.U1 = base + n; sh.F = base + 2 * n;
-  double* nxt = base + 3 * n;
-  if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
-  else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
-  else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
-  sh.xb = nxt; nxt += XB_SLOTS * TT;
-  double* red = nxt; nxt += 6 * (TT / 32);
-  sh.dW = nxt;
-
-  typedef Thread<M, MODE, TT> Th;
-  typedef GpuExecGroup<Th, TT, G> Ex;
-  Th th;
-  th.init(p, tid);
-  Ex ex(th, red, tid);
-  ex.ne_ = p.ne;
-#ifdef PK_PROFILE
-  __shared__ long long tb[16];
-  if (threadIdx.x < 16) tb[threadIdx.x] = 0;
-  __syncthreads();
-  ex.tbuf = tb; ex.tlast = clock64();
-#endif
-  StepIO io;
-  io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
   io.R = a.R; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
-  io.nloop = a.nblk;
+
+  // Persistent CTAs pull work items from a global queue: item i = `nblk` consecutive time steps
+  // (block i / R) of realisation i % R.  Block-major order: the previous block of a realisation was handed
+  // out R items earlier and is normally long finished; its completion counter is awaited before the state
+  // is loaded.  This keeps every resident CTA busy until the queue is dry, whatever R / (CTAs per wave) is.
+  __shared__ int s_item;
   const int nitems = a.nb * a.R;
   int* const done = a.queue + 1;
-
   while (true) {
-    // ---- fetch the next work item of this group; wait for the previous block of that realisation ----
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
       const int item = atomicAdd(a.queue, 1);
       if (item < nitems) {
         const int b = item / a.R, r = item - b * a.R;
         while (atomicAdd(done + r, 0) < b) __nanosleep(200);
         __threadfence();
       }
-      s_item[g] = item;
+      s_item = item;
     }
     __syncthreads();
-    const int item = s_item[g];
-    const bool present = item < nitems;
-    if (!__syncthreads_or(present ? 1 : 0)) break;       // queue dry for the whole block (also fences s_item reuse)
-    const int b = present ? item / a.R : 0, r = present ? item - b * a.R : 0;
+    const int item = s_item;
+    if (item >= nitems) break;
+    const int b = item / a.R, r = item - b * a.R;
     const long long off = (long long)r * p.ne;
-    if (present) {
-      for (int i = tid; i < p.ne; i += TT) {
-        const int sl = row_slot_c<M, TT>(p, i);
-        sh.U0[sl] = __ldcg(a.u + off + i); sh.U1[sl] = __ldcg(a.u1 + off + i); sh.F[sl] = __ldcg(a.dF + off + i);
-        if (MODE == NOISE_FULL) sh.G[sl] = __ldcg(a.dG + off + i);
-      }
+    // coalesced global reads (L2: the state may have been written by another SM during this launch),
+    // scattered into the chunk-interleaved shared layout
+    for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
+      const int sl = row_slot_c<M, TT>(p, i);
+      sh.U0[sl] = __ldcg(a.u + off + i); sh.U1[sl] = __ldcg(a.u1 + off + i); sh.F[sl] = __ldcg(a.dF + off + i);
+      if (MODE == NOISE_FULL) sh.G[sl] = __ldcg(a.dG + off + i);
     }
     __syncthreads();
-    io.r = r; io.rid = a.rid0 + (unsigned)r; io.present = present;
+    io.r = r; io.rid = a.rid0 + (unsigned)r;
     io.n0 = b * a.nblk; io.n1 = min(io.n0 + a.nblk, a.nsteps);
-    run_steps<M, MODE, TT, Ex, Th>(ex, p, sh, io);
+    run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT>, Thread<M, MODE, TT> >(ex, p, sh, io);
     __syncthreads();
-    if (present) {
-      for (int i = tid; i < p.ne; i += TT) {
-        const int sl = row_slot_c<M, TT>(p, i);
-        a.u[off + i] = sh.U0[sl]; a.u1[off + i] = sh.U1[sl]; a.dF[off + i] = sh.F[sl];
-        if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[sl];
-      }
-      __threadfence();
+    for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
+      const int sl = row_slot_c<M, TT>(p, i);
+      a.u[off + i] = sh.U0[sl]; a.u1[off + i] = sh.U1[sl]; a.dF[off + i] = sh.F[sl];
+      if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[sl];
     }
-    __syncthreads();
-    if (present && tid == 0) { __threadfence(); atomicExch(done + r, b + 1); }
+    __threadfence();
+    __syncthreads();      // all stores of the block are fenced; s_item may be overwritten
+    if (threadIdx.x == 0) { __threadfence(); atomicExch(done + r, b + 1); }
   }
 #ifdef PK_PROFILE
   if (a.prof && threadIdx.x < 16) a.prof[blockIdx.x * 16 + threadIdx.x] = tb[threadIdx.x];
@@ -414,7 +242,6 @@ struct GpuExecCluster {
   __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
   __device__ __forceinline__ void tick(int) {}
   template <class F> __device__ __forceinline__ void one(F f) { if (rank == 0 && threadIdx.x == 0) f(); }
-  __device__ __forceinline__ bool any(bool b) { return b; }     // one realisation per cluster
   __device__ __forceinline__ double* area() {
     const int nw = blockDim.x >> 5;
     double* a = red + flip * (3 * nw + 3);
@@ -497,14 +324,14 @@ struct GpuExecCluster {
     const bool first = (DIR > 0) ? (lane == 0) : (lane == 31);
     in0 = first ? w0 : q0; in1 = first ? w1 : q1;
   }
-  template <class G, class P> __device__ __forceinline__ void scan_fwd(bool, G get, P put) {
+  template <class G, class P> __device__ __forceinline__ void scan_fwd(G get, P put) {
     double A = 1.0, c0 = 0.0, c1 = 0.0, in0, in1;
     get(th, A, c0, c1);
     cyc_scan<+1>(A, c0, c1, in0, in1);
     rA = 1.0; rc0 = 0.0; rc1 = 0.0;
     put(th, in0, in1, rA, rc0, rc1);
   }
-  template <class F> __device__ __forceinline__ void scan_rev(bool, F fin) {
+  template <class F> __device__ __forceinline__ void scan_rev(F fin) {
     double in0, in1;
     cyc_scan<-1>(rA, rc0, rc1, in0, in1);
     fin(th, in0, in1);
@@ -548,7 +375,7 @@ __global__ void __launch_bounds__(TB, 1) pk_step_cluster_kernel(const __grid_con
   StepIO io;
   io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
   io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
-  io.n0 = 0; io.n1 = a.nsteps; io.nloop = a.nsteps; io.present = true;
+  io.n0 = 0; io.n1 = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   run_steps<M, MODE, 0, GpuExecCluster<M, MODE>, Thread<M, MODE, 0> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory

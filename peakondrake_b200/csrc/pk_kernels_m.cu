@@ -37,23 +37,7 @@ template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {
   }
 }
 
-// persistent lock-step kernels: 384 threads = G groups of T threads
-template <int M, int MODE> static kern_t pick_group_t(int T) {
-  if (T == 128) return pk_step_group_kernel<M, MODE, 128, 3>;
-  if (T == 64) return pk_step_group_kernel<M, MODE, 64, 6>;
-  if (T == 32) return pk_step_group_kernel<M, MODE, 32, 12>;
-  return nullptr;
-}
-template <int M> static kern_t pick_group(int mode, int T) {
-  switch (mode) {
-    case NOISE_SCALAR: return pick_group_t<M, NOISE_SCALAR>(T);
-    case NOISE_X: return pick_group_t<M, NOISE_X>(T);
-    default: return pick_group_t<M, NOISE_FULL>(T);
-  }
-}
-
 #define PK_CAT2(a, b) a##b
 #define PK_CAT(a, b) PK_CAT2(a, b)
 kern_t PK_CAT(pk_pick_kernel_m, PK_M)(int mode, int block, int T, int minb) { return pick_mode<PK_M>(mode, block, T, minb); }
-kern_t PK_CAT(pk_pick_group_kernel_m, PK_M)(int mode, int T) { return pick_group<PK_M>(mode, T); }
 ckern_t PK_CAT(pk_pick_cluster_kernel_m, PK_M)(int mode, int Tc) { return pick_cmode<PK_M>(mode, Tc); }

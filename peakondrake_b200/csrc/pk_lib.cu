@@ -311,26 +311,16 @@ static kern_t pick_kernel(const Params& p, int block) {
   }
   return nullptr;
 }
-static kern_t pick_group_kernel(const Params& p) {
-  switch (p.M) {
-    case 5: return pk_pick_group_kernel_m5(p.mode, p.T);
-    case 6: return pk_pick_group_kernel_m6(p.mode, p.T);
-    case 7: return pk_pick_group_kernel_m7(p.mode, p.T);
-    case 8: return pk_pick_group_kernel_m8(p.mode, p.T);
-  }
-  return nullptr;
-}
-
-// Split K steps of R realisations into work items for S lock-step slots: nb blocks of nblk steps per
+// Split K steps of R realisations into work items for S resident CTAs: nb blocks of nblk steps per
 // realisation.  A round (all slots advance one item) costs nblk steps plus the state reload / noise
-// window redraw (~0.4 step); blocks of one realisation are sequential, so rounds >= nb.
+// window redraw (~0.15 step, measured); blocks of one realisation are sequential, so rounds >= nb.
 static void choose_blocks(int R, int K, int S, int* nb_out, int* nblk_out) {
   double best = 1e300; int bnb = 1, bblk = K;
   for (int nblk = 1; nblk <= K; ++nblk) {
     const int nb = (K + nblk - 1) / nblk;
     long long rounds = ((long long)R * nb + S - 1) / S;
     if (rounds < nb) rounds = nb;
-    const double cost = (double)rounds * (nblk + 0.4);
+    const double cost = (double)rounds * (nblk + 0.15);
     if (cost < best - 1e-9) { best = cost; bnb = nb; bblk = nblk; }
   }
   *nb_out = bnb; *nblk_out = bblk;
@@ -362,7 +352,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     return fail(nullptr, "pk_create: scalar noise supports one Xi only (reference stochastic_functions.py:111-112)");
   pk_ctx* c = new pk_ctx();
   c->cfg = *cfg;
-  c->group = 0; c->gdoubles = 0; c->d_queue = nullptr; c->last_nb = c->last_nblk = c->last_grid = 0;
+  c->slots = 0; c->d_queue = nullptr; c->last_nb = c->last_nblk = c->last_grid = 0;
   c->sms = 148;
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, cfg->device);
   Params& p = c->p;
@@ -386,18 +376,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   }
   int force = 0;
   { const char* e = getenv("PK_FORCE_CLUSTER"); force = e ? atoi(e) : 0; }   // testing: split small meshes too
-  int nogroup = 0;
-  { const char* e = getenv("PK_NO_GROUP"); nogroup = e ? atoi(e) : 0; }       // A/B: one independent CTA per realisation
-  if (cfg->scheme == 0 && force <= 1 && !nogroup && (p.T == 32 || p.T == 64 || p.T == 128)) {
-    // persistent lock-step kernel: G = 384 / T realisations per CTA, one CTA per SM
-    const int G = 384 / p.T;
-    size_t gd = (size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 6 * (p.T / 32) + (p.nxi > 0 ? p.nxi : 1);
-    gd = (gd + 1) & ~(size_t)1;
-    if (sizeof(double) * gd * G <= 227 * 1024) {
-      c->group = G; c->gdoubles = (int)gd; c->block = 384; c->smem = sizeof(double) * gd * G;
-    }
-  }
-  if (cfg->scheme == 0 && !c->group && (force > 1 || c->block > 512 || c->smem > 227 * 1024)) {
+  if (cfg->scheme == 0 && (force > 1 || c->block > 512 || c->smem > 227 * 1024)) {
     // one realisation per thread-block cluster: C CTAs of Tc threads
     int Tc = 256, C = p.T / Tc;
     if (force > 1) { C = force; Tc = p.T / C; }
@@ -415,12 +394,18 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->timed = false;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
-  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block)
-                  : (c->group ? (const void*)pick_group_kernel(p) : (const void*)pick_kernel(p, c->block));
+  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block) : (const void*)pick_kernel(p, c->block);
   if (!k) { delete c; return fail(nullptr, "pk_create: no kernel for this layout"); }
   if (c->cluster > 8) cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   e = cfg->scheme == 1 ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaFuncSetAttribute(smem=%zu): %s", c->smem, m.c_str()); }
+  if (cfg->scheme == 0 && c->cluster == 1) {
+    // persistent CTAs: as many as are resident at once
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, c->block, c->smem);
+    if (e != cudaSuccess || per_sm < 1) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "occupancy query failed: %s", m.c_str()); }
+    c->slots = per_sm * c->sms;
+  }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
   *out = c;
   return 0;
@@ -482,7 +467,7 @@ extern "C" int pk_get_layout(const pk_ctx* c, int32_t* T, int32_t* M, int32_t* r
 
 extern "C" int pk_get_work_split(const pk_ctx* c, int32_t* group, int32_t* nb, int32_t* nblk, int32_t* grid) {
   if (!c) return -1;
-  if (group) *group = c->group; if (nb) *nb = c->last_nb; if (nblk) *nblk = c->last_nblk; if (grid) *grid = c->last_grid;
+  if (group) *group = c->slots; if (nb) *nb = c->last_nb; if (nblk) *nblk = c->last_nblk; if (grid) *grid = c->last_grid;
   return 0;
 }
 
@@ -501,7 +486,7 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
   a.u = u; a.u1 = u1; a.dF = dF; a.dG = dG; a.xi = c->xi; a.xi_x = c->xi_x; a.xi_xx = c->xi_xx;
   a.dW_in = dW_in; a.dW_out = dW_out; a.fail_step = fail_step; a.its_last = its_last; a.its_total = its_total;
   a.prof = c->d_prof;
-  a.queue = nullptr; a.nblk = nsteps; a.nb = 1; a.gdoubles = 0;
+  a.queue = nullptr; a.nblk = nsteps; a.nb = 1;
   a.R = c->cfg.R; a.step0 = (int)c->step; a.nsteps = nsteps; a.rid0 = c->cfg.rid_offset; a.seed = c->cfg.seed;
   cudaStream_t st = (cudaStream_t)stream;
   CK(c, cudaEventRecord(c->ev0, st));
@@ -514,23 +499,19 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
     at[0].val.clusterDim.x = (unsigned)c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
     CK(c, cudaLaunchKernelEx(&lc, pick_cluster_kernel(c->p, c->block), c->p, a, c->lgTc));
-  } else if (c->group) {
+  } else {
     const int R = c->cfg.R;
     if (!c->d_queue) CK(c, cudaMalloc(&c->d_queue, sizeof(int) * (size_t)(R + 1)));
-    int grid = (R + c->group - 1) / c->group;
-    if (grid > c->sms) grid = c->sms;
+    const int grid = R < c->slots ? R : c->slots;
     int nb = 1, nblk = nsteps;
-    choose_blocks(R, nsteps, grid * c->group, &nb, &nblk);
+    choose_blocks(R, nsteps, grid, &nb, &nblk);
     { const char* e = getenv("PK_NBLK"); const int v = e ? atoi(e) : 0; if (v > 0) { nblk = v < nsteps ? v : nsteps; nb = (nsteps + nblk - 1) / nblk; } }
-    a.queue = c->d_queue; a.nblk = nblk; a.nb = nb; a.gdoubles = c->gdoubles;
+    a.queue = c->d_queue; a.nblk = nblk; a.nb = nb;
     c->last_nb = nb; c->last_nblk = nblk; c->last_grid = grid;
     CK(c, cudaMemsetAsync(c->d_queue, 0, sizeof(int) * (size_t)(R + 1), st));
     CK(c, cudaEventRecord(c->ev0, st));      // time the kernel alone
-    kern_t k = pick_group_kernel(c->p);
-    k<<<grid, c->block, c->smem, st>>>(c->p, a);
-  } else {
     kern_t k = pick_kernel(c->p, c->block);
-    k<<<c->cfg.R, c->block, c->smem, st>>>(c->p, a);
+    k<<<grid, c->block, c->smem, st>>>(c->p, a);
   }
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(c->ev1, st));
@@ -679,9 +660,6 @@ extern "C" int pk_profile_enable(pk_ctx* c) {
 kern_t pk_pick_kernel_m5(int, int, int, int) { return nullptr; }
 kern_t pk_pick_kernel_m6(int, int, int, int) { return nullptr; }
 kern_t pk_pick_kernel_m7(int, int, int, int) { return nullptr; }
-kern_t pk_pick_group_kernel_m5(int, int) { return nullptr; }
-kern_t pk_pick_group_kernel_m6(int, int) { return nullptr; }
-kern_t pk_pick_group_kernel_m7(int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m5(int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m6(int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m7(int, int) { return nullptr; }

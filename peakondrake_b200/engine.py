@@ -125,8 +125,8 @@ class EnsembleIntegrator(object):
                  ctas_per_realisation=max(1, c))
         g, nb, nblk, grid = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32())
         self.lib.pk_get_work_split(self.ctx, ctypes.byref(g), ctypes.byref(nb), ctypes.byref(nblk), ctypes.byref(grid))
-        if g.value:     # persistent lock-step kernel: realisations per CTA and the work split of the last launch
-            d.update(realisations_per_cta=g.value, step_blocks=nb.value, steps_per_block=nblk.value, ctas=grid.value)
+        if g.value:     # persistent CTAs + work queue: the split of the last launch
+            d.update(resident_ctas=g.value, step_blocks=nb.value, steps_per_block=nblk.value, ctas=grid.value)
         return d
 
     @property

@@ -63,7 +63,6 @@ struct EmuExecT {
   void sync() {}
   void tick(int) {}
   template <class F> void one(F f) { f(); }
-  bool any(bool b) { return b; }
   template <class F> void allreduce3(F f, double* out) {
     out[0] = out[1] = out[2] = 0.0;
     for (int t = 0; t < T; ++t) { double v[3]; f(th[t], v); out[0] += v[0]; out[1] += v[1]; out[2] += v[2]; }
@@ -93,8 +92,6 @@ struct EmuExecT {
     cyc_scan(-1, in0, in1);
     each([&](Th& h) { fin(h, in0[h.t], in1[h.t]); });
   }
-  template <class G, class P> void scan_fwd(bool, G get, P put) { scan_fwd(get, put); }
-  template <class F> void scan_rev(bool, F fin) { scan_rev(fin); }
 };
 
 template <int M, int MODE>
@@ -142,12 +139,11 @@ static void run_one(const Params& p, StepIO io, double* u, double* u1, double* d
     sh.G[sl] = (MODE == NOISE_FULL) ? dG[off + i] : 0.0;
   }
   // g_emu_nblk > 0: advance in work items of g_emu_nblk steps, each with fresh per-thread state (what a
-  // different slot of the persistent lock-step kernel sees when it picks up the next block); the trip
-  // count is padded by one barrier-only iteration like an uneven last block
+  // different persistent CTA sees when it pulls the next block of the realisation from the queue)
   const int nblk = g_emu_nblk > 0 ? g_emu_nblk : io.nsteps;
   for (int b0 = 0; b0 < io.nsteps || b0 == 0; b0 += nblk) {
     EmuExec<M, MODE> ex(p, order);
-    io.n0 = b0; io.n1 = b0 + nblk < io.nsteps ? b0 + nblk : io.nsteps; io.nloop = nblk + (g_emu_nblk > 0 ? 1 : 0);
+    io.n0 = b0; io.n1 = b0 + nblk < io.nsteps ? b0 + nblk : io.nsteps;
     run_steps<M, MODE, 0, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
     if (nblk <= 0) break;
   }
@@ -211,7 +207,7 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
     StepIO io;
     io.dW_in = dW_in; io.dW_out = dW_out; io.xi = tab[0]; io.xi_x = tab[1]; io.xi_xx = tab[2];
     io.R = R; io.r = r; io.rid = rid0 + r; io.seed = seed; io.step0 = step0; io.nsteps = nsteps;
-    io.n0 = 0; io.n1 = nsteps; io.nloop = nsteps; io.present = true;
+    io.n0 = 0; io.n1 = nsteps;
     io.fail_step = fail_step; io.its_last = its_last; io.its_total = its_total; io.fail_reason = fail_reason;
     switch (p.M) {
       case 5: run_mode<5>(p, io, u, u1, dF, dG, order); break;

@@ -151,9 +151,9 @@ def test_upwind_oracle_properties():
 
 
 def test_step_blocks_are_bit_identical_to_one_pass():
-    """The persistent lock-step kernel hands a launch out in work items of `nblk` steps that different
-    slots pick up with fresh per-thread state (pk_step_group_kernel): the Philox window is re-drawn at
-    a block start, counters continue, padded barrier-only iterations change nothing."""
+    """The persistent step kernel hands a launch out in work items of `nblk` steps that different CTAs
+    pick up with fresh per-thread state (pk_step_kernel): the Philox window is re-drawn at a block start,
+    the failure / iteration counters continue."""
     ne, Ld, dt, nsteps, nxi = 200, 40.0, 1e-3, 11, 4
     mesh = O.Mesh1D(ne, Ld)
     u0 = O.initial_u(mesh, 'proper_peak')
