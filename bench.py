@@ -110,67 +110,101 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port, one worker per core, whole realisations each
 # ---------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    seed, nsteps = args
+_W = {}
+
+
+def _cpu_init():
+    """Per-worker set-up (untimed): mesh, IC, noise tables, one warm-up step."""
     from oracle import ch_oracle as O
     mesh = O.Mesh1D(NE, LD)
-    u0 = O.initial_u(mesh, IC)
-    tabs = O.noise_tables(mesh, 'sines', NXI, SIGMA)
-    dW = O.reference_dW(seed, nsteps + 1, NXI, DT)
-    orc = O.CHOracle(NE, LD, DT)
-    u = orc.solve(u0, dW[0] @ tabs[0], dW[0] @ tabs[1], dW[0] @ tabs[2])      # warm-up step (untimed)
+    _W['O'] = O
+    _W['tabs'] = O.noise_tables(mesh, 'sines', NXI, SIGMA)
+    _W['orc'] = O.CHOracle(NE, LD, DT)
+    _W['u'] = O.initial_u(mesh, IC)
+    _W['seed'] = os.getpid()
+    _cpu_worker(1)
+
+
+def _cpu_worker(nsteps):
+    """Advance this worker's realisation by nsteps steps of the bench workload; returns its busy time."""
+    O, tabs, orc = _W['O'], _W['tabs'], _W['orc']
+    dW = O.reference_dW(_W['seed'], nsteps, NXI, DT)
+    _W['seed'] += 7919
+    u = _W['u']
     t0 = time.perf_counter()
-    for n in range(1, nsteps + 1):
+    for n in range(nsteps):
         u = orc.solve(u, dW[n] @ tabs[0], dW[n] @ tabs[1], dW[n] @ tabs[2])
+    _W['u'] = u
     return time.perf_counter() - t0
 
 
-def cpu_rate(nsteps, workers=None, rounds=1):
-    """realisation*steps/s of the oracle on this host: `workers` processes, each integrating one
-    realisation of the bench workload for `nsteps` steps; returns (rate, workers, sample string)."""
-    import multiprocessing as mp
-    workers = workers or (os.cpu_count() or 1)
-    os.environ.setdefault('OMP_NUM_THREADS', '1')
-    ctx = mp.get_context('fork')
-    t0 = time.perf_counter()
-    with ctx.Pool(workers) as pool:
-        for _ in range(rounds):
-            pool.map(_cpu_worker, [(s, nsteps) for s in range(workers)])
-    wall = time.perf_counter() - t0
-    # wall includes per-worker set-up (IC, tables, first step); the rate uses wall -> conservative
-    rate = workers * nsteps * rounds / wall
-    return rate, workers, ('%d realisations (one per core) x %d steps of the bench workload, oracle '
-                           '(NumPy/SciPy monolithic sparse-LU Newton), wall %.1f s' % (workers * rounds, nsteps, wall))
+class CpuArm(object):
+    """The oracle port of the reference's Firedrake path on all host cores: one process per core (the
+    reference's own job-array parallelism), each integrating whole realisations of the bench workload."""
+
+    def __init__(self, workers=None):
+        import multiprocessing as mp
+        self.workers = workers or (os.cpu_count() or 1)
+        os.environ.setdefault('OMP_NUM_THREADS', '1')
+        self.pool = mp.get_context('fork').Pool(self.workers, initializer=_cpu_init)
+        self.pool.map(_cpu_worker, [1] * self.workers)      # every worker is up and warm
+
+    def step(self, nsteps):
+        """One bench step = nsteps timesteps of `workers` realisations; returns (rate, wall seconds)."""
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker, [nsteps] * self.workers, chunksize=1)
+        wall = time.perf_counter() - t0
+        return self.workers * nsteps / wall, wall
+
+    def sample(self, nsteps, wall):
+        return ('%d realisations (one per core) x %d steps of the bench workload, oracle (NumPy/SciPy '
+                'monolithic sparse-LU Newton), wall %.1f s' % (self.workers, nsteps, wall))
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+
+def cpu_rate(target_seconds=15.0):
+    """cpu_baseline of the own arm: a bounded sample (about target_seconds of wall on every core)."""
+    arm = CpuArm()
+    r0, _ = arm.step(20)
+    nsteps = max(20, int(target_seconds * r0 / arm.workers))
+    rate, wall = arm.step(nsteps)
+    sample = arm.sample(nsteps, wall)
+    cores = arm.workers
+    arm.close()
+    return rate, cores, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    workers = os.cpu_count() or 1
-    nsteps = 300
-    # calibrate so that the whole run (W + K bench steps) stays within a few minutes
-    t0 = time.perf_counter()
-    rates = []
+    arm = CpuArm()
+    r0, _ = arm.step(20)
+    # each bench step is a bounded sample sized so that warm-up + K steps end within ~3 minutes
+    budget = 170.0 / max(1, args.steps + args.warmup)
+    nsteps = max(4, int(budget * r0 / arm.workers))
     for _ in range(args.warmup):
-        cpu_rate(max(4, nsteps // 4), workers)
+        arm.step(nsteps)
+    rates, walls = [], []
     for _ in range(args.steps):
-        r, w, sample = cpu_rate(nsteps, workers)
-        rates.append(r)
-        if time.perf_counter() - t0 > 240:
-            break
-    rate = float(np.mean(rates))
-    units = workers * nsteps
+        r, w = arm.step(nsteps)
+        rates.append(r); walls.append(w)
+    units = arm.workers * nsteps
+    rate = units * len(rates) / sum(walls)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': len(rates), 'warmup': args.warmup, 'ms_per_step': 1e3 * units / rate,
+        'steps': len(rates), 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(walls) / len(walls),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'note': 'CPU arm: Firedrake is not installable offline; this is the '
                    'oracle port of the same weak form (BASELINE.md section 4), each step a bounded sample'},
-        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': workers, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': arm.workers, 'kind': 'port',
+                         'sample': arm.sample(nsteps, sum(walls) / len(walls)) + ' per bench step'},
         'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    arm.close()
     print(json.dumps(line), flush=True)
 
 
@@ -294,7 +328,7 @@ def run_gpu(args):
             'wall_ms_per_step': wall_ms / args.steps,
         }
         if args.cpu_baseline:
-            rate, cores, sample = cpu_rate(500)
+            rate, cores, sample = cpu_rate(15.0)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
         print(json.dumps(line), flush=True)
     if world > 1:
