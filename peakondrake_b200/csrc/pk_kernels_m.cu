@@ -26,7 +26,7 @@ template <int M, int MODE> static kern_t pick_tb(int block, int T, int minb) {
   if (T < 32) return pk_step_kernel<M, MODE, 32, 1, 0>;    // tiny meshes: some lanes of the single warp idle
   if (T == 128) return pk_step_kernel<M, MODE, 128, 3, 128>;
   if (block <= 128) return pk_step_kernel<M, MODE, 128, 2, 0>;
-  if (block <= 256) return pk_step_kernel<M, MODE, 256, 1, 256>;
+  if (block <= 256) return (M <= 5) ? pk_step_kernel<M, MODE, 256, 2, 256> : pk_step_kernel<M, MODE, 256, 1, 256>;
   return pk_step_kernel<M, MODE, 512, 1, 512>;
 }
 template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {

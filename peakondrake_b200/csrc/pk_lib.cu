@@ -364,6 +364,14 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   p.stol = cfg->stol > 0 ? cfg->stol : 1e-8; p.divtol = cfg->divtol > 0 ? cfg->divtol : 1e4;
   p.xi_const = cfg->xi_const;
   if (!choose_layout(p.ne, &p.T, &p.M, &p.rem)) { delete c; return fail(nullptr, "pk_create: no thread layout for ne=%d", cfg->ne); }
+  { // experiments: PK_FORCE_TM="T,M" overrides the layout (chunks of M or M-1 rows, M in 5..8)
+    const char* e = getenv("PK_FORCE_TM"); int ft = 0, fm = 0;
+    if (e && sscanf(e, "%d,%d", &ft, &fm) == 2) {
+      const int rem = p.ne - ft * (fm - 1);
+      if (rem < 0 || rem > ft || fm < 5 || fm > 8) { delete c; return fail(nullptr, "PK_FORCE_TM=%s does not fit ne=%d", e, cfg->ne); }
+      p.T = ft; p.M = fm; p.rem = rem;
+    }
+  }
   fill_constants(p);
   const int narr = p.mode == NOISE_FULL ? 7 : (p.mode == NOISE_X ? 4 : 3);
   c->block = p.T < 32 ? 32 : p.T;

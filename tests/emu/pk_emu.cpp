@@ -210,6 +210,7 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
     io.n0 = 0; io.n1 = nsteps;
     io.fail_step = fail_step; io.its_last = its_last; io.its_total = its_total; io.fail_reason = fail_reason;
     switch (p.M) {
+      case 4: run_mode<4>(p, io, u, u1, dF, dG, order); break;
       case 5: run_mode<5>(p, io, u, u1, dF, dG, order); break;
       case 6: run_mode<6>(p, io, u, u1, dF, dG, order); break;
       case 7: run_mode<7>(p, io, u, u1, dF, dG, order); break;
