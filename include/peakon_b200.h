@@ -78,7 +78,9 @@ typedef struct pk_config {
   double rtol, atol, stol, divtol; /* SNES tolerances (0 -> PETSc defaults 1e-8, 1e-50, 1e-8, 1e4) */
   double xi_const;       /* PK_NOISE_SCALAR: the constant value of xi_0 (sigma for 'constant') */
   int32_t scheme;        /* 0: 'hydrodynamic' / 'no_gradient' with 'midpoint' (equations.py:63-130);
-                            1: 'upwind' with 'ssprk3' (equations.py:28-61) -> pk_step_upwind */
+                            1: 'upwind' with 'ssprk3' (equations.py:28-61) -> pk_step_upwind;
+                            2: 'test' with 'midpoint' (equations.py:132-145): one CG1 unknown, noise_mode SCALAR
+                               or X, stepped by pk_step (dF/dG are ignored), meshes up to ne = 4096 */
 } pk_config;
 
 /* Replaces Equations.__init__ (equations.py:63-95) + PrognosticVariables (simulation.py:227-249)

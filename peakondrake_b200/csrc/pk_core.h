@@ -88,6 +88,13 @@ struct CellC {
   double dgL0, dgL1, dgR0, dgR1;
   // values only (residual evaluation)
   PK_HD void compute_res(const Params& p, const NodeS& A, const NodeS& B) {
+    if (PK_IS_TEST(MODE)) {
+      // 'test' scheme (equations.py:140): - int psi uh (dv)_x, (dv)_x constant on the cell
+      const double dv6 = (B.v - A.v) * (1.0 / 6.0);
+      N1L = -dv6 * (2.0 * A.a + B.a); N1R = -dv6 * (A.a + 2.0 * B.a);
+      fL = fR = gL = gR = 0.0;
+      return;
+    }
     const double da = B.a - A.a;
     const double sL = 2.0 * A.v + B.v, sR = A.v + 2.0 * B.v;
     const double da6 = da * (1.0 / 6.0);
@@ -108,6 +115,14 @@ struct CellC {
   }
   // derivatives with respect to the two nodal values of uh (Jacobian rows)
   PK_HD void compute_jac(const Params& p, const NodeS& A, const NodeS& B) {
+    if (PK_IS_TEST(MODE)) {
+      const double dv6 = (B.v - A.v) * (1.0 / 6.0), d6 = p.dt * (1.0 / 6.0);
+      const double sa = d6 * (2.0 * A.a + B.a), sb = d6 * (A.a + 2.0 * B.a);
+      dN1L0 = sa - 2.0 * dv6; dN1L1 = -sa - dv6;
+      dN1R0 = sb - dv6;       dN1R1 = -sb - 2.0 * dv6;
+      dfL0 = dfL1 = dfR0 = dfR1 = 0.0; dgL0 = dgL1 = dgR0 = dgR1 = 0.0;
+      return;
+    }
     const double da = B.a - A.a;
     const double sL = 2.0 * A.v + B.v, sR = A.v + 2.0 * B.v;
     const double dd = da * (1.0 / 6.0) * p.dt;
@@ -233,15 +248,26 @@ struct Thread {
     const double u0 = sh.ld(sh.U0, i), u1 = sh.ld(sh.U1, i);
     n.a = 0.5 * (u1 + u0);
     n.w = u1 - u0;
-    n.F = sh.ld(sh.F, i);
+    n.F = PK_IS_TEST(MODE) ? 0.0 : sh.ld(sh.F, i);
     if (MODE == NOISE_FULL) { n.G = sh.ld(sh.G, i); n.x = sh.ld(sh.Xx, i); n.y = sh.ld(sh.Xxx, i); }
     else { n.G = 0.0; n.x = 0.0; n.y = 0.0; }
-    const double X = (MODE == NOISE_SCALAR) ? Xs : sh.ld(sh.X, i);
+    const double X = (PK_NOISE_OF(MODE) == NOISE_SCALAR) ? Xs : sh.ld(sh.X, i);
     n.v = p.dt * n.a + X;
   }
 
   // Residual and Jacobian rows of node n0 (neighbours nm, np; cells pc = (nm,n0), cc = (n0,np)).
   PK_HD void node_packet(const Params& p, const CellC<MODE>& cc, Packet& k, bool lite) {
+    if (PK_IS_TEST(MODE)) {
+      // one unknown: R = M (u1 - u) + N1 (N1 = -T), Newton matrix M + N1'/2: row n0 only
+      const double R = p.mb * (nm.w + np.w) + p.ma * n0.w + (pc.N1R + cc.N1L);
+      fn2 += R * R;
+      if (lite) return;
+      k.C0[0] = 0.5 * pc.dN1R0; k.C0[1] = 0.5 * (pc.dN1R1 + cc.dN1L0); k.C0[2] = 0.5 * cc.dN1L1;
+      PK_UNROLL
+      for (int c = 0; c < 3; ++c) { k.Cm[c] = 0.0; k.Cp[c] = 0.0; }
+      k.Q0 = R; k.Qm = 0.0; k.Qp = 0.0;
+      return;
+    }
     const double N1 = pc.N1R + cc.N1L, ff = pc.fR + cc.fL;
     const double Rpsi = p.mb * (nm.w + np.w) + p.ma * n0.w + N1 - 0.5 * (nm.F - np.F)
                         + ((MODE == NOISE_FULL) ? (p.mb * (nm.G + np.G) + p.ma * n0.G) : 0.0);
@@ -620,6 +646,21 @@ struct Thread {
     }
   }
 
+  // ---- scheme 'test': the unknown is u1 alone, no Helmholtz relations to update ------------------
+  template <class SH>
+  PK_HD void test_update(const Params& p, const SH& sh) {
+    sn2 = 0.0; xn2 = 0.0;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (j < m) {
+        const int i = idx(p, j);
+        const double u1n = sh.ld(sh.U1, i) + du[j];
+        sh.st(sh.U1, i, u1n);
+        sn2 += du[j] * du[j]; xn2 += u1n * u1n;
+      }
+    }
+  }
+
   // ---- accept the step: u <- u1 (equations.py:195) ----------------------------------------------
   template <class SH>
   PK_HD void accept(const Params& p, const SH& sh) {
@@ -634,7 +675,7 @@ struct Thread {
   // contiguous and every thread fills exactly its own rows.
   template <class SH>
   PK_HD void fill_noise(const Params& p, const SH& sh, const double* xi, const double* xi_x, const double* xi_xx) {
-    if (MODE == NOISE_SCALAR) return;
+    if (PK_NOISE_OF(MODE) == NOISE_SCALAR) return;
     const int T = TN(p), TM = T * M;
     double X[M], Xx[M], Xxx[M];
     PK_UNROLL
@@ -812,7 +853,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     ex.sync();
     ex.tick(0);
     if (failed >= 0) continue;
-    if (MODE == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
+    if (PK_NOISE_OF(MODE) == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
     else ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
     ex.sync();
     ex.tick(1);
@@ -859,6 +900,13 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       ex.each([&](Th& th) { th.interior_solve(p, sh); });
       ex.sync();
       ex.tick(9);
+      if constexpr (PK_IS_TEST(MODE)) {
+        ex.each([&](Th& th) { th.test_update(p, sh); });
+        ex.sync();
+        ex.tick(11);
+        ++it;
+        continue;
+      }
       // forward cyclic scan (causal filter); its carries feed the anticausal local pass, whose maps
       // are scanned in reverse; the reverse carries finish the update.
       ex.scan_fwd([&](Th& th, double& A, double& c0, double& c1) { th.helm_causal_local(p, sh, A, c0, c1); },

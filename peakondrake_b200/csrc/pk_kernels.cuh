@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
   double* nxt = smem + 3 * n;
   if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
-  else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
+  else if (PK_NOISE_OF(MODE) == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
   sh.xb = nxt; nxt += XB_SLOTS * Tn;
   double* red = nxt; nxt += 6 * (blockDim.x >> 5);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(TB, 1) pk_step_cluster_kernel(const __grid_con
   sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
   double* nxt = smem + 3 * n;
   if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
-  else if (MODE == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
+  else if (PK_NOISE_OF(MODE) == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
   sh.xb = nxt; nxt += XB_SLOTS * Tc;
   double* red = nxt; nxt += 2 * (3 * (Tc >> 5) + 3);

@@ -8,6 +8,7 @@
 
 
 template <int M> static ckern_t pick_cmode(int mode, int Tc) {
+  if (PK_IS_TEST(mode)) return nullptr;      // scheme 'test': single-CTA meshes only
   if (Tc <= 256) {
     switch (mode) {
       case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 256>;
@@ -33,6 +34,8 @@ template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {
   switch (mode) {
     case NOISE_SCALAR: return pick_tb<M, NOISE_SCALAR>(block, T, minb);
     case NOISE_X: return pick_tb<M, NOISE_X>(block, T, minb);
+    case TEST_SCALAR: return pick_tb<M, TEST_SCALAR>(block, T, minb);
+    case TEST_X: return pick_tb<M, TEST_X>(block, T, minb);
     default: return pick_tb<M, NOISE_FULL>(block, T, minb);
   }
 }

@@ -345,7 +345,9 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (cfg->R < 1) return fail(nullptr, "pk_create: R must be >= 1");
   if (cfg->noise_mode < 0 || cfg->noise_mode > 2) return fail(nullptr, "pk_create: bad noise_mode %d", cfg->noise_mode);
   if (cfg->num_xis < 0) return fail(nullptr, "pk_create: num_xis < 0");
-  if (cfg->scheme != 0 && cfg->scheme != 1) return fail(nullptr, "pk_create: bad scheme %d", cfg->scheme);
+  if (cfg->scheme < 0 || cfg->scheme > 2) return fail(nullptr, "pk_create: bad scheme %d", cfg->scheme);
+  if (cfg->scheme == 2 && cfg->noise_mode == PK_NOISE_FULL)
+    return fail(nullptr, "pk_create: the 'test' scheme takes dXi only (noise_mode SCALAR or X)");
   if (cfg->scheme == 1 && cfg->noise_mode == PK_NOISE_FULL)
     return fail(nullptr, "pk_create: the upwind scheme takes dXi only (noise_mode SCALAR or X)");
   if (cfg->noise_mode == PK_NOISE_SCALAR && cfg->num_xis > 1)
@@ -358,7 +360,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   Params& p = c->p;
   memset(&p, 0, sizeof(p));
   p.ne = cfg->ne; p.h = cfg->Ld / cfg->ne; p.dt = cfg->dt; p.alphasq = cfg->alphasq;
-  p.mode = cfg->noise_mode; p.nxi = cfg->num_xis; p.nupd = cfg->nxi_updates > 0 ? cfg->nxi_updates : 1;
+  p.mode = cfg->noise_mode + (cfg->scheme == 2 ? 3 : 0); p.nxi = cfg->num_xis; p.nupd = cfg->nxi_updates > 0 ? cfg->nxi_updates : 1;
   p.max_it = cfg->max_it > 0 ? cfg->max_it : 50;
   p.rtol = cfg->rtol > 0 ? cfg->rtol : 1e-8; p.atol = cfg->atol > 0 ? cfg->atol : 1e-50;
   p.stol = cfg->stol > 0 ? cfg->stol : 1e-8; p.divtol = cfg->divtol > 0 ? cfg->divtol : 1e4;
@@ -373,7 +375,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     }
   }
   fill_constants(p);
-  const int narr = p.mode == NOISE_FULL ? 7 : (p.mode == NOISE_X ? 4 : 3);
+  const int narr = p.mode == NOISE_FULL ? 7 : (PK_NOISE_OF(p.mode) == NOISE_X ? 4 : 3);
   c->block = p.T < 32 ? 32 : p.T;
   c->cluster = 1; c->lgTc = 0;
   c->smem = sizeof(double) * ((size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1));
@@ -384,6 +386,10 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   }
   int force = 0;
   { const char* e = getenv("PK_FORCE_CLUSTER"); force = e ? atoi(e) : 0; }   // testing: split small meshes too
+  if (cfg->scheme == 2 && (c->block > 512 || c->smem > 227 * 1024)) {
+    const int ne = p.ne; delete c;
+    return fail(nullptr, "pk_create: the 'test' scheme supports ne <= 4096 (ne=%d)", ne);
+  }
   if (cfg->scheme == 0 && (force > 1 || c->block > 512 || c->smem > 227 * 1024)) {
     // one realisation per thread-block cluster: C CTAs of Tc threads
     int Tc = 256, C = p.T / Tc;
@@ -407,7 +413,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (c->cluster > 8) cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   e = cfg->scheme == 1 ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaFuncSetAttribute(smem=%zu): %s", c->smem, m.c_str()); }
-  if (cfg->scheme == 0 && c->cluster == 1) {
+  if (cfg->scheme != 1 && c->cluster == 1) {
     // persistent CTAs: as many as are resident at once
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, c->block, c->smem);
@@ -444,10 +450,10 @@ __global__ void pk_permute_table_kernel(const __grid_constant__ Params p, const 
 
 extern "C" int pk_set_tables(pk_ctx* c, const double* xi, const double* xi_x, const double* xi_xx) {
   if (!c) return -1;
-  if (c->p.mode != NOISE_SCALAR && c->p.nxi > 0 && !xi) return fail(c, "pk_set_tables: xi is required");
+  if (PK_NOISE_OF(c->p.mode) != NOISE_SCALAR && c->p.nxi > 0 && !xi) return fail(c, "pk_set_tables: xi is required");
   if (c->p.mode == NOISE_FULL && c->p.nxi > 0 && (!xi_x || !xi_xx)) return fail(c, "pk_set_tables: xi_x and xi_xx are required for PK_NOISE_FULL");
   c->xi = c->xi_x = c->xi_xx = nullptr;
-  if (c->p.nxi == 0 || c->p.mode == NOISE_SCALAR) return 0;
+  if (c->p.nxi == 0 || PK_NOISE_OF(c->p.mode) == NOISE_SCALAR) return 0;
   CK(c, cudaSetDevice(c->cfg.device));
   const size_t n = (size_t)c->p.nxi * c->p.T * c->p.M;
   const double* src[3] = {xi, xi_x, xi_xx};
@@ -484,10 +490,10 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
                        int32_t* its_total, void* stream) {
   if (!c) return -1;
   if (nsteps < 0) return fail(c, "pk_step: nsteps < 0");
-  if (c->cfg.scheme != 0) return fail(c, "pk_step: context was created for the upwind scheme; use pk_step_upwind");
+  if (c->cfg.scheme == 1) return fail(c, "pk_step: context was created for the upwind scheme; use pk_step_upwind");
   if (!u || !u1 || !dF || !fail_step || !its_last || !its_total) return fail(c, "pk_step: null state/counter pointer");
   if (c->p.mode == NOISE_FULL && !dG) return fail(c, "pk_step: dG is required for PK_NOISE_FULL");
-  if (c->p.mode != NOISE_SCALAR && c->p.nxi > 0 && !c->xi) return fail(c, "pk_step: noise tables not set (pk_set_tables)");
+  if (PK_NOISE_OF(c->p.mode) != NOISE_SCALAR && c->p.nxi > 0 && !c->xi) return fail(c, "pk_step: noise tables not set (pk_set_tables)");
   if (nsteps == 0) return 0;
   CK(c, cudaSetDevice(c->cfg.device));
   StepArgs a;

@@ -20,8 +20,14 @@ namespace pk {
 enum NoiseMode {
   NOISE_SCALAR = 0,   // dXi is one number per step (num_Xis==0, or Xi_family 'constant'); dXi_x=dXi_xx=0 => dG == 0
   NOISE_X = 1,        // dXi varies in space, dXi_x=dXi_xx=0 ('no_gradient', stochastic_functions.py:121,189,232) => dG == 0
-  NOISE_FULL = 2      // 'hydrodynamic' with tables xi, xi_x, xi_xx (stochastic_functions.py:128-154,189-201)
+  NOISE_FULL = 2,     // 'hydrodynamic' with tables xi, xi_x, xi_xx (stochastic_functions.py:128-154,189-201)
+  // scheme 'test' (equations.py:132-145): one CG1 unknown u1, residual M(u1-u) - int psi uh (dv)_x, noise as in
+  // NOISE_SCALAR / NOISE_X.  Encoded in the mode so that the same kernels, executors and dispatch serve it.
+  TEST_SCALAR = 3,
+  TEST_X = 4
 };
+#define PK_IS_TEST(MODE) ((MODE) >= 3)
+#define PK_NOISE_OF(MODE) ((MODE) >= 3 ? (MODE) - 3 : (MODE))
 
 struct Params {
   int ne;        // cells == CG1 dofs
@@ -69,6 +75,7 @@ static inline void fill_constants(Params& p) {
   p.hm0 = 2.0 * p.hb * p.mb + p.ha * p.ma;
   p.hm1 = p.hb * p.ma + p.ha * p.mb;
   p.hm2 = p.hb * p.mb;
+  if (PK_IS_TEST(p.mode)) { p.hm0 = p.ma; p.hm1 = p.mb; p.hm2 = 0.0; }   // 'test': the Newton matrix is M - T'/2 (tridiagonal)
   p.c1 = p.dt * h / 12.0; p.c2 = a2 * p.dt / (4.0 * h);
   p.h6 = h / 6.0; p.a26 = a2 / 6.0;
   const double disc = std::sqrt(p.ha * p.ha - 4.0 * p.hb * p.hb);

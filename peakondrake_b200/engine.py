@@ -14,7 +14,7 @@ import torch
 from peakondrake_b200 import _lib
 from peakondrake_b200.stochastic_functions import build_tables, circulant_tridiag_solve
 
-CG1_MIDPOINT_SCHEMES = ('hydrodynamic', 'no_gradient')
+CG1_MIDPOINT_SCHEMES = ('hydrodynamic', 'no_gradient', 'test')
 
 
 def validate_scheme(scheme, timestepping, alphasq=1.0, gamma=0.0):
@@ -24,10 +24,6 @@ def validate_scheme(scheme, timestepping, alphasq=1.0, gamma=0.0):
             return
         if scheme == 'upwind' and timestepping == 'ssprk3':
             return
-        if (scheme, timestepping) in (('test', 'midpoint'),):
-            raise NotImplementedError('Scheme %s with %s exists in the reference but is outside the '
-                                      'B200 hot path built so far (DESIGN.md, "out of scope").'
-                                      % (scheme, timestepping))
         raise ValueError('Scheme %s and timestepping %s either not compatible or not recognised.'
                          % (scheme, timestepping))
     elif alphasq == 0.0 and gamma > 0.0:
@@ -83,7 +79,7 @@ class EnsembleIntegrator(object):
                             device=self.device.index, seed=int(seed), rid_offset=int(rid_offset), max_it=0,
                             rtol=0.0, atol=0.0, stol=0.0, divtol=0.0,
                             xi_const=float(xi[0, 0]) if (spatially_constant and self.num_Xis) else 0.0,
-                            scheme=1 if self.upwind else 0)
+                            scheme=1 if self.upwind else (2 if scheme == 'test' else 0))
         ctx = ctypes.c_void_p()
         rc = self.lib.pk_create(ctypes.byref(cfg), ctypes.byref(ctx))
         if rc != 0:

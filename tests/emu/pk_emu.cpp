@@ -168,6 +168,8 @@ static void run_mode(const Params& p, StepIO io, double* u, double* u1, double* 
   switch (p.mode) {
     case NOISE_SCALAR: run_one<M, NOISE_SCALAR>(p, io, u, u1, dF, dG, order); break;
     case NOISE_X: run_one<M, NOISE_X>(p, io, u, u1, dF, dG, order); break;
+    case TEST_SCALAR: run_one<M, TEST_SCALAR>(p, io, u, u1, dF, dG, order); break;
+    case TEST_X: run_one<M, TEST_X>(p, io, u, u1, dF, dG, order); break;
     default: run_one<M, NOISE_FULL>(p, io, u, u1, dF, dG, order); break;
   }
 }

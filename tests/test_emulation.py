@@ -171,3 +171,28 @@ def test_step_blocks_are_bit_identical_to_one_pass():
         for a, b in zip(out[0], o):
             assert np.array_equal(a, b)
     assert out[0][5].min() >= 2 * nsteps and np.abs(out[0][4]).min() > 0
+
+
+@pytest.mark.parametrize('ne,fam,nxi,sigma', [(200, 'sines', 3, 0.2), (1000, 'sines', 4, 0.2), (300, 'constant', 1, 1.0),
+                                             (64, 'sines', 0, 0.0), (37, 'gaussians', 2, 0.3)])
+def test_test_scheme(ne, fam, nxi, sigma):
+    """Scheme 'test' (equations.py:132-145): one CG1 unknown, M(u1-u) - int psi uh (dv)_x = 0, served by the
+    same kernel code with modes TEST_SCALAR / TEST_X (tridiagonal Newton matrix through the pentadiagonal solver)."""
+    Ld, dt, nsteps = 40.0, 1e-3, 6
+    mesh = O.Mesh1D(ne, Ld)
+    u0 = O.initial_u(mesh, 'proper_peak')
+    tabs = O.noise_tables(mesh, fam, nxi, sigma, scheme='test') if nxi else None
+    dW = O.reference_dW(3, nsteps, nxi, dt) if nxi else None
+    ref = O.run(ne, Ld, dt, nsteps, u0, dW, tabs, scheme='test')
+    assert rel(ref['u'], u0) > 1e-6
+    u = u0[None].copy(); u1 = np.zeros_like(u); dF = np.zeros_like(u); dG = np.zeros_like(u)
+    if nxi == 0 or fam == 'constant':
+        mode, xc = 3, (tabs[0][0, 1] if nxi else 0.0)
+    else:
+        mode, xc = 4, 0.0
+    tc = [np.ascontiguousarray(t) for t in tabs] if tabs is not None else None
+    r = emu_step(ne, Ld, dt, mode, u, u1, dF, dG, tc, None if dW is None else np.ascontiguousarray(dW[:, None, :]),
+                 nsteps, xi_const=xc, nxi=nxi)
+    assert r['fail_step'][0] == -1 and r['its_total'][0] == ref['its'].sum()
+    assert rel(u[0], ref['u']) <= TOL and rel(u1[0], ref['w1'][:ne]) <= TOL
+    assert not dF.any() and not dG.any()

@@ -200,3 +200,24 @@ def test_experiment_multi_parameter_sweep_schema(tmp_path, monkeypatch):
             orc = ref['oracle']
             e = ref['u'] @ (orc.M @ ref['u']) + ref['u'] @ (orc.K @ ref['u'])
             assert abs(d['energy'][2, ir, js, 1] - e) <= 1e-10 * e
+
+
+def test_experiment_with_the_test_scheme(tmp_path, monkeypatch):
+    """scheme 'test' / 'midpoint' (equations.py:132-145) through the drop-in: seeds batched, u_field and
+    energy against the oracle run with the reference's stream per seed."""
+    from peakondrake_b200 import experiment, outputting as out
+    monkeypatch.chdir(tmp_path)
+    Ld, dt, ne, nxi, sigma, seeds = 40., 1e-3, 150, 3, 0.2, [1, 4]
+    experiment('tscheme', Ld, 0.006, resolutions=ne, dts=dt, sigmas=sigma, seeds=seeds, schemes='test',
+               timesteppings='midpoint', ics='proper_peak', num_Xis=nxi, Xi_family='sines', alphasq=1.0, c0=0.,
+               gamma=0., diagnostics=['energy', 'l2_u', 'u_field'], ndump=3)
+    d = out.read_data_file('results/tscheme/data.nc')
+    mesh = O.Mesh1D(ne, Ld)
+    u0 = O.initial_u(mesh, 'proper_peak')
+    tabs = O.noise_tables(mesh, 'sines', nxi, sigma, scheme='test')
+    orc = O.CHOracle(ne, Ld, dt, scheme='test')
+    for k, s in enumerate(seeds):
+        ref = O.run(ne, Ld, dt, 6, u0, O.reference_dW(s, 6, nxi, dt), tabs, scheme='test')
+        assert rel(d['u_field'][2, k], ref['u']) <= 1e-10
+        e = ref['u'] @ (orc.M @ ref['u']) + ref['u'] @ (orc.K @ ref['u'])
+        assert abs(d['energy'][2, k] - e) <= 1e-10 * e

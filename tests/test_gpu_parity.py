@@ -100,6 +100,30 @@ def test_no_gradient_scheme():
     assert run_case(400, 3, 8, scheme='no_gradient', nxi=3) <= TOL
 
 
+@pytest.mark.parametrize('ne,fam,nxi,sigma', [(400, 'sines', 3, 0.2), (1000, 'sines', 4, 0.2), (300, 'constant', 1, 1.0),
+                                             (64, 'sines', 0, 0.0), (2000, 'sines', 2, 0.1)])
+def test_test_scheme(ne, fam, nxi, sigma):
+    """Scheme 'test' / 'midpoint' (equations.py:132-145) against the oracle: same Newton counts, u within 1e-10."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, draw_dW
+    Ld, dt, nsteps, R = 40.0, 1e-3, 9, 3
+    u0 = build_initial_u(ne, Ld, 'proper_peak')
+    eng = EnsembleIntegrator(ne, Ld, dt, R, scheme='test', num_Xis=nxi, Xi_family=fam, sigma=sigma)
+    eng.set_state(u0)
+    dW = np.stack([draw_dW(r, nsteps, nxi, dt) for r in range(R)], axis=1) if nxi else None
+    eng.step(4, dW=None if dW is None else dW[:4])
+    eng.step(5, dW=None if dW is None else dW[4:])
+    torch.cuda.synchronize()
+    tabs = O.noise_tables(O.Mesh1D(ne, Ld), fam, nxi, sigma, scheme='test') if nxi else None
+    u, u1 = eng.u.cpu().numpy(), eng.u1.cpu().numpy()
+    for r in range(R):
+        ref = O.run(ne, Ld, dt, nsteps, u0, None if dW is None else dW[:, r, :], tabs, scheme='test')
+        assert eng.fail_step[r].item() == -1 and eng.its_total[r].item() == ref['its'].sum()
+        assert rel(u[r], ref['u']) <= TOL and rel(u1[r], ref['w1'][:ne]) <= TOL
+    assert not eng.dF.any().item()
+    eng.close()
+
+
 def test_no_noise_modes():
     assert run_case(300, 2, 8, nxi=0) <= TOL
 
