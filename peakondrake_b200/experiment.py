@@ -166,7 +166,8 @@ def experiment(code, Ld, tmax, resolutions=[],
                 return tuple(si if k == 'seed' else combo_index[k] for k in keys)
 
             res = run_batch(p, seed_vals, list(range(len(seed_vals))), df, diagnostics, index_of,
-                            rng=rng, device=device, return_state=expected_u)
+                            rng=rng, device=device, return_state=expected_u,
+                            fields_to_output=fields_to_output, dim_names=keys)
             if expected_u:
                 mean_u = res['u'].mean(axis=0)
             df.save()

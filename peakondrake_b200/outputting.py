@@ -182,3 +182,109 @@ def mu_diagnostic(u, du, x_cells, Ld):
             print('No peakon detected, using half-mu instead')
             alt.append(wrap(abs(xmin - xmax)) / 2)
     return old, alt
+
+
+# ---------------------------------------------------------------------------------------------------
+# Field dumps: the reference writes `dirname/fields[_<dim><index>...]_output.pvd` through Firedrake's
+# File (outputting.py:59-68,224-232), i.e. a ParaView collection of .vtu pieces, one per dump.  On a
+# periodic interval Firedrake's output space is DG1 (every cell owns its two end points), which holds
+# CG1, DG0 and DG1 fields alike; the same layout is written here as ASCII VTK XML.
+# ---------------------------------------------------------------------------------------------------
+
+
+def m_from_u(u, Ld, alphasq):
+    """Diagnostic field m (diagnostic_equations.py:236-243): M m = (M + alphasq K) u on the periodic CG1 mesh."""
+    from peakondrake_b200.stochastic_functions import circulant_tridiag_solve
+    u = np.asarray(u, dtype=float)
+    h = Ld / u.shape[-1]
+    hb, ha = h / 6.0 - alphasq / h, 2.0 * h / 3.0 + 2.0 * alphasq / h
+    b = hb * (np.roll(u, 1, -1) + np.roll(u, -1, -1)) + ha * u
+    return circulant_tridiag_solve(h / 6.0, 2.0 * h / 3.0, b)
+
+
+def u_sde_field(x, Ld, alphasq, p_true, q, periodic):
+    """Nodal values of the peakon profile (diagnostic_equations.py:254-279) with the amplitude of :377; the
+    third periodic branch keeps the reference's parenthesis as written (:270)."""
+    a = np.sqrt(alphasq)
+    x = np.asarray(x, dtype=float)
+    E = np.exp(-Ld / a)
+    p = p_true * 0.5 * (1 + E) / (1 - E)
+    with np.errstate(over='ignore'):
+        if periodic:
+            b1 = p * ((np.exp(-(x - q + Ld) / a) + E * np.exp((x - q + Ld) / a)) / (1 - E))
+            b2 = p * ((np.exp(-np.sqrt((q - x) ** 2 / alphasq)) + E * np.exp(np.sqrt((q - x) ** 2 / alphasq))) / (1 - E))
+            b3 = p * ((np.exp(-(q + Ld - x) / a) + np.exp(-Ld / a * np.exp((q + Ld - x) / a))) / (1 - E))
+        else:
+            b1 = p * np.exp(-(x - q + Ld) / a)
+            b2 = p * np.exp(-np.sqrt((q - x) ** 2 / alphasq))
+            b3 = p * np.exp(-(q + Ld - x) / a)
+    return np.where(x < q - Ld / 2, b1, np.where(x < q + Ld / 2, b2, b3))
+
+
+def field_file_name(dirname, dim_names, indices):
+    name = dirname + '/fields'
+    for d, i in zip(dim_names, indices):
+        name += '_' + str(d) + str(i)                                       # outputting.py:61-63
+    return name + '_output.pvd'
+
+
+def to_dg1(values, space):
+    """[ne] CG1 / DG0 values or [ne, 2] DG1 values -> [ne, 2] (left end, right end) of every cell."""
+    v = np.asarray(values, dtype=float)
+    if space == 'DG1':
+        return v.reshape(-1, 2)
+    if space == 'DG0':
+        return np.stack([v, v], axis=1)
+    return np.stack([v, np.roll(v, -1)], axis=1)                           # CG1: cell i = [node i, node i+1]
+
+
+class FieldFile(object):
+    """`File(name.pvd)` + `.write(*fields, time=t)` of the reference (outputting.py:63,231)."""
+
+    def __init__(self, pvd_name, ne, Ld):
+        self.pvd_name, self.ne, self.Ld = pvd_name, int(ne), float(Ld)
+        self.base = pvd_name[:-4]
+        self.entries = []
+
+    def write(self, fields, time):
+        """fields: ordered mapping name -> (values, 'CG1' | 'DG0' | 'DG1')."""
+        ne, h = self.ne, self.Ld / self.ne
+        piece = '%s_%d.vtu' % (self.base, len(self.entries))
+        xl = np.arange(ne) * h
+        pts = np.stack([xl, xl + h], axis=1).ravel()
+        with open(piece, 'w') as f:
+            f.write('<?xml version="1.0" ?>\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian">\n')
+            f.write('<UnstructuredGrid>\n<Piece NumberOfPoints="%d" NumberOfCells="%d">\n' % (2 * ne, ne))
+            f.write('<Points>\n<DataArray type="Float64" NumberOfComponents="3" format="ascii">\n')
+            f.write(' '.join('%.17g 0 0' % x for x in pts))
+            f.write('\n</DataArray>\n</Points>\n<Cells>\n<DataArray type="Int32" Name="connectivity" format="ascii">\n')
+            f.write(' '.join('%d %d' % (2 * i, 2 * i + 1) for i in range(ne)))
+            f.write('\n</DataArray>\n<DataArray type="Int32" Name="offsets" format="ascii">\n')
+            f.write(' '.join(str(2 * (i + 1)) for i in range(ne)))
+            f.write('\n</DataArray>\n<DataArray type="UInt8" Name="types" format="ascii">\n')
+            f.write(' '.join(['3'] * ne))                                   # VTK_LINE
+            f.write('\n</DataArray>\n</Cells>\n<PointData>\n')
+            for name, (vals, space) in fields.items():
+                f.write('<DataArray type="Float64" Name="%s" NumberOfComponents="1" format="ascii">\n' % name)
+                f.write(' '.join('%.17g' % v for v in to_dg1(vals, space).ravel()))
+                f.write('\n</DataArray>\n')
+            f.write('</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n')
+        self.entries.append((float(time), piece.split('/')[-1]))
+        with open(self.pvd_name, 'w') as f:
+            f.write('<?xml version="1.0" ?>\n<VTKFile type="Collection" version="0.1" byte_order="LittleEndian">\n<Collection>\n')
+            for t, name in self.entries:
+                f.write('<DataSet timestep="%.17g" part="0" file="%s" />\n' % (t, name))
+            f.write('</Collection>\n</VTKFile>\n')
+
+
+def read_field_piece(vtu_name):
+    """Test helper: {'points': [2 ne], name: [ne, 2]} of one .vtu piece written by FieldFile."""
+    import re
+    txt = open(vtu_name).read()
+    res = {}
+    m = re.search(r'<Points>\s*<DataArray[^>]*>\s*(.*?)\s*</DataArray>', txt, re.S)
+    res['points'] = np.array(m.group(1).split(), dtype=float).reshape(-1, 3)[:, 0]
+    pd = txt[txt.index('<PointData>'):]
+    for m in re.finditer(r'<DataArray type="Float64" Name="([^"]+)"[^>]*>\s*(.*?)\s*</DataArray>', pd, re.S):
+        res[m.group(1)] = np.array(m.group(2).split(), dtype=float).reshape(-1, 2)
+    return res

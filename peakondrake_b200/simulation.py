@@ -13,6 +13,7 @@ Loop semantics kept from the reference (simulation.py:81-135):
   * diagnostics are dumped at t=0 and then every `ndump` steps (:88,114-125).
 """
 import time
+from math import gcd
 from collections import OrderedDict
 import numpy as np
 
@@ -73,8 +74,11 @@ def _val(p, key):
     return p[key][-1]
 
 
+SUPPORTED_FIELDS = ('du', 'jump_du', 'm', 'u_sde', 'u_sde_weak', 'uscalar', 'Xiscalar')
+
+
 def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng='mt19937', device=None,
-              philox_seed=0, max_chunk=1000, return_state=False):
+              philox_seed=0, max_chunk=1000, return_state=False, fields_to_output=None, dim_names=()):
     """
     Integrate `len(seeds)` realisations that share every parameter but the seed.
 
@@ -82,6 +86,9 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
       seeds       : list of seed values; seed_indices: their indices along the 'seed' dimension
       data_file   : outputting.DataFile (or None); index_of(seed_index) -> tuple of indices of the swept
                     dimensions for that realisation (the reference's index_slices, outputting.py:43-50)
+      fields_to_output, dim_names : diagnostic fields of the .pvd dumps (written every field_ndump steps when
+                    field_ndump > 0, outputting.py:59-68,224-232) and the names of the swept dimensions that
+                    index_of() addresses (they go into the file name)
       rng         : 'mt19937' reproduces the reference's per-seed NumPy stream (host-drawn, uploaded);
                     'philox' draws in-kernel (throughput path)
     """
@@ -92,6 +99,15 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
     ic, num_Xis, fam = _val(params, 'ic'), int(_val(params, 'num_Xis')), _val(params, 'Xi_family')
     sigma = float(_val(params, 'sigma')) if num_Xis != 0 else 0.0
     ndump = int(_val(params, 'ndump'))
+    field_ndump = int(_val(params, 'field_ndump')) if 'field_ndump' in params else -1
+    fields_to_output = list(fields_to_output or [])
+    for fld in fields_to_output:
+        if fld in ('uscalar', 'Xiscalar') and scheme != 'upwind':
+            raise ValueError('Output field %s only usable with upwind scheme, not %s' % (fld, scheme))   # simulation.py:272-276
+        if field_ndump > 0 and fld not in SUPPORTED_FIELDS:
+            raise NotImplementedError('Output field %s is not part of the B200 hot path (DESIGN.md, out of scope)' % fld)
+        if field_ndump > 0 and fld == 'm' and scheme == 'upwind':
+            raise ValueError("'m' is a prognostic field of the upwind scheme and is always dumped")
     nupd = int(_val(params, 'nXi_updates'))
     allow_fail = bool(_val(params, 'allow_fail'))
     only_peakons = bool(_val(params, 'only_peakons'))
@@ -255,17 +271,72 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
                 data_file.put('q', ix, peq.q[k])
         return vals, idx
 
+    # ---- field dumps (.pvd collection per realisation) ----
+    field_files = None
+    if field_ndump > 0:
+        if ('u_sde' in fields_to_output or 'u_sde_weak' in fields_to_output) and true_pq is None:
+            raise ValueError('Output fields u_sde / u_sde_weak need true_peakon_data')
+        dirname = _val(params, 'dirname')
+        field_files = [out.FieldFile(out.field_file_name(dirname, dim_names, index_of(si)), ne, Ld)
+                       for si in seed_indices]
+    last_dW = [None]
+
+    def dump_fields(t, t_idx_now):
+        """prognostic fields in the order PrognosticVariables registers them (simulation.py:154-249), then the
+        requested diagnostic fields (outputting.py:66-68); nothing once a realisation has failed (simulation.py:129)"""
+        u_host = eng.u.cpu().numpy()
+        m_host = eng.m.cpu().numpy() if eng.upwind else None
+        failed = eng.fail_step.cpu().numpy() >= 0
+        xi, xi_x, xi_xx = eng.tables_host
+        for k, ff in enumerate(field_files):
+            if failed[k] and t > 0:
+                continue
+            w = np.zeros(num_Xis) if last_dW[0] is None else last_dW[0][k]
+            f = OrderedDict()
+            f['u'] = (u_host[k], 'CG1')
+            if scheme == 'upwind':
+                f['m'] = (m_host[k], 'DG1')
+            elif scheme == 'hydrodynamic':
+                f['dXi_x'] = (w @ xi_x if num_Xis else np.zeros(ne), 'CG1')
+                f['dXi_xx'] = (w @ xi_xx if num_Xis else np.zeros(ne), 'CG1')
+            f['dXi'] = (w @ xi if num_Xis else np.zeros(ne), 'CG1')
+            for fld in fields_to_output:
+                du = (np.roll(u_host[k], -1) - u_host[k]) * (ne / Ld)            # diagnostic_equations.py:94-101
+                if fld == 'du':
+                    f[fld] = (du, 'DG0')
+                elif fld == 'jump_du':
+                    f[fld] = (np.abs(du - np.roll(du, 1)), 'CG1')                # :103-113
+                elif fld == 'm':
+                    f[fld] = (out.m_from_u(u_host[k], Ld, alphasq), 'CG1')       # :236-243
+                elif fld == 'uscalar':
+                    f[fld] = (u_host[k], 'CG1')                                  # :79-80
+                elif fld == 'Xiscalar':
+                    f[fld] = (f['dXi'][0], 'CG1')                                # :81-82
+                elif fld in ('u_sde', 'u_sde_weak'):
+                    j = min(t_idx_now, len(true_pq[0]) - 1)
+                    us = out.u_sde_field(x_nodes, Ld, alphasq, true_pq[0][j], true_pq[1][j], periodic)   # :254-279
+                    # u_sde_weak: M w = M (u - u_sde) (:281-289), i.e. w = u - u_sde nodally
+                    f[fld] = (us if fld == 'u_sde' else u_host[k] - us, 'CG1')
+            ff.write(f, t)
+
     dump(0, 0.0)
+    if field_files is not None:
+        dump_fields(0.0, 0)                                                     # simulation.py:88-89
     t, done, t_idx = 0.0, 0, 1
     chunk = ndump if ndump > 0 else min(nsteps, max_chunk)
+    if field_ndump > 0:
+        chunk = gcd(chunk, field_ndump) if ndump > 0 else field_ndump
     while done < nsteps:
         c = min(chunk, nsteps - done)
         dW_chunk = None if host_dW is None else host_dW[done:done + c]
-        need_export = peq is not None and host_dW is None and num_Xis > 0
+        need_export = (peq is not None or field_files is not None) and host_dW is None and num_Xis > 0
         exported = eng.step(c, dW=dW_chunk, export_dW=need_export)
-        if peq is not None:
+        used = None
+        if peq is not None or field_files is not None:
             used = dW_chunk if dW_chunk is not None else (exported.cpu().numpy() if exported is not None
                                                           else np.zeros((c, R, 0)))
+            last_dW[0] = used[-1]
+        if peq is not None:
             for n in range(c):
                 peq.update(used[n])
         done += c
@@ -277,9 +348,12 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
                 k = int(np.argmax(fs >= 0))
                 raise ConvergenceError('Nonlinear solve failed to converge for seed %s at step %d'
                                        % (seeds[k], fs[k]))
-        if ndump > 0 and c == ndump:
+        if ndump > 0 and done % ndump == 0:
             dump(t_idx, t)
             t_idx += 1
+        if field_files is not None and done % field_ndump == 0:
+            # p, q of u_sde are read at the diagnostics index current at that moment (diagnostic_equations.py:373-378)
+            dump_fields(t, t_idx - 1 if (ndump > 0 and done % ndump == 0) else t_idx)   # simulation.py:128-131
 
     fs = eng.fail_step.cpu().numpy()
     if data_file is not None:
@@ -317,7 +391,8 @@ def simulation(simulation_parameters, diagnostic_values=None, fields_to_output=N
     fixed_index = tuple(simulation_parameters[d][0] for d in dims)
     seed = simulation_parameters['seed'][-1]
     res = run_batch(simulation_parameters, [seed], [0], data_file, diagnostic_values,
-                    index_of=lambda si: fixed_index, rng=rng, device=device, return_state=expected_u)
+                    index_of=lambda si: fixed_index, rng=rng, device=device, return_state=expected_u,
+                    fields_to_output=fields_to_output, dim_names=dims)
     if data_file is not None:
         data_file.save()
     if expected_u:

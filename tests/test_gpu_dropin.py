@@ -49,6 +49,18 @@ def test_experiment_seed_ensemble_matches_oracle_per_seed(tmp_path, monkeypatch)
             for name, v in sd.items():
                 assert abs(d[name][t, k] - v) <= 1e-9 * max(1.0, abs(v)), (name, t, k)
         assert abs(d['energy'][0, k] - (u0 @ (orc.M @ u0) + u0 @ (orc.K @ u0))) < 1e-12
+    # field dumps (outputting.py:59-68,224-232): one .pvd collection per realisation, prognostic fields + 'du'
+    for k, s in enumerate(seeds):
+        pvd = 'results/test_one_run/fields_seed%d_output.pvd' % k
+        assert open(pvd).read().count('<DataSet') == 11
+        piece = out.read_field_piece(pvd[:-4] + '_10.vtu')
+        assert sorted(piece) == sorted(['points', 'u', 'dXi_x', 'dXi_xx', 'dXi', 'du'])
+        assert np.array_equal(piece['u'][:, 0], d['u_field'][10, k]) and np.array_equal(piece['u'][:, 1], np.roll(d['u_field'][10, k], -1))
+        dW = O.reference_dW(s, 10, nxi, dt)
+        assert np.allclose(piece['dXi'][:, 0], dW[9] @ tabs[0], rtol=0, atol=1e-15)
+        assert np.allclose(piece['dXi_xx'][:, 0], dW[9] @ tabs[2], rtol=0, atol=1e-13)
+        assert np.allclose(piece['du'][:, 0], O.du_field(mesh, d['u_field'][10, k]), rtol=0, atol=1e-12)
+        assert not out.read_field_piece(pvd[:-4] + '_0.vtu')['dXi'].any()
     assert np.isfinite(d['mu_0']).all() and np.isnan(d['mu_1']).all()        # single peak
     assert np.isfinite(d['peakon_mu']).all() and (d['peakon_max_u'] > 0.4).all()
 
@@ -98,6 +110,13 @@ def test_true_peakon_workflow(tmp_path, monkeypatch):
     s = out.read_data_file('results/strong/data.nc')
     assert s['u_error_with_sde'].shape == (2,) and s['u_error_with_sde'][1] < 0.05
     assert s['u_error_with_sde'][1] == s['u_error_weak'][1]
+    # only_peakons: the PDE never runs, fields are dumped at t=0 only (simulation.py:88-89,128-131)
+    assert open('results/true_peakon_data/fields_output.pvd').read().count('<DataSet') == 1
+    piece = out.read_field_piece('results/strong/fields_output_1.vtu')
+    us = O.u_sde_field(O.Mesh1D(400, 40.), t['p'][1], t['q'][1], 1.0, True)
+    assert np.allclose(piece['u_sde'][:, 0], us, rtol=1e-13)
+    err = piece['u_sde_weak'][:, 0]
+    assert abs(np.sqrt(err @ (O.Mesh1D(400, 40.).mass() @ err)) - s['u_error_with_sde'][1]) < 1e-12
     # same Brownian path: the PDE peak follows the SDE peakon to within a few cells
     assert abs(s['q_pde'][1] - t['q'][1]) < 0.5
 
@@ -168,6 +187,10 @@ def test_reference_test_dumping_script_parameters(tmp_path, monkeypatch):
         for name, v in (('l2_u', l2u), ('h1_u', h1u), ('energy', u @ (orc.M @ u) + u @ (orc.K @ u)),
                         ('l2_m', nm['l2_m']), ('h1_m', nm['h1_m'])):
             assert abs(d[name][n] - v) <= 1e-10 * max(1.0, abs(v)), (name, n)
+    piece = out.read_field_piece('results/test_one_run/fields_output_10.vtu')
+    assert sorted(piece) == sorted(['points', 'u', 'm', 'dXi', 'uscalar', 'Xiscalar'])
+    assert np.allclose(piece['m'], m.reshape(20, 2), rtol=1e-10, atol=1e-12) and np.allclose(piece['uscalar'][:, 0], u, atol=1e-12)
+    assert np.allclose(piece['Xiscalar'][:, 0], dW[9] @ xi, atol=1e-15)
     with pytest.raises(IOError):          # re-running needs a fresh results directory (experiment.py:25-27)
         experiment(code, Ld, tmax, resolutions=20, dts=dt, sigmas=0.25, seeds=0, schemes='upwind',
                    timesteppings='ssprk3', ics='one_peak', num_Xis=7, Xi_family='sines', alphasq=1.0, c0=0., gamma=0.,
