@@ -6,7 +6,8 @@ timestep (BASELINE.json metric), workload = BASELINE config 2 per GPU:
   1024 realisations per GPU (weak scaling), Brownian increments drawn in-kernel (Philox).
 
 A bench "step" is ONE pass of the hot path over the batch: one kernel launch that advances every
-realisation of the shard by STEPS_PER_LAUNCH timesteps (the reference's dump cadence, ndump=50).
+realisation of the shard by STEPS_PER_LAUNCH timesteps (the reference's dump cadence, ndump=50);
+its persistent CTAs pull (realisation, block of timesteps) items from a work queue.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            own arm (GPU)
   python bench.py --impl reference ...                            CPU arm: the oracle port of the
@@ -31,7 +32,7 @@ NE, LD, DT, NXI, SIGMA, IC = 1000, 40.0, 1e-3, 4, 0.2, 'proper_peak'
 R_PER_GPU = 1024
 STEPS_PER_LAUNCH = 50
 B_ALG = 16 * NE + 8 * NXI      # algorithmic bytes per realisation-step
-DRAM_TRAFFIC_PER_LAUNCH = 35.36e6   # bytes, ncu capture profiles/r1a_ncu_full_pk_step_kernel.csv
+DRAM_TRAFFIC_PER_LAUNCH = 34.78e6   # bytes, ncu capture profiles/r1c_ncu_full_pk_step_kernel.csv
 METRIC = 'realisation_steps_per_sec'
 UNIT = 'realisation*steps/s'
 WORKLOAD = ('C2: stochastic CH hydrodynamic/midpoint, ne=1000, Ld=40, dt=1e-3, 4 sines sigma=0.2, '
@@ -323,8 +324,9 @@ def run_gpu(args):
                                          '(state is loaded once per launch and stepped on-chip for 50 timesteps)',
                          'kernel': 'pk_step_kernel', 'kernel_ms': k_ms,
                          'algorithmic_bytes_per_realisation_step': B_ALG,
-                         'note': 'fp64-pipe/latency bound by construction (SURVEY.md 8d): ~600 fp64 flop per '
-                                 'node-step against 16 algorithmic bytes; see DESIGN.md'},
+                         'note': 'not HBM-bound by construction (SURVEY.md 8d): ~700 fp64 instructions per node-step '
+                                 'against 16 algorithmic bytes; measured limiter is the instruction supply '
+                                 '(gcc instruction requests 96 % of peak, fp64 pipe 45 %), see DESIGN.md section 4'},
             'wall_ms_per_step': wall_ms / args.steps,
         }
         if args.cpu_baseline:
