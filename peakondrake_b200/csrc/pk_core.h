@@ -398,27 +398,32 @@ struct Thread {
     sh.st(sh.xb, 13 * TN(p) + t, wQm1);
 
     // back-substitute the five columns  x_I = y + Wn1 xs0 + Wn2 xs1 + Vn1 xR0 + Vn2 xR1
-    const int nI = m - 2;
+    // (a chunk has NI or NI-1 interior rows: the top row is skipped by short chunks, and the tips at the last
+    // two interior rows are picked once at the end instead of per row and column)
     double xp1[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
     double xp2[5] = {0.0, 0.0, 0.0, 0.0, 1.0};
-    double L2a[5], L2b[5];
+    double xa[5], xb_[5], xc[5];          // columns at interior rows NI-1, NI-2, NI-3
     PK_UNROLL
-    for (int c = 0; c < 5; ++c) { L2a[c] = L2b[c] = 0.0; F2a[c] = F2b[c] = 0.0; }
+    for (int c = 0; c < 5; ++c) { xa[c] = xb_[c] = xc[c] = 0.0; F2a[c] = F2b[c] = 0.0; }
     PK_UNROLL
     for (int k = NI - 1; k >= 0; --k) {
-      if (k < nI) {
+      if (k < NI - 1 || ext) {
         const double zc[5] = {zb[k], -zw1[k], -zw2[k], 0.0, 0.0};
         PK_UNROLL
         for (int c = 0; c < 5; ++c) {
           const double x = r[k] * (zc[c] - e[k] * xp1[c] - f[k] * xp2[c]);
           xp2[c] = xp1[c]; xp1[c] = x;
-          if (k == nI - 1) L2b[c] = x;
-          if (k == nI - 2) L2a[c] = x;
+          if (k == NI - 1) xa[c] = x;
+          if (k == NI - 2) xb_[c] = x;
+          if (k == NI - 3) xc[c] = x;
           if (k == 1) F2b[c] = x;
           if (k == 0) F2a[c] = x;
         }
       }
     }
+    double L2a[5], L2b[5];
+    PK_UNROLL
+    for (int c = 0; c < 5; ++c) { L2b[c] = ext ? xa[c] : xb_[c]; L2a[c] = ext ? xb_[c] : xc[c]; }
     // slots 0..9: tips at the LAST two interior rows, read by the right neighbour
     sh.st(sh.xb, 0 * TN(p) + t, L2a[0]); sh.st(sh.xb, 1 * TN(p) + t, L2b[0]);
     sh.st(sh.xb, 2 * TN(p) + t, L2a[1]); sh.st(sh.xb, 3 * TN(p) + t, L2a[2]);
@@ -621,11 +626,9 @@ struct Thread {
     sn2 = 0.0; xn2 = 0.0;
     // x_j = xl_j + rho^(m-j) * carry
     double pwv[M];
-    double pw = p.rho;
+    double pw = ext ? p.rho : 1.0;        // short chunks: row M-1 does not exist, row M-2 is the last one
     PK_UNROLL
-    for (int j = M - 1; j >= 0; --j) {
-      if (j < m) { pwv[j] = pw; pw *= p.rho; } else { pwv[j] = 0.0; }
-    }
+    for (int j = M - 1; j >= 0; --j) { pwv[j] = pw; pw *= p.rho; }
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       if (j < m) {
@@ -813,16 +816,17 @@ struct StepIO {
 
 // SNES convergence test (SNESConvergedDefault + divergence tolerance).
 // returns 0 = keep iterating, 1 = converged, 2 = diverged (reason set)
-PK_HD int snes_test(const Params& p, int it, const double* nrm, double& fnorm0, int& reason) {
-  const double fnorm = sqrt(nrm[0]);
-  if (!(fnorm == fnorm) || fnorm > 1.7e308) { reason = 2; return 2; }
+// The comparisons are made on the squared 2-norms (no square roots on the device); fnorm0sq keeps |F_0|^2.
+PK_HD int snes_test(const Params& p, int it, const double* nrm, double& fnorm0sq, int& reason) {
+  const double f2 = nrm[0];
+  if (!(f2 <= 1.7976931348623157e308)) { reason = 2; return 2; }      // NaN or Inf
   if (it == 0) {
-    fnorm0 = fnorm;
-    if (fnorm < p.atol) return 1;
+    fnorm0sq = f2;
+    if (f2 < p.atol2) return 1;
   } else {
-    if (fnorm < p.atol || fnorm <= p.rtol * fnorm0) return 1;
-    if (sqrt(nrm[1]) < p.stol * sqrt(nrm[2])) return 1;
-    if (fnorm > p.divtol * fnorm0) { reason = 3; return 2; }
+    if (f2 < p.atol2 || f2 <= p.rtol2 * fnorm0sq) return 1;
+    if (nrm[1] < p.stol2 * nrm[2]) return 1;
+    if (f2 > p.divtol2 * fnorm0sq) { reason = 3; return 2; }
   }
   if (it >= p.max_it) { reason = 1; return 2; }
   return 0;

@@ -14,9 +14,11 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 // AA ("all active") is true for every launch with T >= 32 chunks: then no thread of the block is idle and
 // the phase calls are unconditional, which lets the compiler see the per-thread arrays die between phases.
-template <class ThT, bool AA>
+// TBC > 0: block size known at compile time (warp counts fold, the small per-warp loops unroll exactly).
+template <class ThT, bool AA, int TBC = 0>
 struct GpuExecT {
   typedef ThT Th;
+  static __device__ __forceinline__ int nwarps() { return TBC > 0 ? TBC / 32 : (int)(blockDim.x >> 5); }
   Th& th;
   double* red;          // [2][3*nw] reduction / scan scratch in shared memory, used alternately (ping-pong)
   int flip;             // so that a collective needs one barrier only: the area written by collective k
@@ -38,7 +40,7 @@ struct GpuExecT {
 #endif
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
   __device__ __forceinline__ double* area() {
-    const int nw = blockDim.x >> 5;
+    const int nw = nwarps();
     double* a = red + flip * 3 * nw;
     flip ^= 1;
     return a;
@@ -53,11 +55,12 @@ struct GpuExecT {
       v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
       v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
     double* sc = area();
     if (lane == 0) { sc[w] = v[0]; sc[nw + w] = v[1]; sc[2 * nw + w] = v[2]; }
     __syncthreads();
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
     for (int i = 0; i < nw; ++i) { s0 += sc[i]; s1 += sc[nw + i]; s2 += sc[2 * nw + i]; }
     out[0] = s0; out[1] = s1; out[2] = s2;
   }
@@ -66,7 +69,7 @@ struct GpuExecT {
   // entering thread t comes from t-1; DIR=-1: order T-1..0. Inactive threads carry the identity.
   template <int DIR>
   __device__ __forceinline__ void cyc_scan(double A, double c0, double c1, double& in0, double& in1) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
     // inclusive scan inside the warp (Kogge-Stone); "earlier" = lower lane for DIR=+1, higher for -1
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -83,11 +86,18 @@ struct GpuExecT {
     double* sc = area();
     if (lane == last) { sc[w] = A; sc[nw + w] = c0; sc[2 * nw + w] = c1; }
     __syncthreads();
-    // compose the warp aggregates in scan order; remember the prefix in front of my warp
-    double tA = 1.0, t0 = 0.0, t1 = 0.0, eA = 1.0, e0 = 0.0, e1 = 0.0;
-    for (int k = 0; k < nw; ++k) {
+    // compose the warp aggregates in scan order; the prefix in front of my warp is the state after `pos`
+    // of them (warp-uniform trip counts, no selects)
+    double tA = 1.0, t0 = 0.0, t1 = 0.0;
+    const int pos = (DIR > 0) ? w : nw - 1 - w;
+    for (int k = 0; k < pos; ++k) {
       const int ww = (DIR > 0) ? k : nw - 1 - k;
-      if (ww == w) { eA = tA; e0 = t0; e1 = t1; }
+      const double a = sc[ww];
+      t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
+    }
+    const double eA = tA, e0 = t0, e1 = t1;
+    for (int k = pos; k < nw; ++k) {
+      const int ww = (DIR > 0) ? k : nw - 1 - k;
       const double a = sc[ww];
       t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
     }
@@ -116,7 +126,7 @@ struct GpuExecT {
   }
 };
 
-template <int M, int MODE, bool AA, int TT> using GpuExec = GpuExecT<Thread<M, MODE, TT>, AA>;
+template <int M, int MODE, bool AA, int TT> using GpuExec = GpuExecT<Thread<M, MODE, TT>, AA, TT>;
 
 #include "pk_args.h"
 

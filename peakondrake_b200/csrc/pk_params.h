@@ -46,6 +46,7 @@ struct Params {
   double h6, a26;         // h/6, alphasq/6
   double rho, ikappa;     // H = kappa (1 - rho S)(1 - rho S^-1): |rho|<1
   double rtol, atol, stol, divtol;  // PETSc SNES defaults 1e-8, 1e-50, 1e-8, 1e4
+  double rtol2, atol2, stol2, divtol2;  // their squares (fill_constants): the tests compare squared norms
   double sdt;             // sqrt(dt / nupd)
   double xi_const;        // NOISE_SCALAR: the (spatially constant) value of xi_0, 0 if nxi==0
 };
@@ -83,6 +84,7 @@ static inline void fill_constants(Params& p) {
   p.rho = -p.hb / kappa;
   p.ikappa = 1.0 / kappa;
   p.sdt = std::sqrt(p.dt / (p.nupd > 0 ? p.nupd : 1));
+  p.rtol2 = p.rtol * p.rtol; p.atol2 = p.atol * p.atol; p.stol2 = p.stol * p.stol; p.divtol2 = p.divtol * p.divtol;
 }
 
 }  // namespace pk
