@@ -87,19 +87,25 @@ struct GpuExecT {
     if (lane == last) { sc[w] = A; sc[nw + w] = c0; sc[2 * nw + w] = c1; }
     __syncthreads();
     // compose the warp aggregates in scan order; the prefix in front of my warp is the state after `pos`
-    // of them (warp-uniform trip counts, no selects)
+    // of them (warp-uniform branches, no selects; unrolled exactly when the warp count is a constant)
     double tA = 1.0, t0 = 0.0, t1 = 0.0;
     const int pos = (DIR > 0) ? w : nw - 1 - w;
-    for (int k = 0; k < pos; ++k) {
-      const int ww = (DIR > 0) ? k : nw - 1 - k;
-      const double a = sc[ww];
-      t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
+#pragma unroll
+    for (int k = 0; k < (TBC > 0 ? TBC / 32 : nw); ++k) {
+      if (k < pos) {
+        const int ww = (DIR > 0) ? k : nw - 1 - k;
+        const double a = sc[ww];
+        t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
+      }
     }
     const double eA = tA, e0 = t0, e1 = t1;
-    for (int k = pos; k < nw; ++k) {
-      const int ww = (DIR > 0) ? k : nw - 1 - k;
-      const double a = sc[ww];
-      t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
+#pragma unroll
+    for (int k = 0; k < (TBC > 0 ? TBC / 32 : nw); ++k) {
+      if (k >= pos) {
+        const int ww = (DIR > 0) ? k : nw - 1 - k;
+        const double a = sc[ww];
+        t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
+      }
     }
     const double inv = PK_RCP(1.0 - tA);
     const double x0 = t0 * inv, x1 = t1 * inv;          // value entering the first thread (cyclic closure)
