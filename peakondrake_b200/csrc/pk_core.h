@@ -39,6 +39,7 @@ struct Shared {
   double *U0, *U1, *F, *G, *X, *Xx, *Xxx;
   double *xb;   // [18*T] exchange slots / PCR rows: slot c of thread t at c*T + t
   double *dW;   // [max(nxi,1)]
+  double *fac;  // FS variant only: [6*(M-2)*T] level-1 factors, component c of interior row k of thread t at (c*(M-2)+k)*T + t
   // flat index i = j*T + t (row j of chunk t).  One CTA per realisation: plain shared memory.
   PK_HD double ld(const double* a, int i) const { return a[i]; }
   PK_HD void st(double* a, int i, double v) const { a[i] = v; }
@@ -113,32 +114,34 @@ struct CellC {
       gL = gR = 0.0;
     }
   }
-  // derivatives with respect to the two nodal values of uh (Jacobian rows)
+  // derivatives with respect to the two nodal values of uh, PRE-SCALED the way the Newton matrix uses them
+  // (u1 enters through uh = (u1+u)/2):  dN1* = N1'/2,  df* = f'/4 (the matrix has -+ D f'/2 with D = +-1/2),
+  // dg* = g'/2.  All scalings are by powers of two, i.e. exact.
   PK_HD void compute_jac(const Params& p, const NodeS& A, const NodeS& B) {
     if (PK_IS_TEST(MODE)) {
-      const double dv6 = (B.v - A.v) * (1.0 / 6.0), d6 = p.dt * (1.0 / 6.0);
-      const double sa = d6 * (2.0 * A.a + B.a), sb = d6 * (A.a + 2.0 * B.a);
-      dN1L0 = sa - 2.0 * dv6; dN1L1 = -sa - dv6;
-      dN1R0 = sb - dv6;       dN1R1 = -sb - 2.0 * dv6;
+      const double dv12 = (B.v - A.v) * (1.0 / 12.0);
+      const double sa = p.dt12 * (2.0 * A.a + B.a), sb = p.dt12 * (A.a + 2.0 * B.a);
+      dN1L0 = sa - 2.0 * dv12; dN1L1 = -sa - dv12;
+      dN1R0 = sb - dv12;       dN1R1 = -sb - 2.0 * dv12;
       dfL0 = dfL1 = dfR0 = dfR1 = 0.0; dgL0 = dgL1 = dgR0 = dgR1 = 0.0;
       return;
     }
     const double da = B.a - A.a;
     const double sL = 2.0 * A.v + B.v, sR = A.v + 2.0 * B.v;
-    const double dd = da * (1.0 / 6.0) * p.dt;
-    dN1L0 = -sL * (1.0 / 6.0) + 2.0 * dd; dN1L1 = sL * (1.0 / 6.0) + dd;
-    dN1R0 = -sR * (1.0 / 6.0) + dd;       dN1R1 = sR * (1.0 / 6.0) + 2.0 * dd;
+    const double dd = da * p.dt12;
+    dN1L0 = -sL * (1.0 / 12.0) + 2.0 * dd; dN1L1 = sL * (1.0 / 12.0) + dd;
+    dN1R0 = -sR * (1.0 / 12.0) + dd;       dN1R1 = sR * (1.0 / 12.0) + 2.0 * dd;
     const double a0 = A.a, a1 = B.a;
-    const double k = 2.0 * p.c2 * da;
-    const double s2 = 2.0 * p.c1 * (a0 + a1);
-    dfL0 = p.c1 * (6.0 * a0 + 2.0 * a1) - k; dfL1 = s2 + k;
-    dfR0 = s2 - k;                           dfR1 = p.c1 * (2.0 * a0 + 6.0 * a1) + k;
+    const double k = p.c2h * da;
+    const double s2 = p.c1h * (a0 + a1);
+    dfL0 = p.c1q * (6.0 * a0 + 2.0 * a1) - k; dfL1 = s2 + k;
+    dfR0 = s2 - k;                            dfR1 = p.c1q * (2.0 * a0 + 6.0 * a1) + k;
     if (MODE == NOISE_FULL) {
       const double x0 = A.x, x1 = B.x, y0 = A.y, y1 = B.y;
       const double yL = 2.0 * y0 + y1, yR = y0 + 2.0 * y1;
       const double xs = x0 + x1;
-      dgL0 = p.h6 * (3.0 * x0 + x1) - p.a26 * yL; dgL1 = p.h6 * xs + p.a26 * yL;
-      dgR0 = p.h6 * xs - p.a26 * yR;              dgR1 = p.h6 * (x0 + 3.0 * x1) + p.a26 * yR;
+      dgL0 = p.h12 * (3.0 * x0 + x1) - p.a212 * yL; dgL1 = p.h12 * xs + p.a212 * yL;
+      dgR0 = p.h12 * xs - p.a212 * yR;              dgR1 = p.h12 * (x0 + 3.0 * x1) + p.a212 * yR;
     } else {
       dgL0 = dgL1 = dgR0 = dgR1 = 0.0;
     }
@@ -171,9 +174,19 @@ PK_HD void mva2(const double* A, const double* x, double* y) {
 
 // TT > 0: number of threads per realisation known at compile time (constant-folds the shared-memory
 // address arithmetic); TT == 0: read it from Params.
-template <int M, int MODE, int TT = 0>
+// FSV ("factors in shared memory"): the level-1 factors and the solution increment live in shared memory instead
+// of per-thread register arrays, so the row loops of the assembly / elimination, of the tip back-substitution and
+// of the interior solve are ROLLED (a few KB of code that stays in the instruction caches) instead of unrolled
+// over the M rows of a thread.  Costs 6(M-2) doubles of shared memory per thread.
+// VAR = 0 (default): fully unrolled Newton pass with register-resident factors; the residual-only pass (no factors
+//          involved) runs as a rolled loop (VAR = 4 unrolls that too).  Measured on B200:
+//          VAR 0 beats 4 by 6 %, and beats the rolled variants 1 and 2 by 24 % and 29 %.
+// VAR = 2 ("rolled assembly"): factors stay in registers, but the per-row assembly code is shared by a rolled loop
+// and only the elimination step of each interior row (static register indices) is selected by a switch.
+template <int M, int MODE, int TT = 0, int VAR = 0>
 struct Thread {
-  enum { NI = M - 2 };
+  enum { NI = M - 2, FS = (VAR == 1) ? 1 : 0, ROLL = (VAR == 2) ? 1 : 0, ROLL_LITE = (VAR != 4) ? 1 : 0 };
+  double h1[6], h2[6];            // FS: (r, e, f, zb, zw1, zw2) of the two previously eliminated interior rows
   static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
   // geometry
   int t, m, s, ext, tl, tr, ml, active;
@@ -214,12 +227,15 @@ struct Thread {
   // and time-step loops (~190 registers); these "kills" end those live ranges explicitly.
   PK_HD void kill_factors() {
     PK_UNROLL
+    for (int c = 0; c < 6; ++c) { h1[c] = 0.0; h2[c] = 0.0; }
+    if (FS) return;
+    PK_UNROLL
     for (int k = 0; k < NI; ++k) { r[k] = 0.0; e[k] = 0.0; f[k] = 0.0; zb[k] = 0.0; zw1[k] = 0.0; zw2[k] = 0.0; }
   }
   PK_HD void kill_all() {
     kill_factors();
     PK_UNROLL
-    for (int j = 0; j < M; ++j) { du[j] = 0.0; hF[j] = 0.0; hG[j] = 0.0; }
+    for (int j = 0; j < M; ++j) { if (!FS) du[j] = 0.0; hF[j] = 0.0; hG[j] = 0.0; }
     PK_UNROLL
     for (int c = 0; c < 5; ++c) { sp0[c] = 0.0; sp1[c] = 0.0; F2a[c] = 0.0; F2b[c] = 0.0; }
     PK_UNROLL
@@ -262,7 +278,7 @@ struct Thread {
       const double R = p.mb * (nm.w + np.w) + p.ma * n0.w + (pc.N1R + cc.N1L);
       fn2 += R * R;
       if (lite) return;
-      k.C0[0] = 0.5 * pc.dN1R0; k.C0[1] = 0.5 * (pc.dN1R1 + cc.dN1L0); k.C0[2] = 0.5 * cc.dN1L1;
+      k.C0[0] = pc.dN1R0; k.C0[1] = pc.dN1R1 + cc.dN1L0; k.C0[2] = cc.dN1L1;
       PK_UNROLL
       for (int c = 0; c < 3; ++c) { k.Cm[c] = 0.0; k.Cp[c] = 0.0; }
       k.Q0 = R; k.Qm = 0.0; k.Qp = 0.0;
@@ -276,15 +292,16 @@ struct Thread {
     if (MODE == NOISE_FULL) Rzeta = p.hb * (nm.G + np.G) + p.ha * n0.G - (pc.gR + cc.gL);
     fn2 += Rpsi * Rpsi + Rphi * Rphi + Rzeta * Rzeta;
     if (lite) return;                    // residual norm only (uniform across the block)
-    const double B[3] = {0.5 * pc.dN1R0, 0.5 * (pc.dN1R1 + cc.dN1L0), 0.5 * cc.dN1L1};
-    const double Fm[3] = {0.5 * pc.dfR0, 0.5 * (pc.dfR1 + cc.dfL0), 0.5 * cc.dfL1};
+    // tridiagonal rows of N1'/2, f'/4, g'/2 at node n0 (compute_jac delivers them pre-scaled)
+    const double B[3] = {pc.dN1R0, pc.dN1R1 + cc.dN1L0, cc.dN1L1};
+    const double Fq[3] = {pc.dfR0, pc.dfR1 + cc.dfL0, cc.dfL1};
     double Gm[3] = {0.0, 0.0, 0.0};
-    if (MODE == NOISE_FULL) { Gm[0] = 0.5 * pc.dgR0; Gm[1] = 0.5 * (pc.dgR1 + cc.dgL0); Gm[2] = 0.5 * cc.dgL1; }
+    if (MODE == NOISE_FULL) { Gm[0] = pc.dgR0; Gm[1] = pc.dgR1 + cc.dgL0; Gm[2] = cc.dgL1; }
     PK_UNROLL
     for (int c = 0; c < 3; ++c) {
       const double S = p.hb * B[c] + p.mb * Gm[c];
-      k.Cm[c] = S - 0.5 * Fm[c];
-      k.Cp[c] = S + 0.5 * Fm[c];
+      k.Cm[c] = S - Fq[c];
+      k.Cp[c] = S + Fq[c];
       k.C0[c] = p.ha * B[c] + p.ma * Gm[c];
     }
     const double hr = p.hb * Rpsi - p.mb * Rzeta;
@@ -364,6 +381,158 @@ struct Thread {
     nm = n0; n0 = np; pc = cc;
   }
 
+  // ================= FS variant: rolled row loops, factors in shared memory =================================
+  PK_HD int fidx(const Params& p, int c, int k) const { return (c * NI + k) * TN(p) + t; }
+  // solution increment of my row j: registers (du[]) or, FS, exchange slot j (free between the PCR and the update)
+  template <class SH>
+  PK_HD double get_du(const Params& p, const SH& sh, int j) const {
+    if (FS) return sh.ld(sh.xb, j * TN(p) + t);
+    return du[j < M ? j : M - 1];
+  }
+
+  // LU step of interior row k (runtime k).  With a zero history the generic recurrence reproduces the k = 0, 1
+  // special cases of elim(): there the sub-diagonal entries couple to the separators and seed the spike columns.
+  template <class SH>
+  PK_HD void elim_fs(const Params& p, const SH& sh, int k, double a, double b, double c, double ee, double ff, double rhs) {
+    const double l2 = a * h2[0];
+    const double bb = b - l2 * h2[1];
+    const double l1 = bb * h1[0];
+    const double d = c - l2 * h2[2] - l1 * h1[1];
+    ee = ee - l1 * h1[2];
+    const double z = rhs - l2 * h2[3] - l1 * h1[3];
+    double w1 = -l2 * h2[4] - l1 * h1[4];
+    double w2 = -l2 * h2[5] - l1 * h1[5];
+    if (k == 0) { w1 += a; w2 += b; }
+    if (k == 1) w2 += a;
+    const double rr = PK_RCP(d);
+    sh.st(sh.fac, fidx(p, 0, k), rr); sh.st(sh.fac, fidx(p, 1, k), ee); sh.st(sh.fac, fidx(p, 2, k), ff);
+    sh.st(sh.fac, fidx(p, 3, k), z); sh.st(sh.fac, fidx(p, 4, k), w1); sh.st(sh.fac, fidx(p, 5, k), w2);
+    PK_UNROLL
+    for (int q = 0; q < 6; ++q) h2[q] = h1[q];
+    h1[0] = rr; h1[1] = ee; h1[2] = ff; h1[3] = z; h1[4] = w1; h1[5] = w2;
+  }
+
+  template <class SH>
+  PK_HD void finish_row_fs(const Params& p, const SH& sh, int row, const double* cp, double qp) {
+    if (row == 0) {
+      sp0[2] += cp[0]; sp0[3] += cp[1]; sp0[4] += cp[2]; sb0 -= qp;
+      return;
+    }
+    const double a = p.hm2 + wCm2[0];
+    const double b = p.hm1 + wCm2[1] + wC01[0];
+    const double c = p.hm0 + wCm2[2] + wC01[1] + cp[0];
+    const double ee = p.hm1 + wC01[2] + cp[1];
+    const double ff = p.hm2 + cp[2];
+    const double rhs = -(wQm2 + wQ01 + qp);
+    if (row == 1) {
+      sp1[0] = a; sp1[1] = b; sp1[2] = c; sp1[3] = ee; sp1[4] = ff; sb1 = rhs;
+    } else if (FS) {
+      elim_fs(p, sh, row - 2, a, b, c, ee, ff, rhs);
+    } else {
+      // register-resident factors: the elimination step with static indices, picked by the (thread-uniform) row
+      switch (row - 2) {
+        case 0: elim(0, a, b, c, ee, ff, rhs); break;
+        case 1: if (NI > 1) elim(NI > 1 ? 1 : 0, a, b, c, ee, ff, rhs); break;
+        case 2: if (NI > 2) elim(NI > 2 ? 2 : 0, a, b, c, ee, ff, rhs); break;
+        case 3: if (NI > 3) elim(NI > 3 ? 3 : 0, a, b, c, ee, ff, rhs); break;
+        case 4: if (NI > 4) elim(NI > 4 ? 4 : 0, a, b, c, ee, ff, rhs); break;
+        default: if (NI > 5) elim(NI > 5 ? 5 : 0, a, b, c, ee, ff, rhs); break;
+      }
+    }
+  }
+
+  // streaming iteration q >= 2 (runtime q): cell (q-1, q); finalises node q-1 and row q-2
+  template <class SH>
+  PK_HD void stream_fs(const Params& p, const SH& sh, int q, bool lite) {
+    load_node(p, sh, q, np);
+    CellC<MODE> cc; cc.compute_res(p, n0, np);
+    if (!lite) cc.compute_jac(p, n0, np);
+    Packet k; node_packet(p, cc, k, lite);     // node q-1
+    if (lite) { nm = n0; n0 = np; pc.N1R = cc.N1R; pc.fR = cc.fR; pc.gR = cc.gR; return; }
+    finish_row_fs(p, sh, q - 2, k.Cp, k.Qp);
+    push_packet(k);
+    nm = n0; n0 = np; pc = cc;
+  }
+
+  // residual-only pass (no Jacobian, no factors): one rolled loop over the rows of the chunk
+  template <class SH>
+  PK_HD void residual_finish_rolled(const Params& p, const SH& sh) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int q = 2; q <= m; ++q) {
+      load_node(p, sh, q, np);
+      CellC<MODE> cc; cc.compute_res(p, n0, np);
+      Packet k; node_packet(p, cc, k, true);
+      nm = n0; n0 = np; pc.N1R = cc.N1R; pc.fR = cc.fR; pc.gR = cc.gR;
+    }
+  }
+
+  template <class SH>
+  PK_HD void assemble_finish_fs(const Params& p, const SH& sh, bool lite) {
+    if (lite) { residual_finish_rolled(p, sh); return; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int q = 2; q <= m; ++q) stream_fs(p, sh, q, false);
+    // last row (m-1): Cp,Qp come from the right neighbour's first node
+    double cp[3];
+    cp[0] = sh.ld(sh.xb, 14 * TN(p) + tr); cp[1] = sh.ld(sh.xb, 15 * TN(p) + tr); cp[2] = sh.ld(sh.xb, 16 * TN(p) + tr);
+    const double qp = sh.ld(sh.xb, 17 * TN(p) + tr);
+    finish_row_fs(p, sh, m - 1, cp, qp);
+    sh.st(sh.xb, 10 * TN(p) + t, wCm1[0]); sh.st(sh.xb, 11 * TN(p) + t, wCm1[1]); sh.st(sh.xb, 12 * TN(p) + t, wCm1[2]);
+    sh.st(sh.xb, 13 * TN(p) + t, wQm1);
+    if (!FS) { tips_registers(p, sh); return; }
+
+    // tips: back-substitute the five columns (y, W1, W2, V1, V2) through the interior rows
+    const int nI = m - 2;
+    double xp1[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
+    double xp2[5] = {0.0, 0.0, 0.0, 0.0, 1.0};
+    double L2a[5], L2b[5];
+    PK_UNROLL
+    for (int c = 0; c < 5; ++c) { L2a[c] = L2b[c] = 0.0; F2a[c] = F2b[c] = 0.0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = nI - 1; k >= 0; --k) {
+      const double rk = sh.ld(sh.fac, fidx(p, 0, k)), ek = sh.ld(sh.fac, fidx(p, 1, k)), fk = sh.ld(sh.fac, fidx(p, 2, k));
+      const double zc[5] = {sh.ld(sh.fac, fidx(p, 3, k)), -sh.ld(sh.fac, fidx(p, 4, k)), -sh.ld(sh.fac, fidx(p, 5, k)), 0.0, 0.0};
+      PK_UNROLL
+      for (int c = 0; c < 5; ++c) {
+        const double x = rk * (zc[c] - ek * xp1[c] - fk * xp2[c]);
+        xp2[c] = xp1[c]; xp1[c] = x;
+        if (k == nI - 1) L2b[c] = x;
+        if (k == nI - 2) L2a[c] = x;
+        if (k == 1) F2b[c] = x;
+        if (k == 0) F2a[c] = x;
+      }
+    }
+    sh.st(sh.xb, 0 * TN(p) + t, L2a[0]); sh.st(sh.xb, 1 * TN(p) + t, L2b[0]);
+    sh.st(sh.xb, 2 * TN(p) + t, L2a[1]); sh.st(sh.xb, 3 * TN(p) + t, L2a[2]);
+    sh.st(sh.xb, 4 * TN(p) + t, L2b[1]); sh.st(sh.xb, 5 * TN(p) + t, L2b[2]);
+    sh.st(sh.xb, 6 * TN(p) + t, L2a[3]); sh.st(sh.xb, 7 * TN(p) + t, L2a[4]);
+    sh.st(sh.xb, 8 * TN(p) + t, L2b[3]); sh.st(sh.xb, 9 * TN(p) + t, L2b[4]);
+  }
+
+  // interior solution with known separators; the increment of row j goes to exchange slot j
+  template <class SH>
+  PK_HD void interior_solve_fs(const Params& p, const SH& sh) {
+    const int T = TN(p);
+    const int nI = m - 2;
+    double xp1 = sh.ld(sh.xb, 14 * T + tr), xp2 = sh.ld(sh.xb, 15 * T + tr);
+    sh.st(sh.xb, 0 * T + t, xs0); sh.st(sh.xb, 1 * T + t, xs1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = nI - 1; k >= 0; --k) {
+      const double z = sh.ld(sh.fac, fidx(p, 3, k)) - sh.ld(sh.fac, fidx(p, 4, k)) * xs0 - sh.ld(sh.fac, fidx(p, 5, k)) * xs1;
+      const double x = sh.ld(sh.fac, fidx(p, 0, k)) * (z - sh.ld(sh.fac, fidx(p, 1, k)) * xp1 - sh.ld(sh.fac, fidx(p, 2, k)) * xp2);
+      xp2 = xp1; xp1 = x;
+      sh.st(sh.xb, (k + 2) * T + t, x);
+      if (k == nI - 1) sh.st(sh.xb, 16 * T + t, x);     // my last row, for the right neighbour
+    }
+  }
+
   // ---- phase A1: first two cells, publish first-node packet --------------------------------
   template <class SH>
   // lite: evaluate the residual norm only (no Jacobian, no elimination) -- the same code, so that the
@@ -397,6 +566,12 @@ struct Thread {
     sh.st(sh.xb, 10 * TN(p) + t, wCm1[0]); sh.st(sh.xb, 11 * TN(p) + t, wCm1[1]); sh.st(sh.xb, 12 * TN(p) + t, wCm1[2]);
     sh.st(sh.xb, 13 * TN(p) + t, wQm1);
 
+    tips_registers(p, sh);
+  }
+
+  // tips of the interior solution columns from the register-resident factors
+  template <class SH>
+  PK_HD void tips_registers(const Params& p, const SH& sh) {
     // back-substitute the five columns  x_I = y + Wn1 xs0 + Wn2 xs1 + Vn1 xR0 + Vn2 xR1
     // (a chunk has NI or NI-1 interior rows: the top row is skipped by short chunks, and the tips at the last
     // two interior rows are picked once at the end instead of per row and column)
@@ -544,15 +719,17 @@ struct Thread {
   template <class SH>
   PK_HD void helm_causal_local(const Params& p, const SH& sh, double& A, double& cF, double& cG) {
     // Right-hand sides  f(uh) + f'(uh) e  and  g(uh) + g'(uh) e  with e = du/2 (the change of uh).
-    // f is a homogeneous quadratic form in uh, g is linear in uh, hence exactly
-    //    f(uh) + f'(uh) e = f(uh + e) - f(e),        g(uh) + g'(uh) e = g(uh + e).
+    // f is a homogeneous quadratic form, f(a) = B(a, a) with B symmetric bilinear, and g is linear in uh, hence
+    //    f(uh) + f'(uh) e = B(uh, uh + 2e) = B(uh, uh + du),        g(uh) + g'(uh) e = g(uh + e),
+    // with  B_L(a, s) = c1 (a0 (3 s0 + s1) + a1 (s0 + s1)) + c2 (a1 - a0)(s1 - s0)  on a cell (B_R mirrored).
     const int T = TN(p);
-    double a0, x0 = 0.0, y0 = 0.0, e0;
+    double a0, s0, b0, x0 = 0.0, y0 = 0.0;
     {
       const int i = nidx(p, -1);
       a0 = 0.5 * (sh.ld(sh.U0, i) + sh.ld(sh.U1, i));
       if (MODE == NOISE_FULL) { x0 = sh.ld(sh.Xx, i); y0 = sh.ld(sh.Xxx, i); }
-      e0 = 0.5 * sh.ld(sh.xb, 16 * T + tl);           // half the increment of the left neighbour's last row
+      const double d0 = sh.ld(sh.xb, 16 * T + tl);          // increment of the left neighbour's last row
+      s0 = a0 + d0; b0 = a0 + 0.5 * d0;
     }
     double prevFR = 0.0, prevGR = 0.0;
     PK_UNROLL
@@ -564,24 +741,21 @@ struct Thread {
         const double a1 = 0.5 * (sh.ld(sh.U0, i) + sh.ld(sh.U1, i));
         double x1 = 0.0, y1 = 0.0;
         if (MODE == NOISE_FULL) { x1 = sh.ld(sh.Xx, i); y1 = sh.ld(sh.Xxx, i); }
-        const double e1 = 0.5 * ((q < m) ? du[q < M ? q : M - 1] : sh.ld(sh.xb, 14 * T + tr));
-        const double b0 = a0 + e0, b1 = a1 + e1;            // uh + e at the two nodes of the cell
-        const double db = b1 - b0, de = e1 - e0;
-        const double qb = b0 * b0 + b1 * b1, pb = b0 * b1, qe = e0 * e0 + e1 * e1, pe = e0 * e1;
-        // fL = c1 (3 b0^2 + 2 b0 b1 + b1^2) + c2 db^2 ;  fR = c1 (b0^2 + 2 b0 b1 + 3 b1^2) + c2 db^2
-        const double sb = p.c1 * (qb + 2.0 * pb) + p.c2 * db * db;
-        const double se = p.c1 * (qe + 2.0 * pe) + p.c2 * de * de;
-        const double fLv = (sb + 2.0 * p.c1 * b0 * b0) - (se + 2.0 * p.c1 * e0 * e0);
-        const double fRv = (sb + 2.0 * p.c1 * b1 * b1) - (se + 2.0 * p.c1 * e1 * e1);
+        const double d1 = (q < m) ? get_du(p, sh, q) : sh.ld(sh.xb, 14 * T + tr);
+        const double s1 = a1 + d1, b1 = a1 + 0.5 * d1;      // uh + du and uh + e at the right node of the cell
+        const double ss = s0 + s1;
+        const double cdd = p.c2 * (a1 - a0) * (s1 - s0);
+        const double fLv = p.c1 * (a0 * (2.0 * s0 + ss) + a1 * ss) + cdd;
+        const double fRv = p.c1 * (a0 * ss + a1 * (2.0 * s1 + ss)) + cdd;
         double gLv = 0.0, gRv = 0.0;
         if (MODE == NOISE_FULL) {
-          const double xs = x0 + x1;
+          const double xs = x0 + x1, db = b1 - b0;
           gLv = p.h6 * (b0 * (3.0 * x0 + x1) + b1 * xs) + p.a26 * db * (2.0 * y0 + y1);
           gRv = p.h6 * (b0 * xs + b1 * (x0 + 3.0 * x1)) + p.a26 * db * (y0 + 2.0 * y1);
         }
         if (q >= 1) { hF[q - 1] = (prevFR + fLv) * p.ikappa; hG[q - 1] = (prevGR + gLv) * p.ikappa; }
         prevFR = fRv; prevGR = gRv;
-        a0 = a1; x0 = x1; y0 = y1; e0 = e1;
+        a0 = a1; s0 = s1; b0 = b1; x0 = x1; y0 = y1;
       }
     }
     // causal recurrence with zero carry-in
@@ -633,11 +807,12 @@ struct Thread {
     for (int j = 0; j < M; ++j) {
       if (j < m) {
         const int i = idx(p, j);
-        const double u1n = sh.ld(sh.U1, i) + du[j];
+        const double duj = get_du(p, sh, j);
+        const double u1n = sh.ld(sh.U1, i) + duj;
         const double Fn = hF[j] + pwv[j] * inF;
         const double dFv = Fn - sh.ld(sh.F, i);
         sh.st(sh.U1, i, u1n); sh.st(sh.F, i, Fn);
-        double s2 = du[j] * du[j] + dFv * dFv, x2 = u1n * u1n + Fn * Fn;
+        double s2 = duj * duj + dFv * dFv, x2 = u1n * u1n + Fn * Fn;
         if (MODE == NOISE_FULL) {
           const double Gn = hG[j] + pwv[j] * inG;
           const double dGv = Gn - sh.ld(sh.G, i);
@@ -657,9 +832,10 @@ struct Thread {
     for (int j = 0; j < M; ++j) {
       if (j < m) {
         const int i = idx(p, j);
-        const double u1n = sh.ld(sh.U1, i) + du[j];
+        const double duj = get_du(p, sh, j);
+        const double u1n = sh.ld(sh.U1, i) + duj;
         sh.st(sh.U1, i, u1n);
-        sn2 += du[j] * du[j]; xn2 += u1n * u1n;
+        sn2 += duj * duj; xn2 += u1n * u1n;
       }
     }
   }
@@ -870,7 +1046,8 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
         // convergence is expected here: evaluate the residual only; fall through to the full
         // assembly (which recomputes it) in the rare case it is not
         ex.each([&](Th& th) { th.assemble_begin(p, sh, true); });
-        ex.each([&](Th& th) { th.assemble_finish(p, sh, true); });
+        if constexpr (Th::ROLL_LITE) ex.each([&](Th& th) { th.residual_finish_rolled(p, sh); });
+        else ex.each([&](Th& th) { th.assemble_finish(p, sh, true); });
         ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
         status = snes_test(p, it, nrm, fnorm0, reason);
         ex.tick(2);
@@ -879,7 +1056,8 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       ex.each([&](Th& th) { th.assemble_begin(p, sh, false); });
       ex.sync();
       ex.tick(3);
-      ex.each([&](Th& th) { th.assemble_finish(p, sh, false); });
+      if constexpr (Th::FS || Th::ROLL) ex.each([&](Th& th) { th.assemble_finish_fs(p, sh, false); });
+      else ex.each([&](Th& th) { th.assemble_finish(p, sh, false); });
       ex.tick(4);
       ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, nrm);
       status = snes_test(p, it, nrm, fnorm0, reason);
@@ -901,7 +1079,8 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       ex.each([&](Th& th) { th.pcr_final(p, sh); });
       ex.sync();
       ex.tick(8);
-      ex.each([&](Th& th) { th.interior_solve(p, sh); });
+      if constexpr (Th::FS) ex.each([&](Th& th) { th.interior_solve_fs(p, sh); });
+      else ex.each([&](Th& th) { th.interior_solve(p, sh); });
       ex.sync();
       ex.tick(9);
       if constexpr (PK_IS_TEST(MODE)) {

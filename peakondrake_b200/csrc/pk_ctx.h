@@ -16,6 +16,7 @@ struct pk_ctx {
   int block;
   int cluster;         // CTAs per realisation (1 = single-CTA kernel)
   int lgTc;
+  int fs;              // 1: FS variant of the single-CTA step kernel (factors in shared memory, rolled row loops)
   int slots;           // CTAs of the single-CTA step kernel resident at once (persistent grid), 0 = other kernel
   int sms;             // multiprocessors of the device
   int* d_queue;        // [1 + R] work counter + per-realisation finished-block counters

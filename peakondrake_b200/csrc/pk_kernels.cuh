@@ -132,14 +132,14 @@ struct GpuExecT {
   }
 };
 
-template <int M, int MODE, bool AA, int TT> using GpuExec = GpuExecT<Thread<M, MODE, TT>, AA, TT>;
+template <int M, int MODE, bool AA, int TT, int VAR = 0> using GpuExec = GpuExecT<Thread<M, MODE, TT, VAR>, AA, TT>;
 
 #include "pk_args.h"
 
 
 template <int MODE> struct NArr { enum { n = (MODE == NOISE_FULL) ? 7 : (MODE == NOISE_X ? 4 : 3) }; };
 
-template <int M, int MODE, int TB, int MINB, int TT>
+template <int M, int MODE, int TB, int MINB, int TT, int VAR = 0>
 __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int Tn = TT > 0 ? TT : p.T;
@@ -152,11 +152,12 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
   sh.xb = nxt; nxt += XB_SLOTS * Tn;
   double* red = nxt; nxt += 6 * (blockDim.x >> 5);
-  sh.dW = nxt;
+  sh.dW = nxt; nxt += (p.nxi > 0 ? p.nxi : 1);
+  sh.fac = (VAR == 1) ? nxt + ((nxt - smem) & 1) : nullptr;     // [6*(M-2)*T], 16-byte aligned like the rest
 
-  Thread<M, MODE, TT> th;
+  Thread<M, MODE, TT, VAR> th;
   th.init(p, threadIdx.x);
-  GpuExec<M, MODE, (TB > 32), TT> ex(th, red);
+  GpuExec<M, MODE, (TB > 32), TT, VAR> ex(th, red);
   ex.ne_ = p.ne;
 #ifdef PK_PROFILE
   __shared__ long long tb[16];
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
     __syncthreads();
     io.r = r; io.rid = a.rid0 + (unsigned)r;
     io.n0 = b * a.nblk; io.n1 = min(io.n0 + a.nblk, a.nsteps);
-    run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT>, Thread<M, MODE, TT> >(ex, p, sh, io);
+    run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT, VAR>, Thread<M, MODE, TT, VAR> >(ex, p, sh, io);
     __syncthreads();
     for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
       const int sl = row_slot_c<M, TT>(p, i);

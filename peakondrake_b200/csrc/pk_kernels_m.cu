@@ -25,7 +25,16 @@ template <int M> static ckern_t pick_cmode(int mode, int Tc) {
 
 template <int M, int MODE> static kern_t pick_tb(int block, int T, int minb) {
   if (T < 32) return pk_step_kernel<M, MODE, 32, 1, 0>;    // tiny meshes: some lanes of the single warp idle
-  if (T == 128) return pk_step_kernel<M, MODE, 128, 3, 128>;
+  if (T == 128) {
+#ifdef PK_EXPERIMENTAL_VARIANTS      // A/B builds only (profiles/exp_fs.py); see Thread<> in pk_core.h
+    if (minb == 2) return pk_step_kernel<M, MODE, 128, 2, 128, 1>;    // FS variant (2 CTAs/SM)
+    if (minb == 4) return pk_step_kernel<M, MODE, 128, 3, 128, 2>;    // rolled assembly, register factors
+    if (minb == 5) return pk_step_kernel<M, MODE, 128, 3, 128, 4>;    // residual-only pass unrolled as well
+#else
+    if (minb != 3) return nullptr;
+#endif
+    return pk_step_kernel<M, MODE, 128, 3, 128>;
+  }
   if (block <= 128) return pk_step_kernel<M, MODE, 128, 2, 0>;
   if (block <= 256) return (M <= 5) ? pk_step_kernel<M, MODE, 256, 2, 256> : pk_step_kernel<M, MODE, 256, 1, 256>;
   return pk_step_kernel<M, MODE, 512, 1, 512>;

@@ -302,12 +302,15 @@ int pk_fail(pk_ctx* c, const char* fmt, ...) {
   return -1;
 }
 
-static kern_t pick_kernel(const Params& p, int block) {
+static kern_t pick_kernel(const Params& p, int block, int fs) {
+  // fs = 1: FS variant (factors in shared memory, rolled row loops, 2 CTAs/SM); 2: rolled assembly with register
+  // factors; 0: fully unrolled register variant
+  const int v = fs == 1 ? 2 : (fs == 2 ? 4 : (fs == 4 ? 5 : 3));
   switch (p.M) {
-    case 5: return pk_pick_kernel_m5(p.mode, block, p.T, 3);
-    case 6: return pk_pick_kernel_m6(p.mode, block, p.T, 3);
-    case 7: return pk_pick_kernel_m7(p.mode, block, p.T, 3);
-    case 8: return pk_pick_kernel_m8(p.mode, block, p.T, 3);
+    case 5: return pk_pick_kernel_m5(p.mode, block, p.T, v);
+    case 6: return pk_pick_kernel_m6(p.mode, block, p.T, v);
+    case 7: return pk_pick_kernel_m7(p.mode, block, p.T, v);
+    case 8: return pk_pick_kernel_m8(p.mode, block, p.T, v);
   }
   return nullptr;
 }
@@ -379,6 +382,12 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->block = p.T < 32 ? 32 : p.T;
   c->cluster = 1; c->lgTc = 0;
   c->smem = sizeof(double) * ((size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1));
+  c->fs = 0;
+  { const char* e = getenv("PK_FS"); const int want = e ? atoi(e) : 0;
+    if (want && cfg->scheme != 1 && p.T == 128) {      // FS variant: + level-1 factors in shared memory
+      c->fs = (want == 1 || want == 2 || want == 4) ? want : 1;     // needs a -DPK_EXPERIMENTAL_VARIANTS build
+      if (c->fs == 1) c->smem += sizeof(double) * ((size_t)6 * (p.M - 2) * p.T + 1);
+    } }
   if (cfg->scheme == 1) {
     // upwind/ssprk3: state in registers, only exchange slots in shared memory (pk_upwind_lib.cu)
     c->smem = sizeof(double) * ((size_t)UW_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1) + 2);
@@ -408,7 +417,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->timed = false;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
-  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block) : (const void*)pick_kernel(p, c->block);
+  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block) : (const void*)pick_kernel(p, c->block, c->fs);
   if (!k) { delete c; return fail(nullptr, "pk_create: no kernel for this layout"); }
   if (c->cluster > 8) cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   e = cfg->scheme == 1 ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
@@ -524,7 +533,7 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
     c->last_nb = nb; c->last_nblk = nblk; c->last_grid = grid;
     CK(c, cudaMemsetAsync(c->d_queue, 0, sizeof(int) * (size_t)(R + 1), st));
     CK(c, cudaEventRecord(c->ev0, st));      // time the kernel alone
-    kern_t k = pick_kernel(c->p, c->block);
+    kern_t k = pick_kernel(c->p, c->block, c->fs);
     k<<<grid, c->block, c->smem, st>>>(c->p, a);
   }
   CK(c, cudaGetLastError());

@@ -44,6 +44,8 @@ struct Params {
   double hm0, hm1, hm2;   // H*M circulant, offsets 0, +-1, +-2
   double c1, c2;          // Dt*h/12, alphasq*Dt/(4h)
   double h6, a26;         // h/6, alphasq/6
+  double c1q, c1h, c2h, h12, a212, dt12;   // c1/4, c1/2, c2/2, h/12, alphasq/12, dt/12: the Jacobian enters the Newton
+                                           // matrix as N1'/2, f'/4 (+-), g'/2, assembled pre-scaled (exact binary scalings)
   double rho, ikappa;     // H = kappa (1 - rho S)(1 - rho S^-1): |rho|<1
   double rtol, atol, stol, divtol;  // PETSc SNES defaults 1e-8, 1e-50, 1e-8, 1e4
   double rtol2, atol2, stol2, divtol2;  // their squares (fill_constants): the tests compare squared norms
@@ -79,6 +81,7 @@ static inline void fill_constants(Params& p) {
   if (PK_IS_TEST(p.mode)) { p.hm0 = p.ma; p.hm1 = p.mb; p.hm2 = 0.0; }   // 'test': the Newton matrix is M - T'/2 (tridiagonal)
   p.c1 = p.dt * h / 12.0; p.c2 = a2 * p.dt / (4.0 * h);
   p.h6 = h / 6.0; p.a26 = a2 / 6.0;
+  p.c1q = 0.25 * p.c1; p.c1h = 0.5 * p.c1; p.c2h = 0.5 * p.c2; p.h12 = 0.5 * p.h6; p.a212 = 0.5 * p.a26; p.dt12 = p.dt * (1.0 / 12.0);
   const double disc = std::sqrt(p.ha * p.ha - 4.0 * p.hb * p.hb);
   const double kappa = 0.5 * (p.ha + disc);
   p.rho = -p.hb / kappa;

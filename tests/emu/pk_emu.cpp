@@ -123,15 +123,16 @@ static int run_one_cluster(const Params& p, StepIO io, double* u, double* u1, do
   return bad;
 }
 
-static int g_emu_nblk = 0;
-template <int M, int MODE>
-static void run_one(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
+static int g_emu_nblk = 0, g_emu_fs = 0;
+template <int M, int MODE, int FS>
+static void run_one_t(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
   const int n = p.T * p.M;
-  std::vector<double> buf(7 * n + XB_SLOTS * p.T + (p.nxi > 0 ? p.nxi : 1), 0.0);
+  std::vector<double> buf(7 * n + XB_SLOTS * p.T + (p.nxi > 0 ? p.nxi : 1) + 6 * (p.M - 2) * p.T, 0.0);
   Shared sh;
   sh.U0 = &buf[0]; sh.U1 = &buf[n]; sh.F = &buf[2 * n]; sh.G = &buf[3 * n];
   sh.X = &buf[4 * n]; sh.Xx = &buf[5 * n]; sh.Xxx = &buf[6 * n];
   sh.xb = &buf[7 * n]; sh.dW = &buf[7 * n + XB_SLOTS * p.T];
+  sh.fac = FS == 1 ? &buf[7 * n + XB_SLOTS * p.T + (p.nxi > 0 ? p.nxi : 1)] : nullptr;
   const long long off = (long long)io.r * p.ne;
   for (int i = 0; i < p.ne; ++i) {
     const int sl = row_slot(p, i);
@@ -140,11 +141,12 @@ static void run_one(const Params& p, StepIO io, double* u, double* u1, double* d
   }
   // g_emu_nblk > 0: advance in work items of g_emu_nblk steps, each with fresh per-thread state (what a
   // different persistent CTA sees when it pulls the next block of the realisation from the queue)
+  typedef Thread<M, MODE, 0, FS> Th;
   const int nblk = g_emu_nblk > 0 ? g_emu_nblk : io.nsteps;
   for (int b0 = 0; b0 < io.nsteps || b0 == 0; b0 += nblk) {
-    EmuExec<M, MODE> ex(p, order);
+    EmuExecT<Th> ex(p, order);
     io.n0 = b0; io.n1 = b0 + nblk < io.nsteps ? b0 + nblk : io.nsteps;
-    run_steps<M, MODE, 0, EmuExec<M, MODE>, Thread<M, MODE> >(ex, p, sh, io);
+    run_steps<M, MODE, 0, EmuExecT<Th>, Th>(ex, p, sh, io);
     if (nblk <= 0) break;
   }
   for (int i = 0; i < p.ne; ++i) {
@@ -152,6 +154,13 @@ static void run_one(const Params& p, StepIO io, double* u, double* u1, double* d
     u[off + i] = sh.U0[sl]; u1[off + i] = sh.U1[sl]; dF[off + i] = sh.F[sl];
     if (MODE == NOISE_FULL) dG[off + i] = sh.G[sl];
   }
+}
+template <int M, int MODE>
+static void run_one(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order) {
+  if (g_emu_fs == 1) run_one_t<M, MODE, 1>(p, io, u, u1, dF, dG, order);
+  else if (g_emu_fs == 2) run_one_t<M, MODE, 2>(p, io, u, u1, dF, dG, order);
+  else if (g_emu_fs == 4) run_one_t<M, MODE, 4>(p, io, u, u1, dF, dG, order);
+  else run_one_t<M, MODE, 0>(p, io, u, u1, dF, dG, order);
 }
 
 static int g_emuC = 1, g_bad = 0;
@@ -176,6 +185,10 @@ static void run_mode(const Params& p, StepIO io, double* u, double* u1, double* 
 // emulate a thread-block cluster of C CTAs per realisation (1 = off); returns the number of
 // non-local stores seen so far (must stay 0)
 extern "C" int pk_emu_set_cluster(int C) { g_emuC = C; return g_bad; }
+
+// per-thread code variant (Thread<..., VAR>): 0 default, 1 FS (factors in shared memory, rolled row loops),
+// 2 rolled assembly with register-resident factors, 4 everything unrolled
+extern "C" int pk_emu_set_fs(int on) { g_emu_fs = on; return 0; }
 
 // advance in step blocks of nblk steps (0 = whole launch at once), see run_one
 extern "C" int pk_emu_set_block(int nblk) { g_emu_nblk = nblk; return 0; }

@@ -196,3 +196,21 @@ def test_test_scheme(ne, fam, nxi, sigma):
     assert r['fail_step'][0] == -1 and r['its_total'][0] == ref['its'].sum()
     assert rel(u[0], ref['u']) <= TOL and rel(u1[0], ref['w1'][:ne]) <= TOL
     assert not dF.any() and not dG.any()
+
+
+@pytest.mark.parametrize('var', [1, 2, 4])
+def test_code_variants_are_bit_identical(var):
+    """Thread<..., VAR> (pk_core.h): factors in shared memory with rolled loops (1), rolled assembly with register
+    factors behind a switch (2), everything unrolled (4) -- same arithmetic in the same order as the default."""
+    out = []
+    for v in (0, var):
+        lib().pk_emu_set_fs(v)
+        try:
+            res = [compare(ne, nsteps=4, nxi=3, seed=5) for ne in (20, 37, 200, 1000)]
+            res.append(compare(300, scheme='no_gradient', nxi=2))
+            res.append(compare(400, fam='constant', nxi=1, ic='periodic_peakon', sigma=1.0))
+        finally:
+            lib().pk_emu_set_fs(0)
+        out.append(res)
+    for a, b in zip(out[0], out[1]):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
