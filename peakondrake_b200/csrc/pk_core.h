@@ -251,11 +251,14 @@ struct Thread {
     pc.dgL0 = pc.dgL1 = pc.dgR0 = pc.dgR1 = 0.0;
   }
 
+  // row j of my chunk exists: rows 0..M-2 always do (compile-time true), row M-1 only in full chunks
+  PK_HD bool has_row(int j) const { return j < M - 1 || ext; }
+
   // ---- smem index helpers -------------------------------------------------------------
   PK_HD int idx(const Params& p, int j) const { return j * TN(p) + t; }
   // node with local index j in [-1, m]: own rows, last row of the left chunk, first row of the right chunk
   PK_HD int nidx(const Params& p, int j) const {
-    return j < 0 ? (ml - 1) * TN(p) + tl : (j < m ? j * TN(p) + t : tr);
+    return j < 0 ? (ml - 1) * TN(p) + tl : ((j < M - 1 || (j == M - 1 && ext)) ? j * TN(p) + t : tr);
   }
 
   template <class SH>
@@ -697,12 +700,11 @@ struct Thread {
   template <class SH>
   PK_HD void interior_solve(const Params& p, const SH& sh) {
     const int T = TN(p);
-    const int nI = m - 2;
     double xp1 = sh.ld(sh.xb, 14 * T + tr), xp2 = sh.ld(sh.xb, 15 * T + tr);
     du[0] = xs0; du[1] = xs1;
     PK_UNROLL
     for (int k = NI - 1; k >= 0; --k) {
-      if (k < nI) {
+      if (k < NI - 1 || ext) {
         const double z = zb[k] - zw1[k] * xs0 - zw2[k] * xs1;
         const double x = r[k] * (z - e[k] * xp1 - f[k] * xp2);
         xp2 = xp1; xp1 = x;
@@ -736,62 +738,52 @@ struct Thread {
     for (int j = 0; j < M; ++j) { hF[j] = 0.0; hG[j] = 0.0; }
     PK_UNROLL
     for (int q = 0; q <= M; ++q) {
-      if (q <= m) {
+      if (q < M || ext) {
         const int i = nidx(p, q);
         const double a1 = 0.5 * (sh.ld(sh.U0, i) + sh.ld(sh.U1, i));
         double x1 = 0.0, y1 = 0.0;
         if (MODE == NOISE_FULL) { x1 = sh.ld(sh.Xx, i); y1 = sh.ld(sh.Xxx, i); }
-        const double d1 = (q < m) ? get_du(p, sh, q) : sh.ld(sh.xb, 14 * T + tr);
+        const double d1 = (q < M - 1 || (q == M - 1 && ext)) ? get_du(p, sh, q) : sh.ld(sh.xb, 14 * T + tr);
         const double s1 = a1 + d1, b1 = a1 + 0.5 * d1;      // uh + du and uh + e at the right node of the cell
         const double ss = s0 + s1;
-        const double cdd = p.c2 * (a1 - a0) * (s1 - s0);
-        const double fLv = p.c1 * (a0 * (2.0 * s0 + ss) + a1 * ss) + cdd;
-        const double fRv = p.c1 * (a0 * ss + a1 * (2.0 * s1 + ss)) + cdd;
+        const double cdd = p.c2k * (a1 - a0) * (s1 - s0);        // (constants carry the 1/kappa of the filter)
+        const double fLv = p.c1k * (a0 * (2.0 * s0 + ss) + a1 * ss) + cdd;
+        const double fRv = p.c1k * (a0 * ss + a1 * (2.0 * s1 + ss)) + cdd;
         double gLv = 0.0, gRv = 0.0;
         if (MODE == NOISE_FULL) {
           const double xs = x0 + x1, db = b1 - b0;
-          gLv = p.h6 * (b0 * (3.0 * x0 + x1) + b1 * xs) + p.a26 * db * (2.0 * y0 + y1);
-          gRv = p.h6 * (b0 * xs + b1 * (x0 + 3.0 * x1)) + p.a26 * db * (y0 + 2.0 * y1);
+          gLv = p.h6k * (b0 * (3.0 * x0 + x1) + b1 * xs) + p.a26k * db * (2.0 * y0 + y1);
+          gRv = p.h6k * (b0 * xs + b1 * (x0 + 3.0 * x1)) + p.a26k * db * (y0 + 2.0 * y1);
         }
-        if (q >= 1) { hF[q - 1] = (prevFR + fLv) * p.ikappa; hG[q - 1] = (prevGR + gLv) * p.ikappa; }
+        if (q >= 1) { hF[q - 1] = prevFR + fLv; hG[q - 1] = prevGR + gLv; }
         prevFR = fRv; prevGR = gRv;
         a0 = a1; s0 = s1; b0 = b1; x0 = x1; y0 = y1;
       }
     }
     // causal recurrence with zero carry-in
-    double yF = 0.0, yG = 0.0, pw = 1.0;
+    double yF = 0.0, yG = 0.0;
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
-      if (j < m) {
+      if (has_row(j)) {
         yF = hF[j] + p.rho * yF; hF[j] = yF;
         if (MODE == NOISE_FULL) { yG = hG[j] + p.rho * yG; hG[j] = yG; }
-        pw *= p.rho;
       }
     }
-    A = pw; cF = yF; cG = yG;
+    A = ext ? p.rpow[M] : p.rpow[M - 1]; cF = yF; cG = yG;
   }
 
   // ---- phase D2: apply causal carry, anticausal local pass -----------------------------------
   PK_HD void helm_anticausal_local(const Params& p, double inF, double inG, double& A, double& cF, double& cG) {
-    double pw = p.rho;
-    PK_UNROLL
-    for (int j = 0; j < M; ++j) {
-      if (j < m) {
-        hF[j] += pw * inF;
-        if (MODE == NOISE_FULL) hG[j] += pw * inG;
-        pw *= p.rho;
-      }
-    }
-    double xF = 0.0, xG = 0.0; pw = 1.0;
+    // carry-in of the causal filter: y_j += rho^(j+1) * in, then the anticausal recurrence with zero carry-in
+    double xF = 0.0, xG = 0.0;
     PK_UNROLL
     for (int j = M - 1; j >= 0; --j) {
-      if (j < m) {
-        xF = hF[j] + p.rho * xF; hF[j] = xF;
-        if (MODE == NOISE_FULL) { xG = hG[j] + p.rho * xG; hG[j] = xG; }
-        pw *= p.rho;
+      if (has_row(j)) {
+        xF = (hF[j] + p.rpow[j + 1] * inF) + p.rho * xF; hF[j] = xF;
+        if (MODE == NOISE_FULL) { xG = (hG[j] + p.rpow[j + 1] * inG) + p.rho * xG; hG[j] = xG; }
       }
     }
-    A = pw; cF = xF; cG = xG;
+    A = ext ? p.rpow[M] : p.rpow[M - 1]; cF = xF; cG = xG;
   }
 
   // ---- phase D3: apply anticausal carry, write the new iterate, accumulate |delta|^2, |w1|^2 ---
@@ -799,13 +791,14 @@ struct Thread {
   PK_HD void helm_finish_update(const Params& p, const SH& sh, double inF, double inG) {
     sn2 = 0.0; xn2 = 0.0;
     // x_j = xl_j + rho^(m-j) * carry
+    // weights rho^(m-j): for short chunks (m = M-1) fold the missing factor rho into the carry
+    if (!ext) { inF *= p.irho; inG *= p.irho; }
     double pwv[M];
-    double pw = ext ? p.rho : 1.0;        // short chunks: row M-1 does not exist, row M-2 is the last one
     PK_UNROLL
-    for (int j = M - 1; j >= 0; --j) { pwv[j] = pw; pw *= p.rho; }
+    for (int j = 0; j < M; ++j) pwv[j] = p.rpow[M - j];
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
-      if (j < m) {
+      if (has_row(j)) {
         const int i = idx(p, j);
         const double duj = get_du(p, sh, j);
         const double u1n = sh.ld(sh.U1, i) + duj;
@@ -830,7 +823,7 @@ struct Thread {
     sn2 = 0.0; xn2 = 0.0;
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
-      if (j < m) {
+      if (has_row(j)) {
         const int i = idx(p, j);
         const double duj = get_du(p, sh, j);
         const double u1n = sh.ld(sh.U1, i) + duj;
@@ -845,7 +838,7 @@ struct Thread {
   PK_HD void accept(const Params& p, const SH& sh) {
     PK_UNROLL
     for (int j = 0; j < M; ++j)
-      if (j < m) { const int i = idx(p, j); sh.st(sh.U0, i, sh.ld(sh.U1, i)); }
+      if (has_row(j)) { const int i = idx(p, j); sh.st(sh.U0, i, sh.ld(sh.U1, i)); }
   }
 
   // ---- noise fields of this step: dXi = sum_k dW_k xi_k etc. (stochastic_functions.py:229-234) ----
@@ -873,7 +866,7 @@ struct Thread {
     }
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
-      if (j < m) {
+      if (has_row(j)) {
         sh.st(sh.X, j * T + t, X[j]);
         if (MODE == NOISE_FULL) { sh.st(sh.Xx, j * T + t, Xx[j]); sh.st(sh.Xxx, j * T + t, Xxx[j]); }
       }

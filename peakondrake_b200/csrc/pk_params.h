@@ -47,6 +47,9 @@ struct Params {
   double c1q, c1h, c2h, h12, a212, dt12;   // c1/4, c1/2, c2/2, h/12, alphasq/12, dt/12: the Jacobian enters the Newton
                                            // matrix as N1'/2, f'/4 (+-), g'/2, assembled pre-scaled (exact binary scalings)
   double rho, ikappa;     // H = kappa (1 - rho S)(1 - rho S^-1): |rho|<1
+  double rpow[10];        // rho^0 .. rho^9 (chunk-local carry weights; a chunk has at most 8 rows)
+  double irho;            // 1 / rho
+  double c1k, c2k, h6k, a26k;   // c1, c2, h6, a26 times ikappa (Helmholtz right-hand sides pre-divided by kappa)
   double rtol, atol, stol, divtol;  // PETSc SNES defaults 1e-8, 1e-50, 1e-8, 1e4
   double rtol2, atol2, stol2, divtol2;  // their squares (fill_constants): the tests compare squared norms
   double sdt;             // sqrt(dt / nupd)
@@ -86,6 +89,10 @@ static inline void fill_constants(Params& p) {
   const double kappa = 0.5 * (p.ha + disc);
   p.rho = -p.hb / kappa;
   p.ikappa = 1.0 / kappa;
+  p.rpow[0] = 1.0;
+  for (int i = 1; i < 10; ++i) p.rpow[i] = p.rpow[i - 1] * p.rho;
+  p.irho = 1.0 / p.rho;
+  p.c1k = p.c1 * p.ikappa; p.c2k = p.c2 * p.ikappa; p.h6k = p.h6 * p.ikappa; p.a26k = p.a26 * p.ikappa;
   p.sdt = std::sqrt(p.dt / (p.nupd > 0 ? p.nupd : 1));
   p.rtol2 = p.rtol * p.rtol; p.atol2 = p.atol * p.atol; p.stol2 = p.stol * p.stol; p.divtol2 = p.divtol * p.divtol;
 }
