@@ -696,6 +696,131 @@ struct Thread {
     sh.st(sh.xb, 14 * T + t, xs0); sh.st(sh.xb, 15 * T + t, xs1);
   }
 
+  // =========== hybrid Schur solve: cyclic reduction down to 32 block rows, PCR inside ONE warp, back-substitution ===========
+  // Plain PCR keeps all T threads busy for log2(T) steps (O(T log T) work).  Here the rows are halved by cyclic
+  // reduction with the work COMPACTED onto the leading threads (row 2 s k of level s is handled by thread k, so
+  // whole warps drop out), the remaining 32 rows are solved by warp 0 with warp-level synchronisation only, and
+  // the eliminated rows are recovered level by level.  Rows live in the exchange slots: L 0-3, U 4-7, D^-1 8-11,
+  // r 12-13, D 14-17; the solution goes to slots 14-15 (D is dead by then).
+  template <class SH>
+  PK_HD void hyb_publish(const Params& p, const SH& sh) {
+    const int T = TN(p);
+    double Di[4]; inv2(Db, Di);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) {
+      sh.st(sh.xb, c * T + t, Lb[c]); sh.st(sh.xb, (4 + c) * T + t, Ub[c]); sh.st(sh.xb, (8 + c) * T + t, Di[c]);
+      sh.st(sh.xb, (14 + c) * T + t, Db[c]);
+    }
+    sh.st(sh.xb, 12 * T + t, rb[0]); sh.st(sh.xb, 13 * T + t, rb[1]);
+  }
+  // one elimination: row i absorbs its neighbours il, ir (rows given as smem indices); result in L_, D_, U_, r_
+  template <class SH>
+  PK_HD void hyb_absorb(const Params& p, const SH& sh, int il, int ir, double* L_, double* D_, double* U_, double* r_) const {
+    const int T = TN(p);
+    double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) {
+      Ll[c] = sh.ld(sh.xb, c * T + il); Ul[c] = sh.ld(sh.xb, (4 + c) * T + il); Dl[c] = sh.ld(sh.xb, (8 + c) * T + il);
+      Lr[c] = sh.ld(sh.xb, c * T + ir); Ur[c] = sh.ld(sh.xb, (4 + c) * T + ir); Dr[c] = sh.ld(sh.xb, (8 + c) * T + ir);
+    }
+    rl[0] = sh.ld(sh.xb, 12 * T + il); rl[1] = sh.ld(sh.xb, 13 * T + il);
+    rr[0] = sh.ld(sh.xb, 12 * T + ir); rr[1] = sh.ld(sh.xb, 13 * T + ir);
+    double al[4], ga[4], Ln[4], Un[4];
+    mm2(L_, Dl, al); mm2(U_, Dr, ga);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { al[c] = -al[c]; ga[c] = -ga[c]; }
+    mm2(al, Ll, Ln);
+    mm2(ga, Ur, Un);
+    mma2(al, Ul, D_); mma2(ga, Lr, D_);
+    mva2(al, rl, r_); mva2(ga, rr, r_);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { L_[c] = Ln[c]; U_[c] = Un[c]; }
+  }
+  // cyclic-reduction level with stride s: thread k (called for k < T/(2s)) rewrites row 2 s k in place
+  template <class SH>
+  PK_HD void hyb_down(const Params& p, const SH& sh, int s_) {
+    const int T = TN(p);
+    const int i = 2 * s_ * t, il = (i - s_) & (T - 1), ir = (i + s_) & (T - 1);
+    double L_[4], D_[4], U_[4], r_[2];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { L_[c] = sh.ld(sh.xb, c * T + i); U_[c] = sh.ld(sh.xb, (4 + c) * T + i); D_[c] = sh.ld(sh.xb, (14 + c) * T + i); }
+    r_[0] = sh.ld(sh.xb, 12 * T + i); r_[1] = sh.ld(sh.xb, 13 * T + i);
+    hyb_absorb(p, sh, il, ir, L_, D_, U_, r_);
+    double Di[4]; inv2(D_, Di);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) {
+      sh.st(sh.xb, c * T + i, L_[c]); sh.st(sh.xb, (4 + c) * T + i, U_[c]); sh.st(sh.xb, (8 + c) * T + i, Di[c]);
+      sh.st(sh.xb, (14 + c) * T + i, D_[c]);
+    }
+    sh.st(sh.xb, 12 * T + i, r_[0]); sh.st(sh.xb, 13 * T + i, r_[1]);
+  }
+  // warp 0, lane t: the 32 remaining rows S*t.  step 0: load my row; odd steps 2j+1: PCR step with distance 2^j
+  // (reads), even steps 2j+2: publish (writes); last step: closed 2-block solve with the row 16 lanes away.
+  template <class SH>
+  PK_HD void hyb_warp_step(const Params& p, const SH& sh, int S_, int step) {
+    const int T = TN(p);
+    const int i = S_ * t;
+    if (step == 0) {
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) { Lb[c] = sh.ld(sh.xb, c * T + i); Ub[c] = sh.ld(sh.xb, (4 + c) * T + i); Db[c] = sh.ld(sh.xb, (14 + c) * T + i); }
+      rb[0] = sh.ld(sh.xb, 12 * T + i); rb[1] = sh.ld(sh.xb, 13 * T + i);
+      return;
+    }
+    if (step == 9) {
+      const int q = S_ * ((t + 16) & 31);
+      double Lq[4], Uq[4], Dq[4], rq[2];
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) {
+        Lq[c] = sh.ld(sh.xb, c * T + q); Uq[c] = sh.ld(sh.xb, (4 + c) * T + q); Dq[c] = sh.ld(sh.xb, (8 + c) * T + q);
+      }
+      rq[0] = sh.ld(sh.xb, 12 * T + q); rq[1] = sh.ld(sh.xb, 13 * T + q);
+      double Sm[4], Sq[4], SD[4], A[4], Ai[4], rhs[2];
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) { Sm[c] = Lb[c] + Ub[c]; Sq[c] = Lq[c] + Uq[c]; A[c] = Db[c]; }
+      mm2(Sm, Dq, SD);
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) SD[c] = -SD[c];
+      mma2(SD, Sq, A);
+      rhs[0] = rb[0]; rhs[1] = rb[1];
+      mva2(SD, rq, rhs);
+      inv2(A, Ai);
+      sh.st(sh.xb, 14 * T + i, Ai[0] * rhs[0] + Ai[1] * rhs[1]);
+      sh.st(sh.xb, 15 * T + i, Ai[2] * rhs[0] + Ai[3] * rhs[1]);
+      return;
+    }
+    if (step & 1) {
+      const int d = 1 << ((step - 1) >> 1);
+      hyb_absorb(p, sh, S_ * ((t - d) & 31), S_ * ((t + d) & 31), Lb, Db, Ub, rb);
+    } else {
+      double Di[4]; inv2(Db, Di);
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) {
+        sh.st(sh.xb, c * T + i, Lb[c]); sh.st(sh.xb, (4 + c) * T + i, Ub[c]); sh.st(sh.xb, (8 + c) * T + i, Di[c]);
+      }
+      sh.st(sh.xb, 12 * T + i, rb[0]); sh.st(sh.xb, 13 * T + i, rb[1]);
+    }
+  }
+  // back-substitution level with stride s: thread k (k < T/(2s)) recovers row 2 s k + s from its two neighbours
+  template <class SH>
+  PK_HD void hyb_up(const Params& p, const SH& sh, int s_) {
+    const int T = TN(p);
+    const int i = 2 * s_ * t + s_, il = i - s_, ir = (i + s_) & (T - 1);
+    double L_[4], U_[4], Di[4];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { L_[c] = sh.ld(sh.xb, c * T + i); U_[c] = sh.ld(sh.xb, (4 + c) * T + i); Di[c] = sh.ld(sh.xb, (8 + c) * T + i); }
+    const double xl[2] = {sh.ld(sh.xb, 14 * T + il), sh.ld(sh.xb, 15 * T + il)};
+    const double xr[2] = {sh.ld(sh.xb, 14 * T + ir), sh.ld(sh.xb, 15 * T + ir)};
+    double v[2] = {sh.ld(sh.xb, 12 * T + i), sh.ld(sh.xb, 13 * T + i)};
+    v[0] -= L_[0] * xl[0] + L_[1] * xl[1] + U_[0] * xr[0] + U_[1] * xr[1];
+    v[1] -= L_[2] * xl[0] + L_[3] * xl[1] + U_[2] * xr[0] + U_[3] * xr[1];
+    sh.st(sh.xb, 14 * T + i, Di[0] * v[0] + Di[1] * v[1]);
+    sh.st(sh.xb, 15 * T + i, Di[2] * v[0] + Di[3] * v[1]);
+  }
+  template <class SH>
+  PK_HD void hyb_load_xs(const Params& p, const SH& sh) {
+    xs0 = sh.ld(sh.xb, 14 * TN(p) + t); xs1 = sh.ld(sh.xb, 15 * TN(p) + t);
+  }
+
   // ---- phase C: interior solution with known separators --------------------------------------
   template <class SH>
   PK_HD void interior_solve(const Params& p, const SH& sh) {
@@ -965,6 +1090,9 @@ PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int 
 //                      realisation: block-local thread id / count, whether the block is the cluster
 //                      leader, and the range of mesh rows the block owns
 //   one(f)             run f() once (thread 0)
+//   hybrid(T)          true if the executor supports the compacted Schur solve for T threads per realisation:
+//   each_first(n, f)     run f on the threads t < n only (the others fall through to the next barrier)
+//   warp0_steps(n, f)    threads t < 32: for step = 0..n-1 { f(th, step); warp-level barrier }
 // ------------------------------------------------------------------------------------------------
 struct StepIO {
   const double* dW_in;    // [nsteps, R, nxi] or null -> Philox
@@ -1059,19 +1187,41 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       // ---- linear solve + update ----
       ex.each([&](Th& th) { th.reduce_build(p, sh); });
       ex.sync();
-      ex.each([&](Th& th) { th.reduce_publish(p, sh); });
-      ex.sync();
-      ex.tick(6);
-      for (int d = 1; d < (TT > 0 ? TT : p.T) / 2; d *= 2) {
-        ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
+      const int Tn = (TT > 0 ? TT : p.T);
+      if (ex.hybrid(Tn)) {
+        // cyclic reduction (compacted onto the leading threads) -> 32 rows -> PCR inside warp 0 -> back-substitution
+        ex.each([&](Th& th) { th.hyb_publish(p, sh); });
         ex.sync();
+        ex.tick(6);
+        int S = 1;
+        for (; Tn / (2 * S) >= 32; S *= 2) {
+          ex.each_first(Tn / (2 * S), [&](Th& th) { th.hyb_down(p, sh, S); });
+          ex.sync();
+        }
+        ex.warp0_steps(10, [&](Th& th, int step) { th.hyb_warp_step(p, sh, S, step); });
+        ex.sync();
+        ex.tick(7);
+        for (int s2 = S / 2; s2 >= 1; s2 /= 2) {
+          ex.each_first(Tn / (2 * s2), [&](Th& th) { th.hyb_up(p, sh, s2); });
+          ex.sync();
+        }
+        ex.each([&](Th& th) { th.hyb_load_xs(p, sh); });
+        ex.tick(8);
+      } else {
         ex.each([&](Th& th) { th.reduce_publish(p, sh); });
         ex.sync();
+        ex.tick(6);
+        for (int d = 1; d < Tn / 2; d *= 2) {
+          ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
+          ex.sync();
+          ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+          ex.sync();
+        }
+        ex.tick(7);
+        ex.each([&](Th& th) { th.pcr_final(p, sh); });
+        ex.sync();
+        ex.tick(8);
       }
-      ex.tick(7);
-      ex.each([&](Th& th) { th.pcr_final(p, sh); });
-      ex.sync();
-      ex.tick(8);
       if constexpr (Th::FS) ex.each([&](Th& th) { th.interior_solve_fs(p, sh); });
       else ex.each([&](Th& th) { th.interior_solve(p, sh); });
       ex.sync();

@@ -39,6 +39,20 @@ struct GpuExecT {
   __device__ __forceinline__ void tick(int) {}
 #endif
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
+  // compacted Schur solve (pk_core.h, hyb_*): needs >= 32 threads per realisation, all of one block.  Measured
+  // 12 % SLOWER than plain PCR on B200 (the serial single-warp phases stall the whole CTA; profiles/r1d_exp_variants.log),
+  // so it is only compiled into -DPK_HYBRID_SCHUR experiment builds.
+#ifdef PK_HYBRID_SCHUR
+  __device__ __forceinline__ bool hybrid(int T) const { return AA && T >= 32; }
+#else
+  __device__ __forceinline__ bool hybrid(int) const { return false; }
+#endif
+  template <class F> __device__ __forceinline__ void each_first(int n, F f) { if ((int)threadIdx.x < n) f(th); }
+  template <class F> __device__ __forceinline__ void warp0_steps(int n, F f) {
+    if (threadIdx.x < 32) {
+      for (int s = 0; s < n; ++s) { f(th, s); __syncwarp(); }
+    }
+  }
   __device__ __forceinline__ double* area() {
     const int nw = nwarps();
     double* a = red + flip * 3 * nw;
@@ -259,6 +273,9 @@ struct GpuExecCluster {
   __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
   __device__ __forceinline__ void tick(int) {}
   template <class F> __device__ __forceinline__ void one(F f) { if (rank == 0 && threadIdx.x == 0) f(); }
+  __device__ __forceinline__ bool hybrid(int) const { return false; }     // rows are spread over the CTAs of the cluster
+  template <class F> __device__ __forceinline__ void each_first(int, F) {}
+  template <class F> __device__ __forceinline__ void warp0_steps(int, F) {}
   __device__ __forceinline__ double* area() {
     const int nw = blockDim.x >> 5;
     double* a = red + flip * (3 * nw + 3);

@@ -15,6 +15,7 @@
 
 using namespace pk;
 
+static int g_emu_hybrid = 0;      // 1: compacted Schur solve (hyb_* in pk_core.h) where T >= 32; 0: plain PCR
 template <class ThT> struct EmuExecT;
 template <int M, int MODE> using EmuExec = EmuExecT<Thread<M, MODE> >;
 
@@ -63,6 +64,14 @@ struct EmuExecT {
   void sync() {}
   void tick(int) {}
   template <class F> void one(F f) { f(); }
+  bool hybrid(int Tn) const { return g_emu_hybrid && C == 1 && Tn >= 32; }
+  template <class F> void each_first(int n, F f) {
+    for (int k = 0; k < n; ++k) { const int t = order == 0 ? k : n - 1 - k; cur = t / Tc; f(th[t]); }
+  }
+  template <class F> void warp0_steps(int n, F f) {
+    for (int s = 0; s < n; ++s)
+      for (int k = 0; k < 32; ++k) { const int t = order == 0 ? k : 31 - k; f(th[t], s); }
+  }
   template <class F> void allreduce3(F f, double* out) {
     out[0] = out[1] = out[2] = 0.0;
     for (int t = 0; t < T; ++t) { double v[3]; f(th[t], v); out[0] += v[0]; out[1] += v[1]; out[2] += v[2]; }
@@ -189,6 +198,8 @@ extern "C" int pk_emu_set_cluster(int C) { g_emuC = C; return g_bad; }
 // per-thread code variant (Thread<..., VAR>): 0 default, 1 FS (factors in shared memory, rolled row loops),
 // 2 rolled assembly with register-resident factors, 4 everything unrolled
 extern "C" int pk_emu_set_fs(int on) { g_emu_fs = on; return 0; }
+
+extern "C" int pk_emu_set_hybrid(int on) { g_emu_hybrid = on; return 0; }
 
 // advance in step blocks of nblk steps (0 = whole launch at once), see run_one
 extern "C" int pk_emu_set_block(int nblk) { g_emu_nblk = nblk; return 0; }

@@ -214,3 +214,16 @@ def test_code_variants_are_bit_identical(var):
         out.append(res)
     for a, b in zip(out[0], out[1]):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_hybrid_schur_solve_variant():
+    """Cyclic reduction compacted onto the leading threads + PCR inside one warp + back-substitution (hyb_* in
+    pk_core.h; an experiment build option, slower than plain PCR on B200): same answers to rounding."""
+    lib().pk_emu_set_hybrid(1)
+    try:
+        for ne in (200, 256, 500, 1000, 1500, 4000):
+            a = compare(ne, nsteps=3, nxi=2, order=0)
+            b = compare(ne, nsteps=3, nxi=2, order=1)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    finally:
+        lib().pk_emu_set_hybrid(0)
