@@ -30,6 +30,8 @@ template <int M, int MODE> static kern_t pick_tb(int block, int T, int minb) {
     if (minb == 2) return pk_step_kernel<M, MODE, 128, 2, 128, 1>;    // FS variant (2 CTAs/SM)
     if (minb == 4) return pk_step_kernel<M, MODE, 128, 3, 128, 2>;    // rolled assembly, register factors
     if (minb == 5) return pk_step_kernel<M, MODE, 128, 3, 128, 4>;    // residual-only pass unrolled as well
+    if (minb == 6) return pk_step_kernel<M, MODE, 128, 2, 128, 0>;    // default code, 2 CTAs/SM (up to 255 registers)
+    if (minb == 7) return pk_step_kernel<M, MODE, 128, 4, 128, 0>;    // default code, 4 CTAs/SM (128 registers)
 #else
     if (minb != 3) return nullptr;
 #endif

@@ -305,7 +305,7 @@ int pk_fail(pk_ctx* c, const char* fmt, ...) {
 static kern_t pick_kernel(const Params& p, int block, int fs) {
   // fs = 1: FS variant (factors in shared memory, rolled row loops, 2 CTAs/SM); 2: rolled assembly with register
   // factors; 0: fully unrolled register variant
-  const int v = fs == 1 ? 2 : (fs == 2 ? 4 : (fs == 4 ? 5 : 3));
+  const int v = fs == 1 ? 2 : (fs == 2 ? 4 : (fs == 4 ? 5 : (fs == 6 ? 6 : (fs == 7 ? 7 : 3))));
   switch (p.M) {
     case 5: return pk_pick_kernel_m5(p.mode, block, p.T, v);
     case 6: return pk_pick_kernel_m6(p.mode, block, p.T, v);
@@ -385,7 +385,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->fs = 0;
   { const char* e = getenv("PK_FS"); const int want = e ? atoi(e) : 0;
     if (want && cfg->scheme != 1 && p.T == 128) {      // FS variant: + level-1 factors in shared memory
-      c->fs = (want == 1 || want == 2 || want == 4) ? want : 1;     // needs a -DPK_EXPERIMENTAL_VARIANTS build
+      c->fs = (want == 1 || want == 2 || want == 4 || want == 6 || want == 7) ? want : 1;     // needs a -DPK_EXPERIMENTAL_VARIANTS build
       if (c->fs == 1) c->smem += sizeof(double) * ((size_t)6 * (p.M - 2) * p.T + 1);
     } }
   if (cfg->scheme == 1) {
