@@ -6,7 +6,8 @@ struct StepArgs {
   const double* dW_in;
   double* dW_out;
   int *fail_step, *its_last, *its_total;
-  int R, step0, nsteps;
+  int R, step0, nsteps;   // R: realisations of the context (stride of dW_in / dW_out and of the state arrays)
+  int r0, Rq;             // this launch advances realisations [r0, r0 + Rq)
   long long* prof;    // [R,16] cycle buckets, PK_PROFILE builds only
   unsigned rid0;
   unsigned long long seed;

@@ -19,7 +19,9 @@ struct pk_ctx {
   int fs;              // 1: FS variant of the single-CTA step kernel (factors in shared memory, rolled row loops)
   int slots;           // CTAs of the single-CTA step kernel resident at once (persistent grid), 0 = other kernel
   int sms;             // multiprocessors of the device
-  int* d_queue;        // [1 + R] work counter + per-realisation finished-block counters
+  int* d_queue;        // [PK_HOST_CHUNKS][1 + R] work counter + per-realisation finished-block counters (one set per concurrent launch)
+  cudaStream_t hs[4];  // pk_step_host: streams of the chunk pipeline (H2D -> kernel -> D2H per chunk)
+  cudaEvent_t hev;
   int last_nb, last_nblk, last_grid;   // work split of the last pk_step launch (pk_get_work_split)
   std::string err;
   // internal device buffers for the *_host entry points

@@ -189,14 +189,14 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   // out R items earlier and is normally long finished; its completion counter is awaited before the state
   // is loaded.  This keeps every resident CTA busy until the queue is dry, whatever R / (CTAs per wave) is.
   __shared__ int s_item;
-  const int nitems = a.nb * a.R;
+  const int nitems = a.nb * a.Rq;
   int* const done = a.queue + 1;
   while (true) {
     if (threadIdx.x == 0) {
       const int item = atomicAdd(a.queue, 1);
       if (item < nitems) {
-        const int b = item / a.R, r = item - b * a.R;
-        while (atomicAdd(done + r, 0) < b) __nanosleep(200);
+        const int b = item / a.Rq, rl = item - b * a.Rq;
+        while (atomicAdd(done + rl, 0) < b) __nanosleep(200);
         __threadfence();
       }
       s_item = item;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
     __syncthreads();
     const int item = s_item;
     if (item >= nitems) break;
-    const int b = item / a.R, r = item - b * a.R;
+    const int b = item / a.Rq, rl = item - b * a.Rq, r = a.r0 + rl;
     const long long off = (long long)r * p.ne;
     // coalesced global reads (L2: the state may have been written by another SM during this launch),
     // scattered into the chunk-interleaved shared layout
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
     }
     __threadfence();
     __syncthreads();      // all stores of the block are fenced; s_item may be overwritten
-    if (threadIdx.x == 0) { __threadfence(); atomicExch(done + r, b + 1); }
+    if (threadIdx.x == 0) { __threadfence(); atomicExch(done + rl, b + 1); }
   }
 #ifdef PK_PROFILE
   if (a.prof && threadIdx.x < 16) a.prof[blockIdx.x * 16 + threadIdx.x] = tb[threadIdx.x];

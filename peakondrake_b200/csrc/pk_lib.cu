@@ -430,6 +430,8 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     c->slots = per_sm * c->sms;
   }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  for (int q = 0; q < 4; ++q) cudaStreamCreateWithFlags(&c->hs[q], cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->hev, cudaEventDisableTiming);
   *out = c;
   return 0;
 }
@@ -445,7 +447,8 @@ extern "C" void pk_destroy(pk_ctx* c) {
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_mom) cudaFree(c->d_mom);
   for (int q = 0; q < 3; ++q) if (c->d_tab[q]) cudaFree(c->d_tab[q]);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->hev);
+  for (int q = 0; q < 4; ++q) cudaStreamDestroy(c->hs[q]);
   delete c;
 }
 
@@ -494,26 +497,14 @@ extern "C" int pk_get_work_split(const pk_ctx* c, int32_t* group, int32_t* nb, i
   return 0;
 }
 
-extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
-                       const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
-                       int32_t* its_total, void* stream) {
-  if (!c) return -1;
-  if (nsteps < 0) return fail(c, "pk_step: nsteps < 0");
-  if (c->cfg.scheme == 1) return fail(c, "pk_step: context was created for the upwind scheme; use pk_step_upwind");
-  if (!u || !u1 || !dF || !fail_step || !its_last || !its_total) return fail(c, "pk_step: null state/counter pointer");
-  if (c->p.mode == NOISE_FULL && !dG) return fail(c, "pk_step: dG is required for PK_NOISE_FULL");
-  if (PK_NOISE_OF(c->p.mode) != NOISE_SCALAR && c->p.nxi > 0 && !c->xi) return fail(c, "pk_step: noise tables not set (pk_set_tables)");
-  if (nsteps == 0) return 0;
-  CK(c, cudaSetDevice(c->cfg.device));
-  StepArgs a;
-  a.u = u; a.u1 = u1; a.dF = dF; a.dG = dG; a.xi = c->xi; a.xi_x = c->xi_x; a.xi_xx = c->xi_xx;
-  a.dW_in = dW_in; a.dW_out = dW_out; a.fail_step = fail_step; a.its_last = its_last; a.its_total = its_total;
-  a.prof = c->d_prof;
-  a.queue = nullptr; a.nblk = nsteps; a.nb = 1;
-  a.R = c->cfg.R; a.step0 = (int)c->step; a.nsteps = nsteps; a.rid0 = c->cfg.rid_offset; a.seed = c->cfg.seed;
-  cudaStream_t st = (cudaStream_t)stream;
-  CK(c, cudaEventRecord(c->ev0, st));
+// Launch the step kernel for realisations [r0, r0 + nr) of the context on stream st.  `slot` selects one of the
+// PK_HOST_CHUNKS queue areas (launches that may run concurrently need their own).  Does not advance c->step.
+enum { PK_HOST_CHUNKS = 4 };
+static int launch_range(pk_ctx* c, StepArgs a, int nsteps, int r0, int nr, int slot, cudaStream_t st, bool timed) {
+  a.r0 = r0; a.Rq = nr;
   if (c->cluster > 1) {
+    if (r0 != 0 || nr != c->cfg.R) return fail(c, "internal: the cluster kernel advances the whole ensemble");
+    if (timed) CK(c, cudaEventRecord(c->ev0, st));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(c->cfg.R * c->cluster)); lc.blockDim = dim3((unsigned)c->block);
     lc.dynamicSmemBytes = c->smem; lc.stream = st;
@@ -524,21 +515,50 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
     CK(c, cudaLaunchKernelEx(&lc, pick_cluster_kernel(c->p, c->block), c->p, a, c->lgTc));
   } else {
     const int R = c->cfg.R;
-    if (!c->d_queue) CK(c, cudaMalloc(&c->d_queue, sizeof(int) * (size_t)(R + 1)));
-    const int grid = R < c->slots ? R : c->slots;
+    if (!c->d_queue) CK(c, cudaMalloc(&c->d_queue, sizeof(int) * (size_t)(R + 1) * PK_HOST_CHUNKS));
+    int* queue = c->d_queue + (size_t)slot * (R + 1);
+    const int grid = nr < c->slots ? nr : c->slots;
     int nb = 1, nblk = nsteps;
-    choose_blocks(R, nsteps, grid, &nb, &nblk);
+    choose_blocks(nr, nsteps, grid, &nb, &nblk);
     { const char* e = getenv("PK_NBLK"); const int v = e ? atoi(e) : 0; if (v > 0) { nblk = v < nsteps ? v : nsteps; nb = (nsteps + nblk - 1) / nblk; } }
-    a.queue = c->d_queue; a.nblk = nblk; a.nb = nb;
+    a.queue = queue; a.nblk = nblk; a.nb = nb;
     c->last_nb = nb; c->last_nblk = nblk; c->last_grid = grid;
-    CK(c, cudaMemsetAsync(c->d_queue, 0, sizeof(int) * (size_t)(R + 1), st));
-    CK(c, cudaEventRecord(c->ev0, st));      // time the kernel alone
+    CK(c, cudaMemsetAsync(queue, 0, sizeof(int) * (size_t)(nr + 1), st));
+    if (timed) CK(c, cudaEventRecord(c->ev0, st));      // time the kernel alone
     kern_t k = pick_kernel(c->p, c->block, c->fs);
     k<<<grid, c->block, c->smem, st>>>(c->p, a);
   }
   CK(c, cudaGetLastError());
-  CK(c, cudaEventRecord(c->ev1, st));
-  c->timed = true;
+  if (timed) { CK(c, cudaEventRecord(c->ev1, st)); c->timed = true; }
+  return 0;
+}
+
+static int step_args(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* dF, double* dG, const double* dW_in,
+                     double* dW_out, int32_t* fail_step, int32_t* its_last, int32_t* its_total, StepArgs* a) {
+  if (nsteps < 0) return fail(c, "pk_step: nsteps < 0");
+  if (c->cfg.scheme == 1) return fail(c, "pk_step: context was created for the upwind scheme; use pk_step_upwind");
+  if (!u || !u1 || !dF || !fail_step || !its_last || !its_total) return fail(c, "pk_step: null state/counter pointer");
+  if (c->p.mode == NOISE_FULL && !dG) return fail(c, "pk_step: dG is required for PK_NOISE_FULL");
+  if (PK_NOISE_OF(c->p.mode) != NOISE_SCALAR && c->p.nxi > 0 && !c->xi) return fail(c, "pk_step: noise tables not set (pk_set_tables)");
+  a->u = u; a->u1 = u1; a->dF = dF; a->dG = dG; a->xi = c->xi; a->xi_x = c->xi_x; a->xi_xx = c->xi_xx;
+  a->dW_in = dW_in; a->dW_out = dW_out; a->fail_step = fail_step; a->its_last = its_last; a->its_total = its_total;
+  a->prof = c->d_prof;
+  a->queue = nullptr; a->nblk = nsteps; a->nb = 1; a->r0 = 0; a->Rq = c->cfg.R;
+  a->R = c->cfg.R; a->step0 = (int)c->step; a->nsteps = nsteps; a->rid0 = c->cfg.rid_offset; a->seed = c->cfg.seed;
+  return 0;
+}
+
+extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                       const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                       int32_t* its_total, void* stream) {
+  if (!c) return -1;
+  StepArgs a;
+  int rc = step_args(c, nsteps, u, u1, dF, dG, dW_in, dW_out, fail_step, its_last, its_total, &a);
+  if (rc) return rc;
+  if (nsteps == 0) return 0;
+  CK(c, cudaSetDevice(c->cfg.device));
+  rc = launch_range(c, a, nsteps, 0, c->cfg.R, 0, (cudaStream_t)stream, true);
+  if (rc) return rc;
   c->step += nsteps;
   return 0;
 }
@@ -574,26 +594,44 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
   }
   double *du = c->d_state, *du1 = du + fld, *ddF = du + 2 * fld, *ddG = du + 3 * fld;
   int *dfs = c->d_cnt, *dil = dfs + R, *dit = dfs + 2 * R;
-  cudaStream_t st = 0;
-  CK(c, cudaMemcpyAsync(du, u, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
-  CK(c, cudaMemcpyAsync(du1, u1, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
-  CK(c, cudaMemcpyAsync(ddF, dF, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
-  if (hasG) CK(c, cudaMemcpyAsync(ddG, dG, sizeof(double) * fld, cudaMemcpyHostToDevice, st));
-  CK(c, cudaMemcpyAsync(dfs, fail_step, sizeof(int) * R, cudaMemcpyHostToDevice, st));
-  CK(c, cudaMemcpyAsync(dit, its_total, sizeof(int) * R, cudaMemcpyHostToDevice, st));
-  if (dW_in && ndw) CK(c, cudaMemcpyAsync(c->d_dWin, dW_in, sizeof(double) * ndw, cudaMemcpyHostToDevice, st));
-  int rc = pk_step(c, nsteps, du, du1, ddF, hasG ? ddG : nullptr, (dW_in && ndw) ? c->d_dWin : nullptr,
-                   (dW_out && ndw) ? c->d_dWout : nullptr, dfs, dil, dit, (void*)st);
+  StepArgs a;
+  int rc = step_args(c, nsteps, du, du1, ddF, hasG ? ddG : nullptr, (dW_in && ndw) ? c->d_dWin : nullptr,
+                     (dW_out && ndw) ? c->d_dWout : nullptr, dfs, dil, dit, &a);
   if (rc) return rc;
-  CK(c, cudaMemcpyAsync(u, du, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaMemcpyAsync(u1, du1, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaMemcpyAsync(dF, ddF, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
-  if (hasG) CK(c, cudaMemcpyAsync(dG, ddG, sizeof(double) * fld, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaMemcpyAsync(fail_step, dfs, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaMemcpyAsync(its_last, dil, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaMemcpyAsync(its_total, dit, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
-  if (dW_out && ndw) CK(c, cudaMemcpyAsync(dW_out, c->d_dWout, sizeof(double) * ndw, cudaMemcpyDeviceToHost, st));
-  CK(c, cudaStreamSynchronize(st));
+  if (nsteps == 0) return 0;
+  // Chunk pipeline: the realisations are split into NC contiguous chunks, each with its own stream doing
+  // H2D -> step kernel -> D2H, so the copies of one chunk overlap the kernel of another (the persistent kernels of
+  // two chunks share the SMs work-conservingly).  Host buffers should be pinned for the copies to be asynchronous.
+  int NC = (c->cluster > 1 || R < 256) ? 1 : PK_HOST_CHUNKS;
+  { const char* e = getenv("PK_HOST_NCHUNK"); const int v = e ? atoi(e) : 0; if (v >= 1 && v <= PK_HOST_CHUNKS && c->cluster == 1) NC = v; }
+  if (dW_in && ndw) {       // [nsteps, R, nxi]: not contiguous per chunk -> one copy up front, every chunk waits for it
+    CK(c, cudaMemcpyAsync(c->d_dWin, dW_in, sizeof(double) * ndw, cudaMemcpyHostToDevice, c->hs[0]));
+    CK(c, cudaEventRecord(c->hev, c->hs[0]));
+  }
+  for (int k = 0; k < NC; ++k) {
+    const size_t r0 = R * k / NC, r1 = R * (k + 1) / NC, nr = r1 - r0, o = r0 * ne, nb = sizeof(double) * nr * ne;
+    cudaStream_t st = c->hs[k];
+    if (dW_in && ndw && k > 0) CK(c, cudaStreamWaitEvent(st, c->hev, 0));
+    CK(c, cudaMemcpyAsync(du + o, u + o, nb, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(du1 + o, u1 + o, nb, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(ddF + o, dF + o, nb, cudaMemcpyHostToDevice, st));
+    if (hasG) CK(c, cudaMemcpyAsync(ddG + o, dG + o, nb, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(dfs + r0, fail_step + r0, sizeof(int) * nr, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(dit + r0, its_total + r0, sizeof(int) * nr, cudaMemcpyHostToDevice, st));
+    rc = launch_range(c, a, nsteps, (int)r0, (int)nr, k, st, false);
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(u + o, du + o, nb, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(u1 + o, du1 + o, nb, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(dF + o, ddF + o, nb, cudaMemcpyDeviceToHost, st));
+    if (hasG) CK(c, cudaMemcpyAsync(dG + o, ddG + o, nb, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(fail_step + r0, dfs + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(its_last + r0, dil + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(its_total + r0, dit + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
+  }
+  for (int k = 0; k < NC; ++k) CK(c, cudaStreamSynchronize(c->hs[k]));
+  if (dW_out && ndw) CK(c, cudaMemcpy(dW_out, c->d_dWout, sizeof(double) * ndw, cudaMemcpyDeviceToHost));
+  c->timed = false;
+  c->step += nsteps;
   return 0;
 }
 
