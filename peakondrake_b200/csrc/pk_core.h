@@ -162,14 +162,14 @@ PK_HD void mm2(const double* A, const double* B, double* C) {
   C[0] = A[0] * B[0] + A[1] * B[2]; C[1] = A[0] * B[1] + A[1] * B[3];
   C[2] = A[2] * B[0] + A[3] * B[2]; C[3] = A[2] * B[1] + A[3] * B[3];
 }
-// C += A*B
+// C += A*B   (written as accumulation chains: two fused multiply-adds per entry)
 PK_HD void mma2(const double* A, const double* B, double* C) {
-  C[0] += A[0] * B[0] + A[1] * B[2]; C[1] += A[0] * B[1] + A[1] * B[3];
-  C[2] += A[2] * B[0] + A[3] * B[2]; C[3] += A[2] * B[1] + A[3] * B[3];
+  C[0] = A[1] * B[2] + (A[0] * B[0] + C[0]); C[1] = A[1] * B[3] + (A[0] * B[1] + C[1]);
+  C[2] = A[3] * B[2] + (A[2] * B[0] + C[2]); C[3] = A[3] * B[3] + (A[2] * B[1] + C[3]);
 }
 // y += A*x
 PK_HD void mva2(const double* A, const double* x, double* y) {
-  y[0] += A[0] * x[0] + A[1] * x[1]; y[1] += A[2] * x[0] + A[3] * x[1];
+  y[0] = A[1] * x[1] + (A[0] * x[0] + y[0]); y[1] = A[3] * x[1] + (A[2] * x[0] + y[1]);
 }
 
 // TT > 0: number of threads per realisation known at compile time (constant-folds the shared-memory
@@ -266,9 +266,9 @@ struct Thread {
     const int i = nidx(p, j);
     const double u0 = sh.ld(sh.U0, i), u1 = sh.ld(sh.U1, i);
     n.a = 0.5 * (u1 + u0);
-    n.w = u1 - u0;
+    n.w = u1 - u0;                       // + dG below (NOISE_FULL): R_psi = M (u1 - u + dG) + ...
     n.F = PK_IS_TEST(MODE) ? 0.0 : sh.ld(sh.F, i);
-    if (MODE == NOISE_FULL) { n.G = sh.ld(sh.G, i); n.x = sh.ld(sh.Xx, i); n.y = sh.ld(sh.Xxx, i); }
+    if (MODE == NOISE_FULL) { n.G = sh.ld(sh.G, i); n.x = sh.ld(sh.Xx, i); n.y = sh.ld(sh.Xxx, i); n.w += n.G; }
     else { n.G = 0.0; n.x = 0.0; n.y = 0.0; }
     const double X = (PK_NOISE_OF(MODE) == NOISE_SCALAR) ? Xs : sh.ld(sh.X, i);
     n.v = p.dt * n.a + X;
@@ -281,19 +281,19 @@ struct Thread {
       const double R = p.mb * (nm.w + np.w) + p.ma * n0.w + (pc.N1R + cc.N1L);
       fn2 += R * R;
       if (lite) return;
-      k.C0[0] = pc.dN1R0; k.C0[1] = pc.dN1R1 + cc.dN1L0; k.C0[2] = cc.dN1L1;
+      k.C0[0] = pc.dN1R0 + p.hm1; k.C0[1] = (pc.dN1R1 + cc.dN1L0) + p.hm0; k.C0[2] = cc.dN1L1 + p.hm1;   // + constant part (M)
       PK_UNROLL
       for (int c = 0; c < 3; ++c) { k.Cm[c] = 0.0; k.Cp[c] = 0.0; }
       k.Q0 = R; k.Qm = 0.0; k.Qp = 0.0;
       return;
     }
     const double N1 = pc.N1R + cc.N1L, ff = pc.fR + cc.fL;
-    const double Rpsi = p.mb * (nm.w + np.w) + p.ma * n0.w + N1 - 0.5 * (nm.F - np.F)
-                        + ((MODE == NOISE_FULL) ? (p.mb * (nm.G + np.G) + p.ma * n0.G) : 0.0);
-    const double Rphi = p.hb * (nm.F + np.F) + p.ha * n0.F - ff;
+    // NodeS::w = (u1 - u) + dG: the mass matrix acts on both in R_psi.  Accumulation chains (one FMA per term).
+    const double Rpsi = p.ma * n0.w + (p.mb * (nm.w + np.w) + (0.5 * (np.F - nm.F) + N1));
+    const double Rphi = p.ha * n0.F + (p.hb * (nm.F + np.F) - ff);
     double Rzeta = 0.0;
-    if (MODE == NOISE_FULL) Rzeta = p.hb * (nm.G + np.G) + p.ha * n0.G - (pc.gR + cc.gL);
-    fn2 += Rpsi * Rpsi + Rphi * Rphi + Rzeta * Rzeta;
+    if (MODE == NOISE_FULL) Rzeta = p.ha * n0.G + (p.hb * (nm.G + np.G) - (pc.gR + cc.gL));
+    fn2 = Rzeta * Rzeta + (Rphi * Rphi + (Rpsi * Rpsi + fn2));
     if (lite) return;                    // residual norm only (uniform across the block)
     // tridiagonal rows of N1'/2, f'/4, g'/2 at node n0 (compute_jac delivers them pre-scaled)
     const double B[3] = {pc.dN1R0, pc.dN1R1 + cc.dN1L0, cc.dN1L1};
@@ -305,7 +305,8 @@ struct Thread {
       const double S = p.hb * B[c] + p.mb * Gm[c];
       k.Cm[c] = S - Fq[c];
       k.Cp[c] = S + Fq[c];
-      k.C0[c] = p.ha * B[c] + p.ma * Gm[c];
+      // the node's own row also carries the constant part H M of the Newton matrix (offsets -1, 0, +1)
+      k.C0[c] = p.ha * B[c] + (p.ma * Gm[c] + (c == 1 ? p.hm0 : p.hm1));
     }
     const double hr = p.hb * Rpsi - p.mb * Rzeta;
     k.Qm = hr + 0.5 * Rphi;
@@ -343,9 +344,9 @@ struct Thread {
       return;
     }
     const double a = p.hm2 + wCm2[0];
-    const double b = p.hm1 + wCm2[1] + wC01[0];
-    const double c = p.hm0 + wCm2[2] + wC01[1] + cp[0];
-    const double ee = p.hm1 + wC01[2] + cp[1];
+    const double b = wCm2[1] + wC01[0];            // (C0 carries the constants of offsets -1, 0, +1)
+    const double c = wCm2[2] + wC01[1] + cp[0];
+    const double ee = wC01[2] + cp[1];
     const double ff = p.hm2 + cp[2];
     const double rhs = -(wQm2 + wQ01 + qp);
     if (row == 1) {
@@ -372,7 +373,7 @@ struct Thread {
     const int n = q - 1;
     if (n == 0) {
       // separator row 0 so far: H*M part, own C0/Q0 (Cm of the left neighbour is added in reduce_build)
-      sp0[0] = p.hm2; sp0[1] = p.hm1 + k.C0[0]; sp0[2] = p.hm0 + k.C0[1]; sp0[3] = p.hm1 + k.C0[2]; sp0[4] = p.hm2;
+      sp0[0] = p.hm2; sp0[1] = k.C0[0]; sp0[2] = k.C0[1]; sp0[3] = k.C0[2]; sp0[4] = p.hm2;
       sb0 = -k.Q0;
       // publish what the left neighbour's last row needs from my first node
       sh.st(sh.xb, 14 * TN(p) + t, k.Cp[0]); sh.st(sh.xb, 15 * TN(p) + t, k.Cp[1]); sh.st(sh.xb, 16 * TN(p) + t, k.Cp[2]);
@@ -422,9 +423,9 @@ struct Thread {
       return;
     }
     const double a = p.hm2 + wCm2[0];
-    const double b = p.hm1 + wCm2[1] + wC01[0];
-    const double c = p.hm0 + wCm2[2] + wC01[1] + cp[0];
-    const double ee = p.hm1 + wC01[2] + cp[1];
+    const double b = wCm2[1] + wC01[0];            // (C0 carries the constants of offsets -1, 0, +1)
+    const double c = wCm2[2] + wC01[1] + cp[0];
+    const double ee = wC01[2] + cp[1];
     const double ff = p.hm2 + cp[2];
     const double rhs = -(wQm2 + wQ01 + qp);
     if (row == 1) {
@@ -930,14 +931,13 @@ struct Thread {
         const double Fn = hF[j] + pwv[j] * inF;
         const double dFv = Fn - sh.ld(sh.F, i);
         sh.st(sh.U1, i, u1n); sh.st(sh.F, i, Fn);
-        double s2 = duj * duj + dFv * dFv, x2 = u1n * u1n + Fn * Fn;
+        sn2 = dFv * dFv + (duj * duj + sn2); xn2 = Fn * Fn + (u1n * u1n + xn2);     // accumulation chains (FMAs)
         if (MODE == NOISE_FULL) {
           const double Gn = hG[j] + pwv[j] * inG;
           const double dGv = Gn - sh.ld(sh.G, i);
           sh.st(sh.G, i, Gn);
-          s2 += dGv * dGv; x2 += Gn * Gn;
+          sn2 = dGv * dGv + sn2; xn2 = Gn * Gn + xn2;
         }
-        sn2 += s2; xn2 += x2;
       }
     }
   }
@@ -953,7 +953,7 @@ struct Thread {
         const double duj = get_du(p, sh, j);
         const double u1n = sh.ld(sh.U1, i) + duj;
         sh.st(sh.U1, i, u1n);
-        sn2 += duj * duj; xn2 += u1n * u1n;
+        sn2 = duj * duj + sn2; xn2 = u1n * u1n + xn2;
       }
     }
   }
