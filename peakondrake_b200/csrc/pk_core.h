@@ -83,7 +83,8 @@ struct NodeS { double a, v, w, F, G, x, y; };
 // with respect to the two nodal values of uh.  SURVEY.md App. A.1.
 template <int MODE>
 struct CellC {
-  double N1L, N1R, fL, fR, gL, gR;
+  double N1L, N1R;
+  double fL, fR, gL, gR;          // HALF the cell contributions of f and g (node_packet doubles them in an FMA)
   double dN1L0, dN1L1, dN1R0, dN1R1;
   double dfL0, dfL1, dfR0, dfR1;
   double dgL0, dgL1, dgR0, dgR1;
@@ -102,17 +103,29 @@ struct CellC {
     N1L = da6 * sL; N1R = da6 * sR;
     const double a0 = A.a, a1 = B.a;
     const double a00 = a0 * a0, a01 = a0 * a1, a11 = a1 * a1;
-    const double cda2 = p.c2 * da * da;
-    fL = p.c1 * (3.0 * a00 + 2.0 * a01 + a11) + cda2;
-    fR = p.c1 * (a00 + 2.0 * a01 + 3.0 * a11) + cda2;
+    const double cda2 = p.c2h * da * da;
+    fL = p.c1h * (3.0 * a00 + 2.0 * a01 + a11) + cda2;
+    fR = p.c1h * (a00 + 2.0 * a01 + 3.0 * a11) + cda2;
     if (MODE == NOISE_FULL) {
       const double x0 = A.x, x1 = B.x, y0 = A.y, y1 = B.y;
       const double xs = x0 + x1;
-      gL = p.h6 * (a0 * (3.0 * x0 + x1) + a1 * xs) + p.a26 * da * (2.0 * y0 + y1);
-      gR = p.h6 * (a0 * xs + a1 * (x0 + 3.0 * x1)) + p.a26 * da * (y0 + 2.0 * y1);
+      gL = p.h12 * (a0 * (3.0 * x0 + x1) + a1 * xs) + p.a212 * da * (2.0 * y0 + y1);
+      gR = p.h12 * (a0 * xs + a1 * (x0 + 3.0 * x1)) + p.a212 * da * (y0 + 2.0 * y1);
     } else {
       gL = gR = 0.0;
     }
+  }
+  // values AND derivatives (Newton pass).  f is a homogeneous quadratic form and g is linear in uh, so by Euler's
+  // theorem their values follow from the derivative entries computed for the Jacobian anyway:
+  //    f/2 = (f'/4) . 2 uh / 2 ... i.e.  fL/2 = dfL0 a0 + dfL1 a1,   gL/2 = dgL0 a0 + dgL1 a1   (df = f'/4, dg = g'/2).
+  PK_HD void compute_full(const Params& p, const NodeS& A, const NodeS& B) {
+    compute_jac(p, A, B);
+    if (PK_IS_TEST(MODE)) { compute_res(p, A, B); return; }
+    const double da6 = (B.a - A.a) * (1.0 / 6.0);
+    N1L = da6 * (2.0 * A.v + B.v); N1R = da6 * (A.v + 2.0 * B.v);
+    fL = dfL0 * A.a + dfL1 * B.a; fR = dfR0 * A.a + dfR1 * B.a;
+    if (MODE == NOISE_FULL) { gL = dgL0 * A.a + dgL1 * B.a; gR = dgR0 * A.a + dgR1 * B.a; }
+    else { gL = gR = 0.0; }
   }
   // derivatives with respect to the two nodal values of uh, PRE-SCALED the way the Newton matrix uses them
   // (u1 enters through uh = (u1+u)/2):  dN1* = N1'/2,  df* = f'/4 (the matrix has -+ D f'/2 with D = +-1/2),
@@ -146,7 +159,6 @@ struct CellC {
       dgL0 = dgL1 = dgR0 = dgR1 = 0.0;
     }
   }
-  PK_HD void compute(const Params& p, const NodeS& A, const NodeS& B) { compute_res(p, A, B); compute_jac(p, A, B); }
 };
 
 // What node l contributes to pentadiagonal rows l-1 (Cp,Qp), l (C0,Q0) and l+1 (Cm,Qm).
@@ -290,9 +302,9 @@ struct Thread {
     const double N1 = pc.N1R + cc.N1L, ff = pc.fR + cc.fL;
     // NodeS::w = (u1 - u) + dG: the mass matrix acts on both in R_psi.  Accumulation chains (one FMA per term).
     const double Rpsi = p.ma * n0.w + (p.mb * (nm.w + np.w) + (0.5 * (np.F - nm.F) + N1));
-    const double Rphi = p.ha * n0.F + (p.hb * (nm.F + np.F) - ff);
+    const double Rphi = p.ha * n0.F + (p.hb * (nm.F + np.F) - 2.0 * ff);          // ff, gg: half values (CellC)
     double Rzeta = 0.0;
-    if (MODE == NOISE_FULL) Rzeta = p.ha * n0.G + (p.hb * (nm.G + np.G) - (pc.gR + cc.gL));
+    if (MODE == NOISE_FULL) Rzeta = p.ha * n0.G + (p.hb * (nm.G + np.G) - 2.0 * (pc.gR + cc.gL));
     fn2 = Rzeta * Rzeta + (Rphi * Rphi + (Rpsi * Rpsi + fn2));
     if (lite) return;                    // residual norm only (uniform across the block)
     // tridiagonal rows of N1'/2, f'/4, g'/2 at node n0 (compute_jac delivers them pre-scaled)
@@ -366,8 +378,8 @@ struct Thread {
   template <class SH>
   PK_HD void stream(const Params& p, const SH& sh, int q, bool lite) {
     load_node(p, sh, q, np);
-    CellC<MODE> cc; cc.compute_res(p, n0, np);
-    if (!lite) cc.compute_jac(p, n0, np);
+    CellC<MODE> cc;
+    if (lite) cc.compute_res(p, n0, np); else cc.compute_full(p, n0, np);
     Packet k; node_packet(p, cc, k, lite);     // node q-1
     if (lite) { nm = n0; n0 = np; pc.N1R = cc.N1R; pc.fR = cc.fR; pc.gR = cc.gR; return; }
     const int n = q - 1;
@@ -449,8 +461,8 @@ struct Thread {
   template <class SH>
   PK_HD void stream_fs(const Params& p, const SH& sh, int q, bool lite) {
     load_node(p, sh, q, np);
-    CellC<MODE> cc; cc.compute_res(p, n0, np);
-    if (!lite) cc.compute_jac(p, n0, np);
+    CellC<MODE> cc;
+    if (lite) cc.compute_res(p, n0, np); else cc.compute_full(p, n0, np);
     Packet k; node_packet(p, cc, k, lite);     // node q-1
     if (lite) { nm = n0; n0 = np; pc.N1R = cc.N1R; pc.fR = cc.fR; pc.gR = cc.gR; return; }
     finish_row_fs(p, sh, q - 2, k.Cp, k.Qp);
@@ -546,8 +558,7 @@ struct Thread {
     kill_factors();
     load_node(p, sh, -1, nm);
     load_node(p, sh, 0, n0);
-    pc.compute_res(p, nm, n0);
-    if (!lite) pc.compute_jac(p, nm, n0);
+    if (lite) pc.compute_res(p, nm, n0); else pc.compute_full(p, nm, n0);
     PK_UNROLL
     for (int c = 0; c < 3; ++c) { wCm1[c] = 0.0; wCm2[c] = 0.0; wC01[c] = 0.0; }
     wQm1 = wQm2 = wQ01 = 0.0;
