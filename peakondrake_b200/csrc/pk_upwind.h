@@ -9,6 +9,9 @@
 //   Q  = (2 mL s0 + mL s1 + mR s0 + 2 mR s1)/6,   sx = (s1-s0)/h,
 //   Phi_v = s_v * (s_v > 0 ? mR_{v-1} : mL_v)                       (upwind flux at vertex v)
 //   rhs0 = -Q - sx h/6 (2mL+mR) + Phi_i ,  rhs1 = +Q - sx h/6 (mL+2mR) - Phi_{i+1},  dm = M_e^-1 rhs.
+// The volume terms collapse exactly (expand 6Q +- (s1-s0)(..)):
+//   rhs0 = Phi_i - s1 (mL+mR)/2 ,   rhs1 = s0 (mL+mR)/2 - Phi_{i+1},
+// which is what the kernel evaluates (a third of the flops; each vertex flux Phi is computed once).
 //
 // Layout: one CTA per realisation, the same chunk geometry as the midpoint kernel (thread t owns
 // cells/nodes [s_t, s_t+m_t)), but the scheme is explicit and local, so the WHOLE state of a thread
@@ -38,7 +41,7 @@ struct UpwindIO {
 
 template <int M, int XARR, int TT = 0>
 struct UpwindThread {
-  int t, m, s, tl, tr, active;
+  int t, m, s, tl, tr, active, ext;
   double mL[M], mR[M];       // m0: the state
   double aL[M], aR[M];       // trial
   double u[M];               // nodal u of my nodes
@@ -52,9 +55,11 @@ struct UpwindThread {
     t = tid; active = (tid < p.T);
     const int tt = active ? tid : 0;
     t = tt;
-    m = chunk_rows(p, tt); s = chunk_start(p, tt);
+    m = chunk_rows(p, tt); s = chunk_start(p, tt); ext = (m == M);
     tl = (tt + p.T - 1) & (p.T - 1); tr = (tt + 1) & (p.T - 1);
   }
+  // cell / node j of my chunk exists: 0..M-2 always (folds at compile time), M-1 only in full chunks
+  PK_HD bool has_row(int j) const { return j < M - 1 || ext; }
 
   PK_HD void load(const Params& p, const UpwindIO& io) {
     const long long off = (long long)io.r * p.ne;
@@ -79,7 +84,7 @@ struct UpwindThread {
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       double X = 0.0;
-      if (j < m) {
+      if (has_row(j)) {
         if (XARR) { for (int k = 0; k < p.nxi; ++k) X += sh.dw(k) * xi[k * T * M + j * T + t]; }
         else X = (p.nxi > 0) ? sh.dw(0) * p.xi_const : 0.0;
       }
@@ -88,7 +93,7 @@ struct UpwindThread {
     }
     sh.st(sh.xb, UW_S0 * T + t, sv[0]);
     sh.st(sh.xb, UW_A_L * T + t, aL[0]);
-    sh.st(sh.xb, UW_A_R * T + t, (m == M) ? aR[M - 1] : aR[M - 2]);
+    sh.st(sh.xb, UW_A_R * T + t, ext ? aR[M - 1] : aR[M - 2]);
   }
 
   // one SSPRK3 stage: d = dm(trial) and the stage combination, edges published to the other slot set
@@ -99,31 +104,31 @@ struct UpwindThread {
     if (k == 1) sR = sh.ld(sh.xb, UW_S0 * T + tr);     // us at the node right of my last cell
     const double upL = sh.ld(sh.xb, inR * T + tl);   // trial value just left of my first vertex
     const double dnR = sh.ld(sh.xb, inL * T + tr);   // trial value just right of my last vertex
-    const double ih = 1.0 / p.h, h6 = p.h6;
     double nL[M], nR[M];
+    // upwind flux at my first vertex; the flux at the right vertex of cell j is the left flux of cell j+1
+    double phi0 = sv[0] * (sv[0] > 0.0 ? upL : aL[0]);
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       nL[j] = aL[j]; nR[j] = aR[j];
-      if (j < m) {
-        const double s0 = sv[j], s1 = (j == m - 1) ? sR : sv[j + 1 < M ? j + 1 : M - 1];
+      if (has_row(j)) {
+        const bool last = (j == M - 1) || (j == M - 2 && !ext);
+        const double s0 = sv[j], s1 = last ? sR : sv[j + 1 < M ? j + 1 : M - 1];
         const double a = aL[j], b = aR[j];
-        const double left = (j == 0) ? upL : aR[j > 0 ? j - 1 : 0];
-        const double right = (j == m - 1) ? dnR : aL[j + 1 < M ? j + 1 : M - 1];
-        const double phi0 = s0 * (s0 > 0.0 ? left : a);
+        const double right = last ? dnR : aL[j + 1 < M ? j + 1 : M - 1];
         const double phi1 = s1 * (s1 > 0.0 ? b : right);
-        const double Q = (1.0 / 6.0) * (a * (2.0 * s0 + s1) + b * (s0 + 2.0 * s1));
-        const double sx = (s1 - s0) * ih;
-        const double r0 = -Q - sx * h6 * (2.0 * a + b) + phi0;
-        const double r1 = Q - sx * h6 * (a + 2.0 * b) - phi1;
-        const double d0 = (2.0 * ih) * (2.0 * r0 - r1), d1 = (2.0 * ih) * (2.0 * r1 - r0);   // M_e^-1
+        const double ab = a + b;
+        const double r0 = phi0 - 0.5 * (s1 * ab);
+        const double r1 = 0.5 * (s0 * ab) - phi1;
+        const double d0 = p.ih2 * (2.0 * r0 - r1), d1 = p.ih2 * (2.0 * r1 - r0);   // M_e^-1
         if (k == 1) { nL[j] = mL[j] + d0; nR[j] = mR[j] + d1; }
         else if (k == 2) { nL[j] = 0.75 * mL[j] + 0.25 * (a + d0); nR[j] = 0.75 * mR[j] + 0.25 * (b + d1); }
         else { nL[j] = (1.0 / 3.0) * mL[j] + (2.0 / 3.0) * (a + d0); nR[j] = (1.0 / 3.0) * mR[j] + (2.0 / 3.0) * (b + d1); }
+        phi0 = phi1;
       }
     }
     PK_UNROLL
     for (int j = 0; j < M; ++j) { aL[j] = nL[j]; aR[j] = nR[j]; }
-    const double lastL = (m == M) ? aL[M - 1] : aL[M - 2], lastR = (m == M) ? aR[M - 1] : aR[M - 2];
+    const double lastL = ext ? aL[M - 1] : aL[M - 2], lastR = ext ? aR[M - 1] : aR[M - 2];
     if (k == 1) { sh.st(sh.xb, UW_B_L * T + t, aL[0]); sh.st(sh.xb, UW_B_R * T + t, lastR); }
     else if (k == 2) { sh.st(sh.xb, UW_A_L * T + t, aL[0]); sh.st(sh.xb, UW_A_R * T + t, lastR); }
     else {
@@ -138,35 +143,32 @@ struct UpwindThread {
   PK_HD void helm_causal(const Params& p, const SH& sh, double& A, double& c0, double& c1) {
     const int T = TN(p);
     double pL = sh.ld(sh.xb, UW_H_L * T + tl), pR = sh.ld(sh.xb, UW_H_R * T + tl);
-    double y = 0.0, pw = 1.0;
+    double y = 0.0;
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       hh[j] = 0.0;
-      if (j < m) {
-        const double b = p.h6 * ((pL + 2.0 * pR) + (2.0 * mL[j] + mR[j]));
-        y = b * p.ikappa + p.rho * y; hh[j] = y; pw *= p.rho;
+      if (has_row(j)) {
+        const double b = (pL + 2.0 * pR) + (2.0 * mL[j] + mR[j]);      // (P m)_j * 6/h
+        y = b * p.h6k + p.rho * y; hh[j] = y;
         pL = mL[j]; pR = mR[j];
       }
     }
-    A = pw; c0 = y; c1 = 0.0;
+    A = ext ? p.rpow[M] : p.rpow[M - 1]; c0 = y; c1 = 0.0;
   }
   PK_HD void helm_anticausal(const Params& p, double in0, double& A, double& c0, double& c1) {
-    double pw = p.rho;
+    double x = 0.0;
     PK_UNROLL
-    for (int j = 0; j < M; ++j) if (j < m) { hh[j] += pw * in0; pw *= p.rho; }
-    double x = 0.0; pw = 1.0;
-    PK_UNROLL
-    for (int j = M - 1; j >= 0; --j) if (j < m) { x = hh[j] + p.rho * x; hh[j] = x; pw *= p.rho; }
-    A = pw; c0 = x; c1 = 0.0;
+    for (int j = M - 1; j >= 0; --j) if (has_row(j)) { x = (hh[j] + p.rpow[j + 1] * in0) + p.rho * x; hh[j] = x; }
+    A = ext ? p.rpow[M] : p.rpow[M - 1]; c0 = x; c1 = 0.0;
   }
   // returns true if every new u of this thread is finite
   PK_HD bool helm_finish(const Params& p, double in0) {
-    double pw = p.rho;
+    if (!ext) in0 *= p.irho;              // short chunks: fold the missing factor rho into the carry
     bool ok = true;
     PK_UNROLL
     for (int j = M - 1; j >= 0; --j) {
-      if (j < m) {
-        u[j] = hh[j] + pw * in0; pw *= p.rho;
+      if (has_row(j)) {
+        u[j] = hh[j] + p.rpow[M - j] * in0;
         ok = ok && (u[j] - u[j] == 0.0);
       }
     }
