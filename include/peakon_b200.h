@@ -115,11 +115,18 @@ int pk_step(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, doub
             int32_t* its_total, void* stream);
 
 /* Same, with HOST buffers: copies state (and dW_in) to internal device buffers, steps, copies the
- * state, dW_out and the counters back, and synchronises.  This is the call a host application
- * without device arrays makes; bench.py's "e2e" times it. */
+ * state, dW_out and the counters back, and synchronises (the realisations go through a 4-chunk
+ * H2D / kernel / D2H pipeline on internal streams; pin the host buffers).  This is the call a host
+ * application without device arrays makes; bench.py's "e2e" times it.
+ * u1 = dF = dG = NULL selects the reference's own ownership: the Newton unknown w1 = (u1, dF, dG) is
+ * internal state of the solver object there (equations.py:71,89: created as zero, never reset, never seen
+ * by simulation()), so it stays resident in the context and only u and the counters cross the bus.
+ * pk_reset_warm_start() zeroes it again (a new initial condition). */
 int pk_step_host(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
                  const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
                  int32_t* its_total);
+
+int pk_reset_warm_start(pk_ctx* ctx);
 
 /* Replaces `nsteps` passes of  Xis.update(t); equations.solve()  for scheme 'upwind', timestepping
  * 'ssprk3' (equations.py:172-185): three SSPRK3 stages of the DG1 upwind transport of m with the

@@ -25,6 +25,7 @@ struct pk_ctx {
   int last_nb, last_nblk, last_grid;   // work split of the last pk_step launch (pk_get_work_split)
   std::string err;
   // internal device buffers for the *_host entry points
+  bool w1_resident;    // pk_step_host keeps (u1, dF, dG) in d_state between calls (u1 = dF = dG = NULL mode)
   double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;
   double* d_scratch;   // diagnostics scratch [R,2,ne]
   double* d_mom;       // moments partial sums [32, 2*ne]

@@ -413,6 +413,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     c->cluster = C; c->block = Tc; c->lgTc = lg; c->smem = sm;
   }
   c->xi = c->xi_x = c->xi_xx = nullptr;
+  c->w1_resident = false;
   c->step = 0; c->d_state = nullptr; c->d_dWin = c->d_dWout = nullptr; c->d_cnt = nullptr; c->dW_cap = 0; c->d_scratch = nullptr; c->d_mom = nullptr; c->d_prof = nullptr; c->d_tab[0] = c->d_tab[1] = c->d_tab[2] = nullptr;
   c->timed = false;
   cudaError_t e = cudaSetDevice(cfg->device);
@@ -563,6 +564,12 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
   return 0;
 }
 
+extern "C" int pk_reset_warm_start(pk_ctx* c) {
+  if (!c) return -1;
+  c->w1_resident = false;
+  return 0;
+}
+
 extern "C" double pk_last_step_kernel_ms(pk_ctx* c) {
   if (!c || !c->timed) return -1.0;
   if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
@@ -575,15 +582,23 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
                             const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
                             int32_t* its_total) {
   if (!c) return -1;
-  if (!u || !u1 || !dF || !fail_step || !its_last || !its_total) return fail(c, "pk_step_host: null state/counter pointer");
+  const bool resident = (!u1 && !dF && !dG);       // w1 = (u1, dF, dG) stays in the context (see the header)
+  if (!u || !fail_step || !its_last || !its_total || (!resident && (!u1 || !dF)))
+    return fail(c, "pk_step_host: null state/counter pointer");
   CK(c, cudaSetDevice(c->cfg.device));
   const size_t R = c->cfg.R, ne = c->p.ne, fld = R * ne;
   const bool hasG = (c->p.mode == NOISE_FULL);
-  if (hasG && !dG) return fail(c, "pk_step_host: dG is required for PK_NOISE_FULL");
+  if (hasG && !dG && !resident) return fail(c, "pk_step_host: dG is required for PK_NOISE_FULL");
   if (!c->d_state) {
     CK(c, cudaMalloc(&c->d_state, sizeof(double) * 4 * fld));
     CK(c, cudaMalloc(&c->d_cnt, sizeof(int) * 3 * R));
+    c->w1_resident = false;
   }
+  if (resident && !c->w1_resident) {               // first call in this mode: w1 = 0 (equations.py:71)
+    CK(c, cudaMemset(c->d_state + fld, 0, sizeof(double) * 3 * fld));
+    c->w1_resident = true;
+  }
+  if (!resident) c->w1_resident = false;
   const size_t ndw = (size_t)nsteps * R * (size_t)c->p.nxi;
   if (ndw > c->dW_cap) {
     if (c->d_dWin) cudaFree(c->d_dWin);
@@ -613,17 +628,21 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
     cudaStream_t st = c->hs[k];
     if (dW_in && ndw && k > 0) CK(c, cudaStreamWaitEvent(st, c->hev, 0));
     CK(c, cudaMemcpyAsync(du + o, u + o, nb, cudaMemcpyHostToDevice, st));
-    CK(c, cudaMemcpyAsync(du1 + o, u1 + o, nb, cudaMemcpyHostToDevice, st));
-    CK(c, cudaMemcpyAsync(ddF + o, dF + o, nb, cudaMemcpyHostToDevice, st));
-    if (hasG) CK(c, cudaMemcpyAsync(ddG + o, dG + o, nb, cudaMemcpyHostToDevice, st));
+    if (!resident) {
+      CK(c, cudaMemcpyAsync(du1 + o, u1 + o, nb, cudaMemcpyHostToDevice, st));
+      CK(c, cudaMemcpyAsync(ddF + o, dF + o, nb, cudaMemcpyHostToDevice, st));
+      if (hasG) CK(c, cudaMemcpyAsync(ddG + o, dG + o, nb, cudaMemcpyHostToDevice, st));
+    }
     CK(c, cudaMemcpyAsync(dfs + r0, fail_step + r0, sizeof(int) * nr, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(dit + r0, its_total + r0, sizeof(int) * nr, cudaMemcpyHostToDevice, st));
     rc = launch_range(c, a, nsteps, (int)r0, (int)nr, k, st, false);
     if (rc) return rc;
     CK(c, cudaMemcpyAsync(u + o, du + o, nb, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(u1 + o, du1 + o, nb, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(dF + o, ddF + o, nb, cudaMemcpyDeviceToHost, st));
-    if (hasG) CK(c, cudaMemcpyAsync(dG + o, ddG + o, nb, cudaMemcpyDeviceToHost, st));
+    if (!resident) {
+      CK(c, cudaMemcpyAsync(u1 + o, du1 + o, nb, cudaMemcpyDeviceToHost, st));
+      CK(c, cudaMemcpyAsync(dF + o, ddF + o, nb, cudaMemcpyDeviceToHost, st));
+      if (hasG) CK(c, cudaMemcpyAsync(dG + o, ddG + o, nb, cudaMemcpyDeviceToHost, st));
+    }
     CK(c, cudaMemcpyAsync(fail_step + r0, dfs + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(its_last + r0, dil + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(its_total + r0, dit + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));

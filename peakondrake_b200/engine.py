@@ -184,13 +184,18 @@ class EnsembleIntegrator(object):
         return float(self.lib.pk_last_step_kernel_ms(self.ctx))
 
     def step_host(self, nsteps, u, u1, dF, dG, dW, fail_step, its_last, its_total, dW_out=None):
-        """pk_step_host on (pinned or pageable) host NumPy arrays, in place. Synchronous."""
+        """pk_step_host on (pinned or pageable) host NumPy arrays, in place. Synchronous.
+        u1 = dF = dG = None: the Newton warm start stays resident in the context, as it does inside the
+        reference's Equations object (equations.py:71,89); `reset_warm_start()` zeroes it."""
         if self.upwind:
             raise NotImplementedError('step_host is provided for the midpoint schemes')
         p = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)
         rc = self.lib.pk_step_host(self.ctx, int(nsteps), p(u), p(u1), p(dF), p(dG), p(dW), p(dW_out),
                                    p(fail_step), p(its_last), p(its_total))
         _lib.check(self.lib, self.ctx, rc)
+
+    def reset_warm_start(self):
+        _lib.check(self.lib, self.ctx, self.lib.pk_reset_warm_start(self.ctx))
 
     # -- diagnostics --------------------------------------------------------------------------
     def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False):

@@ -180,6 +180,34 @@ def test_host_buffer_entry_point_equals_device_path():
     assert (fs == -1).all() and (it == its_dev).all()
 
 
+def test_host_entry_point_chunk_pipeline_and_resident_warm_start():
+    """R >= 256 goes through the 4-chunk H2D / kernel / D2H pipeline; u1 = dF = dG = None keeps the Newton unknown
+    in the context (the reference's Equations object owns it, equations.py:71,89).  Two calls of 3 steps must equal
+    the device path's 6 steps bit for bit, in both modes, with Philox streams independent of the chunking."""
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    ne, Ld, dt, R, nxi = 150, 40.0, 1e-3, 300, 3
+    u0 = build_initial_u(ne, Ld, 'proper_peak')
+    eng = EnsembleIntegrator(ne, Ld, dt, R, num_Xis=nxi, sigma=0.2, seed=11)
+    eng.set_state(u0)
+    eng.step(6)
+    u_dev, w_dev = eng.u.cpu().numpy(), [t.cpu().numpy() for t in (eng.u1, eng.dF, eng.dG)]
+    its_dev = eng.its_total.cpu().numpy().copy()
+    for resident in (False, True):
+        eng.lib.pk_set_step_counter(eng.ctx, 0)
+        eng.reset_warm_start()
+        u = np.tile(u0, (R, 1)); u1 = np.zeros_like(u); dF = np.zeros_like(u); dG = np.zeros_like(u)
+        fs = np.full(R, -1, np.int32); il = np.zeros(R, np.int32); it = np.zeros(R, np.int32)
+        for _ in range(2):
+            if resident:
+                eng.step_host(3, u, None, None, None, None, fs, il, it)
+            else:
+                eng.step_host(3, u, u1, dF, dG, None, fs, il, it)
+        assert np.array_equal(u, u_dev) and (it == its_dev).all() and (fs == -1).all()
+        if not resident:
+            assert all(np.array_equal(a, b) for a, b in zip((u1, dF, dG), w_dev))
+    eng.close()
+
+
 def test_failure_latch():
     """A step SNES cannot solve latches the realisation (simulation.py:99-106): u frozen at the last
     accepted value, fail_step recorded, diagnostics NaN (outputting.py:107-108); healthy
