@@ -47,7 +47,7 @@ struct Shared {
   PK_HD void set_dw(int k, double v) const { dW[k] = v; }
 };
 
-enum { XB_SLOTS = 18 };
+enum { XB_SLOTS = 18, XB_SLOTS_PP = 32, XB_PP_BASE = 18 };   // _PP: room for a second PCR row buffer (slots 18..31)
 
 // natural row index i in [0, ne)  ->  interleaved slot j*T + t
 PK_HD int row_slot(const Params& p, int i) {
@@ -649,29 +649,30 @@ struct Thread {
 
   // write my block row (L, U, D^-1, r) to the exchange slots 0..13
   template <class SH>
-  PK_HD void reduce_publish(const Params& p, const SH& sh) {
+  PK_HD void reduce_publish(const Params& p, const SH& sh, int base = 0) {
     const int T = TN(p);
     double Di[4]; inv2(Db, Di);
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
-      sh.st(sh.xb, c * T + t, Lb[c]); sh.st(sh.xb, (4 + c) * T + t, Ub[c]); sh.st(sh.xb, (8 + c) * T + t, Di[c]);
+      sh.st(sh.xb, (base + c) * T + t, Lb[c]); sh.st(sh.xb, (base + 4 + c) * T + t, Ub[c]); sh.st(sh.xb, (base + 8 + c) * T + t, Di[c]);
     }
-    sh.st(sh.xb, 12 * T + t, rb[0]); sh.st(sh.xb, 13 * T + t, rb[1]);
+    sh.st(sh.xb, (base + 12) * T + t, rb[0]); sh.st(sh.xb, (base + 13) * T + t, rb[1]);
   }
 
   // one parallel-cyclic-reduction step with stride d (reads only)
   template <class SH>
-  PK_HD void pcr_step(const Params& p, const SH& sh, int d) {
+  // base: first exchange slot of the row buffer to read (0, or XB_PP_BASE when the rows ping-pong between two buffers)
+  PK_HD void pcr_step(const Params& p, const SH& sh, int d, int base = 0) {
     const int T = TN(p);
     const int ql = (t + T - d) & (T - 1), qr = (t + d) & (T - 1);
     double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
-      Ll[c] = sh.ld(sh.xb, c * T + ql); Ul[c] = sh.ld(sh.xb, (4 + c) * T + ql); Dl[c] = sh.ld(sh.xb, (8 + c) * T + ql);
-      Lr[c] = sh.ld(sh.xb, c * T + qr); Ur[c] = sh.ld(sh.xb, (4 + c) * T + qr); Dr[c] = sh.ld(sh.xb, (8 + c) * T + qr);
+      Ll[c] = sh.ld(sh.xb, (base + c) * T + ql); Ul[c] = sh.ld(sh.xb, (base + 4 + c) * T + ql); Dl[c] = sh.ld(sh.xb, (base + 8 + c) * T + ql);
+      Lr[c] = sh.ld(sh.xb, (base + c) * T + qr); Ur[c] = sh.ld(sh.xb, (base + 4 + c) * T + qr); Dr[c] = sh.ld(sh.xb, (base + 8 + c) * T + qr);
     }
-    rl[0] = sh.ld(sh.xb, 12 * T + ql); rl[1] = sh.ld(sh.xb, 13 * T + ql);
-    rr[0] = sh.ld(sh.xb, 12 * T + qr); rr[1] = sh.ld(sh.xb, 13 * T + qr);
+    rl[0] = sh.ld(sh.xb, (base + 12) * T + ql); rl[1] = sh.ld(sh.xb, (base + 13) * T + ql);
+    rr[0] = sh.ld(sh.xb, (base + 12) * T + qr); rr[1] = sh.ld(sh.xb, (base + 13) * T + qr);
     double al[4], ga[4];
     mm2(Lb, Dl, al); mm2(Ub, Dr, ga);
     PK_UNROLL
@@ -684,15 +685,15 @@ struct Thread {
 
   // last level: rows t and t+T/2 form a closed 2-block system
   template <class SH>
-  PK_HD void pcr_final(const Params& p, const SH& sh) {
+  PK_HD void pcr_final(const Params& p, const SH& sh, int base = 0) {
     const int T = TN(p);
     const int q = (t + T / 2) & (T - 1);
     double Lq[4], Uq[4], Dq[4], rq[2];
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
-      Lq[c] = sh.ld(sh.xb, c * T + q); Uq[c] = sh.ld(sh.xb, (4 + c) * T + q); Dq[c] = sh.ld(sh.xb, (8 + c) * T + q);
+      Lq[c] = sh.ld(sh.xb, (base + c) * T + q); Uq[c] = sh.ld(sh.xb, (base + 4 + c) * T + q); Dq[c] = sh.ld(sh.xb, (base + 8 + c) * T + q);
     }
-    rq[0] = sh.ld(sh.xb, 12 * T + q); rq[1] = sh.ld(sh.xb, 13 * T + q);
+    rq[0] = sh.ld(sh.xb, (base + 12) * T + q); rq[1] = sh.ld(sh.xb, (base + 13) * T + q);
     double S[4], Sq[4], SD[4], A[4], Ai[4], rhs[2];
     PK_UNROLL
     for (int c = 0; c < 4; ++c) { S[c] = Lb[c] + Ub[c]; Sq[c] = Lq[c] + Uq[c]; A[c] = Db[c]; }
@@ -1101,6 +1102,7 @@ PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int 
 //                      realisation: block-local thread id / count, whether the block is the cluster
 //                      leader, and the range of mesh rows the block owns
 //   one(f)             run f() once (thread 0)
+//   pingpong()         true if the exchange area has XB_SLOTS_PP slots (second PCR row buffer)
 //   hybrid(T)          true if the executor supports the compacted Schur solve for T threads per realisation:
 //   each_first(n, f)     run f on the threads t < n only (the others fall through to the next barrier)
 //   warp0_steps(n, f)    threads t < 32: for step = 0..n-1 { f(th, step); warp-level barrier }
@@ -1222,14 +1224,24 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
         ex.each([&](Th& th) { th.reduce_publish(p, sh); });
         ex.sync();
         ex.tick(6);
-        for (int d = 1; d < Tn / 2; d *= 2) {
-          ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
-          ex.sync();
-          ex.each([&](Th& th) { th.reduce_publish(p, sh); });
-          ex.sync();
+        int base = 0;
+        if (ex.pingpong()) {
+          // two row buffers: a step reads one and publishes into the other -> ONE barrier per PCR step
+          for (int d = 1; d < Tn / 2; d *= 2) {
+            ex.each([&](Th& th) { th.pcr_step(p, sh, d, base); th.reduce_publish(p, sh, XB_PP_BASE - base); });
+            ex.sync();
+            base = XB_PP_BASE - base;
+          }
+        } else {
+          for (int d = 1; d < Tn / 2; d *= 2) {
+            ex.each([&](Th& th) { th.pcr_step(p, sh, d); });
+            ex.sync();
+            ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+            ex.sync();
+          }
         }
         ex.tick(7);
-        ex.each([&](Th& th) { th.pcr_final(p, sh); });
+        ex.each([&](Th& th) { th.pcr_final(p, sh, base); });
         ex.sync();
         ex.tick(8);
       }

@@ -39,6 +39,7 @@ struct GpuExecT {
   __device__ __forceinline__ void tick(int) {}
 #endif
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
+  __device__ __forceinline__ bool pingpong() const { return false; }     // no shared memory to spare at 3 CTAs/SM
   // compacted Schur solve (pk_core.h, hyb_*): needs >= 32 threads per realisation, all of one block.  Measured
   // 12 % SLOWER than plain PCR on B200 (the serial single-warp phases stall the whole CTA; profiles/r1d_exp_variants.log),
   // so it is only compiled into -DPK_HYBRID_SCHUR experiment builds.
@@ -274,6 +275,7 @@ struct GpuExecCluster {
   __device__ __forceinline__ void tick(int) {}
   template <class F> __device__ __forceinline__ void one(F f) { if (rank == 0 && threadIdx.x == 0) f(); }
   __device__ __forceinline__ bool hybrid(int) const { return false; }     // rows are spread over the CTAs of the cluster
+  __device__ __forceinline__ bool pingpong() const { return true; }       // XB_SLOTS_PP exchange slots: one cluster barrier per PCR step
   template <class F> __device__ __forceinline__ void each_first(int, F) {}
   template <class F> __device__ __forceinline__ void warp0_steps(int, F) {}
   __device__ __forceinline__ double* area() {
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(TB, 1) pk_step_cluster_kernel(const __grid_con
   if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
   else if (PK_NOISE_OF(MODE) == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
-  sh.xb = nxt; nxt += XB_SLOTS * Tc;
+  sh.xb = nxt; nxt += XB_SLOTS_PP * Tc;
   double* red = nxt; nxt += 2 * (3 * (Tc >> 5) + 3);
   sh.dW = nxt;
 

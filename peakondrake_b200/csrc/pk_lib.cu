@@ -405,7 +405,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     if (force > 1) { C = force; Tc = p.T / C; }
     while (C > 16 && Tc < 512) { Tc *= 2; C /= 2; }
     int lg = 0; while ((1 << lg) < Tc) ++lg;
-    const size_t sm = sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)XB_SLOTS * Tc + 2 * (3 * (Tc / 32) + 3) + (p.nxi > 0 ? p.nxi : 1));
+    const size_t sm = sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)XB_SLOTS_PP * Tc + 2 * (3 * (Tc / 32) + 3) + (p.nxi > 0 ? p.nxi : 1));
     if (C < 2 || C > 16 || (C & (C - 1)) || Tc < 32 || C * Tc != p.T || sm > 227 * 1024) {
       const int ne = p.ne; delete c;
       return fail(nullptr, "pk_create: no cluster layout for ne=%d (threads %d)", ne, p.T);

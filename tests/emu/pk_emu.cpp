@@ -65,6 +65,7 @@ struct EmuExecT {
   void tick(int) {}
   template <class F> void one(F f) { f(); }
   bool hybrid(int Tn) const { return g_emu_hybrid && C == 1 && Tn >= 32; }
+  bool pingpong() const { return C > 1; }      // like the cluster kernel: XB_SLOTS_PP slots
   template <class F> void each_first(int n, F f) {
     for (int k = 0; k < n; ++k) { const int t = order == 0 ? k : n - 1 - k; cur = t / Tc; f(th[t]); }
   }
@@ -106,13 +107,13 @@ struct EmuExecT {
 template <int M, int MODE>
 static int run_one_cluster(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order, int C) {
   const int Tc = p.T / C, n = Tc * p.M;
-  std::vector<std::vector<double> > bufs(C, std::vector<double>(7 * n + XB_SLOTS * Tc + (p.nxi > 0 ? p.nxi : 1), 0.0));
+  std::vector<std::vector<double> > bufs(C, std::vector<double>(7 * n + XB_SLOTS_PP * Tc + (p.nxi > 0 ? p.nxi : 1), 0.0));
   EmuExec<M, MODE> ex(p, order, C);
   int bad = 0;
   EmuSharedCluster sh;
   double* z = (double*)0;
   sh.U0 = z; sh.U1 = z + n; sh.F = z + 2 * n; sh.G = z + 3 * n; sh.X = z + 4 * n; sh.Xx = z + 5 * n; sh.Xxx = z + 6 * n;
-  sh.xb = z + 7 * n; sh.dW = z + 7 * n + XB_SLOTS * Tc;
+  sh.xb = z + 7 * n; sh.dW = z + 7 * n + XB_SLOTS_PP * Tc;
   sh.bufs = &bufs; sh.Tc = Tc; sh.nxi_ = p.nxi; sh.cur = &ex.cur; sh.bad = &bad;
   sh.lgTc = 0; while ((1 << sh.lgTc) < Tc) ++sh.lgTc;
   sh.lgT = 0; while ((1 << sh.lgT) < p.T) ++sh.lgT;
