@@ -43,6 +43,10 @@ struct Shared {
   // flat index i = j*T + t (row j of chunk t).  One CTA per realisation: plain shared memory.
   PK_HD double ld(const double* a, int i) const { return a[i]; }
   PK_HD void st(double* a, int i, double v) const { a[i] = v; }
+  // slot j of the CALLING thread t (T threads per realisation): same flat index here; the cluster variant turns
+  // it into a block-local address without decoding (pk_kernels.cuh, SharedCluster)
+  PK_HD double ldo(const double* a, int j, int T, int t) const { return a[j * T + t]; }
+  PK_HD void sto(double* a, int j, int T, int t, double v) const { a[j * T + t] = v; }
   PK_HD double dw(int k) const { return dW[k]; }
   PK_HD void set_dw(int k, double v) const { dW[k] = v; }
 };
@@ -273,16 +277,22 @@ struct Thread {
     return j < 0 ? (ml - 1) * TN(p) + tl : ((j < M - 1 || (j == M - 1 && ext)) ? j * TN(p) + t : tr);
   }
 
+  // field value at node j of my chunk (j in [-1, m]): own rows through the block-local accessor, the two halo
+  // nodes (last row of the left chunk, first row of the right chunk) through the generic one
+  PK_HD bool own_node(int j) const { return j >= 0 && (j < M - 1 || (j == M - 1 && ext)); }
+  template <class SH>
+  PK_HD double ldn(const Params& p, const SH& sh, const double* a, int j) const {
+    return own_node(j) ? sh.ldo(a, j, TN(p), t) : sh.ld(a, nidx(p, j));
+  }
   template <class SH>
   PK_HD void load_node(const Params& p, const SH& sh, int j, NodeS& n) const {
-    const int i = nidx(p, j);
-    const double u0 = sh.ld(sh.U0, i), u1 = sh.ld(sh.U1, i);
+    const double u0 = ldn(p, sh, sh.U0, j), u1 = ldn(p, sh, sh.U1, j);
     n.a = 0.5 * (u1 + u0);
     n.w = u1 - u0;                       // + dG below (NOISE_FULL): R_psi = M (u1 - u + dG) + ...
-    n.F = PK_IS_TEST(MODE) ? 0.0 : sh.ld(sh.F, i);
-    if (MODE == NOISE_FULL) { n.G = sh.ld(sh.G, i); n.x = sh.ld(sh.Xx, i); n.y = sh.ld(sh.Xxx, i); n.w += n.G; }
+    n.F = PK_IS_TEST(MODE) ? 0.0 : ldn(p, sh, sh.F, j);
+    if (MODE == NOISE_FULL) { n.G = ldn(p, sh, sh.G, j); n.x = ldn(p, sh, sh.Xx, j); n.y = ldn(p, sh, sh.Xxx, j); n.w += n.G; }
     else { n.G = 0.0; n.x = 0.0; n.y = 0.0; }
-    const double X = (PK_NOISE_OF(MODE) == NOISE_SCALAR) ? Xs : sh.ld(sh.X, i);
+    const double X = (PK_NOISE_OF(MODE) == NOISE_SCALAR) ? Xs : ldn(p, sh, sh.X, j);
     n.v = p.dt * n.a + X;
   }
 
@@ -388,8 +398,8 @@ struct Thread {
       sp0[0] = p.hm2; sp0[1] = k.C0[0]; sp0[2] = k.C0[1]; sp0[3] = k.C0[2]; sp0[4] = p.hm2;
       sb0 = -k.Q0;
       // publish what the left neighbour's last row needs from my first node
-      sh.st(sh.xb, 14 * TN(p) + t, k.Cp[0]); sh.st(sh.xb, 15 * TN(p) + t, k.Cp[1]); sh.st(sh.xb, 16 * TN(p) + t, k.Cp[2]);
-      sh.st(sh.xb, 17 * TN(p) + t, k.Qp);
+      sh.sto(sh.xb, 14, TN(p), t, k.Cp[0]); sh.sto(sh.xb, 15, TN(p), t, k.Cp[1]); sh.sto(sh.xb, 16, TN(p), t, k.Cp[2]);
+      sh.sto(sh.xb, 17, TN(p), t, k.Qp);
     } else {
       finish_row(p, n - 1, k.Cp, k.Qp);
     }
@@ -402,7 +412,7 @@ struct Thread {
   // solution increment of my row j: registers (du[]) or, FS, exchange slot j (free between the PCR and the update)
   template <class SH>
   PK_HD double get_du(const Params& p, const SH& sh, int j) const {
-    if (FS) return sh.ld(sh.xb, j * TN(p) + t);
+    if (FS) return sh.ldo(sh.xb, j, TN(p), t);
     return du[j < M ? j : M - 1];
   }
 
@@ -496,8 +506,8 @@ struct Thread {
     cp[0] = sh.ld(sh.xb, 14 * TN(p) + tr); cp[1] = sh.ld(sh.xb, 15 * TN(p) + tr); cp[2] = sh.ld(sh.xb, 16 * TN(p) + tr);
     const double qp = sh.ld(sh.xb, 17 * TN(p) + tr);
     finish_row_fs(p, sh, m - 1, cp, qp);
-    sh.st(sh.xb, 10 * TN(p) + t, wCm1[0]); sh.st(sh.xb, 11 * TN(p) + t, wCm1[1]); sh.st(sh.xb, 12 * TN(p) + t, wCm1[2]);
-    sh.st(sh.xb, 13 * TN(p) + t, wQm1);
+    sh.sto(sh.xb, 10, TN(p), t, wCm1[0]); sh.sto(sh.xb, 11, TN(p), t, wCm1[1]); sh.sto(sh.xb, 12, TN(p), t, wCm1[2]);
+    sh.sto(sh.xb, 13, TN(p), t, wQm1);
     if (!FS) { tips_registers(p, sh); return; }
 
     // tips: back-substitute the five columns (y, W1, W2, V1, V2) through the interior rows
@@ -523,11 +533,11 @@ struct Thread {
         if (k == 0) F2a[c] = x;
       }
     }
-    sh.st(sh.xb, 0 * TN(p) + t, L2a[0]); sh.st(sh.xb, 1 * TN(p) + t, L2b[0]);
-    sh.st(sh.xb, 2 * TN(p) + t, L2a[1]); sh.st(sh.xb, 3 * TN(p) + t, L2a[2]);
-    sh.st(sh.xb, 4 * TN(p) + t, L2b[1]); sh.st(sh.xb, 5 * TN(p) + t, L2b[2]);
-    sh.st(sh.xb, 6 * TN(p) + t, L2a[3]); sh.st(sh.xb, 7 * TN(p) + t, L2a[4]);
-    sh.st(sh.xb, 8 * TN(p) + t, L2b[3]); sh.st(sh.xb, 9 * TN(p) + t, L2b[4]);
+    sh.sto(sh.xb, 0, TN(p), t, L2a[0]); sh.sto(sh.xb, 1, TN(p), t, L2b[0]);
+    sh.sto(sh.xb, 2, TN(p), t, L2a[1]); sh.sto(sh.xb, 3, TN(p), t, L2a[2]);
+    sh.sto(sh.xb, 4, TN(p), t, L2b[1]); sh.sto(sh.xb, 5, TN(p), t, L2b[2]);
+    sh.sto(sh.xb, 6, TN(p), t, L2a[3]); sh.sto(sh.xb, 7, TN(p), t, L2a[4]);
+    sh.sto(sh.xb, 8, TN(p), t, L2b[3]); sh.sto(sh.xb, 9, TN(p), t, L2b[4]);
   }
 
   // interior solution with known separators; the increment of row j goes to exchange slot j
@@ -536,7 +546,7 @@ struct Thread {
     const int T = TN(p);
     const int nI = m - 2;
     double xp1 = sh.ld(sh.xb, 14 * T + tr), xp2 = sh.ld(sh.xb, 15 * T + tr);
-    sh.st(sh.xb, 0 * T + t, xs0); sh.st(sh.xb, 1 * T + t, xs1);
+    sh.sto(sh.xb, 0, T, t, xs0); sh.sto(sh.xb, 1, T, t, xs1);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -544,8 +554,8 @@ struct Thread {
       const double z = sh.ld(sh.fac, fidx(p, 3, k)) - sh.ld(sh.fac, fidx(p, 4, k)) * xs0 - sh.ld(sh.fac, fidx(p, 5, k)) * xs1;
       const double x = sh.ld(sh.fac, fidx(p, 0, k)) * (z - sh.ld(sh.fac, fidx(p, 1, k)) * xp1 - sh.ld(sh.fac, fidx(p, 2, k)) * xp2);
       xp2 = xp1; xp1 = x;
-      sh.st(sh.xb, (k + 2) * T + t, x);
-      if (k == nI - 1) sh.st(sh.xb, 16 * T + t, x);     // my last row, for the right neighbour
+      sh.sto(sh.xb, (k + 2), T, t, x);
+      if (k == nI - 1) sh.sto(sh.xb, 16, T, t, x);     // my last row, for the right neighbour
     }
   }
 
@@ -578,8 +588,8 @@ struct Thread {
     const double qp = sh.ld(sh.xb, 17 * TN(p) + tr);
     if (ext) finish_row(p, M - 1, cp, qp); else finish_row(p, M - 2, cp, qp);
     // publish my last node's Cm,Qm for the right neighbour's separator row 0
-    sh.st(sh.xb, 10 * TN(p) + t, wCm1[0]); sh.st(sh.xb, 11 * TN(p) + t, wCm1[1]); sh.st(sh.xb, 12 * TN(p) + t, wCm1[2]);
-    sh.st(sh.xb, 13 * TN(p) + t, wQm1);
+    sh.sto(sh.xb, 10, TN(p), t, wCm1[0]); sh.sto(sh.xb, 11, TN(p), t, wCm1[1]); sh.sto(sh.xb, 12, TN(p), t, wCm1[2]);
+    sh.sto(sh.xb, 13, TN(p), t, wQm1);
 
     tips_registers(p, sh);
   }
@@ -615,11 +625,11 @@ struct Thread {
     PK_UNROLL
     for (int c = 0; c < 5; ++c) { L2b[c] = ext ? xa[c] : xb_[c]; L2a[c] = ext ? xb_[c] : xc[c]; }
     // slots 0..9: tips at the LAST two interior rows, read by the right neighbour
-    sh.st(sh.xb, 0 * TN(p) + t, L2a[0]); sh.st(sh.xb, 1 * TN(p) + t, L2b[0]);
-    sh.st(sh.xb, 2 * TN(p) + t, L2a[1]); sh.st(sh.xb, 3 * TN(p) + t, L2a[2]);
-    sh.st(sh.xb, 4 * TN(p) + t, L2b[1]); sh.st(sh.xb, 5 * TN(p) + t, L2b[2]);
-    sh.st(sh.xb, 6 * TN(p) + t, L2a[3]); sh.st(sh.xb, 7 * TN(p) + t, L2a[4]);
-    sh.st(sh.xb, 8 * TN(p) + t, L2b[3]); sh.st(sh.xb, 9 * TN(p) + t, L2b[4]);
+    sh.sto(sh.xb, 0, TN(p), t, L2a[0]); sh.sto(sh.xb, 1, TN(p), t, L2b[0]);
+    sh.sto(sh.xb, 2, TN(p), t, L2a[1]); sh.sto(sh.xb, 3, TN(p), t, L2a[2]);
+    sh.sto(sh.xb, 4, TN(p), t, L2b[1]); sh.sto(sh.xb, 5, TN(p), t, L2b[2]);
+    sh.sto(sh.xb, 6, TN(p), t, L2a[3]); sh.sto(sh.xb, 7, TN(p), t, L2a[4]);
+    sh.sto(sh.xb, 8, TN(p), t, L2b[3]); sh.sto(sh.xb, 9, TN(p), t, L2b[4]);
   }
 
   // ---- phase B1: build the reduced (Schur) block row of my separator pair -------------------
@@ -654,9 +664,9 @@ struct Thread {
     double Di[4]; inv2(Db, Di);
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
-      sh.st(sh.xb, (base + c) * T + t, Lb[c]); sh.st(sh.xb, (base + 4 + c) * T + t, Ub[c]); sh.st(sh.xb, (base + 8 + c) * T + t, Di[c]);
+      sh.sto(sh.xb, (base + c), T, t, Lb[c]); sh.sto(sh.xb, (base + 4 + c), T, t, Ub[c]); sh.sto(sh.xb, (base + 8 + c), T, t, Di[c]);
     }
-    sh.st(sh.xb, (base + 12) * T + t, rb[0]); sh.st(sh.xb, (base + 13) * T + t, rb[1]);
+    sh.sto(sh.xb, (base + 12), T, t, rb[0]); sh.sto(sh.xb, (base + 13), T, t, rb[1]);
   }
 
   // one parallel-cyclic-reduction step with stride d (reads only)
@@ -706,7 +716,7 @@ struct Thread {
     inv2(A, Ai);
     xs0 = Ai[0] * rhs[0] + Ai[1] * rhs[1];
     xs1 = Ai[2] * rhs[0] + Ai[3] * rhs[1];
-    sh.st(sh.xb, 14 * T + t, xs0); sh.st(sh.xb, 15 * T + t, xs1);
+    sh.sto(sh.xb, 14, T, t, xs0); sh.sto(sh.xb, 15, T, t, xs1);
   }
 
   // =========== hybrid Schur solve: cyclic reduction down to 32 block rows, PCR inside ONE warp, back-substitution ===========
@@ -851,7 +861,7 @@ struct Thread {
         du[k + 2] = 0.0;
       }
     }
-    sh.st(sh.xb, 16 * T + t, ext ? du[M - 1] : du[M - 2]);   // my last row, for the right neighbour
+    sh.sto(sh.xb, 16, T, t, ext ? du[M - 1] : du[M - 2]);   // my last row, for the right neighbour
   }
 
   // ---- phase D1: Helmholtz right-hand sides f + f'/2 du, g + g'/2 du; causal local pass ------
@@ -865,9 +875,8 @@ struct Thread {
     const int T = TN(p);
     double a0, s0, b0, x0 = 0.0, y0 = 0.0;
     {
-      const int i = nidx(p, -1);
-      a0 = 0.5 * (sh.ld(sh.U0, i) + sh.ld(sh.U1, i));
-      if (MODE == NOISE_FULL) { x0 = sh.ld(sh.Xx, i); y0 = sh.ld(sh.Xxx, i); }
+      a0 = 0.5 * (ldn(p, sh, sh.U0, -1) + ldn(p, sh, sh.U1, -1));
+      if (MODE == NOISE_FULL) { x0 = ldn(p, sh, sh.Xx, -1); y0 = ldn(p, sh, sh.Xxx, -1); }
       const double d0 = sh.ld(sh.xb, 16 * T + tl);          // increment of the left neighbour's last row
       s0 = a0 + d0; b0 = a0 + 0.5 * d0;
     }
@@ -877,10 +886,9 @@ struct Thread {
     PK_UNROLL
     for (int q = 0; q <= M; ++q) {
       if (q < M || ext) {
-        const int i = nidx(p, q);
-        const double a1 = 0.5 * (sh.ld(sh.U0, i) + sh.ld(sh.U1, i));
+        const double a1 = 0.5 * (ldn(p, sh, sh.U0, q) + ldn(p, sh, sh.U1, q));
         double x1 = 0.0, y1 = 0.0;
-        if (MODE == NOISE_FULL) { x1 = sh.ld(sh.Xx, i); y1 = sh.ld(sh.Xxx, i); }
+        if (MODE == NOISE_FULL) { x1 = ldn(p, sh, sh.Xx, q); y1 = ldn(p, sh, sh.Xxx, q); }
         const double d1 = (q < M - 1 || (q == M - 1 && ext)) ? get_du(p, sh, q) : sh.ld(sh.xb, 14 * T + tr);
         const double s1 = a1 + d1, b1 = a1 + 0.5 * d1;      // uh + du and uh + e at the right node of the cell
         const double ss = s0 + s1;
@@ -937,17 +945,17 @@ struct Thread {
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       if (has_row(j)) {
-        const int i = idx(p, j);
+        const int T = TN(p);
         const double duj = get_du(p, sh, j);
-        const double u1n = sh.ld(sh.U1, i) + duj;
+        const double u1n = sh.ldo(sh.U1, j, T, t) + duj;
         const double Fn = hF[j] + pwv[j] * inF;
-        const double dFv = Fn - sh.ld(sh.F, i);
-        sh.st(sh.U1, i, u1n); sh.st(sh.F, i, Fn);
+        const double dFv = Fn - sh.ldo(sh.F, j, T, t);
+        sh.sto(sh.U1, j, T, t, u1n); sh.sto(sh.F, j, T, t, Fn);
         sn2 = dFv * dFv + (duj * duj + sn2); xn2 = Fn * Fn + (u1n * u1n + xn2);     // accumulation chains (FMAs)
         if (MODE == NOISE_FULL) {
           const double Gn = hG[j] + pwv[j] * inG;
-          const double dGv = Gn - sh.ld(sh.G, i);
-          sh.st(sh.G, i, Gn);
+          const double dGv = Gn - sh.ldo(sh.G, j, T, t);
+          sh.sto(sh.G, j, T, t, Gn);
           sn2 = dGv * dGv + sn2; xn2 = Gn * Gn + xn2;
         }
       }
@@ -961,10 +969,9 @@ struct Thread {
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       if (has_row(j)) {
-        const int i = idx(p, j);
         const double duj = get_du(p, sh, j);
-        const double u1n = sh.ld(sh.U1, i) + duj;
-        sh.st(sh.U1, i, u1n);
+        const double u1n = sh.ldo(sh.U1, j, TN(p), t) + duj;
+        sh.sto(sh.U1, j, TN(p), t, u1n);
         sn2 = duj * duj + sn2; xn2 = u1n * u1n + xn2;
       }
     }
@@ -975,7 +982,7 @@ struct Thread {
   PK_HD void accept(const Params& p, const SH& sh) {
     PK_UNROLL
     for (int j = 0; j < M; ++j)
-      if (has_row(j)) { const int i = idx(p, j); sh.st(sh.U0, i, sh.ld(sh.U1, i)); }
+      if (has_row(j)) sh.sto(sh.U0, j, TN(p), t, sh.ldo(sh.U1, j, TN(p), t));
   }
 
   // ---- noise fields of this step: dXi = sum_k dW_k xi_k etc. (stochastic_functions.py:229-234) ----
@@ -1004,8 +1011,8 @@ struct Thread {
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       if (has_row(j)) {
-        sh.st(sh.X, j * T + t, X[j]);
-        if (MODE == NOISE_FULL) { sh.st(sh.Xx, j * T + t, Xx[j]); sh.st(sh.Xxx, j * T + t, Xxx[j]); }
+        sh.sto(sh.X, j, T, t, X[j]);
+        if (MODE == NOISE_FULL) { sh.sto(sh.Xx, j, T, t, Xx[j]); sh.sto(sh.Xxx, j, T, t, Xxx[j]); }
       }
     }
   }

@@ -256,6 +256,9 @@ struct SharedCluster {
     const int tg = i & ((1 << lgT) - 1), j = i >> lgT;
     a[(j << lgTc) + (tg & (Tc - 1))] = v;
   }
+  // slot j of the calling thread: block-local, no decoding of the flat index (most accesses are of this kind)
+  __device__ __forceinline__ double ldo(const double* a, int j, int, int) const { return a[(j << lgTc) + (int)threadIdx.x]; }
+  __device__ __forceinline__ void sto(double* a, int j, int, int, double v) const { a[(j << lgTc) + (int)threadIdx.x] = v; }
   __device__ __forceinline__ double dw(int k) const { return dW[k]; }
   __device__ __forceinline__ void set_dw(int k, double v) const { dW[k] = v; }
 };

@@ -36,6 +36,9 @@ struct EmuSharedCluster {
   }
   double ld(const double* a, int i) const { return *at(a, i, false); }
   void st(double* a, int i, double v) const { *at(a, i, true) = v; }
+  // own-slot accessors: must be block-local (checked like the device's sto/ldo, which do not decode)
+  double ldo(const double* a, int j, int T, int t) const { if (((t & ((1 << lgT) - 1)) >> lgTc) != *cur) ++*bad; return *at(a, j * T + t, false); }
+  void sto(double* a, int j, int T, int t, double v) const { *at(a, j * T + t, true) = v; }
   double dw(int k) const { return (*bufs)[*cur][(dW - (double*)0) + k]; }
   void set_dw(int k, double v) const { (*bufs)[*cur][(dW - (double*)0) + k] = v; }
 };
