@@ -51,7 +51,8 @@ struct Shared {
   PK_HD void set_dw(int k, double v) const { dW[k] = v; }
 };
 
-enum { XB_SLOTS = 18, XB_SLOTS_PP = 32, XB_PP_BASE = 18 };   // _PP: room for a second PCR row buffer (slots 18..31)
+enum { XB_SLOTS = 18, XB_SLOTS_PP = 30, XB_PP_BASE = 16 };   // _PP: room for a second PCR row buffer (slots 16..29;
+                                                             // 16, 17 are dead while the PCR runs, 14, 15 receive its result)
 
 // natural row index i in [0, ne)  ->  interleaved slot j*T + t
 PK_HD int row_slot(const Params& p, int i) {

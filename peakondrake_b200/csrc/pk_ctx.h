@@ -16,6 +16,7 @@ struct pk_ctx {
   int block;
   int cluster;         // CTAs per realisation (1 = single-CTA kernel)
   int lgTc;
+  int cminb;           // resident CTAs/SM the cluster kernel is compiled for (2: two clusters share their SMs)
   int fs;              // 1: FS variant of the single-CTA step kernel (factors in shared memory, rolled row loops)
   int slots;           // CTAs of the single-CTA step kernel resident at once (persistent grid), 0 = other kernel
   int sms;             // multiprocessors of the device

@@ -8,7 +8,7 @@ kern_t pk_pick_kernel_m5(int mode, int block, int T, int minb);
 kern_t pk_pick_kernel_m6(int mode, int block, int T, int minb);
 kern_t pk_pick_kernel_m7(int mode, int block, int T, int minb);
 kern_t pk_pick_kernel_m8(int mode, int block, int T, int minb);
-ckern_t pk_pick_cluster_kernel_m5(int mode, int Tc);
-ckern_t pk_pick_cluster_kernel_m6(int mode, int Tc);
-ckern_t pk_pick_cluster_kernel_m7(int mode, int Tc);
-ckern_t pk_pick_cluster_kernel_m8(int mode, int Tc);
+ckern_t pk_pick_cluster_kernel_m5(int mode, int Tc, int minb);
+ckern_t pk_pick_cluster_kernel_m6(int mode, int Tc, int minb);
+ckern_t pk_pick_cluster_kernel_m7(int mode, int Tc, int minb);
+ckern_t pk_pick_cluster_kernel_m8(int mode, int Tc, int minb);

@@ -377,8 +377,8 @@ struct GpuExecCluster {
   }
 };
 
-template <int M, int MODE, int TB>
-__global__ void __launch_bounds__(TB, 1) pk_step_cluster_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a, int lgTc) {
+template <int M, int MODE, int TB, int MINB = 1>
+__global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a, int lgTc) {
   extern __shared__ __align__(16) double smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), C = cluster.num_blocks();

@@ -7,9 +7,11 @@
 #endif
 
 
-template <int M> static ckern_t pick_cmode(int mode, int Tc) {
+template <int M> static ckern_t pick_cmode(int mode, int Tc, int minb) {
   if (PK_IS_TEST(mode)) return nullptr;      // scheme 'test': single-CTA meshes only
   if (Tc <= 256) {
+    // two clusters share the SMs when two CTAs fit one SM's shared memory (128 registers per thread)
+    if (minb == 2 && mode == NOISE_SCALAR) return pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2>;
     switch (mode) {
       case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 256>;
       case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 256>;
@@ -54,4 +56,4 @@ template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {
 #define PK_CAT2(a, b) a##b
 #define PK_CAT(a, b) PK_CAT2(a, b)
 kern_t PK_CAT(pk_pick_kernel_m, PK_M)(int mode, int block, int T, int minb) { return pick_mode<PK_M>(mode, block, T, minb); }
-ckern_t PK_CAT(pk_pick_cluster_kernel_m, PK_M)(int mode, int Tc) { return pick_cmode<PK_M>(mode, Tc); }
+ckern_t PK_CAT(pk_pick_cluster_kernel_m, PK_M)(int mode, int Tc, int minb) { return pick_cmode<PK_M>(mode, Tc, minb); }

@@ -328,12 +328,12 @@ static void choose_blocks(int R, int K, int S, int* nb_out, int* nblk_out) {
   }
   *nb_out = bnb; *nblk_out = bblk;
 }
-static ckern_t pick_cluster_kernel(const Params& p, int Tc) {
+static ckern_t pick_cluster_kernel(const Params& p, int Tc, int minb) {
   switch (p.M) {
-    case 5: return pk_pick_cluster_kernel_m5(p.mode, Tc);
-    case 6: return pk_pick_cluster_kernel_m6(p.mode, Tc);
-    case 7: return pk_pick_cluster_kernel_m7(p.mode, Tc);
-    case 8: return pk_pick_cluster_kernel_m8(p.mode, Tc);
+    case 5: return pk_pick_cluster_kernel_m5(p.mode, Tc, minb);
+    case 6: return pk_pick_cluster_kernel_m6(p.mode, Tc, minb);
+    case 7: return pk_pick_cluster_kernel_m7(p.mode, Tc, minb);
+    case 8: return pk_pick_cluster_kernel_m8(p.mode, Tc, minb);
   }
   return nullptr;
 }
@@ -382,7 +382,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->block = p.T < 32 ? 32 : p.T;
   c->cluster = 1; c->lgTc = 0;
   c->smem = sizeof(double) * ((size_t)narr * p.T * p.M + (size_t)XB_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1));
-  c->fs = 0;
+  c->fs = 0; c->cminb = 1;
   { const char* e = getenv("PK_FS"); const int want = e ? atoi(e) : 0;
     if (want && cfg->scheme != 1 && p.T == 128) {      // FS variant: + level-1 factors in shared memory
       c->fs = (want == 1 || want == 2 || want == 4 || want == 6 || want == 7) ? want : 1;     // needs a -DPK_EXPERIMENTAL_VARIANTS build
@@ -411,6 +411,19 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
       return fail(nullptr, "pk_create: no cluster layout for ne=%d (threads %d)", ne, p.T);
     }
     c->cluster = C; c->block = Tc; c->lgTc = lg; c->smem = sm;
+    // two CTAs per SM (two clusters interleaved on the same SMs) when the shared memory allows it
+    c->cminb = 1;
+    if (Tc == 256 && p.mode == NOISE_SCALAR && 2 * (sm + 1024) <= 227 * 1024) {
+      // does the 128-register variant really get two CTAs per SM?
+      cudaSetDevice(cfg->device);
+      const void* k2 = (const void*)pick_cluster_kernel(p, Tc, 2);
+      int per_sm = 0;
+      if (k2 && cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, Tc, sm) == cudaSuccess && per_sm >= 2)
+        c->cminb = 2;
+      cudaGetLastError();
+    }
+    { const char* e = getenv("PK_CLUSTER_MINB"); if (e && atoi(e) == 1) c->cminb = 1; }
   }
   c->xi = c->xi_x = c->xi_xx = nullptr;
   c->w1_resident = false;
@@ -418,7 +431,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->timed = false;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
-  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block) : (const void*)pick_kernel(p, c->block, c->fs);
+  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block, c->cminb) : (const void*)pick_kernel(p, c->block, c->fs);
   if (!k) { delete c; return fail(nullptr, "pk_create: no kernel for this layout"); }
   if (c->cluster > 8) cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   e = cfg->scheme == 1 ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
@@ -513,7 +526,7 @@ static int launch_range(pk_ctx* c, StepArgs a, int nsteps, int r0, int nr, int s
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    CK(c, cudaLaunchKernelEx(&lc, pick_cluster_kernel(c->p, c->block), c->p, a, c->lgTc));
+    CK(c, cudaLaunchKernelEx(&lc, pick_cluster_kernel(c->p, c->block, c->cminb), c->p, a, c->lgTc));
   } else {
     const int R = c->cfg.R;
     if (!c->d_queue) CK(c, cudaMalloc(&c->d_queue, sizeof(int) * (size_t)(R + 1) * PK_HOST_CHUNKS));
@@ -740,7 +753,7 @@ extern "C" int pk_profile_enable(pk_ctx* c) {
 kern_t pk_pick_kernel_m5(int, int, int, int) { return nullptr; }
 kern_t pk_pick_kernel_m6(int, int, int, int) { return nullptr; }
 kern_t pk_pick_kernel_m7(int, int, int, int) { return nullptr; }
-ckern_t pk_pick_cluster_kernel_m5(int, int) { return nullptr; }
-ckern_t pk_pick_cluster_kernel_m6(int, int) { return nullptr; }
-ckern_t pk_pick_cluster_kernel_m7(int, int) { return nullptr; }
+ckern_t pk_pick_cluster_kernel_m5(int, int, int) { return nullptr; }
+ckern_t pk_pick_cluster_kernel_m6(int, int, int) { return nullptr; }
+ckern_t pk_pick_cluster_kernel_m7(int, int, int) { return nullptr; }
 #endif

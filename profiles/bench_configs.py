@@ -14,8 +14,8 @@ HBM = 6465.2e9
 CASES = [
     dict(name='C2 ne=1000 4 sines', ne=1000, R=1024, K=50, dt=1e-3, fam='sines', nxi=4, sigma=0.2, ic='proper_peak'),
     dict(name='C3 ne=2000 4 sines', ne=2000, R=592, K=20, dt=1e-3, fam='sines', nxi=4, sigma=0.2, ic='periodic_peakon'),
-    dict(name='C4 ne=16384 constant', ne=16384, R=72, K=10, dt=5e-4, fam='constant', nxi=1, sigma=0.2, ic='new_peak'),
-    dict(name='C5 ne=20000 constant sigma=1', ne=20000, R=36, K=10, dt=1e-3, fam='constant', nxi=1, sigma=1.0, ic='periodic_peakon'),
+    dict(name='C4 ne=16384 constant', ne=16384, R=144, K=10, dt=5e-4, fam='constant', nxi=1, sigma=0.2, ic='new_peak'),
+    dict(name='C5 ne=20000 constant sigma=1', ne=20000, R=72, K=10, dt=1e-3, fam='constant', nxi=1, sigma=1.0, ic='periodic_peakon'),
     dict(name='ne=1000 deterministic (C1)', ne=1000, R=1024, K=50, dt=1e-3, fam='sines', nxi=1, sigma=0.0, ic='one_peak'),
 ]
 CASES += [
