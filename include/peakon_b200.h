@@ -170,6 +170,17 @@ int pk_diagnostics(pk_ctx* ctx, const double* u, const double* pq, int32_t perio
 int pk_peakon_suite(pk_ctx* ctx, const double* u, const int32_t* idx, const int32_t* fail_step,
                     double* vals, int32_t* ids, void* stream);
 
+/* Replaces find_mus (outputting.py:260-370), the `mu` diagnostic, for every realisation: peaks = + -> - sign changes
+ * of the DG0 slope whose CG1 value exceeds twice the mean of u; per peak zone the distance between the maximum and
+ * the minimum slope (mu) and between the peak and the minimum slope (alt_mu), four highest peaks only; the quirks of
+ * the reference are kept as written (bit-equal to the reference helper on its golden vectors).
+ *   x_cells [ne]  DG0 coordinate array (cell centres), device memory; coordinates are looked up, never recomputed
+ *   out [R,8]     mu_0..3, alt_mu_0..3 (NaN where the reference's lists are shorter or the realisation has failed)
+ *   status [R]    number of peaks (>= 0); -1: more peaks than the device routine holds, -2: the reference itself
+ *                 would raise for this field (run the host routine for that realisation), -3: failed realisation */
+int pk_mu(pk_ctx* ctx, const double* u, const double* x_cells, const int32_t* fail_step, double* out,
+          int32_t* status, void* stream);
+
 /* Ensemble statistics for one dump (the quantities the reference accumulates across seeds off-line:
  * running mean of u, experiment.py:224-227; histograms plotted by plotting/plot_stochastic_histograms.py:61-67).
  *   diag/idx: outputs of pk_diagnostics for the same state

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(256) pk_moments_final(const double* __restrict
 // host side
 // ------------------------------------------------------------------------------------------------
 #include "pk_ctx.h"
+#include "pk_mu.h"
 
 std::string g_create_err;
 int pk_fail(pk_ctx* c, const char* fmt, ...) {
@@ -721,6 +722,52 @@ extern "C" int pk_peakon_suite(pk_ctx* c, const double* u, const int32_t* idx, c
   if (!u || !idx || !vals || !ids) return fail(c, "pk_peakon_suite: null pointer");
   CK(c, cudaSetDevice(c->cfg.device));
   pk_peakon_suite_kernel<<<c->cfg.R, 128, 0, (cudaStream_t)stream>>>(u, idx, fail_step, c->p.ne, c->p.h, vals, ids);
+  CK(c, cudaGetLastError());
+  return 0;
+}
+
+// ---- mu diagnostic (find_mus, outputting.py:260-370): one realisation per block, the serial reference logic run by
+// thread 0 on shared-memory copies of u and du (global memory when the mesh does not fit) -- pk_mu.h
+__global__ void pk_mu_kernel(const double* __restrict__ u, const double* __restrict__ x, const int32_t* __restrict__ fail_step,
+                             int ne, double h, double Ld, int use_smem, double* __restrict__ du_scratch,
+                             double* __restrict__ out, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) double mu_smem[];
+  const int r = blockIdx.x;
+  const double* ur = u + (size_t)r * ne;
+  double* su = use_smem ? mu_smem : nullptr;
+  double* sdu = use_smem ? mu_smem + ne : du_scratch + (size_t)r * ne;
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    const int ip = (i + 1 == ne) ? 0 : i + 1;
+    const double u0 = ur[i];
+    if (su) su[i] = u0;
+    sdu[i] = (ur[ip] - u0) / h;              // DG0 slope, the expression of pk_diag_kernel
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double old4[4], alt4[4];
+    int rc = -3;
+    if (fail_step && fail_step[r] >= 0) {
+      for (int j = 0; j < 4; ++j) { old4[j] = pk::nan_value(); alt4[j] = pk::nan_value(); }
+    } else {
+      rc = pk::mu_serial(su ? su : ur, sdu, x, ne, Ld, old4, alt4);
+    }
+    for (int j = 0; j < 4; ++j) { out[(size_t)r * 8 + j] = old4[j]; out[(size_t)r * 8 + 4 + j] = alt4[j]; }
+    status[r] = rc;
+  }
+}
+
+extern "C" int pk_mu(pk_ctx* c, const double* u, const double* x_cells, const int32_t* fail_step,
+                     double* out, int32_t* status, void* stream) {
+  if (!c) return -1;
+  if (!u || !x_cells || !out || !status) return fail(c, "pk_mu: null pointer");
+  CK(c, cudaSetDevice(c->cfg.device));
+  const int ne = c->p.ne, R = c->cfg.R;
+  const size_t sm = sizeof(double) * 2 * (size_t)ne;
+  const int use_smem = sm <= 200 * 1024;
+  if (!use_smem && !c->d_scratch) CK(c, cudaMalloc(&c->d_scratch, sizeof(double) * 2 * (size_t)R * ne));
+  if (use_smem && sm > 48 * 1024) CK(c, cudaFuncSetAttribute(pk_mu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  pk_mu_kernel<<<R, 128, use_smem ? sm : 0, (cudaStream_t)stream>>>(u, x_cells, fail_step, ne, c->p.h, c->cfg.Ld, use_smem,
+                                                                    c->d_scratch, out, status);
   CK(c, cudaGetLastError());
   return 0;
 }

@@ -220,6 +220,19 @@ class EnsembleIntegrator(object):
         self._keep_d = pq_dev
         return self.diag, self.didx, du
 
+    def mu(self):
+        """The `mu` diagnostic (find_mus, outputting.py:260-370) on the device: ([R, 8] mu_0..3, alt_mu_0..3; [R] status)."""
+        if getattr(self, '_x_cells', None) is None:
+            xc = (np.arange(self.ne) + 0.5) * (self.Ld / self.ne)          # DiagnosticVariables.coords (simulation.py:265)
+            self._x_cells = torch.from_numpy(xc).to(self.device)
+            self._mu_out = torch.empty(self.R, 8, dtype=torch.float64, device=self.device)
+            self._mu_status = torch.empty(self.R, dtype=torch.int32, device=self.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.pk_mu(self.ctx, _ptr(self.u), _ptr(self._x_cells), _ptr(self.fail_step), _ptr(self._mu_out),
+                            _ptr(self._mu_status), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        return self._mu_out, self._mu_status
+
     def peakon_suite(self):
         """Device part of peakon_diagnostics (outputting.py:373-450); call after diagnostics().
         Returns (vals [R,2] = (min_du, max_du), ids [R,3] = (argmax u, min_du_idx, max_du_idx))."""

@@ -155,7 +155,7 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
     if any(d in SDE_DIAGNOSTICS for d in diagnostics) and true_pq is None:
         raise ValueError('u_error_with_sde / u_error_weak need true_peakon_data')
     want_m = any(d in M_DIAGNOSTICS for d in diagnostics)
-    want_du = 'mu' in diagnostics
+    want_du = False       # `mu` runs on the device (pk_mu); the host routine is only the fallback for flagged realisations
     pfac = (1 - np.exp(-Ld / np.sqrt(alphasq))) if periodic else 1.0
 
     # Brownian increments for the whole run when reproducing the reference's streams
@@ -193,8 +193,12 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
             pv, pi = eng.peakon_suite()
             pk_v, pk_i = pv.cpu().numpy(), pi.cpu().numpy()
         vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
-        du = du.cpu().numpy() if du is not None else None
-        u_host = eng.u.cpu().numpy() if ('u_field' in diagnostics or 'mu' in diagnostics) else None
+        mu_vals = mu_status = None
+        if 'mu' in diagnostics:
+            mv, ms = eng.mu()
+            mu_vals, mu_status = mv.cpu().numpy(), ms.cpu().numpy()
+        u_host = eng.u.cpu().numpy() if ('u_field' in diagnostics or
+                                         (mu_status is not None and ((mu_status == -1) | (mu_status == -2)).any())) else None
         failed = eng.fail_step.cpu().numpy() >= 0
         if data_file is None:
             return vals, idx
@@ -204,13 +208,18 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, index_of, rng
             v, ii = vals[k], idx[k]
             for d in diagnostics:
                 if d == 'mu':
-                    if failed[k]:
-                        old, alt = [np.nan], [np.nan]
-                    else:
-                        old, alt = out.mu_diagnostic(u_host[k], du[k], x_cells, Ld)
+                    if not failed[k] and mu_status[k] in (-1, -2):
+                        # more peaks than the device routine holds, or a field on which the reference itself raises:
+                        # the host restatement of find_mus decides (and raises like the reference)
+                        du_k = (np.roll(u_host[k], -1) - u_host[k]) / (Ld / ne)
+                        old, alt = out.mu_diagnostic(u_host[k], du_k, x_cells, Ld)
+                        for j in range(4):
+                            data_file.put('mu_%d' % j, ix, old[j] if j < len(old) else np.nan)
+                            data_file.put('alt_mu_%d' % j, ix, alt[j] if j < len(old) else np.nan)
+                        continue
                     for j in range(4):
-                        data_file.put('mu_%d' % j, ix, old[j] if j < len(old) else np.nan)
-                        data_file.put('alt_mu_%d' % j, ix, alt[j] if j < len(old) else np.nan)
+                        data_file.put('mu_%d' % j, ix, mu_vals[k, j])
+                        data_file.put('alt_mu_%d' % j, ix, mu_vals[k, 4 + j])
                     continue
                 if d == 'peakon_suite':
                     if failed[k]:

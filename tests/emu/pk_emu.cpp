@@ -12,6 +12,7 @@
 #include <cmath>
 #include "../../peakondrake_b200/csrc/pk_core.h"
 #include "../../peakondrake_b200/csrc/pk_upwind.h"
+#include "../../peakondrake_b200/csrc/pk_mu.h"
 
 using namespace pk;
 
@@ -286,3 +287,9 @@ extern "C" int pk_emu_step_upwind(int ne, double Ld, double dt, double alphasq, 
   }
   return 0;
 }
+
+// ---- mu diagnostic (pk_mu.h): the device routine on host arrays ------------------------------------
+extern "C" int pk_emu_mu(const double* u, const double* du, const double* x, int n, double Ld, double* old4, double* alt4) {
+  return mu_serial(u, du, x, n, Ld, old4, alt4);
+}
+extern "C" double pk_emu_pairwise_sum(const double* a, int n) { return np_pairwise_sum(a, n); }

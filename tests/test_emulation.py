@@ -227,3 +227,69 @@ def test_hybrid_schur_solve_variant():
             assert all(np.array_equal(x, y) for x, y in zip(a, b))
     finally:
         lib().pk_emu_set_hybrid(0)
+
+
+def _emu_mu(u, du, x, Ld):
+    import ctypes
+    L = lib()
+    L.pk_emu_mu.restype = ctypes.c_int
+    old4, alt4 = np.zeros(4), np.zeros(4)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    u, du, x = [np.ascontiguousarray(a, dtype=float) for a in (u, du, x)]
+    rc = L.pk_emu_mu(dp(u), dp(du), dp(x), len(u), ctypes.c_double(Ld), dp(old4), dp(alt4))
+    return rc, old4, alt4
+
+
+def test_device_mu_routine_against_reference_golden_vectors():
+    """pk_mu.h (the routine pk_mu_kernel runs per realisation) on the arrays behind tests/golden: bit-equal to the
+    reference's own find_mus outputs (outputting.py:260-370), including the multi-peak zone logic; NumPy's pairwise
+    summation is reproduced exactly."""
+    import ctypes, os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_helpers.npz'))
+    L = lib(); L.pk_emu_pairwise_sum.restype = ctypes.c_double
+    rng = np.random.default_rng(1)
+    for n in list(range(1, 200, 7)) + [1000, 2000, 16384, 20000]:
+        a = rng.standard_normal(n) * 10 ** rng.uniform(-2, 2)
+        assert L.pk_emu_pairwise_sum(a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n) == np.sum(a)
+    for name in [str(n) for n in gold['names']]:
+        u = gold[name + '/u']; ne = len(u); Ld = 40.0; h = Ld / ne
+        x = (np.arange(ne) + 0.5) * h
+        du = (np.roll(u, -1) - u) / h
+        rc, old4, alt4 = _emu_mu(u, du, x, Ld)
+        n_old = int(gold[name + '/nmus'][0])
+        assert rc >= 0
+        want_old = np.full(4, np.nan); want_alt = np.full(4, np.nan)
+        k = min(4, n_old)
+        want_old[:k] = gold[name + '/mus'][:k]; want_alt[:k] = gold[name + '/alt'][:k]
+        assert np.array_equal(old4, want_old, equal_nan=True) and np.array_equal(alt4, want_alt, equal_nan=True), name
+
+
+def test_device_mu_routine_equals_host_restatement_on_random_fields():
+    from peakondrake_b200 import outputting as out
+    rng = np.random.default_rng(7)
+    Ld = 40.0
+    for trial in range(60):
+        ne = int(rng.choice([64, 100, 257, 1000]))
+        h = Ld / ne
+        xn = np.arange(ne) * h
+        npk = int(rng.integers(0, 7))
+        u = 0.05 * rng.standard_normal() + np.zeros(ne)
+        for _ in range(npk):
+            c, a, w = rng.uniform(0, Ld), rng.uniform(0.3, 2.0), rng.uniform(0.5, 3.0)
+            d = np.abs(xn - c); d = np.minimum(d, Ld - d)
+            u = u + a * np.exp(-d / w)
+        u += 1e-3 * rng.standard_normal(ne) * (trial % 3 == 0)
+        x = (np.arange(ne) + 0.5) * h
+        du = (np.roll(u, -1) - u) / h
+        try:
+            old, alt = out.mu_diagnostic(u, du, x, Ld)
+        except (IndexError, ValueError):
+            assert _emu_mu(u, du, x, Ld)[0] == -2
+            continue
+        rc, old4, alt4 = _emu_mu(u, du, x, Ld)
+        assert rc >= 0 or rc == -1
+        if rc < 0:
+            continue
+        k = min(4, len(old))
+        assert np.array_equal(old4[:k], np.array(old[:k])) and np.array_equal(alt4[:k], np.array(alt[:k])), trial
+        assert np.isnan(old4[k:]).all() and np.isnan(alt4[k:]).all()

@@ -244,3 +244,41 @@ def test_experiment_with_the_test_scheme(tmp_path, monkeypatch):
         assert rel(d['u_field'][2, k], ref['u']) <= 1e-10
         e = ref['u'] @ (orc.M @ ref['u']) + ref['u'] @ (orc.K @ ref['u'])
         assert abs(d['energy'][2, k] - e) <= 1e-10 * e
+
+
+def test_device_mu_against_reference_helper_and_host_routine():
+    """pk_mu (find_mus on the device, outputting.py:260-370): bit-equal to the reference helper's golden outputs and,
+    on evolved stochastic states of a large ensemble, to the host restatement; failed realisations give NaN."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, outputting as out
+    names = [str(n) for n in GOLD['names']]
+    ne, Ld = len(GOLD[names[0] + '/u']), 40.0
+    assert all(len(GOLD[n + '/u']) == ne for n in names)
+    eng = EnsembleIntegrator(ne, Ld, 1e-3, len(names))
+    eng.u.copy_(torch.from_numpy(np.stack([GOLD[n + '/u'] for n in names])).to(eng.device))
+    eng.fail_step[-1] = 3
+    vals, status = [t.cpu().numpy() for t in eng.mu()]
+    for k, name in enumerate(names[:-1]):
+        n_old = int(GOLD[name + '/nmus'][0]); kk = min(4, n_old)
+        want = np.full(8, np.nan)
+        want[:kk] = GOLD[name + '/mus'][:kk]; want[4:4 + kk] = GOLD[name + '/alt'][:kk]
+        assert status[k] >= 0 and np.array_equal(vals[k], want, equal_nan=True), name
+    assert status[-1] == -3 and np.isnan(vals[-1]).all()
+    eng.close()
+    # evolved stochastic ensemble, several resolutions (shared-memory and global-memory paths)
+    for ne, R, nsteps in ((1000, 300, 40), (16384, 6, 2)):
+        eng = EnsembleIntegrator(ne, Ld, 1e-3, R, num_Xis=(4 if ne == 1000 else 1),
+                                 Xi_family=('sines' if ne == 1000 else 'constant'), sigma=0.3, seed=2)
+        eng.set_state(build_initial_u(ne, Ld, 'two_peaks' if ne == 1000 else 'proper_peak'))
+        eng.step(nsteps)
+        vals, status = [t.cpu().numpy() for t in eng.mu()]
+        u = eng.u.cpu().numpy()
+        x = (np.arange(ne) + 0.5) * (Ld / ne)
+        assert (status >= 0).all()
+        for r in range(min(R, 40)):
+            du = (np.roll(u[r], -1) - u[r]) / (Ld / ne)
+            old, alt = out.mu_diagnostic(u[r], du, x, Ld)
+            kk = min(4, len(old))
+            assert np.array_equal(vals[r, :kk], np.array(old[:kk])) and np.array_equal(vals[r, 4:4 + kk], np.array(alt[:kk]))
+            assert np.isnan(vals[r, kk:4]).all() and np.isnan(vals[r, 4 + kk:]).all()
+        eng.close()
