@@ -282,3 +282,48 @@ def test_device_mu_against_reference_helper_and_host_routine():
             assert np.array_equal(vals[r, :kk], np.array(old[:kk])) and np.array_equal(vals[r, 4:4 + kk], np.array(alt[:kk]))
             assert np.isnan(vals[r, kk:4]).all() and np.isnan(vals[r, 4 + kk:]).all()
         eng.close()
+
+
+def test_publication_script_patterns_scaled_down(tmp_path, monkeypatch):
+    """The parameter patterns of the reference's publication scripts, scaled down in time:
+    experiments/publication/stochastic/mu_stochastic_sine.py (resolution x sigma x seed sweep, 6 sines, mu) with a
+    resolution that needs the cluster kernel with noise tables, and experiments/publication/deterministic/
+    shallow_demo.py (ne=20000, sigma=0 with one 'sines' mode, u_field and slope locations)."""
+    from peakondrake_b200 import experiment, outputting as out
+    monkeypatch.chdir(tmp_path)
+    Ld, dt = 40., 1e-3
+    tmax = 4 * dt
+    res, sigmas, seeds = [1000, 3000], [0.05, 0.5], range(5, 8)
+    experiment('mu_sine', Ld, tmax, resolutions=res, dts=dt, sigmas=sigmas, seeds=seeds, schemes='hydrodynamic',
+               timesteppings='midpoint', ics='proper_peak', num_Xis=6, Xi_family='sines', alphasq=1.0, c0=0., gamma=0.,
+               diagnostics=['mu', 'max_du', 'min_du'], fields_to_output=['du'], ndump=2, field_ndump=4,
+               allow_fail=True, nXi_updates=1)
+    d = out.read_data_file('results/mu_sine/data.nc')
+    assert d['mu_0'].shape == (3, 2, 3, 2) and d['min_du'].shape == (3, 2, 3, 2) and np.isfinite(d['mu_0']).all()
+    assert np.isnan(d['mu_1']).all() and np.isnan(d['failed_time']).all()
+    assert os.path.exists('results/mu_sine/fields_resolution1_seed2_sigma1_output_1.vtu')
+    for ir, ne in enumerate(res):
+        mesh = O.Mesh1D(ne, Ld)
+        u0 = O.initial_u(mesh, 'proper_peak')
+        orc = O.CHOracle(ne, Ld, dt)
+        for jg, sg in enumerate(sigmas):
+            tabs = O.noise_tables(mesh, 'sines', 6, sg)
+            s = list(seeds)[1]
+            ref = O.run(ne, Ld, dt, 4, u0, O.reference_dW(s, 4, 6, dt), tabs)
+            sd = O.scalar_diagnostics(orc, ref['u'], ['max_du', 'min_du'])
+            for name, v in sd.items():
+                assert abs(d[name][2, ir, 1, jg] - v) <= 1e-9 * max(1.0, abs(v)), (name, ne, sg)
+    # shallow_demo.py: deterministic, ne = 20000 (clusters of 16)
+    ne = 20000
+    experiment('shallow_demo', Ld, 3 * dt, resolutions=ne, dts=dt, sigmas=0.0, seeds=0, schemes='hydrodynamic',
+               timesteppings='midpoint', ics='new_peak', num_Xis=1, Xi_family='sines', alphasq=1.0, c0=0., gamma=0.,
+               diagnostics=['u_field', 'max_du_loc', 'min_du_loc'], fields_to_output=[], ndump=3, field_ndump=3,
+               allow_fail=True, nXi_updates=1, peak_width=1.0)
+    d = out.read_data_file('results/shallow_demo/data.nc')
+    mesh = O.Mesh1D(ne, Ld)
+    u0 = O.initial_u(mesh, 'new_peak', peak_width=1.0)
+    ref = O.run(ne, Ld, dt, 3, u0, np.zeros((3, 1)), O.noise_tables(mesh, 'sines', 1, 0.0))
+    assert rel(d['u_field'][1], ref['u']) <= 1e-10
+    du = O.du_field(mesh, ref['u'])
+    x = (np.arange(ne) + 0.5) * (Ld / ne)          # the DG0 coordinate array the drop-in looks locations up in
+    assert d['max_du_loc'][1] == x[np.argmax(du)] and d['min_du_loc'][1] == x[np.argmin(du)]
