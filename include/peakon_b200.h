@@ -203,6 +203,10 @@ int pk_get_work_split(const pk_ctx* ctx, int32_t* slots, int32_t* nb, int32_t* n
 /* measured duration (ms) of the kernels launched by the last pk_step(_host) call, from CUDA events
  * recorded on the launching stream; synchronises on the second event. */
 double pk_last_step_kernel_ms(pk_ctx* ctx);
+/* sum of the device durations (ms) of the step kernels launched by pk_step since the previous call of this function
+ * (at most the last 64 launches; *count = how many), from CUDA event pairs recorded around each kernel on the
+ * launching stream; synchronises once, on the last one -- lets a caller time a loop without a sync per step. */
+double pk_step_kernel_ms_since(pk_ctx* ctx, int32_t* count);
 
 #ifdef __cplusplus
 }

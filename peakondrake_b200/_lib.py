@@ -19,7 +19,7 @@ I_ARGMAX_DU, I_ARGMIN_DU, I_ARGMAX_U, I_ARGMAX_JUMP, NIDX = range(5)
 
 EXPORTS = ['pk_create', 'pk_destroy', 'pk_last_error', 'pk_set_tables', 'pk_step', 'pk_step_host',
            'pk_set_step_counter', 'pk_get_step_counter', 'pk_diagnostics', 'pk_get_layout',
-           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite', 'pk_step_upwind', 'pk_diagnostics_dg1', 'pk_get_work_split', 'pk_reset_warm_start', 'pk_mu']
+           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite', 'pk_step_upwind', 'pk_diagnostics_dg1', 'pk_get_work_split', 'pk_reset_warm_start', 'pk_mu', 'pk_step_kernel_ms_since']
 
 
 class PkConfig(ctypes.Structure):
@@ -66,6 +66,8 @@ def load():
     lib.pk_diagnostics.argtypes = [vp, dp, dp, ctypes.c_int32, ctypes.c_int32, dp, ip, dp, ip, vp]
     lib.pk_get_layout.restype = ctypes.c_int
     lib.pk_get_layout.argtypes = [vp] + [ctypes.POINTER(ctypes.c_int32)] * 4
+    lib.pk_step_kernel_ms_since.restype = ctypes.c_double
+    lib.pk_step_kernel_ms_since.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     lib.pk_mu.restype = ctypes.c_int
     lib.pk_mu.argtypes = [vp, dp, dp, ip, dp, ip, vp]
     lib.pk_reset_warm_start.restype = ctypes.c_int

@@ -32,7 +32,9 @@ struct pk_ctx {
   double* d_mom;       // moments partial sums [32, 2*ne]
   long long* d_prof;   // PK_PROFILE: [R,16] cycle buckets
   double* d_tab[3];    // chunk-interleaved copies of the noise tables [nxi, T*M]
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev1;            // the event pair around the last step kernel (one of the ring below)
+  cudaEvent_t evr[2][64];          // ring of event pairs: pk_step_kernel_ms_since() sums them without per-step syncs
+  long long evn, evq;              // pairs recorded / pairs already summed
   bool timed;
 };
 

@@ -444,7 +444,8 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     if (e != cudaSuccess || per_sm < 1) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "occupancy query failed: %s", m.c_str()); }
     c->slots = per_sm * c->sms;
   }
-  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  for (int q = 0; q < 64; ++q) { cudaEventCreate(&c->evr[0][q]); cudaEventCreate(&c->evr[1][q]); }
+  c->ev0 = c->evr[0][0]; c->ev1 = c->evr[1][0]; c->evn = c->evq = 0;
   for (int q = 0; q < 4; ++q) cudaStreamCreateWithFlags(&c->hs[q], cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->hev, cudaEventDisableTiming);
   *out = c;
@@ -462,7 +463,8 @@ extern "C" void pk_destroy(pk_ctx* c) {
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_mom) cudaFree(c->d_mom);
   for (int q = 0; q < 3; ++q) if (c->d_tab[q]) cudaFree(c->d_tab[q]);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->hev);
+  for (int q = 0; q < 64; ++q) { cudaEventDestroy(c->evr[0][q]); cudaEventDestroy(c->evr[1][q]); }
+  cudaEventDestroy(c->hev);
   for (int q = 0; q < 4; ++q) cudaStreamDestroy(c->hs[q]);
   delete c;
 }
@@ -517,6 +519,7 @@ extern "C" int pk_get_work_split(const pk_ctx* c, int32_t* group, int32_t* nb, i
 enum { PK_HOST_CHUNKS = 4 };
 static int launch_range(pk_ctx* c, StepArgs a, int nsteps, int r0, int nr, int slot, cudaStream_t st, bool timed) {
   a.r0 = r0; a.Rq = nr;
+  if (timed) { const int k = (int)(c->evn % 64); c->ev0 = c->evr[0][k]; c->ev1 = c->evr[1][k]; ++c->evn; }
   if (c->cluster > 1) {
     if (r0 != 0 || nr != c->cfg.R) return fail(c, "internal: the cluster kernel advances the whole ensemble");
     if (timed) CK(c, cudaEventRecord(c->ev0, st));
@@ -582,6 +585,23 @@ extern "C" int pk_reset_warm_start(pk_ctx* c) {
   if (!c) return -1;
   c->w1_resident = false;
   return 0;
+}
+
+extern "C" double pk_step_kernel_ms_since(pk_ctx* c, int32_t* count) {
+  if (count) *count = 0;
+  if (!c || !c->timed) return -1.0;
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0;
+  long long first = c->evq;
+  if (c->evn - first > 64) first = c->evn - 64;          // older pairs have been overwritten
+  double tot = 0.0;
+  for (long long k = first; k < c->evn; ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->evr[0][k % 64], c->evr[1][k % 64]) != cudaSuccess) return -1.0;
+    tot += ms;
+  }
+  if (count) *count = (int32_t)(c->evn - first);
+  c->evq = c->evn;
+  return tot;
 }
 
 extern "C" double pk_last_step_kernel_ms(pk_ctx* c) {

@@ -183,6 +183,12 @@ class EnsembleIntegrator(object):
     def last_kernel_ms(self):
         return float(self.lib.pk_last_step_kernel_ms(self.ctx))
 
+    def kernel_ms_since(self):
+        """(total ms, launches) of the step kernels since the last call (CUDA events around each kernel; one sync)."""
+        n = ctypes.c_int32()
+        ms = float(self.lib.pk_step_kernel_ms_since(self.ctx, ctypes.byref(n)))
+        return ms, n.value
+
     def step_host(self, nsteps, u, u1, dF, dG, dW, fail_step, its_last, its_total, dW_out=None):
         """pk_step_host on (pinned or pageable) host NumPy arrays, in place. Synchronous.
         u1 = dF = dG = None: the Newton warm start stays resident in the context, as it does inside the
