@@ -451,3 +451,40 @@ def test_c3_full_size_shard_statistics():
     assert np.allclose(s1 / n, um, rtol=1e-12, atol=1e-14)
     assert (s2 / n + 1e-15 >= (s1 / n) ** 2).all()
     eng.close()
+
+
+def test_c1_full_length_and_c2_long_path():
+    """BASELINE config 1 at its full length (ne=1000, dt=1e-3, T=5: 5000 steps, deterministic single peakon) and one
+    stochastic C2 path over 1000 steps: the error against the oracle must not accumulate beyond 1e-10 and the
+    Newton iteration totals must be identical over the whole run."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, draw_dW
+    ne, Ld, dt = 1000, 40.0, 1e-3
+    # C1: sigma = 0 with one 'sines' mode (SURVEY.md 8d), ic 'one_peak'
+    nsteps = 5000
+    u0 = build_initial_u(ne, Ld, 'one_peak')
+    eng = EnsembleIntegrator(ne, Ld, dt, 1, num_Xis=1, Xi_family='sines', sigma=0.0)
+    eng.set_state(u0)
+    dW = draw_dW(0, nsteps, 1, dt)[:, None, :]
+    for k in range(0, nsteps, 1000):
+        eng.step(1000, dW=dW[k:k + 1000])
+    torch.cuda.synchronize()
+    ref = O.run(ne, Ld, dt, nsteps, u0, dW[:, 0, :], O.noise_tables(O.Mesh1D(ne, Ld), 'sines', 1, 0.0))
+    assert eng.fail_step[0].item() == -1 and ref['fail_step'] == -1
+    assert eng.its_total[0].item() == ref['its'].sum()
+    err = rel(eng.u[0].cpu().numpy(), ref['u'])
+    assert err <= TOL, err
+    eng.close()
+    # C2: one stochastic path, 1000 steps, the reference's MT19937 stream for seed 7
+    nsteps, nxi, sigma = 1000, 4, 0.2
+    u0 = build_initial_u(ne, Ld, 'proper_peak')
+    eng = EnsembleIntegrator(ne, Ld, dt, 2, num_Xis=nxi, Xi_family='sines', sigma=sigma)
+    eng.set_state(u0)
+    dW = np.stack([draw_dW(s, nsteps, nxi, dt) for s in (7, 8)], axis=1)
+    eng.step(nsteps, dW=dW)
+    torch.cuda.synchronize()
+    ref = O.run(ne, Ld, dt, nsteps, u0, dW[:, 0, :], O.noise_tables(O.Mesh1D(ne, Ld), 'sines', nxi, sigma))
+    assert eng.its_total[0].item() == ref['its'].sum()
+    err = rel(eng.u[0].cpu().numpy(), ref['u'])
+    assert err <= TOL, err
+    eng.close()
