@@ -47,6 +47,22 @@ struct Shared {
   // it into a block-local address without decoding (pk_kernels.cuh, SharedCluster)
   PK_HD double ldo(const double* a, int j, int T, int t) const { return a[j * T + t]; }
   PK_HD void sto(double* a, int j, int T, int t, double v) const { a[j * T + t] = v; }
+  // pairs of doubles (16-byte shared-memory accesses): pair slot q of thread tt lives at doubles 2 (q T + tt), +1.
+  // Used for the PCR rows, which travel as whole 2x2 blocks.
+  PK_HD void ld2(const double* a, int q, int T, int tt, double& v0, double& v1) const {
+#if defined(__CUDA_ARCH__)
+    const double2 v = reinterpret_cast<const double2*>(a)[q * T + tt]; v0 = v.x; v1 = v.y;
+#else
+    v0 = a[2 * (q * T + tt)]; v1 = a[2 * (q * T + tt) + 1];
+#endif
+  }
+  PK_HD void st2o(double* a, int q, int T, int t, double v0, double v1) const {
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<double2*>(a)[q * T + t] = make_double2(v0, v1);
+#else
+    a[2 * (q * T + t)] = v0; a[2 * (q * T + t) + 1] = v1;
+#endif
+  }
   PK_HD double dw(int k) const { return dW[k]; }
   PK_HD void set_dw(int k, double v) const { dW[k] = v; }
 };
@@ -663,11 +679,21 @@ struct Thread {
   PK_HD void reduce_publish(const Params& p, const SH& sh, int base = 0) {
     const int T = TN(p);
     double Di[4]; inv2(Db, Di);
-    PK_UNROLL
-    for (int c = 0; c < 4; ++c) {
-      sh.sto(sh.xb, (base + c), T, t, Lb[c]); sh.sto(sh.xb, (base + 4 + c), T, t, Ub[c]); sh.sto(sh.xb, (base + 8 + c), T, t, Di[c]);
-    }
-    sh.sto(sh.xb, (base + 12), T, t, rb[0]); sh.sto(sh.xb, (base + 13), T, t, rb[1]);
+    // seven 16-byte stores: (L0 L1)(L2 L3)(U0 U1)(U2 U3)(D^-1 ...)(r0 r1), pair slots base/2 .. base/2 + 6
+    const int b2 = base >> 1;
+    sh.st2o(sh.xb, b2 + 0, T, t, Lb[0], Lb[1]); sh.st2o(sh.xb, b2 + 1, T, t, Lb[2], Lb[3]);
+    sh.st2o(sh.xb, b2 + 2, T, t, Ub[0], Ub[1]); sh.st2o(sh.xb, b2 + 3, T, t, Ub[2], Ub[3]);
+    sh.st2o(sh.xb, b2 + 4, T, t, Di[0], Di[1]); sh.st2o(sh.xb, b2 + 5, T, t, Di[2], Di[3]);
+    sh.st2o(sh.xb, b2 + 6, T, t, rb[0], rb[1]);
+  }
+  // one published row (pair layout of reduce_publish) of thread q
+  template <class SH>
+  PK_HD void pcr_load_row(const Params& p, const SH& sh, int b2, int q, double* L_, double* U_, double* Di_, double* r_) const {
+    const int T = TN(p);
+    sh.ld2(sh.xb, b2 + 0, T, q, L_[0], L_[1]); sh.ld2(sh.xb, b2 + 1, T, q, L_[2], L_[3]);
+    sh.ld2(sh.xb, b2 + 2, T, q, U_[0], U_[1]); sh.ld2(sh.xb, b2 + 3, T, q, U_[2], U_[3]);
+    sh.ld2(sh.xb, b2 + 4, T, q, Di_[0], Di_[1]); sh.ld2(sh.xb, b2 + 5, T, q, Di_[2], Di_[3]);
+    sh.ld2(sh.xb, b2 + 6, T, q, r_[0], r_[1]);
   }
 
   // one parallel-cyclic-reduction step with stride d (reads only)
@@ -677,13 +703,8 @@ struct Thread {
     const int T = TN(p);
     const int ql = (t + T - d) & (T - 1), qr = (t + d) & (T - 1);
     double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
-    PK_UNROLL
-    for (int c = 0; c < 4; ++c) {
-      Ll[c] = sh.ld(sh.xb, (base + c) * T + ql); Ul[c] = sh.ld(sh.xb, (base + 4 + c) * T + ql); Dl[c] = sh.ld(sh.xb, (base + 8 + c) * T + ql);
-      Lr[c] = sh.ld(sh.xb, (base + c) * T + qr); Ur[c] = sh.ld(sh.xb, (base + 4 + c) * T + qr); Dr[c] = sh.ld(sh.xb, (base + 8 + c) * T + qr);
-    }
-    rl[0] = sh.ld(sh.xb, (base + 12) * T + ql); rl[1] = sh.ld(sh.xb, (base + 13) * T + ql);
-    rr[0] = sh.ld(sh.xb, (base + 12) * T + qr); rr[1] = sh.ld(sh.xb, (base + 13) * T + qr);
+    pcr_load_row(p, sh, base >> 1, ql, Ll, Ul, Dl, rl);
+    pcr_load_row(p, sh, base >> 1, qr, Lr, Ur, Dr, rr);
     double al[4], ga[4];
     mm2(Lb, Dl, al); mm2(Ub, Dr, ga);
     PK_UNROLL
@@ -700,11 +721,7 @@ struct Thread {
     const int T = TN(p);
     const int q = (t + T / 2) & (T - 1);
     double Lq[4], Uq[4], Dq[4], rq[2];
-    PK_UNROLL
-    for (int c = 0; c < 4; ++c) {
-      Lq[c] = sh.ld(sh.xb, (base + c) * T + q); Uq[c] = sh.ld(sh.xb, (base + 4 + c) * T + q); Dq[c] = sh.ld(sh.xb, (base + 8 + c) * T + q);
-    }
-    rq[0] = sh.ld(sh.xb, (base + 12) * T + q); rq[1] = sh.ld(sh.xb, (base + 13) * T + q);
+    pcr_load_row(p, sh, base >> 1, q, Lq, Uq, Dq, rq);
     double S[4], Sq[4], SD[4], A[4], Ai[4], rhs[2];
     PK_UNROLL
     for (int c = 0; c < 4; ++c) { S[c] = Lb[c] + Ub[c]; Sq[c] = Lq[c] + Uq[c]; A[c] = Db[c]; }

@@ -256,6 +256,16 @@ struct SharedCluster {
     const int tg = i & ((1 << lgT) - 1), j = i >> lgT;
     a[(j << lgTc) + (tg & (Tc - 1))] = v;
   }
+  // pairs of doubles (PCR rows): pair slot q of thread tt, 16-byte accesses; remote rows through DSMEM
+  __device__ __forceinline__ void ld2(const double* a, int q, int, int tt, double& v0, double& v1) const {
+    const unsigned owner = (unsigned)tt >> lgTc;
+    const double2* pl = reinterpret_cast<const double2*>(a) + (q << lgTc) + (tt & (Tc - 1));
+    const double2 v = (owner == rank) ? *pl : *cg::this_cluster().map_shared_rank(const_cast<double2*>(pl), owner);
+    v0 = v.x; v1 = v.y;
+  }
+  __device__ __forceinline__ void st2o(double* a, int q, int, int, double v0, double v1) const {
+    reinterpret_cast<double2*>(a)[(q << lgTc) + (int)threadIdx.x] = make_double2(v0, v1);
+  }
   // slot j of the calling thread: block-local, no decoding of the flat index (most accesses are of this kind)
   __device__ __forceinline__ double ldo(const double* a, int j, int, int) const { return a[(j << lgTc) + (int)threadIdx.x]; }
   __device__ __forceinline__ void sto(double* a, int j, int, int, double v) const { a[(j << lgTc) + (int)threadIdx.x] = v; }

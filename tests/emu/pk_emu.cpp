@@ -37,6 +37,18 @@ struct EmuSharedCluster {
   }
   double ld(const double* a, int i) const { return *at(a, i, false); }
   void st(double* a, int i, double v) const { *at(a, i, true) = v; }
+  // pairs of doubles (PCR rows): pair slot q of thread tt at doubles 2 (q Tc + tt_local), +1 in tt's CTA
+  void ld2(const double* a, int q, int T, int tt, double& v0, double& v1) const {
+    const int owner = tt >> lgTc;
+    const size_t o = (a - (const double*)0) + 2 * ((size_t)(q << lgTc) + (tt & (Tc - 1)));
+    v0 = (*bufs)[owner][o]; v1 = (*bufs)[owner][o + 1];
+  }
+  void st2o(double* a, int q, int T, int t, double v0, double v1) const {
+    const int owner = (t & ((1 << lgT) - 1)) >> lgTc;
+    if (owner != *cur) ++*bad;
+    const size_t o = (a - (double*)0) + 2 * ((size_t)(q << lgTc) + (t & (Tc - 1)));
+    (*bufs)[owner][o] = v0; (*bufs)[owner][o + 1] = v1;
+  }
   // own-slot accessors: must be block-local (checked like the device's sto/ldo, which do not decode)
   double ldo(const double* a, int j, int T, int t) const { if (((t & ((1 << lgT) - 1)) >> lgTc) != *cur) ++*bad; return *at(a, j * T + t, false); }
   void sto(double* a, int j, int T, int t, double v) const { *at(a, j * T + t, true) = v; }
