@@ -1224,7 +1224,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       if (status) break;
       // ---- linear solve + update ----
       ex.each([&](Th& th) { th.reduce_build(p, sh); });
-      ex.sync();
+      if (!ex.pingpong()) ex.sync();         // the publish below reuses the slots the neighbours read their tips from
       const int Tn = (TT > 0 ? TT : p.T);
       if (ex.hybrid(Tn)) {
         // cyclic reduction (compacted onto the leading threads) -> 32 rows -> PCR inside warp 0 -> back-substitution
@@ -1246,10 +1246,17 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
         ex.each([&](Th& th) { th.hyb_load_xs(p, sh); });
         ex.tick(8);
       } else {
-        ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+        int base = 0;
+        if (ex.pingpong()) {
+          // second row buffer: the first publish does not overwrite the tips the neighbours are still reading, so it
+          // needs no barrier after reduce_build (whose barrier below is reused)
+          base = XB_PP_BASE;
+          ex.each([&](Th& th) { th.reduce_publish(p, sh, XB_PP_BASE); });
+        } else {
+          ex.each([&](Th& th) { th.reduce_publish(p, sh); });
+        }
         ex.sync();
         ex.tick(6);
-        int base = 0;
         if (ex.pingpong()) {
           // two row buffers: a step reads one and publishes into the other -> ONE barrier per PCR step
           for (int d = 1; d < Tn / 2; d *= 2) {
