@@ -14,5 +14,6 @@ struct StepArgs {
   // single-CTA step kernel (persistent CTAs + work queue)
   int* queue;         // [1 + R]: work counter, then per realisation the number of finished step blocks
   int nblk;           // steps per work item
+  int part;           // cluster kernel: 1 = Schur solve partitioned by CTA (default), 0 = flat PCR over the cluster
   int nb;             // step blocks per realisation: items = nb * R, item i = (block i / R, realisation i % R)
 };

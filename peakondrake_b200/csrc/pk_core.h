@@ -56,6 +56,7 @@ struct Shared {
     v0 = a[2 * (q * T + tt)]; v1 = a[2 * (q * T + tt) + 1];
 #endif
   }
+  PK_HD void ld2l(const double* a, int q, int T, int tt, double& v0, double& v1) const { ld2(a, q, T, tt, v0, v1); }
   PK_HD void st2o(double* a, int q, int T, int t, double v0, double v1) const {
 #if defined(__CUDA_ARCH__)
     reinterpret_cast<double2*>(a)[q * T + t] = make_double2(v0, v1);
@@ -696,6 +697,16 @@ struct Thread {
     sh.ld2(sh.xb, b2 + 6, T, q, r_[0], r_[1]);
   }
 
+  // same for a row of my own CTA (cluster variant: block-local address, no owner decode)
+  template <class SH>
+  PK_HD void pcr_load_row_local(const Params& p, const SH& sh, int b2, int q, double* L_, double* U_, double* Di_, double* r_) const {
+    const int T = TN(p);
+    sh.ld2l(sh.xb, b2 + 0, T, q, L_[0], L_[1]); sh.ld2l(sh.xb, b2 + 1, T, q, L_[2], L_[3]);
+    sh.ld2l(sh.xb, b2 + 2, T, q, U_[0], U_[1]); sh.ld2l(sh.xb, b2 + 3, T, q, U_[2], U_[3]);
+    sh.ld2l(sh.xb, b2 + 4, T, q, Di_[0], Di_[1]); sh.ld2l(sh.xb, b2 + 5, T, q, Di_[2], Di_[3]);
+    sh.ld2l(sh.xb, b2 + 6, T, q, r_[0], r_[1]);
+  }
+
   // one parallel-cyclic-reduction step with stride d (reads only)
   template <class SH>
   // base: first exchange slot of the row buffer to read (0, or XB_PP_BASE when the rows ping-pong between two buffers)
@@ -713,6 +724,57 @@ struct Thread {
     mm2(ga, Ur, Ub);
     mma2(al, Ul, Db); mma2(ga, Lr, Db);
     mva2(al, rl, rb); mva2(ga, rr, rb);
+  }
+
+  // ---- partitioned Schur solve (thread-block-cluster variant) ------------------------------------------------
+  // The T block rows are cut into C segments of Tc rows, one per CTA.  Row 0 of a segment is the segment's
+  // SEPARATOR s_k; rows 1..Tc-1 are reduced by a PCR that never leaves the segment: a row whose partner at
+  // distance d would lie outside keeps its coupling, which from then on is the coupling to the separator on that
+  // side (left: s_k, the own CTA's; right: s_{k+1}).  A row is never coupled to an in-segment row and to the
+  // separator on the same side at once, so the L / U slots carry either meaning and no extra storage or flops
+  // are needed.  After ceil(log2(Tc-1)) steps (block-local barriers, block-local loads) every interior row reads
+  //     L s_k + D x + U s_{k+1} = r .
+  // The separators then eliminate their two neighbours (an ordinary PCR step at distance 1) and form a cyclic
+  // block-tridiagonal system of C rows, solved by PCR among the C leading threads (strides Tc, 2Tc, ...).
+  template <class SH>
+  PK_HD void pcr_step_local(const Params& p, const SH& sh, int d, int base, int Tc) {
+    const int tl_ = t & (Tc - 1);
+    const bool hl = tl_ - d >= 1, hr = tl_ != 0 && tl_ + d <= Tc - 1;
+    double al[4], ga[4];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) al[c] = ga[c] = 0.0;
+    double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
+    if (hl) {
+      pcr_load_row_local(p, sh, base >> 1, t - d, Ll, Ul, Dl, rl);
+      mm2(Lb, Dl, al);
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) al[c] = -al[c];
+      mm2(al, Ll, Lb);
+    }
+    if (hr) {
+      pcr_load_row_local(p, sh, base >> 1, t + d, Lr, Ur, Dr, rr);
+      mm2(Ub, Dr, ga);
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) ga[c] = -ga[c];
+      mm2(ga, Ur, Ub);
+    }
+    if (hl) { mma2(al, Ul, Db); mva2(al, rl, rb); }
+    if (hr) { mma2(ga, Lr, Db); mva2(ga, rr, rb); }
+  }
+  // interior rows of a segment once the separators are known (slots 14, 15 of the leading threads)
+  template <class SH>
+  PK_HD void part_back(const Params& p, const SH& sh, int Tc) {
+    const int T = TN(p);
+    const int lead = t - (t & (Tc - 1)), nxt = (lead + Tc) & (T - 1);
+    const double sL[2] = {sh.ld(sh.xb, 14 * T + lead), sh.ld(sh.xb, 15 * T + lead)};
+    const double sR[2] = {sh.ld(sh.xb, 14 * T + nxt), sh.ld(sh.xb, 15 * T + nxt)};
+    double tmp[2] = {0.0, 0.0}, Di[4];
+    mva2(Lb, sL, tmp); mva2(Ub, sR, tmp);
+    const double r0 = rb[0] - tmp[0], r1 = rb[1] - tmp[1];
+    inv2(Db, Di);
+    xs0 = Di[0] * r0 + Di[1] * r1;
+    xs1 = Di[2] * r0 + Di[3] * r1;
+    sh.sto(sh.xb, 14, T, t, xs0); sh.sto(sh.xb, 15, T, t, xs1);
   }
 
   // last level: rows t and t+T/2 form a closed 2-block system
@@ -1257,7 +1319,28 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
         }
         ex.sync();
         ex.tick(6);
-        if (ex.pingpong()) {
+        if (ex.partitioned()) {
+          // segment-local PCR (block-local barriers and loads), then PCR among the C separators
+          const int Tc = ex.tc();
+          for (int d = 1; d <= Tc - 2; d *= 2) {
+            ex.each([&](Th& th) { th.pcr_step_local(p, sh, d, base, Tc); th.reduce_publish(p, sh, XB_PP_BASE - base); });
+            base = XB_PP_BASE - base;
+            if (2 * d <= Tc - 2) ex.sync_local();
+          }
+          ex.sync();
+          ex.each([&](Th& th) { if ((th.t & (Tc - 1)) == 0) { th.pcr_step(p, sh, 1, base); th.reduce_publish(p, sh, XB_PP_BASE - base); } });
+          base = XB_PP_BASE - base;
+          ex.sync();
+          for (int d = Tc; d < Tn / 2; d *= 2) {
+            ex.each([&](Th& th) { if ((th.t & (Tc - 1)) == 0) { th.pcr_step(p, sh, d, base); th.reduce_publish(p, sh, XB_PP_BASE - base); } });
+            base = XB_PP_BASE - base;
+            ex.sync();
+          }
+          ex.tick(7);
+          ex.each([&](Th& th) { if ((th.t & (Tc - 1)) == 0) th.pcr_final(p, sh, base); });
+          ex.sync();
+          ex.each([&](Th& th) { if ((th.t & (Tc - 1)) != 0) th.part_back(p, sh, Tc); });
+        } else if (ex.pingpong()) {
           // two row buffers: a step reads one and publishes into the other -> ONE barrier per PCR step
           for (int d = 1; d < Tn / 2; d *= 2) {
             ex.each([&](Th& th) { th.pcr_step(p, sh, d, base); th.reduce_publish(p, sh, XB_PP_BASE - base); });
@@ -1272,8 +1355,10 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
             ex.sync();
           }
         }
-        ex.tick(7);
-        ex.each([&](Th& th) { th.pcr_final(p, sh, base); });
+        if (!ex.partitioned()) {
+          ex.tick(7);
+          ex.each([&](Th& th) { th.pcr_final(p, sh, base); });
+        }
         ex.sync();
         ex.tick(8);
       }

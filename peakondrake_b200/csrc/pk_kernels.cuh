@@ -40,6 +40,9 @@ struct GpuExecT {
 #endif
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
   __device__ __forceinline__ bool pingpong() const { return false; }     // no shared memory to spare at 3 CTAs/SM
+  __device__ __forceinline__ bool partitioned() const { return false; }
+  __device__ __forceinline__ int tc() const { return (int)blockDim.x; }
+  __device__ __forceinline__ void sync_local() { __syncthreads(); }
   // compacted Schur solve (pk_core.h, hyb_*): needs >= 32 threads per realisation, all of one block.  Measured
   // 12 % SLOWER than plain PCR on B200 (the serial single-warp phases stall the whole CTA; profiles/r1d_exp_variants.log),
   // so it is only compiled into -DPK_HYBRID_SCHUR experiment builds.
@@ -263,6 +266,11 @@ struct SharedCluster {
     const double2 v = (owner == rank) ? *pl : *cg::this_cluster().map_shared_rank(const_cast<double2*>(pl), owner);
     v0 = v.x; v1 = v.y;
   }
+  // row of a thread of my own CTA: no owner decode
+  __device__ __forceinline__ void ld2l(const double* a, int q, int, int tt, double& v0, double& v1) const {
+    const double2 v = reinterpret_cast<const double2*>(a)[(q << lgTc) + (tt & (Tc - 1))];
+    v0 = v.x; v1 = v.y;
+  }
   __device__ __forceinline__ void st2o(double* a, int q, int, int, double v0, double v1) const {
     reinterpret_cast<double2*>(a)[(q << lgTc) + (int)threadIdx.x] = make_double2(v0, v1);
   }
@@ -285,10 +293,24 @@ struct GpuExecCluster {
   template <class F> __device__ __forceinline__ void each(F f) { f(th); }
   template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, (int)blockDim.x, rank == 0, g0, g1); }
   __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+#ifdef PK_PROFILE
+  long long tlast; long long* tbuf;
+  __device__ __forceinline__ void tick(int id) {
+    if (threadIdx.x == 0) { const long long c = clock64(); tbuf[id] += c - tlast; tlast = c; }
+  }
+#else
   __device__ __forceinline__ void tick(int) {}
+#endif
   template <class F> __device__ __forceinline__ void one(F f) { if (rank == 0 && threadIdx.x == 0) f(); }
   __device__ __forceinline__ bool hybrid(int) const { return false; }     // rows are spread over the CTAs of the cluster
   __device__ __forceinline__ bool pingpong() const { return true; }       // XB_SLOTS_PP exchange slots: one cluster barrier per PCR step
+  // Schur solve partitioned by CTA (pk_core.h, pcr_step_local): the PCR steps inside a CTA need block barriers and
+  // block-local loads only; the C separator rows are solved by the leading threads.  part = 0 keeps the flat PCR
+  // over all C*Tc rows (every step a cluster barrier and, from stride Tc/2 on, DSMEM-bandwidth-bound row loads).
+  int part;
+  __device__ __forceinline__ bool partitioned() const { return part != 0; }
+  __device__ __forceinline__ int tc() const { return (int)blockDim.x; }
+  __device__ __forceinline__ void sync_local() { __syncthreads(); }
   template <class F> __device__ __forceinline__ void each_first(int, F) {}
   template <class F> __device__ __forceinline__ void warp0_steps(int, F) {}
   __device__ __forceinline__ double* area() {
@@ -420,7 +442,13 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   Thread<M, MODE, 0> th;
   th.init(p, t0 + (int)threadIdx.x);
   GpuExecCluster<M, MODE> ex(th, red);
-  ex.rank = rank; ex.C = C; ex.g0 = g0; ex.g1 = g1;
+  ex.rank = rank; ex.C = C; ex.g0 = g0; ex.g1 = g1; ex.part = a.part;
+#ifdef PK_PROFILE
+  __shared__ long long tb[16];
+  if (threadIdx.x < 16) tb[threadIdx.x] = 0;
+  __syncthreads();
+  ex.tbuf = tb; ex.tlast = clock64();
+#endif
   StepIO io;
   io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
   io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
@@ -428,6 +456,9 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   run_steps<M, MODE, 0, GpuExecCluster<M, MODE>, Thread<M, MODE, 0> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
+#ifdef PK_PROFILE
+  if (a.prof && rank == 0 && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];
+#endif
 
   for (int i = g0 + threadIdx.x; i < g1; i += blockDim.x) {
     const int sl = row_slot_c<M, 0>(p, i);

@@ -562,6 +562,7 @@ static int step_args(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* d
   a->dW_in = dW_in; a->dW_out = dW_out; a->fail_step = fail_step; a->its_last = its_last; a->its_total = its_total;
   a->prof = c->d_prof;
   a->queue = nullptr; a->nblk = nsteps; a->nb = 1; a->r0 = 0; a->Rq = c->cfg.R;
+  { const char* e = getenv("PK_CLUSTER_FLAT_PCR"); a->part = (e && atoi(e) == 1) ? 0 : 1; }
   a->R = c->cfg.R; a->step0 = (int)c->step; a->nsteps = nsteps; a->rid0 = c->cfg.rid_offset; a->seed = c->cfg.seed;
   return 0;
 }

@@ -8,7 +8,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 lib_path = os.path.join(ROOT, 'peakondrake_b200', 'libpeakon_b200_prof.so')
-subprocess.check_call(['/usr/local/cuda/bin/nvcc', '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a',
+if not os.path.exists(lib_path) or os.environ.get('REBUILD'):
+  subprocess.check_call(['/usr/local/cuda/bin/nvcc', '-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a',
                        '-lineinfo', '-Xcompiler', '-fPIC', '-shared', '-diag-suppress', '128', '-DPK_PROFILE',
                        '-DPK_M=8', '-DPK_PROFILE_SINGLE_M', '-o', lib_path,
                        os.path.join(ROOT, 'peakondrake_b200', 'csrc', 'pk_lib.cu'),
@@ -18,9 +19,9 @@ from peakondrake_b200 import _lib
 _lib.LIB_PATH = lib_path
 import torch
 from peakondrake_b200 import EnsembleIntegrator, build_initial_u
-ne, R, K = int(os.environ.get('NE', 1000)), int(os.environ.get('R', 1024)), 50
+ne, R, K = int(os.environ.get('NE', 1000)), int(os.environ.get('R', 1024)), int(os.environ.get('K', 50))
 fam = os.environ.get('FAM', 'sines'); nxi = 4 if fam == 'sines' else 1
-eng = EnsembleIntegrator(ne, 40.0, 1e-3, R, num_Xis=nxi, Xi_family=fam, sigma=0.2, seed=1)
+eng = EnsembleIntegrator(ne, 40.0, float(os.environ.get('DT', 1e-3)), R, num_Xis=nxi, Xi_family=fam, sigma=0.2, seed=1)
 eng.set_state(build_initial_u(ne, 40.0, 'proper_peak'))
 eng.step(K); torch.cuda.synchronize()
 eng.lib.pk_profile_enable.argtypes = [ctypes.c_void_p]; eng.lib.pk_profile_read.argtypes = [ctypes.c_void_p, ctypes.c_void_p]

@@ -16,6 +16,7 @@
 
 using namespace pk;
 
+static int g_emu_part = 1;        // cluster emulation: Schur solve partitioned by CTA (1, like the device) or flat PCR (0)
 static int g_emu_hybrid = 0;      // 1: compacted Schur solve (hyb_* in pk_core.h) where T >= 32; 0: plain PCR
 template <class ThT> struct EmuExecT;
 template <int M, int MODE> using EmuExec = EmuExecT<Thread<M, MODE> >;
@@ -42,6 +43,10 @@ struct EmuSharedCluster {
     const int owner = tt >> lgTc;
     const size_t o = (a - (const double*)0) + 2 * ((size_t)(q << lgTc) + (tt & (Tc - 1)));
     v0 = (*bufs)[owner][o]; v1 = (*bufs)[owner][o + 1];
+  }
+  void ld2l(const double* a, int q, int T, int tt, double& v0, double& v1) const {     // must be block-local
+    if ((tt >> lgTc) != *cur) ++*bad;
+    ld2(a, q, T, tt, v0, v1);
   }
   void st2o(double* a, int q, int T, int t, double v0, double v1) const {
     const int owner = (t & ((1 << lgT) - 1)) >> lgTc;
@@ -82,6 +87,9 @@ struct EmuExecT {
   template <class F> void one(F f) { f(); }
   bool hybrid(int Tn) const { return g_emu_hybrid && C == 1 && Tn >= 32; }
   bool pingpong() const { return C > 1; }      // like the cluster kernel: XB_SLOTS_PP slots
+  bool partitioned() const { return C > 1 && g_emu_part; }
+  int tc() const { return Tc; }
+  void sync_local() {}
   template <class F> void each_first(int n, F f) {
     for (int k = 0; k < n; ++k) { const int t = order == 0 ? k : n - 1 - k; cur = t / Tc; f(th[t]); }
   }
@@ -217,6 +225,7 @@ extern "C" int pk_emu_set_cluster(int C) { g_emuC = C; return g_bad; }
 extern "C" int pk_emu_set_fs(int on) { g_emu_fs = on; return 0; }
 
 extern "C" int pk_emu_set_hybrid(int on) { g_emu_hybrid = on; return 0; }
+extern "C" int pk_emu_set_partitioned(int on) { g_emu_part = on; return 0; }
 
 // advance in step blocks of nblk steps (0 = whole launch at once), see run_one
 extern "C" int pk_emu_set_block(int nblk) { g_emu_nblk = nblk; return 0; }

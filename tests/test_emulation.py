@@ -103,18 +103,22 @@ def test_philox_generator_statistics_and_reproducibility():
     assert abs(r['dW'][3, 1, 1] - w) < 1e-16          # kernel scales each sub-draw, then sums
 
 
-@pytest.mark.parametrize('ne,C', [(1000, 2), (1000, 4), (250, 2), (2000, 8)])
-def test_cluster_layout_emulated(ne, C):
+@pytest.mark.parametrize('ne,C,part', [(1000, 2, 1), (1000, 4, 1), (250, 2, 1), (2000, 8, 1), (2000, 16, 1), (128, 8, 1), (256, 8, 1), (200, 2, 1),
+                                        (1000, 4, 0), (2000, 8, 0)])
+def test_cluster_layout_emulated(ne, C, part):
     """Thread-block-cluster variant (large meshes): shared arrays distributed over C CTAs, foreign
-    rows read remotely, every store local -- same decode as SharedCluster in pk_lib.cu."""
+    rows read remotely, every store local -- same decode as SharedCluster in pk_lib.cu.  part=1: Schur solve
+    partitioned by CTA (segment-local PCR + PCR among the C separators, the device default); part=0: flat PCR."""
     L = lib()
     try:
+        L.pk_emu_set_partitioned(part)
         assert L.pk_emu_set_cluster(C) == 0
         compare(ne, nsteps=3, nxi=2)
         compare(ne, nsteps=2, fam='constant', nxi=1, ic='periodic_peakon', sigma=0.5)
         assert L.pk_emu_set_cluster(1) == 0          # no non-local stores happened
     finally:
         L.pk_emu_set_cluster(1)
+        L.pk_emu_set_partitioned(1)
 
 
 # ---- upwind / ssprk3 ---------------------------------------------------------------------------------
