@@ -12,6 +12,10 @@
 // The volume terms collapse exactly (expand 6Q +- (s1-s0)(..)):
 //   rhs0 = Phi_i - s1 (mL+mR)/2 ,   rhs1 = s0 (mL+mR)/2 - Phi_{i+1},
 // which is what the kernel evaluates (a third of the flops; each vertex flux Phi is computed once).
+// With the factor 2/h of M_e^-1 folded into the frozen velocity, s' = (2/h) us, Phi' = s' * (upwind value):
+//   dm0 = (2 Phi'_i + Phi'_{i+1}) - (mL+mR) (s'1 + s'0/2),   dm1 = (mL+mR) (s'0 + s'1/2) - (2 Phi'_{i+1} + Phi'_i),
+// i.e. 6 fp64 instructions per cell and stage before the stage combination; the upwind side is picked from the sign
+// bit of s' and the blow-up test reads the exponent bits (integer pipe): the kernel is fp64-issue-bound.
 //
 // Layout: one CTA per realisation, the same chunk geometry as the midpoint kernel (thread t owns
 // cells/nodes [s_t, s_t+m_t)), but the scheme is explicit and local, so the WHOLE state of a thread
@@ -19,6 +23,7 @@
 // chunk-edge values travel through a handful of shared-memory exchange slots.  The Helmholtz solve
 // reuses the recursive-filter + cyclic affine scan of pk_core.h.
 #pragma once
+#include <cmath>
 #include "pk_core.h"
 
 namespace pk {
@@ -39,14 +44,31 @@ struct UpwindIO {
   int* fail_step;         // [R] in/out
 };
 
+// sign bit clear.  Equals (x > 0) except at x = +0 and NaN, where the flux s * (either side) is 0 / NaN anyway.
+PK_HD bool uw_positive(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x) >= 0;
+#else
+  return !std::signbit(x);
+#endif
+}
+// finite: exponent bits not all ones
+PK_HD bool uw_finite(double x) {
+#if defined(__CUDA_ARCH__)
+  return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000;
+#else
+  return std::isfinite(x);
+#endif
+}
+
 template <int M, int XARR, int TT = 0>
 struct UpwindThread {
   int t, m, s, tl, tr, active, ext;
   double mL[M], mR[M];       // m0: the state
   double aL[M], aR[M];       // trial
   double u[M];               // nodal u of my nodes
-  double sv[M];              // us at my nodes
-  double sR;                 // us at the first node of the right neighbour
+  double sv[M];              // s' = (2/h) us at my nodes
+  double sR;                 // s' at the first node of the right neighbour
   double hh[M];              // Helmholtz work
   double dw_hold;            // my pre-drawn Brownian increment (draw_step)
   static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
@@ -81,15 +103,20 @@ struct UpwindThread {
   template <class SH>
   PK_HD void begin_step(const Params& p, const SH& sh, const double* xi) {
     const int T = TN(p);
+    const double kdt = p.ih2 * p.dt;
+    const double Xc = (!XARR && p.nxi > 0) ? p.ih2 * (sh.dw(0) * p.xi_const) : 0.0;
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
-      double X = 0.0;
-      if (has_row(j)) {
-        if (XARR) { for (int k = 0; k < p.nxi; ++k) X += sh.dw(k) * xi[k * T * M + j * T + t]; }
-        else X = (p.nxi > 0) ? sh.dw(0) * p.xi_const : 0.0;
-      }
-      sv[j] = p.dt * u[j] + X;
+      sv[j] = kdt * u[j] + Xc;
       aL[j] = mL[j]; aR[j] = mR[j];
+    }
+    if (XARR) {
+      for (int k = 0; k < p.nxi; ++k) {
+        const double w = p.ih2 * sh.dw(k);
+        PK_UNROLL
+        for (int j = 0; j < M; ++j)
+          if (has_row(j)) sv[j] += w * xi[k * T * M + j * T + t];
+      }
     }
     sh.st(sh.xb, UW_S0 * T + t, sv[0]);
     sh.st(sh.xb, UW_A_L * T + t, aL[0]);
@@ -106,7 +133,7 @@ struct UpwindThread {
     const double dnR = sh.ld(sh.xb, inL * T + tr);   // trial value just right of my last vertex
     double nL[M], nR[M];
     // upwind flux at my first vertex; the flux at the right vertex of cell j is the left flux of cell j+1
-    double phi0 = sv[0] * (sv[0] > 0.0 ? upL : aL[0]);
+    double phi0 = sv[0] * (uw_positive(sv[0]) ? upL : aL[0]);
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       nL[j] = aL[j]; nR[j] = aR[j];
@@ -115,14 +142,16 @@ struct UpwindThread {
         const double s0 = sv[j], s1 = last ? sR : sv[j + 1 < M ? j + 1 : M - 1];
         const double a = aL[j], b = aR[j];
         const double right = last ? dnR : aL[j + 1 < M ? j + 1 : M - 1];
-        const double phi1 = s1 * (s1 > 0.0 ? b : right);
+        const double phi1 = s1 * (uw_positive(s1) ? b : right);
         const double ab = a + b;
-        const double r0 = phi0 - 0.5 * (s1 * ab);
-        const double r1 = 0.5 * (s0 * ab) - phi1;
-        const double d0 = p.ih2 * (2.0 * r0 - r1), d1 = p.ih2 * (2.0 * r1 - r0);   // M_e^-1
-        if (k == 1) { nL[j] = mL[j] + d0; nR[j] = mR[j] + d1; }
-        else if (k == 2) { nL[j] = 0.75 * mL[j] + 0.25 * (a + d0); nR[j] = 0.75 * mR[j] + 0.25 * (b + d1); }
-        else { nL[j] = (1.0 / 3.0) * mL[j] + (2.0 / 3.0) * (a + d0); nR[j] = (1.0 / 3.0) * mR[j] + (2.0 / 3.0) * (b + d1); }
+        const double c0 = 0.5 * s0 + s1, c1 = 0.5 * s1 + s0;
+        const double t0 = 2.0 * phi0 + phi1, t1 = 2.0 * phi1 + phi0;
+        // base + dm with dm0 = t0 - ab c0, dm1 = ab c1 - t1; base = m0 (stage 1) or the trial value (stages 2, 3)
+        const double e0 = (t0 + (k == 1 ? mL[j] : a)) - ab * c0;
+        const double e1 = ((k == 1 ? mR[j] : b) - t1) + ab * c1;
+        if (k == 1) { nL[j] = e0; nR[j] = e1; }
+        else if (k == 2) { nL[j] = 0.75 * mL[j] + 0.25 * e0; nR[j] = 0.75 * mR[j] + 0.25 * e1; }
+        else { nL[j] = (1.0 / 3.0) * mL[j] + (2.0 / 3.0) * e0; nR[j] = (1.0 / 3.0) * mR[j] + (2.0 / 3.0) * e1; }
         phi0 = phi1;
       }
     }
@@ -169,7 +198,7 @@ struct UpwindThread {
     for (int j = M - 1; j >= 0; --j) {
       if (has_row(j)) {
         u[j] = hh[j] + p.rpow[M - j] * in0;
-        ok = ok && (u[j] - u[j] == 0.0);
+        ok = ok && uw_finite(u[j]);
       }
     }
     return ok;
@@ -193,7 +222,7 @@ PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const Upwin
     // the reference's linear solves raise on a non-finite residual: a non-finite increment fails the
     // step before the state is touched; a blow-up of the state is caught one step after it happened
     bool bad = (*flag != 0);
-    for (int k = 0; k < p.nxi; ++k) { const double w = sh.dw(k); bad = bad || !(w - w == 0.0); }
+    for (int k = 0; k < p.nxi; ++k) bad = bad || !uw_finite(sh.dw(k));
     if (bad) { failed = (*flag != 0) ? io.step0 + n - 1 : io.step0 + n; continue; }
     ex.each([&](Th& th) { th.begin_step(p, sh, io.xi); });
     ex.sync();
