@@ -1328,6 +1328,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
             if (2 * d <= Tc - 2) ex.sync_local();
           }
           ex.sync();
+          ex.tick(13);
           ex.each([&](Th& th) { if ((th.t & (Tc - 1)) == 0) { th.pcr_step(p, sh, 1, base); th.reduce_publish(p, sh, XB_PP_BASE - base); } });
           base = XB_PP_BASE - base;
           ex.sync();
@@ -1339,6 +1340,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
           ex.tick(7);
           ex.each([&](Th& th) { if ((th.t & (Tc - 1)) == 0) th.pcr_final(p, sh, base); });
           ex.sync();
+          ex.tick(14);
           ex.each([&](Th& th) { if ((th.t & (Tc - 1)) != 0) th.part_back(p, sh, Tc); });
         } else if (ex.pingpong()) {
           // two row buffers: a step reads one and publishes into the other -> ONE barrier per PCR step

@@ -12,3 +12,5 @@ ckern_t pk_pick_cluster_kernel_m5(int mode, int Tc, int minb);
 ckern_t pk_pick_cluster_kernel_m6(int mode, int Tc, int minb);
 ckern_t pk_pick_cluster_kernel_m7(int mode, int Tc, int minb);
 ckern_t pk_pick_cluster_kernel_m8(int mode, int Tc, int minb);
+ckern_t pk_pick_cluster_kernel_m9(int mode, int Tc, int minb);
+ckern_t pk_pick_cluster_kernel_m10(int mode, int Tc, int minb);

@@ -1,9 +1,9 @@
-// pk_kernels_m.cu -- instantiates the step kernels for ONE chunk size PK_M (5..8); compiled four times.
+// pk_kernels_m.cu -- instantiates the step kernels for ONE chunk size PK_M (5..8; 9 and 10: cluster kernels only).
 #include "pk_kernels.cuh"
 #include "pk_dispatch.h"
 
 #ifndef PK_M
-#error "compile with -DPK_M=5|6|7|8"
+#error "compile with -DPK_M=5..10"
 #endif
 
 
@@ -11,7 +11,7 @@ template <int M> static ckern_t pick_cmode(int mode, int Tc, int minb) {
   if (PK_IS_TEST(mode)) return nullptr;      // scheme 'test': single-CTA meshes only
   if (Tc <= 256) {
     // two clusters share the SMs when two CTAs fit one SM's shared memory (128 registers per thread)
-    if (minb == 2 && mode == NOISE_SCALAR) return pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2>;
+    if constexpr (M <= 8) { if (minb == 2 && mode == NOISE_SCALAR) return pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2>; }
     switch (mode) {
       case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 256>;
       case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 256>;
@@ -25,6 +25,7 @@ template <int M> static ckern_t pick_cmode(int mode, int Tc, int minb) {
   }
 }
 
+#if PK_M <= 8
 template <int M, int MODE> static kern_t pick_tb(int block, int T, int minb) {
   if (T < 32) return pk_step_kernel<M, MODE, 32, 1, 0>;    // tiny meshes: some lanes of the single warp idle
   if (T == 128) {
@@ -53,7 +54,11 @@ template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {
   }
 }
 
+#endif
+
 #define PK_CAT2(a, b) a##b
 #define PK_CAT(a, b) PK_CAT2(a, b)
+#if PK_M <= 8
 kern_t PK_CAT(pk_pick_kernel_m, PK_M)(int mode, int block, int T, int minb) { return pick_mode<PK_M>(mode, block, T, minb); }
+#endif
 ckern_t PK_CAT(pk_pick_cluster_kernel_m, PK_M)(int mode, int Tc, int minb) { return pick_cmode<PK_M>(mode, Tc, minb); }

@@ -335,6 +335,8 @@ static ckern_t pick_cluster_kernel(const Params& p, int Tc, int minb) {
     case 6: return pk_pick_cluster_kernel_m6(p.mode, Tc, minb);
     case 7: return pk_pick_cluster_kernel_m7(p.mode, Tc, minb);
     case 8: return pk_pick_cluster_kernel_m8(p.mode, Tc, minb);
+    case 9: return pk_pick_cluster_kernel_m9(p.mode, Tc, minb);
+    case 10: return pk_pick_cluster_kernel_m10(p.mode, Tc, minb);
   }
   return nullptr;
 }
@@ -370,6 +372,11 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   p.stol = cfg->stol > 0 ? cfg->stol : 1e-8; p.divtol = cfg->divtol > 0 ? cfg->divtol : 1e4;
   p.xi_const = cfg->xi_const;
   if (!choose_layout(p.ne, &p.T, &p.M, &p.rem)) { delete c; return fail(nullptr, "pk_create: no thread layout for ne=%d", cfg->ne); }
+  // cluster meshes that would end at 5 rows per thread: 9 or 10 rows on half the threads (choose_layout_wide)
+  if (cfg->scheme == 0 && p.T > 512) {
+    const char* e = getenv("PK_NO_WIDE_CHUNKS");
+    if (!(e && atoi(e) == 1)) choose_layout_wide(p.ne, &p.T, &p.M, &p.rem);
+  }
   { // experiments: PK_FORCE_TM="T,M" overrides the layout (chunks of M or M-1 rows, M in 5..8)
     const char* e = getenv("PK_FORCE_TM"); int ft = 0, fm = 0;
     if (e && sscanf(e, "%d,%d", &ft, &fm) == 2) {
@@ -824,4 +831,6 @@ kern_t pk_pick_kernel_m7(int, int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m5(int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m6(int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m7(int, int, int) { return nullptr; }
+ckern_t pk_pick_cluster_kernel_m9(int, int, int) { return nullptr; }
+ckern_t pk_pick_cluster_kernel_m10(int, int, int) { return nullptr; }
 #endif

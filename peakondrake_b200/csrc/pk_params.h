@@ -47,7 +47,7 @@ struct Params {
   double c1q, c1h, c2h, h12, a212, dt12;   // c1/4, c1/2, c2/2, h/12, alphasq/12, dt/12: the Jacobian enters the Newton
                                            // matrix as N1'/2, f'/4 (+-), g'/2, assembled pre-scaled (exact binary scalings)
   double rho, ikappa;     // H = kappa (1 - rho S)(1 - rho S^-1): |rho|<1
-  double rpow[10];        // rho^0 .. rho^9 (chunk-local carry weights; a chunk has at most 8 rows)
+  double rpow[12];        // rho^0 .. rho^11 (chunk-local carry weights; a chunk has at most 10 rows)
   double irho;            // 1 / rho
   double ih2;             // 2 / h   (inverse DG1 element mass matrix M_e^-1 = (2/h) [[2,-1],[-1,2]])
   double c1k, c2k, h6k, a26k;   // c1, c2, h6, a26 times ikappa (Helmholtz right-hand sides pre-divided by kappa)
@@ -75,6 +75,21 @@ static inline bool choose_layout(int ne, int* T, int* M, int* rem) {
   return (*M >= 5 && *M <= 8);
 }
 
+// Wide chunks for the thread-block-cluster kernels: when the standard layout ends at 5 rows per thread (ne just above
+// a power of two times 4: ne = 20 000 -> 4096 x 5), half the threads with 9 or 10 rows each do the same assembly work
+// with half the separator rows, half the CTAs per cluster and one PCR level less.
+static inline bool choose_layout_wide(int ne, int* T, int* M, int* rem) {
+  int t, m, r;
+  if (!choose_layout(ne, &t, &m, &r) || m != 5 || t < 4) return false;
+  t /= 2;
+  const int lo = ne / t;
+  r = ne - lo * t;
+  if (r == 0) { m = lo; r = t; } else m = lo + 1;
+  if (m < 9 || m > 10) return false;
+  *T = t; *M = m; *rem = r;
+  return true;
+}
+
 static inline void fill_constants(Params& p) {
   const double h = p.h, a2 = p.alphasq;
   p.mb = h / 6.0; p.ma = 2.0 * h / 3.0;
@@ -91,7 +106,7 @@ static inline void fill_constants(Params& p) {
   p.rho = -p.hb / kappa;
   p.ikappa = 1.0 / kappa;
   p.rpow[0] = 1.0;
-  for (int i = 1; i < 10; ++i) p.rpow[i] = p.rpow[i - 1] * p.rho;
+  for (int i = 1; i < 12; ++i) p.rpow[i] = p.rpow[i - 1] * p.rho;
   p.irho = 1.0 / p.rho;
   p.ih2 = 2.0 / h;
   p.c1k = p.c1 * p.ikappa; p.c2k = p.c2 * p.ikappa; p.h6k = p.h6 * p.ikappa; p.a26k = p.a26 * p.ikappa;

@@ -31,7 +31,8 @@ buf = np.zeros((R, 16), dtype=np.int64)
 assert eng.lib.pk_profile_read(eng.ctx, buf.ctypes.data_as(ctypes.c_void_p)) == 0
 names = ['dW draw', 'noise fill', 'residual-only check', 'assemble_begin', 'assemble_finish(+LU,tips)',
          'allreduce+test', 'reduce build/publish', 'PCR steps', 'PCR final', 'interior solve',
-         'helm causal+scan', 'helm anticausal+scan+update', 'accept']
+         'helm causal+scan', 'helm anticausal+scan+update', 'accept',
+         'cluster: segment-local PCR', 'cluster: separator final + barrier']
 tot = buf.sum(1).mean()
 print('kernel %.3f ms; mean cycles per CTA per step %.0f (its/step %.2f)' % (ms, tot / K, eng.its_total.double().mean().item() / (2 * K)))
 for i, n in enumerate(names):

@@ -231,6 +231,7 @@ extern "C" int pk_emu_set_partitioned(int on) { g_emu_part = on; return 0; }
 extern "C" int pk_emu_set_block(int nblk) { g_emu_nblk = nblk; return 0; }
 
 extern "C" int pk_emu_layout(int ne, int* T, int* M, int* rem) { return choose_layout(ne, T, M, rem) ? 0 : -1; }
+extern "C" int pk_emu_layout_wide(int ne, int* T, int* M, int* rem) { return choose_layout_wide(ne, T, M, rem) ? 0 : -1; }
 
 extern "C" double pk_emu_philox_normal(unsigned long long seed, unsigned rid, unsigned step, unsigned mode, unsigned sub) {
   return philox_normal(seed, rid, step, mode, sub);
@@ -267,6 +268,8 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
       case 6: run_mode<6>(p, io, u, u1, dF, dG, order); break;
       case 7: run_mode<7>(p, io, u, u1, dF, dG, order); break;
       case 8: run_mode<8>(p, io, u, u1, dF, dG, order); break;
+      case 9: run_mode<9>(p, io, u, u1, dF, dG, order); break;
+      case 10: run_mode<10>(p, io, u, u1, dF, dG, order); break;
       default: return -3;
     }
   }

@@ -121,6 +121,37 @@ def test_cluster_layout_emulated(ne, C, part):
         L.pk_emu_set_partitioned(1)
 
 
+@pytest.mark.parametrize('ne,T,M,C', [(2500, 256, 10, 8), (2200, 256, 9, 4), (2350, 256, 10, 1), (1250, 128, 10, 2)])
+def test_wide_chunk_layouts_emulated(ne, T, M, C):
+    """9 or 10 rows per thread (choose_layout_wide): what the cluster kernels use where the standard layout would end
+    at 5 rows per thread (BASELINE config 5, ne = 20 000 -> 2048 threads x 10 rows, clusters of 8)."""
+    L = lib()
+    try:
+        assert L.pk_emu_set_cluster(C) == 0
+        compare(ne, nsteps=3, nxi=2, T=T, M=M)
+        compare(ne, nsteps=2, fam='constant', nxi=1, ic='periodic_peakon', sigma=0.5, T=T, M=M)
+        assert L.pk_emu_set_cluster(1) == 0
+    finally:
+        L.pk_emu_set_cluster(1)
+
+
+def test_wide_layout_choice():
+    import ctypes
+    L = lib()
+    T, M, rem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert L.pk_emu_layout_wide(20000, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem)) == 0
+    assert (T.value, M.value, rem.value) == (2048, 10, 1568)
+    assert L.pk_emu_layout_wide(17000, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem)) == 0
+    assert (T.value, M.value, rem.value) == (2048, 9, 616)
+    assert L.pk_emu_layout_wide(18432, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem)) == 0
+    assert (T.value, M.value, rem.value) == (2048, 9, 2048)
+    for ne in (16384, 24000, 1000, 12000):       # standard layout has 6..8 rows per thread: no wide variant
+        assert L.pk_emu_layout_wide(ne, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem)) != 0
+    for ne in (20000, 17000, 18432, 20480):
+        assert L.pk_emu_layout_wide(ne, ctypes.byref(T), ctypes.byref(M), ctypes.byref(rem)) == 0
+        assert rem.value * M.value + (T.value - rem.value) * (M.value - 1) == ne and 0 < rem.value <= T.value
+
+
 # ---- upwind / ssprk3 ---------------------------------------------------------------------------------
 @pytest.mark.parametrize('ne,nxi,fam', [(20, 7, 'sines'), (1000, 7, 'sines'), (200, 1, 'constant'), (333, 0, 'sines'), (9, 2, 'sines')])
 def test_upwind_kernel_emulated(ne, nxi, fam):
