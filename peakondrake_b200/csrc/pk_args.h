@@ -14,6 +14,7 @@ struct StepArgs {
   // single-CTA step kernel (persistent CTAs + work queue)
   int* queue;         // [1 + R]: work counter, then per realisation the number of finished step blocks
   int nblk;           // steps per work item
-  int part;           // cluster kernel: 1 = Schur solve partitioned by CTA (default), 0 = flat PCR over the cluster
+  int part;           // cluster kernel: 1 = Schur solve partitioned by CTA, separators solved redundantly in every CTA (default);
+                      // 2 = same, separators solved by the leading threads (a cluster barrier per level); 0 = flat PCR
   int nb;             // step blocks per realisation: items = nb * R, item i = (block i / R, realisation i % R)
 };

@@ -57,6 +57,9 @@ struct Shared {
 #endif
   }
   PK_HD void ld2l(const double* a, int q, int T, int tt, double& v0, double& v1) const { ld2(a, q, T, tt, v0, v1); }
+  // raw offsets into the calling CTA's own copy of an array (scratch use of dead exchange slots)
+  PK_HD double ldl(const double* a, int off) const { return a[off]; }
+  PK_HD void stl(double* a, int off, double v) const { a[off] = v; }
   PK_HD void st2o(double* a, int q, int T, int t, double v0, double v1) const {
 #if defined(__CUDA_ARCH__)
     reinterpret_cast<double2*>(a)[q * T + t] = make_double2(v0, v1);
@@ -677,9 +680,11 @@ struct Thread {
 
   // write my block row (L, U, D^-1, r) to the exchange slots 0..13
   template <class SH>
-  PK_HD void reduce_publish(const Params& p, const SH& sh, int base = 0) {
+  PK_HD void reduce_publish(const Params& p, const SH& sh, int base = 0, bool rawD = false) {
     const int T = TN(p);
-    double Di[4]; inv2(Db, Di);
+    double Di[4];
+    if (rawD) { Di[0] = Db[0]; Di[1] = Db[1]; Di[2] = Db[2]; Di[3] = Db[3]; }     // separator rows travel with D itself
+    else inv2(Db, Di);
     // seven 16-byte stores: (L0 L1)(L2 L3)(U0 U1)(U2 U3)(D^-1 ...)(r0 r1), pair slots base/2 .. base/2 + 6
     const int b2 = base >> 1;
     sh.st2o(sh.xb, b2 + 0, T, t, Lb[0], Lb[1]); sh.st2o(sh.xb, b2 + 1, T, t, Lb[2], Lb[3]);
@@ -774,6 +779,100 @@ struct Thread {
     inv2(Db, Di);
     xs0 = Di[0] * r0 + Di[1] * r1;
     xs1 = Di[2] * r0 + Di[3] * r1;
+    sh.sto(sh.xb, 14, T, t, xs0); sh.sto(sh.xb, 15, T, t, xs1);
+  }
+
+  // ---- separator system solved REDUNDANTLY by the first C threads of every CTA (no cluster barrier inside) ----
+  // Thread j < C of each CTA builds separator row j from three published rows (separator j with its raw diagonal
+  // block, the last interior row of segment j-1, the first interior row of segment j; DSMEM loads), then the C rows
+  // are reduced by PCR through a scratch area in the CTA's own shared memory (the row buffer that is not being
+  // read: 2 x C rows of 14 doubles, then the C solutions), with block barriers only.  The separator row lives in
+  // Lb/Ub/Db/rb of the solving thread, which reloads its own (published) row afterwards: no extra per-thread state.
+  static PK_HD int sep_scratch_doubles(int C) { return 30 * C; }
+  template <class SH>
+  PK_HD void sep_store(const SH& sh, int scr_off, int half, int C, int j) {
+    double Di[4]; inv2(Db, Di);
+    const int o = scr_off + (half * C + j) * 14;
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { sh.stl(sh.xb, o + c, Lb[c]); sh.stl(sh.xb, o + 4 + c, Ub[c]); sh.stl(sh.xb, o + 8 + c, Di[c]); }
+    sh.stl(sh.xb, o + 12, rb[0]); sh.stl(sh.xb, o + 13, rb[1]);
+  }
+  template <class SH>
+  PK_HD void sep_load(const SH& sh, int scr_off, int half, int C, int j, double* L_, double* U_, double* Di_, double* r_) const {
+    const int o = scr_off + (half * C + j) * 14;
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { L_[c] = sh.ldl(sh.xb, o + c); U_[c] = sh.ldl(sh.xb, o + 4 + c); Di_[c] = sh.ldl(sh.xb, o + 8 + c); }
+    r_[0] = sh.ldl(sh.xb, o + 12); r_[1] = sh.ldl(sh.xb, o + 13);
+  }
+  template <class SH>
+  PK_HD void sep_absorb(const double* Ll, const double* Ul, const double* Dl, const double* rl,
+                        const double* Lr, const double* Ur, const double* Dr, const double* rr) {
+    double al[4], ga[4], Ln[4], Un[4];
+    mm2(Lb, Dl, al); mm2(Ub, Dr, ga);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { al[c] = -al[c]; ga[c] = -ga[c]; }
+    mm2(al, Ll, Ln); mm2(ga, Ur, Un);
+    mma2(al, Ul, Db); mma2(ga, Lr, Db);
+    mva2(al, rl, rb); mva2(ga, rr, rb);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { Lb[c] = Ln[c]; Ub[c] = Un[c]; }
+  }
+  template <class SH>
+  PK_HD void sep_build(const Params& p, const SH& sh, int base, int Tc, int C, int scr_off) {
+    const int T = TN(p);
+    const int j = t & (Tc - 1), lead = j * Tc;
+    double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
+    pcr_load_row(p, sh, base >> 1, lead, Lb, Ub, Db, rb);                     // raw D (reduce_publish rawD)
+    pcr_load_row(p, sh, base >> 1, (lead + T - 1) & (T - 1), Ll, Ul, Dl, rl);
+    pcr_load_row(p, sh, base >> 1, lead + 1, Lr, Ur, Dr, rr);
+    sep_absorb<SH>(Ll, Ul, Dl, rl, Lr, Ur, Dr, rr);
+    sep_store(sh, scr_off, 0, C, j);
+  }
+  template <class SH>
+  PK_HD void sep_step(const SH& sh, int d, int half, int Tc, int C, int scr_off) {
+    const int j = t & (Tc - 1);
+    double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
+    sep_load(sh, scr_off, half, C, (j + C - d) & (C - 1), Ll, Ul, Dl, rl);
+    sep_load(sh, scr_off, half, C, (j + d) & (C - 1), Lr, Ur, Dr, rr);
+    sep_absorb<SH>(Ll, Ul, Dl, rl, Lr, Ur, Dr, rr);
+    sep_store(sh, scr_off, half ^ 1, C, j);
+  }
+  template <class SH>
+  PK_HD void sep_final(const SH& sh, int half, int Tc, int C, int scr_off) {
+    const int j = t & (Tc - 1);
+    double Lq[4], Uq[4], Dq[4], rq[2];
+    sep_load(sh, scr_off, half, C, (j + C / 2) & (C - 1), Lq, Uq, Dq, rq);
+    double S[4], Sq[4], SD[4], A[4], Ai[4], rhs[2];
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { S[c] = Lb[c] + Ub[c]; Sq[c] = Lq[c] + Uq[c]; A[c] = Db[c]; }
+    mm2(S, Dq, SD);
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) SD[c] = -SD[c];
+    mma2(SD, Sq, A);
+    rhs[0] = rb[0]; rhs[1] = rb[1];
+    mva2(SD, rq, rhs);
+    inv2(A, Ai);
+    sh.stl(sh.xb, scr_off + 28 * C + 2 * j, Ai[0] * rhs[0] + Ai[1] * rhs[1]);
+    sh.stl(sh.xb, scr_off + 28 * C + 2 * j + 1, Ai[2] * rhs[0] + Ai[3] * rhs[1]);
+  }
+  // every thread: its separator-pair solution from the separators of its own and the next segment
+  template <class SH>
+  PK_HD void part_back_local(const Params& p, const SH& sh, int Tc, int C, int scr_off, int base) {
+    const int T = TN(p);
+    const int k = t / Tc, kn = (k + 1) & (C - 1);
+    const double sL_[2] = {sh.ldl(sh.xb, scr_off + 28 * C + 2 * k), sh.ldl(sh.xb, scr_off + 28 * C + 2 * k + 1)};
+    if ((t & (Tc - 1)) == 0) { xs0 = sL_[0]; xs1 = sL_[1]; }
+    else {
+      const double sR_[2] = {sh.ldl(sh.xb, scr_off + 28 * C + 2 * kn), sh.ldl(sh.xb, scr_off + 28 * C + 2 * kn + 1)};
+      double tmp[2] = {0.0, 0.0}, Di[4];
+      // the threads that solved a separator row get their own row back from the published copy (L, U, D^-1, r)
+      if ((t & (Tc - 1)) < C) pcr_load_row_local(p, sh, base >> 1, t, Lb, Ub, Di, rb);
+      else inv2(Db, Di);
+      mva2(Lb, sL_, tmp); mva2(Ub, sR_, tmp);
+      const double r0 = rb[0] - tmp[0], r1 = rb[1] - tmp[1];
+      xs0 = Di[0] * r0 + Di[1] * r1;
+      xs1 = Di[2] * r0 + Di[3] * r1;
+    }
     sh.sto(sh.xb, 14, T, t, xs0); sh.sto(sh.xb, 15, T, t, xs1);
   }
 
@@ -1321,14 +1420,32 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
         ex.tick(6);
         if (ex.partitioned()) {
           // segment-local PCR (block-local barriers and loads), then PCR among the C separators
-          const int Tc = ex.tc();
+          const int Tc = ex.tc(), Cn = Tn / Tc;
+          // separators solved redundantly in every CTA when the idle row buffer can hold the scratch rows
+          const bool red = ex.redundant() && 14 * Tc >= Th::sep_scratch_doubles(Cn);
           for (int d = 1; d <= Tc - 2; d *= 2) {
-            ex.each([&](Th& th) { th.pcr_step_local(p, sh, d, base, Tc); th.reduce_publish(p, sh, XB_PP_BASE - base); });
+            ex.each([&](Th& th) { th.pcr_step_local(p, sh, d, base, Tc); th.reduce_publish(p, sh, XB_PP_BASE - base, red && (th.t & (Tc - 1)) == 0); });
             base = XB_PP_BASE - base;
             if (2 * d <= Tc - 2) ex.sync_local();
           }
           ex.sync();
           ex.tick(13);
+          if (red) {
+            const int scr = (XB_PP_BASE - base) * Tc;      // offset of the idle row buffer in the CTA's exchange area
+            ex.each_cta_first(Cn, [&](Th& th) { th.sep_build(p, sh, base, Tc, Cn, scr); });
+            ex.sync_local();
+            int half = 0;
+            for (int d = 1; d < Cn / 2; d *= 2) {
+              ex.each_cta_first(Cn, [&](Th& th) { th.sep_step(sh, d, half, Tc, Cn, scr); });
+              half ^= 1;
+              ex.sync_local();
+            }
+            ex.tick(7);
+            ex.each_cta_first(Cn, [&](Th& th) { th.sep_final(sh, half, Tc, Cn, scr); });
+            ex.sync_local();
+            ex.tick(14);
+            ex.each([&](Th& th) { th.part_back_local(p, sh, Tc, Cn, scr, base); });
+          } else {
           ex.each([&](Th& th) { if ((th.t & (Tc - 1)) == 0) { th.pcr_step(p, sh, 1, base); th.reduce_publish(p, sh, XB_PP_BASE - base); } });
           base = XB_PP_BASE - base;
           ex.sync();
@@ -1342,6 +1459,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
           ex.sync();
           ex.tick(14);
           ex.each([&](Th& th) { if ((th.t & (Tc - 1)) != 0) th.part_back(p, sh, Tc); });
+          }
         } else if (ex.pingpong()) {
           // two row buffers: a step reads one and publishes into the other -> ONE barrier per PCR step
           for (int d = 1; d < Tn / 2; d *= 2) {

@@ -41,6 +41,8 @@ struct GpuExecT {
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
   __device__ __forceinline__ bool pingpong() const { return false; }     // no shared memory to spare at 3 CTAs/SM
   __device__ __forceinline__ bool partitioned() const { return false; }
+  __device__ __forceinline__ bool redundant() const { return false; }
+  template <class F> __device__ __forceinline__ void each_cta_first(int, F) {}
   __device__ __forceinline__ int tc() const { return (int)blockDim.x; }
   __device__ __forceinline__ void sync_local() { __syncthreads(); }
   // compacted Schur solve (pk_core.h, hyb_*): needs >= 32 threads per realisation, all of one block.  Measured
@@ -271,6 +273,8 @@ struct SharedCluster {
     const double2 v = reinterpret_cast<const double2*>(a)[(q << lgTc) + (tt & (Tc - 1))];
     v0 = v.x; v1 = v.y;
   }
+  __device__ __forceinline__ double ldl(const double* a, int off) const { return a[off]; }
+  __device__ __forceinline__ void stl(double* a, int off, double v) const { a[off] = v; }
   __device__ __forceinline__ void st2o(double* a, int q, int, int, double v0, double v1) const {
     reinterpret_cast<double2*>(a)[(q << lgTc) + (int)threadIdx.x] = make_double2(v0, v1);
   }
@@ -309,6 +313,8 @@ struct GpuExecCluster {
   // over all C*Tc rows (every step a cluster barrier and, from stride Tc/2 on, DSMEM-bandwidth-bound row loads).
   int part;
   __device__ __forceinline__ bool partitioned() const { return part != 0; }
+  __device__ __forceinline__ bool redundant() const { return part == 1; }      // part = 2: separators by the leading threads
+  template <class F> __device__ __forceinline__ void each_cta_first(int n, F f) { if ((int)threadIdx.x < n) f(th); }
   __device__ __forceinline__ int tc() const { return (int)blockDim.x; }
   __device__ __forceinline__ void sync_local() { __syncthreads(); }
   template <class F> __device__ __forceinline__ void each_first(int, F) {}

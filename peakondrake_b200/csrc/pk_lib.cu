@@ -421,7 +421,10 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     c->cluster = C; c->block = Tc; c->lgTc = lg; c->smem = sm;
     // two CTAs per SM (two clusters interleaved on the same SMs) when the shared memory allows it
     c->cminb = 1;
-    if (Tc == 256 && p.mode == NOISE_SCALAR && 2 * (sm + 1024) <= 227 * 1024) {
+    // (since the Schur solve is partitioned by CTA the spill-free 255-register variant with ONE cluster per SM set is
+    //  as fast or faster -- C4 3.91e5 vs 3.85e5 realisation-steps/s -- so sharing is opt-in: PK_CLUSTER_MINB=2)
+    const char* e2 = getenv("PK_CLUSTER_MINB");
+    if (e2 && atoi(e2) == 2 && Tc == 256 && p.mode == NOISE_SCALAR && 2 * (sm + 1024) <= 227 * 1024) {
       // does the 128-register variant really get two CTAs per SM?
       cudaSetDevice(cfg->device);
       const void* k2 = (const void*)pick_cluster_kernel(p, Tc, 2);
@@ -431,7 +434,6 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
         c->cminb = 2;
       cudaGetLastError();
     }
-    { const char* e = getenv("PK_CLUSTER_MINB"); if (e && atoi(e) == 1) c->cminb = 1; }
   }
   c->xi = c->xi_x = c->xi_xx = nullptr;
   c->w1_resident = false;
@@ -569,7 +571,8 @@ static int step_args(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* d
   a->dW_in = dW_in; a->dW_out = dW_out; a->fail_step = fail_step; a->its_last = its_last; a->its_total = its_total;
   a->prof = c->d_prof;
   a->queue = nullptr; a->nblk = nsteps; a->nb = 1; a->r0 = 0; a->Rq = c->cfg.R;
-  { const char* e = getenv("PK_CLUSTER_FLAT_PCR"); a->part = (e && atoi(e) == 1) ? 0 : 1; }
+  { const char* e = getenv("PK_CLUSTER_FLAT_PCR"); a->part = (e && atoi(e) == 1) ? 0 : 1;
+    e = getenv("PK_CLUSTER_LEADER_SEP"); if (a->part && e && atoi(e) == 1) a->part = 2; }
   a->R = c->cfg.R; a->step0 = (int)c->step; a->nsteps = nsteps; a->rid0 = c->cfg.rid_offset; a->seed = c->cfg.seed;
   return 0;
 }

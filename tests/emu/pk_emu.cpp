@@ -57,6 +57,8 @@ struct EmuSharedCluster {
   // own-slot accessors: must be block-local (checked like the device's sto/ldo, which do not decode)
   double ldo(const double* a, int j, int T, int t) const { if (((t & ((1 << lgT) - 1)) >> lgTc) != *cur) ++*bad; return *at(a, j * T + t, false); }
   void sto(double* a, int j, int T, int t, double v) const { *at(a, j * T + t, true) = v; }
+  double ldl(const double* a, int off) const { return (*bufs)[*cur][(a - (const double*)0) + off]; }
+  void stl(double* a, int off, double v) const { (*bufs)[*cur][(a - (double*)0) + off] = v; }
   double dw(int k) const { return (*bufs)[*cur][(dW - (double*)0) + k]; }
   void set_dw(int k, double v) const { (*bufs)[*cur][(dW - (double*)0) + k] = v; }
 };
@@ -88,6 +90,11 @@ struct EmuExecT {
   bool hybrid(int Tn) const { return g_emu_hybrid && C == 1 && Tn >= 32; }
   bool pingpong() const { return C > 1; }      // like the cluster kernel: XB_SLOTS_PP slots
   bool partitioned() const { return C > 1 && g_emu_part; }
+  bool redundant() const { return g_emu_part == 1; }
+  template <class F> void each_cta_first(int n, F f) {
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < n && k < Tc; ++k) { const int kk = order == 0 ? k : n - 1 - k; cur = c; f(th[c * Tc + kk]); }
+  }
   int tc() const { return Tc; }
   void sync_local() {}
   template <class F> void each_first(int n, F f) {

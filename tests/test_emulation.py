@@ -104,11 +104,12 @@ def test_philox_generator_statistics_and_reproducibility():
 
 
 @pytest.mark.parametrize('ne,C,part', [(1000, 2, 1), (1000, 4, 1), (250, 2, 1), (2000, 8, 1), (2000, 16, 1), (128, 8, 1), (256, 8, 1), (200, 2, 1),
-                                        (1000, 4, 0), (2000, 8, 0)])
+                                        (1000, 4, 0), (2000, 8, 0), (1000, 4, 2), (2000, 8, 2), (2000, 16, 2)])
 def test_cluster_layout_emulated(ne, C, part):
     """Thread-block-cluster variant (large meshes): shared arrays distributed over C CTAs, foreign
     rows read remotely, every store local -- same decode as SharedCluster in pk_lib.cu.  part=1: Schur solve
-    partitioned by CTA (segment-local PCR + PCR among the C separators, the device default); part=0: flat PCR."""
+    partitioned by CTA (segment-local PCR, the C separators solved redundantly in every CTA: the device default);
+    part=2: separators solved by the leading threads; part=0: flat PCR."""
     L = lib()
     try:
         L.pk_emu_set_partitioned(part)
