@@ -71,6 +71,9 @@ struct Shared {
   PK_HD void set_dw(int k, double v) const { dW[k] = v; }
 };
 
+// windowed drawing of the Brownian increments (draw_step): the (step, mode) pair a thread owns inside a window
+struct DrawSlot { int mine = 0, k = 0; };
+
 enum { XB_SLOTS = 18, XB_SLOTS_PP = 30, XB_PP_BASE = 16 };   // _PP: room for a second PCR row buffer (slots 16..29;
                                                              // 16, 17 are dead while the PCR runs, 14, 15 receive its result)
 
@@ -248,6 +251,7 @@ struct Thread {
   double fn2, sn2, xn2;           // partial sums: |R|^2, |delta|^2, |w1|^2
   double Xs;                      // NOISE_SCALAR: dXi value of this step
   double dw_hold;                 // my pre-drawn Brownian increment (draw_step)
+  DrawSlot dw_slot;               // which (step, mode) of a window it belongs to
 
   PK_HD void init(const Params& p, int tid) {
     t = tid; active = (tid < TN(p));
@@ -1245,7 +1249,21 @@ struct DrawIO {
   unsigned rid;
   unsigned long long seed;
   int n0 = 0;             // first step (launch-local index) this call sequence executes: a window is (re)drawn there too
+  // windowed drawing (nxi <= threads): per = steps per window, w0 = first step of the current window.  Set by
+  // draw_begin() once and advanced by draw_advance() every step (no integer division in the step loop).
+  int per = 0, w0 = 0;
 };
+PK_HD void draw_begin(const Params& p, DrawIO& d, int nth) {
+  if (p.nxi <= 0 || p.nxi > nth) return;
+  d.per = nth / p.nxi;
+  d.w0 = d.n0 - (d.n0 % d.per);
+}
+PK_HD void draw_advance(DrawIO& d, int n) { if (d.per > 0 && n - d.w0 >= d.per) d.w0 += d.per; }
+PK_HD DrawSlot draw_slot(const Params& p, int tid) {
+  DrawSlot s;
+  if (p.nxi > 0) { s.mine = tid / p.nxi; s.k = tid - s.mine * p.nxi; }
+  return s;
+}
 PK_HD double draw_one(const Params& p, const DrawIO& d, int n, int k) {
   const long long o = ((long long)n * d.R + d.r) * p.nxi + k;
   if (d.dW_in) return d.dW_in[o];
@@ -1255,7 +1273,7 @@ PK_HD double draw_one(const Params& p, const DrawIO& d, int n, int k) {
   return w;
 }
 template <class SH>
-PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int tid, int nth, bool leader, double& hold) {
+PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int tid, int nth, bool leader, double& hold, const DrawSlot& slot) {
   if (p.nxi <= 0) return;
   if (p.nxi > nth) {                       // more modes than threads: plain loop
     for (int k = tid; k < p.nxi; k += nth) {
@@ -1265,9 +1283,8 @@ PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int 
     }
     return;
   }
-  const int per = nth / p.nxi;             // steps per window
-  const int mine = tid / p.nxi, k = tid - mine * p.nxi;
-  const int w0 = n - (n % per);            // first step of the current window
+  const int per = d.per, w0 = d.w0;        // steps per window, first step of the current window
+  const int mine = slot.mine, k = slot.k;
   if ((n == w0 || n == d.n0) && mine < per && w0 + mine < d.nsteps) hold = draw_one(p, d, w0 + mine, k);
   if (mine == n - w0 && mine < per) {
     sh.set_dw(k, hold);
@@ -1344,11 +1361,13 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
   dio.dW_in = io.dW_in; dio.dW_out = io.dW_out; dio.R = io.R; dio.r = io.r; dio.step0 = io.step0;
   dio.nsteps = io.nsteps; dio.rid = io.rid; dio.seed = io.seed; dio.n0 = io.n0;
   int expect = 2;     // iteration at which convergence is expected: there only the residual is evaluated first
+  ex.each_tid([&](Th& th, int tid, int nth, bool, int, int) { th.dw_slot = draw_slot(p, tid); if (dio.per == 0) draw_begin(p, dio, nth); });
   for (int n = io.n0; n < io.n1; ++n) {
     ex.each([&](Th& th) { th.kill_all(); });
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
+    draw_advance(dio, n);
     ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
-      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold);
+      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold, th.dw_slot);
     });
     ex.sync();
     ex.tick(0);

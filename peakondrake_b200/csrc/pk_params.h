@@ -49,6 +49,7 @@ struct Params {
   double rho, ikappa;     // H = kappa (1 - rho S)(1 - rho S^-1): |rho|<1
   double rpow[12];        // rho^0 .. rho^11 (chunk-local carry weights; a chunk has at most 10 rows)
   double irho;            // 1 / rho
+  double inv1mrn;         // 1 / (1 - rho^ne): cyclic closure of the Helmholtz scans
   double ih2;             // 2 / h   (inverse DG1 element mass matrix M_e^-1 = (2/h) [[2,-1],[-1,2]])
   double c1k, c2k, h6k, a26k;   // c1, c2, h6, a26 times ikappa (Helmholtz right-hand sides pre-divided by kappa)
   double rtol, atol, stol, divtol;  // PETSc SNES defaults 1e-8, 1e-50, 1e-8, 1e4
@@ -108,6 +109,7 @@ static inline void fill_constants(Params& p) {
   p.rpow[0] = 1.0;
   for (int i = 1; i < 12; ++i) p.rpow[i] = p.rpow[i - 1] * p.rho;
   p.irho = 1.0 / p.rho;
+  p.inv1mrn = 1.0 / (1.0 - std::pow(p.rho, (double)p.ne));
   p.ih2 = 2.0 / h;
   p.c1k = p.c1 * p.ikappa; p.c2k = p.c2 * p.ikappa; p.h6k = p.h6 * p.ikappa; p.a26k = p.a26 * p.ikappa;
   p.sdt = std::sqrt(p.dt / (p.nupd > 0 ? p.nupd : 1));

@@ -71,6 +71,7 @@ struct UpwindThread {
   double sR;                 // s' at the first node of the right neighbour
   double hh[M];              // Helmholtz work
   double dw_hold;            // my pre-drawn Brownian increment (draw_step)
+  DrawSlot dw_slot;
   static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
 
   PK_HD void init(const Params& p, int tid) {
@@ -213,16 +214,18 @@ PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const Upwin
   dio.nsteps = io.nsteps; dio.rid = io.rid; dio.seed = io.seed;
   ex.each([&](Th& th) { th.load(p, io); });
   ex.one([&]() { *flag = 0; });
+  ex.each_tid([&](Th& th, int tid, int nth, bool, int, int) { th.dw_slot = draw_slot(p, tid); if (dio.per == 0) draw_begin(p, dio, nth); });
   for (int n = 0; n < io.nsteps; ++n) {
+    draw_advance(dio, n);
     ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
-      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold);
+      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold, th.dw_slot);
     });
     ex.sync();
     if (failed >= 0) continue;
     // the reference's linear solves raise on a non-finite residual: a non-finite increment fails the
     // step before the state is touched; a blow-up of the state is caught one step after it happened
     bool bad = (*flag != 0);
-    for (int k = 0; k < p.nxi; ++k) bad = bad || !uw_finite(sh.dw(k));
+    { double sw = 0.0; for (int k = 0; k < p.nxi; ++k) sw += sh.dw(k); bad = bad || !uw_finite(sw); }   // any non-finite increment makes the sum non-finite
     if (bad) { failed = (*flag != 0) ? io.step0 + n - 1 : io.step0 + n; continue; }
     ex.each([&](Th& th) { th.begin_step(p, sh, io.xi); });
     ex.sync();

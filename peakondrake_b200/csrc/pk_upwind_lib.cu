@@ -9,13 +9,15 @@
 using namespace pk;
 
 // the block executor of pk_lib.cu, restated for this translation unit (same collectives)
-template <class ThT, bool AA>
+template <class ThT, bool AA, int TBC = 0>
 struct UwExec {
   typedef ThT Th;
+  static __device__ __forceinline__ int nwarps() { return TBC > 0 ? TBC / 32 : (int)(blockDim.x >> 5); }
   Th& th;
   double* red;
   int flip, ne_;
   double rA, rc0, rc1;
+  double inv;           // 1 / (1 - rho^ne): the cyclic closure of both scans (the product of all maps' A is rho^ne)
   __device__ __forceinline__ UwExec(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
   template <class F> __device__ __forceinline__ void each(F f) { if (AA || th.active) f(th); }
   template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, (int)blockDim.x, true, 0, ne_); }
@@ -23,14 +25,14 @@ struct UwExec {
   __device__ __forceinline__ void tick(int) {}
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
   __device__ __forceinline__ double* area() {
-    const int nw = blockDim.x >> 5;
+    const int nw = nwarps();
     double* a = red + flip * 3 * nw;
     flip ^= 1;
     return a;
   }
   template <int DIR>
   __device__ __forceinline__ void cyc_scan(double A, double c0, double& in0) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       double Ao, c0o;
@@ -43,14 +45,27 @@ struct UwExec {
     double* sc = area();
     if (lane == last) { sc[w] = A; sc[nw + w] = c0; }
     __syncthreads();
-    double tA = 1.0, t0 = 0.0, eA = 1.0, e0 = 0.0;
-    for (int k = 0; k < nw; ++k) {
-      const int ww = (DIR > 0) ? k : nw - 1 - k;
-      if (ww == w) { eA = tA; e0 = t0; }
-      const double a = sc[ww];
-      t0 = a * t0 + sc[nw + ww]; tA = a * tA;
+    // compose the warp aggregates in scan order: first the `pos` warps in front of mine (their composition enters my
+    // warp), then the rest (warp-uniform branches, no selects; unrolled exactly when the warp count is a constant)
+    double tA = 1.0, t0 = 0.0;
+    const int pos = (DIR > 0) ? w : nw - 1 - w;
+#pragma unroll
+    for (int k = 0; k < (TBC > 0 ? TBC / 32 : nw); ++k) {
+      if (k < pos) {
+        const int ww = (DIR > 0) ? k : nw - 1 - k;
+        const double a = sc[ww];
+        t0 = a * t0 + sc[nw + ww]; tA = a * tA;
+      }
     }
-    const double x0 = t0 * PK_RCP(1.0 - tA);
+    const double eA = tA, e0 = t0;
+#pragma unroll
+    for (int k = 0; k < (TBC > 0 ? TBC / 32 : nw); ++k) {
+      if (k >= pos) {
+        const int ww = (DIR > 0) ? k : nw - 1 - k;
+        t0 = sc[ww] * t0 + sc[nw + ww];
+      }
+    }
+    const double x0 = t0 * inv;
     const double w0 = eA * x0 + e0;
     const double o0 = A * w0 + c0;
     const double p0 = (DIR > 0) ? __shfl_up_sync(0xffffffffu, o0, 1) : __shfl_down_sync(0xffffffffu, o0, 1);
@@ -95,13 +110,13 @@ __global__ void __launch_bounds__(TB, MINB) pk_upwind_kernel(const __grid_consta
   typedef UpwindThread<M, XARR, TT> Th;
   Th th;
   th.init(p, threadIdx.x);
-  UwExec<Th, (TB > 32)> ex(th, red);
-  ex.ne_ = p.ne;
+  UwExec<Th, (TB > 32), TT> ex(th, red);
+  ex.ne_ = p.ne; ex.inv = p.inv1mrn;
   UpwindIO io;
   io.m = a.m; io.u = a.u; io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi;
   io.R = a.R; io.r = blockIdx.x; io.rid = a.rid0 + blockIdx.x; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step;
-  run_upwind_steps<M, XARR, TT, UwExec<Th, (TB > 32)>, Th>(ex, p, sh, io, flag);
+  run_upwind_steps<M, XARR, TT, UwExec<Th, (TB > 32), TT>, Th>(ex, p, sh, io, flag);
 }
 
 typedef void (*ukern_t)(const Params, const UpwindArgs);

@@ -1,7 +1,9 @@
 """Summaries kept under profiles/ from the scratch captures in gpurun_out/:
-   python profiles/summarise_ncu.py <tag>     (reads gpurun_out/prof_<tag>.ncu-rep, launches_<tag>.csv, bench_<tag>.log)"""
+   python profiles/summarise_ncu.py <tag> [kernel-label]    (reads gpurun_out/prof_<tag>.ncu-rep, launches_<tag>.csv,
+   bench_<tag>.log; writes profiles/<tag>_ncu_full_<kernel-label>.csv, label default pk_step_kernel)"""
 import csv, collections, os, subprocess, sys
 tag = sys.argv[1]
+label = sys.argv[2] if len(sys.argv) > 2 else 'pk_step_kernel'
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 go = os.path.join(root, 'gpurun_out')
 raw = subprocess.run(['ncu', '-i', os.path.join(go, 'prof_%s.ncu-rep' % tag), '--page', 'raw', '--csv'],
@@ -19,7 +21,7 @@ keep = ['Kernel Name', 'Block Size', 'Grid Size', 'dram__bytes_read.sum', 'dram_
         'smsp__inst_executed.sum', 'sm__icc_request_hit_rate.pct', 'sm__icc_requests.sum.pct_of_peak_sustained_elapsed',
         'gcc__cache_requests_type_instruction.sum', 'gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed',
         'smsp__issue_active.avg.per_cycle_active']
-with open(os.path.join(root, 'profiles', '%s_ncu_full_pk_step_kernel.csv' % tag), 'w') as f:
+with open(os.path.join(root, 'profiles', '%s_ncu_full_%s.csv' % (tag, label)), 'w') as f:
     f.write('metric,unit,value\n')
     for h, u, v in zip(hdr, units, vals):
         if h in keep or (h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio')):

@@ -323,6 +323,25 @@ def test_cluster_with_noise_tables_4096():
     assert run_case(4096, 2, 4, nxi=4) <= TOL
 
 
+def test_wide_chunk_cluster_layouts(monkeypatch):
+    # meshes whose standard layout ends at 5 rows per thread run with 9 / 10 rows on half the threads
+    from peakondrake_b200 import EnsembleIntegrator
+    for ne, rows in ((20000, 10), (17000, 9)):
+        eng = EnsembleIntegrator(ne, 40.0, 1e-3, 1, num_Xis=1, Xi_family='constant', sigma=0.2)
+        assert eng.layout['threads'] == 2048 and eng.layout['rows_per_thread'] == rows and eng.layout['ctas_per_realisation'] == 8
+        eng.close()
+    assert run_case(17000, 2, 3, ic='periodic_peakon', fam='constant', nxi=1, sigma=0.5) <= TOL
+    assert run_case(20000, 1, 2, nxi=4) <= TOL                 # 10 rows per thread with noise tables (7 fields in smem)
+    # the standard layout and the older Schur-solve variants stay selectable for A/B runs and agree with the oracle too
+    monkeypatch.setenv('PK_NO_WIDE_CHUNKS', '1')
+    assert run_case(20000, 1, 2, ic='periodic_peakon', fam='constant', nxi=1, sigma=1.0, dt=1e-2) <= TOL
+    monkeypatch.delenv('PK_NO_WIDE_CHUNKS')
+    for var in ('PK_CLUSTER_FLAT_PCR', 'PK_CLUSTER_LEADER_SEP'):
+        monkeypatch.setenv(var, '1')
+        assert run_case(16384, 1, 2, ic='new_peak', fam='constant', nxi=1, sigma=0.2, dt=5e-4, peak_width=1 / 6) <= TOL
+        monkeypatch.delenv(var)
+
+
 # ---- upwind / ssprk3 (equations.py:28-61,172-185) ---------------------------------------------------
 def run_upwind_case(ne, R, nsteps, ic='one_peak', fam='sines', nxi=7, sigma=0.25, dt=1e-3, Ld=40.0):
     import torch
