@@ -115,8 +115,7 @@ struct UpwindThread {
       for (int k = 0; k < p.nxi; ++k) {
         const double w = p.ih2 * sh.dw(k);
         PK_UNROLL
-        for (int j = 0; j < M; ++j)
-          if (has_row(j)) sv[j] += w * xi[k * T * M + j * T + t];
+        for (int j = 0; j < M; ++j) sv[j] += w * xi[k * T * M + j * T + t];      // padding rows of the table are 0
       }
     }
     sh.st(sh.xb, UW_S0 * T + t, sv[0]);
@@ -124,40 +123,39 @@ struct UpwindThread {
     sh.st(sh.xb, UW_A_R * T + t, ext ? aR[M - 1] : aR[M - 2]);
   }
 
-  // one SSPRK3 stage: d = dm(trial) and the stage combination, edges published to the other slot set
+  // one SSPRK3 stage: d = dm(trial) and the stage combination, edges published to the other slot set.
+  // Short chunks (M-1 cells) carry a GHOST cell M-1: a copy of the right neighbour's first cell (trial value and
+  // velocity), refreshed at the start of every stage, so that the loop below is the same straight-line code for
+  // every thread (no per-row existence tests or selects); what the ghost computes is never published or stored.
   template <class SH>
   PK_HD void stage(const Params& p, const SH& sh, int k) {
     const int T = TN(p);
     const int inL = (k == 2) ? UW_B_L : UW_A_L, inR = (k == 2) ? UW_B_R : UW_A_R;
-    if (k == 1) sR = sh.ld(sh.xb, UW_S0 * T + tr);     // us at the node right of my last cell
+    if (k == 1) sR = sh.ld(sh.xb, UW_S0 * T + tr);     // s' at the node right of my last cell
     const double upL = sh.ld(sh.xb, inR * T + tl);   // trial value just left of my first vertex
     const double dnR = sh.ld(sh.xb, inL * T + tr);   // trial value just right of my last vertex
-    double nL[M], nR[M];
+    if (!ext) { aL[M - 1] = dnR; if (k == 1) sv[M - 1] = sR; }
     // upwind flux at my first vertex; the flux at the right vertex of cell j is the left flux of cell j+1
     double phi0 = sv[0] * (uw_positive(sv[0]) ? upL : aL[0]);
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
-      nL[j] = aL[j]; nR[j] = aR[j];
-      if (has_row(j)) {
-        const bool last = (j == M - 1) || (j == M - 2 && !ext);
-        const double s0 = sv[j], s1 = last ? sR : sv[j + 1 < M ? j + 1 : M - 1];
-        const double a = aL[j], b = aR[j];
-        const double right = last ? dnR : aL[j + 1 < M ? j + 1 : M - 1];
-        const double phi1 = s1 * (uw_positive(s1) ? b : right);
-        const double ab = a + b;
-        const double c0 = 0.5 * s0 + s1, c1 = 0.5 * s1 + s0;
-        const double t0 = 2.0 * phi0 + phi1, t1 = 2.0 * phi1 + phi0;
-        // base + dm with dm0 = t0 - ab c0, dm1 = ab c1 - t1; base = m0 (stage 1) or the trial value (stages 2, 3)
-        const double e0 = (t0 + (k == 1 ? mL[j] : a)) - ab * c0;
-        const double e1 = ((k == 1 ? mR[j] : b) - t1) + ab * c1;
-        if (k == 1) { nL[j] = e0; nR[j] = e1; }
-        else if (k == 2) { nL[j] = 0.75 * mL[j] + 0.25 * e0; nR[j] = 0.75 * mR[j] + 0.25 * e1; }
-        else { nL[j] = (1.0 / 3.0) * mL[j] + (2.0 / 3.0) * e0; nR[j] = (1.0 / 3.0) * mR[j] + (2.0 / 3.0) * e1; }
-        phi0 = phi1;
-      }
+      const bool last = (j == M - 1);
+      const double s0 = sv[j], s1 = last ? sR : sv[j + 1 < M ? j + 1 : M - 1];
+      const double a = aL[j], b = aR[j];
+      const double right = last ? dnR : aL[j + 1 < M ? j + 1 : M - 1];
+      const double phi1 = s1 * (uw_positive(s1) ? b : right);
+      const double ab = a + b;
+      const double c0 = 0.5 * s0 + s1, c1 = 0.5 * s1 + s0;
+      const double t0 = 2.0 * phi0 + phi1, t1 = 2.0 * phi1 + phi0;
+      // base + dm with dm0 = t0 - ab c0, dm1 = ab c1 - t1; base = m0 (stage 1) or the trial value (stages 2, 3)
+      const double e0 = (t0 + (k == 1 ? mL[j] : a)) - ab * c0;
+      const double e1 = ((k == 1 ? mR[j] : b) - t1) + ab * c1;
+      // in place: cell j+1 reads only its own trial values and the carried flux
+      if (k == 1) { aL[j] = e0; aR[j] = e1; }
+      else if (k == 2) { aL[j] = 0.75 * mL[j] + 0.25 * e0; aR[j] = 0.75 * mR[j] + 0.25 * e1; }
+      else { aL[j] = (1.0 / 3.0) * mL[j] + (2.0 / 3.0) * e0; aR[j] = (1.0 / 3.0) * mR[j] + (2.0 / 3.0) * e1; }
+      phi0 = phi1;
     }
-    PK_UNROLL
-    for (int j = 0; j < M; ++j) { aL[j] = nL[j]; aR[j] = nR[j]; }
     const double lastL = ext ? aL[M - 1] : aL[M - 2], lastR = ext ? aR[M - 1] : aR[M - 2];
     if (k == 1) { sh.st(sh.xb, UW_B_L * T + t, aL[0]); sh.st(sh.xb, UW_B_R * T + t, lastR); }
     else if (k == 2) { sh.st(sh.xb, UW_A_L * T + t, aL[0]); sh.st(sh.xb, UW_A_R * T + t, lastR); }
@@ -168,27 +166,27 @@ struct UpwindThread {
     }
   }
 
-  // Helmholtz right-hand side b = P m and the causal local pass
+  // Helmholtz right-hand side b = P m and the causal local pass (the ghost row of a short chunk is computed and ignored)
   template <class SH>
   PK_HD void helm_causal(const Params& p, const SH& sh, double& A, double& c0, double& c1) {
     const int T = TN(p);
     double pL = sh.ld(sh.xb, UW_H_L * T + tl), pR = sh.ld(sh.xb, UW_H_R * T + tl);
-    double y = 0.0;
+    double y = 0.0, yS = 0.0;
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
-      hh[j] = 0.0;
-      if (has_row(j)) {
-        const double b = (pL + 2.0 * pR) + (2.0 * mL[j] + mR[j]);      // (P m)_j * 6/h
-        y = b * p.h6k + p.rho * y; hh[j] = y;
-        pL = mL[j]; pR = mR[j];
-      }
+      const double b = (pL + 2.0 * pR) + (2.0 * mL[j] + mR[j]);      // (P m)_j * 6/h
+      y = b * p.h6k + p.rho * y; hh[j] = y;
+      pL = mL[j]; pR = mR[j];
+      if (j == M - 2) yS = y;
     }
-    A = ext ? p.rpow[M] : p.rpow[M - 1]; c0 = y; c1 = 0.0;
+    A = ext ? p.rpow[M] : p.rpow[M - 1]; c0 = ext ? y : yS; c1 = 0.0;
   }
   PK_HD void helm_anticausal(const Params& p, double in0, double& A, double& c0, double& c1) {
-    double x = 0.0;
+    const double xg = hh[M - 1] + p.rpow[M] * in0;
+    double x = ext ? xg : 0.0;
+    hh[M - 1] = x;
     PK_UNROLL
-    for (int j = M - 1; j >= 0; --j) if (has_row(j)) { x = (hh[j] + p.rpow[j + 1] * in0) + p.rho * x; hh[j] = x; }
+    for (int j = M - 2; j >= 0; --j) { x = (hh[j] + p.rpow[j + 1] * in0) + p.rho * x; hh[j] = x; }
     A = ext ? p.rpow[M] : p.rpow[M - 1]; c0 = x; c1 = 0.0;
   }
   // returns true if every new u of this thread is finite
@@ -197,10 +195,8 @@ struct UpwindThread {
     bool ok = true;
     PK_UNROLL
     for (int j = M - 1; j >= 0; --j) {
-      if (has_row(j)) {
-        u[j] = hh[j] + p.rpow[M - j] * in0;
-        ok = ok && uw_finite(u[j]);
-      }
+      u[j] = hh[j] + p.rpow[M - j] * in0;
+      ok = ok && (uw_finite(u[j]) || (j == M - 1 && !ext));
     }
     return ok;
   }
