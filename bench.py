@@ -32,7 +32,7 @@ NE, LD, DT, NXI, SIGMA, IC = 1000, 40.0, 1e-3, 4, 0.2, 'proper_peak'
 R_PER_GPU = 1024
 STEPS_PER_LAUNCH = 50
 B_ALG = 16 * NE + 8 * NXI      # algorithmic bytes per realisation-step
-DRAM_TRAFFIC_PER_LAUNCH = 33.65e6   # bytes, ncu capture profiles/r1e_ncu_full_pk_step_kernel.csv
+DRAM_TRAFFIC_PER_LAUNCH = 33.69e6   # bytes, ncu capture profiles/r1g_ncu_full_pk_step_kernel.csv
 METRIC = 'realisation_steps_per_sec'
 UNIT = 'realisation*steps/s'
 WORKLOAD = ('C2: stochastic CH hydrodynamic/midpoint, ne=1000, Ld=40, dt=1e-3, 4 sines sigma=0.2, '
