@@ -320,7 +320,7 @@ def run_gpu(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps,
-                    'api': 'pk_step_host: u in/out through pinned host buffers (4-chunk H2D/kernel/D2H pipeline); the Newton '
+                    'api': 'pk_step_host: u in/out through pinned host buffers (2-chunk H2D/kernel/D2H pipeline); the Newton '
                            'warm start (u1, dF, dG) is solver-internal state as in the reference and stays in the context'},
             'gpu_launches': args.steps * 4,   # per step: pk_step_kernel, pk_diag_kernel, pk_moments_partial, pk_moments_final
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

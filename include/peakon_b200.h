@@ -115,7 +115,7 @@ int pk_step(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, doub
             int32_t* its_total, void* stream);
 
 /* Same, with HOST buffers: copies state (and dW_in) to internal device buffers, steps, copies the
- * state, dW_out and the counters back, and synchronises (the realisations go through a 4-chunk
+ * state, dW_out and the counters back, and synchronises (the realisations go through a 2-chunk
  * H2D / kernel / D2H pipeline on internal streams; pin the host buffers).  This is the call a host
  * application without device arrays makes; bench.py's "e2e" times it.
  * u1 = dF = dG = NULL selects the reference's own ownership: the Newton unknown w1 = (u1, dF, dG) is

@@ -662,7 +662,9 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
   // Chunk pipeline: the realisations are split into NC contiguous chunks, each with its own stream doing
   // H2D -> step kernel -> D2H, so the copies of one chunk overlap the kernel of another (the persistent kernels of
   // two chunks share the SMs work-conservingly).  Host buffers should be pinned for the copies to be asynchronous.
-  int NC = (c->cluster > 1 || R < 256) ? 1 : PK_HOST_CHUNKS;
+  // (measured on the bench workload, R = 1024: 1 chunk 14.9e6, 2 chunks 15.2e6, 3 / 4 chunks 14.8e6 realisation-steps/s --
+  //  the copies are 0.3 ms of a 3.4 ms call and every chunk adds seven small-copy latencies)
+  int NC = (c->cluster > 1 || R < 256) ? 1 : 2;
   { const char* e = getenv("PK_HOST_NCHUNK"); const int v = e ? atoi(e) : 0; if (v >= 1 && v <= PK_HOST_CHUNKS && c->cluster == 1) NC = v; }
   if (dW_in && ndw) {       // [nsteps, R, nxi]: not contiguous per chunk -> one copy up front, every chunk waits for it
     CK(c, cudaMemcpyAsync(c->d_dWin, dW_in, sizeof(double) * ndw, cudaMemcpyHostToDevice, c->hs[0]));

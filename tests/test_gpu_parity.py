@@ -181,7 +181,7 @@ def test_host_buffer_entry_point_equals_device_path():
 
 
 def test_host_entry_point_chunk_pipeline_and_resident_warm_start():
-    """R >= 256 goes through the 4-chunk H2D / kernel / D2H pipeline; u1 = dF = dG = None keeps the Newton unknown
+    """R >= 256 goes through the chunked H2D / kernel / D2H pipeline; u1 = dF = dG = None keeps the Newton unknown
     in the context (the reference's Equations object owns it, equations.py:71,89).  Two calls of 3 steps must equal
     the device path's 6 steps bit for bit, in both modes, with Philox streams independent of the chunking."""
     from peakondrake_b200 import EnsembleIntegrator, build_initial_u
