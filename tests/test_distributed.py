@@ -54,13 +54,17 @@ def test_two_rank_sharding_and_packed_allreduce():
             ids += list(range(o, o + c))
         assert ids == list(range(R))
     R_total, world = 7, 2
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from emu_util import lib
+    lib()          # build the emulation harness HERE if it is stale (minutes of g++), not concurrently in both workers
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
     procs = [ctx.Process(target=_worker, args=(r, world, port, R_total, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    got = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
