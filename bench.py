@@ -32,7 +32,7 @@ NE, LD, DT, NXI, SIGMA, IC = 1000, 40.0, 1e-3, 4, 0.2, 'proper_peak'
 R_PER_GPU = 1024
 STEPS_PER_LAUNCH = 50
 B_ALG = 16 * NE + 8 * NXI      # algorithmic bytes per realisation-step
-DRAM_TRAFFIC_PER_LAUNCH = 33.69e6   # bytes, ncu capture profiles/r1g_ncu_full_pk_step_kernel.csv
+DRAM_TRAFFIC_PER_LAUNCH = 33.70e6   # bytes, ncu capture profiles/r1j_ncu_full_pk_step_kernel.csv
 METRIC = 'realisation_steps_per_sec'
 UNIT = 'realisation*steps/s'
 WORKLOAD = ('C2: stochastic CH hydrodynamic/midpoint, ne=1000, Ld=40, dt=1e-3, 4 sines sigma=0.2, '
@@ -331,7 +331,7 @@ def run_gpu(args):
                          'algorithmic_bytes_per_realisation_step': B_ALG,
                          'note': 'not HBM-bound by construction (SURVEY.md 8d): ~700 fp64 instructions per node-step '
                                  'against 16 algorithmic bytes; measured limiters are fp64 issue and instruction supply '
-                                 '(fp64 pipe 56 %, instruction cache 87 % of its request peak), see DESIGN.md section 4'},
+                                 '(fp64 pipe 53 %, instruction cache 87 % of its request peak), see DESIGN.md section 4'},
             'wall_ms_per_step': wall_ms / args.steps,
         }
         if args.cpu_baseline:

@@ -50,6 +50,7 @@ struct Params {
   double rpow[12];        // rho^0 .. rho^11 (chunk-local carry weights; a chunk has at most 10 rows)
   double irho;            // 1 / rho
   double inv1mrn;         // 1 / (1 - rho^ne): cyclic closure of the Helmholtz scans
+  double cert_k, cert_floor2;   // convergence certificate of the Newton iteration (run_steps); cert_k = 0 disables it
   double ih2;             // 2 / h   (inverse DG1 element mass matrix M_e^-1 = (2/h) [[2,-1],[-1,2]])
   double c1k, c2k, h6k, a26k;   // c1, c2, h6, a26 times ikappa (Helmholtz right-hand sides pre-divided by kappa)
   double rtol, atol, stol, divtol;  // PETSc SNES defaults 1e-8, 1e-50, 1e-8, 1e4
@@ -110,6 +111,9 @@ static inline void fill_constants(Params& p) {
   for (int i = 1; i < 12; ++i) p.rpow[i] = p.rpow[i - 1] * p.rho;
   p.irho = 1.0 / p.rho;
   p.inv1mrn = 1.0 / (1.0 - std::pow(p.rho, (double)p.ne));
+  // |R(x + d)|_2 <= cert_k |d|_2^2 once R(x) + J d = 0 (see run_steps); evaluation noise of R: ~1.5e-14 h sqrt(ne + |w|^2)
+  p.cert_k = p.dt * (2.4 + 4.0 * h / 3.0 + 2.0 * a2 / h) * 0.25;
+  p.cert_floor2 = (1.5e-14 * h) * (1.5e-14 * h);
   p.ih2 = 2.0 / h;
   p.c1k = p.c1 * p.ikappa; p.c2k = p.c2 * p.ikappa; p.h6k = p.h6 * p.ikappa; p.a26k = p.a26 * p.ikappa;
   p.sdt = std::sqrt(p.dt / (p.nupd > 0 ? p.nupd : 1));
