@@ -17,6 +17,7 @@
 using namespace pk;
 
 static int g_emu_part = 1;        // cluster emulation: Schur solve partitioned by CTA (1, like the device) or flat PCR (0)
+static int g_emu_cert = 1;        // 0: always evaluate the last residual (no convergence certificate)
 static int g_emu_hybrid = 0;      // 1: compacted Schur solve (hyb_* in pk_core.h) where T >= 32; 0: plain PCR
 template <class ThT> struct EmuExecT;
 template <int M, int MODE> using EmuExec = EmuExecT<Thread<M, MODE> >;
@@ -232,6 +233,7 @@ extern "C" int pk_emu_set_cluster(int C) { g_emuC = C; return g_bad; }
 extern "C" int pk_emu_set_fs(int on) { g_emu_fs = on; return 0; }
 
 extern "C" int pk_emu_set_hybrid(int on) { g_emu_hybrid = on; return 0; }
+extern "C" int pk_emu_set_certificate(int on) { g_emu_cert = on; return 0; }
 extern "C" int pk_emu_set_partitioned(int on) { g_emu_part = on; return 0; }
 
 // advance in step blocks of nblk steps (0 = whole launch at once), see run_one
@@ -259,6 +261,7 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
   if (forceT > 0) { p.T = forceT; p.M = forceM; p.rem = ne - forceT * (forceM - 1); if (p.rem < 0 || p.rem > p.T) return -2; }
   else if (!choose_layout(ne, &p.T, &p.M, &p.rem)) return -1;
   fill_constants(p);
+  if (!g_emu_cert) p.cert_k = 0.0;
   std::vector<double> pt[3];
   const double* src[3] = {xi, xi_x, xi_xx};
   const double* tab[3] = {nullptr, nullptr, nullptr};

@@ -66,6 +66,23 @@ def test_thread_order_independence():
         assert np.array_equal(x, y)
 
 
+def test_convergence_certificate_changes_nothing():
+    """The Newton convergence certificate (run_steps: |R(w_new)| <= cert_k |delta|^2 for the quadratic residual)
+    only replaces the last residual EVALUATION: iterates, iteration counts and results are bit-identical with it
+    switched off, on meshes where it fires (steady steps) and where it cannot (first step, coarse bound)."""
+    L = lib()
+    cases = [dict(ne=1000, nsteps=6, nxi=4), dict(ne=200, nsteps=5, nxi=2), dict(ne=400, nsteps=4, fam='constant', nxi=1, ic='periodic_peakon', sigma=1.0),
+             dict(ne=300, nsteps=4, nxi=0), dict(ne=2000, nsteps=3, ic='periodic_peakon', fam='constant', nxi=1, sigma=1.0, dt=1e-2)]
+    for kw in cases:
+        try:
+            L.pk_emu_set_certificate(1); a = compare(**kw)
+            L.pk_emu_set_certificate(0); b = compare(**kw)
+        finally:
+            L.pk_emu_set_certificate(1)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
 def test_fine_mesh_large_noise():
     # C5-like spacing h = 40/2000 with sigma = 1: P is strongly non diagonally dominant here
     compare(2000, nsteps=3, ic='periodic_peakon', fam='constant', nxi=1, sigma=1.0, dt=1e-2)

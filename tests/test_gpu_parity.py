@@ -297,6 +297,25 @@ def test_argmax_ties_take_lowest_index():
         assert idx[r, _lib.I_ARGMAX_DU] == np.argmax(du[r]) and idx[r, _lib.I_ARGMIN_DU] == np.argmin(du[r])
 
 
+def test_convergence_certificate_is_bit_neutral(monkeypatch):
+    """PK_NO_CERTIFICATE=1 evaluates the last residual of every Newton solve like the reference does; the default
+    decides the same test from |delta|^2.  Same iterates => bit-identical states and counters."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    out = []
+    for off in ('0', '1'):
+        monkeypatch.setenv('PK_NO_CERTIFICATE', off)
+        eng = EnsembleIntegrator(1000, 40.0, 1e-3, 64, num_Xis=4, Xi_family='sines', sigma=0.2, seed=5)
+        eng.set_state(build_initial_u(1000, 40.0, 'proper_peak'))
+        eng.step(40); eng.step(23)
+        torch.cuda.synchronize()
+        out.append([t.cpu().numpy().copy() for t in (eng.u, eng.u1, eng.dF, eng.dG, eng.its_total, eng.fail_step)])
+        eng.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+    assert out[0][4].min() >= 2 * 63 - 2
+
+
 # ---- thread-block-cluster variant (one realisation per cluster of CTAs, DSMEM) -------------------
 @pytest.mark.parametrize('ne,C', [(1000, 2), (1000, 4), (2000, 8), (500, 2)])
 def test_cluster_variant_forced_on_small_meshes(ne, C, monkeypatch):
