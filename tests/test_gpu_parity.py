@@ -313,7 +313,7 @@ def test_convergence_certificate_is_bit_neutral(monkeypatch):
         eng.close()
     for a, b in zip(*out):
         assert np.array_equal(a, b)
-    assert out[0][4].min() >= 2 * 63 - 2
+    assert (out[0][5] == -1).all() and out[0][4].min() >= 63        # nobody failed; at least one iteration per step
 
 
 # ---- thread-block-cluster variant (one realisation per cluster of CTAs, DSMEM) -------------------
