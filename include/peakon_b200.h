@@ -192,6 +192,40 @@ int pk_ensemble_stats(pk_ctx* ctx, const double* u, const int32_t* fail_step, co
                       const int32_t* idx, int32_t nbins, double q_lo, double q_hi, double d_lo,
                       double d_hi, double* packed, void* stream);
 
+/* Per-diagnostic ensemble statistics of one dump (sum / sum of squares per scalar diagnostic, extrema,
+ * fail count), over the healthy realisations of this shard, from the table pk_diagnostics wrote:
+ *   sums [2*PK_NDIAG + 2] = sum_r v_k | sum_r v_k^2 | number of healthy realisations | number of failed ones
+ *   ext  [2*PK_NDIAG]     = min_r v_k | -max_r v_k
+ * A multi-GPU caller all-reduces `sums` with ncclSum and `ext` with ncclMin (the negated maxima make one
+ * collective serve both extrema).  Fixed summation order; NaN columns (not requested) are skipped. */
+int pk_ensemble_scalars(pk_ctx* ctx, const double* diag, const int32_t* fail_step, double* sums, double* ext,
+                        void* stream);
+
+/* Replaces `nsteps` calls of PeakonEquations.update() (peakon_equations.py:34-65) for every realisation: the
+ * (p, q) SDE of a peakon driven by the SAME Brownian increments as the PDE.
+ *   p, q [R]      in/out (peakon_equations.py:28-32 gives the initial values)
+ *   dW_in [nsteps, R, num_xis] increments (e.g. the dW_out of pk_step), or NULL: drawn in-kernel with the Philox
+ *                 counters pk_step uses for the global steps step0 .. step0+nsteps-1 (identical numbers)
+ *   xi, xi_x, xi_xx [num_xis, ne]  the CG1 fields pure_xi, pure_xi_x, pure_xi_xx (stochastic_functions.py:175-182),
+ *                 natural node order; evaluated at q by CG1 point evaluation (`.at`, peakon_equations.py:42-44)
+ *   method        0 = 'ito_euler' (:39-47), 1 = 'milstein' (:49-57)
+ *   E             exp(-Ld/alpha), computed by the caller (so that host and device agree on it to the bit)
+ *   traj [nsteps/stride, R, 2] or NULL: (p, q) after every `stride` steps (the values dump_diagnostics would write,
+ *                 outputting.py:216-218)
+ * The arithmetic is the reference's, operation by operation, with individually rounded operations. */
+int pk_peakon_sde_step(pk_ctx* ctx, int32_t nsteps, double* p, double* q, const double* dW_in, int64_t step0,
+                       const double* xi, const double* xi_x, const double* xi_xx, int32_t method, double E,
+                       double* traj, int32_t stride, void* stream);
+
+/* Replaces Projector(du, du_smooth) (diagnostic_equations.py:115-119) + find_max / find_min on it
+ * (outputting.py:135-138): L2 projection of the DG0 slope onto periodic CG5 by static condensation (constant
+ * cyclic tridiagonal system for the vertex values), extrema with lowest-dof-index tie-break.
+ *   consts [16] host: the condensed reference-element constants (peakondrake_b200/outputting.py: cg5_condensed)
+ *   out [R,4] = (max, x of max, min, x of min), idx [R,2] = CG5 dof index (5*cell + local node) of max / min
+ *   field [R, 5*ne] or NULL: du_smooth itself */
+int pk_du_smooth_loc(pk_ctx* ctx, const double* u, const int32_t* fail_step, const double* consts, double* out,
+                     int32_t* idx, double* field, void* stream);
+
 /* layout query (for tests / documentation): threads per realisation, rows per thread, remainder */
 int pk_get_layout(const pk_ctx* ctx, int32_t* T, int32_t* M, int32_t* rem, int32_t* smem_bytes);
 

@@ -704,3 +704,95 @@ def dg1_norms(orc, m):
     semi = np.sum((mR - mL) ** 2 / h)
     return dict(l2_m=float(np.sqrt(l2sq)), h1_m=float(np.sqrt(l2sq + semi)), mass_m=float(np.sum(h / 2.0 * (mL + mR))),
                 m_max=float(max(mL.max(), mR.max())))
+
+
+# ----------------------------------------------------------------------------
+# peakon SDE: peakon_equations.py:13-65 (pinned by tests/golden: the reference's own update() run verbatim)
+# ----------------------------------------------------------------------------
+
+def cg1_at(table, Ld, q):
+    """CG1 point evaluation on the periodic mesh (Function.at on a CG1 field)."""
+    ne = table.shape[-1]
+    s = np.asarray(q, dtype=float) / (Ld / ne)
+    fl = np.floor(s)
+    i = fl.astype(np.int64) % ne
+    th = s - fl
+    return (1 - th) * table[i] + th * table[(i + 1) % ne]
+
+
+class PeakonSDE(object):
+    """(p, q) of R realisations; update(dW[R, num_Xis]) follows peakon_equations.py:34-65 statement by statement."""
+
+    def __init__(self, p0, q0, Ld, dt, alphasq, tables, R, method='ito_euler'):
+        self.Ld, self.dt, self.alpha, self.method = float(Ld), float(dt), float(np.sqrt(alphasq)), method
+        self.xi, self.xi_x, self.xi_xx = tables
+        self.p = np.full(R, p0, dtype=float)
+        self.q = np.full(R, q0, dtype=float)
+
+    def update(self, dW):
+        E = np.exp(-self.Ld / self.alpha)
+        p, q, dt = self.p, self.q, self.dt
+        dp = np.zeros_like(p)
+        dq = (p / 2) * (1 + E) / (1 - E) * dt                                   # :37
+        for k in range(self.xi.shape[0]):
+            xi = cg1_at(self.xi[k], self.Ld, q)
+            xi_x = cg1_at(self.xi_x[k], self.Ld, q)
+            xi_xx = cg1_at(self.xi_xx[k], self.Ld, q)
+            w = dW[:, k]
+            if self.method == 'ito_euler':                                      # :45-46
+                dp = dp + (p / 2 * (xi_x * xi_x - xi * xi_xx) * dt - p * xi_x * w)
+                dq = dq + (0.5 * xi * xi_x * dt + xi * w)
+            elif self.method == 'milstein':                                     # :55-56
+                dp = dp + (p / 2 * (xi_x * xi_x - xi * xi_xx) * w ** 2 - p * xi_x * w)
+                dq = dq + (0.5 * xi * xi_x * w ** 2 + xi * w)
+        self.p = p + dp
+        q = q + dq
+        q = np.where(q < 0, q + self.Ld, q)                                     # :62-65
+        q = np.where(q > self.Ld, q - self.Ld, q)
+        self.q = q
+
+
+# ----------------------------------------------------------------------------
+# du_smooth: Projector(du, du_smooth) into CG5 (diagnostic_equations.py:115-119), global sparse solve
+# ----------------------------------------------------------------------------
+
+def cg5_reference_mass():
+    """6x6 mass matrix and load vector of the equispaced Lagrange P5 basis on [0, 1]."""
+    from numpy.polynomial import polynomial as P
+    t = np.arange(6) / 5.0
+    basis = []
+    for k in range(6):
+        c = np.array([1.0])
+        for j in range(6):
+            if j != k:
+                c = P.polymul(c, np.array([-t[j], 1.0]) / (t[k] - t[j]))
+        basis.append(c)
+    xq, wq = gauss(6)                                   # exact for degree 10
+    B = np.array([P.polyval(xq, b) for b in basis])     # [6, nq]
+    return (B * wq) @ B.T, B @ wq
+
+
+def du_smooth_field(mesh, u):
+    """L2 projection of the DG0 slope onto periodic CG5: dof 5 i + k is local node k of cell i (k = 0..4),
+    at x = (i + k/5) h.  Monolithic sparse LU of the 5 ne x 5 ne CG5 mass matrix."""
+    ne, h = mesh.ne, mesh.h
+    Mref, c = cg5_reference_mass()
+    du = du_field(mesh, u)
+    n = 5 * ne
+    rows, cols, vals = [], [], []
+    b = np.zeros(n)
+    for i in range(ne):
+        dofs = [(5 * i + k) % n for k in range(6)]
+        for a in range(6):
+            b[dofs[a]] += h * c[a] * du[i]
+            for bb in range(6):
+                rows.append(dofs[a]); cols.append(dofs[bb]); vals.append(h * Mref[a, bb])
+    A = sp.csc_matrix((vals, (rows, cols)), shape=(n, n))
+    return spla.splu(A).solve(b)
+
+
+def smooth_locs(mesh, u):
+    """(max_du_smooth_loc, min_du_smooth_loc) of outputting.py:135-138 with smooth_coords = CG5 node coordinates."""
+    w = du_smooth_field(mesh, u)
+    x = (np.arange(5 * mesh.ne) / 5.0) * mesh.h
+    return float(x[np.argmax(w)]), float(x[np.argmin(w)]), w

@@ -204,12 +204,14 @@ class EnsembleIntegrator(object):
         _lib.check(self.lib, self.ctx, self.lib.pk_reset_warm_start(self.ctx))
 
     # -- diagnostics --------------------------------------------------------------------------
-    def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False):
+    def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False, fail_step='own'):
         """
         Fused per-realisation reductions. Returns (vals [R, NDIAG] float64, idx [R, NIDX] int32,
         du [R, ne] or None) as device tensors; columns are _lib.D_* / _lib.I_*.
-        Failed realisations give NaN rows (outputting.py:107-108).
+        Failed realisations give NaN rows (outputting.py:107-108); fail_step=None computes every row (the dump
+        at t = 0, simulation.py:88).
         """
+        fs = self.fail_step if isinstance(fail_step, str) else fail_step
         pq_dev = None
         if pq is not None:
             pq_dev = torch.as_tensor(pq, dtype=torch.float64).to(self.device).contiguous()
@@ -217,16 +219,16 @@ class EnsembleIntegrator(object):
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         rc = self.lib.pk_diagnostics(self.ctx, _ptr(self.u), _ptr(pq_dev), int(bool(periodic)),
                                      int(bool(want_m) and not self.upwind),
-                                     _ptr(self.diag), _ptr(self.didx), _ptr(du), _ptr(self.fail_step), stream)
+                                     _ptr(self.diag), _ptr(self.didx), _ptr(du), _ptr(fs), stream)
         _lib.check(self.lib, self.ctx, rc)
         if self.upwind:      # m is prognostic (DG1): its norms come from the state, not from a Helmholtz solve
-            rc = self.lib.pk_diagnostics_dg1(self.ctx, _ptr(self.m), _ptr(self.u), _ptr(self.fail_step),
+            rc = self.lib.pk_diagnostics_dg1(self.ctx, _ptr(self.m), _ptr(self.u), _ptr(fs),
                                              _ptr(self.diag), stream)
             _lib.check(self.lib, self.ctx, rc)
         self._keep_d = pq_dev
         return self.diag, self.didx, du
 
-    def mu(self):
+    def mu(self, fail_step='own'):
         """The `mu` diagnostic (find_mus, outputting.py:260-370) on the device: ([R, 8] mu_0..3, alt_mu_0..3; [R] status)."""
         if getattr(self, '_x_cells', None) is None:
             xc = (np.arange(self.ne) + 0.5) * (self.Ld / self.ne)          # DiagnosticVariables.coords (simulation.py:265)
@@ -234,19 +236,69 @@ class EnsembleIntegrator(object):
             self._mu_out = torch.empty(self.R, 8, dtype=torch.float64, device=self.device)
             self._mu_status = torch.empty(self.R, dtype=torch.int32, device=self.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.lib.pk_mu(self.ctx, _ptr(self.u), _ptr(self._x_cells), _ptr(self.fail_step), _ptr(self._mu_out),
+        fs = self.fail_step if isinstance(fail_step, str) else fail_step
+        rc = self.lib.pk_mu(self.ctx, _ptr(self.u), _ptr(self._x_cells), _ptr(fs), _ptr(self._mu_out),
                             _ptr(self._mu_status), stream)
         _lib.check(self.lib, self.ctx, rc)
         return self._mu_out, self._mu_status
 
-    def peakon_suite(self):
+    def peakon_suite(self, fail_step='own'):
         """Device part of peakon_diagnostics (outputting.py:373-450); call after diagnostics().
         Returns (vals [R,2] = (min_du, max_du), ids [R,3] = (argmax u, min_du_idx, max_du_idx))."""
         if not hasattr(self, 'pk_vals'):
             self.pk_vals = torch.zeros(self.R, 2, dtype=torch.float64, device=self.device)
             self.pk_ids = torch.zeros(self.R, 3, dtype=torch.int32, device=self.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.lib.pk_peakon_suite(self.ctx, _ptr(self.u), _ptr(self.didx), _ptr(self.fail_step),
+        fs = self.fail_step if isinstance(fail_step, str) else fail_step
+        rc = self.lib.pk_peakon_suite(self.ctx, _ptr(self.u), _ptr(self.didx), _ptr(fs),
                                       _ptr(self.pk_vals), _ptr(self.pk_ids), stream)
         _lib.check(self.lib, self.ctx, rc)
         return self.pk_vals, self.pk_ids
+
+    def du_smooth_loc(self, want_field=False, fail_step='own'):
+        """du_smooth (CG5 L2 projection of du, diagnostic_equations.py:115-119) and the locations of its extrema
+        (outputting.py:135-138): (out [R,4] = max, x_max, min, x_min; idx [R,2] CG5 dof indices; field [R,5 ne] or None)."""
+        from peakondrake_b200.outputting import cg5_condensed
+        if not hasattr(self, '_sm_out'):
+            self._sm_consts = np.ascontiguousarray(cg5_condensed(), dtype=np.float64)
+            self._sm_out = torch.empty(self.R, 4, dtype=torch.float64, device=self.device)
+            self._sm_idx = torch.empty(self.R, 2, dtype=torch.int32, device=self.device)
+        field = torch.empty(self.R, 5 * self.ne, dtype=torch.float64, device=self.device) if want_field else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        fs = self.fail_step if isinstance(fail_step, str) else fail_step
+        rc = self.lib.pk_du_smooth_loc(self.ctx, _ptr(self.u), _ptr(fs),
+                                       ctypes.c_void_p(self._sm_consts.ctypes.data), _ptr(self._sm_out),
+                                       _ptr(self._sm_idx), _ptr(field), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        return self._sm_out, self._sm_idx, field
+
+    # -- ensemble statistics (local part; ensemble.EnsembleStatistics owns the buffers and the all-reduce) -----
+    def ensemble_stats_into(self, stats, vals, idx, stream=None):
+        if stream is None:
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.pk_ensemble_stats(self.ctx, _ptr(self.u), _ptr(self.fail_step), _ptr(vals), _ptr(idx), stats.nbins,
+                                        stats.q_lo, stats.q_hi, stats.d_lo, stats.d_hi, _ptr(stats.packed), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        rc = self.lib.pk_ensemble_scalars(self.ctx, _ptr(vals), _ptr(self.fail_step), _ptr(stats.sums), _ptr(stats.ext), stream)
+        _lib.check(self.lib, self.ctx, rc)
+
+    # -- peakon SDE (PeakonEquations.update, peakon_equations.py:34-65) ------------------------------------------
+    def peakon_sde_step(self, nsteps, p, q, tables, E, method='ito_euler', dW=None, step0=0, traj_stride=0):
+        """Advance the (p, q) of every realisation `nsteps` SDE steps on the device.
+        p, q: device tensors [R] (in/out); tables: device tensors (pure_xi, pure_xi_x, pure_xi_xx) [num_Xis, ne];
+        dW: device tensor [nsteps, R, num_Xis] (e.g. what step(export_dW=True) returned) or None to draw the
+        Philox increments of global steps step0.. in-kernel; traj_stride > 0 returns (p, q) after every
+        traj_stride steps as a device tensor [nsteps // traj_stride, R, 2]."""
+        if method not in ('ito_euler', 'milstein'):
+            raise ValueError('peakon_method must be ito_euler or milstein, not %s' % method)
+        traj = None
+        if traj_stride > 0:
+            traj = torch.empty(nsteps // traj_stride, self.R, 2, dtype=torch.float64, device=self.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.pk_peakon_sde_step(self.ctx, int(nsteps), _ptr(p), _ptr(q), _ptr(dW), int(step0),
+                                         _ptr(tables[0]), _ptr(tables[1]), _ptr(tables[2]),
+                                         0 if method == 'ito_euler' else 1, float(E), _ptr(traj),
+                                         int(max(traj_stride, 1)), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        self._keep_sde = (dW, traj)
+        return traj

@@ -10,6 +10,7 @@ diagnostics that are post-processing of device results.
     eight numbers of peakon_diagnostics (outputting.py:373-450) with the host's coordinate array, so
     coordinates are looked up, never recomputed (bit-exact locations).
 """
+from collections import OrderedDict
 import numpy as np
 from scipy.io import netcdf_file
 
@@ -17,30 +18,80 @@ PEAKON_DIAGNOSTICS = ['peakon_loc', 'peakon_min_du', 'peakon_max_du', 'peakon_mi
                       'peakon_max_du_loc', 'peakon_max_u', 'peakon_mu', 'peakon_nu']
 
 _NC_TYPES = {float: 'd', int: 'i', 'S1': 'c'}
+# NetCDF classic (CDF-1/2) type codes, big-endian numpy types, element sizes
+_NC_CODE = {'d': (6, '>f8', 8), 'i': (4, '>i4', 4), 'c': (2, 'S1', 1)}
+
+
+def _pad4(n):
+    return (n + 3) & ~3
 
 
 class DataFile(object):
-    """In-memory image of results/<code>/data[_dtI].nc, flushed to disk with save()."""
+    """
+    results/<code>/data[_dtI].nc written as NetCDF-3 (64-bit-offset classic format, CDF-2) by a small native
+    writer, so that the file GROWS like the reference's netCDF4 'a'-mode file does (outputting.py:32,198-220):
+
+      * createDimension / createVariable build the schema (experiment.py:99-156); the header is laid out on the
+        first write and is final from then on;
+      * a dump writes ONE record (all record variables at that time index, one contiguous slab) at its place at
+        the end of the file and updates the record count -- O(record) per dump, nothing is rewritten, and every
+        dump already made survives a later crash or ConvergenceError;
+      * fixed-size variables (x, deltax, swept parameter values, wallclock_time, failed_time) are written in
+        place by sync().
+
+    An in-memory mirror (`data[name]`, record variables grow along axis 0) keeps the put()/data[...] interface and
+    lets later batches of an experiment fill other slices of an existing record (the record is then re-written).
+    The result is readable by any NetCDF-3 reader (tests read it back with scipy.io.netcdf_file).
+    """
 
     def __init__(self, file_name):
         self.file_name = file_name
-        self.dims = {}          # name -> size (None = unlimited)
-        self.vars = {}          # name -> (nc type char, dims tuple)
-        self.data = {}          # name -> ndarray (record variables grow along axis 0)
+        self.dims = OrderedDict()   # name -> size (None = unlimited)
+        self.vars = OrderedDict()   # name -> (nc type char, dims tuple)
+        self.data = {}              # name -> ndarray
+        self._fh = None
+        self._begin = {}            # name -> file offset (record variables: offset inside the first record)
+        self._recsize = 0
+        self._rec0 = 0
+        self._nrec_disk = 0
+        self._dirty = set()         # record indices changed since the last flush
 
+    @classmethod
+    def reopen(cls, file_name):
+        """Open an existing result file for appending (the reference's Dataset(file_name, 'a'), outputting.py:32):
+        the schema and contents are loaded; the first sync() lays the file out again."""
+        f = netcdf_file(file_name, 'r', mmap=False)          # raises if the file does not exist
+        self = cls(file_name)
+        for name, size in f.dimensions.items():
+            self.dims[name] = size
+        nrec = 0
+        rev = {'d': float, 'i': int, 'c': 'S1'}
+        for name, v in f.variables.items():
+            tc = v.typecode()
+            self.createVariable(name, rev.get(tc, float), v.dimensions)
+            a = np.array(v.data)
+            if a.dtype.kind in 'fi':
+                a = a.astype(a.dtype.newbyteorder('='))
+            self.data[name] = a.reshape(v.shape) if v.shape else a
+            if self._is_rec(name):
+                nrec = max(nrec, a.shape[0])
+        f.close()
+        self._nrec = nrec
+        self._dirty = set(range(nrec))
+        return self
+
+    # ---- schema ----
     def createDimension(self, name, size):
+        if self._fh is not None:
+            raise RuntimeError('DataFile: the schema is final once data has been written')
         self.dims[name] = size
 
     def createVariable(self, name, typ, dims):
+        if self._fh is not None:
+            raise RuntimeError('DataFile: the schema is final once data has been written')
         tc = _NC_TYPES.get(typ, 'd')
-        if len(tuple(dims)) == 0:
-            # scipy's NetCDF-3 writer corrupts record variables when a 0-d variable is present;
-            # scalars are stored with a length-1 dimension instead (read as var[0], like the
-            # reference's own `data_file['failed_time'][0]`, outputting.py:241)
-            if 'scalar' not in self.dims:
-                self.createDimension('scalar', 1)
-            dims = ('scalar',)
-        self.vars[name] = (tc, tuple(dims))
+        dims = tuple(dims)
+        self.vars[name] = (tc, dims)
         shape = tuple(0 if self.dims[d] is None else self.dims[d] for d in dims)
         if tc == 'c':
             self.data[name] = np.full(shape, b' ', dtype='S1')
@@ -49,46 +100,193 @@ class DataFile(object):
         else:
             self.data[name] = np.full(shape, np.nan)
 
+    def _is_rec(self, name):
+        dims = self.vars[name][1]
+        return bool(dims) and self.dims[dims[0]] is None
+
     def _grow(self, name, n):
         a = self.data[name]
         if a.shape[0] < n:
-            pad = np.full((n - a.shape[0],) + a.shape[1:], np.nan if a.dtype.kind == 'f' else 0, dtype=a.dtype)
+            cap = max(n, 2 * a.shape[0])            # amortised growth; `nrec` tracks the logical length
+            fill = np.nan if a.dtype.kind == 'f' else (b' ' if a.dtype.kind == 'S' else 0)
+            pad = np.full((cap - a.shape[0],) + a.shape[1:], fill, dtype=a.dtype)
             self.data[name] = np.concatenate([a, pad], axis=0)
 
+    @property
+    def nrec(self):
+        return getattr(self, '_nrec', 0)
+
+    def _touch(self, name, t):
+        t = int(t)
+        self._grow(name, t + 1)
+        if t + 1 > self.nrec:
+            self._nrec = t + 1
+        self._dirty.add(t)
+
+    # ---- data ----
     def put(self, name, index, value):
         """data[name][index] = value; index[0] may exceed the current length of an unlimited axis."""
-        _, dims = self.vars[name]
-        if dims and self.dims[dims[0]] is None:
-            t = index[0] if isinstance(index, tuple) else index
-            self._grow(name, int(t) + 1)
+        if self._is_rec(name):
+            self._touch(name, index[0] if isinstance(index, tuple) else index)
         self.data[name][index] = value
 
-    def save(self):
-        f = netcdf_file(self.file_name, 'w')
-        nrec = max([self.data[v].shape[0] for v, (_, d) in self.vars.items() if d and self.dims[d[0]] is None] or [0])
-        for name, size in self.dims.items():
-            f.createDimension(name, size)
-        handles = {}
-        for name, (tc, dims) in self.vars.items():
-            handles[name] = f.createVariable(name, tc, dims)
-        for name, (tc, dims) in self.vars.items():
-            a = self.data[name]
-            if dims and self.dims[dims[0]] is None:
-                self._grow(name, nrec)
-                a = self.data[name]
-                for t in range(nrec):
-                    handles[name][t] = a[t]
+    def put_block(self, name, index, values):
+        """Vectorised put: `index` may contain slices (the realisation axis of a batch): ONE array assignment per
+        diagnostic and dump instead of one call per realisation."""
+        self.put(name, index, values)
+
+    def view(self, name):
+        """The logical contents of a variable (record variables cut to the number of records written)."""
+        a = self.data[name]
+        return a[:self.nrec] if self._is_rec(name) else a
+
+    # ---- file layout ----
+    def _name_bytes(self, s):
+        b = s.encode()
+        return np.array(len(b), '>i4').tobytes() + b + b'\0' * (_pad4(len(b)) - len(b))
+
+    def _vsize(self, name):
+        tc, dims = self.vars[name]
+        n = 1
+        for d in dims:
+            if self.dims[d] is not None:
+                n *= self.dims[d]
+        return _pad4(n * _NC_CODE[tc][2])
+
+    def _layout(self):
+        names = list(self.vars)
+        dim_ids = {d: i for i, d in enumerate(self.dims)}
+        fixed = [v for v in names if not self._is_rec(v)]
+        recs = [v for v in names if self._is_rec(v)]
+
+        def header(begins, nrec):
+            h = b'CDF\x02' + np.array(nrec, '>i4').tobytes()
+            if self.dims:
+                h += np.array([0x0A, len(self.dims)], '>i4').tobytes()
+                for d, size in self.dims.items():
+                    h += self._name_bytes(d) + np.array(0 if size is None else size, '>i4').tobytes()
             else:
-                handles[name][:] = a
-        f.close()
+                h += np.zeros(2, '>i4').tobytes()
+            h += np.zeros(2, '>i4').tobytes()                       # no global attributes
+            if names:
+                h += np.array([0x0B, len(names)], '>i4').tobytes()
+                for v in names:
+                    tc, dims = self.vars[v]
+                    h += self._name_bytes(v) + np.array([len(dims)] + [dim_ids[d] for d in dims], '>i4').tobytes()
+                    h += np.zeros(2, '>i4').tobytes()               # no attributes
+                    h += np.array([_NC_CODE[tc][0], self._vsize(v)], '>i4').tobytes()
+                    h += np.array(begins.get(v, 0), '>i8').tobytes()
+            else:
+                h += np.zeros(2, '>i4').tobytes()
+            return h
+
+        hlen = len(header({}, 0))
+        off, begins = hlen, {}
+        for v in fixed:
+            begins[v] = off
+            off += self._vsize(v)
+        self._rec0 = off
+        rel = 0
+        for v in recs:
+            begins[v] = off + rel
+            rel += self._vsize(v)
+        self._recsize = rel
+        self._begin, self._fixed, self._recs, self._header = begins, fixed, recs, header
+
+    def _open(self):
+        if self._fh is None:
+            self._layout()
+            self._fh = open(self.file_name, 'w+b')
+            self._fh.write(self._header(self._begin, 0))
+            self._write_fixed()
+
+    def _write_fixed(self):
+        fh = self._fh
+        for v in self._fixed:
+            tc = self.vars[v][0]
+            raw = np.ascontiguousarray(self.data[v]).astype(_NC_CODE[tc][1]).tobytes()
+            fh.seek(self._begin[v])
+            fh.write(raw + b'\0' * (self._vsize(v) - len(raw)))
+
+    def _record_bytes(self, t):
+        parts = []
+        for v in self._recs:
+            tc = self.vars[v][0]
+            a = self.data[v]
+            self._grow(v, t + 1)
+            raw = np.ascontiguousarray(self.data[v][t]).astype(_NC_CODE[tc][1]).tobytes()
+            parts.append(raw + b'\0' * (self._vsize(v) - len(raw)))
+        return b''.join(parts)
+
+    def sync(self):
+        """Write what changed since the last call: dirty records (appended or re-written in place), the record
+        count and the fixed-size variables."""
+        self._open()
+        fh = self._fh
+        for t in sorted(self._dirty):
+            fh.seek(self._rec0 + t * self._recsize)
+            fh.write(self._record_bytes(t))
+        if self.nrec > self._nrec_disk:
+            # records never touched (gaps) must exist on disk too
+            for t in range(self._nrec_disk, self.nrec):
+                if t not in self._dirty:
+                    fh.seek(self._rec0 + t * self._recsize)
+                    fh.write(self._record_bytes(t))
+            self._nrec_disk = self.nrec
+            fh.seek(4)
+            fh.write(np.array(self.nrec, '>i4').tobytes())
+        self._dirty.clear()
+        self._write_fixed()
+        fh.flush()
+
+    def save(self):
+        self.sync()
+
+    def close(self):
+        if self._fh is not None or self.vars:
+            self.sync()
+            self._fh.close()
+            self._fh = None
 
 
 def read_data_file(file_name):
     """Load every variable of a NetCDF-3 result file into a dict of arrays."""
     f = netcdf_file(file_name, 'r', mmap=False)
-    out = {k: np.array(v.data) for k, v in f.variables.items()}
+    out = {}
+    for k, v in f.variables.items():
+        a = np.array(v.data)
+        out[k] = a.astype(a.dtype.newbyteorder('=')) if a.dtype.kind in 'fi' else a
     f.close()
     return out
+
+
+def cg5_condensed():
+    """
+    Constants of the statically condensed CG5 L2 projection of a piecewise-constant field (du_smooth,
+    diagnostic_equations.py:115-119) on a uniform periodic mesh, per unit cell length, for equispaced Lagrange
+    nodes t_k = k/5 (the CG5 convention of this build):
+        [sa, sb, cL, cR, e_1..4, l_1..4, r_1..4]
+    vertex system  sb (v_{i-1} + v_{i+1}) + sa v_i = cL g_{i-1} + cR g_i,  interior dofs  w_k = e_k g_i + l_k v_i + r_k v_{i+1}.
+    """
+    from numpy.polynomial import polynomial as P
+    t = np.arange(6) / 5.0
+    basis = []
+    for k in range(6):
+        c = np.array([1.0])
+        for j in range(6):
+            if j != k:
+                c = P.polymul(c, np.array([-t[j], 1.0]) / (t[k] - t[j]))
+        basis.append(c)
+    integ = lambda c: P.polyval(1.0, P.polyint(c)) - P.polyval(0.0, P.polyint(c))
+    M = np.array([[integ(P.polymul(basis[a], basis[b])) for b in range(6)] for a in range(6)])
+    c = np.array([integ(b) for b in basis])
+    I, V = [1, 2, 3, 4], [0, 5]
+    MII = M[np.ix_(I, I)]; MIV = M[np.ix_(I, V)]; MVI = M[np.ix_(V, I)]; MVV = M[np.ix_(V, V)]
+    e = np.linalg.solve(MII, c[I])
+    LR = -np.linalg.solve(MII, MIV)
+    S = MVV - MVI @ np.linalg.solve(MII, MIV)
+    cl = c[V] - MVI @ e
+    return np.concatenate([[S[0, 0] + S[1, 1], S[0, 1], cl[1], cl[0]], e, LR[:, 0], LR[:, 1]])
 
 
 def peakon_suite_from_indices(x_cells, max_u, vals, ids):

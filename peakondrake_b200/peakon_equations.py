@@ -4,9 +4,11 @@ realisations.  Two doubles per realisation per step, driven by the SAME Brownian
 PDE (it shares `dW_nums` with StochasticFunctions, peakon_equations.py:15) -- so it consumes the
 increments the step kernel used (imported, or exported from the in-kernel Philox stream).
 
-State is tiny (p, q per realisation), so this runs vectorised on the host; the PDE kernel is the
-hot path.  `pure_xi`, `pure_xi_x`, `pure_xi_xx` are CG1 fields (stochastic_functions.py:175-182)
-evaluated at q by CG1 point evaluation (`.at`, peakon_equations.py:42-44).
+The update runs on the device (pk_peakon_sde_step: one thread per realisation, any number of steps per
+launch, the reference's arithmetic operation by operation), fed either with the increments the step kernel
+exported / imported or -- when no PDE runs (`only_peakons`) -- with the same in-kernel Philox stream.
+`pure_xi`, `pure_xi_x`, `pure_xi_xx` are CG1 fields (stochastic_functions.py:175-182) evaluated at q by
+CG1 point evaluation (`.at`, peakon_equations.py:42-44); they are built once on the host (set-up).
 """
 import numpy as np
 from peakondrake_b200.stochastic_functions import xi_functions, xi_derivative_functions, circulant_tridiag_solve
@@ -49,48 +51,42 @@ def pure_xi_tables(ne, Ld, Xi_family, num_Xis, sigma, nquad=3):
     return xi, xi_x, xi_xx
 
 
-def cg1_at(table, Ld, q):
-    """CG1 point evaluation of table [ne] at positions q [R] on the periodic mesh."""
-    ne = table.shape[-1]
-    s = np.asarray(q, dtype=float) / (Ld / ne)
-    fl = np.floor(s)
-    i = fl.astype(np.int64) % ne
-    th = s - fl
-    return (1 - th) * table[i] + th * table[(i + 1) % ne]
+def initial_pq(u0, x_nodes, Ld, alphasq, peakon_speed=None):
+    """p0, q0 of peakon_equations.py:28-32."""
+    alpha = float(np.sqrt(alphasq))
+    E = np.exp(-float(Ld) / alpha)
+    u0 = np.asarray(u0, dtype=float)
+    p0 = np.max(u0) * 2 * (1 - E) / (1 + E)                           # :28
+    q0 = x_nodes[np.argmax(u0)]                                       # :29 (CG1 projection of x)
+    return (peakon_speed if peakon_speed is not None else p0), q0
 
 
 class PeakonEquations(object):
-    """Batched (p, q) of the peakon SDE; update(dW) mirrors peakon_equations.py:34-65."""
+    """Batched (p, q) of the peakon SDE on the device; update(nsteps, dW) replaces nsteps calls of
+    peakon_equations.py:34-65 for every realisation of `engine`."""
 
-    def __init__(self, u0, x_nodes, Ld, dt, alphasq, tables, R, peakon_speed=None, method='ito_euler'):
-        self.Ld, self.dt, self.alpha, self.method = float(Ld), float(dt), float(np.sqrt(alphasq)), method
-        self.xi, self.xi_x, self.xi_xx = tables
-        E = np.exp(-self.Ld / self.alpha)
-        u0 = np.asarray(u0, dtype=float)
-        p0 = np.max(u0) * 2 * (1 - E) / (1 + E)                       # :28
-        q0 = x_nodes[np.argmax(u0)]                                   # :29 (CG1 projection of x)
-        self.p = np.full(R, peakon_speed if peakon_speed is not None else p0, dtype=float)
-        self.q = np.full(R, q0, dtype=float)
+    def __init__(self, engine, u0, x_nodes, tables, peakon_speed=None, method='ito_euler'):
+        import torch
+        self.eng, self.method = engine, method
+        if method not in ('ito_euler', 'milstein'):
+            raise ValueError('peakon_method must be ito_euler or milstein, not %s' % method)
+        self.alpha = float(np.sqrt(engine.alphasq))
+        self.E = float(np.exp(-engine.Ld / self.alpha))
+        p0, q0 = initial_pq(u0, x_nodes, engine.Ld, engine.alphasq, peakon_speed)
+        dev = engine.device
+        self.p_dev = torch.full((engine.R,), float(p0), dtype=torch.float64, device=dev)
+        self.q_dev = torch.full((engine.R,), float(q0), dtype=torch.float64, device=dev)
+        self.tables = tuple(torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64)).to(dev) for t in tables)
 
-    def update(self, dW):
-        """dW: [R, num_Xis] increments of this step."""
-        E = np.exp(-self.Ld / self.alpha)
-        p, q, dt = self.p, self.q, self.dt
-        dp = np.zeros_like(p)
-        dq = (p / 2) * (1 + E) / (1 - E) * dt
-        for k in range(self.xi.shape[0]):
-            xi = cg1_at(self.xi[k], self.Ld, q)
-            xi_x = cg1_at(self.xi_x[k], self.Ld, q)
-            xi_xx = cg1_at(self.xi_xx[k], self.Ld, q)
-            w = dW[:, k]
-            if self.method == 'ito_euler':
-                dp = dp + p / 2 * (xi_x * xi_x - xi * xi_xx) * dt - p * xi_x * w
-                dq = dq + 0.5 * xi * xi_x * dt + xi * w
-            elif self.method == 'milstein':
-                dp = dp + p / 2 * (xi_x * xi_x - xi * xi_xx) * w ** 2 - p * xi_x * w
-                dq = dq + 0.5 * xi * xi_x * w ** 2 + xi * w
-        self.p = p + dp
-        q = q + dq
-        q = np.where(q < 0, q + self.Ld, q)
-        q = np.where(q > self.Ld, q - self.Ld, q)
-        self.q = q
+    def update(self, nsteps, dW=None, step0=0, traj_stride=0):
+        """dW: device tensor [nsteps, R, num_Xis] or None (Philox of global steps step0..)."""
+        return self.eng.peakon_sde_step(nsteps, self.p_dev, self.q_dev, self.tables, self.E, self.method,
+                                        dW=dW, step0=step0, traj_stride=traj_stride)
+
+    @property
+    def p(self):
+        return self.p_dev.cpu().numpy()
+
+    @property
+    def q(self):
+        return self.q_dev.cpu().numpy()
