@@ -32,11 +32,28 @@ NE, LD, DT, NXI, SIGMA, IC = 1000, 40.0, 1e-3, 4, 0.2, 'proper_peak'
 R_PER_GPU = 1024
 STEPS_PER_LAUNCH = 50
 B_ALG = 16 * NE + 8 * NXI      # algorithmic bytes per realisation-step
-DRAM_TRAFFIC_PER_LAUNCH = 33.70e6   # bytes, ncu capture profiles/r1j_ncu_full_pk_step_kernel.csv
 METRIC = 'realisation_steps_per_sec'
 UNIT = 'realisation*steps/s'
 WORKLOAD = ('C2: stochastic CH hydrodynamic/midpoint, ne=1000, Ld=40, dt=1e-3, 4 sines sigma=0.2, '
             'ic proper_peak, %d realisations/GPU, %d timesteps per launch' % (R_PER_GPU, STEPS_PER_LAUNCH))
+
+
+def shared_config(world):
+    """`config` is the SAME object in both arms (the driver compares them); arm-specific facts go to `details`."""
+    return {'workload': WORKLOAD, 'realisations_total': world * R_PER_GPU, 'ne': NE, 'dt': DT,
+            'timesteps_per_launch': STEPS_PER_LAUNCH, 'noise_modes': NXI, 'sigma': SIGMA, 'ic': IC,
+            'l2': 'GPU arm: flushed between timed iterations (256 MB memset); CPU arm: not applicable'}
+
+
+def measured_traffic():
+    """dram bytes per launch of the headline kernel, from the file profiles/ncu_traffic.py writes out of an
+    `ncu --set full` capture of this very command (never a literal here); None if no capture has been summarised."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            t = json.load(f)
+        return float(t['pk_step_kernel']['dram_bytes_per_launch']), t['pk_step_kernel'].get('source')
+    except Exception:
+        return None, None
 
 
 def measured_peak():
@@ -198,8 +215,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': len(rates), 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(walls) / len(walls),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'note': 'CPU arm: Firedrake is not installable offline; this is the '
-                   'oracle port of the same weak form (BASELINE.md section 4), each step a bounded sample'},
+        'config': shared_config(args.gpus),
+        'details': {'note': 'CPU arm: Firedrake is not installable offline; this is the oracle port of the same weak form '
+                            '(BASELINE.md section 4), each step a bounded sample extrapolated linearly (realisations are independent)'},
         'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': arm.workers, 'kind': 'port',
                          'sample': arm.sample(nsteps, sum(walls) / len(walls)) + ' per bench step'},
         'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -212,6 +230,91 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
+def extra_configs(rank, world, local, peak):
+    """The other BASELINE configurations and the upwind scheme, measured in the same process after the headline
+    (VERDICT r1 #4): per-GPU shard at full size, device-timed (CUDA events around the whole leg, max over ranks),
+    step-kernel time from the library's own event pairs."""
+    import torch
+    import torch.distributed as dist
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    from peakondrake_b200 import ensemble as ens
+    dev = torch.device('cuda', local)
+    comm = ens.Comm.world(dev)
+    out = {}
+
+    def leg(name, ne, R, dt, ic, fam, nxi, sigma, launches, steps_per_launch, scheme='hydrodynamic', peak_width=1.0,
+            nupd=1, per_launch=None, b_alg=None, note=''):
+        eng = EnsembleIntegrator(ne, LD, dt, R, scheme=scheme, timestepping='ssprk3' if scheme == 'upwind' else 'midpoint',
+                                 num_Xis=nxi, Xi_family=fam, sigma=sigma, nXi_updates=nupd, seed=2026,
+                                 rid_offset=rank * R, device=local)
+        eng.set_state(build_initial_u(ne, LD, ic, peak_width=peak_width))
+        ctx = dict(eng=eng, comm=comm)
+        if per_launch is not None:
+            per_launch(ctx, True)
+        eng.step(steps_per_launch)                      # warm-up launch
+        if per_launch is not None:
+            per_launch(ctx, False)
+        torch.cuda.synchronize()
+        eng.kernel_ms_since()
+        n0 = eng.launch_count
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(launches):
+            eng.step(steps_per_launch)
+            if per_launch is not None:
+                per_launch(ctx, False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        kms, kn = eng.kernel_ms_since()
+        units = world * R * launches * steps_per_launch
+        rate = units / (ms.item() * 1e-3)
+        b = b_alg if b_alg is not None else (16 * ne + 8 * nxi)
+        failed = int((eng.fail_step >= 0).sum().item())
+        out[name] = {'workload': note, 'ne': ne, 'realisations_per_gpu': R, 'timesteps': launches * steps_per_launch,
+                     'value': rate, 'unit': UNIT, 'ms_total': ms.item(),
+                     'step_kernel_ms_per_launch': (kms / kn) if kn else None,
+                     'step_kernel_rate': (R * steps_per_launch * kn / (kms * 1e-3)) if kn and kms > 0 else None,
+                     'algorithmic_bytes_per_realisation_step': b, 'hbm_frac': rate / world * b / (peak * 1e9),
+                     'gpu_launches': eng.launch_count - n0, 'failed_realisations': failed, 'layout': eng.layout}
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+
+    # C3: 8192 realisations per GPU, ne=2000, 4 sines, moments + histograms all-reduced every 100 steps
+    def c3_stats(ctx, first):
+        if first:
+            ctx['stats'] = ens.EnsembleStatistics(ctx['eng'], nbins=64, lo=0.0, hi=LD)
+            return
+        ctx['stats'].update(comm=ctx['comm'])
+    leg('C3', 2000, 8192, 1e-3, 'periodic_peakon', 'sines', 4, 0.2, 3, 100, per_launch=c3_stats,
+        note='65536 realisations over 8 GPUs = 8192/GPU, ne=2000, periodic_peakon, 4 sines sigma=0.2, dt=1e-3; per-x moments, '
+             'scalar moments/extrema and the q_pde / min_du histograms all-reduced every 100 steps')
+
+    # C4: 4096 realisations, ne=16384, steep front, diagnostics every step
+    def c4_diag(ctx, first):
+        if first:
+            return
+        ctx['eng'].diagnostics()
+        ctx['eng'].peakon_suite()
+    leg('C4', 16384, 4096, 5e-4, 'new_peak', 'constant', 1, 0.2, 30, 1, peak_width=1 / 6, per_launch=c4_diag,
+        b_alg=16 * 16384 + 8 + 8 * 18,
+        note='4096 realisations, ne=16384, new_peak width 1/6, constant Xi sigma=0.2, dt=5e-4, min_du / max_du / '
+             'max_jump_local / peakon_suite every step')
+    # C5: strong-convergence sweep shard, ne=20000, sigma=1 (the dt=1e-3 member, nXi_updates=1000)
+    leg('C5', 20000, 8192, 1e-3, 'periodic_peakon', 'constant', 1, 1.0, 2, 20, nupd=1000,
+        note='8192 realisations, ne=20000, periodic_peakon, constant Xi sigma=1, dt=1e-3 with nXi_updates=1000 (the '
+             'dt-sweep member in the middle of peakon_strong_dt.py), in-kernel Philox sub-updates')
+    # upwind / ssprk3 (the genuinely HBM-shaped scheme), ne=1000, 4 sines
+    leg('upwind_ssprk3', 1000, 4096, 1e-3, 'proper_peak', 'sines', 4, 0.02, 3, 50, scheme='upwind', b_alg=32 * 1000 + 8 * 4,
+        note='upwind/ssprk3 (equations.py:28-61), ne=1000, 4 sines sigma=0.02, 4096 realisations, 50 steps per launch')
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -225,6 +328,7 @@ def run_gpu(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    comm = ens.Comm.world(dev)
 
     R = R_PER_GPU
     u0 = build_initial_u(NE, LD, IC)
@@ -234,14 +338,26 @@ def run_gpu(args):
     stats = ens.EnsembleStatistics(eng, nbins=64, lo=0.0, hi=LD)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > L2 (126 MB)
     side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    # The ensemble statistics of a launch (local fused reductions + the packed all-reduces) run on a side stream,
+    # overlapping the NEXT step kernel.  They work on a SNAPSHOT of (u, fail_step) taken on the main stream, and the
+    # next snapshot waits for the side stream: nothing the statistics read is being overwritten.
+    snap_u = torch.empty_like(eng.u)
+    snap_fs = torch.empty_like(eng.fail_step)
+    snap_ready = torch.cuda.Event()
+    side_done = torch.cuda.Event()
+    side_done.record(side)
 
     def one_step():
         flush.zero_()                         # L2 flush between timed iterations
         eng.step(STEPS_PER_LAUNCH)            # (CUDA events around the kernel are recorded on the launching stream)
-        # ensemble statistics: local fused reduction + ONE packed all-reduce on a side stream
-        side.wait_stream(torch.cuda.current_stream(dev))
+        main.wait_event(side_done)            # the previous statistics are done with the snapshot
+        snap_u.copy_(eng.u); snap_fs.copy_(eng.fail_step)
+        snap_ready.record(main)
+        side.wait_event(snap_ready)
         with torch.cuda.stream(side):
-            stats.update(world > 1)
+            stats.update(comm=comm, u=snap_u, fail_step=snap_fs)
+            side_done.record(side)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -254,6 +370,7 @@ def run_gpu(args):
         dist.barrier()
     torch.cuda.synchronize()
     sampler.mark_begin()
+    launches0 = eng.launch_count
     kms, klaunches = 0.0, 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -263,7 +380,7 @@ def run_gpu(args):
         if (i + 1) % 48 == 0 or i + 1 == args.steps:      # the event ring holds 64 launches
             ms_, n_ = eng.kernel_ms_since()
             kms += ms_; klaunches += n_
-    torch.cuda.current_stream(dev).wait_stream(side)
+    main.wait_stream(side)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -272,6 +389,7 @@ def run_gpu(args):
     sampler.mark_end()
     wall = time.perf_counter() - t0
     dev_ms = ev0.elapsed_time(ev1)
+    gpu_launches = eng.launch_count - launches0          # counted by the library at every kernel launch
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: the host-buffer C-ABI call, pinned host arrays, H2D + kernel + D2H every step ----
@@ -286,7 +404,7 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     te0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 20))
     for _ in range(e2e_steps):
         eng.step_host(STEPS_PER_LAUNCH, hu, None, None, None, None, hfs, hil, hit)
         energy_check = float(hu[0].max())       # the host reads the step's result
@@ -303,37 +421,53 @@ def run_gpu(args):
     e2e_value = units_per_step * e2e_steps / (e2e_ms * 1e-3)
     failed = int((eng.fail_step >= 0).sum().item())
     its_per_step = float(eng.its_total.double().mean().item()) / ((args.warmup + args.steps) * STEPS_PER_LAUNCH)
+    layout = eng.layout
+    eng.close()
+    del eng, flush, snap_u
+    torch.cuda.empty_cache()
+
+    peak, which = measured_peak()
+    configs = None
+    if args.configs:
+        try:
+            configs = extra_configs(rank, world, local, peak)
+        except Exception as e:          # the headline line must survive a failing extra leg
+            configs = {'error': repr(e)}
 
     if rank == 0:
-        peak, which = measured_peak()
         k_ms = kms / max(1, klaunches)
         achieved = R * STEPS_PER_LAUNCH * B_ALG / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic()
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'realisations_total': world * R, 'ne': NE, 'dt': DT,
-                       'timesteps_per_launch': STEPS_PER_LAUNCH, 'noise': 'Philox4x32-10 in-kernel',
-                       'l2': 'flushed between timed iterations (256 MB memset)',
-                       'layout': eng.layout, 'failed_realisations': failed,
-                       'mean_newton_its_per_step': its_per_step},
+            'config': shared_config(world),
+            'details': {'noise': 'Philox4x32-10 in-kernel', 'layout': layout, 'failed_realisations': failed,
+                       'mean_newton_its_per_step': its_per_step,
+                       'statistics': 'per launch: fused diagnostics + per-x moments + scalar moments/extrema + histograms on a '
+                                     'snapshot of the state, side stream, two packed all-reduces (sum, min)'},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps,
-                    'api': 'pk_step_host: u in/out through pinned host buffers (2-chunk H2D/kernel/D2H pipeline); the Newton '
-                           'warm start (u1, dF, dG) is solver-internal state as in the reference and stays in the context'},
-            'gpu_launches': args.steps * 4,   # per step: pk_step_kernel, pk_diag_kernel, pk_moments_partial, pk_moments_final
+                    'api': 'pk_step_host: u in/out through pinned host buffers (chunked H2D/kernel/D2H pipeline, counters in one '
+                           'staging block per chunk); the Newton warm start (u1, dF, dG) is solver-internal state as in the '
+                           'reference and stays in the context'},
+            'gpu_launches': gpu_launches,
+            'gpu_launches_note': 'pk_launch_count: per step pk_step_kernel, pk_diag_kernel, pk_moments_partial, pk_moments_final, '
+                                 'pk_ensemble_scalars_kernel',
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': DRAM_TRAFFIC_PER_LAUNCH, 'peak_source': which,
-                         'traffic_note': 'dram__bytes_read+write per launch from the ncu --set full capture in profiles/ '
-                                         '(state is loaded once per launch and stepped on-chip for 50 timesteps)',
+                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': which,
+                         'traffic_note': 'dram__bytes_read+write per launch, read from profiles/traffic.json (%s); the state is '
+                                         'loaded once per launch and stepped on-chip for 50 timesteps' % traffic_src,
                          'kernel': 'pk_step_kernel', 'kernel_ms': k_ms,
                          'algorithmic_bytes_per_realisation_step': B_ALG,
-                         'note': 'not HBM-bound by construction (SURVEY.md 8d): ~700 fp64 instructions per node-step '
-                                 'against 16 algorithmic bytes; measured limiters are fp64 issue and instruction supply '
-                                 '(fp64 pipe 53 %, instruction cache 87 % of its request peak), see DESIGN.md section 4'},
+                         'note': 'not HBM-bound by construction (SURVEY.md 8d): ~600 fp64 instructions per node-step against '
+                                 '16 algorithmic bytes; the binding resource is the fp64 pipe (DESIGN.md section 4)'},
             'wall_ms_per_step': wall_ms / args.steps,
         }
+        if configs is not None:
+            line['configs'] = configs
         if args.cpu_baseline:
             rate, cores, sample = cpu_rate(15.0)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
@@ -349,6 +483,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='cpu_baseline', action='store_false')
+    ap.add_argument('--no-configs', dest='configs', action='store_false',
+                    help='skip the extra legs (C3, C4, C5, upwind) measured after the headline')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
     if args.impl == 'reference':

@@ -114,6 +114,20 @@ int pk_step(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, doub
             const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
             int32_t* its_total, void* stream);
 
+/* pk_step with the dump diagnostics FUSED into the step kernel: after every dump_every-th step of the launch the
+ * kernel evaluates, on the state it holds in shared memory, what DiagnosticEquations.solve() + dump_diagnostics
+ * (simulation.py:118-125) compute on a dump step, and writes row d = (n+1)/dump_every - 1 (n = launch-local step):
+ *   diag_out [nsteps/dump_every, R, PK_NDIAG], diag_idx [nsteps/dump_every, R, PK_NIDX]: the columns PK_D_ENERGY ..
+ *            PK_D_MAX_U and the four indices of pk_diagnostics (bit-identical extrema / indices; sums differ in
+ *            summation order only); the m- and SDE-based columns are NaN -- use pk_diagnostics for those;
+ *   suite_vals [.., R, 2], suite_ids [.., R, 3] or both NULL: the output of pk_peakon_suite for the same state.
+ * One launch serves all dumps of the chunk: a run that dumps every step (BASELINE config 4) needs no second
+ * kernel and never re-reads u.  The step counter must be a multiple of dump_every on entry. */
+int pk_step_dump(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                 const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                 int32_t* its_total, int32_t dump_every, double* diag_out, int32_t* diag_idx,
+                 double* suite_vals, int32_t* suite_ids, void* stream);
+
 /* Same, with HOST buffers: copies state (and dW_in) to internal device buffers, steps, copies the
  * state, dW_out and the counters back, and synchronises (the realisations go through a 2-chunk
  * H2D / kernel / D2H pipeline on internal streams; pin the host buffers).  This is the call a host
@@ -225,6 +239,9 @@ int pk_peakon_sde_step(pk_ctx* ctx, int32_t nsteps, double* p, double* q, const 
  *   field [R, 5*ne] or NULL: du_smooth itself */
 int pk_du_smooth_loc(pk_ctx* ctx, const double* u, const int32_t* fail_step, const double* consts, double* out,
                      int32_t* idx, double* field, void* stream);
+
+/* number of kernels of this library launched through the context so far (bench.py's gpu_launches) */
+int64_t pk_launch_count(const pk_ctx* ctx);
 
 /* layout query (for tests / documentation): threads per realisation, rows per thread, remainder */
 int pk_get_layout(const pk_ctx* ctx, int32_t* T, int32_t* M, int32_t* rem, int32_t* smem_bytes);

@@ -19,7 +19,7 @@ I_ARGMAX_DU, I_ARGMIN_DU, I_ARGMAX_U, I_ARGMAX_JUMP, NIDX = range(5)
 
 EXPORTS = ['pk_create', 'pk_destroy', 'pk_last_error', 'pk_set_tables', 'pk_step', 'pk_step_host',
            'pk_set_step_counter', 'pk_get_step_counter', 'pk_diagnostics', 'pk_get_layout',
-           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite', 'pk_step_upwind', 'pk_diagnostics_dg1', 'pk_get_work_split', 'pk_reset_warm_start', 'pk_mu', 'pk_step_kernel_ms_since', 'pk_ensemble_scalars', 'pk_peakon_sde_step', 'pk_du_smooth_loc']
+           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite', 'pk_step_upwind', 'pk_diagnostics_dg1', 'pk_get_work_split', 'pk_reset_warm_start', 'pk_mu', 'pk_step_kernel_ms_since', 'pk_ensemble_scalars', 'pk_peakon_sde_step', 'pk_du_smooth_loc', 'pk_launch_count', 'pk_step_dump']
 
 
 class PkConfig(ctypes.Structure):
@@ -91,6 +91,10 @@ def load():
                                        ctypes.c_double, dp, ctypes.c_int32, vp]
     lib.pk_du_smooth_loc.restype = ctypes.c_int
     lib.pk_du_smooth_loc.argtypes = [vp, dp, ip, dp, dp, ip, dp, vp]
+    lib.pk_step_dump.restype = ctypes.c_int
+    lib.pk_step_dump.argtypes = [vp, ctypes.c_int32, dp, dp, dp, dp, dp, dp, ip, ip, ip, ctypes.c_int32, dp, ip, dp, ip, vp]
+    lib.pk_launch_count.restype = ctypes.c_int64
+    lib.pk_launch_count.argtypes = [vp]
     _lib = lib
     return lib
 

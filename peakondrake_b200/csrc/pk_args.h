@@ -17,4 +17,7 @@ struct StepArgs {
   int part;           // cluster kernel: 1 = Schur solve partitioned by CTA, separators solved redundantly in every CTA (default);
                       // 2 = same, separators solved by the leading threads (a cluster barrier per level); 0 = flat PCR
   int nb;             // step blocks per realisation: items = nb * R, item i = (block i / R, realisation i % R)
+  // fused dumps (pk_step_dump): see StepIO in pk_core.h
+  int diag_every;
+  double* diag_out; int* diag_idx; double* suite_vals; int* suite_ids;
 };

@@ -103,6 +103,7 @@ extern "C" int pk_peakon_sde_step(pk_ctx* c, int32_t nsteps, double* p, double* 
   a.step0 = step0; a.rid0 = c->cfg.rid_offset; a.seed = c->cfg.seed;
   a.dt = c->p.dt; a.Ld = c->cfg.Ld; a.h = c->cfg.Ld / c->p.ne; a.E = E; a.sdt = c->p.sdt;
   pk_peakon_sde_kernel<<<(a.R + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }
@@ -155,6 +156,7 @@ extern "C" int pk_ensemble_scalars(pk_ctx* c, const double* diag, const int32_t*
   if (!diag || !fail_step || !sums || !ext) return fail(c, "pk_ensemble_scalars: null pointer");
   CK(c, cudaSetDevice(c->cfg.device));
   pk_ensemble_scalars_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(diag, fail_step, c->cfg.R, sums, ext);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }
@@ -285,6 +287,7 @@ extern "C" int pk_du_smooth_loc(pk_ctx* c, const double* u, const int32_t* fail_
   if (2 * K + 1 <= ne) { a.K = K; a.gscale = 1.0 / (kappa * (1.0 - a.rho * a.rho)); }      // |rho|^K < 1e-40
   else { a.K = -1; a.gscale = 1.0 / (kappa * (1.0 - a.rho * a.rho) * (1.0 - a.rn)); }
   pk_du_smooth_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(a);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }

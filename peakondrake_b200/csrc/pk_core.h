@@ -1200,6 +1200,65 @@ struct Thread {
     }
   }
 
+  // ---- fused dump diagnostics on the state in shared memory -----------------------------------------
+  // What pk_diag_kernel computes from global memory (outputting.py:106-142,156-162 on the fields of
+  // diagnostic_equations.py:94-113), evaluated by every thread on its own rows, with the SAME per-node expressions
+  // (du = (u_{i+1} - u_i)/h, jump = |du_i - du_{i-1}|), so extrema and indices are bit-identical to the separate
+  // kernel; sums differ only in summation order.  av/ai: candidates of  max du, max -du, max u, max |jump|
+  // (ties -> lowest node index, NumPy argmax / argmin).
+  template <class SH>
+  PK_HD double ldn2(const Params& p, const SH& sh, const double* a, int j) const {      // j in [-1, m + 1]
+    const int mm = ext ? M : M - 1;
+    return j <= mm ? ldn(p, sh, a, j) : sh.ld(a, TN(p) + tr);                           // row 1 of the right neighbour
+  }
+  template <class SH>
+  PK_HD void diag_local(const Params& p, const SH& sh, double* s3, double* av, int* ai) const {
+    const double h = p.h, ih = 1.0 / p.h, h3 = p.h * (1.0 / 3.0);
+    double sM = 0.0, sK = 0.0, sU = 0.0;
+    PK_UNROLL
+    for (int c = 0; c < 4; ++c) { av[c] = -1.7976931348623157e308 * 2.0; ai[c] = 0x7fffffff; }
+    double um = ldn(p, sh, sh.U0, -1), u0 = ldn(p, sh, sh.U0, 0);
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (has_row(j)) {
+        const double up = ldn(p, sh, sh.U0, j + 1);
+        const int i = s + j;
+        const double du = (up - u0) / h, dum = (u0 - um) / h;
+        const double jmp = fabs(du - dum);
+        sM += h3 * (u0 * u0 + u0 * up + up * up);
+        sK += (up - u0) * (up - u0) * ih;
+        sU += h * u0;
+        const double cand[4] = {du, -du, u0, jmp};
+        PK_UNROLL
+        for (int c = 0; c < 4; ++c)
+          if (cand[c] > av[c] || (cand[c] == av[c] && i < ai[c])) { av[c] = cand[c]; ai[c] = i; }
+        um = u0; u0 = up;
+      }
+    }
+    s3[0] = sM; s3[1] = sK; s3[2] = sU;
+  }
+  // the two scans of peakon_diagnostics (outputting.py:401-435) as "smallest k" searches (pk_peakon_suite_kernel):
+  //   k2[0]: smallest k in [0, ne/2) with du[D] > du[D-1], D = pc + k;   k2[1]: ... with du[D] < du[D+1], D = pc - 1 - k
+  template <class SH>
+  PK_HD void suite_local(const Params& p, const SH& sh, int pc, int* k2) const {
+    const int ne = p.ne, S = ne / 2;
+    const double h = p.h;
+    k2[0] = k2[1] = 0x7fffffff;
+    double u0 = ldn2(p, sh, sh.U0, 0), up = ldn2(p, sh, sh.U0, 1);
+    double dum = (u0 - ldn2(p, sh, sh.U0, -1)) / h, du0 = (up - u0) / h;
+    PK_UNROLL
+    for (int j = 0; j < M; ++j) {
+      if (has_row(j)) {
+        const double upp = ldn2(p, sh, sh.U0, j + 2);
+        const double dup = (upp - up) / h;
+        const int i = s + j;
+        if (du0 > dum) { int k = i - pc; if (k < 0) k += ne; if (k < S && k < k2[0]) k2[0] = k; }
+        if (du0 < dup) { int k = pc - 1 - i; if (k < 0) k += ne; if (k < S && k < k2[1]) k2[1] = k; }
+        dum = du0; du0 = dup; up = upp;
+      }
+    }
+  }
+
   // ---- NOISE_SCALAR: the dXi value of this step ------------------------------------------------
   template <class SH>
   PK_HD void set_scalar_noise(const Params& p, const SH& sh) {
@@ -1325,7 +1384,76 @@ struct StepIO {
   int* its_last;          // [R] out: Newton iterations of the last attempted step
   int* its_total;         // [R] in/out: accumulated Newton iterations
   int* fail_reason;       // [R] out: 0 ok, 1 max_it, 2 nan, 3 dtol
+  // fused dumps: after every diag_every-th step of the launch (launch-local step n with (n+1) % diag_every == 0) the
+  // diagnostics of the state are written to row d = (n+1)/diag_every - 1 of these arrays (0 = off)
+  int diag_every = 0;
+  double* diag_out = nullptr;     // [ndumps, R, DIAG_NCOL]
+  int* diag_idx = nullptr;        // [ndumps, R, DIAG_NIDX]
+  double* suite_vals = nullptr;   // [ndumps, R, 2] or null
+  int* suite_ids = nullptr;       // [ndumps, R, 3] or null
 };
+
+// column layout of the fused dump == include/peakon_b200.h (PK_D_*, PK_I_*); static_assert'ed in pk_lib.cu
+enum { DIAG_NCOL = 14, DIAG_NIDX = 4,
+       DG_ENERGY = 0, DG_L2U2 = 1, DG_H1SEMI2 = 2, DG_MASS_U = 3, DG_MAX_DU = 4, DG_MIN_DU = 5, DG_MAX_JUMP = 6, DG_MAX_U = 7,
+       DGI_ARGMAX_DU = 0, DGI_ARGMIN_DU = 1, DGI_ARGMAX_U = 2, DGI_ARGMAX_JUMP = 3 };
+PK_HD double nan_quiet() {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(0x7ff8000000000000LL);
+#else
+  return std::nan("");
+#endif
+}
+
+// One fused dump of the realisation whose state is resident in `sh` (executor collectives: allreduce3, argmax4, minint2).
+template <int M, int MODE, int TT, class Exec, class Th, class SH>
+PK_HD void diag_dump(Exec& ex, const Params& p, const SH& sh, const StepIO& io, int d, bool failed) {
+  const long long row = (long long)d * io.R + io.r;
+  double* out = io.diag_out + row * DIAG_NCOL;
+  int* idx = io.diag_idx + row * DIAG_NIDX;
+  if (failed) {          // outputting.py:107-108
+    ex.one([&]() {
+      for (int k = 0; k < DIAG_NCOL; ++k) out[k] = nan_quiet();
+      for (int k = 0; k < DIAG_NIDX; ++k) idx[k] = -1;
+      if (io.suite_vals) { io.suite_vals[2 * row] = nan_quiet(); io.suite_vals[2 * row + 1] = nan_quiet(); }
+      if (io.suite_ids) { io.suite_ids[3 * row] = -1; io.suite_ids[3 * row + 1] = -1; io.suite_ids[3 * row + 2] = -1; }
+    });
+    return;
+  }
+  double sums[3], av[4];
+  int ai[4];
+  // (one pass over the rows feeds both collectives; the partials live in the threads' fn2/sn2/xn2 slots, dead here)
+  ex.argmax4([&](Th& th, double* v, int* i) { double s3[3]; th.diag_local(p, sh, s3, v, i); th.fn2 = s3[0]; th.sn2 = s3[1]; th.xn2 = s3[2]; },
+             av, ai, sh.xb);
+  ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, sums);
+  int k2[2] = {0x7fffffff, 0x7fffffff};
+  if (io.suite_vals) ex.minint2([&](Th& th, int* k) { th.suite_local(p, sh, ai[2], k); }, k2, sh.xb);
+  ex.one([&]() {
+    out[DG_ENERGY] = sums[0] + p.alphasq * sums[1];
+    out[DG_L2U2] = sums[0]; out[DG_H1SEMI2] = sums[1]; out[DG_MASS_U] = sums[2];
+    out[DG_MAX_DU] = av[0]; out[DG_MIN_DU] = -av[1]; out[DG_MAX_JUMP] = av[3]; out[DG_MAX_U] = av[2];
+    for (int k = DG_MAX_U + 1; k < DIAG_NCOL; ++k) out[k] = nan_quiet();      // m- and SDE-based columns: pk_diagnostics
+    idx[DGI_ARGMAX_DU] = ai[0]; idx[DGI_ARGMIN_DU] = ai[1]; idx[DGI_ARGMAX_U] = ai[2]; idx[DGI_ARGMAX_JUMP] = ai[3];
+    if (io.suite_vals) {
+      const int ne = p.ne, pc = ai[2];
+      auto uat = [&](int i) { return sh.ld(sh.U0, row_slot_c<M, TT>(p, i)); };
+      auto du = [&](int i) { i %= ne; if (i < 0) i += ne; const int ip = (i + 1 == ne) ? 0 : i + 1; return (uat(ip) - uat(i)) / p.h; };
+      double* vals = io.suite_vals + 2 * row;
+      int* ids = io.suite_ids + 3 * row;
+      ids[0] = pc;
+      if (k2[0] != 0x7fffffff) {
+        const int D = (pc + k2[0]) % ne; int j = D - 1; if (j < 0) j += ne;
+        vals[0] = du(j); ids[1] = j;
+      } else { vals[0] = nan_quiet(); ids[1] = -1; }
+      if (k2[1] != 0x7fffffff) {
+        int D = (pc - 1 - k2[1]) % ne; if (D < 0) D += ne;
+        int j = D - 1; if (j < 0) j += ne;
+        vals[1] = du(D + 1); ids[2] = j;
+      } else { vals[1] = nan_quiet(); ids[2] = -1; }
+    }
+  });
+  ex.sync();       // the exchange area served as scratch: nobody may start the next step before all have read it
+}
 
 // SNES convergence test (SNESConvergedDefault + divergence tolerance).
 // returns 0 = keep iterating, 1 = converged, 2 = diverged (reason set)
@@ -1372,7 +1500,11 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     });
     ex.sync();
     ex.tick(0);
-    if (failed >= 0) continue;
+    if (failed >= 0) {
+      if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
+        diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, true);
+      continue;
+    }
     if (PK_NOISE_OF(MODE) == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
     else ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
     ex.sync();
@@ -1553,6 +1685,8 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     }
     ex.sync();
     ex.tick(12);
+    if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
+      diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, failed >= 0);
   }
   ex.one([&]() {
     io.fail_step[io.r] = failed; io.its_last[io.r] = its_last; io.its_total[io.r] = its_total;

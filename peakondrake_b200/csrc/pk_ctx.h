@@ -36,6 +36,8 @@ struct pk_ctx {
   cudaEvent_t evr[2][64];          // ring of event pairs: pk_step_kernel_ms_since() sums them without per-step syncs
   long long evn, evq;              // pairs recorded / pairs already summed
   bool timed;
+  long long nlaunch;               // kernels of this library launched through the context (pk_launch_count)
+  int* h_stage;                    // pinned [3 R] staging of the counters for pk_step_host
 };
 
 extern std::string g_create_err;

@@ -66,6 +66,59 @@ struct GpuExecT {
     return a;
   }
 
+
+  // ---- collectives of the fused dump diagnostics (diag_dump in pk_core.h) ----
+  // argmax4: four (value, index) candidates per thread -> largest value, lowest index among equals, known to every
+  // thread.  minint2: two ints per thread -> minima.  scratch: CTA-local shared memory (the exchange area, idle at the
+  // end of a step); argmax4 uses doubles [0, 6 nw), minint2 ints from double offset 6 nw on.
+  template <class F> __device__ __forceinline__ void argmax4(F f, double* outv, int* outi, double* scratch) {
+    double v[4]; int ix[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { v[c] = -INFINITY; ix[c] = 0x7fffffff; }
+    if (AA || th.active) f(th, v, ix);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v[c], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix[c], o);
+        if (ov > v[c] || (ov == v[c] && oi < ix[c])) { v[c] = ov; ix[c] = oi; }
+      }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
+    int* si = reinterpret_cast<int*>(scratch + 4 * nw);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { scratch[c * nw + w] = v[c]; si[c * nw + w] = ix[c]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double rv = scratch[c * nw]; int ri = si[c * nw];
+      for (int k = 1; k < nw; ++k) {
+        const double ov = scratch[c * nw + k]; const int oi = si[c * nw + k];
+        if (ov > rv || (ov == rv && oi < ri)) { rv = ov; ri = oi; }
+      }
+      outv[c] = rv; outi[c] = ri;
+    }
+  }
+  template <class F> __device__ __forceinline__ void minint2(F f, int* out, double* scratch) {
+    int k[2] = {0x7fffffff, 0x7fffffff};
+    if (AA || th.active) f(th, k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      k[0] = min(k[0], __shfl_xor_sync(0xffffffffu, k[0], o));
+      k[1] = min(k[1], __shfl_xor_sync(0xffffffffu, k[1], o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
+    int* si = reinterpret_cast<int*>(scratch + 6 * nw);
+    if (lane == 0) { si[w] = k[0]; si[nw + w] = k[1]; }
+    __syncthreads();
+    int r0 = si[0], r1 = si[nw];
+    for (int q = 1; q < nw; ++q) { r0 = min(r0, si[q]); r1 = min(r1, si[nw + q]); }
+    out[0] = r0; out[1] = r1;
+  }
+
   template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
     double v[3] = {0.0, 0.0, 0.0};
     if (AA || th.active) f(th, v);
@@ -189,6 +242,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi; io.xi_x = a.xi_x; io.xi_xx = a.xi_xx;
   io.R = a.R; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
+  io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
 
   // Persistent CTAs pull work items from a global queue: item i = `nblk` consecutive time steps
   // (block i / R) of realisation i % R.  Block-major order: the previous block of a realisation was handed
@@ -339,6 +393,83 @@ struct GpuExecCluster {
     flip ^= 1;
     return a;
   }
+
+  // collectives of the fused dump diagnostics: block-level result, then the C block aggregates through DSMEM
+  // (scratch layout: argmax4 doubles [0, 6 nw) + aggregate [6 nw, 6 nw + 6); minint2 ints from double offset 6 nw + 6)
+  template <class F> __device__ __forceinline__ void argmax4(F f, double* outv, int* outi, double* scratch) {
+    double v[4]; int ix[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { v[c] = -INFINITY; ix[c] = 0x7fffffff; }
+    f(th, v, ix);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v[c], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ix[c], o);
+        if (ov > v[c] || (ov == v[c] && oi < ix[c])) { v[c] = ov; ix[c] = oi; }
+      }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int* si = reinterpret_cast<int*>(scratch + 4 * nw);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { scratch[c * nw + w] = v[c]; si[c * nw + w] = ix[c]; }
+    }
+    __syncthreads();
+    double* agg = scratch + 6 * nw;
+    int* aggi = reinterpret_cast<int*>(agg + 4);
+    if (threadIdx.x == 0) {
+      for (int c = 0; c < 4; ++c) {
+        double rv = scratch[c * nw]; int ri = si[c * nw];
+        for (int k = 1; k < nw; ++k) {
+          const double ov = scratch[c * nw + k]; const int oi = si[c * nw + k];
+          if (ov > rv || (ov == rv && oi < ri)) { rv = ov; ri = oi; }
+        }
+        agg[c] = rv; aggi[c] = ri;
+      }
+    }
+    cg::cluster_group cl = cg::this_cluster();
+    sync();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { outv[c] = -INFINITY; outi[c] = 0x7fffffff; }
+    for (unsigned b = 0; b < C; ++b) {
+      const double* qa = cl.map_shared_rank(agg, b);
+      const int* qi = reinterpret_cast<const int*>(qa + 4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double ov = qa[c]; const int oi = qi[c];
+        if (ov > outv[c] || (ov == outv[c] && oi < outi[c])) { outv[c] = ov; outi[c] = oi; }
+      }
+    }
+  }
+  template <class F> __device__ __forceinline__ void minint2(F f, int* out, double* scratch) {
+    int k[2] = {0x7fffffff, 0x7fffffff};
+    f(th, k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      k[0] = min(k[0], __shfl_xor_sync(0xffffffffu, k[0], o));
+      k[1] = min(k[1], __shfl_xor_sync(0xffffffffu, k[1], o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int* si = reinterpret_cast<int*>(scratch + 6 * nw + 6);
+    if (lane == 0) { si[w] = k[0]; si[nw + w] = k[1]; }
+    __syncthreads();
+    int* agg = si + 2 * nw;
+    if (threadIdx.x == 0) {
+      int r0 = si[0], r1 = si[nw];
+      for (int q = 1; q < nw; ++q) { r0 = min(r0, si[q]); r1 = min(r1, si[nw + q]); }
+      agg[0] = r0; agg[1] = r1;
+    }
+    cg::cluster_group cl = cg::this_cluster();
+    sync();
+    out[0] = out[1] = 0x7fffffff;
+    for (unsigned b = 0; b < C; ++b) {
+      const int* q = cl.map_shared_rank(agg, b);
+      out[0] = min(out[0], q[0]); out[1] = min(out[1], q[1]);
+    }
+  }
+
   template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
     double v[3] = {0.0, 0.0, 0.0};
     f(th, v);
@@ -474,6 +605,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   io.R = a.R; io.r = r; io.rid = a.rid0 + (unsigned)r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.n0 = 0; io.n1 = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
+  io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
   run_steps<M, MODE, 0, GpuExecCluster<M, MODE>, Thread<M, MODE, 0> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
 #ifdef PK_PROFILE

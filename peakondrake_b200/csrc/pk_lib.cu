@@ -439,7 +439,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->xi = c->xi_x = c->xi_xx = nullptr;
   c->w1_resident = false;
   c->step = 0; c->d_state = nullptr; c->d_dWin = c->d_dWout = nullptr; c->d_cnt = nullptr; c->dW_cap = 0; c->d_scratch = nullptr; c->d_mom = nullptr; c->d_prof = nullptr; c->d_tab[0] = c->d_tab[1] = c->d_tab[2] = nullptr;
-  c->timed = false;
+  c->timed = false; c->nlaunch = 0; c->h_stage = nullptr;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
   const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block, c->cminb) : (const void*)pick_kernel(p, c->block, c->fs);
@@ -472,6 +472,7 @@ extern "C" void pk_destroy(pk_ctx* c) {
   if (c->d_queue) cudaFree(c->d_queue);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_mom) cudaFree(c->d_mom);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   for (int q = 0; q < 3; ++q) if (c->d_tab[q]) cudaFree(c->d_tab[q]);
   for (int q = 0; q < 64; ++q) { cudaEventDestroy(c->evr[0][q]); cudaEventDestroy(c->evr[1][q]); }
   cudaEventDestroy(c->hev);
@@ -502,12 +503,15 @@ extern "C" int pk_set_tables(pk_ctx* c, const double* xi, const double* xi_x, co
     CK(c, cudaMemset(c->d_tab[q], 0, sizeof(double) * n));
     dim3 g((c->p.ne + 255) / 256, c->p.nxi);
     pk_permute_table_kernel<<<g, 256>>>(c->p, src[q], c->d_tab[q]);
+    ++c->nlaunch;
     CK(c, cudaGetLastError());
   }
   CK(c, cudaDeviceSynchronize());
   c->xi = c->d_tab[0]; c->xi_x = c->d_tab[1]; c->xi_xx = c->d_tab[2];
   return 0;
 }
+
+extern "C" int64_t pk_launch_count(const pk_ctx* c) { return c ? c->nlaunch : -1; }
 
 extern "C" int pk_set_step_counter(pk_ctx* c, int64_t s) { if (!c) return -1; c->step = s; return 0; }
 extern "C" int64_t pk_get_step_counter(const pk_ctx* c) { return c ? c->step : -1; }
@@ -541,6 +545,7 @@ static int launch_range(pk_ctx* c, StepArgs a, int nsteps, int r0, int nr, int s
     at[0].val.clusterDim.x = (unsigned)c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = 1;
     CK(c, cudaLaunchKernelEx(&lc, pick_cluster_kernel(c->p, c->block, c->cminb), c->p, a, c->lgTc));
+    ++c->nlaunch;
   } else {
     const int R = c->cfg.R;
     if (!c->d_queue) CK(c, cudaMalloc(&c->d_queue, sizeof(int) * (size_t)(R + 1) * PK_HOST_CHUNKS));
@@ -555,6 +560,7 @@ static int launch_range(pk_ctx* c, StepArgs a, int nsteps, int r0, int nr, int s
     if (timed) CK(c, cudaEventRecord(c->ev0, st));      // time the kernel alone
     kern_t k = pick_kernel(c->p, c->block, c->fs);
     k<<<grid, c->block, c->smem, st>>>(c->p, a);
+    ++c->nlaunch;
   }
   CK(c, cudaGetLastError());
   if (timed) { CK(c, cudaEventRecord(c->ev1, st)); c->timed = true; }
@@ -575,6 +581,7 @@ static int step_args(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* d
   { const char* e = getenv("PK_CLUSTER_FLAT_PCR"); a->part = (e && atoi(e) == 1) ? 0 : 1;
     e = getenv("PK_CLUSTER_LEADER_SEP"); if (a->part && e && atoi(e) == 1) a->part = 2; }
   a->R = c->cfg.R; a->step0 = (int)c->step; a->nsteps = nsteps; a->rid0 = c->cfg.rid_offset; a->seed = c->cfg.seed;
+  a->diag_every = 0; a->diag_out = nullptr; a->diag_idx = nullptr; a->suite_vals = nullptr; a->suite_ids = nullptr;
   return 0;
 }
 
@@ -586,6 +593,32 @@ extern "C" int pk_step(pk_ctx* c, int32_t nsteps, double* u, double* u1, double*
   int rc = step_args(c, nsteps, u, u1, dF, dG, dW_in, dW_out, fail_step, its_last, its_total, &a);
   if (rc) return rc;
   if (nsteps == 0) return 0;
+  CK(c, cudaSetDevice(c->cfg.device));
+  rc = launch_range(c, a, nsteps, 0, c->cfg.R, 0, (cudaStream_t)stream, true);
+  if (rc) return rc;
+  c->step += nsteps;
+  return 0;
+}
+
+static_assert((int)DIAG_NCOL == (int)PK_NDIAG && (int)DIAG_NIDX == (int)PK_NIDX && (int)DG_ENERGY == (int)PK_D_ENERGY && (int)DG_L2U2 == (int)PK_D_L2U2 &&
+              (int)DG_H1SEMI2 == (int)PK_D_H1SEMI2 && (int)DG_MASS_U == (int)PK_D_MASS_U && (int)DG_MAX_DU == (int)PK_D_MAX_DU && (int)DG_MIN_DU == (int)PK_D_MIN_DU &&
+              (int)DG_MAX_JUMP == (int)PK_D_MAX_JUMP_LOCAL && (int)DG_MAX_U == (int)PK_D_MAX_U && (int)DGI_ARGMAX_DU == (int)PK_I_ARGMAX_DU &&
+              (int)DGI_ARGMIN_DU == (int)PK_I_ARGMIN_DU && (int)DGI_ARGMAX_U == (int)PK_I_ARGMAX_U && (int)DGI_ARGMAX_JUMP == (int)PK_I_ARGMAX_JUMP,
+              "fused dump layout (pk_core.h) must match include/peakon_b200.h");
+
+extern "C" int pk_step_dump(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                            const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                            int32_t* its_total, int32_t dump_every, double* diag_out, int32_t* diag_idx,
+                            double* suite_vals, int32_t* suite_ids, void* stream) {
+  if (!c) return -1;
+  if (dump_every < 1 || !diag_out || !diag_idx) return fail(c, "pk_step_dump: dump_every >= 1 and the dump arrays are required");
+  if ((suite_vals == nullptr) != (suite_ids == nullptr)) return fail(c, "pk_step_dump: suite_vals and suite_ids go together");
+  if (c->step % dump_every != 0) return fail(c, "pk_step_dump: the step counter (%lld) must be a multiple of dump_every", c->step);
+  StepArgs a;
+  int rc = step_args(c, nsteps, u, u1, dF, dG, dW_in, dW_out, fail_step, its_last, its_total, &a);
+  if (rc) return rc;
+  if (nsteps == 0) return 0;
+  a.diag_every = dump_every; a.diag_out = diag_out; a.diag_idx = diag_idx; a.suite_vals = suite_vals; a.suite_ids = suite_ids;
   CK(c, cudaSetDevice(c->cfg.device));
   rc = launch_range(c, a, nsteps, 0, c->cfg.R, 0, (cudaStream_t)stream, true);
   if (rc) return rc;
@@ -654,17 +687,18 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
     c->dW_cap = ndw;
   }
   double *du = c->d_state, *du1 = du + fld, *ddF = du + 2 * fld, *ddG = du + 3 * fld;
-  int *dfs = c->d_cnt, *dil = dfs + R, *dit = dfs + 2 * R;
+  if (!c->h_stage) CK(c, cudaMallocHost(&c->h_stage, sizeof(int) * 3 * R));
   StepArgs a;
   int rc = step_args(c, nsteps, du, du1, ddF, hasG ? ddG : nullptr, (dW_in && ndw) ? c->d_dWin : nullptr,
-                     (dW_out && ndw) ? c->d_dWout : nullptr, dfs, dil, dit, &a);
+                     (dW_out && ndw) ? c->d_dWout : nullptr, c->d_cnt, c->d_cnt, c->d_cnt, &a);
   if (rc) return rc;
   if (nsteps == 0) return 0;
   // Chunk pipeline: the realisations are split into NC contiguous chunks, each with its own stream doing
   // H2D -> step kernel -> D2H, so the copies of one chunk overlap the kernel of another (the persistent kernels of
   // two chunks share the SMs work-conservingly).  Host buffers should be pinned for the copies to be asynchronous.
-  // (measured on the bench workload, R = 1024: 1 chunk 14.9e6, 2 chunks 15.2e6, 3 / 4 chunks 14.8e6 realisation-steps/s --
-  //  the copies are 0.3 ms of a 3.4 ms call and every chunk adds seven small-copy latencies)
+  // The three counters travel through ONE pinned staging block per chunk, laid out chunk by chunk as
+  // [fail_step | its_total | its_last] (device and staging alike): one H2D of the first two and one D2H of all three
+  // per chunk instead of five small copies (each small copy costs a launch latency, as much as the state copies).
   int NC = (c->cluster > 1 || R < 256) ? 1 : 2;
   { const char* e = getenv("PK_HOST_NCHUNK"); const int v = e ? atoi(e) : 0; if (v >= 1 && v <= PK_HOST_CHUNKS && c->cluster == 1) NC = v; }
   if (dW_in && ndw) {       // [nsteps, R, nxi]: not contiguous per chunk -> one copy up front, every chunk waits for it
@@ -675,14 +709,19 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
     const size_t r0 = R * k / NC, r1 = R * (k + 1) / NC, nr = r1 - r0, o = r0 * ne, nb = sizeof(double) * nr * ne;
     cudaStream_t st = c->hs[k];
     if (dW_in && ndw && k > 0) CK(c, cudaStreamWaitEvent(st, c->hev, 0));
+    int* hs = c->h_stage + 3 * r0;
+    memcpy(hs, fail_step + r0, sizeof(int) * nr);
+    memcpy(hs + nr, its_total + r0, sizeof(int) * nr);
+    int* dc = c->d_cnt + 3 * r0;
     CK(c, cudaMemcpyAsync(du + o, u + o, nb, cudaMemcpyHostToDevice, st));
     if (!resident) {
       CK(c, cudaMemcpyAsync(du1 + o, u1 + o, nb, cudaMemcpyHostToDevice, st));
       CK(c, cudaMemcpyAsync(ddF + o, dF + o, nb, cudaMemcpyHostToDevice, st));
       if (hasG) CK(c, cudaMemcpyAsync(ddG + o, dG + o, nb, cudaMemcpyHostToDevice, st));
     }
-    CK(c, cudaMemcpyAsync(dfs + r0, fail_step + r0, sizeof(int) * nr, cudaMemcpyHostToDevice, st));
-    CK(c, cudaMemcpyAsync(dit + r0, its_total + r0, sizeof(int) * nr, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(dc, hs, sizeof(int) * 2 * nr, cudaMemcpyHostToDevice, st));
+    // the kernels index the counters by the realisation number r in [r0, r1)
+    a.fail_step = dc - r0; a.its_total = dc + nr - r0; a.its_last = dc + 2 * nr - r0;
     rc = launch_range(c, a, nsteps, (int)r0, (int)nr, k, st, false);
     if (rc) return rc;
     CK(c, cudaMemcpyAsync(u + o, du + o, nb, cudaMemcpyDeviceToHost, st));
@@ -691,11 +730,16 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
       CK(c, cudaMemcpyAsync(dF + o, ddF + o, nb, cudaMemcpyDeviceToHost, st));
       if (hasG) CK(c, cudaMemcpyAsync(dG + o, ddG + o, nb, cudaMemcpyDeviceToHost, st));
     }
-    CK(c, cudaMemcpyAsync(fail_step + r0, dfs + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(its_last + r0, dil + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(its_total + r0, dit + r0, sizeof(int) * nr, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(hs, dc, sizeof(int) * 3 * nr, cudaMemcpyDeviceToHost, st));
   }
-  for (int k = 0; k < NC; ++k) CK(c, cudaStreamSynchronize(c->hs[k]));
+  for (int k = 0; k < NC; ++k) {
+    CK(c, cudaStreamSynchronize(c->hs[k]));
+    const size_t r0 = R * k / NC, r1 = R * (k + 1) / NC, nr = r1 - r0;
+    const int* hs = c->h_stage + 3 * r0;
+    memcpy(fail_step + r0, hs, sizeof(int) * nr);
+    memcpy(its_total + r0, hs + nr, sizeof(int) * nr);
+    memcpy(its_last + r0, hs + 2 * nr, sizeof(int) * nr);
+  }
   if (dW_out && ndw) CK(c, cudaMemcpy(dW_out, c->d_dWout, sizeof(double) * ndw, cudaMemcpyDeviceToHost));
   c->timed = false;
   c->step += nsteps;
@@ -725,6 +769,7 @@ extern "C" int pk_diagnostics(pk_ctx* c, const double* u, const double* pq, int3
   if (c->p.ne >= 160) { a.K = 64; a.gscale = 1.0 / (kappa * (1.0 - rho * rho)); }   // |rho|^64 ~ 2e-37
   else { a.K = -1; a.gscale = 1.0 / (kappa * (1.0 - rho * rho) * (1.0 - rn)); }
   pk_diag_kernel<<<c->cfg.R, 256, 0, (cudaStream_t)stream>>>(a);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }
@@ -742,10 +787,12 @@ extern "C" int pk_ensemble_stats(pk_ctx* c, const double* u, const int32_t* fail
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g((ne + 127) / 128, ntile);
   pk_moments_partial<<<g, 128, 0, st>>>(u, fail_step, R, ne, rows, c->d_mom);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   int nb = (2 * ne + 255) / 256; if (nb > 64) nb = 64;
   pk_moments_final<<<nb, 256, sizeof(int) * (2 * nbins + 1), st>>>(c->d_mom, ntile, ne, fail_step, diag, idx, R, nbins,
                                                                 c->p.h, q_lo, q_hi, d_lo, d_hi, packed);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }
@@ -756,6 +803,7 @@ extern "C" int pk_peakon_suite(pk_ctx* c, const double* u, const int32_t* idx, c
   if (!u || !idx || !vals || !ids) return fail(c, "pk_peakon_suite: null pointer");
   CK(c, cudaSetDevice(c->cfg.device));
   pk_peakon_suite_kernel<<<c->cfg.R, 128, 0, (cudaStream_t)stream>>>(u, idx, fail_step, c->p.ne, c->p.h, vals, ids);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }
@@ -802,6 +850,7 @@ extern "C" int pk_mu(pk_ctx* c, const double* u, const double* x_cells, const in
   if (use_smem && sm > 48 * 1024) CK(c, cudaFuncSetAttribute(pk_mu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   pk_mu_kernel<<<R, 128, use_smem ? sm : 0, (cudaStream_t)stream>>>(u, x_cells, fail_step, ne, c->p.h, c->cfg.Ld, use_smem,
                                                                     c->d_scratch, out, status);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }

@@ -154,6 +154,7 @@ extern "C" int pk_step_upwind(pk_ctx* c, int32_t nsteps, double* m, double* u, c
   ukern_t k = pick_ukernel(c->p, c->block);
   CK(c, cudaEventRecord(c->ev0, st));
   k<<<c->cfg.R, c->block, c->smem, st>>>(c->p, a);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(c->ev1, st));
   c->timed = true;
@@ -207,6 +208,7 @@ extern "C" int pk_diagnostics_dg1(pk_ctx* c, const double* m, const double* u, c
   if (!m || !u || !out) return fail(c, "pk_diagnostics_dg1: null pointer");
   CK(c, cudaSetDevice(c->cfg.device));
   pk_diag_dg1_kernel<<<c->cfg.R, 256, 0, (cudaStream_t)stream>>>(m, u, fail_step, c->p.ne, c->p.h, out);
+  ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
 }

@@ -126,6 +126,11 @@ class EnsembleIntegrator(object):
         return d
 
     @property
+    def launch_count(self):
+        """kernels of libpeakon_b200 launched through this context so far"""
+        return int(self.lib.pk_launch_count(self.ctx))
+
+    @property
     def step_counter(self):
         return int(self.lib.pk_get_step_counter(self.ctx))
 
@@ -180,6 +185,36 @@ class EnsembleIntegrator(object):
         self._keep = (dW_dev, out)      # keep inputs alive until the stream has consumed them
         return out
 
+    def step_dump(self, nsteps, dump_every, dW=None, export_dW=False, suite=False):
+        """
+        `nsteps` steps in ONE launch with the dump diagnostics fused into the step kernel (pk_step_dump): returns
+        (exported dW or None, diag [nsteps//dump_every, R, NDIAG], idx [.., R, NIDX], suite_vals [.., R, 2] or None,
+        suite_ids [.., R, 3] or None) as device tensors.  Midpoint schemes only; the m- and SDE-based columns are NaN.
+        """
+        if self.upwind:
+            raise NotImplementedError('step_dump is provided for the midpoint schemes')
+        dW_dev = None
+        if dW is not None and self.num_Xis > 0:
+            dW_dev = torch.as_tensor(dW, dtype=torch.float64).to(self.device).contiguous()
+            if tuple(dW_dev.shape) != (nsteps, self.R, self.num_Xis):
+                raise ValueError('dW must have shape (nsteps, R, num_Xis) = %s, got %s'
+                                 % ((nsteps, self.R, self.num_Xis), tuple(dW_dev.shape)))
+        out = None
+        if export_dW and self.num_Xis > 0:
+            out = torch.empty(nsteps, self.R, self.num_Xis, dtype=torch.float64, device=self.device)
+        nd = nsteps // dump_every
+        diag = torch.empty(nd, self.R, _lib.NDIAG, dtype=torch.float64, device=self.device)
+        idx = torch.empty(nd, self.R, _lib.NIDX, dtype=torch.int32, device=self.device)
+        sv = torch.empty(nd, self.R, 2, dtype=torch.float64, device=self.device) if suite else None
+        si = torch.empty(nd, self.R, 3, dtype=torch.int32, device=self.device) if suite else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.lib.pk_step_dump(self.ctx, int(nsteps), _ptr(self.u), _ptr(self.u1), _ptr(self.dF), _ptr(self.dG),
+                                   _ptr(dW_dev), _ptr(out), _ptr(self.fail_step), _ptr(self.its_last),
+                                   _ptr(self.its_total), int(dump_every), _ptr(diag), _ptr(idx), _ptr(sv), _ptr(si), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        self._keep = (dW_dev, out)
+        return out, diag, idx, sv, si
+
     def last_kernel_ms(self):
         return float(self.lib.pk_last_step_kernel_ms(self.ctx))
 
@@ -204,7 +239,7 @@ class EnsembleIntegrator(object):
         _lib.check(self.lib, self.ctx, self.lib.pk_reset_warm_start(self.ctx))
 
     # -- diagnostics --------------------------------------------------------------------------
-    def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False, fail_step='own'):
+    def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False, fail_step='own', u=None):
         """
         Fused per-realisation reductions. Returns (vals [R, NDIAG] float64, idx [R, NIDX] int32,
         du [R, ne] or None) as device tensors; columns are _lib.D_* / _lib.I_*.
@@ -217,7 +252,7 @@ class EnsembleIntegrator(object):
             pq_dev = torch.as_tensor(pq, dtype=torch.float64).to(self.device).contiguous()
         du = torch.empty(self.R, self.ne, dtype=torch.float64, device=self.device) if want_du else None
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.lib.pk_diagnostics(self.ctx, _ptr(self.u), _ptr(pq_dev), int(bool(periodic)),
+        rc = self.lib.pk_diagnostics(self.ctx, _ptr(self.u if u is None else u), _ptr(pq_dev), int(bool(periodic)),
                                      int(bool(want_m) and not self.upwind),
                                      _ptr(self.diag), _ptr(self.didx), _ptr(du), _ptr(fs), stream)
         _lib.check(self.lib, self.ctx, rc)
@@ -273,13 +308,15 @@ class EnsembleIntegrator(object):
         return self._sm_out, self._sm_idx, field
 
     # -- ensemble statistics (local part; ensemble.EnsembleStatistics owns the buffers and the all-reduce) -----
-    def ensemble_stats_into(self, stats, vals, idx, stream=None):
+    def ensemble_stats_into(self, stats, vals, idx, stream=None, u=None, fail_step=None):
         if stream is None:
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.lib.pk_ensemble_stats(self.ctx, _ptr(self.u), _ptr(self.fail_step), _ptr(vals), _ptr(idx), stats.nbins,
+        u = self.u if u is None else u
+        fs = self.fail_step if fail_step is None else fail_step
+        rc = self.lib.pk_ensemble_stats(self.ctx, _ptr(u), _ptr(fs), _ptr(vals), _ptr(idx), stats.nbins,
                                         stats.q_lo, stats.q_hi, stats.d_lo, stats.d_hi, _ptr(stats.packed), stream)
         _lib.check(self.lib, self.ctx, rc)
-        rc = self.lib.pk_ensemble_scalars(self.ctx, _ptr(vals), _ptr(self.fail_step), _ptr(stats.sums), _ptr(stats.ext), stream)
+        rc = self.lib.pk_ensemble_scalars(self.ctx, _ptr(vals), _ptr(fs), _ptr(stats.sums), _ptr(stats.ext), stream)
         _lib.check(self.lib, self.ctx, rc)
 
     # -- peakon SDE (PeakonEquations.update, peakon_equations.py:34-65) ------------------------------------------

@@ -109,17 +109,21 @@ class EnsembleStatistics(object):
         self.ext = torch.zeros(2 * nd, dtype=torch.float64, device=engine.device)
         self.launches = 0
 
-    def update(self, allreduce=False, comm=None, diagnostics_done=False, **diag_kw):
-        """Recompute the statistics of the engine's current state (on the current stream)."""
+    def update(self, allreduce=False, comm=None, diagnostics_done=False, u=None, fail_step=None, **diag_kw):
+        """Recompute the statistics of the engine's current state (on the current stream).  u / fail_step: a snapshot
+        of the state to work on instead (lets the statistics run on a side stream while the next step kernel already
+        overwrites the live state; the context's statistics scratch is only touched from that one stream)."""
         eng = self.eng
         if diagnostics_done:
             vals, idx = eng.diag, eng.didx
         else:
+            if u is not None:
+                diag_kw = dict(diag_kw, u=u, fail_step=fail_step)
             vals, idx, _ = eng.diagnostics(**diag_kw)
             self.launches += 1
         stream = ctypes.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream) if eng.device.type == 'cuda' else None
         p = lambda t: ctypes.c_void_p(t.data_ptr())
-        eng.ensemble_stats_into(self, vals, idx, stream)
+        eng.ensemble_stats_into(self, vals, idx, stream, u=u, fail_step=fail_step)
         self.launches += 3      # pk_moments_partial + pk_moments_final + pk_ensemble_scalars
         if comm is not None:
             comm.allreduce(self.all_sums, 'sum')

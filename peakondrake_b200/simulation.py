@@ -290,7 +290,9 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
             raise ValueError('If reading in true peakon data, the dump frequency must be the same as that used '
                              'for the true peakon data. Length of true peakon data as %i, but proposed length is %i'
                              % (len(tp['time']), expect))
-        if np.shape(tp['p']) != (expect,):                                 # :57-59
+        # :57-59 wants one path, shape (expect,); the ensemble extension also takes one path PER SEED, shape
+        # (expect, number of seeds), as an `only_peakons` experiment over the same seeds writes it
+        if np.shape(tp['p']) not in ((expect,), (expect, n_total)):
             raise ValueError('True peakon data shape %s must be the same shape as proposed data %s'
                              % ((expect,), np.shape(tp['p'])))
         true_pq = (np.asarray(tp['p'], dtype=float), np.asarray(tp['q'], dtype=float))
@@ -326,6 +328,16 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
                       'u_error_with_sde_mean': ['u_sde_mean'], 'u_error_weak_mean': ['u_sde_mean', 'u_sde_weak_mean']}.get(d, [])
         first = OrderedDict((f, None) for f in order if f in ('u_sde', 'u_sde_mean'))
         mean_follows_file = list(first)[-1] == 'u_sde_mean'
+
+    def true_at(t_idx, k=None):
+        """(p, q) of the true peakon at dump index t_idx: [R, 2], or the pair of realisation k"""
+        p_, q_ = true_pq
+        if p_.ndim == 1:
+            one = np.array([[p_[t_idx], q_[t_idx]]])
+            return np.tile(one, (R, 1)) if k is None else one[0]
+        rows = np.stack([p_[t_idx, seed_indices], q_[t_idx, seed_indices]], axis=1)
+        return rows if k is None else rows[k]
+
     want_m = any(d in M_DIAGNOSTICS for d in diagnostics)
     want_smooth = any(d in SMOOTH_DIAGNOSTICS for d in diagnostics)
     pfac = (1 - np.exp(-Ld / np.sqrt(alphasq))) if periodic else 1.0
@@ -385,12 +397,12 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
             if want_mean and mean_follows_file:
                 pq = np.tile(np.array([[1.0, Ld / 2]]), (R, 1))            # u_sde keeps its initial Constants (:258-259)
             else:
-                pq = np.tile(np.array([[true_pq[0][t_idx], true_pq[1][t_idx]]]), (R, 1))
+                pq = true_at(t_idx)
         extra = {}
         if want_mean:
             # u_sde_mean: the non-periodic profile with its own Constants (diagnostic_equations.py:291-303)
-            pm = np.array([[true_pq[0][t_idx], true_pq[1][t_idx]]]) if mean_follows_file else np.array([[1.0 / amp, Ld / 2]])
-            vm, _, _ = eng.diagnostics(pq=np.tile(pm, (R, 1)), periodic=False, fail_step=fs_dev)
+            pm = true_at(t_idx) if mean_follows_file else np.tile(np.array([[1.0 / amp, Ld / 2]]), (R, 1))
+            vm, _, _ = eng.diagnostics(pq=pm, periodic=False, fail_step=fs_dev)
             extra['err_mean2'] = vm[:, _lib.D_ERR_SDE2].cpu().numpy().copy()
         vals, idx, _ = eng.diagnostics(pq=pq, periodic=periodic, want_m=want_m, fail_step=fs_dev)
         if stats is not None:
@@ -427,8 +439,13 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
         if peq is not None:
             cols['p'] = peq.p
             cols['q'] = peq.q
+        write_columns(t_idx, t, cols)
+        return vals, idx
+
+    def write_columns(t_idx, t, cols, sync=True):
+        """one dump: gather the per-realisation columns to rank 0 and write the record (+ the ensemble statistics)"""
         if data_file is None and comm is None:
-            return vals, idx
+            return
         # one gather per dump: the scalar columns packed side by side; u_field on its own
         scal = [k for k in cols if k != 'u_field']
         packed = gather(np.stack([cols[k] for k in scal], axis=1)) if scal else None
@@ -458,8 +475,8 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
                     if d in STAT_COLUMN:
                         for s, val in zip(('mean', 'var', 'min', 'max'), stats.scalar_stats(STAT_COLUMN[d])):
                             put1('ens_%s_%s' % (d, s), val)
-            data_file.sync()                                                # the record is on disk from here on
-        return vals, idx
+            if sync:
+                data_file.sync()                                            # the record is on disk from here on
 
     # ---- field dumps (.pvd collection per realisation) ----
     field_files = None
@@ -511,7 +528,8 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
                     f[fld] = (f['dXi'][0], 'CG1')                                # :81-82
                 elif fld in ('u_sde', 'u_sde_weak'):
                     j = min(t_idx_now, len(true_pq[0]) - 1)
-                    us = out.u_sde_field(x_nodes, Ld, alphasq, true_pq[0][j], true_pq[1][j], periodic)   # :254-279
+                    pj, qj = true_at(j, k)
+                    us = out.u_sde_field(x_nodes, Ld, alphasq, pj, qj, periodic)   # :254-279
                     # u_sde_weak: M w = M (u - u_sde) (:281-289), i.e. w = u - u_sde nodally
                     f[fld] = (us if fld == 'u_sde' else u_host[k] - us, 'CG1')
             ff.write(f, t)
@@ -531,6 +549,53 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
             # bound the upload of one launch (imported increments travel as [steps, R, num_Xis] doubles)
             chunk = max(1, min(chunk, (1 << 26) // max(1, R * num_Xis)))
         pde_runs = not only_peakons
+        # Dumps whose diagnostics are all columns of the fused in-kernel dump (pk_step_dump) need no second kernel and
+        # no launch per dump: up to `kmax` dumps per launch, one device-to-host copy of their tables, one record each.
+        fused = (pde_runs and ndump > 0 and hasattr(eng, 'step_dump') and not eng.upwind and field_files is None
+                 and stats is None and not (want_m or want_sde or want_mean or want_smooth)
+                 and 'mu' not in diagnostics and 'u_field' not in diagnostics)
+        kmax = max(1, min(256, (1 << 24) // max(1, R * ndump * max(1, num_Xis)))) if host_dW is not None else 256
+        kmax = max(1, min(kmax, (1 << 23) // max(1, R * 23)))
+        while fused and nsteps - done >= ndump:
+            k = min(kmax, (nsteps - done) // ndump)
+            c = k * ndump
+            dW_dev = None
+            if host_dW is not None:
+                dW_dev = torch.from_numpy(np.ascontiguousarray(host_dW[done:done + c])).to(eng.device)
+            want_suite = 'peakon_suite' in diagnostics
+            exported, dg, di, sv, si = eng.step_dump(c, ndump, dW=dW_dev, export_dW=(peq is not None and dW_dev is None and num_Xis > 0),
+                                                     suite=want_suite)
+            traj = None
+            if peq is not None:
+                traj = peq.update(c, dW=dW_dev if dW_dev is not None else exported, step0=done, traj_stride=ndump).cpu().numpy()
+            dg, di = dg.cpu().numpy(), di.cpu().numpy()
+            if want_suite:
+                sv, si = sv.cpu().numpy(), si.cpu().numpy()
+            fs = eng.fail_step.cpu().numpy()
+            for j in range(k):
+                for _ in range(ndump):
+                    t += dt
+                failed = di[j, :, 0] < 0
+                if not allow_fail and failed.any():
+                    break
+                extra = {}
+                if want_suite:
+                    extra['peakon_suite'] = peakon_suite_columns(x_cells, dg[j][:, _lib.D_MAX_U], sv[j], si[j], failed)
+                cols = diagnostic_columns(diagnostics, dg[j], di[j], failed, x_cells, alphasq, pfac, extra)
+                if traj is not None:
+                    cols['p'] = traj[j, :, 0]
+                    cols['q'] = traj[j, :, 1]
+                write_columns(t_idx, t, cols, sync=(j == k - 1))
+                t_idx += 1
+            done += c
+            if not allow_fail:
+                bad = (fs >= 0).any()
+                if comm is not None:
+                    bad = comm.any(bad)
+                if bad:
+                    kk = int(np.argmax(fs >= 0)) if (fs >= 0).any() else -1
+                    raise ConvergenceError('Nonlinear solve failed to converge for seed %s at step %s'
+                                           % (seeds[kk] if kk >= 0 else '(other rank)', fs[kk] if kk >= 0 else '?'))
         while done < nsteps:
             c = min(chunk, nsteps - done)
             dW_dev = None

@@ -27,6 +27,15 @@ with open(os.path.join(root, 'profiles', '%s_ncu_full_%s.csv' % (tag, label)), '
         if h in keep or (h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio')):
             f.write('%s,%s,%s\n' % (h, u, v.replace(',', ';')))
             print(h, v)
+# dram traffic per launch of the headline kernel -> profiles/traffic.json (bench.py's roofline.traffic reads it)
+if label == 'pk_step_kernel':
+    import json
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    col = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+    tot = sum(float(col[k][1].replace(',', '')) * scale[col[k][0]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+    json.dump({'pk_step_kernel': {'dram_bytes_per_launch': tot, 'source': 'profiles/%s_ncu_full_%s.csv' % (tag, label),
+                                  'kernel': col['Kernel Name'][1]}},
+              open(os.path.join(root, 'profiles', 'traffic.json'), 'w'), indent=1)
 lf = os.path.join(go, 'launches_%s.csv' % tag)
 if os.path.exists(lf):
     rows = [r for r in csv.reader(open(lf)) if len(r) > 5]

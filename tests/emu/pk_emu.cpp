@@ -105,6 +105,26 @@ struct EmuExecT {
     for (int s = 0; s < n; ++s)
       for (int k = 0; k < 32; ++k) { const int t = order == 0 ? k : 31 - k; f(th[t], s); }
   }
+  template <class F> void argmax4(F f, double* outv, int* outi, double*) {
+    for (int c = 0; c < 4; ++c) { outv[c] = -INFINITY; outi[c] = 0x7fffffff; }
+    for (int k = 0; k < T; ++k) {
+      const int t = order == 0 ? k : T - 1 - k; cur = t / Tc;
+      double v[4]; int ix[4];
+      for (int c = 0; c < 4; ++c) { v[c] = -INFINITY; ix[c] = 0x7fffffff; }
+      f(th[t], v, ix);
+      for (int c = 0; c < 4; ++c) if (v[c] > outv[c] || (v[c] == outv[c] && ix[c] < outi[c])) { outv[c] = v[c]; outi[c] = ix[c]; }
+    }
+  }
+  template <class F> void minint2(F f, int* out, double*) {
+    out[0] = out[1] = 0x7fffffff;
+    for (int k = 0; k < T; ++k) {
+      const int t = order == 0 ? k : T - 1 - k; cur = t / Tc;
+      int kk[2] = {0x7fffffff, 0x7fffffff};
+      f(th[t], kk);
+      if (kk[0] < out[0]) out[0] = kk[0];
+      if (kk[1] < out[1]) out[1] = kk[1];
+    }
+  }
   template <class F> void allreduce3(F f, double* out) {
     out[0] = out[1] = out[2] = 0.0;
     for (int t = 0; t < T; ++t) { double v[3]; f(th[t], v); out[0] += v[0]; out[1] += v[1]; out[2] += v[2]; }
@@ -236,6 +256,13 @@ extern "C" int pk_emu_set_hybrid(int on) { g_emu_hybrid = on; return 0; }
 extern "C" int pk_emu_set_certificate(int on) { g_emu_cert = on; return 0; }
 extern "C" int pk_emu_set_partitioned(int on) { g_emu_part = on; return 0; }
 
+// fused dumps (StepIO::diag_every etc.) for the next pk_emu_step calls; every = 0 switches them off
+static int g_dump_every = 0; static double* g_dump_out = nullptr; static int* g_dump_idx = nullptr;
+static double* g_dump_sv = nullptr; static int* g_dump_si = nullptr;
+extern "C" int pk_emu_set_dump(int every, double* out, int* idx, double* suite_vals, int* suite_ids) {
+  g_dump_every = every; g_dump_out = out; g_dump_idx = idx; g_dump_sv = suite_vals; g_dump_si = suite_ids; return 0;
+}
+
 // advance in step blocks of nblk steps (0 = whole launch at once), see run_one
 extern "C" int pk_emu_set_block(int nblk) { g_emu_nblk = nblk; return 0; }
 
@@ -272,6 +299,7 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
     io.R = R; io.r = r; io.rid = rid0 + r; io.seed = seed; io.step0 = step0; io.nsteps = nsteps;
     io.n0 = 0; io.n1 = nsteps;
     io.fail_step = fail_step; io.its_last = its_last; io.its_total = its_total; io.fail_reason = fail_reason;
+    io.diag_every = g_dump_every; io.diag_out = g_dump_out; io.diag_idx = g_dump_idx; io.suite_vals = g_dump_sv; io.suite_ids = g_dump_si;
     switch (p.M) {
       case 4: run_mode<4>(p, io, u, u1, dF, dG, order); break;
       case 5: run_mode<5>(p, io, u, u1, dF, dG, order); break;

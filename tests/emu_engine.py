@@ -71,14 +71,27 @@ class EmuEngine(object):
         self.stepc += nsteps
         return None if dWo is None else torch.from_numpy(dWo)
 
+    def step_dump(self, nsteps, dump_every, dW=None, export_dW=False, suite=False):
+        nd = nsteps // dump_every
+        dg = np.zeros((nd, self.R, L.NDIAG)); di = np.zeros((nd, self.R, L.NIDX), np.int32)
+        sv = np.zeros((nd, self.R, 2)) if suite else None
+        si = np.zeros((nd, self.R, 3), np.int32) if suite else None
+        lib().pk_emu_set_dump(int(dump_every), _p(dg), _p(di, ctypes.c_int), _p(sv), _p(si, ctypes.c_int))
+        try:
+            out = self.step(nsteps, dW=dW, export_dW=export_dW)
+        finally:
+            lib().pk_emu_set_dump(0, None, None, None, None)
+        t = torch.from_numpy
+        return out, t(dg), t(di), (t(sv) if suite else None), (t(si) if suite else None)
+
     # ---- NumPy restatements of the device diagnostics (column layout of include/peakon_b200.h) ----
     def _failed(self, fail_step):
         fs = self.fail_step if isinstance(fail_step, str) else fail_step
         return np.zeros(self.R, bool) if fs is None else (fs.numpy() >= 0)
 
-    def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False, fail_step='own'):
+    def diagnostics(self, pq=None, periodic=False, want_m=False, want_du=False, fail_step='own', u=None):
         failed = self._failed(fail_step)
-        u = self.u.numpy()
+        u = (self.u if u is None else u).numpy()
         h, a2 = self.Ld / self.ne, self.alphasq
         M, K = self.orc.M, self.orc.K
         d = np.full((self.R, L.NDIAG), np.nan); ix = np.full((self.R, L.NIDX), -1, np.int32)
@@ -143,8 +156,8 @@ class EmuEngine(object):
             outv[r] = [w.max(), xmax, w.min(), xmin]; ids[r] = [np.argmax(w), np.argmin(w)]; fld[r] = w
         return torch.from_numpy(outv), torch.from_numpy(ids), (torch.from_numpy(fld) if want_field else None)
 
-    def ensemble_stats_into(self, stats, vals, idx, stream=None):
-        u = self.u.numpy(); ok = self.fail_step.numpy() < 0
+    def ensemble_stats_into(self, stats, vals, idx, stream=None, u=None, fail_step=None):
+        u = (self.u if u is None else u).numpy(); ok = (self.fail_step if fail_step is None else fail_step).numpy() < 0
         ne, nb = self.ne, stats.nbins
         v, ix = vals.numpy(), idx.numpy()
         pk = np.zeros(stats.n_packed)

@@ -65,6 +65,43 @@ def test_experiment_ensemble_axis_records_and_statistics(tmp_path, monkeypatch, 
     assert (d['ens_hist_min_du'].sum(axis=1) == 5).all()
 
 
+def test_fused_dump_path_equals_separate_kernels(tmp_path, monkeypatch, built):
+    """Diagnostics that are columns of the in-kernel dump take the pk_step_dump path (several dumps per launch, no
+    second kernel); with u_field in the list the separate-kernel path runs.  Same file either way (scalars to rounding
+    of the sums, extrema / locations / peakon suite / p, q bit for bit)."""
+    from emu_engine import EmuEngine
+    from peakondrake_b200 import experiment, outputting as out
+    monkeypatch.chdir(tmp_path)
+    diags = ['energy', 'l2_u', 'h1_u', 'mass_u', 'max_du', 'min_du', 'max_jump_local', 'max_jump_global', 'max_du_loc',
+             'min_du_loc', 'p_pde', 'q_pde', 'E_0', 'E_1', 'E_3', 'peakon_suite']
+    calls = []
+    orig = EmuEngine.step_dump
+
+    def spy(self, *a, **k):
+        calls.append(a[:2])
+        return orig(self, *a, **k)
+    monkeypatch.setattr(EmuEngine, 'step_dump', spy)
+    kw = dict(seeds=[5, 6, 7], ndump=2, allow_fail=True, peakon_equations=True, engine_cls=EmuEngine, **KW)
+    experiment('fused', 40., 0.009, diagnostics=diags, **kw)                 # 9 steps: 4 dumps fused + 1 trailing step
+    experiment('plain', 40., 0.009, diagnostics=diags + ['u_field'], **kw)
+    assert calls == [(8, 2)]
+    a, b = out.read_data_file('results/fused/data.nc'), out.read_data_file('results/plain/data.nc')
+    assert a['time'].shape == (5,) and np.array_equal(a['time'], b['time'])
+    for k in a:
+        if k in ('wallclock_time',):
+            continue
+        if k in ('energy', 'l2_u', 'h1_u', 'mass_u', 'E_0', 'E_1', 'E_3'):
+            assert np.allclose(a[k], b[k], rtol=1e-12, atol=0), k
+        else:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+    # a failure inside a fused chunk: NaN rows from the failing dump on, failed_time recorded
+    blow = lambda t: float('nan') if t > 0.0045 else 0.01
+    experiment('fail', 40., 0.008, diagnostics=['energy', 'min_du'], seeds=[1, 2], ndump=2, allow_fail=True, smooth_t=blow,
+               engine_cls=EmuEngine, **KW)
+    f = out.read_data_file('results/fail/data.nc')
+    assert np.isfinite(f['energy'][:3]).all() and np.isnan(f['energy'][3:]).all() and np.allclose(f['failed_time'], 0.005)
+
+
 def test_seed_axis_is_not_capped(tmp_path, monkeypatch, built):
     """experiment.py:164-166 refuses more than 1000 simulation() calls; the seeds of one combination are ONE batched
     launch here, so 1024 (BASELINE config 2) and more are legal."""

@@ -346,3 +346,92 @@ def test_device_mu_routine_equals_host_restatement_on_random_fields():
         k = min(4, len(old))
         assert np.array_equal(old4[:k], np.array(old[:k])) and np.array_equal(alt4[:k], np.array(alt[:k])), trial
         assert np.isnan(old4[k:]).all() and np.isnan(alt4[k:]).all()
+
+
+def _numpy_dump(u, h, alphasq=1.0):
+    """pk_diag_kernel's per-node expressions in NumPy (columns PK_D_ENERGY..PK_D_MAX_U and the four indices)."""
+    up = np.roll(u, -1); um = np.roll(u, 1)
+    du = (up - u) / h; dum = (u - um) / h; jmp = np.abs(du - dum)
+    sM = np.sum(h * (1.0 / 3.0) * (u * u + u * up + up * up)); sK = np.sum((up - u) * (up - u) * (1.0 / h)); sU = np.sum(h * u)
+    vals = [sM + alphasq * sK, sM, sK, sU, du.max(), du.min(), jmp.max(), u.max()]
+    return np.array(vals), np.array([np.argmax(du), np.argmin(du), np.argmax(u), np.argmax(jmp)])
+
+
+@pytest.mark.parametrize('ne,C,T,M', [(250, 1, 0, 0), (1000, 1, 0, 0), (37, 1, 0, 0), (1000, 4, 0, 0), (2000, 8, 0, 0), (2500, 8, 256, 10), (200, 2, 0, 0)])
+def test_fused_dump_diagnostics_emulated(ne, C, T, M):
+    """pk_step_dump: the dump diagnostics evaluated INSIDE the step kernel on the shared-memory state (diag_dump in
+    pk_core.h) every `every` steps equal the separate kernels' expressions on the state of that step: extrema, indices
+    and the peakon-suite scans bit for bit, sums to rounding; both thread orders agree bit-wise; cluster layouts too."""
+    import ctypes
+    from emu_util import _p
+    L = lib()
+    Ld, dt, nsteps, every, nxi, R = 40.0, 1e-3, 6, 2, 2, 2
+    mesh = O.Mesh1D(ne, Ld); h = mesh.h
+    u0 = O.initial_u(mesh, 'proper_peak')
+    tabs = [np.ascontiguousarray(t) for t in O.noise_tables(mesh, 'sines', nxi, 0.3)]
+    dW = np.ascontiguousarray(np.stack([O.reference_dW(s, nsteps, nxi, dt) for s in range(R)], axis=1))
+    nd = nsteps // every
+    outs = []
+    try:
+        assert L.pk_emu_set_cluster(C) == 0
+        for order in (0, 1):
+            dg = np.zeros((nd, R, 14)); di = np.zeros((nd, R, 4), np.int32); sv = np.zeros((nd, R, 2)); si = np.zeros((nd, R, 3), np.int32)
+            L.pk_emu_set_dump(every, _p(dg), _p(di, ctypes.c_int), _p(sv), _p(si, ctypes.c_int))
+            u = np.tile(u0, (R, 1)); z = [np.zeros_like(u) for _ in range(3)]
+            emu_step(ne, Ld, dt, 2, u, z[0], z[1], z[2], tabs, dW, nsteps, order=order, T=T, M=M)
+            outs.append((dg, di, sv, si, u))
+        L.pk_emu_set_dump(0, None, None, None, None)
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b, equal_nan=True)
+        dg, di, sv, si, _ = outs[0]
+        # the state at the dump steps, from plain launches
+        u = np.tile(u0, (R, 1)); z = [np.zeros_like(u) for _ in range(3)]
+        from test_host_logic import _device_scan_restated
+        for d in range(nd):
+            for n in range(every):      # one step per call keeps the Brownian path aligned with the single launch above
+                emu_step(ne, Ld, dt, 2, u, z[0], z[1], z[2], tabs, np.ascontiguousarray(dW[d * every + n:d * every + n + 1]), 1,
+                         T=T, M=M, step0=d * every + n)
+            for r in range(R):
+                v, ix = _numpy_dump(u[r], h)
+                assert np.array_equal(di[d, r], ix)
+                assert np.array_equal(dg[d, r, 4:8], v[4:8])                        # extrema: bit-identical
+                assert np.allclose(dg[d, r, :4], v[:4], rtol=1e-13, atol=0) and np.isnan(dg[d, r, 8:]).all()
+                pv, pi = _device_scan_restated(u[r], ne, h)
+                assert np.array_equal(sv[d, r], pv, equal_nan=True) and np.array_equal(si[d, r], pi)
+        assert np.array_equal(u, outs[0][4])
+        assert L.pk_emu_set_cluster(1) == 0              # no non-local stores happened
+    finally:
+        L.pk_emu_set_dump(0, None, None, None, None)
+        L.pk_emu_set_cluster(1)
+
+
+def test_fused_dump_of_failed_realisation_and_golden_suite():
+    """A failed realisation dumps NaN rows / -1 indices (outputting.py:107-108); on the reference helper's golden
+    fields the fused peakon-suite scan returns the indices the reference's own peakon_diagnostics resolves."""
+    import ctypes, os
+    from emu_util import _p
+    from peakondrake_b200 import outputting as out
+    L = lib()
+    GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_helpers.npz'))
+    try:
+        for name in [str(n) for n in GOLD['names']]:
+            u0 = GOLD[name + '/u']; ne = len(u0); Ld = 40.0
+            # a zero-length time step leaves the field as it is (dt -> 0: u1 = u is the Newton solution)
+            dg = np.zeros((1, 1, 14)); di = np.zeros((1, 1, 4), np.int32); sv = np.zeros((1, 1, 2)); si = np.zeros((1, 1, 3), np.int32)
+            L.pk_emu_set_dump(1, _p(dg), _p(di, ctypes.c_int), _p(sv), _p(si, ctypes.c_int))
+            u = u0[None].copy(); u1 = u.copy(); dF = np.zeros_like(u); dG = np.zeros_like(u)
+            emu_step(ne, Ld, 0.0, 0, u, u1, dF, dG, None, None, 1, nxi=0)
+            assert np.array_equal(u[0], u0)
+            x = (np.arange(ne) + 0.5) * (Ld / ne)
+            pk = out.peakon_suite_from_indices(x, dg[0, 0, 7], sv[0, 0], si[0, 0])
+            got = np.array([pk[k] for k in out.PEAKON_DIAGNOSTICS])
+            assert np.array_equal(got, GOLD[name + '/peakon'], equal_nan=True), name
+        # failure: NaN increments make SNES fail at the first step
+        ne = 64; u0 = O.initial_u(O.Mesh1D(ne, 40.0), 'proper_peak')
+        dg = np.zeros((2, 1, 14)); di = np.zeros((2, 1, 4), np.int32); sv = np.zeros((2, 1, 2)); si = np.zeros((2, 1, 3), np.int32)
+        L.pk_emu_set_dump(1, _p(dg), _p(di, ctypes.c_int), _p(sv), _p(si, ctypes.c_int))
+        u = u0[None].copy(); z = [np.zeros_like(u) for _ in range(3)]
+        r = emu_step(ne, 40.0, 1e-3, 0, u, z[0], z[1], z[2], None, np.full((2, 1, 1), np.nan), 2, xi_const=0.2, nxi=1)
+        assert r['fail_step'][0] == 0 and np.isnan(dg).all() and (di == -1).all() and np.isnan(sv).all() and (si == -1).all()
+    finally:
+        L.pk_emu_set_dump(0, None, None, None, None)
