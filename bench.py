@@ -243,7 +243,7 @@ def extra_configs(rank, world, local, peak):
     out = {}
 
     def leg(name, ne, R, dt, ic, fam, nxi, sigma, launches, steps_per_launch, scheme='hydrodynamic', peak_width=1.0,
-            nupd=1, per_launch=None, b_alg=None, note=''):
+            nupd=1, per_launch=None, b_alg=None, note='', dump_every=0):
         eng = EnsembleIntegrator(ne, LD, dt, R, scheme=scheme, timestepping='ssprk3' if scheme == 'upwind' else 'midpoint',
                                  num_Xis=nxi, Xi_family=fam, sigma=sigma, nXi_updates=nupd, seed=2026,
                                  rid_offset=rank * R, device=local)
@@ -251,7 +251,13 @@ def extra_configs(rank, world, local, peak):
         ctx = dict(eng=eng, comm=comm)
         if per_launch is not None:
             per_launch(ctx, True)
-        eng.step(steps_per_launch)                      # warm-up launch
+        def advance():
+            if dump_every:      # dump diagnostics + peakon suite fused into the step kernel, D2H of the tables per launch
+                _, dg, di, sv, si = eng.step_dump(steps_per_launch, dump_every, suite=True)
+                ctx['host'] = [t.to('cpu', non_blocking=True) for t in (dg, di, sv, si)]
+            else:
+                eng.step(steps_per_launch)
+        advance()                                       # warm-up launch
         if per_launch is not None:
             per_launch(ctx, False)
         torch.cuda.synchronize()
@@ -262,7 +268,7 @@ def extra_configs(rank, world, local, peak):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(launches):
-            eng.step(steps_per_launch)
+            advance()
             if per_launch is not None:
                 per_launch(ctx, False)
         e1.record()
@@ -296,15 +302,11 @@ def extra_configs(rank, world, local, peak):
              'scalar moments/extrema and the q_pde / min_du histograms all-reduced every 100 steps')
 
     # C4: 4096 realisations, ne=16384, steep front, diagnostics every step
-    def c4_diag(ctx, first):
-        if first:
-            return
-        ctx['eng'].diagnostics()
-        ctx['eng'].peakon_suite()
-    leg('C4', 16384, 4096, 5e-4, 'new_peak', 'constant', 1, 0.2, 30, 1, peak_width=1 / 6, per_launch=c4_diag,
+    leg('C4', 16384, 4096, 5e-4, 'new_peak', 'constant', 1, 0.2, 3, 10, peak_width=1 / 6, dump_every=1,
         b_alg=16 * 16384 + 8 + 8 * 18,
         note='4096 realisations, ne=16384, new_peak width 1/6, constant Xi sigma=0.2, dt=5e-4, min_du / max_du / '
-             'max_jump_local / peakon_suite every step')
+             'max_jump_local / peakon_suite EVERY step, fused into the step kernel (pk_step_dump: one launch per 10 steps, '
+             'the [10, R, 14+4+2+3] tables copied to the host per launch)')
     # C5: strong-convergence sweep shard, ne=20000, sigma=1 (the dt=1e-3 member, nXi_updates=1000)
     leg('C5', 20000, 8192, 1e-3, 'periodic_peakon', 'constant', 1, 1.0, 2, 20, nupd=1000,
         note='8192 realisations, ne=20000, periodic_peakon, constant Xi sigma=1, dt=1e-3 with nXi_updates=1000 (the '

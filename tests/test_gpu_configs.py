@@ -278,12 +278,15 @@ def test_c5_configuration_strong_dt_sweep(tmp_path, monkeypatch, nocert):
             assert sh['q_pde'][1, k] == mesh.x_cells[np.argmax(ref['u'])]
     errs = np.array(errs)                       # [dt, seed]
     rms = np.sqrt((errs ** 2).mean(axis=1))
-    # strong convergence (plotting/peakon_strong_dt_plotter.py:37-39 fits log error against log dt): for constant Xi the
-    # SPDE solution is the deterministic one shifted by sigma W(t), which the implicit midpoint rule follows with strong
-    # order 1 until the spatial error of the ne=20000 mesh takes over
-    slope = np.polyfit(np.log(DTS_C5[:4]), np.log(rms[:4]), 1)[0]
-    print('C5 rms u_error_with_sde per dt:', dict(zip(DTS_C5, rms)), 'fitted order (dt >= 1e-3): %.3f' % slope)
-    assert (np.diff(rms[:4]) < 0).all() and 0.7 <= slope <= 1.3
+    # Strong convergence, fitted like plotting/peakon_strong_dt_plotter.py:37-39 (log error against log dt).  Expected
+    # order 1/2: for constant Xi the SPDE solution is the deterministic peakon shifted by sigma W(t), and the coarse
+    # increments are sums of the fine ones, so the only error is the midpoint rule's phase error of pure transport,
+    # theta^3/12 per step and Fourier mode (theta = k * displacement).  Summed over the steps it is k^3 S / 12 with
+    # S = sum_n d_n^3 / 1 = O(dt) (3 c sigma^2 T dt in the mean); a peakon's spectrum decays like k^-2 (the kink), so
+    # ||error||_L2^2 ~ int min(k^6 S^2, 4) k^-4 dk ~ S, i.e. ||error|| ~ dt^(1/2).
+    slope = np.polyfit(np.log(DTS_C5), np.log(rms), 1)[0]
+    print('C5 rms u_error_with_sde per dt:', dict(zip(DTS_C5, rms)), 'fitted strong order: %.3f' % slope)
+    assert (np.diff(rms) < 0).all() and 0.35 <= slope <= 0.65
 
 
 @pytest.mark.parametrize('ne,fam,nxi,force', [(1000, 'sines', 4, 0), (200, 'sines', 2, 0), (20, 'sines', 1, 0), (2000, 'sines', 4, 0),
@@ -304,6 +307,7 @@ def test_fused_dump_equals_separate_kernels(ne, fam, nxi, force, monkeypatch):
     u0 = build_initial_u(ne, 40.0, ic, peak_width=1 / 6)
     a.set_state(u0); b.set_state(u0)
     a.fail_step[3] = 0; b.fail_step[3] = 0            # a failed realisation dumps NaN rows
+    na = a.launch_count
     _, dg, di, sv, si = a.step_dump(every * nd, every, suite=True)
     torch.cuda.synchronize()
     dg, di, sv, si = [t.cpu().numpy() for t in (dg, di, sv, si)]
@@ -319,5 +323,5 @@ def test_fused_dump_equals_separate_kernels(ne, fam, nxi, force, monkeypatch):
         ok = np.arange(R) != 3
         assert np.allclose(dg[d][ok, :4], v[ok, :4], rtol=1e-12, atol=0) and np.isnan(dg[d][3]).all() and np.isnan(dg[d][:, 8:]).all()
     assert torch.equal(a.u, b.u) and torch.equal(a.its_total, b.its_total)
-    assert b.launch_count - n0 == 3 * nd and a.launch_count == 1          # one kernel for all dumps of the chunk
+    assert b.launch_count - n0 == 3 * nd and a.launch_count - na == 1     # one kernel for all dumps of the chunk
     a.close(); b.close()
