@@ -80,7 +80,9 @@ typedef struct pk_config {
   int32_t scheme;        /* 0: 'hydrodynamic' / 'no_gradient' with 'midpoint' (equations.py:63-130);
                             1: 'upwind' with 'ssprk3' (equations.py:28-61) -> pk_step_upwind;
                             2: 'test' with 'midpoint' (equations.py:132-145): one CG1 unknown, noise_mode SCALAR
-                               or X, stepped by pk_step (dF/dG are ignored), meshes up to ne = 4096 */
+                               or X, stepped by pk_step (dF/dG are ignored).
+                            Every scheme runs one realisation per CTA while the mesh fits (ne <= 4096) and per thread-block
+                            cluster beyond (ne <= 32768). */
 } pk_config;
 
 /* Replaces Equations.__init__ (equations.py:63-95) + PrognosticVariables (simulation.py:227-249)

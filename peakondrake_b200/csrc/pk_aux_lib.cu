@@ -57,11 +57,7 @@ __global__ void __launch_bounds__(128) pk_peakon_sde_kernel(const __grid_constan
     for (int k = 0; k < a.nxi; ++k) {
       double w;
       if (a.dW_in) w = a.dW_in[((long long)n * a.R + r) * a.nxi + k];
-      else {
-        w = 0.0;
-        for (int j = 0; j < a.nupd; ++j)
-          w += philox_normal(a.seed, a.rid0 + (unsigned)r, (unsigned)(a.step0 + n), (unsigned)k, (unsigned)j) * a.sdt;
-      }
+      else w = philox_increment(a.seed, a.rid0 + (unsigned)r, (unsigned)(a.step0 + n), (unsigned)k, a.nupd, a.sdt);
       const double xi = cg1_at(a.xi + (size_t)k * a.ne, a.ne, a.h, q);
       const double xi_x = cg1_at(a.xi_x + (size_t)k * a.ne, a.ne, a.h, q);
       const double xi_xx = cg1_at(a.xi_xx + (size_t)k * a.ne, a.ne, a.h, q);

@@ -1302,6 +1302,33 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 // its value in a register (`hold`), so the generator runs once per window on all threads instead of
 // once per step on nxi threads.  Every block of a cluster draws the same numbers; the leader exports.
 // ------------------------------------------------------------------------------------------------
+// One Brownian increment of the Philox path: the sum of the nupd sub-update draws (stochastic_functions.py:213-217), each
+// scaled by sqrt(dt/nupd) before it is added.  Summation order (part of the definition: every code path -- step kernels,
+// peakon-SDE kernel, emulation -- produces the same bits):
+//   nupd <  PK_COOP_NUPD : j = 0, 1, ..., nupd-1 in sequence;
+//   nupd >= PK_COOP_NUPD : 32 interleaved partial sums (lane l adds j = l, l+32, ... in sequence), combined by the xor
+//                          butterfly 16, 8, 4, 2, 1 -- the order a warp produces when its 32 lanes share the draws.
+enum { PK_COOP_NUPD = 64 };
+PK_HD double philox_partial(unsigned long long seed, unsigned rid, unsigned step, unsigned k, int nupd, double sdt, int lane) {
+  double s = 0.0;
+  for (int j = lane; j < nupd; j += 32) s += philox_normal(seed, rid, step, k, (unsigned)j) * sdt;
+  return s;
+}
+PK_HD double philox_increment(unsigned long long seed, unsigned rid, unsigned step, unsigned k, int nupd, double sdt) {
+  if (nupd < PK_COOP_NUPD) {
+    double w = 0.0;
+    for (int j = 0; j < nupd; ++j) w += philox_normal(seed, rid, step, k, (unsigned)j) * sdt;
+    return w;
+  }
+  double pa[32], qa[32];
+  for (int l = 0; l < 32; ++l) pa[l] = philox_partial(seed, rid, step, k, nupd, sdt, l);
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < 32; ++l) qa[l] = pa[l] + pa[l ^ o];
+    for (int l = 0; l < 32; ++l) pa[l] = qa[l];
+  }
+  return pa[0];
+}
+
 struct DrawIO {
   const double* dW_in; double* dW_out;
   int R, r, step0, nsteps;
@@ -1311,10 +1338,12 @@ struct DrawIO {
   // windowed drawing (nxi <= threads): per = steps per window, w0 = first step of the current window.  Set by
   // draw_begin() once and advanced by draw_advance() every step (no integer division in the step loop).
   int per = 0, w0 = 0;
+  int coop = 0;           // many sub-updates: a WARP owns a step of the window and shares the draws of each increment
 };
 PK_HD void draw_begin(const Params& p, DrawIO& d, int nth) {
   if (p.nxi <= 0 || p.nxi > nth) return;
-  d.per = nth / p.nxi;
+  d.coop = (!d.dW_in && p.nupd >= PK_COOP_NUPD && p.nxi <= 32 && nth >= 32) ? 1 : 0;
+  d.per = d.coop ? (nth >> 5) : nth / p.nxi;
   d.w0 = d.n0 - (d.n0 % d.per);
 }
 PK_HD void draw_advance(DrawIO& d, int n) { if (d.per > 0 && n - d.w0 >= d.per) d.w0 += d.per; }
@@ -1326,10 +1355,7 @@ PK_HD DrawSlot draw_slot(const Params& p, int tid) {
 PK_HD double draw_one(const Params& p, const DrawIO& d, int n, int k) {
   const long long o = ((long long)n * d.R + d.r) * p.nxi + k;
   if (d.dW_in) return d.dW_in[o];
-  double w = 0.0;
-  for (int j = 0; j < p.nupd; ++j)
-    w += philox_normal(d.seed, d.rid, (unsigned)(d.step0 + n), (unsigned)k, (unsigned)j) * p.sdt;
-  return w;
+  return philox_increment(d.seed, d.rid, (unsigned)(d.step0 + n), (unsigned)k, p.nupd, p.sdt);
 }
 template <class SH>
 PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int tid, int nth, bool leader, double& hold, const DrawSlot& slot) {
@@ -1343,6 +1369,28 @@ PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int 
     return;
   }
   const int per = d.per, w0 = d.w0;        // steps per window, first step of the current window
+  if (d.coop) {
+    // warp w of the block owns step w0 + w of the window; its lanes share the nupd draws of every increment and lane k
+    // keeps the increment of mode k (philox_increment's summation order)
+    const int w = tid >> 5, lane = tid & 31;
+    if ((n == w0 || n == d.n0) && w0 + w < d.nsteps) {
+      for (int k = 0; k < p.nxi; ++k) {
+#if defined(__CUDA_ARCH__)
+        double s = philox_partial(d.seed, d.rid, (unsigned)(d.step0 + w0 + w), (unsigned)k, p.nupd, p.sdt, lane);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == k) hold = s;
+#else
+        if (lane == k) hold = philox_increment(d.seed, d.rid, (unsigned)(d.step0 + w0 + w), (unsigned)k, p.nupd, p.sdt);
+#endif
+      }
+    }
+    if (w == n - w0 && lane < p.nxi) {
+      sh.set_dw(lane, hold);
+      if (leader && d.dW_out) d.dW_out[((long long)n * d.R + d.r) * p.nxi + lane] = hold;
+    }
+    return;
+  }
   const int mine = slot.mine, k = slot.k;
   if ((n == w0 || n == d.n0) && mine < per && w0 + mine < d.nsteps) hold = draw_one(p, d, w0 + mine, k);
   if (mine == n - w0 && mine < per) {

@@ -339,15 +339,15 @@ struct SharedCluster {
   __device__ __forceinline__ void set_dw(int k, double v) const { dW[k] = v; }
 };
 
-template <int M, int MODE>
-struct GpuExecCluster {
-  typedef Thread<M, MODE, 0> Th;
+template <class ThT>
+struct GpuExecClusterT {
+  typedef ThT Th;
   Th& th;
   double* red;          // [2][3*nw + 3]: warp partials + this CTA's aggregate, ping-pong
   int flip, g0, g1;
   unsigned rank, C;
   double rA, rc0, rc1;
-  __device__ __forceinline__ GpuExecCluster(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
+  __device__ __forceinline__ GpuExecClusterT(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
   template <class F> __device__ __forceinline__ void each(F f) { f(th); }
   template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, (int)blockDim.x, rank == 0, g0, g1); }
   // Cluster barrier.  cg's sync() arrives with release semantics, which ptxas turns into MEMBAR.ALL.GPU + ERRBAR in front
@@ -374,6 +374,14 @@ struct GpuExecCluster {
   __device__ __forceinline__ void tick(int) {}
 #endif
   template <class F> __device__ __forceinline__ void one(F f) { if (rank == 0 && threadIdx.x == 0) f(); }
+  // a per-CTA flag in shared memory, raised by any thread: true if any CTA of the cluster has raised its own
+  // (call after a cluster barrier that follows the writes)
+  __device__ __forceinline__ bool any_flag(int* flag) const {
+    cg::cluster_group cl = cg::this_cluster();
+    int v = 0;
+    for (unsigned b = 0; b < C; ++b) v |= *cl.map_shared_rank(flag, b);
+    return v != 0;
+  }
   __device__ __forceinline__ bool hybrid(int) const { return false; }     // rows are spread over the CTAs of the cluster
   __device__ __forceinline__ bool pingpong() const { return true; }       // XB_SLOTS_PP exchange slots: one cluster barrier per PCR step
   // Schur solve partitioned by CTA (pk_core.h, pcr_step_local): the PCR steps inside a CTA need block barriers and
@@ -559,6 +567,8 @@ struct GpuExecCluster {
     fin(th, in0, in1);
   }
 };
+
+template <int M, int MODE> using GpuExecCluster = GpuExecClusterT<Thread<M, MODE, 0> >;
 
 template <int M, int MODE, int TB, int MINB = 1>
 __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a, int lgTc) {

@@ -8,19 +8,22 @@
 
 
 template <int M> static ckern_t pick_cmode(int mode, int Tc, int minb) {
-  if (PK_IS_TEST(mode)) return nullptr;      // scheme 'test': single-CTA meshes only
   if (Tc <= 256) {
     // two clusters share the SMs when two CTAs fit one SM's shared memory (128 registers per thread)
     if constexpr (M <= 8) { if (minb == 2 && mode == NOISE_SCALAR) return pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2>; }
     switch (mode) {
       case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 256>;
       case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 256>;
+      case TEST_SCALAR: return pk_step_cluster_kernel<M, TEST_SCALAR, 256>;
+      case TEST_X: return pk_step_cluster_kernel<M, TEST_X, 256>;
       default: return pk_step_cluster_kernel<M, NOISE_FULL, 256>;
     }
   }
   switch (mode) {
     case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 512>;
     case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 512>;
+    case TEST_SCALAR: return pk_step_cluster_kernel<M, TEST_SCALAR, 512>;
+    case TEST_X: return pk_step_cluster_kernel<M, TEST_X, 512>;
     default: return pk_step_cluster_kernel<M, NOISE_FULL, 512>;
   }
 }

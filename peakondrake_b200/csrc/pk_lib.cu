@@ -21,6 +21,7 @@ using namespace pk;
 #include "pk_args.h"
 #include "pk_dispatch.h"
 #include "pk_upwind.h"
+const void* pk_upwind_cluster_kernel_ptr(const pk::Params& p, int Tc);     // pk_upwind_lib.cu
 
 // ------------------------------------------------------------------------------------------------
 // diagnostics kernel: one CTA per realisation, natural order, coalesced
@@ -400,21 +401,18 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   if (cfg->scheme == 1) {
     // upwind/ssprk3: state in registers, only exchange slots in shared memory (pk_upwind_lib.cu)
     c->smem = sizeof(double) * ((size_t)UW_SLOTS * p.T + 6 * (c->block / 32) + (p.nxi > 0 ? p.nxi : 1) + 2);
-    if (c->block > 512) { const int ne = p.ne; delete c; return fail(nullptr, "pk_create: upwind scheme supports ne <= 4096 (ne=%d)", ne); }
   }
   int force = 0;
   { const char* e = getenv("PK_FORCE_CLUSTER"); force = e ? atoi(e) : 0; }   // testing: split small meshes too
-  if (cfg->scheme == 2 && (c->block > 512 || c->smem > 227 * 1024)) {
-    const int ne = p.ne; delete c;
-    return fail(nullptr, "pk_create: the 'test' scheme supports ne <= 4096 (ne=%d)", ne);
-  }
-  if (cfg->scheme == 0 && (force > 1 || c->block > 512 || c->smem > 227 * 1024)) {
+  if (force > 1 || c->block > 512 || c->smem > 227 * 1024) {
     // one realisation per thread-block cluster: C CTAs of Tc threads
     int Tc = 256, C = p.T / Tc;
     if (force > 1) { C = force; Tc = p.T / C; }
     while (C > 16 && Tc < 512) { Tc *= 2; C /= 2; }
     int lg = 0; while ((1 << lg) < Tc) ++lg;
-    const size_t sm = sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)XB_SLOTS_PP * Tc + 2 * (3 * (Tc / 32) + 3) + (p.nxi > 0 ? p.nxi : 1));
+    const size_t sm = cfg->scheme == 1
+        ? sizeof(double) * ((size_t)UW_SLOTS * Tc + 2 * (3 * (Tc / 32) + 3) + (p.nxi > 0 ? p.nxi : 1) + 2)
+        : sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)XB_SLOTS_PP * Tc + 2 * (3 * (Tc / 32) + 3) + (p.nxi > 0 ? p.nxi : 1));
     if (C < 2 || C > 16 || (C & (C - 1)) || Tc < 32 || C * Tc != p.T || sm > 227 * 1024) {
       const int ne = p.ne; delete c;
       return fail(nullptr, "pk_create: no cluster layout for ne=%d (threads %d)", ne, p.T);
@@ -442,10 +440,11 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   c->timed = false; c->nlaunch = 0; c->h_stage = nullptr;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
-  const void* k = c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block, c->cminb) : (const void*)pick_kernel(p, c->block, c->fs);
+  const void* k = cfg->scheme == 1 ? (c->cluster > 1 ? pk_upwind_cluster_kernel_ptr(p, c->block) : (const void*)&g_create_err /* own launch path */)
+                  : (c->cluster > 1 ? (const void*)pick_cluster_kernel(p, c->block, c->cminb) : (const void*)pick_kernel(p, c->block, c->fs));
   if (!k) { delete c; return fail(nullptr, "pk_create: no kernel for this layout"); }
   if (c->cluster > 8) cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  e = cfg->scheme == 1 ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
+  e = (cfg->scheme == 1 && c->cluster == 1) ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaFuncSetAttribute(smem=%zu): %s", c->smem, m.c_str()); }
   if (cfg->scheme != 1 && c->cluster == 1) {
     // persistent CTAs: as many as are resident at once

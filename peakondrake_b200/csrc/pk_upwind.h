@@ -220,9 +220,9 @@ PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const Upwin
     if (failed >= 0) continue;
     // the reference's linear solves raise on a non-finite residual: a non-finite increment fails the
     // step before the state is touched; a blow-up of the state is caught one step after it happened
-    bool bad = (*flag != 0);
+    bool bad = ex.any_flag(flag);
     { double sw = 0.0; for (int k = 0; k < p.nxi; ++k) sw += sh.dw(k); bad = bad || !uw_finite(sw); }   // any non-finite increment makes the sum non-finite
-    if (bad) { failed = (*flag != 0) ? io.step0 + n - 1 : io.step0 + n; continue; }
+    if (bad) { failed = ex.any_flag(flag) ? io.step0 + n - 1 : io.step0 + n; continue; }
     ex.each([&](Th& th) { th.begin_step(p, sh, io.xi); });
     ex.sync();
     ex.each([&](Th& th) { th.stage(p, sh, 1); });
@@ -236,7 +236,7 @@ PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const Upwin
     ex.scan_rev([&](Th& th, double in0, double) { if (!th.helm_finish(p, in0)) *flag = 1; });
   }
   ex.sync();
-  if (failed < 0 && *flag != 0) failed = io.step0 + io.nsteps - 1;
+  if (failed < 0 && ex.any_flag(flag)) failed = io.step0 + io.nsteps - 1;
   ex.each([&](Th& th) { th.store(p, io); });
   ex.one([&]() { io.fail_step[io.r] = failed; });
 }

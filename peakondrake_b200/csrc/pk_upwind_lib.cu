@@ -2,11 +2,9 @@
 // the diagnostics of its prognostic DG1 field m.  Thread-level phases: pk_upwind.h.
 #include <cuda_runtime.h>
 #include <cstdlib>
-#include "pk_core.h"
+#include "pk_kernels.cuh"      // SharedCluster, GpuExecClusterT (the thread-block-cluster executor of the midpoint kernels)
 #include "pk_upwind.h"
 #include "pk_ctx.h"
-
-using namespace pk;
 
 // the block executor of pk_lib.cu, restated for this translation unit (same collectives)
 template <class ThT, bool AA, int TBC = 0>
@@ -24,6 +22,7 @@ struct UwExec {
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void tick(int) {}
   template <class F> __device__ __forceinline__ void one(F f) { if (threadIdx.x == 0) f(); }
+  __device__ __forceinline__ bool any_flag(int* flag) const { return *flag != 0; }
   __device__ __forceinline__ double* area() {
     const int nw = nwarps();
     double* a = red + flip * 3 * nw;
@@ -119,7 +118,59 @@ __global__ void __launch_bounds__(TB, MINB) pk_upwind_kernel(const __grid_consta
   run_upwind_steps<M, XARR, TT, UwExec<Th, (TB > 32), TT>, Th>(ex, p, sh, io, flag);
 }
 
+// Thread-block-cluster variant (meshes beyond 512 threads: ne > 4096): one realisation per cluster of C CTAs.  The state
+// still lives in the registers of its threads; the chunk-edge exchange slots are distributed over the CTAs (foreign
+// slots read through DSMEM, all stores local) and the two Helmholtz scans get a cross-CTA level -- the executor and the
+// shared-memory decode of the midpoint cluster kernels.
+template <int M, int XARR, int TB>
+__global__ void __launch_bounds__(TB, 1) pk_upwind_cluster_kernel(const __grid_constant__ Params p, const __grid_constant__ UpwindArgs a, int lgTc) {
+  extern __shared__ __align__(16) double smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank(), C = cluster.num_blocks();
+  const int Tc = blockDim.x;
+  SharedCluster sh;
+  sh.Tc = Tc; sh.lgTc = lgTc; sh.rank = rank;
+  { int lg = 0; while ((1 << lg) < p.T) ++lg; sh.lgT = lg; }
+  sh.U0 = sh.U1 = sh.F = sh.G = sh.X = sh.Xx = sh.Xxx = nullptr;
+  sh.xb = smem;
+  double* red = smem + UW_SLOTS * Tc;
+  sh.dW = red + 2 * (3 * (Tc >> 5) + 3);
+  int* flag = (int*)(sh.dW + (p.nxi > 0 ? p.nxi : 1));
+  if (threadIdx.x == 0) *flag = 0;
+  typedef UpwindThread<M, XARR, 0> Th;
+  Th th;
+  th.init(p, (int)rank * Tc + (int)threadIdx.x);
+  GpuExecClusterT<Th> ex(th, red);
+  const int r = blockIdx.x / C;
+  ex.rank = rank; ex.C = C; ex.part = 0;
+  ex.g0 = chunk_start(p, (int)rank * Tc); ex.g1 = (rank == C - 1) ? p.ne : chunk_start(p, ((int)rank + 1) * Tc);
+  UpwindIO io;
+  io.m = a.m; io.u = a.u; io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi;
+  io.R = a.R; io.r = r; io.rid = a.rid0 + r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
+  io.fail_step = a.fail_step;
+  cluster.sync();
+  run_upwind_steps<M, XARR, 0, GpuExecClusterT<Th>, Th>(ex, p, sh, io, flag);
+  cluster.sync();     // nobody leaves while a peer may still read its shared memory
+}
+
 typedef void (*ukern_t)(const Params, const UpwindArgs);
+typedef void (*uckern_t)(const Params, const UpwindArgs, int);
+template <int M> static uckern_t pick_uck(bool x, int Tc) {
+  if (Tc <= 256) return x ? pk_upwind_cluster_kernel<M, 1, 256> : pk_upwind_cluster_kernel<M, 0, 256>;
+  return x ? pk_upwind_cluster_kernel<M, 1, 512> : pk_upwind_cluster_kernel<M, 0, 512>;
+}
+static uckern_t pick_ucluster_kernel(const Params& p, int Tc) {
+  const bool x = (p.mode != NOISE_SCALAR);
+  switch (p.M) {
+    case 5: return pick_uck<5>(x, Tc);
+    case 6: return pick_uck<6>(x, Tc);
+    case 7: return pick_uck<7>(x, Tc);
+    case 8: return pick_uck<8>(x, Tc);
+  }
+  return nullptr;
+}
+const void* pk_upwind_cluster_kernel_ptr(const Params& p, int Tc) { return (const void*)pick_ucluster_kernel(p, Tc); }
+
 template <int M, int XARR> static ukern_t pick_utb(int block, int T) {
   if (T < 32) return pk_upwind_kernel<M, XARR, 32, 1, 0>;
   if (T == 128) return pk_upwind_kernel<M, XARR, 128, 4, 128>;
@@ -151,9 +202,20 @@ extern "C" int pk_step_upwind(pk_ctx* c, int32_t nsteps, double* m, double* u, c
   a.m = m; a.u = u; a.xi = c->xi; a.dW_in = dW_in; a.dW_out = dW_out; a.fail_step = fail_step;
   a.R = c->cfg.R; a.step0 = (int)c->step; a.nsteps = nsteps; a.rid0 = c->cfg.rid_offset; a.seed = c->cfg.seed;
   cudaStream_t st = (cudaStream_t)stream;
-  ukern_t k = pick_ukernel(c->p, c->block);
   CK(c, cudaEventRecord(c->ev0, st));
-  k<<<c->cfg.R, c->block, c->smem, st>>>(c->p, a);
+  if (c->cluster > 1) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(c->cfg.R * c->cluster)); lc.blockDim = dim3((unsigned)c->block);
+    lc.dynamicSmemBytes = c->smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CK(c, cudaLaunchKernelEx(&lc, pick_ucluster_kernel(c->p, c->block), c->p, a, c->lgTc));
+  } else {
+    ukern_t k = pick_ukernel(c->p, c->block);
+    k<<<c->cfg.R, c->block, c->smem, st>>>(c->p, a);
+  }
   ++c->nlaunch;
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(c->ev1, st));

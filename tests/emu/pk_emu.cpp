@@ -88,6 +88,7 @@ struct EmuExecT {
   void sync() {}
   void tick(int) {}
   template <class F> void one(F f) { f(); }
+  bool any_flag(int* flag) const { return *flag != 0; }
   bool hybrid(int Tn) const { return g_emu_hybrid && C == 1 && Tn >= 32; }
   bool pingpong() const { return C > 1; }      // like the cluster kernel: XB_SLOTS_PP slots
   bool partitioned() const { return C > 1 && g_emu_part; }
@@ -232,6 +233,8 @@ static void run_mode(const Params& p, StepIO io, double* u, double* u1, double* 
     switch (p.mode) {
       case NOISE_SCALAR: g_bad += run_one_cluster<M, NOISE_SCALAR>(p, io, u, u1, dF, dG, order, g_emuC); break;
       case NOISE_X: g_bad += run_one_cluster<M, NOISE_X>(p, io, u, u1, dF, dG, order, g_emuC); break;
+      case TEST_SCALAR: g_bad += run_one_cluster<M, TEST_SCALAR>(p, io, u, u1, dF, dG, order, g_emuC); break;
+      case TEST_X: g_bad += run_one_cluster<M, TEST_X>(p, io, u, u1, dF, dG, order, g_emuC); break;
       default: g_bad += run_one_cluster<M, NOISE_FULL>(p, io, u, u1, dF, dG, order, g_emuC); break;
     }
     return;
@@ -327,6 +330,26 @@ static void run_upwind_one(const Params& p, UpwindIO io, int order) {
   run_upwind_steps<M, XARR, 0, EmuExecT<Th>, Th>(ex, p, sh, io, &flag);
 }
 
+// thread-block-cluster emulation of the upwind kernel: exchange slots distributed over C CTAs (EmuSharedCluster decode)
+template <int M, int XARR>
+static int run_upwind_one_cluster(const Params& p, UpwindIO io, int order, int C) {
+  const int Tc = p.T / C;
+  std::vector<std::vector<double> > bufs(C, std::vector<double>(UW_SLOTS * Tc + (p.nxi > 0 ? p.nxi : 1), 0.0));
+  typedef UpwindThread<M, XARR, 0> Th;
+  EmuExecT<Th> ex(p, order, C);
+  int bad = 0;
+  EmuSharedCluster sh;
+  double* z = (double*)0;
+  sh.U0 = sh.U1 = sh.F = sh.G = sh.X = sh.Xx = sh.Xxx = z;
+  sh.xb = z; sh.dW = z + UW_SLOTS * Tc;
+  sh.bufs = &bufs; sh.Tc = Tc; sh.nxi_ = p.nxi; sh.cur = &ex.cur; sh.bad = &bad;
+  sh.lgTc = 0; while ((1 << sh.lgTc) < Tc) ++sh.lgTc;
+  sh.lgT = 0; while ((1 << sh.lgT) < p.T) ++sh.lgT;
+  int flag = 0;
+  run_upwind_steps<M, XARR, 0, EmuExecT<Th>, Th>(ex, p, sh, io, &flag);
+  return bad;
+}
+
 extern "C" int pk_emu_step_upwind(int ne, double Ld, double dt, double alphasq, int xarr, int nxi, int nupd,
                                   double xi_const, int R, int nsteps, int step0, double* m, double* u,
                                   const double* xi, const double* dW_in, double* dW_out,
@@ -343,7 +366,8 @@ extern "C" int pk_emu_step_upwind(int ne, double Ld, double dt, double alphasq, 
     UpwindIO io;
     io.m = m; io.u = u; io.dW_in = dW_in; io.dW_out = dW_out; io.xi = pt.empty() ? nullptr : pt.data(); io.R = R; io.r = r; io.rid = rid0 + r;
     io.seed = seed; io.step0 = step0; io.nsteps = nsteps; io.fail_step = fail_step;
-#define UW_CASE(MM) case MM: if (xarr) run_upwind_one<MM, 1>(p, io, order); else run_upwind_one<MM, 0>(p, io, order); break;
+#define UW_CASE(MM) case MM: if (g_emuC > 1) { g_bad += xarr ? run_upwind_one_cluster<MM, 1>(p, io, order, g_emuC) : run_upwind_one_cluster<MM, 0>(p, io, order, g_emuC); } \
+                             else if (xarr) run_upwind_one<MM, 1>(p, io, order); else run_upwind_one<MM, 0>(p, io, order); break;
     switch (p.M) { UW_CASE(5) UW_CASE(6) UW_CASE(7) UW_CASE(8) default: return -3; }
 #undef UW_CASE
   }

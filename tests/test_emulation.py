@@ -435,3 +435,86 @@ def test_fused_dump_of_failed_realisation_and_golden_suite():
         assert r['fail_step'][0] == 0 and np.isnan(dg).all() and (di == -1).all() and np.isnan(sv).all() and (si == -1).all()
     finally:
         L.pk_emu_set_dump(0, None, None, None, None)
+
+
+@pytest.mark.parametrize('ne,C,nxi,fam', [(1000, 4, 7, 'sines'), (2000, 8, 2, 'sines'), (250, 2, 1, 'constant'), (333, 2, 0, 'sines')])
+def test_upwind_cluster_kernel_emulated(ne, C, nxi, fam):
+    """upwind/ssprk3 on a thread-block cluster (meshes beyond 4096 cells on the device): exchange slots distributed
+    over C CTAs, every store local, scans with a cross-CTA level -- same numbers as the oracle, both thread orders
+    bit-identical, a blow-up flag raised in one CTA is seen by all."""
+    from emu_util import emu_step_upwind
+    L = lib()
+    Ld, dt, n = 40., 1e-3, 6
+    mesh = O.Mesh1D(ne, Ld); u0 = O.initial_u(mesh, 'one_peak')
+    xi = O.noise_tables(mesh, fam, nxi, 0.25, scheme='upwind')[0] if nxi else None
+    dW = O.reference_dW(0, n, nxi, dt) if nxi else None
+    ref = O.run_upwind(ne, Ld, dt, n, u0, dW, xi)
+    res = []
+    try:
+        assert L.pk_emu_set_cluster(C) == 0
+        for order in (0, 1):
+            m = ref['oracle'].initial_m(u0)[None].copy(); u = u0[None].copy()
+            xc = xi[0, 1] if fam == 'constant' else 0.0
+            emu_step_upwind(ne, Ld, dt, m, u, None if (fam == 'constant' or not nxi) else np.ascontiguousarray(xi),
+                            None if dW is None else np.ascontiguousarray(dW[:, None, :]), n, xi_const=xc, nxi=nxi, order=order)
+            assert rel(u[0], ref['u']) <= TOL and rel(m[0], ref['m']) <= TOL
+            res.append((u.copy(), m.copy()))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        if nxi:      # a non-finite increment fails the realisation in every CTA alike
+            m = ref['oracle'].initial_m(u0)[None].copy(); u = u0[None].copy()
+            bad = np.ascontiguousarray(dW[:, None, :]).copy(); bad[3] = np.inf
+            r = emu_step_upwind(ne, Ld, dt, m, u, None if fam == 'constant' else np.ascontiguousarray(xi), bad, n,
+                                xi_const=(xi[0, 1] if fam == 'constant' else 0.0), nxi=nxi)
+            assert r['fail_step'][0] == 3 and np.isfinite(u).all()
+        assert L.pk_emu_set_cluster(1) == 0          # no non-local stores happened
+    finally:
+        L.pk_emu_set_cluster(1)
+
+
+@pytest.mark.parametrize('ne,C', [(1000, 4), (2000, 8)])
+def test_test_scheme_on_a_cluster_emulated(ne, C):
+    """scheme 'test' (equations.py:132-145) through the cluster executor (meshes beyond 4096 cells on the device)."""
+    L = lib()
+    Ld, dt, n, nxi = 40.0, 1e-3, 4, 2
+    mesh = O.Mesh1D(ne, Ld)
+    u0 = O.initial_u(mesh, 'proper_peak')
+    tabs = O.noise_tables(mesh, 'sines', nxi, 0.2, scheme='test')
+    dW = O.reference_dW(1, n, nxi, dt)
+    ref = O.run(ne, Ld, dt, n, u0, dW, tabs, scheme='test')
+    try:
+        assert L.pk_emu_set_cluster(C) == 0
+        u = u0[None].copy(); z = [np.zeros_like(u) for _ in range(3)]
+        r = emu_step(ne, Ld, dt, 4, u, z[0], z[1], z[2], [np.ascontiguousarray(t) for t in tabs], np.ascontiguousarray(dW[:, None, :]), n)
+        assert r['its_total'][0] == ref['its'].sum() and rel(u[0], ref['u']) <= TOL
+        assert L.pk_emu_set_cluster(1) == 0
+    finally:
+        L.pk_emu_set_cluster(1)
+
+
+def test_philox_many_sub_updates_have_a_fixed_summation_order():
+    """nXi_updates >= 64 (the strong-convergence sweep uses int(dt/1e-6) = 100 ... 10000): the sub-draws of one increment
+    are shared by the 32 lanes of a warp on the device; the summation order (32 interleaved partial sums, xor butterfly) is
+    part of the definition, so the emulation, the peakon-SDE kernel and every block size give the same bits."""
+    L = lib()
+    ne, Ld, dt, nupd, nsteps, R, seed = 64, 40.0, 1e-2, 100, 5, 3, 1234
+    u0 = O.initial_u(O.Mesh1D(ne, Ld), 'periodic_peakon')
+    outs = []
+    for (T, M) in ((0, 0), (8, 8)):         # 32-thread and 8-thread layouts of the same mesh (the latter cannot share draws)
+        u = np.tile(u0, (R, 1)); z = [np.zeros_like(u) for _ in range(3)]
+        r = emu_step(ne, Ld, dt, 0, u, z[0], z[1], z[2], None, None, nsteps, xi_const=0.5, nupd=nupd, seed=seed, rid0=7,
+                     export=True, nxi=1, T=T, M=M + (1 if M else 0))
+        outs.append(r['dW'])
+    assert np.array_equal(outs[0], outs[1])
+    sdt = np.sqrt(dt / nupd)
+    for n in (0, 4):
+        for rr in range(R):
+            pa = [0.0] * 32
+            for l in range(32):
+                s = 0.0
+                for j in range(l, nupd, 32):
+                    s += L.pk_emu_philox_normal(seed, 7 + rr, n, 0, j) * sdt
+                pa[l] = s
+            for o in (16, 8, 4, 2, 1):
+                pa = [pa[l] + pa[l ^ o] for l in range(32)]
+            assert outs[0][n, rr, 0] == pa[0]
+    assert abs(np.std(outs[0]) / np.sqrt(dt) - 1.0) < 0.5

@@ -76,6 +76,29 @@ def test_device_sde_philox_stream_is_the_step_kernels_stream():
     eng.close()
 
 
+def test_philox_sub_updates_same_bits_on_every_layout():
+    """nXi_updates = 128: the draws of an increment are shared by a warp; the exported increments do not depend on the
+    mesh / block size / cluster layout, and the SDE kernel regenerates the same numbers."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u, pure_xi_tables
+    outs = []
+    for ne in (64, 1000, 16384):
+        eng = EnsembleIntegrator(ne, 40.0, 1e-3, 4, num_Xis=1, Xi_family='constant', sigma=0.3, nXi_updates=128, seed=5, rid_offset=3)
+        eng.set_state(build_initial_u(ne, 40.0, 'periodic_peakon'))
+        a = eng.step(3, export_dW=True); b = eng.step(4, export_dW=True)
+        torch.cuda.synchronize()
+        outs.append(torch.cat([a, b]).cpu().numpy())
+        if ne == 64:
+            tabs = [torch.from_numpy(np.ascontiguousarray(t)).to(eng.device) for t in pure_xi_tables(ne, 40.0, 'constant', 1, 0.3)]
+            mk = lambda v: torch.full((4,), v, dtype=torch.float64, device=eng.device)
+            pa, qa, pb, qb = mk(0.7), mk(11.3), mk(0.7), mk(11.3)
+            eng.peakon_sde_step(7, pa, qa, tabs, float(np.exp(-40.0)), 'ito_euler', dW=torch.cat([a, b]))
+            eng.peakon_sde_step(7, pb, qb, tabs, float(np.exp(-40.0)), 'ito_euler', dW=None, step0=0)
+            assert torch.equal(qa, qb)
+        eng.close()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]) and abs(outs[0].std() / np.sqrt(1e-3) - 1) < 0.4
+
+
 def test_du_smooth_and_ensemble_scalars():
     import torch
     from peakondrake_b200 import EnsembleIntegrator, EnsembleStatistics, build_initial_u, _lib

@@ -101,7 +101,8 @@ def test_no_gradient_scheme():
 
 
 @pytest.mark.parametrize('ne,fam,nxi,sigma', [(400, 'sines', 3, 0.2), (1000, 'sines', 4, 0.2), (300, 'constant', 1, 1.0),
-                                             (64, 'sines', 0, 0.0), (2000, 'sines', 2, 0.1)])
+                                             (64, 'sines', 0, 0.0), (2000, 'sines', 2, 0.1), (6000, 'sines', 2, 0.1),
+                                             (20000, 'constant', 1, 0.5)])       # the last two: cluster kernels
 def test_test_scheme(ne, fam, nxi, sigma):
     """Scheme 'test' / 'midpoint' (equations.py:132-145) against the oracle: same Newton counts, u within 1e-10."""
     import torch
@@ -395,8 +396,8 @@ def test_upwind_ssprk3_reference_test_parameters():
     run_upwind_case(20, 2, 10)
 
 
-@pytest.mark.parametrize('ne', [8, 37, 200, 1000, 2000, 4000])
-def test_upwind_mesh_sizes(ne):
+@pytest.mark.parametrize('ne', [8, 37, 200, 1000, 2000, 4000, 6000, 10000, 16384, 20000])
+def test_upwind_mesh_sizes(ne):     # beyond 4096 cells: one realisation per thread-block cluster (pk_upwind_cluster_kernel)
     # the explicit scheme is only stable for |us|/h well below 1: scale the noise with the mesh width,
     # otherwise rounding differences are amplified step by step and path-wise comparison is meaningless
     run_upwind_case(ne, 3, 8, nxi=3, sigma=0.25 * min(1.0, 200.0 / ne))
