@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpeakon_b200.so')
+LIB_PATH = os.environ.get('PK_LIB_PATH') or os.path.join(_HERE, 'libpeakon_b200.so')    # PK_LIB_PATH: A/B builds (profiles/)
 
 PK_NOISE_SCALAR, PK_NOISE_X, PK_NOISE_FULL = 0, 1, 2
 

@@ -32,6 +32,33 @@
 #endif
 
 namespace pk {
+// Reciprocal of a pivot / determinant.  FAST (the single-CTA kernels with a compile-time thread count): MUFU.RCP64H seed
+// (20 bits) + two Newton steps -- 1 ulp instead of correctly rounded, no range checks, no slow path: half the
+// instructions of __drcp_rn and one dependent FMA less on the critical chain of every elimination row and PCR step
+// (+3.5 % on the headline kernel, profiles/r2d_variants.log; the cluster kernels lose 3 % with it and keep __drcp_rn).
+// The arguments are O(1) (hm0 = h^2/2 + alphasq); NaN propagates, which is what the failure detection needs.
+template <bool FAST>
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+double rcp_t(double x) {
+#if defined(__CUDA_ARCH__)
+  if (FAST) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); return fma(r, e, r);
+  }
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+}  // namespace pk
+
+namespace pk {
 
 // Shared (per-realisation) storage. Field arrays are [M*T] doubles, interleaved: row j of chunk t
 // lives at j*T + t (conflict-free when all threads touch their row j).
@@ -192,9 +219,10 @@ struct CellC {
 // What node l contributes to pentadiagonal rows l-1 (Cp,Qp), l (C0,Q0) and l+1 (Cm,Qm).
 struct Packet { double Cm[3], C0[3], Cp[3], Qm, Q0, Qp; };
 
+template <bool FAST = false>
 PK_HD void inv2(const double* D, double* Di) {
   const double det = D[0] * D[3] - D[1] * D[2];
-  const double id = PK_RCP(det);
+  const double id = rcp_t<FAST>(det);
   Di[0] = D[3] * id; Di[1] = -D[1] * id; Di[2] = -D[2] * id; Di[3] = D[0] * id;
 }
 // C = A*B (2x2 row-major)
@@ -225,7 +253,8 @@ PK_HD void mva2(const double* A, const double* x, double* y) {
 // and only the elimination step of each interior row (static register indices) is selected by a switch.
 template <int M, int MODE, int TT = 0, int VAR = 0>
 struct Thread {
-  enum { NI = M - 2, FS = (VAR == 1) ? 1 : 0, ROLL = (VAR == 2) ? 1 : 0, ROLL_LITE = (VAR != 4) ? 1 : 0 };
+  enum { NI = M - 2, FS = (VAR == 1) ? 1 : 0, ROLL = (VAR == 2) ? 1 : 0, ROLL_LITE = (VAR != 4) ? 1 : 0,
+         FASTR = (TT > 0) ? 1 : 0 };      // fast reciprocal in the tuned single-CTA kernels (rcp_t)
   double h1[6], h2[6];            // FS: (r, e, f, zb, zw1, zw2) of the two previously eliminated interior rows
   static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
   // geometry
@@ -380,7 +409,7 @@ struct Thread {
       w1 = -l2 * zw1[k - 2] - l1 * zw1[k - 1];
       w2 = -l2 * zw2[k - 2] - l1 * zw2[k - 1];
     }
-    r[k] = PK_RCP(d); e[k] = ee; f[k] = ff; zb[k] = z; zw1[k] = w1; zw2[k] = w2;
+    r[k] = rcp_t<FASTR != 0>(d); e[k] = ee; f[k] = ff; zb[k] = z; zw1[k] = w1; zw2[k] = w2;
   }
 
   // Row (n-1) is complete once packet n is known: separator rows are stored, interior rows eliminated.
@@ -455,7 +484,7 @@ struct Thread {
     double w2 = -l2 * h2[5] - l1 * h1[5];
     if (k == 0) { w1 += a; w2 += b; }
     if (k == 1) w2 += a;
-    const double rr = PK_RCP(d);
+    const double rr = rcp_t<FASTR != 0>(d);
     sh.st(sh.fac, fidx(p, 0, k), rr); sh.st(sh.fac, fidx(p, 1, k), ee); sh.st(sh.fac, fidx(p, 2, k), ff);
     sh.st(sh.fac, fidx(p, 3, k), z); sh.st(sh.fac, fidx(p, 4, k), w1); sh.st(sh.fac, fidx(p, 5, k), w2);
     PK_UNROLL
@@ -688,7 +717,7 @@ struct Thread {
     const int T = TN(p);
     double Di[4];
     if (rawD) { Di[0] = Db[0]; Di[1] = Db[1]; Di[2] = Db[2]; Di[3] = Db[3]; }     // separator rows travel with D itself
-    else inv2(Db, Di);
+    else inv2<FASTR != 0>(Db, Di);
     // seven 16-byte stores: (L0 L1)(L2 L3)(U0 U1)(U2 U3)(D^-1 ...)(r0 r1), pair slots base/2 .. base/2 + 6
     const int b2 = base >> 1;
     sh.st2o(sh.xb, b2 + 0, T, t, Lb[0], Lb[1]); sh.st2o(sh.xb, b2 + 1, T, t, Lb[2], Lb[3]);
@@ -780,7 +809,7 @@ struct Thread {
     double tmp[2] = {0.0, 0.0}, Di[4];
     mva2(Lb, sL, tmp); mva2(Ub, sR, tmp);
     const double r0 = rb[0] - tmp[0], r1 = rb[1] - tmp[1];
-    inv2(Db, Di);
+    inv2<FASTR != 0>(Db, Di);
     xs0 = Di[0] * r0 + Di[1] * r1;
     xs1 = Di[2] * r0 + Di[3] * r1;
     sh.sto(sh.xb, 14, T, t, xs0); sh.sto(sh.xb, 15, T, t, xs1);
@@ -795,7 +824,7 @@ struct Thread {
   static PK_HD int sep_scratch_doubles(int C) { return 30 * C; }
   template <class SH>
   PK_HD void sep_store(const SH& sh, int scr_off, int half, int C, int j) {
-    double Di[4]; inv2(Db, Di);
+    double Di[4]; inv2<FASTR != 0>(Db, Di);
     const int o = scr_off + (half * C + j) * 14;
     PK_UNROLL
     for (int c = 0; c < 4; ++c) { sh.stl(sh.xb, o + c, Lb[c]); sh.stl(sh.xb, o + 4 + c, Ub[c]); sh.stl(sh.xb, o + 8 + c, Di[c]); }
@@ -855,7 +884,7 @@ struct Thread {
     mma2(SD, Sq, A);
     rhs[0] = rb[0]; rhs[1] = rb[1];
     mva2(SD, rq, rhs);
-    inv2(A, Ai);
+    inv2<FASTR != 0>(A, Ai);
     sh.stl(sh.xb, scr_off + 28 * C + 2 * j, Ai[0] * rhs[0] + Ai[1] * rhs[1]);
     sh.stl(sh.xb, scr_off + 28 * C + 2 * j + 1, Ai[2] * rhs[0] + Ai[3] * rhs[1]);
   }
@@ -871,7 +900,7 @@ struct Thread {
       double tmp[2] = {0.0, 0.0}, Di[4];
       // the threads that solved a separator row get their own row back from the published copy (L, U, D^-1, r)
       if ((t & (Tc - 1)) < C) pcr_load_row_local(p, sh, base >> 1, t, Lb, Ub, Di, rb);
-      else inv2(Db, Di);
+      else inv2<FASTR != 0>(Db, Di);
       mva2(Lb, sL_, tmp); mva2(Ub, sR_, tmp);
       const double r0 = rb[0] - tmp[0], r1 = rb[1] - tmp[1];
       xs0 = Di[0] * r0 + Di[1] * r1;
@@ -896,7 +925,7 @@ struct Thread {
     mma2(SD, Sq, A);
     rhs[0] = rb[0]; rhs[1] = rb[1];
     mva2(SD, rq, rhs);
-    inv2(A, Ai);
+    inv2<FASTR != 0>(A, Ai);
     xs0 = Ai[0] * rhs[0] + Ai[1] * rhs[1];
     xs1 = Ai[2] * rhs[0] + Ai[3] * rhs[1];
     sh.sto(sh.xb, 14, T, t, xs0); sh.sto(sh.xb, 15, T, t, xs1);
@@ -911,7 +940,7 @@ struct Thread {
   template <class SH>
   PK_HD void hyb_publish(const Params& p, const SH& sh) {
     const int T = TN(p);
-    double Di[4]; inv2(Db, Di);
+    double Di[4]; inv2<FASTR != 0>(Db, Di);
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
       sh.st(sh.xb, c * T + t, Lb[c]); sh.st(sh.xb, (4 + c) * T + t, Ub[c]); sh.st(sh.xb, (8 + c) * T + t, Di[c]);
@@ -952,7 +981,7 @@ struct Thread {
     for (int c = 0; c < 4; ++c) { L_[c] = sh.ld(sh.xb, c * T + i); U_[c] = sh.ld(sh.xb, (4 + c) * T + i); D_[c] = sh.ld(sh.xb, (14 + c) * T + i); }
     r_[0] = sh.ld(sh.xb, 12 * T + i); r_[1] = sh.ld(sh.xb, 13 * T + i);
     hyb_absorb(p, sh, il, ir, L_, D_, U_, r_);
-    double Di[4]; inv2(D_, Di);
+    double Di[4]; inv2<FASTR != 0>(D_, Di);
     PK_UNROLL
     for (int c = 0; c < 4; ++c) {
       sh.st(sh.xb, c * T + i, L_[c]); sh.st(sh.xb, (4 + c) * T + i, U_[c]); sh.st(sh.xb, (8 + c) * T + i, Di[c]);
@@ -989,7 +1018,7 @@ struct Thread {
       mma2(SD, Sq, A);
       rhs[0] = rb[0]; rhs[1] = rb[1];
       mva2(SD, rq, rhs);
-      inv2(A, Ai);
+      inv2<FASTR != 0>(A, Ai);
       sh.st(sh.xb, 14 * T + i, Ai[0] * rhs[0] + Ai[1] * rhs[1]);
       sh.st(sh.xb, 15 * T + i, Ai[2] * rhs[0] + Ai[3] * rhs[1]);
       return;
@@ -998,7 +1027,7 @@ struct Thread {
       const int d = 1 << ((step - 1) >> 1);
       hyb_absorb(p, sh, S_ * ((t - d) & 31), S_ * ((t + d) & 31), Lb, Db, Ub, rb);
     } else {
-      double Di[4]; inv2(Db, Di);
+      double Di[4]; inv2<FASTR != 0>(Db, Di);
       PK_UNROLL
       for (int c = 0; c < 4; ++c) {
         sh.st(sh.xb, c * T + i, Lb[c]); sh.st(sh.xb, (4 + c) * T + i, Ub[c]); sh.st(sh.xb, (8 + c) * T + i, Di[c]);
@@ -1306,8 +1335,8 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 // scaled by sqrt(dt/nupd) before it is added.  Summation order (part of the definition: every code path -- step kernels,
 // peakon-SDE kernel, emulation -- produces the same bits):
 //   nupd <  PK_COOP_NUPD : j = 0, 1, ..., nupd-1 in sequence;
-//   nupd >= PK_COOP_NUPD : 32 interleaved partial sums (lane l adds j = l, l+32, ... in sequence), combined by the xor
-//                          butterfly 16, 8, 4, 2, 1 -- the order a warp produces when its 32 lanes share the draws.
+//   nupd >= PK_COOP_NUPD : 32 interleaved partial sums (lane l adds j = l, l+32, ... in sequence), added up in lane
+//                          order 0, 1, ..., 31 -- what a warp produces when its 32 lanes share the draws.
 enum { PK_COOP_NUPD = 64 };
 PK_HD double philox_partial(unsigned long long seed, unsigned rid, unsigned step, unsigned k, int nupd, double sdt, int lane) {
   double s = 0.0;
@@ -1320,13 +1349,9 @@ PK_HD double philox_increment(unsigned long long seed, unsigned rid, unsigned st
     for (int j = 0; j < nupd; ++j) w += philox_normal(seed, rid, step, k, (unsigned)j) * sdt;
     return w;
   }
-  double pa[32], qa[32];
-  for (int l = 0; l < 32; ++l) pa[l] = philox_partial(seed, rid, step, k, nupd, sdt, l);
-  for (int o = 16; o > 0; o >>= 1) {
-    for (int l = 0; l < 32; ++l) qa[l] = pa[l] + pa[l ^ o];
-    for (int l = 0; l < 32; ++l) pa[l] = qa[l];
-  }
-  return pa[0];
+  double w = philox_partial(seed, rid, step, k, nupd, sdt, 0);
+  for (int l = 1; l < 32; ++l) w += philox_partial(seed, rid, step, k, nupd, sdt, l);
+  return w;
 }
 
 struct DrawIO {
@@ -1340,9 +1365,10 @@ struct DrawIO {
   int per = 0, w0 = 0;
   int coop = 0;           // many sub-updates: a WARP owns a step of the window and shares the draws of each increment
 };
+template <bool COOP = true>
 PK_HD void draw_begin(const Params& p, DrawIO& d, int nth) {
   if (p.nxi <= 0 || p.nxi > nth) return;
-  d.coop = (!d.dW_in && p.nupd >= PK_COOP_NUPD && p.nxi <= 32 && nth >= 32) ? 1 : 0;
+  d.coop = (COOP && !d.dW_in && p.nupd >= PK_COOP_NUPD && p.nxi <= 32 && nth >= 32) ? 1 : 0;
   d.per = d.coop ? (nth >> 5) : nth / p.nxi;
   d.w0 = d.n0 - (d.n0 % d.per);
 }
@@ -1357,7 +1383,7 @@ PK_HD double draw_one(const Params& p, const DrawIO& d, int n, int k) {
   if (d.dW_in) return d.dW_in[o];
   return philox_increment(d.seed, d.rid, (unsigned)(d.step0 + n), (unsigned)k, p.nupd, p.sdt);
 }
-template <class SH>
+template <bool COOP = true, class SH>
 PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int tid, int nth, bool leader, double& hold, const DrawSlot& slot) {
   if (p.nxi <= 0) return;
   if (p.nxi > nth) {                       // more modes than threads: plain loop
@@ -1369,16 +1395,16 @@ PK_HD void draw_step(const Params& p, const SH& sh, const DrawIO& d, int n, int 
     return;
   }
   const int per = d.per, w0 = d.w0;        // steps per window, first step of the current window
-  if (d.coop) {
+  if (COOP && d.coop) {
     // warp w of the block owns step w0 + w of the window; its lanes share the nupd draws of every increment and lane k
     // keeps the increment of mode k (philox_increment's summation order)
     const int w = tid >> 5, lane = tid & 31;
     if ((n == w0 || n == d.n0) && w0 + w < d.nsteps) {
       for (int k = 0; k < p.nxi; ++k) {
 #if defined(__CUDA_ARCH__)
-        double s = philox_partial(d.seed, d.rid, (unsigned)(d.step0 + w0 + w), (unsigned)k, p.nupd, p.sdt, lane);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double part = philox_partial(d.seed, d.rid, (unsigned)(d.step0 + w0 + w), (unsigned)k, p.nupd, p.sdt, lane);
+        double s = __shfl_sync(0xffffffffu, part, 0);
+        for (int l = 1; l < 32; ++l) s += __shfl_sync(0xffffffffu, part, l);
         if (lane == k) hold = s;
 #else
         if (lane == k) hold = philox_increment(d.seed, d.rid, (unsigned)(d.step0 + w0 + w), (unsigned)k, p.nupd, p.sdt);
@@ -1453,7 +1479,7 @@ PK_HD double nan_quiet() {
 #endif
 }
 
-// One fused dump of the realisation whose state is resident in `sh` (executor collectives: allreduce3, argmax4, minint2).
+// One fused dump of the realisation whose state is resident in `sh` (executor collectives: argmax4sum3, minint2).
 template <int M, int MODE, int TT, class Exec, class Th, class SH>
 PK_HD void diag_dump(Exec& ex, const Params& p, const SH& sh, const StepIO& io, int d, bool failed) {
   const long long row = (long long)d * io.R + io.r;
@@ -1470,10 +1496,8 @@ PK_HD void diag_dump(Exec& ex, const Params& p, const SH& sh, const StepIO& io, 
   }
   double sums[3], av[4];
   int ai[4];
-  // (one pass over the rows feeds both collectives; the partials live in the threads' fn2/sn2/xn2 slots, dead here)
-  ex.argmax4([&](Th& th, double* v, int* i) { double s3[3]; th.diag_local(p, sh, s3, v, i); th.fn2 = s3[0]; th.sn2 = s3[1]; th.xn2 = s3[2]; },
-             av, ai, sh.xb);
-  ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, sums);
+  // one pass over the rows, ONE collective for the four arg-reductions and the three sums
+  ex.argmax4sum3([&](Th& th, double* v, int* i, double* s3) { th.diag_local(p, sh, s3, v, i); }, av, ai, sums, sh.xb);
   int k2[2] = {0x7fffffff, 0x7fffffff};
   if (io.suite_vals) ex.minint2([&](Th& th, int* k) { th.suite_local(p, sh, ai[2], k); }, k2, sh.xb);
   ex.one([&]() {
@@ -1500,7 +1524,7 @@ PK_HD void diag_dump(Exec& ex, const Params& p, const SH& sh, const StepIO& io, 
       } else { vals[1] = nan_quiet(); ids[2] = -1; }
     }
   });
-  ex.sync();       // the exchange area served as scratch: nobody may start the next step before all have read it
+  // (the exchange area served as scratch; the next step does not write it before its first barrier)
 }
 
 // SNES convergence test (SNESConvergedDefault + divergence tolerance).
@@ -1527,7 +1551,12 @@ PK_HD int snes_test(const Params& p, int it, const double* nrm, double& fnorm0sq
 #define PK_LD_COHERENT(ptr) (*(ptr))
 #endif
 
-template <int M, int MODE, int TT, class Exec, class Th, class SH>
+// FEAT: optional features compiled into the time loop.  bit 0: fused dump diagnostics (diag_dump); bit 1: warp-shared
+// Philox sub-updates (nupd >= PK_COOP_NUPD).  The headline launches (no dumps inside the launch, nXi_updates < 64) use the
+// lean instantiation: the mere presence of the two blocks in the loop costs 4 % of the single-CTA kernel (code placement /
+// scheduling; measured, profiles/r2c_variants.log), although neither is executed.
+enum { FEAT_DUMP = 1, FEAT_COOP = 2, FEAT_ALL = 3 };
+template <int M, int MODE, int TT, class Exec, class Th, class SH, int FEAT = FEAT_ALL>
 PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) {
   // counters may have been written by another SM earlier in this launch (previous step block)
   int failed = PK_LD_COHERENT(io.fail_step + io.r);
@@ -1538,19 +1567,21 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
   dio.nsteps = io.nsteps; dio.rid = io.rid; dio.seed = io.seed; dio.n0 = io.n0;
   int expect = 2;     // iteration at which convergence is expected: there only the residual is evaluated first
   int cert_skip = 0;  // steps during which the convergence certificate is not attempted
-  ex.each_tid([&](Th& th, int tid, int nth, bool, int, int) { th.dw_slot = draw_slot(p, tid); if (dio.per == 0) draw_begin(p, dio, nth); });
+  ex.each_tid([&](Th& th, int tid, int nth, bool, int, int) { th.dw_slot = draw_slot(p, tid); if (dio.per == 0) draw_begin<(FEAT & FEAT_COOP) != 0>(p, dio, nth); });
   for (int n = io.n0; n < io.n1; ++n) {
     ex.each([&](Th& th) { th.kill_all(); });
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
     draw_advance(dio, n);
     ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
-      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold, th.dw_slot);
+      draw_step<(FEAT & FEAT_COOP) != 0>(p, sh, dio, n, tid, nth, leader, th.dw_hold, th.dw_slot);
     });
     ex.sync();
     ex.tick(0);
     if (failed >= 0) {
-      if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
-        diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, true);
+      if constexpr ((FEAT & FEAT_DUMP) != 0) {
+        if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
+          diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, true);
+      }
       continue;
     }
     if (PK_NOISE_OF(MODE) == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
@@ -1733,8 +1764,10 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     }
     ex.sync();
     ex.tick(12);
-    if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
-      diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, failed >= 0);
+    if constexpr ((FEAT & FEAT_DUMP) != 0) {
+      if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
+        diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, failed >= 0);
+    }
   }
   ex.one([&]() {
     io.fail_step[io.r] = failed; io.its_last[io.r] = its_last; io.its_total[io.r] = its_total;

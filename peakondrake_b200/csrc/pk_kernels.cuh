@@ -68,14 +68,15 @@ struct GpuExecT {
 
 
   // ---- collectives of the fused dump diagnostics (diag_dump in pk_core.h) ----
-  // argmax4: four (value, index) candidates per thread -> largest value, lowest index among equals, known to every
-  // thread.  minint2: two ints per thread -> minima.  scratch: CTA-local shared memory (the exchange area, idle at the
-  // end of a step); argmax4 uses doubles [0, 6 nw), minint2 ints from double offset 6 nw on.
-  template <class F> __device__ __forceinline__ void argmax4(F f, double* outv, int* outi, double* scratch) {
-    double v[4]; int ix[4];
+  // argmax4sum3: four (value, index) candidates per thread -> largest value, lowest index among equals; three doubles per
+  // thread -> sums; results known to every thread.  minint2: two ints per thread -> minima.  scratch: CTA-local shared
+  // memory (the exchange area, idle at the end of a step): doubles [0, 4 nw) values, [4 nw, 6 nw) indices, [6 nw, 9 nw) sums;
+  // minint2 uses the ints from double offset 9 nw on.
+  template <class F> __device__ __forceinline__ void argmax4sum3(F f, double* outv, int* outi, double* outs, double* scratch) {
+    double v[4], s3[3] = {0.0, 0.0, 0.0}; int ix[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) { v[c] = -INFINITY; ix[c] = 0x7fffffff; }
-    if (AA || th.active) f(th, v, ix);
+    if (AA || th.active) f(th, v, ix, s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -84,12 +85,17 @@ struct GpuExecT {
         const int oi = __shfl_xor_sync(0xffffffffu, ix[c], o);
         if (ov > v[c] || (ov == v[c] && oi < ix[c])) { v[c] = ov; ix[c] = oi; }
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s3[c] += __shfl_xor_sync(0xffffffffu, s3[c], o);
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
     int* si = reinterpret_cast<int*>(scratch + 4 * nw);
+    double* ss = scratch + 6 * nw;
     if (lane == 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) { scratch[c * nw + w] = v[c]; si[c * nw + w] = ix[c]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ss[c * nw + w] = s3[c];
     }
     __syncthreads();
 #pragma unroll
@@ -101,6 +107,12 @@ struct GpuExecT {
       }
       outv[c] = rv; outi[c] = ri;
     }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double t = 0.0;
+      for (int k = 0; k < nw; ++k) t += ss[c * nw + k];
+      outs[c] = t;
+    }
   }
   template <class F> __device__ __forceinline__ void minint2(F f, int* out, double* scratch) {
     int k[2] = {0x7fffffff, 0x7fffffff};
@@ -111,7 +123,7 @@ struct GpuExecT {
       k[1] = min(k[1], __shfl_xor_sync(0xffffffffu, k[1], o));
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
-    int* si = reinterpret_cast<int*>(scratch + 6 * nw);
+    int* si = reinterpret_cast<int*>(scratch + 9 * nw);
     if (lane == 0) { si[w] = k[0]; si[nw + w] = k[1]; }
     __syncthreads();
     int r0 = si[0], r1 = si[nw];
@@ -180,7 +192,7 @@ struct GpuExecT {
         t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
       }
     }
-    const double inv = PK_RCP(1.0 - tA);
+    const double inv = rcp_t<(TBC > 0)>(1.0 - tA);
     const double x0 = t0 * inv, x1 = t1 * inv;          // value entering the first thread (cyclic closure)
     const double w0 = eA * x0 + e0, w1 = eA * x1 + e1;  // value entering my warp
     const double o0 = A * w0 + c0, o1 = A * w1 + c1;    // value leaving my thread
@@ -212,7 +224,7 @@ template <int M, int MODE, bool AA, int TT, int VAR = 0> using GpuExec = GpuExec
 
 template <int MODE> struct NArr { enum { n = (MODE == NOISE_FULL) ? 7 : (MODE == NOISE_X ? 4 : 3) }; };
 
-template <int M, int MODE, int TB, int MINB, int TT, int VAR = 0>
+template <int M, int MODE, int TB, int MINB, int TT, int VAR = 0, int FEAT = FEAT_ALL>
 __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int Tn = TT > 0 ? TT : p.T;
@@ -276,7 +288,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
     __syncthreads();
     io.r = r; io.rid = a.rid0 + (unsigned)r;
     io.n0 = b * a.nblk; io.n1 = min(io.n0 + a.nblk, a.nsteps);
-    run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT, VAR>, Thread<M, MODE, TT, VAR> >(ex, p, sh, io);
+    run_steps<M, MODE, TT, GpuExec<M, MODE, (TB > 32), TT, VAR>, Thread<M, MODE, TT, VAR>, Shared, FEAT>(ex, p, sh, io);
     __syncthreads();
     for (int i = threadIdx.x; i < p.ne; i += blockDim.x) {
       const int sl = row_slot_c<M, TT>(p, i);
@@ -403,12 +415,13 @@ struct GpuExecClusterT {
   }
 
   // collectives of the fused dump diagnostics: block-level result, then the C block aggregates through DSMEM
-  // (scratch layout: argmax4 doubles [0, 6 nw) + aggregate [6 nw, 6 nw + 6); minint2 ints from double offset 6 nw + 6)
-  template <class F> __device__ __forceinline__ void argmax4(F f, double* outv, int* outi, double* scratch) {
-    double v[4]; int ix[4];
+  // (scratch: doubles [0, 4 nw) values, [4 nw, 6 nw) indices, [6 nw, 9 nw) sums, aggregate [9 nw, 9 nw + 9);
+  //  minint2: ints from double offset 9 nw + 9)
+  template <class F> __device__ __forceinline__ void argmax4sum3(F f, double* outv, int* outi, double* outs, double* scratch) {
+    double v[4], s3[3] = {0.0, 0.0, 0.0}; int ix[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) { v[c] = -INFINITY; ix[c] = 0x7fffffff; }
-    f(th, v, ix);
+    f(th, v, ix, s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -417,15 +430,20 @@ struct GpuExecClusterT {
         const int oi = __shfl_xor_sync(0xffffffffu, ix[c], o);
         if (ov > v[c] || (ov == v[c] && oi < ix[c])) { v[c] = ov; ix[c] = oi; }
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s3[c] += __shfl_xor_sync(0xffffffffu, s3[c], o);
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     int* si = reinterpret_cast<int*>(scratch + 4 * nw);
+    double* ss = scratch + 6 * nw;
     if (lane == 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) { scratch[c * nw + w] = v[c]; si[c * nw + w] = ix[c]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ss[c * nw + w] = s3[c];
     }
     __syncthreads();
-    double* agg = scratch + 6 * nw;
+    double* agg = scratch + 9 * nw;                       // 4 values | 4 indices (2 doubles) | 3 sums
     int* aggi = reinterpret_cast<int*>(agg + 4);
     if (threadIdx.x == 0) {
       for (int c = 0; c < 4; ++c) {
@@ -436,11 +454,17 @@ struct GpuExecClusterT {
         }
         agg[c] = rv; aggi[c] = ri;
       }
+      for (int c = 0; c < 3; ++c) {
+        double t = 0.0;
+        for (int k = 0; k < nw; ++k) t += ss[c * nw + k];
+        agg[6 + c] = t;
+      }
     }
     cg::cluster_group cl = cg::this_cluster();
     sync();
 #pragma unroll
     for (int c = 0; c < 4; ++c) { outv[c] = -INFINITY; outi[c] = 0x7fffffff; }
+    outs[0] = outs[1] = outs[2] = 0.0;
     for (unsigned b = 0; b < C; ++b) {
       const double* qa = cl.map_shared_rank(agg, b);
       const int* qi = reinterpret_cast<const int*>(qa + 4);
@@ -449,6 +473,8 @@ struct GpuExecClusterT {
         const double ov = qa[c]; const int oi = qi[c];
         if (ov > outv[c] || (ov == outv[c] && oi < outi[c])) { outv[c] = ov; outi[c] = oi; }
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) outs[c] += qa[6 + c];
     }
   }
   template <class F> __device__ __forceinline__ void minint2(F f, int* out, double* scratch) {
@@ -460,7 +486,7 @@ struct GpuExecClusterT {
       k[1] = min(k[1], __shfl_xor_sync(0xffffffffu, k[1], o));
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int* si = reinterpret_cast<int*>(scratch + 6 * nw + 6);
+    int* si = reinterpret_cast<int*>(scratch + 9 * nw + 9);
     if (lane == 0) { si[w] = k[0]; si[nw + w] = k[1]; }
     __syncthreads();
     int* agg = si + 2 * nw;

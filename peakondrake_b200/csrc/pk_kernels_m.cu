@@ -29,8 +29,9 @@ template <int M> static ckern_t pick_cmode(int mode, int Tc, int minb) {
 }
 
 #if PK_M <= 8
-template <int M, int MODE> static kern_t pick_tb(int block, int T, int minb) {
-  if (T < 32) return pk_step_kernel<M, MODE, 32, 1, 0>;    // tiny meshes: some lanes of the single warp idle
+// feat = 0: lean time loop (no fused dumps, no warp-shared sub-updates): the headline launches; feat != 0: everything
+template <int M, int MODE, int FEAT> static kern_t pick_tb(int block, int T, int minb) {
+  if (T < 32) return pk_step_kernel<M, MODE, 32, 1, 0, 0, FEAT_ALL>;    // tiny meshes: some lanes of the single warp idle
   if (T == 128) {
 #ifdef PK_EXPERIMENTAL_VARIANTS      // A/B builds only (profiles/exp_fs.py); see Thread<> in pk_core.h
     if (minb == 2) return pk_step_kernel<M, MODE, 128, 2, 128, 1>;    // FS variant (2 CTAs/SM)
@@ -41,19 +42,19 @@ template <int M, int MODE> static kern_t pick_tb(int block, int T, int minb) {
 #else
     if (minb != 3) return nullptr;
 #endif
-    return pk_step_kernel<M, MODE, 128, 3, 128>;
+    return pk_step_kernel<M, MODE, 128, 3, 128, 0, FEAT>;
   }
-  if (block <= 128) return pk_step_kernel<M, MODE, 128, 2, 0>;
-  if (block <= 256) return (M <= 5) ? pk_step_kernel<M, MODE, 256, 2, 256> : pk_step_kernel<M, MODE, 256, 1, 256>;
-  return pk_step_kernel<M, MODE, 512, 1, 512>;
+  if (block <= 128) return pk_step_kernel<M, MODE, 128, 2, 0, 0, FEAT_ALL>;
+  if (block <= 256) return (M <= 5) ? pk_step_kernel<M, MODE, 256, 2, 256, 0, FEAT> : pk_step_kernel<M, MODE, 256, 1, 256, 0, FEAT>;
+  return pk_step_kernel<M, MODE, 512, 1, 512, 0, FEAT_ALL>;
 }
-template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {
+template <int M, int FEAT> static kern_t pick_mode(int mode, int block, int T, int minb) {
   switch (mode) {
-    case NOISE_SCALAR: return pick_tb<M, NOISE_SCALAR>(block, T, minb);
-    case NOISE_X: return pick_tb<M, NOISE_X>(block, T, minb);
-    case TEST_SCALAR: return pick_tb<M, TEST_SCALAR>(block, T, minb);
-    case TEST_X: return pick_tb<M, TEST_X>(block, T, minb);
-    default: return pick_tb<M, NOISE_FULL>(block, T, minb);
+    case NOISE_SCALAR: return pick_tb<M, NOISE_SCALAR, FEAT>(block, T, minb);
+    case NOISE_X: return pick_tb<M, NOISE_X, FEAT>(block, T, minb);
+    case TEST_SCALAR: return pick_tb<M, TEST_SCALAR, FEAT_ALL>(block, T, minb);
+    case TEST_X: return pick_tb<M, TEST_X, FEAT_ALL>(block, T, minb);
+    default: return pick_tb<M, NOISE_FULL, FEAT>(block, T, minb);
   }
 }
 
@@ -62,6 +63,8 @@ template <int M> static kern_t pick_mode(int mode, int block, int T, int minb) {
 #define PK_CAT2(a, b) a##b
 #define PK_CAT(a, b) PK_CAT2(a, b)
 #if PK_M <= 8
-kern_t PK_CAT(pk_pick_kernel_m, PK_M)(int mode, int block, int T, int minb) { return pick_mode<PK_M>(mode, block, T, minb); }
+kern_t PK_CAT(pk_pick_kernel_m, PK_M)(int mode, int block, int T, int minb, int feat) {
+  return feat ? pick_mode<PK_M, FEAT_ALL>(mode, block, T, minb) : pick_mode<PK_M, 0>(mode, block, T, minb);
+}
 #endif
 ckern_t PK_CAT(pk_pick_cluster_kernel_m, PK_M)(int mode, int Tc, int minb) { return pick_cmode<PK_M>(mode, Tc, minb); }

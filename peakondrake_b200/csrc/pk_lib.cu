@@ -304,15 +304,15 @@ int pk_fail(pk_ctx* c, const char* fmt, ...) {
   return -1;
 }
 
-static kern_t pick_kernel(const Params& p, int block, int fs) {
+static kern_t pick_kernel(const Params& p, int block, int fs, int feat = 1) {
   // fs = 1: FS variant (factors in shared memory, rolled row loops, 2 CTAs/SM); 2: rolled assembly with register
   // factors; 0: fully unrolled register variant
   const int v = fs == 1 ? 2 : (fs == 2 ? 4 : (fs == 4 ? 5 : (fs == 6 ? 6 : (fs == 7 ? 7 : 3))));
   switch (p.M) {
-    case 5: return pk_pick_kernel_m5(p.mode, block, p.T, v);
-    case 6: return pk_pick_kernel_m6(p.mode, block, p.T, v);
-    case 7: return pk_pick_kernel_m7(p.mode, block, p.T, v);
-    case 8: return pk_pick_kernel_m8(p.mode, block, p.T, v);
+    case 5: return pk_pick_kernel_m5(p.mode, block, p.T, v, feat);
+    case 6: return pk_pick_kernel_m6(p.mode, block, p.T, v, feat);
+    case 7: return pk_pick_kernel_m7(p.mode, block, p.T, v, feat);
+    case 8: return pk_pick_kernel_m8(p.mode, block, p.T, v, feat);
   }
   return nullptr;
 }
@@ -447,6 +447,9 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   e = (cfg->scheme == 1 && c->cluster == 1) ? cudaSuccess : cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaFuncSetAttribute(smem=%zu): %s", c->smem, m.c_str()); }
   if (cfg->scheme != 1 && c->cluster == 1) {
+    // the lean instantiation of the same kernel (no fused dumps / shared sub-updates in the time loop) needs the attribute too
+    const void* k0 = (const void*)pick_kernel(p, c->block, c->fs, 0);
+    if (k0 && k0 != k) cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem);
     // persistent CTAs: as many as are resident at once
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, c->block, c->smem);
@@ -557,7 +560,9 @@ static int launch_range(pk_ctx* c, StepArgs a, int nsteps, int r0, int nr, int s
     c->last_nb = nb; c->last_nblk = nblk; c->last_grid = grid;
     CK(c, cudaMemsetAsync(queue, 0, sizeof(int) * (size_t)(nr + 1), st));
     if (timed) CK(c, cudaEventRecord(c->ev0, st));      // time the kernel alone
-    kern_t k = pick_kernel(c->p, c->block, c->fs);
+    // lean time loop unless this launch dumps inside the kernel or shares Philox sub-updates within warps
+    const int feat = (a.diag_every > 0 || (!a.dW_in && c->p.nupd >= PK_COOP_NUPD)) ? 1 : 0;
+    kern_t k = pick_kernel(c->p, c->block, c->fs, feat);
     k<<<grid, c->block, c->smem, st>>>(c->p, a);
     ++c->nlaunch;
   }
@@ -879,9 +884,9 @@ extern "C" int pk_profile_enable(pk_ctx* c) {
 
 #ifdef PK_PROFILE_SINGLE_M
 // profiling build: only the M=8 kernels are compiled (profiles/phase_cycles.py)
-kern_t pk_pick_kernel_m5(int, int, int, int) { return nullptr; }
-kern_t pk_pick_kernel_m6(int, int, int, int) { return nullptr; }
-kern_t pk_pick_kernel_m7(int, int, int, int) { return nullptr; }
+kern_t pk_pick_kernel_m5(int, int, int, int, int) { return nullptr; }
+kern_t pk_pick_kernel_m6(int, int, int, int, int) { return nullptr; }
+kern_t pk_pick_kernel_m7(int, int, int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m5(int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m6(int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m7(int, int, int) { return nullptr; }

@@ -106,15 +106,18 @@ struct EmuExecT {
     for (int s = 0; s < n; ++s)
       for (int k = 0; k < 32; ++k) { const int t = order == 0 ? k : 31 - k; f(th[t], s); }
   }
-  template <class F> void argmax4(F f, double* outv, int* outi, double*) {
+  template <class F> void argmax4sum3(F f, double* outv, int* outi, double* outs, double*) {
     for (int c = 0; c < 4; ++c) { outv[c] = -INFINITY; outi[c] = 0x7fffffff; }
+    std::vector<double> part(3 * T);
     for (int k = 0; k < T; ++k) {
       const int t = order == 0 ? k : T - 1 - k; cur = t / Tc;
-      double v[4]; int ix[4];
+      double v[4], s3[3] = {0.0, 0.0, 0.0}; int ix[4];
       for (int c = 0; c < 4; ++c) { v[c] = -INFINITY; ix[c] = 0x7fffffff; }
-      f(th[t], v, ix);
+      f(th[t], v, ix, s3);
       for (int c = 0; c < 4; ++c) if (v[c] > outv[c] || (v[c] == outv[c] && ix[c] < outi[c])) { outv[c] = v[c]; outi[c] = ix[c]; }
+      for (int c = 0; c < 3; ++c) part[3 * t + c] = s3[c];
     }
+    for (int c = 0; c < 3; ++c) { outs[c] = 0.0; for (int t = 0; t < T; ++t) outs[c] += part[3 * t + c]; }   // thread order, whatever `order`
   }
   template <class F> void minint2(F f, int* out, double*) {
     out[0] = out[1] = 0x7fffffff;
