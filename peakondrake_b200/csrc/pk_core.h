@@ -1235,6 +1235,19 @@ struct Thread {
   // (du = (u_{i+1} - u_i)/h, jump = |du_i - du_{i-1}|), so extrema and indices are bit-identical to the separate
   // kernel; sums differ only in summation order.  av/ai: candidates of  max du, max -du, max u, max |jump|
   // (ties -> lowest node index, NumPy argmax / argmin).
+  // x / h, correctly rounded, without a division: q = x * RN(1/h), one fused correction with the exact remainder
+  // (Markstein: with the correctly rounded reciprocal and r = x - q h computed exactly by the FMA, q + r * RN(1/h) rounds
+  // to RN(x / h)).  Three instructions instead of the ~40 of a double division; the same bits as pk_diag_kernel's `/ h`
+  // (tests/test_gpu_configs.py::test_fused_dump_equals_separate_kernels compares them bit for bit).
+  static PK_HD double div_h(const Params& p, double x) {
+#if defined(__CUDA_ARCH__)
+    const double q = x * p.ih;
+    const double r = fma(-q, p.h, x);
+    return fma(r, p.ih, q);
+#else
+    return x / p.h;
+#endif
+  }
   template <class SH>
   PK_HD double ldn2(const Params& p, const SH& sh, const double* a, int j) const {      // j in [-1, m + 1]
     const int mm = ext ? M : M - 1;
@@ -1242,7 +1255,7 @@ struct Thread {
   }
   template <class SH>
   PK_HD void diag_local(const Params& p, const SH& sh, double* s3, double* av, int* ai) const {
-    const double h = p.h, ih = 1.0 / p.h, h3 = p.h * (1.0 / 3.0);
+    const double h = p.h, ih = p.ih, h3 = p.h * (1.0 / 3.0);
     double sM = 0.0, sK = 0.0, sU = 0.0;
     PK_UNROLL
     for (int c = 0; c < 4; ++c) { av[c] = -1.7976931348623157e308 * 2.0; ai[c] = 0x7fffffff; }
@@ -1252,7 +1265,7 @@ struct Thread {
       if (has_row(j)) {
         const double up = ldn(p, sh, sh.U0, j + 1);
         const int i = s + j;
-        const double du = (up - u0) / h, dum = (u0 - um) / h;
+        const double du = div_h(p, up - u0), dum = div_h(p, u0 - um);
         const double jmp = fabs(du - dum);
         sM += h3 * (u0 * u0 + u0 * up + up * up);
         sK += (up - u0) * (up - u0) * ih;
@@ -1271,15 +1284,14 @@ struct Thread {
   template <class SH>
   PK_HD void suite_local(const Params& p, const SH& sh, int pc, int* k2) const {
     const int ne = p.ne, S = ne / 2;
-    const double h = p.h;
     k2[0] = k2[1] = 0x7fffffff;
     double u0 = ldn2(p, sh, sh.U0, 0), up = ldn2(p, sh, sh.U0, 1);
-    double dum = (u0 - ldn2(p, sh, sh.U0, -1)) / h, du0 = (up - u0) / h;
+    double dum = div_h(p, u0 - ldn2(p, sh, sh.U0, -1)), du0 = div_h(p, up - u0);
     PK_UNROLL
     for (int j = 0; j < M; ++j) {
       if (has_row(j)) {
         const double upp = ldn2(p, sh, sh.U0, j + 2);
-        const double dup = (upp - up) / h;
+        const double dup = div_h(p, upp - up);
         const int i = s + j;
         if (du0 > dum) { int k = i - pc; if (k < 0) k += ne; if (k < S && k < k2[0]) k2[0] = k; }
         if (du0 < dup) { int k = pc - 1 - i; if (k < 0) k += ne; if (k < S && k < k2[1]) k2[1] = k; }
@@ -1611,7 +1623,22 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
           ex.allreduce3([&](Th& th, double* v) { v[0] = 0.0; v[1] = th.sn2; v[2] = th.xn2; }, n2);
           // + an allowance for the linear solve: relative residual 1e-6 of the system just solved (measured: < 1e-9)
           const double B = p.cert_k * n2[1] + 1e-6 * sqrt(nrm[0]), thr2 = p.rtol2 * fnorm0;
-          if (B * B <= 0.0625 * thr2 && thr2 >= 100.0 * p.cert_floor2 * ((double)p.ne + n2[2])) { status = 1; break; }
+          if (B * B <= 0.0625 * thr2 && thr2 >= 100.0 * p.cert_floor2 * ((double)p.ne + n2[2])) {
+#ifdef PK_CERT_CHECK
+            // checking build (profiles/cert_check.py): evaluate the residual the certificate claims to bound and FAIL the
+            // realisation (reason 9) if SNES's own test would not have accepted it -- the certificate must be iterate-neutral
+            ex.each([&](Th& th) { th.assemble_begin(p, sh, true); });
+            if constexpr (Th::ROLL_LITE) ex.each([&](Th& th) { th.residual_finish_rolled(p, sh); });
+            else ex.each([&](Th& th) { th.assemble_finish(p, sh, true); });
+            double chk[3];
+            ex.allreduce3([&](Th& th, double* v) { v[0] = th.fn2; v[1] = th.sn2; v[2] = th.xn2; }, chk);
+            if (!(chk[0] <= thr2)) { status = 2; reason = 9; break; }
+#ifdef PK_CERT_CHECK_BOUND      // also: the evaluated |R| (which carries evaluation noise ~ sqrt(cert_floor2 (ne + |w|^2))) within the bound
+            { const double fl = sqrt(p.cert_floor2 * ((double)p.ne + n2[2])); if (!(sqrt(chk[0]) <= B + 10.0 * fl)) { status = 2; reason = 8; break; } }
+#endif
+#endif
+            status = 1; break;
+          }
           cert_skip = 8;      // not provable here (coarse bound / large noise): do not pay the reduction again for a few steps
         }
         // evaluate the residual only; fall through to the full
@@ -1767,6 +1794,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     if constexpr ((FEAT & FEAT_DUMP) != 0) {
       if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
         diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, failed >= 0);
+      ex.tick(15);
     }
   }
   ex.one([&]() {

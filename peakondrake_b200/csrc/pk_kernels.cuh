@@ -408,15 +408,14 @@ struct GpuExecClusterT {
   template <class F> __device__ __forceinline__ void each_first(int, F) {}
   template <class F> __device__ __forceinline__ void warp0_steps(int, F) {}
   __device__ __forceinline__ double* area() {
-    const int nw = blockDim.x >> 5;
-    double* a = red + flip * (3 * nw + 3);
+    double* a = red + flip * cluster_red_half((int)blockDim.x);
     flip ^= 1;
     return a;
   }
 
   // collectives of the fused dump diagnostics: block-level result, then the C block aggregates through DSMEM
-  // (scratch: doubles [0, 4 nw) values, [4 nw, 6 nw) indices, [6 nw, 9 nw) sums, aggregate [9 nw, 9 nw + 9);
-  //  minint2: ints from double offset 9 nw + 9)
+  // (scratch: doubles [0, 4 nw) values, [4 nw, 6 nw) indices, [6 nw, 9 nw) sums, this CTA's aggregate [9 nw, 9 nw + 9), the
+  //  cluster's result [9 nw + 9, 9 nw + 18); minint2: ints from double offset 9 nw + 18)
   template <class F> __device__ __forceinline__ void argmax4sum3(F f, double* outv, int* outi, double* outs, double* scratch) {
     double v[4], s3[3] = {0.0, 0.0, 0.0}; int ix[4];
 #pragma unroll
@@ -462,20 +461,44 @@ struct GpuExecClusterT {
     }
     cg::cluster_group cl = cg::this_cluster();
     sync();
+    // one warp fetches the C aggregates (lane b <- CTA b), combines them and broadcasts through local shared memory
+    double* fin = agg + 9;                                // 4 values | 4 indices (2 doubles) | 3 sums
+    int* fini = reinterpret_cast<int*>(fin + 4);
+    if (w == 0) {
+      double gv[4], gs[3] = {0.0, 0.0, 0.0}; int gi[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { outv[c] = -INFINITY; outi[c] = 0x7fffffff; }
-    outs[0] = outs[1] = outs[2] = 0.0;
-    for (unsigned b = 0; b < C; ++b) {
-      const double* qa = cl.map_shared_rank(agg, b);
-      const int* qi = reinterpret_cast<const int*>(qa + 4);
+      for (int c = 0; c < 4; ++c) { gv[c] = -INFINITY; gi[c] = 0x7fffffff; }
+      if ((unsigned)lane < C) {
+        const double* qa = cl.map_shared_rank(agg, lane);
+        const int* qi = reinterpret_cast<const int*>(qa + 4);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double ov = qa[c]; const int oi = qi[c];
-        if (ov > outv[c] || (ov == outv[c] && oi < outi[c])) { outv[c] = ov; outi[c] = oi; }
+        for (int c = 0; c < 4; ++c) { gv[c] = qa[c]; gi[c] = qi[c]; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gs[c] = qa[6 + c];
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) outs[c] += qa[6 + c];
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double ov = __shfl_xor_sync(0xffffffffu, gv[c], o);
+          const int oi = __shfl_xor_sync(0xffffffffu, gi[c], o);
+          if (ov > gv[c] || (ov == gv[c] && oi < gi[c])) { gv[c] = ov; gi[c] = oi; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gs[c] += __shfl_xor_sync(0xffffffffu, gs[c], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { fin[c] = gv[c]; fini[c] = gi[c]; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) fin[6 + c] = gs[c];
+      }
     }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { outv[c] = fin[c]; outi[c] = fini[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) outs[c] = fin[6 + c];
   }
   template <class F> __device__ __forceinline__ void minint2(F f, int* out, double* scratch) {
     int k[2] = {0x7fffffff, 0x7fffffff};
@@ -486,10 +509,10 @@ struct GpuExecClusterT {
       k[1] = min(k[1], __shfl_xor_sync(0xffffffffu, k[1], o));
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    int* si = reinterpret_cast<int*>(scratch + 9 * nw + 9);
+    int* si = reinterpret_cast<int*>(scratch + 9 * nw + 18);
     if (lane == 0) { si[w] = k[0]; si[nw + w] = k[1]; }
     __syncthreads();
-    int* agg = si + 2 * nw;
+    int* agg = si + 2 * nw;                               // [0,1] this CTA's minima, [2,3] the cluster's
     if (threadIdx.x == 0) {
       int r0 = si[0], r1 = si[nw];
       for (int q = 1; q < nw; ++q) { r0 = min(r0, si[q]); r1 = min(r1, si[nw + q]); }
@@ -497,11 +520,17 @@ struct GpuExecClusterT {
     }
     cg::cluster_group cl = cg::this_cluster();
     sync();
-    out[0] = out[1] = 0x7fffffff;
-    for (unsigned b = 0; b < C; ++b) {
-      const int* q = cl.map_shared_rank(agg, b);
-      out[0] = min(out[0], q[0]); out[1] = min(out[1], q[1]);
+    if (w == 0) {
+      int g0_ = 0x7fffffff, g1_ = 0x7fffffff;
+      if ((unsigned)lane < C) { const int* q = cl.map_shared_rank(agg, lane); g0_ = q[0]; g1_ = q[1]; }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        g0_ = min(g0_, __shfl_xor_sync(0xffffffffu, g0_, o)); g1_ = min(g1_, __shfl_xor_sync(0xffffffffu, g1_, o));
+      }
+      if (lane == 0) { agg[2] = g0_; agg[3] = g1_; }
     }
+    __syncthreads();
+    out[0] = agg[2]; out[1] = agg[3];
   }
 
   template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
@@ -524,12 +553,20 @@ struct GpuExecClusterT {
     }
     cg::cluster_group cl = cg::this_cluster();
     sync();
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (unsigned c = 0; c < C; ++c) {
-      const double* q = cl.map_shared_rank(sc + 3 * nw, c);
-      s0 += q[0]; s1 += q[1]; s2 += q[2];
+    // ONE warp fetches the C aggregates through DSMEM (lane b <- CTA b) and adds them up; the result reaches the other
+    // threads through the CTA's own shared memory.  (Every thread reading all C aggregates remotely costs 3 C DSMEM
+    // loads per thread -- 49 KB per CTA and collective at C = 8, ~2 400 cycles at the measured DSMEM bandwidth.)
+    if (w == 0) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      if ((unsigned)lane < C) { const double* q = cl.map_shared_rank(sc + 3 * nw, lane); a0 = q[0]; a1 = q[1]; a2 = q[2]; }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {      // C <= 16; the same tree in every CTA: identical bits everywhere
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (lane == 0) { sc[3 * nw + 3] = a0; sc[3 * nw + 4] = a1; sc[3 * nw + 5] = a2; }
     }
-    out[0] = s0; out[1] = s1; out[2] = s2;
+    __syncthreads();
+    out[0] = sc[3 * nw + 3]; out[1] = sc[3 * nw + 4]; out[2] = sc[3 * nw + 5];
   }
   template <int DIR>
   __device__ __forceinline__ void cyc_scan(double A, double c0, double c1, double& in0, double& in1) {
@@ -560,18 +597,31 @@ struct GpuExecClusterT {
     if (threadIdx.x == 0) { sc[3 * nw] = tA; sc[3 * nw + 1] = t0; sc[3 * nw + 2] = t1; }
     cg::cluster_group cl = cg::this_cluster();
     sync();
-    // compose the CTA aggregates in scan order
-    double gA = 1.0, g0_ = 0.0, g1_ = 0.0, pA = 1.0, p0 = 0.0, p1 = 0.0;
-    for (unsigned k = 0; k < C; ++k) {
-      const unsigned cc = (DIR > 0) ? k : C - 1 - k;
-      if (cc == rank) { pA = gA; p0 = g0_; p1 = g1_; }
-      const double* q = cl.map_shared_rank(sc + 3 * nw, cc);
-      const double a = q[0];
-      g0_ = a * g0_ + q[1]; g1_ = a * g1_ + q[2]; gA = a * gA;
+    // ONE warp composes the C CTA aggregates (lane b <- the b-th CTA in scan order, through DSMEM; Kogge-Stone over the
+    // lanes), closes the ring and leaves the value entering THIS CTA in the CTA's own shared memory
+    if (w == 0) {
+      double mA = 1.0, m0 = 0.0, m1 = 0.0;
+      if ((unsigned)lane < C) {
+        const unsigned cc = (DIR > 0) ? (unsigned)lane : C - 1 - (unsigned)lane;
+        const double* q = cl.map_shared_rank(sc + 3 * nw, cc);
+        mA = q[0]; m0 = q[1]; m1 = q[2];
+      }
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        const double Ao = __shfl_up_sync(0xffffffffu, mA, o), c0o = __shfl_up_sync(0xffffffffu, m0, o), c1o = __shfl_up_sync(0xffffffffu, m1, o);
+        if (lane >= o) { m0 = mA * c0o + m0; m1 = mA * c1o + m1; mA = mA * Ao; }
+      }
+      // inclusive composition up to lane b in (mA, m0, m1); the whole ring = lane C-1; exclusive prefix = lane b-1
+      const double gA = __shfl_sync(0xffffffffu, mA, (int)C - 1), g0_ = __shfl_sync(0xffffffffu, m0, (int)C - 1), g1_ = __shfl_sync(0xffffffffu, m1, (int)C - 1);
+      double pA = __shfl_up_sync(0xffffffffu, mA, 1), p0 = __shfl_up_sync(0xffffffffu, m0, 1), p1 = __shfl_up_sync(0xffffffffu, m1, 1);
+      if (lane == 0) { pA = 1.0; p0 = 0.0; p1 = 0.0; }
+      const double inv = PK_RCP(1.0 - gA);
+      const double x0 = g0_ * inv, x1 = g1_ * inv;          // entering the first thread of the ring
+      const int mine = (DIR > 0) ? (int)rank : (int)C - 1 - (int)rank;
+      if (lane == mine) { sc[3 * nw + 3] = pA * x0 + p0; sc[3 * nw + 4] = pA * x1 + p1; }      // entering my CTA
     }
-    const double inv = PK_RCP(1.0 - gA);
-    const double x0 = g0_ * inv, x1 = g1_ * inv;          // entering the first thread of the ring
-    const double y0 = pA * x0 + p0, y1 = pA * x1 + p1;    // entering my CTA
+    __syncthreads();
+    const double y0 = sc[3 * nw + 3], y1 = sc[3 * nw + 4];
     const double w0 = eA * y0 + e0, w1 = eA * y1 + e1;    // entering my warp
     const double o0 = A * w0 + c0, o1 = A * w1 + c1;      // leaving my thread
     double q0, q1;
@@ -611,7 +661,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   else if (PK_NOISE_OF(MODE) == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
   sh.xb = nxt; nxt += XB_SLOTS_PP * Tc;
-  double* red = nxt; nxt += 2 * (3 * (Tc >> 5) + 3);
+  double* red = nxt; nxt += cluster_red_doubles(Tc);
   sh.dW = nxt;
 
   const int r = blockIdx.x / C;

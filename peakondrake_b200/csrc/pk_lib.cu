@@ -411,8 +411,8 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     while (C > 16 && Tc < 512) { Tc *= 2; C /= 2; }
     int lg = 0; while ((1 << lg) < Tc) ++lg;
     const size_t sm = cfg->scheme == 1
-        ? sizeof(double) * ((size_t)UW_SLOTS * Tc + 2 * (3 * (Tc / 32) + 3) + (p.nxi > 0 ? p.nxi : 1) + 2)
-        : sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)XB_SLOTS_PP * Tc + 2 * (3 * (Tc / 32) + 3) + (p.nxi > 0 ? p.nxi : 1));
+        ? sizeof(double) * ((size_t)UW_SLOTS * Tc + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1) + 2)
+        : sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)XB_SLOTS_PP * Tc + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1));
     if (C < 2 || C > 16 || (C & (C - 1)) || Tc < 32 || C * Tc != p.T || sm > 227 * 1024) {
       const int ne = p.ne; delete c;
       return fail(nullptr, "pk_create: no cluster layout for ne=%d (threads %d)", ne, p.T);
@@ -891,5 +891,7 @@ ckern_t pk_pick_cluster_kernel_m5(int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m6(int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m7(int, int, int) { return nullptr; }
 ckern_t pk_pick_cluster_kernel_m9(int, int, int) { return nullptr; }
+#ifndef PK_VARIANT_WITH_M10
 ckern_t pk_pick_cluster_kernel_m10(int, int, int) { return nullptr; }
+#endif
 #endif

@@ -52,12 +52,18 @@ struct Params {
   double inv1mrn;         // 1 / (1 - rho^ne): cyclic closure of the Helmholtz scans
   double cert_k, cert_floor2;   // convergence certificate of the Newton iteration (run_steps); cert_k = 0 disables it
   double ih2;             // 2 / h   (inverse DG1 element mass matrix M_e^-1 = (2/h) [[2,-1],[-1,2]])
+  double ih;              // RN(1 / h): reciprocal for the exact quotient x / h of the fused diagnostics (div_h)
   double c1k, c2k, h6k, a26k;   // c1, c2, h6, a26 times ikappa (Helmholtz right-hand sides pre-divided by kappa)
   double rtol, atol, stol, divtol;  // PETSc SNES defaults 1e-8, 1e-50, 1e-8, 1e4
   double rtol2, atol2, stol2, divtol2;  // their squares (fill_constants): the tests compare squared norms
   double sdt;             // sqrt(dt / nupd)
   double xi_const;        // NOISE_SCALAR: the (spatially constant) value of xi_0, 0 if nxi==0
 };
+
+// reduction / scan scratch of the thread-block-cluster executors: two halves (ping-pong) of 3 values per warp, the CTA's
+// aggregate (3) and the cluster-wide result broadcast inside the CTA (up to 3)
+PK_HD int cluster_red_half(int Tc) { return 3 * (Tc >> 5) + 6; }
+PK_HD int cluster_red_doubles(int Tc) { return 2 * cluster_red_half(Tc); }
 
 // chunk geometry
 PK_HD int chunk_rows(const Params& p, int t) { return t < p.rem ? p.M : p.M - 1; }
@@ -114,7 +120,7 @@ static inline void fill_constants(Params& p) {
   // |R(x + d)|_2 <= cert_k |d|_2^2 once R(x) + J d = 0 (see run_steps); evaluation noise of R: ~1.5e-14 h sqrt(ne + |w|^2)
   p.cert_k = p.dt * (2.4 + 4.0 * h / 3.0 + 2.0 * a2 / h) * 0.25;
   p.cert_floor2 = (1.5e-14 * h) * (1.5e-14 * h);
-  p.ih2 = 2.0 / h;
+  p.ih2 = 2.0 / h; p.ih = 1.0 / h;
   p.c1k = p.c1 * p.ikappa; p.c2k = p.c2 * p.ikappa; p.h6k = p.h6 * p.ikappa; p.a26k = p.a26 * p.ikappa;
   p.sdt = std::sqrt(p.dt / (p.nupd > 0 ? p.nupd : 1));
   p.rtol2 = p.rtol * p.rtol; p.atol2 = p.atol * p.atol; p.stol2 = p.stol * p.stol; p.divtol2 = p.divtol * p.divtol;

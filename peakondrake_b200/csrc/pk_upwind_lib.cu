@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(TB, 1) pk_upwind_cluster_kernel(const __grid_c
   sh.U0 = sh.U1 = sh.F = sh.G = sh.X = sh.Xx = sh.Xxx = nullptr;
   sh.xb = smem;
   double* red = smem + UW_SLOTS * Tc;
-  sh.dW = red + 2 * (3 * (Tc >> 5) + 3);
+  sh.dW = red + cluster_red_doubles(Tc);
   int* flag = (int*)(sh.dW + (p.nxi > 0 ? p.nxi : 1));
   if (threadIdx.x == 0) *flag = 0;
   typedef UpwindThread<M, XARR, 0> Th;

@@ -13,6 +13,9 @@ flags = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-li
          '-diag-suppress', '128', '-DPK_PROFILE_SINGLE_M'] + extra
 jobs = [('pk_lib.cu', 'pk_lib.o', []), ('pk_upwind_lib.cu', 'pk_upwind_lib.o', []), ('pk_aux_lib.cu', 'pk_aux_lib.o', []),
         ('pk_kernels_m.cu', 'pk_kernels_m8.o', ['-DPK_M=8'])]
+if os.environ.get('PK_WITH_M10'):      # the wide-chunk cluster kernels of BASELINE config 5
+    jobs.append(('pk_kernels_m.cu', 'pk_kernels_m10.o', ['-DPK_M=10']))
+    flags.append('-DPK_VARIANT_WITH_M10')
 procs = [subprocess.Popen(['/usr/local/cuda/bin/nvcc'] + flags + x + ['-c', '-o', os.path.join(bd, o), os.path.join(d, src)])
          for src, o, x in jobs]
 assert all(p.wait() == 0 for p in procs)

@@ -24,6 +24,17 @@ out = {'lib': os.environ.get('PK_LIB_PATH', 'default')}
 out['C2_median'], out['C2_best'] = run(1000, 1024, 50, 'sines', 4, 1e-3, 'proper_peak')
 if os.environ.get('WITH_C4', '1') == '1':
     out['C4_median'], out['C4_best'] = run(16384, 128, 10, 'constant', 1, 5e-4, 'new_peak', 1 / 6, reps=4)
+    out['C4_R1024_median'], _ = run(16384, 1024, 10, 'constant', 1, 5e-4, 'new_peak', 1 / 6, reps=3)
+    out['C5_R1024_median'], _ = run(20000, 1024, 10, 'constant', 1, 1e-3, 'periodic_peakon', reps=3)
+    # fused per-step dumps (pk_step_dump) on the C4 mesh
+    eng = EnsembleIntegrator(16384, 40.0, 5e-4, 1024, num_Xis=1, Xi_family='constant', sigma=0.2, seed=3)
+    eng.set_state(build_initial_u(16384, 40.0, 'new_peak', peak_width=1 / 6))
+    eng.step_dump(10, 1, suite=True); torch.cuda.synchronize()
+    ms = []
+    for _ in range(3):
+        eng.step_dump(10, 1, suite=True); ms.append(eng.last_kernel_ms())
+    out['C4_R1024_dump_every_step'] = 1024 * 10 / sorted(ms)[1] * 1e3
+    eng.close()
 print(json.dumps(out), flush=True)
 ''' % ROOT
 for name in sys.argv[1:]:

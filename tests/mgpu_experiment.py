@@ -74,7 +74,7 @@ def main():
                     else:
                         assert np.array_equal(a[k], b[k], equal_nan=True), (code, k)
             res['compared'] = True
-            res['c3_ens_count'] = [float(x) for x in b['ens_count']]
+            res['c3_ens_count'] = [float(x) for x in out.read_data_file('results/par_c3/data.nc')['ens_count']]
         print(json.dumps(res), flush=True)
     dist.destroy_process_group()
 
