@@ -382,3 +382,24 @@ extern "C" int pk_emu_mu(const double* u, const double* du, const double* x, int
   return mu_serial(u, du, x, n, Ld, old4, alt4);
 }
 extern "C" double pk_emu_pairwise_sum(const double* a, int n) { return np_pairwise_sum(a, n); }
+
+// ---- closed-form element integrals of pk_core.h (CellC) for one cell, for the symbolic check (tests/test_symbolic.py) ----
+// A7, B7 = NodeS (a, v, w, F, G, x, y) of the left / right node; out[18] = N1L N1R fL fR gL gR | dN1L0 dN1L1 dN1R0 dN1R1 |
+// dfL0 dfL1 dfR0 dfR1 | dgL0 dgL1 dgR0 dgR1, as the kernel holds them (f, g: HALF the cell contributions; derivatives
+// pre-scaled: N1'/2, f'/4, g'/2).  full != 0: compute_full (values from the Jacobian entries), else compute_res + compute_jac.
+extern "C" void pk_emu_cell(double h, double dt, double alphasq, const double* A7, const double* B7, int full, double* out) {
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.ne = 8; p.h = h; p.dt = dt; p.alphasq = alphasq; p.mode = NOISE_FULL; p.nupd = 1;
+  p.rtol = 1e-8; p.atol = 1e-50; p.stol = 1e-8; p.divtol = 1e4;
+  fill_constants(p);
+  NodeS A, B;
+  A.a = A7[0]; A.v = A7[1]; A.w = A7[2]; A.F = A7[3]; A.G = A7[4]; A.x = A7[5]; A.y = A7[6];
+  B.a = B7[0]; B.v = B7[1]; B.w = B7[2]; B.F = B7[3]; B.G = B7[4]; B.x = B7[5]; B.y = B7[6];
+  CellC<NOISE_FULL> c;
+  if (full) c.compute_full(p, A, B);
+  else { c.compute_jac(p, A, B); c.compute_res(p, A, B); }
+  const double v[18] = {c.N1L, c.N1R, c.fL, c.fR, c.gL, c.gR, c.dN1L0, c.dN1L1, c.dN1R0, c.dN1R1,
+                        c.dfL0, c.dfL1, c.dfR0, c.dfR1, c.dgL0, c.dgL1, c.dgR0, c.dgR1};
+  for (int i = 0; i < 18; ++i) out[i] = v[i];
+}
