@@ -312,7 +312,7 @@ def extra_configs(rank, world, local, peak):
         note='8192 realisations, ne=20000, periodic_peakon, constant Xi sigma=1, dt=1e-3 with nXi_updates=1000 (the '
              'dt-sweep member in the middle of peakon_strong_dt.py), in-kernel Philox sub-updates')
     # upwind / ssprk3 (the genuinely HBM-shaped scheme), ne=1000, 4 sines
-    leg('upwind_ssprk3', 1000, 4096, 1e-3, 'proper_peak', 'sines', 4, 0.02, 3, 50, scheme='upwind', b_alg=32 * 1000 + 8 * 4,
+    leg('upwind_ssprk3', 1000, 4096, 1e-3, 'proper_peak', 'sines', 4, 0.02, 20, 50, scheme='upwind', b_alg=32 * 1000 + 8 * 4,
         note='upwind/ssprk3 (equations.py:28-61), ne=1000, 4 sines sigma=0.02, 4096 realisations, 50 steps per launch')
     return out
 

@@ -202,6 +202,7 @@ extern "C" int pk_step_upwind(pk_ctx* c, int32_t nsteps, double* m, double* u, c
   a.m = m; a.u = u; a.xi = c->xi; a.dW_in = dW_in; a.dW_out = dW_out; a.fail_step = fail_step;
   a.R = c->cfg.R; a.step0 = (int)c->step; a.nsteps = nsteps; a.rid0 = c->cfg.rid_offset; a.seed = c->cfg.seed;
   cudaStream_t st = (cudaStream_t)stream;
+  { const int k = (int)(c->evn % 64); c->ev0 = c->evr[0][k]; c->ev1 = c->evr[1][k]; ++c->evn; }     // event ring (pk_step_kernel_ms_since)
   CK(c, cudaEventRecord(c->ev0, st));
   if (c->cluster > 1) {
     cudaLaunchConfig_t lc = {};
