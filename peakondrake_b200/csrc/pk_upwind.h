@@ -202,7 +202,8 @@ struct UpwindThread {
   }
 };
 
-template <int M, int XARR, int TT, class Exec, class Th, class SH>
+// COOP: warp-shared Philox sub-updates compiled in (nXi_updates >= PK_COOP_NUPD); the lean instantiation serves the rest
+template <int M, int XARR, int TT, class Exec, class Th, class SH, bool COOP = false>
 PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const UpwindIO& io, int* flag) {
   int failed = io.fail_step[io.r];
   DrawIO dio;
@@ -210,11 +211,11 @@ PK_HD void run_upwind_steps(Exec& ex, const Params& p, const SH& sh, const Upwin
   dio.nsteps = io.nsteps; dio.rid = io.rid; dio.seed = io.seed;
   ex.each([&](Th& th) { th.load(p, io); });
   ex.one([&]() { *flag = 0; });
-  ex.each_tid([&](Th& th, int tid, int nth, bool, int, int) { th.dw_slot = draw_slot(p, tid); if (dio.per == 0) draw_begin(p, dio, nth); });
+  ex.each_tid([&](Th& th, int tid, int nth, bool, int, int) { th.dw_slot = draw_slot(p, tid); if (dio.per == 0) draw_begin<COOP>(p, dio, nth); });
   for (int n = 0; n < io.nsteps; ++n) {
     draw_advance(dio, n);
     ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
-      draw_step(p, sh, dio, n, tid, nth, leader, th.dw_hold, th.dw_slot);
+      draw_step<COOP>(p, sh, dio, n, tid, nth, leader, th.dw_hold, th.dw_slot);
     });
     ex.sync();
     if (failed >= 0) continue;

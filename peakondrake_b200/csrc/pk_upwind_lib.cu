@@ -96,7 +96,7 @@ struct UpwindArgs {
   unsigned long long seed;
 };
 
-template <int M, int XARR, int TB, int MINB, int TT>
+template <int M, int XARR, int TB, int MINB, int TT, bool COOP = false>
 __global__ void __launch_bounds__(TB, MINB) pk_upwind_kernel(const __grid_constant__ Params p, const __grid_constant__ UpwindArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int Tn = TT > 0 ? TT : p.T;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_upwind_kernel(const __grid_consta
   io.m = a.m; io.u = a.u; io.dW_in = a.dW_in; io.dW_out = a.dW_out; io.xi = a.xi;
   io.R = a.R; io.r = blockIdx.x; io.rid = a.rid0 + blockIdx.x; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step;
-  run_upwind_steps<M, XARR, TT, UwExec<Th, (TB > 32), TT>, Th>(ex, p, sh, io, flag);
+  run_upwind_steps<M, XARR, TT, UwExec<Th, (TB > 32), TT>, Th, Shared, COOP>(ex, p, sh, io, flag);
 }
 
 // Thread-block-cluster variant (meshes beyond 512 threads: ne > 4096): one realisation per cluster of C CTAs.  The state
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(TB, 1) pk_upwind_cluster_kernel(const __grid_c
   io.R = a.R; io.r = r; io.rid = a.rid0 + r; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step;
   cluster.sync();
-  run_upwind_steps<M, XARR, 0, GpuExecClusterT<Th>, Th>(ex, p, sh, io, flag);
+  run_upwind_steps<M, XARR, 0, GpuExecClusterT<Th>, Th, SharedCluster, true>(ex, p, sh, io, flag);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
 }
 
@@ -171,22 +171,26 @@ static uckern_t pick_ucluster_kernel(const Params& p, int Tc) {
 }
 const void* pk_upwind_cluster_kernel_ptr(const Params& p, int Tc) { return (const void*)pick_ucluster_kernel(p, Tc); }
 
-template <int M, int XARR> static ukern_t pick_utb(int block, int T) {
-  if (T < 32) return pk_upwind_kernel<M, XARR, 32, 1, 0>;
-  if (T == 128) return pk_upwind_kernel<M, XARR, 128, 4, 128>;
-  if (block <= 128) return pk_upwind_kernel<M, XARR, 128, 4, 0>;
-  if (block <= 256) return pk_upwind_kernel<M, XARR, 256, 2, 256>;
-  return pk_upwind_kernel<M, XARR, 512, 1, 512>;
+template <int M, int XARR, bool COOP> static ukern_t pick_utb(int block, int T) {
+  if (T < 32) return pk_upwind_kernel<M, XARR, 32, 1, 0, COOP>;
+  if (T == 128) return pk_upwind_kernel<M, XARR, 128, 4, 128, COOP>;
+  if (block <= 128) return pk_upwind_kernel<M, XARR, 128, 4, 0, COOP>;
+  if (block <= 256) return pk_upwind_kernel<M, XARR, 256, 2, 256, COOP>;
+  return pk_upwind_kernel<M, XARR, 512, 1, 512, COOP>;
 }
-static ukern_t pick_ukernel(const Params& p, int block) {
+template <bool COOP> static ukern_t pick_ukernel_t(const Params& p, int block) {
   const bool x = (p.mode != NOISE_SCALAR);
   switch (p.M) {
-    case 5: return x ? pick_utb<5, 1>(block, p.T) : pick_utb<5, 0>(block, p.T);
-    case 6: return x ? pick_utb<6, 1>(block, p.T) : pick_utb<6, 0>(block, p.T);
-    case 7: return x ? pick_utb<7, 1>(block, p.T) : pick_utb<7, 0>(block, p.T);
-    case 8: return x ? pick_utb<8, 1>(block, p.T) : pick_utb<8, 0>(block, p.T);
+    case 5: return x ? pick_utb<5, 1, COOP>(block, p.T) : pick_utb<5, 0, COOP>(block, p.T);
+    case 6: return x ? pick_utb<6, 1, COOP>(block, p.T) : pick_utb<6, 0, COOP>(block, p.T);
+    case 7: return x ? pick_utb<7, 1, COOP>(block, p.T) : pick_utb<7, 0, COOP>(block, p.T);
+    case 8: return x ? pick_utb<8, 1, COOP>(block, p.T) : pick_utb<8, 0, COOP>(block, p.T);
   }
   return nullptr;
+}
+// coop: this launch draws Philox increments with many sub-updates (shared by the lanes of a warp)
+static ukern_t pick_ukernel(const Params& p, int block, bool coop) {
+  return coop ? pick_ukernel_t<true>(p, block) : pick_ukernel_t<false>(p, block);
 }
 
 extern "C" int pk_step_upwind(pk_ctx* c, int32_t nsteps, double* m, double* u, const double* dW_in,
@@ -214,7 +218,7 @@ extern "C" int pk_step_upwind(pk_ctx* c, int32_t nsteps, double* m, double* u, c
     lc.attrs = at; lc.numAttrs = 1;
     CK(c, cudaLaunchKernelEx(&lc, pick_ucluster_kernel(c->p, c->block), c->p, a, c->lgTc));
   } else {
-    ukern_t k = pick_ukernel(c->p, c->block);
+    ukern_t k = pick_ukernel(c->p, c->block, !dW_in && c->p.nupd >= PK_COOP_NUPD);
     k<<<c->cfg.R, c->block, c->smem, st>>>(c->p, a);
   }
   ++c->nlaunch;

@@ -255,14 +255,14 @@ DTS_C5 = [1e-2, 5e-3, 2.5e-3, 1e-3, 5e-4, 2.5e-4, 1e-4]
 def test_c5_configuration_strong_dt_sweep(tmp_path, monkeypatch, nocert):
     """BASELINE config 5 at its parameters (peakon_strong_dt.py:9-37, true_peakon_sde.py:5-30): ne=20000, periodic
     peakon, constant Xi sigma=1, periodic=True, tmax=0.1; the "true" path is the peakon SDE at dt=1e-6 per seed
-    (1e5 Ito-Euler steps on the device), every dt of the sweep runs with nXi_updates=int(dt/1e-6) -- i.e. on the SAME
+    (1e5 Ito-Euler steps on the device, 64 seeds), every dt of the sweep runs with nXi_updates=int(dt/1e-6) -- i.e. on the SAME
     Brownian path -- and reports u_error_with_sde at ne=20000.  Every dt is checked against the oracle on its first
     steps (the oracle needs ~0.3 s per step at this mesh); the errors of the whole sweep give the strong order."""
     from peakondrake_b200 import experiment, outputting as out
     monkeypatch.chdir(tmp_path)
     monkeypatch.setenv('PK_NO_CERTIFICATE', nocert)
     ne, Ld, tmax, dt_true = 20000, 40., 0.1, 1e-6
-    seeds = list(range(8))
+    seeds = list(range(64))
     common = dict(resolutions=ne, sigmas=1.0, seeds=seeds, schemes='hydrodynamic', timesteppings='midpoint',
                   ics='periodic_peakon', num_Xis=1, Xi_family='constant', alphasq=1.0, c0=0., gamma=0.,
                   allow_fail=True, periodic=True)
@@ -270,7 +270,7 @@ def test_c5_configuration_strong_dt_sweep(tmp_path, monkeypatch, nocert):
     experiment('true_peakon_data', Ld, tmax, dts=dt_true, diagnostics=['l2_u'], fields_to_output=[], ndump=nt,
                field_ndump=nt, peakon_equations=True, only_peakons=True, **common)
     tp = out.read_data_file('results/true_peakon_data/data.nc')
-    assert tp['p'].shape == (2, 8) and (tp['p'][1] == tp['p'][0]).all()          # constant Xi: dp = 0
+    assert tp['p'].shape == (2, 64) and (tp['p'][1] == tp['p'][0]).all()          # constant Xi: dp = 0
     # the true path is q0 + c t + sigma W(t) up to the Euler sum's rounding: check against the host stream
     from peakondrake_b200 import draw_dW
     for k, s in enumerate(seeds[:2]):
@@ -286,7 +286,7 @@ def test_c5_configuration_strong_dt_sweep(tmp_path, monkeypatch, nocert):
                    fields_to_output=['u_sde', 'u_sde_weak'], ndump=nst, field_ndump=-1,
                    true_peakon_data='true_peakon_data', nXi_updates=nupd, **common)
         s = out.read_data_file('results/strong_%d/data.nc' % i)
-        assert s['u_error_with_sde'].shape == (2, 8) and np.isfinite(s['u_error_with_sde']).all()
+        assert s['u_error_with_sde'].shape == (2, 64) and np.isfinite(s['u_error_with_sde']).all()
         assert np.array_equal(s['u_error_with_sde'], s['u_error_weak'])
         errs.append(s['u_error_with_sde'][1])
         # oracle on the first steps of this dt, same Brownian path (coarse increments = sums of the fine ones)
@@ -294,7 +294,7 @@ def test_c5_configuration_strong_dt_sweep(tmp_path, monkeypatch, nocert):
         experiment('short_%d' % i, Ld, ncheck * dt, dts=dt, diagnostics=['u_field', 'q_pde'], ndump=ncheck,
                    nXi_updates=nupd, **common)
         sh = out.read_data_file('results/short_%d/data.nc' % i)
-        for k in (0, 7):
+        for k in (0, 63):
             dW = O.reference_dW(seeds[k], ncheck, 1, dt, nupd)
             ref = O.run(ne, Ld, dt, ncheck, u0, dW, tabs)
             assert rel(sh['u_field'][1, k], ref['u']) <= TOL, (dt, k, rel(sh['u_field'][1, k], ref['u']))
