@@ -252,8 +252,9 @@ def extra_configs(rank, world, local, peak):
         if per_launch is not None:
             per_launch(ctx, True)
         def advance():
-            if dump_every:      # dump diagnostics + peakon suite fused into the step kernel, D2H of the tables per launch
-                _, dg, di, sv, si = eng.step_dump(steps_per_launch, dump_every, suite=True)
+            if dump_every:      # per-dump state snapshots inside the launch + ONE batched diagnostics / peakon-suite call,
+                                # D2H of the [dumps, R, 14+4+2+3] tables per launch (what run_batch does)
+                _, dg, di, sv, si, _, _ = eng.step_snap(steps_per_launch, dump_every, suite=True)
                 ctx['host'] = [t.to('cpu', non_blocking=True) for t in (dg, di, sv, si)]
             else:
                 eng.step(steps_per_launch)
@@ -305,8 +306,8 @@ def extra_configs(rank, world, local, peak):
     leg('C4', 16384, 4096, 5e-4, 'new_peak', 'constant', 1, 0.2, 3, 10, peak_width=1 / 6, dump_every=1,
         b_alg=16 * 16384 + 8 + 8 * 18,
         note='4096 realisations, ne=16384, new_peak width 1/6, constant Xi sigma=0.2, dt=5e-4, min_du / max_du / '
-             'max_jump_local / peakon_suite EVERY step, fused into the step kernel (pk_step_dump: one launch per 10 steps, '
-             'the [10, R, 14+4+2+3] tables copied to the host per launch)')
+             'max_jump_local / peakon_suite EVERY step (pk_step_snap: one step launch per 10 steps with a state snapshot per '
+             'step, one batched pk_diagnostics_rows + pk_peakon_suite_rows over the 10 x R snapshots, tables copied to the host)')
     # C5: strong-convergence sweep shard, ne=20000, sigma=1 (the dt=1e-3 member, nXi_updates=1000)
     leg('C5', 20000, 8192, 1e-3, 'periodic_peakon', 'constant', 1, 1.0, 2, 20, nupd=1000,
         note='8192 realisations, ne=20000, periodic_peakon, constant Xi sigma=1, dt=1e-3 with nXi_updates=1000 (the '

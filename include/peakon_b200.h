@@ -130,6 +130,23 @@ int pk_step_dump(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF,
                  int32_t* its_total, int32_t dump_every, double* diag_out, int32_t* diag_idx,
                  double* suite_vals, int32_t* suite_ids, void* stream);
 
+/* pk_step with state SNAPSHOTS for the dumps: after every snap_every-th step of the launch the kernel stores u (natural
+ * node order) into snap_u[d] and the realisation's failure state into snap_flag[d] (-1 healthy, else the failing step),
+ * d = (n+1)/snap_every - 1.  The dump diagnostics of ALL dumps of the launch are then one batched, HBM-streaming call of
+ * pk_diagnostics_rows / pk_peakon_suite_rows over the nsnap*R rows -- cheaper than evaluating reductions inside the
+ * (latency-bound) step kernel: a dump costs the step kernel ~1 % instead of ~11 %, for
+ * nsnap*R*ne*8 bytes of device memory.   snap_u [nsteps/snap_every, R, ne], snap_flag [nsteps/snap_every, R]. */
+int pk_step_snap(pk_ctx* ctx, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                 const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                 int32_t* its_total, int32_t snap_every, double* snap_u, int32_t* snap_flag, void* stream);
+
+/* pk_diagnostics / pk_peakon_suite over an arbitrary number of rows (e.g. the snapshots of pk_step_snap): u [nrows, ne],
+ * pq [nrows, 2] or NULL, out [nrows, PK_NDIAG], idx [nrows, PK_NIDX], row_flag [nrows] or NULL (>= 0: NaN row). */
+int pk_diagnostics_rows(pk_ctx* ctx, const double* u, int32_t nrows, const double* pq, int32_t periodic, int32_t want_m,
+                        double* out, int32_t* idx, double* du_out, const int32_t* row_flag, void* stream);
+int pk_peakon_suite_rows(pk_ctx* ctx, const double* u, int32_t nrows, const int32_t* idx, const int32_t* row_flag,
+                         double* vals, int32_t* ids, void* stream);
+
 /* Same, with HOST buffers: copies state (and dW_in) to internal device buffers, steps, copies the
  * state, dW_out and the counters back, and synchronises (the realisations go through a 2-chunk
  * H2D / kernel / D2H pipeline on internal streams; pin the host buffers).  This is the call a host

@@ -19,7 +19,7 @@ I_ARGMAX_DU, I_ARGMIN_DU, I_ARGMAX_U, I_ARGMAX_JUMP, NIDX = range(5)
 
 EXPORTS = ['pk_create', 'pk_destroy', 'pk_last_error', 'pk_set_tables', 'pk_step', 'pk_step_host',
            'pk_set_step_counter', 'pk_get_step_counter', 'pk_diagnostics', 'pk_get_layout',
-           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite', 'pk_step_upwind', 'pk_diagnostics_dg1', 'pk_get_work_split', 'pk_reset_warm_start', 'pk_mu', 'pk_step_kernel_ms_since', 'pk_ensemble_scalars', 'pk_peakon_sde_step', 'pk_du_smooth_loc', 'pk_launch_count', 'pk_step_dump']
+           'pk_last_step_kernel_ms', 'pk_ensemble_stats', 'pk_peakon_suite', 'pk_step_upwind', 'pk_diagnostics_dg1', 'pk_get_work_split', 'pk_reset_warm_start', 'pk_mu', 'pk_step_kernel_ms_since', 'pk_ensemble_scalars', 'pk_peakon_sde_step', 'pk_du_smooth_loc', 'pk_launch_count', 'pk_step_dump', 'pk_step_snap', 'pk_diagnostics_rows', 'pk_peakon_suite_rows']
 
 
 class PkConfig(ctypes.Structure):
@@ -93,6 +93,12 @@ def load():
     lib.pk_du_smooth_loc.argtypes = [vp, dp, ip, dp, dp, ip, dp, vp]
     lib.pk_step_dump.restype = ctypes.c_int
     lib.pk_step_dump.argtypes = [vp, ctypes.c_int32, dp, dp, dp, dp, dp, dp, ip, ip, ip, ctypes.c_int32, dp, ip, dp, ip, vp]
+    lib.pk_step_snap.restype = ctypes.c_int
+    lib.pk_step_snap.argtypes = [vp, ctypes.c_int32, dp, dp, dp, dp, dp, dp, ip, ip, ip, ctypes.c_int32, dp, ip, vp]
+    lib.pk_diagnostics_rows.restype = ctypes.c_int
+    lib.pk_diagnostics_rows.argtypes = [vp, dp, ctypes.c_int32, dp, ctypes.c_int32, ctypes.c_int32, dp, ip, dp, ip, vp]
+    lib.pk_peakon_suite_rows.restype = ctypes.c_int
+    lib.pk_peakon_suite_rows.argtypes = [vp, dp, ctypes.c_int32, ip, ip, dp, ip, vp]
     lib.pk_launch_count.restype = ctypes.c_int64
     lib.pk_launch_count.argtypes = [vp]
     _lib = lib

@@ -20,4 +20,6 @@ struct StepArgs {
   // fused dumps (pk_step_dump): see StepIO in pk_core.h
   int diag_every;
   double* diag_out; int* diag_idx; double* suite_vals; int* suite_ids;
+  // state snapshots (pk_step_snap)
+  int snap_every; double* snap_u; int* snap_flag;
 };

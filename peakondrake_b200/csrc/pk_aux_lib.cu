@@ -266,7 +266,7 @@ extern "C" int pk_du_smooth_loc(pk_ctx* c, const double* u, const int32_t* fail_
   if (!u || !consts || !out || !idx) return fail(c, "pk_du_smooth_loc: null pointer");
   CK(c, cudaSetDevice(c->cfg.device));
   const int ne = c->p.ne, R = c->cfg.R;
-  if (!c->d_scratch) CK(c, cudaMalloc(&c->d_scratch, sizeof(double) * 2 * (size_t)R * ne));
+  if (pk_ensure_scratch(c, 2 * (size_t)R * ne)) return -1;
   SmoothArgs a;
   a.u = u; a.fail_step = fail_step; a.out = out; a.idx = idx; a.scratch = c->d_scratch; a.field = field;
   a.ne = ne; a.h = c->p.h;

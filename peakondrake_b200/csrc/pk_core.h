@@ -1477,6 +1477,12 @@ struct StepIO {
   int* diag_idx = nullptr;        // [ndumps, R, DIAG_NIDX]
   double* suite_vals = nullptr;   // [ndumps, R, 2] or null
   int* suite_ids = nullptr;       // [ndumps, R, 3] or null
+  // state snapshots: after every snap_every-th step of the launch, u goes to row d = (n+1)/snap_every - 1 of snap_u
+  // (natural node order) and the realisation's fail state to snap_flag (-1 healthy, else the failing step): the dump
+  // diagnostics are then computed for all dumps of the launch by ONE batched streaming kernel (pk_diagnostics_rows)
+  int snap_every = 0;
+  double* snap_u = nullptr;       // [nsnap, R, ne]
+  int* snap_flag = nullptr;       // [nsnap, R]
 };
 
 // column layout of the fused dump == include/peakon_b200.h (PK_D_*, PK_I_*); static_assert'ed in pk_lib.cu
@@ -1489,6 +1495,17 @@ PK_HD double nan_quiet() {
 #else
   return std::nan("");
 #endif
+}
+
+// Snapshot of u (natural node order) for the batched dump diagnostics: every block stores the mesh rows it owns.
+template <int M, int TT, class Exec, class Th, class SH>
+PK_HD void snapshot(Exec& ex, const Params& p, const SH& sh, const StepIO& io, int d, int failed) {
+  const long long row = (long long)d * io.R + io.r;
+  double* dst = io.snap_u + row * p.ne;
+  ex.each_tid([&](Th&, int tid, int nth, bool, int g0, int g1) {
+    for (int i = g0 + tid; i < g1; i += nth) dst[i] = sh.ld(sh.U0, row_slot_c<M, TT>(p, i));
+  });
+  ex.one([&]() { io.snap_flag[row] = failed; });
 }
 
 // One fused dump of the realisation whose state is resident in `sh` (executor collectives: argmax4sum3, minint2).
@@ -1593,6 +1610,8 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       if constexpr ((FEAT & FEAT_DUMP) != 0) {
         if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
           diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, true);
+        if (io.snap_every > 0 && (n + 1) % io.snap_every == 0)
+          snapshot<M, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.snap_every - 1, failed);
       }
       continue;
     }
@@ -1794,6 +1813,8 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     if constexpr ((FEAT & FEAT_DUMP) != 0) {
       if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
         diag_dump<M, MODE, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.diag_every - 1, failed >= 0);
+      if (io.snap_every > 0 && (n + 1) % io.snap_every == 0)
+        snapshot<M, TT, Exec, Th, SH>(ex, p, sh, io, (n + 1) / io.snap_every - 1, failed);
       ex.tick(15);
     }
   }

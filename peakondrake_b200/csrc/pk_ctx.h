@@ -28,7 +28,8 @@ struct pk_ctx {
   // internal device buffers for the *_host entry points
   bool w1_resident;    // pk_step_host keeps (u1, dF, dG) in d_state between calls (u1 = dF = dG = NULL mode)
   double* d_state; double* d_dWin; double* d_dWout; int* d_cnt; size_t dW_cap;
-  double* d_scratch;   // diagnostics scratch [R,2,ne]
+  double* d_scratch;   // diagnostics scratch [rows,2,ne] (rows = R, or the rows of a batched dump)
+  size_t scratch_cap;  // its size in doubles
   double* d_mom;       // moments partial sums [32, 2*ne]
   long long* d_prof;   // PK_PROFILE: [R,16] cycle buckets
   double* d_tab[3];    // chunk-interleaved copies of the noise tables [nxi, T*M]
@@ -44,5 +45,6 @@ extern std::string g_create_err;
 
 int pk_fail(pk_ctx* c, const char* fmt, ...);
 #define fail pk_fail
+int pk_ensure_scratch(pk_ctx* c, size_t doubles);     // (re)allocates d_scratch; 0 on success
 #define CK(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 

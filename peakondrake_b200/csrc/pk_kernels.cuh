@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
   io.R = a.R; io.seed = a.seed; io.step0 = a.step0; io.nsteps = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
+  io.snap_every = a.snap_every; io.snap_u = a.snap_u; io.snap_flag = a.snap_flag;
 
   // Persistent CTAs pull work items from a global queue: item i = `nblk` consecutive time steps
   // (block i / R) of realisation i % R.  Block-major order: the previous block of a realisation was handed
@@ -692,6 +693,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   io.n0 = 0; io.n1 = a.nsteps;
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
+  io.snap_every = a.snap_every; io.snap_u = a.snap_u; io.snap_flag = a.snap_flag;
   run_steps<M, MODE, 0, GpuExecCluster<M, MODE>, Thread<M, MODE, 0> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
 #ifdef PK_PROFILE

@@ -304,6 +304,14 @@ int pk_fail(pk_ctx* c, const char* fmt, ...) {
   return -1;
 }
 
+int pk_ensure_scratch(pk_ctx* c, size_t doubles) {
+  if (c->scratch_cap >= doubles) return 0;
+  if (c->d_scratch) { cudaStreamSynchronize(0); cudaDeviceSynchronize(); cudaFree(c->d_scratch); c->d_scratch = nullptr; c->scratch_cap = 0; }
+  if (cudaMalloc(&c->d_scratch, sizeof(double) * doubles) != cudaSuccess) return fail(c, "out of device memory for the diagnostics scratch (%zu doubles)", doubles);
+  c->scratch_cap = doubles;
+  return 0;
+}
+
 static kern_t pick_kernel(const Params& p, int block, int fs, int feat = 1) {
   // fs = 1: FS variant (factors in shared memory, rolled row loops, 2 CTAs/SM); 2: rolled assembly with register
   // factors; 0: fully unrolled register variant
@@ -436,7 +444,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
   }
   c->xi = c->xi_x = c->xi_xx = nullptr;
   c->w1_resident = false;
-  c->step = 0; c->d_state = nullptr; c->d_dWin = c->d_dWout = nullptr; c->d_cnt = nullptr; c->dW_cap = 0; c->d_scratch = nullptr; c->d_mom = nullptr; c->d_prof = nullptr; c->d_tab[0] = c->d_tab[1] = c->d_tab[2] = nullptr;
+  c->step = 0; c->d_state = nullptr; c->d_dWin = c->d_dWout = nullptr; c->d_cnt = nullptr; c->dW_cap = 0; c->d_scratch = nullptr; c->scratch_cap = 0; c->d_mom = nullptr; c->d_prof = nullptr; c->d_tab[0] = c->d_tab[1] = c->d_tab[2] = nullptr;
   c->timed = false; c->nlaunch = 0; c->h_stage = nullptr;
   cudaError_t e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, "cudaSetDevice(%d): %s", cfg->device, m.c_str()); }
@@ -561,7 +569,7 @@ static int launch_range(pk_ctx* c, StepArgs a, int nsteps, int r0, int nr, int s
     CK(c, cudaMemsetAsync(queue, 0, sizeof(int) * (size_t)(nr + 1), st));
     if (timed) CK(c, cudaEventRecord(c->ev0, st));      // time the kernel alone
     // lean time loop unless this launch dumps inside the kernel or shares Philox sub-updates within warps
-    const int feat = (a.diag_every > 0 || (!a.dW_in && c->p.nupd >= PK_COOP_NUPD)) ? 1 : 0;
+    const int feat = (a.diag_every > 0 || a.snap_every > 0 || (!a.dW_in && c->p.nupd >= PK_COOP_NUPD)) ? 1 : 0;
     kern_t k = pick_kernel(c->p, c->block, c->fs, feat);
     k<<<grid, c->block, c->smem, st>>>(c->p, a);
     ++c->nlaunch;
@@ -586,6 +594,7 @@ static int step_args(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* d
     e = getenv("PK_CLUSTER_LEADER_SEP"); if (a->part && e && atoi(e) == 1) a->part = 2; }
   a->R = c->cfg.R; a->step0 = (int)c->step; a->nsteps = nsteps; a->rid0 = c->cfg.rid_offset; a->seed = c->cfg.seed;
   a->diag_every = 0; a->diag_out = nullptr; a->diag_idx = nullptr; a->suite_vals = nullptr; a->suite_ids = nullptr;
+  a->snap_every = 0; a->snap_u = nullptr; a->snap_flag = nullptr;
   return 0;
 }
 
@@ -623,6 +632,24 @@ extern "C" int pk_step_dump(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
   if (rc) return rc;
   if (nsteps == 0) return 0;
   a.diag_every = dump_every; a.diag_out = diag_out; a.diag_idx = diag_idx; a.suite_vals = suite_vals; a.suite_ids = suite_ids;
+  CK(c, cudaSetDevice(c->cfg.device));
+  rc = launch_range(c, a, nsteps, 0, c->cfg.R, 0, (cudaStream_t)stream, true);
+  if (rc) return rc;
+  c->step += nsteps;
+  return 0;
+}
+
+extern "C" int pk_step_snap(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* dF, double* dG,
+                            const double* dW_in, double* dW_out, int32_t* fail_step, int32_t* its_last,
+                            int32_t* its_total, int32_t snap_every, double* snap_u, int32_t* snap_flag, void* stream) {
+  if (!c) return -1;
+  if (snap_every < 1 || !snap_u || !snap_flag) return fail(c, "pk_step_snap: snap_every >= 1 and the snapshot arrays are required");
+  if (c->step % snap_every != 0) return fail(c, "pk_step_snap: the step counter (%lld) must be a multiple of snap_every", c->step);
+  StepArgs a;
+  int rc = step_args(c, nsteps, u, u1, dF, dG, dW_in, dW_out, fail_step, its_last, its_total, &a);
+  if (rc) return rc;
+  if (nsteps == 0) return 0;
+  a.snap_every = snap_every; a.snap_u = snap_u; a.snap_flag = snap_flag;
   CK(c, cudaSetDevice(c->cfg.device));
   rc = launch_range(c, a, nsteps, 0, c->cfg.R, 0, (cudaStream_t)stream, true);
   if (rc) return rc;
@@ -750,17 +777,17 @@ extern "C" int pk_step_host(pk_ctx* c, int32_t nsteps, double* u, double* u1, do
   return 0;
 }
 
-extern "C" int pk_diagnostics(pk_ctx* c, const double* u, const double* pq, int32_t periodic, int32_t want_m,
-                              double* out, int32_t* idx, double* du_out, const int32_t* fail_step, void* stream) {
+extern "C" int pk_diagnostics_rows(pk_ctx* c, const double* u, int32_t nrows, const double* pq, int32_t periodic, int32_t want_m,
+                                   double* out, int32_t* idx, double* du_out, const int32_t* row_flag, void* stream) {
   if (!c) return -1;
-  if (!u || !out || !idx) return fail(c, "pk_diagnostics: null pointer");
+  if (!u || !out || !idx || nrows < 1) return fail(c, "pk_diagnostics: null pointer / no rows");
   CK(c, cudaSetDevice(c->cfg.device));
   DiagArgs a;
-  a.u = u; a.pq = pq; a.out = out; a.idx = idx; a.du_out = du_out; a.fail_step = fail_step;
+  a.u = u; a.pq = pq; a.out = out; a.idx = idx; a.du_out = du_out; a.fail_step = row_flag;
   a.ne = c->p.ne; a.periodic = periodic; a.h = c->p.h; a.alphasq = c->p.alphasq; a.Ld = c->cfg.Ld;
   a.scratch = nullptr;
   if (want_m) {
-    if (!c->d_scratch) CK(c, cudaMalloc(&c->d_scratch, sizeof(double) * 2 * (size_t)c->cfg.R * c->p.ne));
+    if (pk_ensure_scratch(c, 2 * (size_t)nrows * c->p.ne)) return -1;
     a.scratch = c->d_scratch;
   }
   // M = kappa (1 - rho S)(1 - rho S^-1), rho = -(2 - sqrt 3); circulant inverse entries
@@ -772,10 +799,16 @@ extern "C" int pk_diagnostics(pk_ctx* c, const double* u, const double* pq, int3
   const double rn = pow(rho, (double)c->p.ne);
   if (c->p.ne >= 160) { a.K = 64; a.gscale = 1.0 / (kappa * (1.0 - rho * rho)); }   // |rho|^64 ~ 2e-37
   else { a.K = -1; a.gscale = 1.0 / (kappa * (1.0 - rho * rho) * (1.0 - rn)); }
-  pk_diag_kernel<<<c->cfg.R, 256, 0, (cudaStream_t)stream>>>(a);
+  pk_diag_kernel<<<nrows, 256, 0, (cudaStream_t)stream>>>(a);
   ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
+}
+
+extern "C" int pk_diagnostics(pk_ctx* c, const double* u, const double* pq, int32_t periodic, int32_t want_m,
+                              double* out, int32_t* idx, double* du_out, const int32_t* fail_step, void* stream) {
+  if (!c) return -1;
+  return pk_diagnostics_rows(c, u, c->cfg.R, pq, periodic, want_m, out, idx, du_out, fail_step, stream);
 }
 
 extern "C" int pk_ensemble_stats(pk_ctx* c, const double* u, const int32_t* fail_step, const double* diag,
@@ -801,15 +834,21 @@ extern "C" int pk_ensemble_stats(pk_ctx* c, const double* u, const int32_t* fail
   return 0;
 }
 
-extern "C" int pk_peakon_suite(pk_ctx* c, const double* u, const int32_t* idx, const int32_t* fail_step,
-                               double* vals, int32_t* ids, void* stream) {
+extern "C" int pk_peakon_suite_rows(pk_ctx* c, const double* u, int32_t nrows, const int32_t* idx, const int32_t* row_flag,
+                                    double* vals, int32_t* ids, void* stream) {
   if (!c) return -1;
-  if (!u || !idx || !vals || !ids) return fail(c, "pk_peakon_suite: null pointer");
+  if (!u || !idx || !vals || !ids || nrows < 1) return fail(c, "pk_peakon_suite: null pointer / no rows");
   CK(c, cudaSetDevice(c->cfg.device));
-  pk_peakon_suite_kernel<<<c->cfg.R, 128, 0, (cudaStream_t)stream>>>(u, idx, fail_step, c->p.ne, c->p.h, vals, ids);
+  pk_peakon_suite_kernel<<<nrows, 128, 0, (cudaStream_t)stream>>>(u, idx, row_flag, c->p.ne, c->p.h, vals, ids);
   ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;
+}
+
+extern "C" int pk_peakon_suite(pk_ctx* c, const double* u, const int32_t* idx, const int32_t* fail_step,
+                               double* vals, int32_t* ids, void* stream) {
+  if (!c) return -1;
+  return pk_peakon_suite_rows(c, u, c->cfg.R, idx, fail_step, vals, ids, stream);
 }
 
 // ---- mu diagnostic (find_mus, outputting.py:260-370): one realisation per block, the serial reference logic run by
@@ -850,7 +889,7 @@ extern "C" int pk_mu(pk_ctx* c, const double* u, const double* x_cells, const in
   const int ne = c->p.ne, R = c->cfg.R;
   const size_t sm = sizeof(double) * 2 * (size_t)ne;
   const int use_smem = sm <= 200 * 1024;
-  if (!use_smem && !c->d_scratch) CK(c, cudaMalloc(&c->d_scratch, sizeof(double) * 2 * (size_t)R * ne));
+  if (!use_smem && pk_ensure_scratch(c, 2 * (size_t)R * ne)) return -1;
   if (use_smem && sm > 48 * 1024) CK(c, cudaFuncSetAttribute(pk_mu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   pk_mu_kernel<<<R, 128, use_smem ? sm : 0, (cudaStream_t)stream>>>(u, x_cells, fail_step, ne, c->p.h, c->cfg.Ld, use_smem,
                                                                     c->d_scratch, out, status);

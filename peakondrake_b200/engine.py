@@ -215,6 +215,49 @@ class EnsembleIntegrator(object):
         self._keep = (dW_dev, out)
         return out, diag, idx, sv, si
 
+    def step_snap(self, nsteps, snap_every, dW=None, export_dW=False, pq=None, periodic=False, want_m=False, suite=False):
+        """
+        `nsteps` steps in ONE launch; after every `snap_every`-th step the kernel stores a snapshot of u, and the dump
+        diagnostics of all snapshots are computed by one batched call (pk_step_snap + pk_diagnostics_rows
+        [+ pk_peakon_suite_rows]).  pq: None or [nsnap, R, 2] true-peakon (p, q) per dump and realisation.
+        Returns (exported dW or None, diag [nsnap, R, NDIAG], idx [nsnap, R, NIDX], suite_vals or None, suite_ids or
+        None, snap_u [nsnap, R, ne], snap_flag [nsnap, R]) as device tensors.  Midpoint schemes only.
+        """
+        if self.upwind:
+            raise NotImplementedError('step_snap is provided for the midpoint schemes')
+        dW_dev = None
+        if dW is not None and self.num_Xis > 0:
+            dW_dev = torch.as_tensor(dW, dtype=torch.float64).to(self.device).contiguous()
+            if tuple(dW_dev.shape) != (nsteps, self.R, self.num_Xis):
+                raise ValueError('dW must have shape (nsteps, R, num_Xis) = %s, got %s'
+                                 % ((nsteps, self.R, self.num_Xis), tuple(dW_dev.shape)))
+        out = None
+        if export_dW and self.num_Xis > 0:
+            out = torch.empty(nsteps, self.R, self.num_Xis, dtype=torch.float64, device=self.device)
+        ns = nsteps // snap_every
+        dev = self.device
+        snap_u = torch.empty(ns, self.R, self.ne, dtype=torch.float64, device=dev)
+        snap_flag = torch.empty(ns, self.R, dtype=torch.int32, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = self.lib.pk_step_snap(self.ctx, int(nsteps), _ptr(self.u), _ptr(self.u1), _ptr(self.dF), _ptr(self.dG),
+                                   _ptr(dW_dev), _ptr(out), _ptr(self.fail_step), _ptr(self.its_last),
+                                   _ptr(self.its_total), int(snap_every), _ptr(snap_u), _ptr(snap_flag), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        diag = torch.empty(ns, self.R, _lib.NDIAG, dtype=torch.float64, device=dev)
+        idx = torch.empty(ns, self.R, _lib.NIDX, dtype=torch.int32, device=dev)
+        pq_dev = None if pq is None else torch.as_tensor(pq, dtype=torch.float64).to(dev).contiguous()
+        rc = self.lib.pk_diagnostics_rows(self.ctx, _ptr(snap_u), ns * self.R, _ptr(pq_dev), int(bool(periodic)),
+                                          int(bool(want_m)), _ptr(diag), _ptr(idx), None, _ptr(snap_flag), stream)
+        _lib.check(self.lib, self.ctx, rc)
+        sv = si = None
+        if suite:
+            sv = torch.empty(ns, self.R, 2, dtype=torch.float64, device=dev)
+            si = torch.empty(ns, self.R, 3, dtype=torch.int32, device=dev)
+            rc = self.lib.pk_peakon_suite_rows(self.ctx, _ptr(snap_u), ns * self.R, _ptr(idx), _ptr(snap_flag), _ptr(sv), _ptr(si), stream)
+            _lib.check(self.lib, self.ctx, rc)
+        self._keep = (dW_dev, out, pq_dev)
+        return out, diag, idx, sv, si, snap_u, snap_flag
+
     def last_kernel_ms(self):
         return float(self.lib.pk_last_step_kernel_ms(self.ctx))
 

@@ -549,28 +549,42 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
             # bound the upload of one launch (imported increments travel as [steps, R, num_Xis] doubles)
             chunk = max(1, min(chunk, (1 << 26) // max(1, R * num_Xis)))
         pde_runs = not only_peakons
-        # Dumps whose diagnostics are all columns of the fused in-kernel dump (pk_step_dump) need no second kernel and
-        # no launch per dump: up to `kmax` dumps per launch, one device-to-host copy of their tables, one record each.
-        fused = (pde_runs and ndump > 0 and hasattr(eng, 'step_dump') and not eng.upwind and field_files is None
-                 and stats is None and not (want_m or want_sde or want_mean or want_smooth)
-                 and 'mu' not in diagnostics and 'u_field' not in diagnostics)
+        # Several dumps per launch.  Preferred: state SNAPSHOTS (pk_step_snap: the kernel stores u at every dump step, ONE
+        # batched streaming call computes the diagnostics of all dumps of the launch) -- a dump then costs the step kernel
+        # ~1 % of a step; if the snapshots of even one dump exceed the memory budget (PK_SNAP_BYTES, default 1 GiB): the
+        # dump FUSED into the step kernel (pk_step_dump, no extra memory, ~11 % of a cluster-kernel step per dump).
+        import os
+        batch_ok = (pde_runs and ndump > 0 and not eng.upwind and field_files is None and stats is None
+                    and not (want_mean or want_smooth) and 'mu' not in diagnostics)
+        ksnap = int(os.environ.get('PK_SNAP_BYTES', 1 << 30)) // max(1, R * ne * 8) if hasattr(eng, 'step_snap') else 0
+        fused_ok = (batch_ok and hasattr(eng, 'step_dump') and not (want_m or want_sde) and 'u_field' not in diagnostics)
+        mode = 'snap' if (batch_ok and ksnap >= 1) else ('fused' if fused_ok else None)
         kmax = max(1, min(256, (1 << 24) // max(1, R * ndump * max(1, num_Xis)))) if host_dW is not None else 256
         kmax = max(1, min(kmax, (1 << 23) // max(1, R * 23)))
-        while fused and nsteps - done >= ndump:
+        if mode == 'snap':
+            kmax = max(1, min(kmax, ksnap))
+        want_suite = 'peakon_suite' in diagnostics
+        while mode is not None and nsteps - done >= ndump:
             k = min(kmax, (nsteps - done) // ndump)
             c = k * ndump
             dW_dev = None
             if host_dW is not None:
                 dW_dev = torch.from_numpy(np.ascontiguousarray(host_dW[done:done + c])).to(eng.device)
-            want_suite = 'peakon_suite' in diagnostics
-            exported, dg, di, sv, si = eng.step_dump(c, ndump, dW=dW_dev, export_dW=(peq is not None and dW_dev is None and num_Xis > 0),
-                                                     suite=want_suite)
+            exp_dW = (peq is not None and dW_dev is None and num_Xis > 0)
+            snap_u = None
+            if mode == 'snap':
+                pq_blk = np.stack([true_at(t_idx + j) for j in range(k)]) if (true_pq is not None and want_sde) else None
+                exported, dg, di, sv, si, snap_u, snap_flag = eng.step_snap(c, ndump, dW=dW_dev, export_dW=exp_dW, pq=pq_blk,
+                                                                            periodic=periodic, want_m=want_m, suite=want_suite)
+            else:
+                exported, dg, di, sv, si = eng.step_dump(c, ndump, dW=dW_dev, export_dW=exp_dW, suite=want_suite)
             traj = None
             if peq is not None:
                 traj = peq.update(c, dW=dW_dev if dW_dev is not None else exported, step0=done, traj_stride=ndump).cpu().numpy()
             dg, di = dg.cpu().numpy(), di.cpu().numpy()
             if want_suite:
                 sv, si = sv.cpu().numpy(), si.cpu().numpy()
+            u_snaps = snap_u.cpu().numpy() if (snap_u is not None and 'u_field' in diagnostics) else None
             fs = eng.fail_step.cpu().numpy()
             for j in range(k):
                 for _ in range(ndump):
@@ -581,6 +595,8 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
                 extra = {}
                 if want_suite:
                     extra['peakon_suite'] = peakon_suite_columns(x_cells, dg[j][:, _lib.D_MAX_U], sv[j], si[j], failed)
+                if u_snaps is not None:
+                    extra['u'] = np.where(failed[:, None], np.nan, u_snaps[j])
                 cols = diagnostic_columns(diagnostics, dg[j], di[j], failed, x_cells, alphasq, pfac, extra)
                 if traj is not None:
                     cols['p'] = traj[j, :, 0]

@@ -269,6 +269,9 @@ extern "C" int pk_emu_set_dump(int every, double* out, int* idx, double* suite_v
   g_dump_every = every; g_dump_out = out; g_dump_idx = idx; g_dump_sv = suite_vals; g_dump_si = suite_ids; return 0;
 }
 
+static int g_snap_every = 0; static double* g_snap_u = nullptr; static int* g_snap_flag = nullptr;
+extern "C" int pk_emu_set_snap(int every, double* u, int* flag) { g_snap_every = every; g_snap_u = u; g_snap_flag = flag; return 0; }
+
 // advance in step blocks of nblk steps (0 = whole launch at once), see run_one
 extern "C" int pk_emu_set_block(int nblk) { g_emu_nblk = nblk; return 0; }
 
@@ -306,6 +309,7 @@ extern "C" int pk_emu_step(int ne, double Ld, double dt, double alphasq, int mod
     io.n0 = 0; io.n1 = nsteps;
     io.fail_step = fail_step; io.its_last = its_last; io.its_total = its_total; io.fail_reason = fail_reason;
     io.diag_every = g_dump_every; io.diag_out = g_dump_out; io.diag_idx = g_dump_idx; io.suite_vals = g_dump_sv; io.suite_ids = g_dump_si;
+    io.snap_every = g_snap_every; io.snap_u = g_snap_u; io.snap_flag = g_snap_flag;
     switch (p.M) {
       case 4: run_mode<4>(p, io, u, u1, dF, dG, order); break;
       case 5: run_mode<5>(p, io, u, u1, dF, dG, order); break;

@@ -84,6 +84,29 @@ class EmuEngine(object):
         t = torch.from_numpy
         return out, t(dg), t(di), (t(sv) if suite else None), (t(si) if suite else None)
 
+    def step_snap(self, nsteps, snap_every, dW=None, export_dW=False, pq=None, periodic=False, want_m=False, suite=False):
+        ns = nsteps // snap_every
+        su = np.zeros((ns, self.R, self.ne)); sf = np.zeros((ns, self.R), np.int32)
+        lib().pk_emu_set_snap(int(snap_every), _p(su), _p(sf, ctypes.c_int))
+        try:
+            out = self.step(nsteps, dW=dW, export_dW=export_dW)
+        finally:
+            lib().pk_emu_set_snap(0, None, None)
+        # the batched diagnostics kernels, restated: the per-realisation routines on every snapshot row
+        keep = (self.u.clone(), self.fail_step.clone())
+        dg = np.zeros((ns, self.R, L.NDIAG)); di = np.zeros((ns, self.R, L.NIDX), np.int32)
+        sv = np.zeros((ns, self.R, 2)); si = np.zeros((ns, self.R, 3), np.int32)
+        for d in range(ns):
+            self.u.copy_(torch.from_numpy(su[d])); self.fail_step.copy_(torch.from_numpy(sf[d]))
+            v, ix, _ = self.diagnostics(pq=None if pq is None else pq[d], periodic=periodic, want_m=want_m)
+            dg[d] = v.numpy(); di[d] = ix.numpy()
+            if suite:
+                a, b = self.peakon_suite()
+                sv[d] = a.numpy(); si[d] = b.numpy()
+        self.u.copy_(keep[0]); self.fail_step.copy_(keep[1])
+        t = torch.from_numpy
+        return out, t(dg), t(di), (t(sv) if suite else None), (t(si) if suite else None), t(su), t(sf)
+
     # ---- NumPy restatements of the device diagnostics (column layout of include/peakon_b200.h) ----
     def _failed(self, fail_step):
         fs = self.fail_step if isinstance(fail_step, str) else fail_step

@@ -65,41 +65,46 @@ def test_experiment_ensemble_axis_records_and_statistics(tmp_path, monkeypatch, 
     assert (d['ens_hist_min_du'].sum(axis=1) == 5).all()
 
 
-def test_fused_dump_path_equals_separate_kernels(tmp_path, monkeypatch, built):
-    """Diagnostics that are columns of the in-kernel dump take the pk_step_dump path (several dumps per launch, no
-    second kernel); with u_field in the list the separate-kernel path runs.  Same file either way (scalars to rounding
-    of the sums, extrema / locations / peakon suite / p, q bit for bit)."""
+def test_batched_dump_paths_equal_separate_kernels(tmp_path, monkeypatch, built):
+    """Several dumps per launch: state snapshots + one batched diagnostics call (pk_step_snap, the default), or -- when the
+    snapshot budget is too small -- the dump fused into the step kernel (pk_step_dump); `mu` in the list forces the plain
+    path (one launch and separate kernels per dump).  Same file every way (scalars to rounding of the sums, extrema /
+    locations / peakon suite / u_field / p, q bit for bit)."""
     from emu_engine import EmuEngine
     from peakondrake_b200 import experiment, outputting as out
     monkeypatch.chdir(tmp_path)
     diags = ['energy', 'l2_u', 'h1_u', 'mass_u', 'max_du', 'min_du', 'max_jump_local', 'max_jump_global', 'max_du_loc',
              'min_du_loc', 'p_pde', 'q_pde', 'E_0', 'E_1', 'E_3', 'peakon_suite']
     calls = []
-    orig = EmuEngine.step_dump
-
-    def spy(self, *a, **k):
-        calls.append(a[:2])
-        return orig(self, *a, **k)
-    monkeypatch.setattr(EmuEngine, 'step_dump', spy)
+    for name in ('step_dump', 'step_snap'):
+        def spy(self, *a, _orig=getattr(EmuEngine, name), _name=name, **k):
+            calls.append((_name,) + a[:2])
+            return _orig(self, *a, **k)
+        monkeypatch.setattr(EmuEngine, name, spy)
     kw = dict(seeds=[5, 6, 7], ndump=2, allow_fail=True, peakon_equations=True, engine_cls=EmuEngine, **KW)
-    experiment('fused', 40., 0.009, diagnostics=diags, **kw)                 # 9 steps: 4 dumps fused + 1 trailing step
-    experiment('plain', 40., 0.009, diagnostics=diags + ['u_field'], **kw)
-    assert calls == [(8, 2)]
-    a, b = out.read_data_file('results/fused/data.nc'), out.read_data_file('results/plain/data.nc')
-    assert a['time'].shape == (5,) and np.array_equal(a['time'], b['time'])
-    for k in a:
-        if k in ('wallclock_time',):
-            continue
-        if k in ('energy', 'l2_u', 'h1_u', 'mass_u', 'E_0', 'E_1', 'E_3'):
-            assert np.allclose(a[k], b[k], rtol=1e-12, atol=0), k
-        else:
-            assert np.array_equal(a[k], b[k], equal_nan=True), k
-    # a failure inside a fused chunk: NaN rows from the failing dump on, failed_time recorded
+    experiment('snap', 40., 0.009, diagnostics=diags + ['u_field', 'l2_m', 'E_2'], **kw)     # 9 steps: 4 dumps batched + 1 trailing step
+    monkeypatch.setenv('PK_SNAP_BYTES', '0')
+    experiment('fused', 40., 0.009, diagnostics=diags, **kw)
+    experiment('plain', 40., 0.009, diagnostics=diags + ['u_field', 'l2_m', 'E_2', 'mu'], **kw)
+    assert calls == [('step_snap', 8, 2), ('step_dump', 8, 2)]
+    a, b, c = [out.read_data_file('results/%s/data.nc' % n) for n in ('snap', 'fused', 'plain')]
+    assert a['time'].shape == (5,) and np.array_equal(a['time'], c['time']) and np.array_equal(b['time'], c['time'])
+    for x in (a, b):
+        for k in x:
+            if k in ('wallclock_time',):
+                continue
+            if k in ('energy', 'l2_u', 'h1_u', 'mass_u', 'E_0', 'E_1', 'E_3', 'l2_m', 'E_2'):
+                assert np.allclose(x[k], c[k], rtol=1e-12, atol=0), k
+            else:
+                assert np.array_equal(x[k], c[k], equal_nan=True), k
+    monkeypatch.delenv('PK_SNAP_BYTES')
+    # a failure inside a batched chunk: NaN rows from the failing dump on, failed_time recorded
     blow = lambda t: float('nan') if t > 0.0045 else 0.01
-    experiment('fail', 40., 0.008, diagnostics=['energy', 'min_du'], seeds=[1, 2], ndump=2, allow_fail=True, smooth_t=blow,
+    experiment('fail', 40., 0.008, diagnostics=['energy', 'min_du', 'u_field'], seeds=[1, 2], ndump=2, allow_fail=True, smooth_t=blow,
                engine_cls=EmuEngine, **KW)
     f = out.read_data_file('results/fail/data.nc')
     assert np.isfinite(f['energy'][:3]).all() and np.isnan(f['energy'][3:]).all() and np.allclose(f['failed_time'], 0.005)
+    assert np.isnan(f['u_field'][3:]).all() and np.isfinite(f['u_field'][:3]).all()
 
 
 def test_seed_axis_is_not_capped(tmp_path, monkeypatch, built):

@@ -334,17 +334,29 @@ def test_fused_dump_equals_separate_kernels(ne, fam, nxi, force, monkeypatch):
     _, dg, di, sv, si = a.step_dump(every * nd, every, suite=True)
     torch.cuda.synchronize()
     dg, di, sv, si = [t.cpu().numpy() for t in (dg, di, sv, si)]
+    # third engine: state snapshots + batched diagnostics over all dumps (pk_step_snap + pk_diagnostics_rows + ..._suite_rows)
+    c = mk(); c.set_state(u0); c.fail_step[3] = 0
+    nc = c.launch_count
+    _, cg_, ci, cv, cs, snaps, sflag = c.step_snap(every * nd, every, suite=True, want_m=True)
+    torch.cuda.synchronize()
+    assert c.launch_count - nc == 3
+    cg_, ci, cv, cs, snaps, sflag = [t.cpu().numpy() for t in (cg_, ci, cv, cs, snaps, sflag)]
     n0 = b.launch_count
     for d in range(nd):
         b.step(every)
-        v, ix, _ = b.diagnostics()
+        v, ix, _ = b.diagnostics(want_m=True)
         pv, pi = b.peakon_suite()
         torch.cuda.synchronize()
         v, ix, pv, pi = [t.cpu().numpy() for t in (v, ix, pv, pi)]
+        # the batched rows are the separate kernels' output bit for bit (same kernels, same state)
+        assert np.array_equal(cg_[d][:, :13], v[:, :13], equal_nan=True) and np.array_equal(ci[d], ix)
+        assert np.array_equal(cv[d], pv, equal_nan=True) and np.array_equal(cs[d], pi)
+        assert np.array_equal(snaps[d][np.arange(R) != 3], b.u.cpu().numpy()[np.arange(R) != 3]) and sflag[d][3] == 0 and (sflag[d][np.arange(R) != 3] == -1).all()
         assert np.array_equal(di[d], ix) and np.array_equal(si[d], pi) and np.array_equal(sv[d], pv, equal_nan=True)
         assert np.array_equal(dg[d][:, 4:8], v[:, 4:8], equal_nan=True)
         ok = np.arange(R) != 3
         assert np.allclose(dg[d][ok, :4], v[ok, :4], rtol=1e-12, atol=0) and np.isnan(dg[d][3]).all() and np.isnan(dg[d][:, 8:]).all()
     assert torch.equal(a.u, b.u) and torch.equal(a.its_total, b.its_total)
     assert b.launch_count - n0 == 3 * nd and a.launch_count - na == 1     # one kernel for all dumps of the chunk
-    a.close(); b.close()
+    assert torch.equal(c.u, b.u)
+    a.close(); b.close(); c.close()
