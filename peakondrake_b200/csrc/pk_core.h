@@ -1344,7 +1344,9 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 // once per step on nxi threads.  Every block of a cluster draws the same numbers; the leader exports.
 // ------------------------------------------------------------------------------------------------
 // One Brownian increment of the Philox path: the sum of the nupd sub-update draws (stochastic_functions.py:213-217), each
-// scaled by sqrt(dt/nupd) before it is added.  Summation order (part of the definition: every code path -- step kernels,
+// scaled by sqrt(dt/nupd) before it is added.  Sub-update j of step n is the draw of FINE step n * nupd + j (counter word 1),
+// so a run at dt with nXi_updates = dt/dt0 consumes the same Brownian path as a run at dt0 with nXi_updates = 1 -- the
+// property of the reference's sequential MT19937 stream that its strong-convergence study relies on (:211-217).  Summation order (part of the definition: every code path -- step kernels,
 // peakon-SDE kernel, emulation -- produces the same bits):
 //   nupd <  PK_COOP_NUPD : j = 0, 1, ..., nupd-1 in sequence;
 //   nupd >= PK_COOP_NUPD : 32 interleaved partial sums (lane l adds j = l, l+32, ... in sequence), added up in lane
@@ -1352,13 +1354,13 @@ PK_HD double philox_normal(unsigned long long seed, unsigned rid, unsigned step,
 enum { PK_COOP_NUPD = 64 };
 PK_HD double philox_partial(unsigned long long seed, unsigned rid, unsigned step, unsigned k, int nupd, double sdt, int lane) {
   double s = 0.0;
-  for (int j = lane; j < nupd; j += 32) s += philox_normal(seed, rid, step, k, (unsigned)j) * sdt;
+  for (int j = lane; j < nupd; j += 32) s += philox_normal(seed, rid, step * (unsigned)nupd + (unsigned)j, k, 0u) * sdt;
   return s;
 }
 PK_HD double philox_increment(unsigned long long seed, unsigned rid, unsigned step, unsigned k, int nupd, double sdt) {
   if (nupd < PK_COOP_NUPD) {
     double w = 0.0;
-    for (int j = 0; j < nupd; ++j) w += philox_normal(seed, rid, step, k, (unsigned)j) * sdt;
+    for (int j = 0; j < nupd; ++j) w += philox_normal(seed, rid, step * (unsigned)nupd + (unsigned)j, k, 0u) * sdt;
     return w;
   }
   double w = philox_partial(seed, rid, step, k, nupd, sdt, 0);

@@ -215,7 +215,7 @@ class EmuEngine(object):
                 for r in range(self.R):
                     for k in range(self.num_Xis):
                         for j in range(self.nupd):
-                            w[r, k] += lib().pk_emu_philox_normal(self.seed, self.rid_offset + r, step0 + n, k, j) * np.sqrt(self.dt / self.nupd)
+                            w[r, k] += lib().pk_emu_philox_normal(self.seed, self.rid_offset + r, (step0 + n) * self.nupd + j, k, 0) * np.sqrt(self.dt / self.nupd)
             sde.update(w)
             if traj_stride and (n + 1) % traj_stride == 0:
                 traj.append(np.stack([sde.p, sde.q], 1))

@@ -116,8 +116,16 @@ def test_philox_generator_statistics_and_reproducibility():
     for k in range(2):
         ref = O.run(ne, Ld, dt, n, u0, r['dW'][:, k, :], tabs)
         assert rel(u[k], ref['u']) <= TOL
-    w = sum(L.pk_emu_philox_normal(9, 101, 3, 1, j) for j in range(4)) * np.sqrt(dt / 4)
+    w = sum(L.pk_emu_philox_normal(9, 101, 3 * 4 + j, 1, 0) for j in range(4)) * np.sqrt(dt / 4)       # fine step 3*4+j
     assert abs(r['dW'][3, 1, 1] - w) < 1e-16          # kernel scales each sub-draw, then sums
+    # a coarse run with nXi_updates = 4 consumes the Brownian path of the fine run (stochastic_functions.py:211-217):
+    # its increments are the sums of four consecutive fine increments, bit for bit (dt a power of two: exact scalings)
+    dtf = 2.0 ** -10
+    mk = lambda: (np.tile(u0, (2, 1)), np.zeros((2, ne)), np.zeros((2, ne)), np.zeros((2, ne)))
+    a = mk(); fine = emu_step(ne, Ld, dtf, 2, a[0], a[1], a[2], a[3], tabs, None, 12, nxi=2, seed=9, rid0=100, export=True, nupd=1)['dW']
+    b = mk(); coarse = emu_step(ne, Ld, 4 * dtf, 2, b[0], b[1], b[2], b[3], tabs, None, 3, nxi=2, seed=9, rid0=100, export=True, nupd=4)['dW']
+    acc = ((fine[0::4] + fine[1::4]) + fine[2::4]) + fine[3::4]
+    assert np.array_equal(coarse, acc)
 
 
 @pytest.mark.parametrize('ne,C,part', [(1000, 2, 1), (1000, 4, 1), (250, 2, 1), (2000, 8, 1), (2000, 16, 1), (128, 8, 1), (256, 8, 1), (200, 2, 1),
@@ -512,7 +520,7 @@ def test_philox_many_sub_updates_have_a_fixed_summation_order():
             for l in range(32):
                 s = 0.0
                 for j in range(l, nupd, 32):
-                    s += L.pk_emu_philox_normal(seed, 7 + rr, n, 0, j) * sdt
+                    s += L.pk_emu_philox_normal(seed, 7 + rr, n * nupd + j, 0, 0) * sdt
                 pa[l] = s
             tot = pa[0]
             for l in range(1, 32):

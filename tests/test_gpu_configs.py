@@ -97,6 +97,18 @@ def test_philox_sub_updates_same_bits_on_every_layout():
             assert torch.equal(qa, qb)
         eng.close()
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]) and abs(outs[0].std() / np.sqrt(1e-3) - 1) < 0.4
+    # a coarse run with nXi_updates = dt/dt0 walks the Brownian path of the fine run (the reference's MT19937 property,
+    # stochastic_functions.py:211-217, kept by keying the sub-updates with the fine step index)
+    dt0 = 2.0 ** -14
+    def path(dt, nupd, nsteps):
+        eng = EnsembleIntegrator(64, 40.0, dt, 3, num_Xis=2, Xi_family='sines', sigma=0.1, nXi_updates=nupd, seed=5, rid_offset=3)
+        eng.set_state(build_initial_u(64, 40.0, 'proper_peak'))
+        w = eng.step(nsteps, export_dW=True).cpu().numpy(); eng.close()
+        return w
+    fine = path(dt0, 1, 256 * 4)
+    for nupd in (4, 256):            # serial and warp-shared summation
+        coarse = path(dt0 * nupd, nupd, 1024 // nupd)
+        assert np.allclose(coarse, fine.reshape(1024 // nupd, nupd, 3, 2).sum(axis=1), rtol=1e-12, atol=1e-16)
 
 
 def test_du_smooth_and_ensemble_scalars():
