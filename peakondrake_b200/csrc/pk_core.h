@@ -74,6 +74,10 @@ struct Shared {
   // it into a block-local address without decoding (pk_kernels.cuh, SharedCluster)
   PK_HD double ldo(const double* a, int j, int T, int t) const { return a[j * T + t]; }
   PK_HD void sto(double* a, int j, int T, int t, double v) const { a[j * T + t] = v; }
+  // slot c of the LEFT / RIGHT neighbour thread q = tl / tr of the calling thread (the cluster variant reads these
+  // through two per-thread pointers that already name the owning CTA)
+  PK_HD double ldL(const double* a, int c, int T, int q) const { return a[c * T + q]; }
+  PK_HD double ldR(const double* a, int c, int T, int q) const { return a[c * T + q]; }
   // pairs of doubles (16-byte shared-memory accesses): pair slot q of thread tt lives at doubles 2 (q T + tt), +1.
   // Used for the PCR rows, which travel as whole 2x2 blocks.
   PK_HD void ld2(const double* a, int q, int T, int tt, double& v0, double& v1) const {
@@ -336,7 +340,7 @@ struct Thread {
   PK_HD bool own_node(int j) const { return j >= 0 && (j < M - 1 || (j == M - 1 && ext)); }
   template <class SH>
   PK_HD double ldn(const Params& p, const SH& sh, const double* a, int j) const {
-    return own_node(j) ? sh.ldo(a, j, TN(p), t) : sh.ld(a, nidx(p, j));
+    return own_node(j) ? sh.ldo(a, j, TN(p), t) : (j < 0 ? sh.ldL(a, ml - 1, TN(p), tl) : sh.ldR(a, 0, TN(p), tr));
   }
   template <class SH>
   PK_HD void load_node(const Params& p, const SH& sh, int j, NodeS& n) const {
@@ -557,8 +561,8 @@ struct Thread {
     for (int q = 2; q <= m; ++q) stream_fs(p, sh, q, false);
     // last row (m-1): Cp,Qp come from the right neighbour's first node
     double cp[3];
-    cp[0] = sh.ld(sh.xb, 14 * TN(p) + tr); cp[1] = sh.ld(sh.xb, 15 * TN(p) + tr); cp[2] = sh.ld(sh.xb, 16 * TN(p) + tr);
-    const double qp = sh.ld(sh.xb, 17 * TN(p) + tr);
+    cp[0] = sh.ldR(sh.xb, 14, TN(p), tr); cp[1] = sh.ldR(sh.xb, 15, TN(p), tr); cp[2] = sh.ldR(sh.xb, 16, TN(p), tr);
+    const double qp = sh.ldR(sh.xb, 17, TN(p), tr);
     finish_row_fs(p, sh, m - 1, cp, qp);
     sh.sto(sh.xb, 10, TN(p), t, wCm1[0]); sh.sto(sh.xb, 11, TN(p), t, wCm1[1]); sh.sto(sh.xb, 12, TN(p), t, wCm1[2]);
     sh.sto(sh.xb, 13, TN(p), t, wQm1);
@@ -599,7 +603,7 @@ struct Thread {
   PK_HD void interior_solve_fs(const Params& p, const SH& sh) {
     const int T = TN(p);
     const int nI = m - 2;
-    double xp1 = sh.ld(sh.xb, 14 * T + tr), xp2 = sh.ld(sh.xb, 15 * T + tr);
+    double xp1 = sh.ldR(sh.xb, 14, T, tr), xp2 = sh.ldR(sh.xb, 15, T, tr);
     sh.sto(sh.xb, 0, T, t, xs0); sh.sto(sh.xb, 1, T, t, xs1);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -638,8 +642,8 @@ struct Thread {
     if (lite) return;
     // last row (m-1): Cp,Qp come from the right neighbour's first node
     double cp[3];
-    cp[0] = sh.ld(sh.xb, 14 * TN(p) + tr); cp[1] = sh.ld(sh.xb, 15 * TN(p) + tr); cp[2] = sh.ld(sh.xb, 16 * TN(p) + tr);
-    const double qp = sh.ld(sh.xb, 17 * TN(p) + tr);
+    cp[0] = sh.ldR(sh.xb, 14, TN(p), tr); cp[1] = sh.ldR(sh.xb, 15, TN(p), tr); cp[2] = sh.ldR(sh.xb, 16, TN(p), tr);
+    const double qp = sh.ldR(sh.xb, 17, TN(p), tr);
     if (ext) finish_row(p, M - 1, cp, qp); else finish_row(p, M - 2, cp, qp);
     // publish my last node's Cm,Qm for the right neighbour's separator row 0
     sh.sto(sh.xb, 10, TN(p), t, wCm1[0]); sh.sto(sh.xb, 11, TN(p), t, wCm1[1]); sh.sto(sh.xb, 12, TN(p), t, wCm1[2]);
@@ -690,11 +694,11 @@ struct Thread {
   template <class SH>
   PK_HD void reduce_build(const Params& p, const SH& sh) {
     const int T = TN(p);
-    const double yL[2] = {sh.ld(sh.xb, 0 * T + tl), sh.ld(sh.xb, 1 * T + tl)};
-    const double WL[4] = {sh.ld(sh.xb, 2 * T + tl), sh.ld(sh.xb, 3 * T + tl), sh.ld(sh.xb, 4 * T + tl), sh.ld(sh.xb, 5 * T + tl)};
-    const double VL[4] = {sh.ld(sh.xb, 6 * T + tl), sh.ld(sh.xb, 7 * T + tl), sh.ld(sh.xb, 8 * T + tl), sh.ld(sh.xb, 9 * T + tl)};
-    sp0[0] += sh.ld(sh.xb, 10 * T + tl); sp0[1] += sh.ld(sh.xb, 11 * T + tl); sp0[2] += sh.ld(sh.xb, 12 * T + tl);
-    sb0 -= sh.ld(sh.xb, 13 * T + tl);
+    const double yL[2] = {sh.ldL(sh.xb, 0, T, tl), sh.ldL(sh.xb, 1, T, tl)};
+    const double WL[4] = {sh.ldL(sh.xb, 2, T, tl), sh.ldL(sh.xb, 3, T, tl), sh.ldL(sh.xb, 4, T, tl), sh.ldL(sh.xb, 5, T, tl)};
+    const double VL[4] = {sh.ldL(sh.xb, 6, T, tl), sh.ldL(sh.xb, 7, T, tl), sh.ldL(sh.xb, 8, T, tl), sh.ldL(sh.xb, 9, T, tl)};
+    sp0[0] += sh.ldL(sh.xb, 10, T, tl); sp0[1] += sh.ldL(sh.xb, 11, T, tl); sp0[2] += sh.ldL(sh.xb, 12, T, tl);
+    sb0 -= sh.ldL(sh.xb, 13, T, tl);
     const double E[4] = {sp0[0], sp0[1], 0.0, sp1[0]};
     const double C[4] = {sp0[2], sp0[3], sp1[1], sp1[2]};
     const double Gc[4] = {sp0[4], 0.0, sp1[3], sp1[4]};
@@ -1060,7 +1064,7 @@ struct Thread {
   template <class SH>
   PK_HD void interior_solve(const Params& p, const SH& sh) {
     const int T = TN(p);
-    double xp1 = sh.ld(sh.xb, 14 * T + tr), xp2 = sh.ld(sh.xb, 15 * T + tr);
+    double xp1 = sh.ldR(sh.xb, 14, T, tr), xp2 = sh.ldR(sh.xb, 15, T, tr);
     du[0] = xs0; du[1] = xs1;
     PK_UNROLL
     for (int k = NI - 1; k >= 0; --k) {
@@ -1089,7 +1093,7 @@ struct Thread {
     {
       a0 = 0.5 * (ldn(p, sh, sh.U0, -1) + ldn(p, sh, sh.U1, -1));
       if (MODE == NOISE_FULL) { x0 = ldn(p, sh, sh.Xx, -1); y0 = ldn(p, sh, sh.Xxx, -1); }
-      const double d0 = sh.ld(sh.xb, 16 * T + tl);          // increment of the left neighbour's last row
+      const double d0 = sh.ldL(sh.xb, 16, T, tl);          // increment of the left neighbour's last row
       s0 = a0 + d0; b0 = a0 + 0.5 * d0;
     }
     double prevFR = 0.0, prevGR = 0.0;
@@ -1101,7 +1105,7 @@ struct Thread {
         const double a1 = 0.5 * (ldn(p, sh, sh.U0, q) + ldn(p, sh, sh.U1, q));
         double x1 = 0.0, y1 = 0.0;
         if (MODE == NOISE_FULL) { x1 = ldn(p, sh, sh.Xx, q); y1 = ldn(p, sh, sh.Xxx, q); }
-        const double d1 = (q < M - 1 || (q == M - 1 && ext)) ? get_du(p, sh, q) : sh.ld(sh.xb, 14 * T + tr);
+        const double d1 = (q < M - 1 || (q == M - 1 && ext)) ? get_du(p, sh, q) : sh.ldR(sh.xb, 14, T, tr);
         const double s1 = a1 + d1, b1 = a1 + 0.5 * d1;      // uh + du and uh + e at the right node of the cell
         const double ss = s0 + s1;
         const double cdd = p.c2k * (a1 - a0) * (s1 - s0);        // (constants carry the 1/kappa of the filter)
@@ -1209,7 +1213,11 @@ struct Thread {
     PK_UNROLL
     for (int j = 0; j < M; ++j) { X[j] = 0.0; Xx[j] = 0.0; Xxx[j] = 0.0; }
 #if defined(__CUDA_ARCH__)
+#ifdef PK_EXP_NOISE_UNROLL4
+#pragma unroll 4
+#else
 #pragma unroll 2
+#endif
 #endif
     for (int k = 0; k < p.nxi; ++k) {
       const double w = sh.dw(k);
@@ -1251,7 +1259,7 @@ struct Thread {
   template <class SH>
   PK_HD double ldn2(const Params& p, const SH& sh, const double* a, int j) const {      // j in [-1, m + 1]
     const int mm = ext ? M : M - 1;
-    return j <= mm ? ldn(p, sh, a, j) : sh.ld(a, TN(p) + tr);                           // row 1 of the right neighbour
+    return j <= mm ? ldn(p, sh, a, j) : sh.ldR(a, 1, TN(p), tr);                           // row 1 of the right neighbour
   }
   template <class SH>
   PK_HD void diag_local(const Params& p, const SH& sh, double* s3, double* av, int* ai) const {
@@ -1600,7 +1608,9 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
   int cert_skip = 0;  // steps during which the convergence certificate is not attempted
   ex.each_tid([&](Th& th, int tid, int nth, bool, int, int) { th.dw_slot = draw_slot(p, tid); if (dio.per == 0) draw_begin<(FEAT & FEAT_COOP) != 0>(p, dio, nth); });
   for (int n = io.n0; n < io.n1; ++n) {
+#ifndef PK_EXP_NO_KILL_ALL
     ex.each([&](Th& th) { th.kill_all(); });
+#endif
     // Brownian increments are produced (and exported) every step, failed or not (simulation.py:96)
     draw_advance(dio, n);
     ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {

@@ -313,48 +313,72 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
 // (owner CTA, local offset) and foreign rows are read through distributed shared memory.  All writes
 // are to own rows.  Barriers are cluster barriers.
 // ------------------------------------------------------------------------------------------------
-struct SharedCluster {
+// TCC > 0: threads per CTA known at compile time (= blockDim.x): the block-local offsets (slot * Tc + thread) fold into
+// immediate offsets of the loads and stores -- the runtime shifts of the generic variant were a third of the
+// cluster kernel's instructions (profiles/r2qc source page: IMAD / SHF / LEA / BRA 30 %, fp64 26 %).
+template <int TCC> struct Log2C { enum { v = 1 + Log2C<TCC / 2>::v }; };
+template <> struct Log2C<1> { enum { v = 0 }; };
+template <> struct Log2C<0> { enum { v = 0 }; };
+template <int TCC = 0>
+struct SharedClusterT {
   double *U0, *U1, *F, *G, *X, *Xx, *Xxx, *xb, *dW;
-  int Tc, lgTc, lgT;
+  int Tc_, lgTc_, lgT;
   unsigned rank;
+  // rows of the two NEIGHBOUR threads (t-1, t+1 on the ring): generic pointers to element [0] of the neighbour's column
+  // of this CTA's / the adjacent CTA's shared memory (map_shared_rank), so that slot c of array a of that thread is
+  // nb[(a - base) + c * Tc] -- one load with a constant offset, no owner decode, no branch
+  const double *base, *nbL, *nbR;
+  __device__ __forceinline__ int tcn() const { return TCC > 0 ? TCC : Tc_; }
+  __device__ __forceinline__ int lgtc() const { return TCC > 0 ? (int)Log2C<TCC>::v : lgTc_; }
+  __device__ __forceinline__ void set_neighbours(double* smem0, int tl, int tr) {
+    base = smem0;
+    cg::cluster_group cl = cg::this_cluster();
+    nbL = cl.map_shared_rank(smem0 + (tl & (tcn() - 1)), (unsigned)tl >> lgtc());
+    nbR = cl.map_shared_rank(smem0 + (tr & (tcn() - 1)), (unsigned)tr >> lgtc());
+  }
+  __device__ __forceinline__ double ldL(const double* a, int c, int, int) const { return nbL[(a - base) + c * tcn()]; }
+  __device__ __forceinline__ double ldR(const double* a, int c, int, int) const { return nbR[(a - base) + c * tcn()]; }
   __device__ __forceinline__ double ld(const double* a, int i) const {
     const int tg = i & ((1 << lgT) - 1), j = i >> lgT;
-    const unsigned owner = (unsigned)tg >> lgTc;
-    double* pl = const_cast<double*>(a) + (j << lgTc) + (tg & (Tc - 1));
+    const unsigned owner = (unsigned)tg >> lgtc();
+    double* pl = const_cast<double*>(a) + j * tcn() + (tg & (tcn() - 1));
     if (owner == rank) return *pl;
     return *cg::this_cluster().map_shared_rank(pl, owner);
   }
   __device__ __forceinline__ void st(double* a, int i, double v) const {
     const int tg = i & ((1 << lgT) - 1), j = i >> lgT;
-    a[(j << lgTc) + (tg & (Tc - 1))] = v;
+    a[j * tcn() + (tg & (tcn() - 1))] = v;
   }
   // pairs of doubles (PCR rows): pair slot q of thread tt, 16-byte accesses; remote rows through DSMEM
   __device__ __forceinline__ void ld2(const double* a, int q, int, int tt, double& v0, double& v1) const {
-    const unsigned owner = (unsigned)tt >> lgTc;
-    const double2* pl = reinterpret_cast<const double2*>(a) + (q << lgTc) + (tt & (Tc - 1));
+    const unsigned owner = (unsigned)tt >> lgtc();
+    const double2* pl = reinterpret_cast<const double2*>(a) + q * tcn() + (tt & (tcn() - 1));
     const double2 v = (owner == rank) ? *pl : *cg::this_cluster().map_shared_rank(const_cast<double2*>(pl), owner);
     v0 = v.x; v1 = v.y;
   }
   // row of a thread of my own CTA: no owner decode
   __device__ __forceinline__ void ld2l(const double* a, int q, int, int tt, double& v0, double& v1) const {
-    const double2 v = reinterpret_cast<const double2*>(a)[(q << lgTc) + (tt & (Tc - 1))];
+    const double2 v = reinterpret_cast<const double2*>(a)[q * tcn() + (tt & (tcn() - 1))];
     v0 = v.x; v1 = v.y;
   }
   __device__ __forceinline__ double ldl(const double* a, int off) const { return a[off]; }
   __device__ __forceinline__ void stl(double* a, int off, double v) const { a[off] = v; }
   __device__ __forceinline__ void st2o(double* a, int q, int, int, double v0, double v1) const {
-    reinterpret_cast<double2*>(a)[(q << lgTc) + (int)threadIdx.x] = make_double2(v0, v1);
+    reinterpret_cast<double2*>(a)[q * tcn() + (int)threadIdx.x] = make_double2(v0, v1);
   }
   // slot j of the calling thread: block-local, no decoding of the flat index (most accesses are of this kind)
-  __device__ __forceinline__ double ldo(const double* a, int j, int, int) const { return a[(j << lgTc) + (int)threadIdx.x]; }
-  __device__ __forceinline__ void sto(double* a, int j, int, int, double v) const { a[(j << lgTc) + (int)threadIdx.x] = v; }
+  __device__ __forceinline__ double ldo(const double* a, int j, int, int) const { return a[j * tcn() + (int)threadIdx.x]; }
+  __device__ __forceinline__ void sto(double* a, int j, int, int, double v) const { a[j * tcn() + (int)threadIdx.x] = v; }
   __device__ __forceinline__ double dw(int k) const { return dW[k]; }
   __device__ __forceinline__ void set_dw(int k, double v) const { dW[k] = v; }
 };
+typedef SharedClusterT<0> SharedCluster;
 
-template <class ThT>
+template <class ThT, int TCC = 0>
 struct GpuExecClusterT {
   typedef ThT Th;
+  static __device__ __forceinline__ int bdim() { return TCC > 0 ? TCC : (int)blockDim.x; }
+  static __device__ __forceinline__ int nwarps() { return bdim() >> 5; }
   Th& th;
   double* red;          // [2][3*nw + 3]: warp partials + this CTA's aggregate, ping-pong
   int flip, g0, g1;
@@ -362,7 +386,7 @@ struct GpuExecClusterT {
   double rA, rc0, rc1;
   __device__ __forceinline__ GpuExecClusterT(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
   template <class F> __device__ __forceinline__ void each(F f) { f(th); }
-  template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, (int)blockDim.x, rank == 0, g0, g1); }
+  template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, bdim(), rank == 0, g0, g1); }
   // Cluster barrier.  cg's sync() arrives with release semantics, which ptxas turns into MEMBAR.ALL.GPU + ERRBAR in front
   // of every arrive (22 % of the kernel's stall samples sit on these and on the wait).  Everything the CTAs of a cluster
   // exchange lives in shared memory and is written by its owner, so a CTA-scope fence (the owner's stores and its
@@ -404,12 +428,12 @@ struct GpuExecClusterT {
   __device__ __forceinline__ bool partitioned() const { return part != 0; }
   __device__ __forceinline__ bool redundant() const { return part == 1; }      // part = 2: separators by the leading threads
   template <class F> __device__ __forceinline__ void each_cta_first(int n, F f) { if ((int)threadIdx.x < n) f(th); }
-  __device__ __forceinline__ int tc() const { return (int)blockDim.x; }
+  __device__ __forceinline__ int tc() const { return bdim(); }
   __device__ __forceinline__ void sync_local() { __syncthreads(); }
   template <class F> __device__ __forceinline__ void each_first(int, F) {}
   template <class F> __device__ __forceinline__ void warp0_steps(int, F) {}
   __device__ __forceinline__ double* area() {
-    double* a = red + flip * cluster_red_half((int)blockDim.x);
+    double* a = red + flip * cluster_red_half(bdim());
     flip ^= 1;
     return a;
   }
@@ -433,7 +457,7 @@ struct GpuExecClusterT {
 #pragma unroll
       for (int c = 0; c < 3; ++c) s3[c] += __shfl_xor_sync(0xffffffffu, s3[c], o);
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
     int* si = reinterpret_cast<int*>(scratch + 4 * nw);
     double* ss = scratch + 6 * nw;
     if (lane == 0) {
@@ -509,7 +533,7 @@ struct GpuExecClusterT {
       k[0] = min(k[0], __shfl_xor_sync(0xffffffffu, k[0], o));
       k[1] = min(k[1], __shfl_xor_sync(0xffffffffu, k[1], o));
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
     int* si = reinterpret_cast<int*>(scratch + 9 * nw + 18);
     if (lane == 0) { si[w] = k[0]; si[nw + w] = k[1]; }
     __syncthreads();
@@ -543,7 +567,7 @@ struct GpuExecClusterT {
       v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
       v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
     }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
     double* sc = area();
     if (lane == 0) { sc[w] = v[0]; sc[nw + w] = v[1]; sc[2 * nw + w] = v[2]; }
     __syncthreads();
@@ -571,7 +595,7 @@ struct GpuExecClusterT {
   }
   template <int DIR>
   __device__ __forceinline__ void cyc_scan(double A, double c0, double c1, double& in0, double& in1) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nwarps();
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       double Ao, c0o, c1o;
@@ -645,16 +669,18 @@ struct GpuExecClusterT {
   }
 };
 
-template <int M, int MODE> using GpuExecCluster = GpuExecClusterT<Thread<M, MODE, 0> >;
+template <int M, int MODE, int TCC = 0> using GpuExecCluster = GpuExecClusterT<Thread<M, MODE, 0>, TCC>;
 
-template <int M, int MODE, int TB, int MINB = 1>
+// TCC = TB: launched with exactly TB threads per CTA (the production layouts); TCC = 0: any block size <= TB (forced
+// cluster layouts of small meshes in the tests)
+template <int M, int MODE, int TB, int MINB = 1, int TCC = 0>
 __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_constant__ Params p, const __grid_constant__ StepArgs a, int lgTc) {
   extern __shared__ __align__(16) double smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), C = cluster.num_blocks();
-  const int Tc = blockDim.x, n = Tc * M;
-  SharedCluster sh;
-  sh.Tc = Tc; sh.lgTc = lgTc; sh.rank = rank;
+  const int Tc = TCC > 0 ? TCC : (int)blockDim.x, n = Tc * M;
+  SharedClusterT<TCC> sh;
+  sh.Tc_ = Tc; sh.lgTc_ = lgTc; sh.rank = rank;
   { int lg = 0; while ((1 << lg) < p.T) ++lg; sh.lgT = lg; }
   sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
   double* nxt = smem + 3 * n;
@@ -670,7 +696,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   const int t0 = (int)rank * Tc;
   const int g0 = chunk_start(p, t0);
   const int g1 = (rank == C - 1) ? p.ne : chunk_start(p, t0 + Tc);
-  for (int i = g0 + threadIdx.x; i < g1; i += blockDim.x) {
+  for (int i = g0 + threadIdx.x; i < g1; i += Tc) {
     const int sl = row_slot_c<M, 0>(p, i);
     sh.st(sh.U0, sl, a.u[off + i]); sh.st(sh.U1, sl, a.u1[off + i]); sh.st(sh.F, sl, a.dF[off + i]);
     if (MODE == NOISE_FULL) sh.st(sh.G, sl, a.dG[off + i]);
@@ -679,7 +705,8 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
 
   Thread<M, MODE, 0> th;
   th.init(p, t0 + (int)threadIdx.x);
-  GpuExecCluster<M, MODE> ex(th, red);
+  sh.set_neighbours(smem, th.tl, th.tr);
+  GpuExecCluster<M, MODE, TCC> ex(th, red);
   ex.rank = rank; ex.C = C; ex.g0 = g0; ex.g1 = g1; ex.part = a.part;
 #ifdef PK_PROFILE
   __shared__ long long tb[16];
@@ -694,13 +721,13 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
   io.snap_every = a.snap_every; io.snap_u = a.snap_u; io.snap_flag = a.snap_flag;
-  run_steps<M, MODE, 0, GpuExecCluster<M, MODE>, Thread<M, MODE, 0> >(ex, p, sh, io);
+  run_steps<M, MODE, 0, GpuExecCluster<M, MODE, TCC>, Thread<M, MODE, 0>, SharedClusterT<TCC> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
 #ifdef PK_PROFILE
   if (a.prof && rank == 0 && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];
 #endif
 
-  for (int i = g0 + threadIdx.x; i < g1; i += blockDim.x) {
+  for (int i = g0 + threadIdx.x; i < g1; i += Tc) {
     const int sl = row_slot_c<M, 0>(p, i);
     a.u[off + i] = sh.ld(sh.U0, sl); a.u1[off + i] = sh.ld(sh.U1, sl); a.dF[off + i] = sh.ld(sh.F, sl);
     if (MODE == NOISE_FULL) a.dG[off + i] = sh.ld(sh.G, sl);

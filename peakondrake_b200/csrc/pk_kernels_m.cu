@@ -7,10 +7,21 @@
 #endif
 
 
+// exact = the launch uses exactly 256 / 512 threads per CTA: instantiation with compile-time shared-memory offsets
 template <int M> static ckern_t pick_cmode(int mode, int Tc, int minb) {
   if (Tc <= 256) {
     // two clusters share the SMs when two CTAs fit one SM's shared memory (128 registers per thread)
     if constexpr (M <= 8) { if (minb == 2 && mode == NOISE_SCALAR) return pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2>; }
+    const char* gen = getenv("PK_CLUSTER_GENERIC");      // A/B: the runtime-offset instantiation for every block size
+    if (Tc == 256 && !(gen && atoi(gen) == 1)) {
+      switch (mode) {
+        case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 1, 256>;
+        case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 256, 1, 256>;
+        case TEST_SCALAR: return pk_step_cluster_kernel<M, TEST_SCALAR, 256, 1, 256>;
+        case TEST_X: return pk_step_cluster_kernel<M, TEST_X, 256, 1, 256>;
+        default: return pk_step_cluster_kernel<M, NOISE_FULL, 256, 1, 256>;
+      }
+    }
     switch (mode) {
       case NOISE_SCALAR: return pk_step_cluster_kernel<M, NOISE_SCALAR, 256>;
       case NOISE_X: return pk_step_cluster_kernel<M, NOISE_X, 256>;

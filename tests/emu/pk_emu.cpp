@@ -39,6 +39,9 @@ struct EmuSharedCluster {
   }
   double ld(const double* a, int i) const { return *at(a, i, false); }
   void st(double* a, int i, double v) const { *at(a, i, true) = v; }
+  // slot c of the ring neighbour q of the calling thread (the device reads these through per-thread pointers)
+  double ldL(const double* a, int c, int T, int q) const { return *at(a, c * T + q, false); }
+  double ldR(const double* a, int c, int T, int q) const { return *at(a, c * T + q, false); }
   // pairs of doubles (PCR rows): pair slot q of thread tt at doubles 2 (q Tc + tt_local), +1 in tt's CTA
   void ld2(const double* a, int q, int T, int tt, double& v0, double& v1) const {
     const int owner = tt >> lgTc;
