@@ -1616,7 +1616,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     ex.each_tid([&](Th& th, int tid, int nth, bool leader, int, int) {
       draw_step<(FEAT & FEAT_COOP) != 0>(p, sh, dio, n, tid, nth, leader, th.dw_hold, th.dw_slot);
     });
-    ex.sync();
+    ex.sync_local();        // the increments live in CTA-local shared memory (every CTA of a cluster draws its own copy)
     ex.tick(0);
     if (failed >= 0) {
       if constexpr ((FEAT & FEAT_DUMP) != 0) {
@@ -1627,9 +1627,11 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       }
       continue;
     }
+    // Barriers between two steps: the neighbours' halo reads of the next assembly need ONE (cluster-wide) barrier after
+    // accept() and after the noise arrays are filled.  Scalar noise lives in a register: the barrier that closes the
+    // previous step does it; noise arrays: the barrier below does, and the closing one is dropped (see the end of the step).
     if (PK_NOISE_OF(MODE) == NOISE_SCALAR) ex.each([&](Th& th) { th.set_scalar_noise(p, sh); });
-    else ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); });
-    ex.sync();
+    else { ex.each([&](Th& th) { th.fill_noise(p, sh, io.xi, io.xi_x, io.xi_xx); }); ex.sync(); }
     ex.tick(1);
 
     if (cert_skip > 0) --cert_skip;
@@ -1809,7 +1811,9 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
                     th.helm_anticausal_local(p, in0, in1, A, c0, c1); });
       ex.tick(10);
       ex.scan_rev([&](Th& th, double in0, double in1) { th.helm_finish_update(p, sh, in0, in1); });
-      ex.sync();
+      // the new iterate must be visible to the neighbours before the next assembly; when the convergence certificate
+      // is attempted next, the barrier inside its all-reduce comes first and does it
+      if (!((it + 1 >= expect) && p.cert_k > 0.0 && cert_skip == 0)) ex.sync();
       ex.tick(11);
       ++it;
     }
@@ -1820,7 +1824,15 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
     } else {
       failed = io.step0 + n;
     }
-    ex.sync();
+    // accept() wrote U0: a barrier before anybody reads a neighbour's row -- the one after fill_noise of the next step,
+    // unless the noise is a scalar (no barrier there) or a dump / snapshot of this state follows; the kernels place
+    // their own barrier between the last step and the write-back
+    {
+      bool need = (PK_NOISE_OF(MODE) == NOISE_SCALAR);
+      if constexpr ((FEAT & FEAT_DUMP) != 0)
+        need = need || (io.diag_every > 0 && (n + 1) % io.diag_every == 0) || (io.snap_every > 0 && (n + 1) % io.snap_every == 0);
+      if (need) ex.sync();
+    }
     ex.tick(12);
     if constexpr ((FEAT & FEAT_DUMP) != 0) {
       if (io.diag_every > 0 && (n + 1) % io.diag_every == 0)
