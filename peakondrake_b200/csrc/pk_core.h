@@ -258,7 +258,11 @@ PK_HD void mva2(const double* A, const double* x, double* y) {
 template <int M, int MODE, int TT = 0, int VAR = 0>
 struct Thread {
   enum { NI = M - 2, FS = (VAR == 1) ? 1 : 0, ROLL = (VAR == 2) ? 1 : 0, ROLL_LITE = (VAR != 4) ? 1 : 0,
+#ifdef PK_EXP_FASTR_ALL
+         FASTR = 1 };
+#else
          FASTR = (TT > 0) ? 1 : 0 };      // fast reciprocal in the tuned single-CTA kernels (rcp_t)
+#endif
   double h1[6], h2[6];            // FS: (r, e, f, zb, zw1, zw2) of the two previously eliminated interior rows
   static PK_HD int TN(const Params& p) { return TT > 0 ? TT : p.T; }
   // geometry

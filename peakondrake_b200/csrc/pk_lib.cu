@@ -426,12 +426,14 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
       return fail(nullptr, "pk_create: no cluster layout for ne=%d (threads %d)", ne, p.T);
     }
     c->cluster = C; c->block = Tc; c->lgTc = lg; c->smem = sm;
-    // two CTAs per SM (two clusters interleaved on the same SMs) when the shared memory allows it
+    // two CTAs per SM (two clusters interleaved on the same SMs: one computes while the other waits at a cluster
+    // barrier) when the shared memory allows it -- scalar noise up to ne = 16 384.  The 128-register instantiation
+    // spills ~0.6 KB per thread, yet with the compile-time shared-memory offsets it is 14 % faster than one cluster per
+    // SM set with 255 registers (C4: 5.42e5 vs 4.76e5 realisation-steps/s, profiles/r2w_cluster_ab.log; before that
+    // change the two ran at the same rate).  PK_CLUSTER_MINB=1 keeps one cluster per SM set.
     c->cminb = 1;
-    // (since the Schur solve is partitioned by CTA the spill-free 255-register variant with ONE cluster per SM set is
-    //  as fast or faster -- C4 3.91e5 vs 3.85e5 realisation-steps/s -- so sharing is opt-in: PK_CLUSTER_MINB=2)
     const char* e2 = getenv("PK_CLUSTER_MINB");
-    if (e2 && atoi(e2) == 2 && Tc == 256 && p.mode == NOISE_SCALAR && 2 * (sm + 1024) <= 227 * 1024) {
+    if (!(e2 && atoi(e2) == 1) && cfg->scheme != 1 && Tc == 256 && p.M <= 8 && p.mode == NOISE_SCALAR && 2 * (sm + 1024) <= 227 * 1024) {
       // does the 128-register variant really get two CTAs per SM?
       cudaSetDevice(cfg->device);
       const void* k2 = (const void*)pick_cluster_kernel(p, Tc, 2);

@@ -26,13 +26,17 @@ print(json.dumps(dict(layout=eng.layout, rate=R * K / sorted(ms)[1] * 1e3, its=f
 eng.close()
 ''' % ROOT
 import numpy as np
-CASES = [('c4', 'default', {}), ('c4', 'runtime shared-memory offsets (round-2 midpoint)', {'PK_CLUSTER_GENERIC': '1'}),
+LIB = lambda n: {'PK_LIB_PATH': os.path.join(ROOT, 'peakondrake_b200', 'libpeakon_b200_%s.so' % n)}
+CASES = [('c4', 'default', {}), ('c4', 'two clusters per SM set (128 registers)', {'PK_CLUSTER_MINB': '2'}),
+         ('c4', 'fast reciprocal', LIB('fastr')), ('c5', 'fast reciprocal', LIB('fastr')),
+         ('c4', 'relaxed cluster barrier', LIB('relaxed')), ('c5', 'relaxed cluster barrier', LIB('relaxed')), ('c4', 'runtime shared-memory offsets (round-2 midpoint)', {'PK_CLUSTER_GENERIC': '1'}),
          ('c5', 'runtime shared-memory offsets', {'PK_CLUSTER_GENERIC': '1'}), ('c4', '4096x4 in 8 CTAs of 512', {'PK_FORCE_TM': '4096,5', 'PK_FORCE_CLUSTER': '8'}),
          ('c4', '4096x4 in 16 CTAs of 256', {'PK_FORCE_TM': '4096,5'}),
          ('c5', 'default (2048x10)', {}), ('c5', '4096x5 in 16 CTAs of 256', {'PK_NO_WIDE_CHUNKS': '1'}),
          ('c5', '4096x5 in 8 CTAs of 512', {'PK_NO_WIDE_CHUNKS': '1', 'PK_FORCE_CLUSTER': '8'})]
 if os.environ.get('QUICK', '0') == '1':
     CASES = [c for c in CASES if 'CTAs of' not in c[1]]
+CASES = [c for c in CASES if 'PK_LIB_PATH' not in c[2] or os.path.exists(c[2]['PK_LIB_PATH'])]
 CASES.sort(key=lambda c: c[0])
 ref = {}
 for mesh, name, envx in CASES:
