@@ -374,7 +374,7 @@ struct SharedClusterT {
 };
 typedef SharedClusterT<0> SharedCluster;
 
-template <class ThT, int TCC = 0>
+template <class ThT, int TCC = 0, bool ONEWARP = false>
 struct GpuExecClusterT {
   typedef ThT Th;
   static __device__ __forceinline__ int bdim() { return TCC > 0 ? TCC : (int)blockDim.x; }
@@ -387,19 +387,34 @@ struct GpuExecClusterT {
   __device__ __forceinline__ GpuExecClusterT(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
   template <class F> __device__ __forceinline__ void each(F f) { f(th); }
   template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, bdim(), rank == 0, g0, g1); }
-  // Cluster barrier.  cg's sync() arrives with release semantics, which ptxas turns into MEMBAR.ALL.GPU + ERRBAR in front
-  // of every arrive (22 % of the kernel's stall samples sit on these and on the wait).  Everything the CTAs of a cluster
-  // exchange lives in shared memory and is written by its owner, so a CTA-scope fence (the owner's stores and its
-  // outstanding DSMEM loads are performed) followed by a RELAXED arrive is enough on the hardware: measured +6 % on
-  // BASELINE config 4 (4.14e5 vs 3.92e5 realisation-steps/s), parity green.  The PTX memory model does not promise it for
-  // DSMEM readers, so it is compiled only into -DPK_RELAXED_CLUSTER_BARRIER experiment builds.
+  // Cluster barrier.  cg's sync() lets EVERY thread arrive with release semantics, which ptxas turns into
+  // MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every UCGABAR_ARV: with 256-512 threads per SM doing that ~20 times
+  // per timestep it was the largest single cost of the cluster kernels (a build whose threads arrive RELAXED behind a
+  // CTA-scope fence runs 19 % faster on BASELINE config 4 -- profiles/r2z_cluster_ab.log -- but the PTX memory model
+  // does not promise DSMEM readers anything for it).  The barrier below keeps the release, once per CTA: a block barrier
+  // makes every thread's shared-memory accesses happen-before warp 0, warp 0 alone arrives with RELEASE semantics at
+  // cluster scope (cumulative: it covers what it observed through the block barrier -- the pattern of a grid barrier,
+  // bar.sync / one thread fences and signals / bar.sync), the other warps arrive relaxed, everybody waits with ACQUIRE.
+  // Measured (profiles/r2za_cluster_ab.log): +4 % with two CTAs per SM (512 threads no longer issue the GPU-scope fence:
+  // C4 5.42e5 -> 5.65e5), -2 % with one CTA per SM (the extra block barrier; C5 4.33e5 -> 4.23e5): ONEWARP is set by the
+  // two-CTAs-per-SM instantiations only.  What remains is the latency of the one MEMBAR.ALL.GPU on the critical path.
+  // -DPK_CG_CLUSTER_BARRIER restores cg::cluster_group::sync() everywhere.
   __device__ __forceinline__ void sync() {
-#ifdef PK_RELAXED_CLUSTER_BARRIER
+#if defined(PK_RELAXED_CLUSTER_BARRIER)
     __threadfence_block();
     asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-#else
+#elif defined(PK_CG_CLUSTER_BARRIER)
     cg::this_cluster().sync();
+#else
+    if (ONEWARP) {
+      __syncthreads();
+      if (threadIdx.x < 32) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+      cg::this_cluster().sync();
+    }
 #endif
   }
 #ifdef PK_PROFILE
@@ -669,7 +684,7 @@ struct GpuExecClusterT {
   }
 };
 
-template <int M, int MODE, int TCC = 0> using GpuExecCluster = GpuExecClusterT<Thread<M, MODE, 0>, TCC>;
+template <int M, int MODE, int TCC = 0, bool ONEWARP = false> using GpuExecCluster = GpuExecClusterT<Thread<M, MODE, 0>, TCC, ONEWARP>;
 
 // TCC = TB: launched with exactly TB threads per CTA (the production layouts); TCC = 0: any block size <= TB (forced
 // cluster layouts of small meshes in the tests)
@@ -706,7 +721,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   Thread<M, MODE, 0> th;
   th.init(p, t0 + (int)threadIdx.x);
   sh.set_neighbours(smem, th.tl, th.tr);
-  GpuExecCluster<M, MODE, TCC> ex(th, red);
+  GpuExecCluster<M, MODE, TCC, (MINB > 1)> ex(th, red);
   ex.rank = rank; ex.C = C; ex.g0 = g0; ex.g1 = g1; ex.part = a.part;
 #ifdef PK_PROFILE
   __shared__ long long tb[16];
@@ -721,7 +736,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
   io.snap_every = a.snap_every; io.snap_u = a.snap_u; io.snap_flag = a.snap_flag;
-  run_steps<M, MODE, 0, GpuExecCluster<M, MODE, TCC>, Thread<M, MODE, 0>, SharedClusterT<TCC> >(ex, p, sh, io);
+  run_steps<M, MODE, 0, GpuExecCluster<M, MODE, TCC, (MINB > 1)>, Thread<M, MODE, 0>, SharedClusterT<TCC> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
 #ifdef PK_PROFILE
   if (a.prof && rank == 0 && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];
