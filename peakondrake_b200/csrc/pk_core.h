@@ -107,6 +107,7 @@ struct DrawSlot { int mine = 0, k = 0; };
 
 enum { XB_SLOTS = 18, XB_SLOTS_PP = 30, XB_PP_BASE = 16 };   // _PP: room for a second PCR row buffer (slots 16..29;
                                                              // 16, 17 are dead while the PCR runs, 14, 15 receive its result)
+static_assert(XB_SLOTS == 18 && XB_SLOTS_PP == 30, "cluster_xb_doubles() in pk_params.h sizes the exchange area with these");
 
 // natural row index i in [0, ne)  ->  interleaved slot j*T + t
 PK_HD int row_slot(const Params& p, int i) {
@@ -1731,22 +1732,34 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
         } else {
           ex.each([&](Th& th) { th.reduce_publish(p, sh); });
         }
-        ex.sync();
+        // single row buffer + partitioned solve: the barrier after reduce_build was cluster-wide (the neighbours have read
+        // the tips that the publish overwrote); the first PCR steps read rows of the own CTA only
+        if (ex.partitioned() && !ex.pingpong()) ex.sync_local(); else ex.sync();
         ex.tick(6);
         if (ex.partitioned()) {
           // segment-local PCR (block-local barriers and loads), then PCR among the C separators
           const int Tc = ex.tc(), Cn = Tn / Tc;
-          // separators solved redundantly in every CTA when the idle row buffer can hold the scratch rows
-          const bool red = ex.redundant() && 14 * Tc >= Th::sep_scratch_doubles(Cn);
+          // separators solved redundantly in every CTA when the idle row buffer (or, with a single row buffer, the
+          // scratch area behind the exchange slots) can hold the scratch rows
+          const bool red = ex.redundant() && (!ex.pingpong() || 14 * Tc >= Th::sep_scratch_doubles(Cn));
           for (int d = 1; d <= Tc - 2; d *= 2) {
-            ex.each([&](Th& th) { th.pcr_step_local(p, sh, d, base, Tc); th.reduce_publish(p, sh, XB_PP_BASE - base, red && (th.t & (Tc - 1)) == 0); });
-            base = XB_PP_BASE - base;
-            if (2 * d <= Tc - 2) ex.sync_local();
+            if (ex.pingpong()) {
+              ex.each([&](Th& th) { th.pcr_step_local(p, sh, d, base, Tc); th.reduce_publish(p, sh, XB_PP_BASE - base, red && (th.t & (Tc - 1)) == 0); });
+              base = XB_PP_BASE - base;
+              if (2 * d <= Tc - 2) ex.sync_local();
+            } else {
+              // one row buffer (18 exchange slots instead of 30: room for a second CTA per SM): read, barrier, publish
+              ex.each([&](Th& th) { th.pcr_step_local(p, sh, d, 0, Tc); });
+              ex.sync_local();
+              ex.each([&](Th& th) { th.reduce_publish(p, sh, 0, red && (th.t & (Tc - 1)) == 0); });
+              if (2 * d <= Tc - 2) ex.sync_local();
+            }
           }
           ex.sync();
           ex.tick(13);
           if (red) {
-            const int scr = (XB_PP_BASE - base) * Tc;      // offset of the idle row buffer in the CTA's exchange area
+            // scratch of the separator solve: the idle row buffer, or the area behind the XB_SLOTS exchange slots
+            const int scr = ex.pingpong() ? (XB_PP_BASE - base) * Tc : XB_SLOTS * Tc;
             ex.each_cta_first(Cn, [&](Th& th) { th.sep_build(p, sh, base, Tc, Cn, scr); });
             ex.sync_local();
             int half = 0;

@@ -374,7 +374,9 @@ struct SharedClusterT {
 };
 typedef SharedClusterT<0> SharedCluster;
 
-template <class ThT, int TCC = 0, bool ONEWARP = false>
+// PP: second PCR row buffer in the exchange area (XB_SLOTS_PP slots; one barrier per PCR step) -- false in the
+// two-CTAs-per-SM instantiations, which keep ONE row buffer (XB_SLOTS slots + a scratch area for the separator solve)
+template <class ThT, int TCC = 0, bool ONEWARP = false, bool PP = true>
 struct GpuExecClusterT {
   typedef ThT Th;
   static __device__ __forceinline__ int bdim() { return TCC > 0 ? TCC : (int)blockDim.x; }
@@ -435,13 +437,13 @@ struct GpuExecClusterT {
     return v != 0;
   }
   __device__ __forceinline__ bool hybrid(int) const { return false; }     // rows are spread over the CTAs of the cluster
-  __device__ __forceinline__ bool pingpong() const { return true; }       // XB_SLOTS_PP exchange slots: one cluster barrier per PCR step
+  __device__ __forceinline__ bool pingpong() const { return PP; }         // XB_SLOTS_PP exchange slots: one barrier per PCR step
   // Schur solve partitioned by CTA (pk_core.h, pcr_step_local): the PCR steps inside a CTA need block barriers and
   // block-local loads only; the C separator rows are solved by the leading threads.  part = 0 keeps the flat PCR
   // over all C*Tc rows (every step a cluster barrier and, from stride Tc/2 on, DSMEM-bandwidth-bound row loads).
   int part;
   __device__ __forceinline__ bool partitioned() const { return part != 0; }
-  __device__ __forceinline__ bool redundant() const { return part == 1; }      // part = 2: separators by the leading threads
+  __device__ __forceinline__ bool redundant() const { return part == 1 || !PP; }      // part = 2: separators by the leading threads
   template <class F> __device__ __forceinline__ void each_cta_first(int n, F f) { if ((int)threadIdx.x < n) f(th); }
   __device__ __forceinline__ int tc() const { return bdim(); }
   __device__ __forceinline__ void sync_local() { __syncthreads(); }
@@ -684,7 +686,7 @@ struct GpuExecClusterT {
   }
 };
 
-template <int M, int MODE, int TCC = 0, bool ONEWARP = false> using GpuExecCluster = GpuExecClusterT<Thread<M, MODE, 0>, TCC, ONEWARP>;
+template <int M, int MODE, int TCC = 0, bool ONEWARP = false, bool PP = true> using GpuExecCluster = GpuExecClusterT<Thread<M, MODE, 0>, TCC, ONEWARP, PP>;
 
 // TCC = TB: launched with exactly TB threads per CTA (the production layouts); TCC = 0: any block size <= TB (forced
 // cluster layouts of small meshes in the tests)
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   if (MODE == NOISE_FULL) { sh.G = nxt; sh.X = nxt + n; sh.Xx = nxt + 2 * n; sh.Xxx = nxt + 3 * n; nxt += 4 * n; }
   else if (PK_NOISE_OF(MODE) == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
-  sh.xb = nxt; nxt += XB_SLOTS_PP * Tc;
+  sh.xb = nxt; nxt += cluster_xb_doubles(Tc, MINB > 1);      // two CTAs per SM: one row buffer + separator scratch
   double* red = nxt; nxt += cluster_red_doubles(Tc);
   sh.dW = nxt;
 
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   Thread<M, MODE, 0> th;
   th.init(p, t0 + (int)threadIdx.x);
   sh.set_neighbours(smem, th.tl, th.tr);
-  GpuExecCluster<M, MODE, TCC, (MINB > 1)> ex(th, red);
+  GpuExecCluster<M, MODE, TCC, (MINB > 1), (MINB <= 1)> ex(th, red);
   ex.rank = rank; ex.C = C; ex.g0 = g0; ex.g1 = g1; ex.part = a.part;
 #ifdef PK_PROFILE
   __shared__ long long tb[16];
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
   io.snap_every = a.snap_every; io.snap_u = a.snap_u; io.snap_flag = a.snap_flag;
-  run_steps<M, MODE, 0, GpuExecCluster<M, MODE, TCC, (MINB > 1)>, Thread<M, MODE, 0>, SharedClusterT<TCC> >(ex, p, sh, io);
+  run_steps<M, MODE, 0, GpuExecCluster<M, MODE, TCC, (MINB > 1), (MINB <= 1)>, Thread<M, MODE, 0>, SharedClusterT<TCC> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
 #ifdef PK_PROFILE
   if (a.prof && rank == 0 && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];

@@ -11,9 +11,7 @@
 template <int M> static ckern_t pick_cmode(int mode, int Tc, int minb) {
   if (Tc <= 256) {
     // two clusters share the SMs when two CTAs fit one SM's shared memory (128 registers per thread)
-    if constexpr (M <= 8) {
-      if (minb == 2 && mode == NOISE_SCALAR) return Tc == 256 ? pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2, 256> : pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2>;
-    }
+    if (minb == 2 && mode == NOISE_SCALAR) return Tc == 256 ? pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2, 256> : pk_step_cluster_kernel<M, NOISE_SCALAR, 256, 2>;
     const char* gen = getenv("PK_CLUSTER_GENERIC");      // A/B: the runtime-offset instantiation for every block size
     if (Tc == 256 && !(gen && atoi(gen) == 1)) {
       switch (mode) {

@@ -420,27 +420,31 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     int lg = 0; while ((1 << lg) < Tc) ++lg;
     const size_t sm = cfg->scheme == 1
         ? sizeof(double) * ((size_t)UW_SLOTS * Tc + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1) + 2)
-        : sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)XB_SLOTS_PP * Tc + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1));
+        : sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)cluster_xb_doubles(Tc, false) + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1));
+    // two CTAs per SM: one PCR row buffer + separator scratch instead of two row buffers
+    const size_t sm2 = sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)cluster_xb_doubles(Tc, true) + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1));
     if (C < 2 || C > 16 || (C & (C - 1)) || Tc < 32 || C * Tc != p.T || sm > 227 * 1024) {
       const int ne = p.ne; delete c;
       return fail(nullptr, "pk_create: no cluster layout for ne=%d (threads %d)", ne, p.T);
     }
     c->cluster = C; c->block = Tc; c->lgTc = lg; c->smem = sm;
     // two CTAs per SM (two clusters interleaved on the same SMs: one computes while the other waits at a cluster
-    // barrier) when the shared memory allows it -- scalar noise up to ne = 16 384.  The 128-register instantiation
-    // spills ~0.6 KB per thread, yet with the compile-time shared-memory offsets it is 14 % faster than one cluster per
-    // SM set with 255 registers (C4: 5.42e5 vs 4.76e5 realisation-steps/s, profiles/r2w_cluster_ab.log; before that
-    // change the two ran at the same rate).  PK_CLUSTER_MINB=1 keeps one cluster per SM set.
+    // barrier) when the shared memory allows it -- scalar noise.  These instantiations keep ONE PCR row buffer (18 exchange
+    // slots + separator scratch instead of 30 slots: -22 KB per CTA at 256 threads, so that the ne = 20 000 mesh fits as
+    // well and the spills of the 128-register code find room in L1).  With the compile-time shared-memory offsets two
+    // clusters per SM set are 14 % faster than one with 255 registers (C4: 5.42e5 vs 4.76e5 realisation-steps/s,
+    // profiles/r2w_cluster_ab.log; before that change the two ran at the same rate).  PK_CLUSTER_MINB=1 keeps one.
     c->cminb = 1;
     const char* e2 = getenv("PK_CLUSTER_MINB");
-    if (!(e2 && atoi(e2) == 1) && cfg->scheme != 1 && Tc == 256 && p.M <= 8 && p.mode == NOISE_SCALAR && 2 * (sm + 1024) <= 227 * 1024) {
+    if (!(e2 && atoi(e2) == 1) && cfg->scheme != 1 && Tc <= 256 && Tc >= 32 && p.mode == NOISE_SCALAR && 2 * (sm2 + 1024) <= 227 * 1024) {
       // does the 128-register variant really get two CTAs per SM?
       cudaSetDevice(cfg->device);
       const void* k2 = (const void*)pick_cluster_kernel(p, Tc, 2);
       int per_sm = 0;
-      if (k2 && cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess &&
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, Tc, sm) == cudaSuccess && per_sm >= 2)
-        c->cminb = 2;
+      if (k2 && cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2, Tc, sm2) == cudaSuccess && per_sm >= 2) {
+        c->cminb = 2; c->smem = sm2;
+      }
       cudaGetLastError();
     }
   }

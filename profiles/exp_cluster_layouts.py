@@ -29,7 +29,8 @@ import numpy as np
 LIB = lambda n: {'PK_LIB_PATH': os.path.join(ROOT, 'peakondrake_b200', 'libpeakon_b200_%s.so' % n)}
 CASES = [('c4', 'default', {}), ('c4', 'generic, 1 cluster/SM set', {'PK_CLUSTER_GENERIC': '1', 'PK_CLUSTER_MINB': '1'}),
          ('c4', 'generic, clusters of 16 x 128 threads', {'PK_CLUSTER_GENERIC': '1', 'PK_FORCE_CLUSTER': '16'}),
-         ('c5', 'generic, clusters of 16 x 128 threads', {'PK_CLUSTER_GENERIC': '1', 'PK_FORCE_CLUSTER': '16'}), ('c4', 'two clusters per SM set (128 registers)', {'PK_CLUSTER_MINB': '2'}),
+         ('c5', 'generic, clusters of 16 x 128 threads', {'PK_CLUSTER_GENERIC': '1', 'PK_FORCE_CLUSTER': '16'}), ('c4', 'one cluster per SM set (255 registers, two row buffers)', {'PK_CLUSTER_MINB': '1'}),
+         ('c5', 'one cluster per SM set (255 registers, two row buffers)', {'PK_CLUSTER_MINB': '1'}),
          ('c4', 'fast reciprocal', LIB('fastr')), ('c5', 'fast reciprocal', LIB('fastr')),
          ('c4', 'relaxed cluster barrier', LIB('relaxed')), ('c5', 'relaxed cluster barrier', LIB('relaxed')), ('c4', 'runtime shared-memory offsets (round-2 midpoint)', {'PK_CLUSTER_GENERIC': '1'}),
          ('c5', 'runtime shared-memory offsets', {'PK_CLUSTER_GENERIC': '1'}), ('c4', '4096x4 in 8 CTAs of 512', {'PK_FORCE_TM': '4096,5', 'PK_FORCE_CLUSTER': '8'}),

@@ -16,6 +16,7 @@
 
 using namespace pk;
 
+static int g_emu_pp = 1;          // cluster emulation: two PCR row buffers (1) or the single-buffer layout of the two-CTAs-per-SM kernels (0)
 static int g_emu_part = 1;        // cluster emulation: Schur solve partitioned by CTA (1, like the device) or flat PCR (0)
 static int g_emu_cert = 1;        // 0: always evaluate the last residual (no convergence certificate)
 static int g_emu_hybrid = 0;      // 1: compacted Schur solve (hyb_* in pk_core.h) where T >= 32; 0: plain PCR
@@ -93,9 +94,9 @@ struct EmuExecT {
   template <class F> void one(F f) { f(); }
   bool any_flag(int* flag) const { return *flag != 0; }
   bool hybrid(int Tn) const { return g_emu_hybrid && C == 1 && Tn >= 32; }
-  bool pingpong() const { return C > 1; }      // like the cluster kernel: XB_SLOTS_PP slots
+  bool pingpong() const { return C > 1 && g_emu_pp; }      // like the cluster kernels: XB_SLOTS_PP slots, or one row buffer
   bool partitioned() const { return C > 1 && g_emu_part; }
-  bool redundant() const { return g_emu_part == 1; }
+  bool redundant() const { return g_emu_part == 1 || !g_emu_pp; }
   template <class F> void each_cta_first(int n, F f) {
     for (int c = 0; c < C; ++c)
       for (int k = 0; k < n && k < Tc; ++k) { const int kk = order == 0 ? k : n - 1 - k; cur = c; f(th[c * Tc + kk]); }
@@ -166,13 +167,14 @@ struct EmuExecT {
 template <int M, int MODE>
 static int run_one_cluster(const Params& p, StepIO io, double* u, double* u1, double* dF, double* dG, int order, int C) {
   const int Tc = p.T / C, n = Tc * p.M;
-  std::vector<std::vector<double> > bufs(C, std::vector<double>(7 * n + XB_SLOTS_PP * Tc + (p.nxi > 0 ? p.nxi : 1), 0.0));
+  const int nxb = std::max(cluster_xb_doubles(Tc, false), cluster_xb_doubles(Tc, true));
+  std::vector<std::vector<double> > bufs(C, std::vector<double>(7 * n + nxb + (p.nxi > 0 ? p.nxi : 1), 0.0));
   EmuExec<M, MODE> ex(p, order, C);
   int bad = 0;
   EmuSharedCluster sh;
   double* z = (double*)0;
   sh.U0 = z; sh.U1 = z + n; sh.F = z + 2 * n; sh.G = z + 3 * n; sh.X = z + 4 * n; sh.Xx = z + 5 * n; sh.Xxx = z + 6 * n;
-  sh.xb = z + 7 * n; sh.dW = z + 7 * n + XB_SLOTS_PP * Tc;
+  sh.xb = z + 7 * n; sh.dW = z + 7 * n + nxb;
   sh.bufs = &bufs; sh.Tc = Tc; sh.nxi_ = p.nxi; sh.cur = &ex.cur; sh.bad = &bad;
   sh.lgTc = 0; while ((1 << sh.lgTc) < Tc) ++sh.lgTc;
   sh.lgT = 0; while ((1 << sh.lgT) < p.T) ++sh.lgT;
@@ -264,6 +266,7 @@ extern "C" int pk_emu_set_fs(int on) { g_emu_fs = on; return 0; }
 extern "C" int pk_emu_set_hybrid(int on) { g_emu_hybrid = on; return 0; }
 extern "C" int pk_emu_set_certificate(int on) { g_emu_cert = on; return 0; }
 extern "C" int pk_emu_set_partitioned(int on) { g_emu_part = on; return 0; }
+extern "C" int pk_emu_set_pingpong(int on) { g_emu_pp = on; return 0; }
 
 // fused dumps (StepIO::diag_every etc.) for the next pk_emu_step calls; every = 0 switches them off
 static int g_dump_every = 0; static double* g_dump_out = nullptr; static int* g_dump_idx = nullptr;

@@ -147,6 +147,29 @@ def test_cluster_layout_emulated(ne, C, part):
         L.pk_emu_set_partitioned(1)
 
 
+@pytest.mark.parametrize('ne,C', [(1000, 4), (2000, 8), (512, 4), (200, 2)])
+def test_cluster_single_row_buffer_emulated(ne, C):
+    """The two-CTAs-per-SM cluster kernels keep ONE PCR row buffer (18 exchange slots + separator scratch instead of 30
+    slots): a block barrier between the reads and the publish of every segment-local PCR step, the cluster barrier after
+    reduce_build.  Same arithmetic as the two-buffer layout: against the oracle, and bit for bit against that layout.
+    (Needs at least as many threads per CTA as CTAs per cluster: every CTA solves the separator system itself.)"""
+    L = lib()
+    try:
+        assert L.pk_emu_set_cluster(C) == 0
+        L.pk_emu_set_pingpong(0)
+        compare(ne, nsteps=3, nxi=2)
+        compare(ne, nsteps=2, fam='constant', nxi=1, ic='periodic_peakon', sigma=0.5)
+        assert L.pk_emu_set_cluster(C) == 0          # no non-local stores happened
+        outs = []
+        for pp in (0, 1):
+            L.pk_emu_set_pingpong(pp)
+            outs.append(compare(ne, nsteps=3, fam='constant', nxi=1, sigma=0.3))
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    finally:
+        L.pk_emu_set_pingpong(1)
+        L.pk_emu_set_cluster(1)
+
+
 @pytest.mark.parametrize('ne,T,M,C', [(2500, 256, 10, 8), (2200, 256, 9, 4), (2350, 256, 10, 1), (1250, 128, 10, 2)])
 def test_wide_chunk_layouts_emulated(ne, T, M, C):
     """9 or 10 rows per thread (choose_layout_wide): what the cluster kernels use where the standard layout would end
