@@ -78,6 +78,13 @@ struct Shared {
   // through two per-thread pointers that already name the owning CTA)
   PK_HD double ldL(const double* a, int c, int T, int q) const { return a[c * T + q]; }
   PK_HD double ldR(const double* a, int c, int T, int q) const { return a[c * T + q]; }
+  // the tips a chunk publishes for the separator rows of its right neighbour (exchange slots 0..13), and the separator
+  // solution (slots 14, 15) of the right neighbour: plain slots here; the two-CTAs-per-SM cluster kernels route the
+  // accesses of their edge threads through CTA-local copies, which turns two cluster barriers per Newton iteration
+  // into block barriers (pk_kernels.cuh, SharedClusterT)
+  PK_HD void stTip(int c, int T, int t, double v) const { xb[c * T + t] = v; }
+  PK_HD double ldTip(int c, int T, int q) const { return xb[c * T + q]; }
+  PK_HD double ldXsR(int c, int T, int q) const { return xb[(14 + c) * T + q]; }
   // pairs of doubles (16-byte shared-memory accesses): pair slot q of thread tt lives at doubles 2 (q T + tt), +1.
   // Used for the PCR rows, which travel as whole 2x2 blocks.
   PK_HD void ld2(const double* a, int q, int T, int tt, double& v0, double& v1) const {
@@ -651,8 +658,8 @@ struct Thread {
     const double qp = sh.ldR(sh.xb, 17, TN(p), tr);
     if (ext) finish_row(p, M - 1, cp, qp); else finish_row(p, M - 2, cp, qp);
     // publish my last node's Cm,Qm for the right neighbour's separator row 0
-    sh.sto(sh.xb, 10, TN(p), t, wCm1[0]); sh.sto(sh.xb, 11, TN(p), t, wCm1[1]); sh.sto(sh.xb, 12, TN(p), t, wCm1[2]);
-    sh.sto(sh.xb, 13, TN(p), t, wQm1);
+    sh.stTip(10, TN(p), t, wCm1[0]); sh.stTip(11, TN(p), t, wCm1[1]); sh.stTip(12, TN(p), t, wCm1[2]);
+    sh.stTip(13, TN(p), t, wQm1);
 
     tips_registers(p, sh);
   }
@@ -688,22 +695,22 @@ struct Thread {
     PK_UNROLL
     for (int c = 0; c < 5; ++c) { L2b[c] = ext ? xa[c] : xb_[c]; L2a[c] = ext ? xb_[c] : xc[c]; }
     // slots 0..9: tips at the LAST two interior rows, read by the right neighbour
-    sh.sto(sh.xb, 0, TN(p), t, L2a[0]); sh.sto(sh.xb, 1, TN(p), t, L2b[0]);
-    sh.sto(sh.xb, 2, TN(p), t, L2a[1]); sh.sto(sh.xb, 3, TN(p), t, L2a[2]);
-    sh.sto(sh.xb, 4, TN(p), t, L2b[1]); sh.sto(sh.xb, 5, TN(p), t, L2b[2]);
-    sh.sto(sh.xb, 6, TN(p), t, L2a[3]); sh.sto(sh.xb, 7, TN(p), t, L2a[4]);
-    sh.sto(sh.xb, 8, TN(p), t, L2b[3]); sh.sto(sh.xb, 9, TN(p), t, L2b[4]);
+    sh.stTip(0, TN(p), t, L2a[0]); sh.stTip(1, TN(p), t, L2b[0]);
+    sh.stTip(2, TN(p), t, L2a[1]); sh.stTip(3, TN(p), t, L2a[2]);
+    sh.stTip(4, TN(p), t, L2b[1]); sh.stTip(5, TN(p), t, L2b[2]);
+    sh.stTip(6, TN(p), t, L2a[3]); sh.stTip(7, TN(p), t, L2a[4]);
+    sh.stTip(8, TN(p), t, L2b[3]); sh.stTip(9, TN(p), t, L2b[4]);
   }
 
   // ---- phase B1: build the reduced (Schur) block row of my separator pair -------------------
   template <class SH>
   PK_HD void reduce_build(const Params& p, const SH& sh) {
     const int T = TN(p);
-    const double yL[2] = {sh.ldL(sh.xb, 0, T, tl), sh.ldL(sh.xb, 1, T, tl)};
-    const double WL[4] = {sh.ldL(sh.xb, 2, T, tl), sh.ldL(sh.xb, 3, T, tl), sh.ldL(sh.xb, 4, T, tl), sh.ldL(sh.xb, 5, T, tl)};
-    const double VL[4] = {sh.ldL(sh.xb, 6, T, tl), sh.ldL(sh.xb, 7, T, tl), sh.ldL(sh.xb, 8, T, tl), sh.ldL(sh.xb, 9, T, tl)};
-    sp0[0] += sh.ldL(sh.xb, 10, T, tl); sp0[1] += sh.ldL(sh.xb, 11, T, tl); sp0[2] += sh.ldL(sh.xb, 12, T, tl);
-    sb0 -= sh.ldL(sh.xb, 13, T, tl);
+    const double yL[2] = {sh.ldTip(0, T, tl), sh.ldTip(1, T, tl)};
+    const double WL[4] = {sh.ldTip(2, T, tl), sh.ldTip(3, T, tl), sh.ldTip(4, T, tl), sh.ldTip(5, T, tl)};
+    const double VL[4] = {sh.ldTip(6, T, tl), sh.ldTip(7, T, tl), sh.ldTip(8, T, tl), sh.ldTip(9, T, tl)};
+    sp0[0] += sh.ldTip(10, T, tl); sp0[1] += sh.ldTip(11, T, tl); sp0[2] += sh.ldTip(12, T, tl);
+    sb0 -= sh.ldTip(13, T, tl);
     const double E[4] = {sp0[0], sp0[1], 0.0, sp1[0]};
     const double C[4] = {sp0[2], sp0[3], sp1[1], sp1[2]};
     const double Gc[4] = {sp0[4], 0.0, sp1[3], sp1[4]};
@@ -1069,7 +1076,7 @@ struct Thread {
   template <class SH>
   PK_HD void interior_solve(const Params& p, const SH& sh) {
     const int T = TN(p);
-    double xp1 = sh.ldR(sh.xb, 14, T, tr), xp2 = sh.ldR(sh.xb, 15, T, tr);
+    double xp1 = sh.ldXsR(0, T, tr), xp2 = sh.ldXsR(1, T, tr);
     du[0] = xs0; du[1] = xs1;
     PK_UNROLL
     for (int k = NI - 1; k >= 0; --k) {
@@ -1110,7 +1117,7 @@ struct Thread {
         const double a1 = 0.5 * (ldn(p, sh, sh.U0, q) + ldn(p, sh, sh.U1, q));
         double x1 = 0.0, y1 = 0.0;
         if (MODE == NOISE_FULL) { x1 = ldn(p, sh, sh.Xx, q); y1 = ldn(p, sh, sh.Xxx, q); }
-        const double d1 = (q < M - 1 || (q == M - 1 && ext)) ? get_du(p, sh, q) : sh.ldR(sh.xb, 14, T, tr);
+        const double d1 = (q < M - 1 || (q == M - 1 && ext)) ? get_du(p, sh, q) : sh.ldXsR(0, T, tr);
         const double s1 = a1 + d1, b1 = a1 + 0.5 * d1;      // uh + du and uh + e at the right node of the cell
         const double ss = s0 + s1;
         const double cdd = p.c2k * (a1 - a0) * (s1 - s0);        // (constants carry the 1/kappa of the filter)
@@ -1701,7 +1708,10 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
       if (status) break;
       // ---- linear solve + update ----
       ex.each([&](Th& th) { th.reduce_build(p, sh); });
-      if (!ex.pingpong()) ex.sync();         // the publish below reuses the slots the neighbours read their tips from
+      // the publish below reuses the slots the neighbours read their tips from: a barrier first, unless there is a second
+      // row buffer.  (Single buffer + partitioned solve: the edge threads exchange the tips through a separate area, see
+      // SharedClusterT, so the readers of these slots are all in the own CTA.)
+      if (!ex.pingpong()) { if (ex.partitioned()) ex.sync_local(); else ex.sync(); }
       const int Tn = (TT > 0 ? TT : p.T);
       if (ex.hybrid(Tn)) {
         // cyclic reduction (compacted onto the leading threads) -> 32 rows -> PCR inside warp 0 -> back-substitution
@@ -1807,7 +1817,9 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
           ex.tick(7);
           ex.each([&](Th& th) { th.pcr_final(p, sh, base); });
         }
-        ex.sync();
+        // the separator solution of the right neighbour feeds the interior solve: a thread of the own CTA, or -- edge
+        // thread of a single-buffer cluster kernel -- the next segment's separator in the CTA's own scratch rows
+        if (ex.partitioned() && !ex.pingpong()) ex.sync_local(); else ex.sync();
         ex.tick(8);
       }
       if constexpr (Th::FS) ex.each([&](Th& th) { th.interior_solve_fs(p, sh); });

@@ -319,9 +319,26 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
 template <int TCC> struct Log2C { enum { v = 1 + Log2C<TCC / 2>::v }; };
 template <> struct Log2C<1> { enum { v = 0 }; };
 template <> struct Log2C<0> { enum { v = 0 }; };
-template <int TCC = 0>
+// CMP ("compact", the two-CTAs-per-SM instantiations): one PCR row buffer; behind the 18 exchange slots lie the scratch
+// rows of the separator solve and a 14-double EDGE area that holds a copy of the tips of the CTA's last thread.
+template <int TCC = 0, bool CMP = false>
 struct SharedClusterT {
   double *U0, *U1, *F, *G, *X, *Xx, *Xxx, *xb, *dW;
+  // CMP: my copy of the last thread's tips, the left CTA's copy (DSMEM), the next segment's separator solution in the
+  // scratch rows of the OWN CTA (every CTA solves the separator system itself)
+  double* edge; const double *edgeL, *sepR;
+  __device__ __forceinline__ void stTip(int c, int, int, double v) const {
+    xb[c * tcn() + (int)threadIdx.x] = v;
+    if (CMP && (int)threadIdx.x == tcn() - 1) edge[c] = v;
+  }
+  __device__ __forceinline__ double ldTip(int c, int T, int q) const {
+    if (!CMP) return ldL(xb, c, T, q);
+    return threadIdx.x == 0 ? edgeL[c] : xb[c * tcn() + (int)threadIdx.x - 1];
+  }
+  __device__ __forceinline__ double ldXsR(int c, int T, int q) const {
+    if (!CMP) return ldR(xb, 14 + c, T, q);
+    return (int)threadIdx.x == tcn() - 1 ? sepR[c] : xb[(14 + c) * tcn() + (int)threadIdx.x + 1];
+  }
   int Tc_, lgTc_, lgT;
   unsigned rank;
   // rows of the two NEIGHBOUR threads (t-1, t+1 on the ring): generic pointers to element [0] of the neighbour's column
@@ -372,7 +389,7 @@ struct SharedClusterT {
   __device__ __forceinline__ double dw(int k) const { return dW[k]; }
   __device__ __forceinline__ void set_dw(int k, double v) const { dW[k] = v; }
 };
-typedef SharedClusterT<0> SharedCluster;
+typedef SharedClusterT<0, false> SharedCluster;
 
 // PP: second PCR row buffer in the exchange area (XB_SLOTS_PP slots; one barrier per PCR step) -- false in the
 // two-CTAs-per-SM instantiations, which keep ONE row buffer (XB_SLOTS slots + a scratch area for the separator solve)
@@ -696,7 +713,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank(), C = cluster.num_blocks();
   const int Tc = TCC > 0 ? TCC : (int)blockDim.x, n = Tc * M;
-  SharedClusterT<TCC> sh;
+  SharedClusterT<TCC, (MINB > 1)> sh;
   sh.Tc_ = Tc; sh.lgTc_ = lgTc; sh.rank = rank;
   { int lg = 0; while ((1 << lg) < p.T) ++lg; sh.lgT = lg; }
   sh.U0 = smem; sh.U1 = smem + n; sh.F = smem + 2 * n;
@@ -705,6 +722,12 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   else if (PK_NOISE_OF(MODE) == NOISE_X) { sh.G = nullptr; sh.X = nxt; sh.Xx = nullptr; sh.Xxx = nullptr; nxt += n; }
   else { sh.G = nullptr; sh.X = nullptr; sh.Xx = nullptr; sh.Xxx = nullptr; }
   sh.xb = nxt; nxt += cluster_xb_doubles(Tc, MINB > 1);      // two CTAs per SM: one row buffer + separator scratch
+  sh.edge = nullptr; sh.edgeL = nullptr; sh.sepR = nullptr;
+  if (MINB > 1) {
+    sh.edge = sh.xb + XB_SLOTS * Tc + 30 * 16;
+    sh.edgeL = cluster.map_shared_rank(sh.edge, (rank + C - 1) % C);
+    sh.sepR = sh.xb + XB_SLOTS * Tc + 28 * (int)C + 2 * (int)((rank + 1) % C);      // sep_final's solutions (pk_core.h)
+  }
   double* red = nxt; nxt += cluster_red_doubles(Tc);
   sh.dW = nxt;
 
@@ -738,7 +761,7 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   io.fail_step = a.fail_step; io.its_last = a.its_last; io.its_total = a.its_total; io.fail_reason = nullptr;
   io.diag_every = a.diag_every; io.diag_out = a.diag_out; io.diag_idx = a.diag_idx; io.suite_vals = a.suite_vals; io.suite_ids = a.suite_ids;
   io.snap_every = a.snap_every; io.snap_u = a.snap_u; io.snap_flag = a.snap_flag;
-  run_steps<M, MODE, 0, GpuExecCluster<M, MODE, TCC, (MINB > 1), (MINB <= 1)>, Thread<M, MODE, 0>, SharedClusterT<TCC> >(ex, p, sh, io);
+  run_steps<M, MODE, 0, GpuExecCluster<M, MODE, TCC, (MINB > 1), (MINB <= 1)>, Thread<M, MODE, 0>, SharedClusterT<TCC, (MINB > 1)> >(ex, p, sh, io);
   cluster.sync();     // nobody leaves while a peer may still read its shared memory
 #ifdef PK_PROFILE
   if (a.prof && rank == 0 && threadIdx.x < 16) a.prof[r * 16 + threadIdx.x] = tb[threadIdx.x];

@@ -436,7 +436,10 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
     // profiles/r2w_cluster_ab.log; before that change the two ran at the same rate).  PK_CLUSTER_MINB=1 keeps one.
     c->cminb = 1;
     const char* e2 = getenv("PK_CLUSTER_MINB");
-    if (!(e2 && atoi(e2) == 1) && cfg->scheme != 1 && Tc <= 256 && Tc >= 32 && p.mode == NOISE_SCALAR && 2 * (sm2 + 1024) <= 227 * 1024) {
+    // (the older Schur-solve variants, kept for A/B runs, need the two row buffers)
+    const char *ef = getenv("PK_CLUSTER_FLAT_PCR"), *el = getenv("PK_CLUSTER_LEADER_SEP");
+    const bool older = (ef && atoi(ef) == 1) || (el && atoi(el) == 1);
+    if (!(e2 && atoi(e2) == 1) && !older && cfg->scheme != 1 && Tc <= 256 && Tc >= 32 && p.mode == NOISE_SCALAR && 2 * (sm2 + 1024) <= 227 * 1024) {
       // does the 128-register variant really get two CTAs per SM?
       cudaSetDevice(cfg->device);
       const void* k2 = (const void*)pick_cluster_kernel(p, Tc, 2);
@@ -597,7 +600,8 @@ static int step_args(pk_ctx* c, int32_t nsteps, double* u, double* u1, double* d
   a->prof = c->d_prof;
   a->queue = nullptr; a->nblk = nsteps; a->nb = 1; a->r0 = 0; a->Rq = c->cfg.R;
   { const char* e = getenv("PK_CLUSTER_FLAT_PCR"); a->part = (e && atoi(e) == 1) ? 0 : 1;
-    e = getenv("PK_CLUSTER_LEADER_SEP"); if (a->part && e && atoi(e) == 1) a->part = 2; }
+    e = getenv("PK_CLUSTER_LEADER_SEP"); if (a->part && e && atoi(e) == 1) a->part = 2;
+    if (c->cminb == 2) a->part = 1; }      // single row buffer: separators solved redundantly per CTA
   a->R = c->cfg.R; a->step0 = (int)c->step; a->nsteps = nsteps; a->rid0 = c->cfg.rid_offset; a->seed = c->cfg.seed;
   a->diag_every = 0; a->diag_out = nullptr; a->diag_idx = nullptr; a->suite_vals = nullptr; a->suite_ids = nullptr;
   a->snap_every = 0; a->snap_u = nullptr; a->snap_flag = nullptr;

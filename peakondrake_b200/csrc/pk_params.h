@@ -66,8 +66,8 @@ PK_HD int cluster_red_half(int Tc) { return 3 * (Tc >> 5) + 6; }
 PK_HD int cluster_red_doubles(int Tc) { return 2 * cluster_red_half(Tc); }
 // exchange area of the midpoint cluster kernels: two PCR row buffers (XB_SLOTS_PP = 30 slots per thread), or -- two CTAs per
 // SM -- one row buffer (XB_SLOTS = 18 slots) + the scratch rows of the redundant separator solve (30 doubles per CTA of the
-// cluster, at most 16 CTAs)
-PK_HD int cluster_xb_doubles(int Tc, bool compact) { return compact ? 18 * Tc + 30 * 16 : 30 * Tc; }
+// cluster, at most 16 CTAs) + 16 doubles for the copy of the last thread's tips
+PK_HD int cluster_xb_doubles(int Tc, bool compact) { return compact ? 18 * Tc + 30 * 16 + 16 : 30 * Tc; }
 
 // chunk geometry
 PK_HD int chunk_rows(const Params& p, int t) { return t < p.rem ? p.M : p.M - 1; }

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(TB, 1) pk_upwind_cluster_kernel(const __grid_c
   const unsigned rank = cluster.block_rank(), C = cluster.num_blocks();
   const int Tc = blockDim.x;
   SharedCluster sh;
-  sh.Tc_ = Tc; sh.lgTc_ = lgTc; sh.rank = rank; sh.base = sh.nbL = sh.nbR = nullptr;
+  sh.Tc_ = Tc; sh.lgTc_ = lgTc; sh.rank = rank; sh.base = sh.nbL = sh.nbR = nullptr; sh.edge = nullptr; sh.edgeL = sh.sepR = nullptr;
   { int lg = 0; while ((1 << lg) < p.T) ++lg; sh.lgT = lg; }
   sh.U0 = sh.U1 = sh.F = sh.G = sh.X = sh.Xx = sh.Xxx = nullptr;
   sh.xb = smem;

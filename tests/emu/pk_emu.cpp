@@ -43,6 +43,11 @@ struct EmuSharedCluster {
   // slot c of the ring neighbour q of the calling thread (the device reads these through per-thread pointers)
   double ldL(const double* a, int c, int T, int q) const { return *at(a, c * T + q, false); }
   double ldR(const double* a, int c, int T, int q) const { return *at(a, c * T + q, false); }
+  // tips / separator solution of a ring neighbour: plain slots here (the single-buffer device kernels route their edge
+  // threads through CTA-local copies of the same values)
+  void stTip(int c, int T, int t, double v) const { *at(xb, c * T + t, true) = v; }
+  double ldTip(int c, int T, int q) const { return *at(xb, c * T + q, false); }
+  double ldXsR(int c, int T, int q) const { return *at(xb, (14 + c) * T + q, false); }
   // pairs of doubles (PCR rows): pair slot q of thread tt at doubles 2 (q Tc + tt_local), +1 in tt's CTA
   void ld2(const double* a, int q, int T, int tt, double& v0, double& v1) const {
     const int owner = tt >> lgTc;
