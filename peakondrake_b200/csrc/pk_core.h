@@ -1665,7 +1665,7 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
         // Otherwise fall through.
         if (p.cert_k > 0.0 && cert_skip == 0) {
           double n2[3];
-          ex.allreduce3([&](Th& th, double* v) { v[0] = 0.0; v[1] = th.sn2; v[2] = th.xn2; }, n2);
+          ex.allreduce3_nb([&](Th& th, double* v) { v[0] = 0.0; v[1] = th.sn2; v[2] = th.xn2; }, n2);
           // + an allowance for the linear solve: relative residual 1e-6 of the system just solved (measured: < 1e-9)
           const double B = p.cert_k * n2[1] + 1e-6 * sqrt(nrm[0]), thr2 = p.rtol2 * fnorm0;
           if (B * B <= 0.0625 * thr2 && thr2 >= 100.0 * p.cert_floor2 * ((double)p.ne + n2[2])) {
@@ -1685,6 +1685,8 @@ PK_HD void run_steps(Exec& ex, const Params& p, const SH& sh, const StepIO& io) 
             status = 1; break;
           }
           cert_skip = 8;      // not provable here (coarse bound / large noise): do not pay the reduction again for a few steps
+          // the residual evaluation below reads the neighbours' new iterate: the barrier that was left to the all-reduce
+          if (ex.barrier_free_gather()) ex.sync();
         }
         // evaluate the residual only; fall through to the full
         // assembly (which recomputes it) in the rare case it is not

@@ -131,6 +131,8 @@ struct GpuExecT {
     out[0] = r0; out[1] = r1;
   }
 
+  template <class F> __device__ __forceinline__ void allreduce3_nb(F f, double* out) { allreduce3(f, out); }
+  __device__ __forceinline__ bool barrier_free_gather() const { return false; }
   template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
     double v[3] = {0.0, 0.0, 0.0};
     if (AA || th.active) f(th, v);
@@ -313,6 +315,40 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_kernel(const __grid_constant
 // (owner CTA, local offset) and foreign rows are read through distributed shared memory.  All writes
 // are to own rows.  Barriers are cluster barriers.
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// PUSH exchanges of the single-buffer cluster kernels: the producer writes into the CONSUMER's shared memory with
+// st.async; the bytes are counted by an mbarrier in the consumer's CTA, which the consumer waits on with acquire
+// semantics at cluster scope before it reads its own shared memory.  No fence, no cluster barrier, no DSMEM load on
+// the consumer's critical path: 580 instead of 1 022 cycles per all-gather (profiles/micro/cluster_gather.cu).
+// Every mbarrier has ONE pending arrival per phase -- the consumer's own arrive.expect_tx(bytes) -- so a phase cannot
+// complete before the consumer has armed it, whatever the arrival order of the producers' bytes.
+// ------------------------------------------------------------------------------------------------
+namespace pkx {
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa(unsigned a, unsigned rank) {
+  unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mb_init(unsigned mb, int cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mb), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void mb_arm(unsigned mb, int tx) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(tx) : "memory"); }
+__device__ __forceinline__ void mb_wait(unsigned mb, int parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(mb), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void push2(unsigned dst, double a, double b, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" :: "r"(dst), "d"(a), "d"(b), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void push1(unsigned dst, double a, unsigned mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" :: "r"(dst), "d"(a), "r"(mbar) : "memory");
+}
+// layout of the communication area (doubles from its start; pk_params.h: cluster_comm_doubles())
+enum { GATH_OFF = 0,            // [2 phases][16 source CTAs][4]: the three doubles of an all-gather
+       MB_OFF = 128,            // mbarriers (8 bytes each): 0, 1 = all-gather phases
+       MB_GATH = 0 };
+}  // namespace pkx
+
 // TCC > 0: threads per CTA known at compile time (= blockDim.x): the block-local offsets (slot * Tc + thread) fold into
 // immediate offsets of the loads and stores -- the runtime shifts of the generic variant were a third of the
 // cluster kernel's instructions (profiles/r2qc source page: IMAD / SHF / LEA / BRA 30 %, fp64 26 %).
@@ -403,7 +439,41 @@ struct GpuExecClusterT {
   int flip, g0, g1;
   unsigned rank, C;
   double rA, rc0, rc1;
-  __device__ __forceinline__ GpuExecClusterT(Th& t, double* scratch) : th(t), red(scratch), flip(0) {}
+  // push exchanges (single-buffer kernels, !PP): the communication area of this CTA, all-gathers done so far
+  double* comm; int ngath;
+  static constexpr bool PUSH = !PP;
+  __device__ __forceinline__ GpuExecClusterT(Th& t, double* scratch) : th(t), red(scratch), flip(0), comm(nullptr), ngath(0) {}
+  // once per launch, before the first cluster barrier of the kernel
+  __device__ __forceinline__ void comm_init(double* area) {
+    comm = area;
+    if (PUSH && threadIdx.x == 0) {
+      const unsigned mb = pkx::s32(comm + pkx::MB_OFF);
+      pkx::mb_init(mb + 8 * (pkx::MB_GATH + 0), 1); pkx::mb_init(mb + 8 * (pkx::MB_GATH + 1), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      pkx::mb_arm(mb + 8 * (pkx::MB_GATH + 0), (int)C * 24); pkx::mb_arm(mb + 8 * (pkx::MB_GATH + 1), (int)C * 24);
+    }
+  }
+  __device__ __forceinline__ bool barrier_free_gather() const { return PUSH; }
+  // warp 0: every CTA's (v0, v1, v2) -- valid in lane 0 -- to every CTA; returns CTA `src`'s triple to lane `src` once
+  // all C have arrived (src may be any permutation of the lanes below C)
+  __device__ __forceinline__ void gather3(double& v0, double& v1, double& v2, unsigned src) {
+    const unsigned lane = threadIdx.x & 31;
+    const int ph = ngath & 1, par = (ngath >> 1) & 1;
+    v0 = __shfl_sync(0xffffffffu, v0, 0); v1 = __shfl_sync(0xffffffffu, v1, 0); v2 = __shfl_sync(0xffffffffu, v2, 0);
+    const unsigned base = pkx::s32(comm), mbl = base + 8 * (pkx::MB_OFF + pkx::MB_GATH + ph);
+    if (lane < C) {
+      const unsigned dst = pkx::mapa(base + 8 * (pkx::GATH_OFF + (ph * 16 + (int)rank) * 4), lane), mbr = pkx::mapa(mbl, lane);
+      pkx::push2(dst, v0, v1, mbr); pkx::push1(dst + 16, v2, mbr);
+    }
+    pkx::mb_wait(mbl, par);
+    v0 = 0.0; v1 = 0.0; v2 = 0.0;
+    if (lane < C) {
+      const double* q = comm + pkx::GATH_OFF + (ph * 16 + (int)src) * 4;
+      v0 = q[0]; v1 = q[1]; v2 = q[2];
+    }
+    __syncwarp();
+    if (lane == 0) pkx::mb_arm(mbl, (int)C * 24);       // phase ngath + 2 of this barrier
+  }
   template <class F> __device__ __forceinline__ void each(F f) { f(th); }
   template <class F> __device__ __forceinline__ void each_tid(F f) { f(th, (int)threadIdx.x, bdim(), rank == 0, g0, g1); }
   // Cluster barrier.  cg's sync() lets EVERY thread arrive with release semantics, which ptxas turns into
@@ -592,7 +662,11 @@ struct GpuExecClusterT {
     out[0] = agg[2]; out[1] = agg[3];
   }
 
-  template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) {
+  // allreduce3: the sums AND a cluster-wide barrier (the callers order other exchanges with it); allreduce3_nb: the sums
+  // only -- with push exchanges no barrier at all
+  template <class F> __device__ __forceinline__ void allreduce3(F f, double* out) { allreduce3_t<true>(f, out); }
+  template <class F> __device__ __forceinline__ void allreduce3_nb(F f, double* out) { allreduce3_t<false>(f, out); }
+  template <bool BARRIER, class F> __device__ __forceinline__ void allreduce3_t(F f, double* out) {
     double v[3] = {0.0, 0.0, 0.0};
     f(th, v);
 #pragma unroll
@@ -605,6 +679,23 @@ struct GpuExecClusterT {
     double* sc = area();
     if (lane == 0) { sc[w] = v[0]; sc[nw + w] = v[1]; sc[2 * nw + w] = v[2]; }
     __syncthreads();
+    if (PUSH) {
+      // warp 0: CTA aggregate (same summation order as below), pushed to every CTA; same combination tree
+      if (w == 0) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        if (lane == 0) for (int i = 0; i < nw; ++i) { a0 += sc[i]; a1 += sc[nw + i]; a2 += sc[2 * nw + i]; }
+        gather3(a0, a1, a2, (unsigned)lane);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane == 0) { sc[3 * nw + 3] = a0; sc[3 * nw + 4] = a1; sc[3 * nw + 5] = a2; }
+      }
+      ++ngath;
+      if (BARRIER) sync(); else __syncthreads();
+      out[0] = sc[3 * nw + 3]; out[1] = sc[3 * nw + 4]; out[2] = sc[3 * nw + 5];
+      return;
+    }
     if (threadIdx.x == 0) {
       double s0 = 0.0, s1 = 0.0, s2 = 0.0;
       for (int i = 0; i < nw; ++i) { s0 += sc[i]; s1 += sc[nw + i]; s2 += sc[2 * nw + i]; }
@@ -653,15 +744,22 @@ struct GpuExecClusterT {
       const double a = sc[ww];
       t0 = a * t0 + sc[nw + ww]; t1 = a * t1 + sc[2 * nw + ww]; tA = a * tA;
     }
-    if (threadIdx.x == 0) { sc[3 * nw] = tA; sc[3 * nw + 1] = t0; sc[3 * nw + 2] = t1; }
     cg::cluster_group cl = cg::this_cluster();
-    sync();
-    // ONE warp composes the C CTA aggregates (lane b <- the b-th CTA in scan order, through DSMEM; Kogge-Stone over the
-    // lanes), closes the ring and leaves the value entering THIS CTA in the CTA's own shared memory
+    if (!PUSH) {
+      if (threadIdx.x == 0) { sc[3 * nw] = tA; sc[3 * nw + 1] = t0; sc[3 * nw + 2] = t1; }
+      sync();
+    }
+    // ONE warp composes the C CTA aggregates (lane b <- the b-th CTA in scan order -- pushed into this CTA's shared
+    // memory, or read through DSMEM behind the cluster barrier; Kogge-Stone over the lanes), closes the ring and leaves
+    // the value entering THIS CTA in the CTA's own shared memory
     if (w == 0) {
       double mA = 1.0, m0 = 0.0, m1 = 0.0;
-      if ((unsigned)lane < C) {
-        const unsigned cc = (DIR > 0) ? (unsigned)lane : C - 1 - (unsigned)lane;
+      const unsigned cc = (DIR > 0) ? (unsigned)lane : C - 1 - (unsigned)lane;
+      if (PUSH) {
+        mA = tA; m0 = t0; m1 = t1;                       // (every thread holds the CTA aggregate; lane 0's copy is sent)
+        gather3(mA, m0, m1, cc);
+        if ((unsigned)lane >= C) mA = 1.0;
+      } else if ((unsigned)lane < C) {
         const double* q = cl.map_shared_rank(sc + 3 * nw, cc);
         mA = q[0]; m0 = q[1]; m1 = q[2];
       }
@@ -679,6 +777,7 @@ struct GpuExecClusterT {
       const int mine = (DIR > 0) ? (int)rank : (int)C - 1 - (int)rank;
       if (lane == mine) { sc[3 * nw + 3] = pA * x0 + p0; sc[3 * nw + 4] = pA * x1 + p1; }      // entering my CTA
     }
+    if (PUSH) ++ngath;
     __syncthreads();
     const double y0 = sc[3 * nw + 3], y1 = sc[3 * nw + 4];
     const double w0 = eA * y0 + e0, w1 = eA * y1 + e1;    // entering my warp
@@ -729,7 +828,8 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
     sh.sepR = sh.xb + XB_SLOTS * Tc + 28 * (int)C + 2 * (int)((rank + 1) % C);      // sep_final's solutions (pk_core.h)
   }
   double* red = nxt; nxt += cluster_red_doubles(Tc);
-  sh.dW = nxt;
+  sh.dW = nxt; nxt += (p.nxi > 0 ? p.nxi : 1);
+  double* comm = nxt + ((nxt - smem) & 1);                    // push exchanges (two CTAs per SM): 16-byte aligned
 
   const int r = blockIdx.x / C;
   const long long off = (long long)r * p.ne;
@@ -741,13 +841,14 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
     sh.st(sh.U0, sl, a.u[off + i]); sh.st(sh.U1, sl, a.u1[off + i]); sh.st(sh.F, sl, a.dF[off + i]);
     if (MODE == NOISE_FULL) sh.st(sh.G, sl, a.dG[off + i]);
   }
-  cluster.sync();
 
   Thread<M, MODE, 0> th;
   th.init(p, t0 + (int)threadIdx.x);
   sh.set_neighbours(smem, th.tl, th.tr);
   GpuExecCluster<M, MODE, TCC, (MINB > 1), (MINB <= 1)> ex(th, red);
   ex.rank = rank; ex.C = C; ex.g0 = g0; ex.g1 = g1; ex.part = a.part;
+  ex.comm_init(comm);
+  cluster.sync();       // the state is loaded and the mbarriers of the push exchanges are initialised everywhere
 #ifdef PK_PROFILE
   __shared__ long long tb[16];
   if (threadIdx.x < 16) tb[threadIdx.x] = 0;

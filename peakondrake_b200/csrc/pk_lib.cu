@@ -422,7 +422,7 @@ extern "C" int pk_create(const pk_config* cfg, pk_ctx** out) {
         ? sizeof(double) * ((size_t)UW_SLOTS * Tc + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1) + 2)
         : sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)cluster_xb_doubles(Tc, false) + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1));
     // two CTAs per SM: one PCR row buffer + separator scratch instead of two row buffers
-    const size_t sm2 = sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)cluster_xb_doubles(Tc, true) + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1));
+    const size_t sm2 = sizeof(double) * ((size_t)narr * Tc * p.M + (size_t)cluster_xb_doubles(Tc, true) + cluster_red_doubles(Tc) + (p.nxi > 0 ? p.nxi : 1) + 1 + cluster_comm_doubles());
     if (C < 2 || C > 16 || (C & (C - 1)) || Tc < 32 || C * Tc != p.T || sm > 227 * 1024) {
       const int ne = p.ne; delete c;
       return fail(nullptr, "pk_create: no cluster layout for ne=%d (threads %d)", ne, p.T);

@@ -68,6 +68,8 @@ PK_HD int cluster_red_doubles(int Tc) { return 2 * cluster_red_half(Tc); }
 // SM -- one row buffer (XB_SLOTS = 18 slots) + the scratch rows of the redundant separator solve (30 doubles per CTA of the
 // cluster, at most 16 CTAs) + 16 doubles for the copy of the last thread's tips
 PK_HD int cluster_xb_doubles(int Tc, bool compact) { return compact ? 18 * Tc + 30 * 16 + 16 : 30 * Tc; }
+// communication area of the push exchanges (single-buffer kernels): all-gather inboxes + mbarriers (pk_kernels.cuh, pkx)
+PK_HD int cluster_comm_doubles() { return 160; }
 
 // chunk geometry
 PK_HD int chunk_rows(const Params& p, int t) { return t < p.rem ? p.M : p.M - 1; }

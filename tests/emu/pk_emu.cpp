@@ -138,6 +138,8 @@ struct EmuExecT {
       if (kk[1] < out[1]) out[1] = kk[1];
     }
   }
+  template <class F> void allreduce3_nb(F f, double* out) { allreduce3(f, out); }
+  bool barrier_free_gather() const { return false; }
   template <class F> void allreduce3(F f, double* out) {
     out[0] = out[1] = out[2] = 0.0;
     for (int t = 0; t < T; ++t) { double v[3]; f(th[t], v); out[0] += v[0]; out[1] += v[1]; out[2] += v[2]; }
