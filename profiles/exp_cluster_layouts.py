@@ -32,7 +32,8 @@ CASES = [('c4', 'default', {}), ('c4', 'generic, 1 cluster/SM set', {'PK_CLUSTER
          ('c5', 'generic, clusters of 16 x 128 threads', {'PK_CLUSTER_GENERIC': '1', 'PK_FORCE_CLUSTER': '16'}), ('c4', 'one cluster per SM set (255 registers, two row buffers)', {'PK_CLUSTER_MINB': '1'}),
          ('c5', 'one cluster per SM set (255 registers, two row buffers)', {'PK_CLUSTER_MINB': '1'}),
          ('c4', 'fast reciprocal', LIB('fastr')), ('c5', 'fast reciprocal', LIB('fastr')),
-         ('c4', 'relaxed cluster barrier', LIB('relaxed')), ('c5', 'relaxed cluster barrier', LIB('relaxed')), ('c4', 'runtime shared-memory offsets (round-2 midpoint)', {'PK_CLUSTER_GENERIC': '1'}),
+         ('c4', 'relaxed cluster barrier', LIB('relaxed')), ('c5', 'relaxed cluster barrier', LIB('relaxed')),
+         ('c4', 'edges pushed AND cluster barriers kept', LIB('edgebar')), ('c5', 'edges pushed AND cluster barriers kept', LIB('edgebar')), ('c4', 'runtime shared-memory offsets (round-2 midpoint)', {'PK_CLUSTER_GENERIC': '1'}),
          ('c5', 'runtime shared-memory offsets', {'PK_CLUSTER_GENERIC': '1'}), ('c4', '4096x4 in 8 CTAs of 512', {'PK_FORCE_TM': '4096,5', 'PK_FORCE_CLUSTER': '8'}),
          ('c4', '4096x4 in 16 CTAs of 256', {'PK_FORCE_TM': '4096,5'}),
          ('c5', 'default (2048x10)', {}), ('c5', '4096x5 in 16 CTAs of 256', {'PK_NO_WIDE_CHUNKS': '1'}),
