@@ -339,6 +339,34 @@ def test_c5_fine_mesh_20000_large_noise():
     assert run_case(20000, 2, 3, ic='periodic_peakon', fam='constant', nxi=1, sigma=1.0, dt=1e-2) <= TOL
 
 
+@pytest.mark.parametrize('ne,force,ic,sigma,dt', [(16384, 0, 'new_peak', 0.2, 5e-4), (20000, 0, 'periodic_peakon', 1.0, 1e-3),
+                                                 (2000, 4, 'proper_peak', 0.5, 1e-3), (1000, 2, 'periodic_peakon', 0.5, 1e-3)])
+def test_two_clusters_per_sm_kernels_bit_identical_to_two_buffer_kernels(ne, force, ic, sigma, dt, monkeypatch):
+    """Scalar-noise cluster meshes run the two-CTAs-per-SM instantiations by default: ONE PCR row buffer, the tips and the
+    next separator through CTA-local copies (block barriers instead of cluster barriers), all-gathers pushed with st.async +
+    mbarrier, cluster barrier released by one warp.  PK_CLUSTER_MINB=1 selects the older kernels (two row buffers, every
+    exchange behind a cluster barrier, DSMEM pulls).  Same arithmetic in the same order: bit-identical states and counters,
+    over several launches (the mbarrier phases carry on across the steps of a launch and restart with each launch)."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, build_initial_u
+    if force:
+        monkeypatch.setenv('PK_FORCE_CLUSTER', str(force))
+    out = []
+    for minb in ('0', '1'):
+        monkeypatch.setenv('PK_CLUSTER_MINB', minb)
+        eng = EnsembleIntegrator(ne, 40.0, dt, 5, num_Xis=1, Xi_family='constant', sigma=sigma, seed=11)
+        eng.set_state(build_initial_u(ne, 40.0, ic, peak_width=1 / 6))
+        eng.step(7); eng.step(1); eng.step(4)
+        torch.cuda.synchronize()
+        out.append([t.cpu().numpy().copy() for t in (eng.u, eng.u1, eng.dF, eng.its_total, eng.fail_step)])
+        if minb == '0':
+            assert eng.layout['smem_bytes'] < 110000          # the single-buffer layout was chosen
+        eng.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+    assert (out[0][4] == -1).all() and out[0][3].min() >= 12
+
+
 def test_cluster_with_noise_tables_4096():
     assert run_case(4096, 2, 4, nxi=4) <= TOL
 
