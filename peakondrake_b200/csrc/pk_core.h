@@ -74,6 +74,8 @@ struct Shared {
   // it into a block-local address without decoding (pk_kernels.cuh, SharedCluster)
   PK_HD double ldo(const double* a, int j, int T, int t) const { return a[j * T + t]; }
   PK_HD void sto(double* a, int j, int T, int t, double v) const { a[j * T + t] = v; }
+  // slot j of chunk t, a chunk of the calling thread's own CTA (any thread of it)
+  PK_HD double ldc(const double* a, int j, int T, int t) const { return a[j * T + t]; }
   // slot c of the LEFT / RIGHT neighbour thread q = tl / tr of the calling thread (the cluster variant reads these
   // through two per-thread pointers that already name the owning CTA)
   PK_HD double ldL(const double* a, int c, int T, int q) const { return a[c * T + q]; }
@@ -133,6 +135,14 @@ PK_HD int row_slot_c(const Params& p, int i) {
   if (i < big) { t = i / M; j = i - t * M; }
   else { const int k = i - big; const int q = k / (M - 1); t = p.rem + q; j = k - q * (M - 1); }
   return j * (TT > 0 ? TT : p.T) + t;
+}
+
+// same, as (row j, chunk t)
+template <int M>
+PK_HD void row_jt_c(const Params& p, int i, int& j, int& t) {
+  const int big = p.rem * M;
+  if (i < big) { t = i / M; j = i - t * M; }
+  else { const int k = i - big; const int q = k / (M - 1); t = p.rem + q; j = k - q * (M - 1); }
 }
 
 // chunk-interleaved copy of a [nxi, ne] table: dst[k*T*M + row_slot(i)] = src[k*ne + i], padding rows 0
@@ -731,14 +741,17 @@ struct Thread {
   template <class SH>
   PK_HD void reduce_publish(const Params& p, const SH& sh, int base = 0, bool rawD = false) {
     const int T = TN(p);
-    double Di[4];
-    if (rawD) { Di[0] = Db[0]; Di[1] = Db[1]; Di[2] = Db[2]; Di[3] = Db[3]; }     // separator rows travel with D itself
-    else inv2<FASTR != 0>(Db, Di);
     // seven 16-byte stores: (L0 L1)(L2 L3)(U0 U1)(U2 U3)(D^-1 ...)(r0 r1), pair slots base/2 .. base/2 + 6
     const int b2 = base >> 1;
     sh.st2o(sh.xb, b2 + 0, T, t, Lb[0], Lb[1]); sh.st2o(sh.xb, b2 + 1, T, t, Lb[2], Lb[3]);
     sh.st2o(sh.xb, b2 + 2, T, t, Ub[0], Ub[1]); sh.st2o(sh.xb, b2 + 3, T, t, Ub[2], Ub[3]);
-    sh.st2o(sh.xb, b2 + 4, T, t, Di[0], Di[1]); sh.st2o(sh.xb, b2 + 5, T, t, Di[2], Di[3]);
+    if (rawD) {                                                                    // separator rows travel with D itself
+      sh.st2o(sh.xb, b2 + 4, T, t, Db[0], Db[1]); sh.st2o(sh.xb, b2 + 5, T, t, Db[2], Db[3]);
+    } else {
+      double Di[4];
+      inv2<FASTR != 0>(Db, Di);
+      sh.st2o(sh.xb, b2 + 4, T, t, Di[0], Di[1]); sh.st2o(sh.xb, b2 + 5, T, t, Di[2], Di[3]);
+    }
     sh.st2o(sh.xb, b2 + 6, T, t, rb[0], rb[1]);
   }
   // one published row (pair layout of reduce_publish) of thread q
@@ -794,26 +807,25 @@ struct Thread {
   PK_HD void pcr_step_local(const Params& p, const SH& sh, int d, int base, int Tc) {
     const int tl_ = t & (Tc - 1);
     const bool hl = tl_ - d >= 1, hr = tl_ != 0 && tl_ + d <= Tc - 1;
-    double al[4], ga[4];
-    PK_UNROLL
-    for (int c = 0; c < 4; ++c) al[c] = ga[c] = 0.0;
-    double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
+    // (left partner first, then right: the contributions to D and r are added in that order)
     if (hl) {
+      double Ll[4], Ul[4], Dl[4], rl[2], al[4];
       pcr_load_row_local(p, sh, base >> 1, t - d, Ll, Ul, Dl, rl);
       mm2(Lb, Dl, al);
       PK_UNROLL
       for (int c = 0; c < 4; ++c) al[c] = -al[c];
+      mma2(al, Ul, Db); mva2(al, rl, rb);
       mm2(al, Ll, Lb);
     }
     if (hr) {
+      double Lr[4], Ur[4], Dr[4], rr[2], ga[4];
       pcr_load_row_local(p, sh, base >> 1, t + d, Lr, Ur, Dr, rr);
       mm2(Ub, Dr, ga);
       PK_UNROLL
       for (int c = 0; c < 4; ++c) ga[c] = -ga[c];
+      mma2(ga, Lr, Db); mva2(ga, rr, rb);
       mm2(ga, Ur, Ub);
     }
-    if (hl) { mma2(al, Ul, Db); mva2(al, rl, rb); }
-    if (hr) { mma2(ga, Lr, Db); mva2(ga, rr, rb); }
   }
   // interior rows of a segment once the separators are known (slots 14, 15 of the leading threads)
   template <class SH>
@@ -1525,7 +1537,8 @@ PK_HD void snapshot(Exec& ex, const Params& p, const SH& sh, const StepIO& io, i
   const long long row = (long long)d * io.R + io.r;
   double* dst = io.snap_u + row * p.ne;
   ex.each_tid([&](Th&, int tid, int nth, bool, int g0, int g1) {
-    for (int i = g0 + tid; i < g1; i += nth) dst[i] = sh.ld(sh.U0, row_slot_c<M, TT>(p, i));
+    // (rows [g0, g1) belong to the calling CTA: block-local slot, no decoding of a flat index)
+    for (int i = g0 + tid; i < g1; i += nth) { int j, t; row_jt_c<M>(p, i, j, t); dst[i] = sh.ldc(sh.U0, j, TT > 0 ? TT : p.T, t); }
   });
   ex.one([&]() { io.snap_flag[row] = failed; });
 }

@@ -421,6 +421,7 @@ struct SharedClusterT {
   }
   // slot j of the calling thread: block-local, no decoding of the flat index (most accesses are of this kind)
   __device__ __forceinline__ double ldo(const double* a, int j, int, int) const { return a[j * tcn() + (int)threadIdx.x]; }
+  __device__ __forceinline__ double ldc(const double* a, int j, int, int t) const { return a[j * tcn() + (t & (tcn() - 1))]; }
   __device__ __forceinline__ void sto(double* a, int j, int, int, double v) const { a[j * tcn() + (int)threadIdx.x] = v; }
   __device__ __forceinline__ double dw(int k) const { return dW[k]; }
   __device__ __forceinline__ void set_dw(int k, double v) const { dW[k] = v; }
@@ -836,10 +837,12 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
   const int t0 = (int)rank * Tc;
   const int g0 = chunk_start(p, t0);
   const int g1 = (rank == C - 1) ? p.ne : chunk_start(p, t0 + Tc);
+  // (the rows [g0, g1) of this CTA: block-local slots, no decoding of the flat index)
   for (int i = g0 + threadIdx.x; i < g1; i += Tc) {
-    const int sl = row_slot_c<M, 0>(p, i);
-    sh.st(sh.U0, sl, a.u[off + i]); sh.st(sh.U1, sl, a.u1[off + i]); sh.st(sh.F, sl, a.dF[off + i]);
-    if (MODE == NOISE_FULL) sh.st(sh.G, sl, a.dG[off + i]);
+    int j, t; row_jt_c<M>(p, i, j, t);
+    const int o = j * Tc + (t - t0);
+    sh.U0[o] = a.u[off + i]; sh.U1[o] = a.u1[off + i]; sh.F[o] = a.dF[off + i];
+    if (MODE == NOISE_FULL) sh.G[o] = a.dG[off + i];
   }
 
   Thread<M, MODE, 0> th;
@@ -869,9 +872,10 @@ __global__ void __launch_bounds__(TB, MINB) pk_step_cluster_kernel(const __grid_
 #endif
 
   for (int i = g0 + threadIdx.x; i < g1; i += Tc) {
-    const int sl = row_slot_c<M, 0>(p, i);
-    a.u[off + i] = sh.ld(sh.U0, sl); a.u1[off + i] = sh.ld(sh.U1, sl); a.dF[off + i] = sh.ld(sh.F, sl);
-    if (MODE == NOISE_FULL) a.dG[off + i] = sh.ld(sh.G, sl);
+    int j, t; row_jt_c<M>(p, i, j, t);
+    const int o = j * Tc + (t - t0);
+    a.u[off + i] = sh.U0[o]; a.u1[off + i] = sh.U1[o]; a.dF[off + i] = sh.F[o];
+    if (MODE == NOISE_FULL) a.dG[off + i] = sh.G[o];
   }
 }
 

@@ -65,6 +65,7 @@ struct EmuSharedCluster {
     (*bufs)[owner][o] = v0; (*bufs)[owner][o + 1] = v1;
   }
   // own-slot accessors: must be block-local (checked like the device's sto/ldo, which do not decode)
+  double ldc(const double* a, int j, int T, int t) const { if (((t & ((1 << lgT) - 1)) >> lgTc) != *cur) ++*bad; return *at(a, j * T + t, false); }
   double ldo(const double* a, int j, int T, int t) const { if (((t & ((1 << lgT) - 1)) >> lgTc) != *cur) ++*bad; return *at(a, j * T + t, false); }
   void sto(double* a, int j, int T, int t, double v) const { *at(a, j * T + t, true) = v; }
   double ldl(const double* a, int off) const { return (*bufs)[*cur][(a - (const double*)0) + off]; }
