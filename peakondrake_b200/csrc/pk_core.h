@@ -780,6 +780,7 @@ struct Thread {
   PK_HD void pcr_step(const Params& p, const SH& sh, int d, int base = 0) {
     const int T = TN(p);
     const int ql = (t + T - d) & (T - 1), qr = (t + d) & (T - 1);
+#ifdef PK_EXP_PCR_STEP_WIDE      // A/B: both partner rows live at once (the form up to round 2)
     double Ll[4], Ul[4], Dl[4], rl[2], Lr[4], Ur[4], Dr[4], rr[2];
     pcr_load_row(p, sh, base >> 1, ql, Ll, Ul, Dl, rl);
     pcr_load_row(p, sh, base >> 1, qr, Lr, Ur, Dr, rr);
@@ -791,6 +792,28 @@ struct Thread {
     mm2(ga, Ur, Ub);
     mma2(al, Ul, Db); mma2(ga, Lr, Db);
     mva2(al, rl, rb); mva2(ga, rr, rb);
+#else
+    // left partner, then right partner: one neighbour row live at a time; the contributions to D and r are added in the
+    // same order as before (bit-identical)
+    {
+      double Ll[4], Ul[4], Dl[4], rl[2], al[4];
+      pcr_load_row(p, sh, base >> 1, ql, Ll, Ul, Dl, rl);
+      mm2(Lb, Dl, al);
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) al[c] = -al[c];
+      mma2(al, Ul, Db); mva2(al, rl, rb);
+      mm2(al, Ll, Lb);
+    }
+    {
+      double Lr[4], Ur[4], Dr[4], rr[2], ga[4];
+      pcr_load_row(p, sh, base >> 1, qr, Lr, Ur, Dr, rr);
+      mm2(Ub, Dr, ga);
+      PK_UNROLL
+      for (int c = 0; c < 4; ++c) ga[c] = -ga[c];
+      mma2(ga, Lr, Db); mva2(ga, rr, rb);
+      mm2(ga, Ur, Ub);
+    }
+#endif
   }
 
   // ---- partitioned Schur solve (thread-block-cluster variant) ------------------------------------------------
