@@ -1298,7 +1298,8 @@ struct Thread {
 #if defined(__CUDA_ARCH__)
     const double q = x * p.ih;
     const double r = fma(-q, p.h, x);
-    return fma(r, p.ih, q);
+    const double res = fma(r, p.ih, q);
+    return res == 0.0 ? q : res;           // (-0) / h = -0: the correction loses the sign of a zero
 #else
     return x / p.h;
 #endif

@@ -88,7 +88,22 @@ __device__ __forceinline__ double usde_at(double x, double p_true, double q, dou
   return p * exp(-(q + Ld - x) / al);
 }
 
-__global__ void __launch_bounds__(256) pk_diag_kernel(const __grid_constant__ DiagArgs a) {
+// x / h, correctly rounded, from ih = RN(1/h): q0 = RN(x ih) is within ~1.5 ulp, one FMA correction with the exact
+// remainder makes it faithful, a second one (Markstein's theorem: correctly rounded reciprocal + faithful quotient + exact
+// remainder) makes it RN(x / h).  Five instructions instead of the ~40 of a division.
+static __device__ __forceinline__ double div_h(double x, double h, double ih) {
+  const double q0 = x * ih;
+  const double q = fma(fma(-q0, h, x), ih, q0);
+  const double res = fma(fma(-q, h, x), ih, q);
+  return res == 0.0 ? q0 : res;            // (-0) / h = -0: the corrections lose the sign of a zero
+}
+
+// EXTRA = false: the plain dump (no du field, no m columns, no true-peakon error) -- what the per-step dumps of BASELINE
+// config 4 ask for: a light loop body (4 CTAs per SM instead of 2 at 95 registers) unrolled four times so that twelve
+// loads per thread are in flight (the rolled loop sat at 13 % of the HBM bandwidth with `long_scoreboard` 7.7 per issue,
+// profiles/r2zp).  The per-thread accumulation order is unchanged: same bits.
+template <bool EXTRA>
+__global__ void __launch_bounds__(256, EXTRA ? 2 : 4) pk_diag_kernel(const __grid_constant__ DiagArgs a) {
   __shared__ double ssum[32];
   __shared__ ArgV sarg[32];
   const int r = blockIdx.x, ne = a.ne;
@@ -104,29 +119,33 @@ __global__ void __launch_bounds__(256) pk_diag_kernel(const __grid_constant__ Di
   const double h = a.h, ih = 1.0 / a.h, a2 = a.alphasq;
   double sM = 0.0, sK = 0.0, sU = 0.0, sE = 0.0;
   ArgV mxdu = {-INFINITY, 0x7fffffff}, mndu = {INFINITY, 0x7fffffff}, mxu = {-INFINITY, 0x7fffffff}, mxj = {-INFINITY, 0x7fffffff};
-  double* b = a.scratch ? a.scratch + (long long)r * 2 * ne : nullptr;
+  double* b = (EXTRA && a.scratch) ? a.scratch + (long long)r * 2 * ne : nullptr;
   double* mm = b ? b + ne : nullptr;
-  const double pt = a.pq ? a.pq[2 * r] : 0.0, qq = a.pq ? a.pq[2 * r + 1] : 0.0;
-  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+  const double pt = (EXTRA && a.pq) ? a.pq[2 * r] : 0.0, qq = (EXTRA && a.pq) ? a.pq[2 * r + 1] : 0.0;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < ne; i += 256) {
     const int im = (i == 0) ? ne - 1 : i - 1, ip = (i == ne - 1) ? 0 : i + 1;
     const double um = u[im], u0 = u[i], up = u[ip];
-    const double du = (up - u0) / h;           // DG0 cell i          (diagnostic_equations.py:94-101)
-    const double dum = (u0 - um) / h;          // DG0 cell i-1
+    // x / h, correctly rounded, without a division (Markstein: q = x RN(1/h), the exact remainder by FMA, one fused
+    // correction -- 3 instructions instead of ~40; the two divisions were most of this kernel's instructions and held it
+    // at 13 % of the HBM bandwidth).  Bit-identical to `/ h`: tests/test_gpu_parity.py compares du with NumPy's division.
+    const double du = div_h((up - u0), h, ih);           // DG0 cell i          (diagnostic_equations.py:94-101)
+    const double dum = div_h((u0 - um), h, ih);          // DG0 cell i-1
     const double jmp = fabs(du - dum);         // |jump(du)| at vertex i (:103-113)
     sM += (h * (1.0 / 3.0)) * (u0 * u0 + u0 * up + up * up);   // cell integral of u^2
     sK += (up - u0) * (up - u0) * ih;                          // cell integral of u_x^2
     sU += h * u0;
     amax(mxdu, du, i); amin(mndu, du, i); amax(mxu, u0, i); amax(mxj, jmp, i);
-    if (a.du_out) a.du_out[(long long)r * ne + i] = du;
-    if (b) b[i] = a.h / 6.0 * (um + 4.0 * u0 + up) + a2 * ih * (2.0 * u0 - um - up);
-    if (a.pq) {
+    if (EXTRA && a.du_out) a.du_out[(long long)r * ne + i] = du;
+    if (EXTRA && b) b[i] = a.h / 6.0 * (um + 4.0 * u0 + up) + a2 * ih * (2.0 * u0 - um - up);
+    if (EXTRA && a.pq) {
       const double e0 = u0 - usde_at(i * h, pt, qq, a.Ld, a2, a.periodic);
       const double e1 = up - usde_at(ip * h, pt, qq, a.Ld, a2, a.periodic);
       sE += (h * (1.0 / 3.0)) * (e0 * e0 + e0 * e1 + e1 * e1);
     }
   }
   sM = block_sum(sM, ssum); sK = block_sum(sK, ssum); sU = block_sum(sU, ssum);
-  if (a.pq) sE = block_sum(sE, ssum);
+  if (EXTRA && a.pq) sE = block_sum(sE, ssum);
   mxdu = block_arg<true>(mxdu, sarg); mndu = block_arg<false>(mndu, sarg);
   mxu = block_arg<true>(mxu, sarg); mxj = block_arg<true>(mxj, sarg);
   double sMm = 0.0, sKm = 0.0, sm1 = 0.0, sUm = 0.0, mmax = -INFINITY;
@@ -176,7 +195,7 @@ __global__ void __launch_bounds__(256) pk_diag_kernel(const __grid_constant__ Di
     out[PK_D_MAX_DU] = mxdu.v; out[PK_D_MIN_DU] = mndu.v; out[PK_D_MAX_JUMP_LOCAL] = mxj.v; out[PK_D_MAX_U] = mxu.v;
     out[PK_D_L2M2] = b ? sMm : qnan; out[PK_D_H1SEMI_M2] = b ? sKm : qnan; out[PK_D_MASS_M] = b ? sm1 : qnan;
     out[PK_D_M_MAX] = b ? mmax : qnan; out[PK_D_UMU] = b ? sUm : qnan;
-    out[PK_D_ERR_SDE2] = a.pq ? sE : qnan;
+    out[PK_D_ERR_SDE2] = (EXTRA && a.pq) ? sE : qnan;
     idx[PK_I_ARGMAX_DU] = mxdu.i; idx[PK_I_ARGMIN_DU] = mndu.i; idx[PK_I_ARGMAX_U] = mxu.i; idx[PK_I_ARGMAX_JUMP] = mxj.i;
   }
 }
@@ -809,7 +828,8 @@ extern "C" int pk_diagnostics_rows(pk_ctx* c, const double* u, int32_t nrows, co
   const double rn = pow(rho, (double)c->p.ne);
   if (c->p.ne >= 160) { a.K = 64; a.gscale = 1.0 / (kappa * (1.0 - rho * rho)); }   // |rho|^64 ~ 2e-37
   else { a.K = -1; a.gscale = 1.0 / (kappa * (1.0 - rho * rho) * (1.0 - rn)); }
-  pk_diag_kernel<<<nrows, 256, 0, (cudaStream_t)stream>>>(a);
+  if (a.du_out || a.scratch || a.pq) pk_diag_kernel<true><<<nrows, 256, 0, (cudaStream_t)stream>>>(a);
+  else pk_diag_kernel<false><<<nrows, 256, 0, (cudaStream_t)stream>>>(a);
   ++c->nlaunch;
   CK(c, cudaGetLastError());
   return 0;

@@ -317,6 +317,40 @@ def test_convergence_certificate_is_bit_neutral(monkeypatch):
     assert (out[0][5] == -1).all() and out[0][4].min() >= 63        # nobody failed; at least one iteration per step
 
 
+@pytest.mark.parametrize('ne,Ld', [(1000, 40.0), (16384, 40.0), (777, 13.7), (2000, 1.0)])
+def test_diag_kernel_division_free_slopes_are_ieee_quotients(ne, Ld):
+    """pk_diag_kernel forms du = (u[i+1] - u[i]) / h without a division (q = x RN(1/h), exact remainder by FMA, one fused
+    correction).  With the correctly rounded reciprocal that IS the correctly rounded quotient: compared bit for bit with
+    NumPy's IEEE division on smooth, random, tiny, huge and signed-zero differences, together with the extrema and
+    arg-indices that are built from it (outputting.py:128-142)."""
+    import torch
+    from peakondrake_b200 import EnsembleIntegrator, _lib
+    rng = np.random.default_rng(ne)
+    R = 6
+    u = np.empty((R, ne))
+    x = np.arange(ne) * (Ld / ne)
+    u[0] = np.exp(-np.abs(x - Ld / 2))
+    u[1] = rng.standard_normal(ne)
+    u[2] = rng.standard_normal(ne) * 1e-150
+    u[3] = rng.standard_normal(ne) * 1e150
+    u[4] = np.round(rng.standard_normal(ne) * 4) / 4          # many exact ties and zero differences
+    u[5] = np.ldexp(rng.integers(1, 2 ** 53, ne).astype(np.float64), rng.integers(-60, 60, ne))
+    eng = EnsembleIntegrator(ne, Ld, 1e-3, R)
+    eng.u.copy_(torch.from_numpy(u))
+    vals, idx, du = eng.diagnostics(want_du=True)
+    torch.cuda.synchronize()
+    vals, idx, du = vals.cpu().numpy(), idx.cpu().numpy(), du.cpu().numpy()
+    h = Ld / ne
+    ref = (np.roll(u, -1, axis=1) - u) / h
+    assert np.array_equal(du.view(np.int64), ref.view(np.int64))
+    jump = np.abs(ref - np.roll(ref, 1, axis=1))
+    for r in range(R):
+        assert vals[r, _lib.D_MAX_DU] == ref[r].max() and vals[r, _lib.D_MIN_DU] == ref[r].min()
+        assert idx[r, _lib.I_ARGMAX_DU] == np.argmax(ref[r]) and idx[r, _lib.I_ARGMIN_DU] == np.argmin(ref[r])
+        assert vals[r, _lib.D_MAX_JUMP_LOCAL] == jump[r].max() and idx[r, _lib.I_ARGMAX_JUMP] == np.argmax(jump[r])
+    eng.close()
+
+
 # ---- thread-block-cluster variant (one realisation per cluster of CTAs, DSMEM) -------------------
 @pytest.mark.parametrize('ne,C', [(1000, 2), (1000, 4), (2000, 8), (500, 2)])
 def test_cluster_variant_forced_on_small_meshes(ne, C, monkeypatch):
