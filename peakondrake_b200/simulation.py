@@ -551,12 +551,13 @@ def run_batch(params, seeds, seed_indices, data_file, diagnostics, combo_index=N
         pde_runs = not only_peakons
         # Several dumps per launch.  Preferred: state SNAPSHOTS (pk_step_snap: the kernel stores u at every dump step, ONE
         # batched streaming call computes the diagnostics of all dumps of the launch) -- a dump then costs the step kernel
-        # ~1 % of a step; if the snapshots of even one dump exceed the memory budget (PK_SNAP_BYTES, default 1 GiB): the
+        # ~1 % of a step; if the snapshots of even one dump exceed the memory budget (PK_SNAP_BYTES, default 8 GiB of the 180:
+        # BASELINE config 4 on one GPU then advances 14 steps per launch instead of one): the
         # dump FUSED into the step kernel (pk_step_dump, no extra memory, ~11 % of a cluster-kernel step per dump).
         import os
         batch_ok = (pde_runs and ndump > 0 and not eng.upwind and field_files is None and stats is None
                     and not (want_mean or want_smooth) and 'mu' not in diagnostics)
-        ksnap = int(os.environ.get('PK_SNAP_BYTES', 1 << 30)) // max(1, R * ne * 8) if hasattr(eng, 'step_snap') else 0
+        ksnap = int(os.environ.get('PK_SNAP_BYTES', 8 << 30)) // max(1, R * ne * 8) if hasattr(eng, 'step_snap') else 0
         fused_ok = (batch_ok and hasattr(eng, 'step_dump') and not (want_m or want_sde) and 'u_field' not in diagnostics)
         mode = 'snap' if (batch_ok and ksnap >= 1) else ('fused' if fused_ok else None)
         kmax = max(1, min(256, (1 << 24) // max(1, R * ndump * max(1, num_Xis)))) if host_dW is not None else 256
